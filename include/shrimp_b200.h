@@ -1,0 +1,94 @@
+/*
+ * shrimp_b200.h -- C ABI of the B200-native gmapper hot path.
+ *
+ * Plain C, POD arguments only (pointers + sizes); no CUDA/torch types cross this boundary.
+ * Every entry point names the reference interface (file:line under compbio-UofT/shrimp 2.2.3)
+ * it replaces.  All pointers are HOST pointers unless the name says "_dev"; the library does its
+ * own H2D/D2H.  All functions return 0 on success and a negative SHRIMP_E_* code on failure;
+ * shrimp_gpu_last_error() returns the message of the last failure on the calling thread.
+ *
+ * Data conventions are the reference's own (common/util.h:41-42): sequences are 4 bits per
+ * base, 8 bases per uint32_t, base i in bits 4*(i%8) of word i/8; codes are fasta.h:26-42
+ * (A,C,G,T = 0..3, N = 15); colour-space arrays hold colours 0..3 (N = 15).  Gap/mismatch
+ * scores are passed with the reference's CLI sign (negative penalties), exactly as to
+ * sw_vector_setup().
+ *
+ * There is no CPU fallback: with no usable CUDA device every call fails with SHRIMP_E_CUDA.
+ */
+#ifndef SHRIMP_B200_H
+#define SHRIMP_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SHRIMP_OK          0
+#define SHRIMP_E_CUDA     -1   /* CUDA runtime / no device */
+#define SHRIMP_E_ARG      -2   /* invalid argument */
+#define SHRIMP_E_STATE    -3   /* call order (e.g. map before index build) */
+#define SHRIMP_E_RANGE    -4   /* value outside what the int16 / packed kernels support */
+#define SHRIMP_E_NOMEM    -5
+
+typedef struct shrimp_gpu_ctx shrimp_gpu_ctx;
+
+/* ------------------------------------------------------------------------------------------
+ * Context
+ * ---------------------------------------------------------------------------------------- */
+int          shrimp_gpu_device_count(void);
+int          shrimp_gpu_create(int device, shrimp_gpu_ctx **out);
+void         shrimp_gpu_destroy(shrimp_gpu_ctx *ctx);
+const char  *shrimp_gpu_last_error(void);
+/* Number of kernels this library launched on ctx since creation (bench.py "gpu_launches"). */
+uint64_t     shrimp_gpu_launch_count(const shrimp_gpu_ctx *ctx);
+/* Device-side milliseconds (CUDA events on the library's stream) spent in each pipeline stage
+ * since the last reset; names[] receives static strings.  Returns the number of stages. */
+int          shrimp_gpu_stage_times(shrimp_gpu_ctx *ctx, const char **names, float *ms, uint64_t *launches, int max_n);
+void         shrimp_gpu_stage_times_reset(shrimp_gpu_ctx *ctx);
+
+/* ------------------------------------------------------------------------------------------
+ * Scoring set-up.  Replaces sw_vector_setup (common/sw-vector.c:388-439), sw_gapless_setup
+ * (sw-gapless.c:28-43), sw_full_ls_setup (sw-full-ls.c:573-623) and sw_full_cs_setup
+ * (sw-full-cs.c:1076-1132): one parameter block for every kernel of the context.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct shrimp_sw_params {
+  int match;            /* > 0 */
+  int mismatch;         /* < 0; colour space: match + crossover, as gmapper.c:2935 passes it */
+  int a_gap_open;       /* <= 0, gap that consumes genome ("a", SAM D) */
+  int a_gap_ext;
+  int b_gap_open;       /* <= 0, gap that consumes read ("b", SAM I) */
+  int b_gap_ext;
+  int crossover;        /* < 0, colour space only (sw_full_cs) */
+  int use_colours;      /* 0 letter space, 1 colour space */
+  int anchor_width;     /* sw_full_*: band half-width around the anchor; < 0 = threshold band */
+  int indel_taboo_len;  /* sw_full_cs */
+  int max_read_len;     /* qrlen of the *_setup calls; match*max_read_len must be < 32768 */
+  int max_window_len;   /* dblen of the *_setup calls */
+} shrimp_sw_params;
+
+int shrimp_gpu_sw_setup(shrimp_gpu_ctx *ctx, const shrimp_sw_params *p);
+
+/* ------------------------------------------------------------------------------------------
+ * Batched vector Smith-Waterman filter.  Replaces sw_vector (common/sw-vector.c:453-515), one
+ * call per task: score-only affine-gap local alignment of read (rows) against a genome window
+ * (columns).  Task t scores reads[read_idx[t]] (rlen[t] bases) against genome[goff[t] ..
+ * goff[t]+glen[t]).  Colour space (use_colours): genome is the colour genome, genome_ls the
+ * letter genome (same coordinates) and initbp[t] the read's initial base; row 0 then follows
+ * sw-vector.c:116-146.  Letter space: genome_ls = NULL, initbp = NULL.
+ * ---------------------------------------------------------------------------------------- */
+int shrimp_gpu_sw_vector_batch(shrimp_gpu_ctx *ctx,
+                               const uint32_t *genome, size_t genome_words,
+                               const uint32_t *genome_ls,
+                               const uint32_t *reads, int read_stride_words, int n_reads,
+                               int n_tasks,
+                               const uint32_t *goff, const int32_t *glen,
+                               const int32_t *read_idx, const int32_t *rlen,
+                               const int8_t *initbp,
+                               int32_t *scores_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SHRIMP_B200_H */

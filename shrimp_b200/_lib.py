@@ -1,0 +1,60 @@
+"""ctypes binding of libshrimp_b200.so (the C ABI declared in include/shrimp_b200.h).
+
+The library is built in-tree by ``__graft_entry__.build()`` / ``make -C shrimp_b200/csrc``.  There
+is no fallback: if the shared object is missing, or no CUDA device is usable, the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libshrimp_b200.so")
+
+_lib = None
+
+
+class ShrimpGpuError(RuntimeError):
+    pass
+
+
+class SwParams(C.Structure):
+    _fields_ = [(n, C.c_int) for n in (
+        "match", "mismatch", "a_gap_open", "a_gap_ext", "b_gap_open", "b_gap_ext", "crossover",
+        "use_colours", "anchor_width", "indel_taboo_len", "max_read_len", "max_window_len")]
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ShrimpGpuError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU fallback for the gmapper hot path)")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, u64 = C.c_void_p, C.c_int, C.c_uint64
+    L.shrimp_gpu_device_count.restype = i32
+    L.shrimp_gpu_create.argtypes = [i32, C.POINTER(vp)]
+    L.shrimp_gpu_create.restype = i32
+    L.shrimp_gpu_destroy.argtypes = [vp]
+    L.shrimp_gpu_destroy.restype = None
+    L.shrimp_gpu_last_error.restype = C.c_char_p
+    L.shrimp_gpu_launch_count.argtypes = [vp]
+    L.shrimp_gpu_launch_count.restype = u64
+    L.shrimp_gpu_stage_times.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.POINTER(u64), i32]
+    L.shrimp_gpu_stage_times.restype = i32
+    L.shrimp_gpu_stage_times_reset.argtypes = [vp]
+    L.shrimp_gpu_stage_times_reset.restype = None
+    L.shrimp_gpu_sw_setup.argtypes = [vp, C.POINTER(SwParams)]
+    L.shrimp_gpu_sw_setup.restype = i32
+    L.shrimp_gpu_sw_vector_batch.argtypes = [vp, vp, C.c_size_t, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp]
+    L.shrimp_gpu_sw_vector_batch.restype = i32
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().shrimp_gpu_last_error().decode(errors="replace")
+        raise ShrimpGpuError(f"{what} failed (rc={rc}): {msg}")

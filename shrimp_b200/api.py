@@ -1,0 +1,155 @@
+"""Host-side mirror of the reference's operator interface for the hot path.
+
+Names, argument meaning and error behaviour follow the reference (compbio-UofT/shrimp 2.2.3):
+``sw_vector_setup``/``sw_vector`` (common/sw-vector.c:388,453) etc., but every call takes a batch
+because a GPU call per window would be pointless.  All arithmetic happens in libshrimp_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from ._lib import SwParams, check, lib
+
+# fasta.h:26-42
+_LS_CODE = np.full(256, 255, dtype=np.uint8)
+for _i, _c in enumerate("ACGTUMRWSYKVHDB"):
+    _LS_CODE[ord(_c)] = _i
+    _LS_CODE[ord(_c.lower())] = _i
+for _c in "NnXx.-":
+    _LS_CODE[ord(_c)] = 15
+_CS_CODE = np.full(256, 255, dtype=np.uint8)
+for _i, _c in enumerate("0123"):
+    _CS_CODE[ord(_c)] = _i
+for _c in "4NnXx.":
+    _CS_CODE[ord(_c)] = 15
+
+
+def _pack_codes(codes: np.ndarray, n_words: int | None = None) -> np.ndarray:
+    """4 bits per base, 8 per uint32, base i in bits 4*(i%8) of word i/8 (util.h:41-42)."""
+    n = codes.size
+    nw = (n + 7) // 8 if n_words is None else n_words
+    buf = np.zeros(nw * 8, dtype=np.uint32)
+    buf[:n] = codes
+    buf = buf.reshape(nw, 8)
+    sh = (4 * np.arange(8, dtype=np.uint32))[None, :]
+    return np.bitwise_or.reduce(buf << sh, axis=1).astype(np.uint32)
+
+
+def pack_bases(seq, n_words: int | None = None) -> np.ndarray:
+    """ASCII letters -> packed 4-bit codes (fasta_sequence_to_bitfield, fasta.c:617-676)."""
+    a = np.frombuffer(seq.encode() if isinstance(seq, str) else bytes(seq), dtype=np.uint8) \
+        if not isinstance(seq, np.ndarray) else seq
+    codes = _LS_CODE[a]
+    if (codes == 255).any():
+        raise ValueError("invalid character in letter-space sequence")
+    return _pack_codes(codes, n_words)
+
+
+def pack_colours(seq, n_words: int | None = None) -> np.ndarray:
+    a = np.frombuffer(seq.encode() if isinstance(seq, str) else bytes(seq), dtype=np.uint8) \
+        if not isinstance(seq, np.ndarray) else seq
+    codes = _CS_CODE[a]
+    if (codes == 255).any():
+        raise ValueError("invalid character in colour-space sequence")
+    return _pack_codes(codes, n_words)
+
+
+@dataclass
+class Scores:
+    match: int
+    mismatch: int
+    a_gap_open: int
+    a_gap_ext: int
+    b_gap_open: int
+    b_gap_ext: int
+    crossover: int = 0
+
+
+# gmapper-defaults.h:45-58
+LS_DEFAULT_SCORES = Scores(10, -15, -33, -7, -33, -3, 0)
+CS_DEFAULT_SCORES = Scores(10, -24, -33, -7, -33, -3, -20)
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class GpuContext:
+    """One per process/GPU (the reference's per-thread *_setup state, gmapper.c:2907-2965)."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        self._L = lib()
+        check(self._L.shrimp_gpu_create(device, C.byref(self._h)), "shrimp_gpu_create")
+
+    def close(self):
+        if self._h:
+            self._L.shrimp_gpu_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- set-up -------------------------------------------------------------------------------
+    def sw_setup(self, dblen: int, qrlen: int, scores: Scores, use_colours: bool = False,
+                 anchor_width: int = 8, indel_taboo_len: int = 0):
+        """sw_vector_setup + sw_full_{ls,cs}_setup in one (sw-vector.c:388, sw-full-ls.c:573)."""
+        mismatch = scores.mismatch
+        p = SwParams(scores.match, mismatch, scores.a_gap_open, scores.a_gap_ext, scores.b_gap_open,
+                     scores.b_gap_ext, scores.crossover, int(use_colours), anchor_width, indel_taboo_len,
+                     qrlen, dblen)
+        check(self._L.shrimp_gpu_sw_setup(self._h, C.byref(p)), "shrimp_gpu_sw_setup")
+
+    # alias with the reference's name
+    sw_vector_setup = sw_setup
+
+    # ---- sw_vector ----------------------------------------------------------------------------
+    def sw_vector(self, genome: np.ndarray, goff, glen, reads: np.ndarray, read_idx, rlen,
+                  genome_ls: np.ndarray | None = None, initbp=None) -> np.ndarray:
+        """Batched sw_vector(genome, goff, glen, read, rlen, genome_ls, initbp) (sw-vector.c:453)."""
+        genome = np.ascontiguousarray(genome, dtype=np.uint32)
+        reads = np.ascontiguousarray(reads, dtype=np.uint32)
+        if reads.ndim != 2:
+            raise ValueError("reads must be [n_reads, stride_words]")
+        goff = np.ascontiguousarray(goff, dtype=np.uint32)
+        glen = np.ascontiguousarray(glen, dtype=np.int32)
+        read_idx = np.ascontiguousarray(read_idx, dtype=np.int32)
+        rlen = np.ascontiguousarray(rlen, dtype=np.int32)
+        n = goff.size
+        if not (glen.size == read_idx.size == rlen.size == n):
+            raise ValueError("task arrays must have equal length")
+        if genome_ls is not None:
+            genome_ls = np.ascontiguousarray(genome_ls, dtype=np.uint32)
+            initbp = np.ascontiguousarray(initbp, dtype=np.int8)
+        out = np.empty(n, dtype=np.int32)
+        check(self._L.shrimp_gpu_sw_vector_batch(
+            self._h, _ptr(genome), genome.size, _ptr(genome_ls), _ptr(reads), reads.shape[1], reads.shape[0],
+            n, _ptr(goff), _ptr(glen), _ptr(read_idx), _ptr(rlen), _ptr(initbp), _ptr(out)),
+            "shrimp_gpu_sw_vector_batch")
+        return out
+
+    # ---- accounting ---------------------------------------------------------------------------
+    def launch_count(self) -> int:
+        return int(self._L.shrimp_gpu_launch_count(self._h))
+
+    def stage_times(self) -> dict:
+        names = (C.c_char_p * 16)()
+        ms = (C.c_float * 16)()
+        ln = (C.c_uint64 * 16)()
+        n = self._L.shrimp_gpu_stage_times(self._h, names, ms, ln, 16)
+        return {names[i].decode(): (float(ms[i]), int(ln[i])) for i in range(n)}
+
+    def stage_times_reset(self):
+        self._L.shrimp_gpu_stage_times_reset(self._h)

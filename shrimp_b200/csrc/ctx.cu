@@ -1,0 +1,147 @@
+// Context, error plumbing and scoring set-up of libshrimp_b200.so.
+#include <stdarg.h>
+#include "common.cuh"
+
+namespace shrimp {
+static thread_local char g_err[1024] = "";
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void free_genome(shrimp_gpu_ctx *ctx);
+void free_pipeline(shrimp_gpu_ctx *ctx);
+}  // namespace shrimp
+
+using namespace shrimp;
+
+extern "C" const char *shrimp_gpu_last_error(void) { return g_err; }
+
+extern "C" int shrimp_gpu_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+extern "C" int shrimp_gpu_create(int device, shrimp_gpu_ctx **out) {
+  if (!out) {
+    set_error("shrimp_gpu_create: out == NULL");
+    return SHRIMP_E_ARG;
+  }
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    set_error("no CUDA device available (%s); libshrimp_b200 has no CPU fallback",
+              e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    cudaGetLastError();
+    return SHRIMP_E_CUDA;
+  }
+  if (device < 0 || device >= n) {
+    set_error("device %d out of range [0,%d)", device, n);
+    return SHRIMP_E_ARG;
+  }
+  SH_CUDA(cudaSetDevice(device));
+  shrimp_gpu_ctx *c = new shrimp_gpu_ctx();
+  c->device = device;
+  cudaDeviceProp prop;
+  SH_CUDA(cudaGetDeviceProperties(&prop, device));
+  c->sm_count = prop.multiProcessorCount;
+  SH_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  for (int i = 0; i < ST_COUNT; i++) {
+    SH_CUDA(cudaEventCreate(&c->timers[i].ev0));
+    SH_CUDA(cudaEventCreate(&c->timers[i].ev1));
+  }
+  *out = c;
+  return SHRIMP_OK;
+}
+
+extern "C" void shrimp_gpu_destroy(shrimp_gpu_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  free_pipeline(c);
+  free_genome(c);
+  c->d_genome.release();
+  c->d_genome_ls.release();
+  c->d_reads.release();
+  c->d_task.release();
+  c->d_scores.release();
+  c->d_boundary.release();
+  for (int i = 0; i < ST_COUNT; i++) {
+    if (c->timers[i].ev0) cudaEventDestroy(c->timers[i].ev0);
+    if (c->timers[i].ev1) cudaEventDestroy(c->timers[i].ev1);
+  }
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+extern "C" uint64_t shrimp_gpu_launch_count(const shrimp_gpu_ctx *c) { return c ? c->launches : 0; }
+
+static const char *k_stage_names[ST_COUNT] = {"index_build", "seed_scan", "sw_vector", "pass1_select", "sw_full", "other"};
+
+extern "C" int shrimp_gpu_stage_times(shrimp_gpu_ctx *c, const char **names, float *ms, uint64_t *launches, int max_n) {
+  if (!c) return 0;
+  int n = ST_COUNT < max_n ? ST_COUNT : max_n;
+  for (int i = 0; i < n; i++) {
+    if (names) names[i] = k_stage_names[i];
+    if (ms) ms[i] = c->timers[i].ms;
+    if (launches) launches[i] = c->timers[i].launches;
+  }
+  return n;
+}
+
+extern "C" void shrimp_gpu_stage_times_reset(shrimp_gpu_ctx *c) {
+  if (!c) return;
+  for (int i = 0; i < ST_COUNT; i++) {
+    c->timers[i].ms = 0.f;
+    c->timers[i].launches = 0;
+  }
+}
+
+// sw_vector_setup (sw-vector.c:388-439) + sw_full_{ls,cs}_setup argument conventions: scores come
+// in with the CLI sign and are negated here; match*qrlen must stay below 2^15 for the int16 lanes.
+extern "C" int shrimp_gpu_sw_setup(shrimp_gpu_ctx *c, const shrimp_sw_params *p) {
+  if (!c || !p) {
+    set_error("shrimp_gpu_sw_setup: NULL argument");
+    return SHRIMP_E_ARG;
+  }
+  if (p->match <= 0 || p->mismatch >= 0 || p->a_gap_open > 0 || p->a_gap_ext > 0 || p->b_gap_open > 0 ||
+      p->b_gap_ext > 0 || p->max_read_len <= 0 || p->max_window_len <= 0) {
+    set_error("shrimp_gpu_sw_setup: scores must be match>0, mismatch<0, gap scores<=0, lengths>0");
+    return SHRIMP_E_ARG;
+  }
+  if ((long long)p->match * p->max_read_len >= 32768) {
+    // same guard as sw-vector.c:393
+    set_error("Match Value is too high/reads are too long: match x longest_read_length must be < 32768");
+    return SHRIMP_E_RANGE;
+  }
+  SwScores s;
+  s.match = p->match;
+  s.mismatch = p->mismatch;
+  s.a_open = -p->a_gap_open;
+  s.a_ext = -p->a_gap_ext;
+  s.b_open = -p->b_gap_open;
+  s.b_ext = -p->b_gap_ext;
+  s.xover = p->crossover;
+  s.use_colours = p->use_colours ? 1 : 0;
+  s.anchor_width = p->anchor_width;
+  s.indel_taboo_len = p->indel_taboo_len;
+  s.max_read_len = p->max_read_len;
+  s.max_window_len = p->max_window_len;
+  // smallest shift with 2^shift > match - mismatch; 5-bit codes << shift must stay below 2^15
+  int sh = 1;
+  while ((1 << sh) <= p->match - p->mismatch) sh++;
+  if (sh > 9 || s.a_open + s.a_ext >= 16384 || s.b_open + s.b_ext >= 16384) {
+    set_error("shrimp_gpu_sw_setup: |match - mismatch| or gap scores too large for the packed int16 kernel");
+    return SHRIMP_E_RANGE;
+  }
+  s.shift = sh;
+  s.valid = true;
+  c->sw = s;
+  return SHRIMP_OK;
+}
