@@ -88,6 +88,13 @@ int shrimp_gpu_sw_vector_batch(shrimp_gpu_ctx *ctx,
                                const int8_t *initbp,
                                int32_t *scores_out);
 
+/* ------------------------------------------------------------------------------------------
+ * Measurement helper (no reference counterpart): integer-pipe peak, in giga thread-level
+ * VIADDMNMX.S16x2 instructions per second, measured with a register-resident micro-benchmark.
+ * bench.py uses it as the denominator of the sw_vector roofline.
+ * ---------------------------------------------------------------------------------------- */
+int shrimp_gpu_dpx_peak(shrimp_gpu_ctx *ctx, double *ginstr_per_s);
+
 #ifdef __cplusplus
 }
 #endif

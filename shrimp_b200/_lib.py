@@ -50,6 +50,8 @@ def lib() -> C.CDLL:
     L.shrimp_gpu_sw_setup.restype = i32
     L.shrimp_gpu_sw_vector_batch.argtypes = [vp, vp, C.c_size_t, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp]
     L.shrimp_gpu_sw_vector_batch.restype = i32
+    L.shrimp_gpu_dpx_peak.argtypes = [vp, C.POINTER(C.c_double)]
+    L.shrimp_gpu_dpx_peak.restype = i32
     _lib = L
     return L
 

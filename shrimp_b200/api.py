@@ -140,6 +140,12 @@ class GpuContext:
             "shrimp_gpu_sw_vector_batch")
         return out
 
+    def dpx_peak(self) -> float:
+        """Measured integer-pipe peak in G thread-instructions/s (VIADDMNMX.S16x2)."""
+        v = C.c_double()
+        check(self._L.shrimp_gpu_dpx_peak(self._h, C.byref(v)), "shrimp_gpu_dpx_peak")
+        return float(v.value)
+
     # ---- accounting ---------------------------------------------------------------------------
     def launch_count(self) -> int:
         return int(self._L.shrimp_gpu_launch_count(self._h))

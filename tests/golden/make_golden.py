@@ -33,7 +33,52 @@ def golden_sw_vector():
         print("wrote sw_vector", name, scores[:8])
 
 
-TARGETS = {"sw_vector": golden_sw_vector}
+def golden_mapping():
+    """Runs the reference gmapper (and its DEBUG_HIT_LIST_* build) on the small synthetic configs and
+    stores the hot-path SAM fields and the post-pass1 hit lists."""
+    import re
+    import subprocess
+    import tempfile
+    from mapcases import MAP_CASES, LsCase
+    from oracle import pipeline as op
+    pat = re.compile(r"\(cn:(\d+),st:(\d+),gen_st:(\d+),g_off:(-?\d+),w_len:(\d+),scores:\(wg=(-?\d+),vc=(-?\d+),"
+                     r"fl=(-?\d+),poster=[^)]*\),matches:(\d+),pair_min:-?\d+,pair_max:-?\d+,"
+                     r"anchor:\(x=(-?\d+),y=(-?\d+),ln=(\d+),wd=(\d+)\)\)")
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    for name, spec in sorted(MAP_CASES.items()):
+        case = LsCase(name)
+        with tempfile.TemporaryDirectory() as d:
+            case.write_fasta(d)
+            sam = os.path.join(d, "out.sam")
+            with open(sam, "w") as f:
+                subprocess.run([os.path.join(ref_dir, "gmapper-ls"), *spec["args"], "reads.fa", "genome.fa"], cwd=d,
+                               stdout=f, stderr=subprocess.DEVNULL, check=True)
+            dbg = subprocess.run([os.path.join(ref_dir, "dbgbin", "gmapper-ls"), *spec["args"], "reads.fa", "genome.fa"],
+                                 cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, check=True, text=True).stderr
+            recs = op.parse_sam(sam)
+        name2idx = {n: i for i, n in enumerate(case.read_names)}
+        cn2idx = {n: i for i, n in enumerate(case.contig_names)}
+        sam_int = np.array([[name2idx[r[0]], r[1], cn2idx[r[2]], r[3], r[5], r[6]] for r in recs], dtype=np.int64)
+        cigars = np.array([r[4] for r in recs])
+        stage, mode, ridx = [], None, -1
+        for line in dbg.splitlines():
+            if line.startswith("Dumping hit list after pass1 for read:["):
+                mode, ridx = "p1", name2idx[line.split("[")[1].split("]")[0]]
+                continue
+            if line.startswith("Dumping") or line.startswith("SW full"):
+                mode = None
+                continue
+            if mode == "p1":
+                m = pat.match(line)
+                if m:
+                    v = list(map(int, m.groups()))
+                    stage.append((ridx, v[1], v[0], v[3], v[4], v[5], v[6], v[8], v[9], v[10], v[11], v[12]))
+        np.savez_compressed(os.path.join(HERE, f"map_{name}.npz"), sam=sam_int, cigars=cigars,
+                            stage=np.array(stage, dtype=np.int64))
+        print("wrote map", name, sam_int.shape, len(stage))
+
+
+TARGETS = {"sw_vector": golden_sw_vector, "mapping": golden_mapping}
 
 if __name__ == "__main__":
     assert oracle.have_ref(), "build oracle/_ref first: make -C oracle ref"

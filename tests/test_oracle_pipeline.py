@@ -1,0 +1,55 @@
+"""Pins the oracle's per-read pipeline (oracle/oracle_pipeline.inc) against golden vectors produced by
+the reference gmapper binary: the hot-path SAM fields of every record (flag, contig, pos, CIGAR, AS, NM)
+and the post-pass1 hit lists of its DEBUG_HIT_LIST_PASS1 build (tests/golden/make_golden.py mapping)."""
+import os
+
+import numpy as np
+import pytest
+
+from mapcases import GOLD, MAP_CASES, LsCase, stage_tuple_array
+from oracle import pipeline as op
+
+
+def run_oracle(case: LsCase, **over):
+    g = op.Genome(case.contig_codes, False)
+    ix = op.Index(g, case.seeds)
+    opts = op.MapOptions(scores=case.scores, list_cutoff=op.auto_list_cutoff(g.total_len, max(s.weight for s in case.seeds)),
+                         **over)
+    hits, nper, stage, stats = op.map_reads(g, ix, opts, case.packed, case.read_len, want_stage=True)
+    return g, hits, nper, stage, stats
+
+
+def sam_arrays(case, g, hits):
+    rows, cig = [], []
+    for h in hits:
+        f = op.sam_fields(h, int(case.read_len[h["read_idx"]]), int(g.lens[h["cn"]]))
+        rows.append([int(h["read_idx"]), f[0], f[1], f[2], f[4], f[5]])
+        cig.append(f[3])
+    return np.array(rows, dtype=np.int64).reshape(-1, 6), np.array(cig)
+
+
+@pytest.mark.parametrize("name", sorted(MAP_CASES))
+def test_oracle_pipeline_matches_reference_golden(name):
+    gold = np.load(os.path.join(GOLD, f"map_{name}.npz"))
+    case = LsCase(name)
+    g, hits, nper, stage, stats = run_oracle(case, **MAP_CASES[name]["opts"])
+    sam, cig = sam_arrays(case, g, hits)
+    assert sam.shape == gold["sam"].shape
+    assert np.array_equal(sam, gold["sam"])
+    assert np.array_equal(cig, gold["cigars"])
+    assert np.array_equal(stage_tuple_array(stage), gold["stage"])
+
+
+def test_oracle_index_is_sorted_csr():
+    case = LsCase("c1_small")
+    g = op.Genome(case.contig_codes, False)
+    ix = op.Index(g, case.seeds)
+    for sn, s in enumerate(case.seeds):
+        lens, pos = ix.bucket_lens(sn), ix.positions(sn)
+        # every position once: L - span + 1 per contig (no N in this genome)
+        assert lens.sum() == sum(c.size - s.span + 1 for c in case.contig_codes) == pos.size
+        starts = np.concatenate([[0], np.cumsum(lens.astype(np.int64))[:-1]]).astype(np.int64)
+        big = np.nonzero(lens > 1)[0][:2000]
+        for m in big:
+            seg = pos[int(starts[m]):int(starts[m]) + int(lens[m])]
+            assert (np.diff(seg.astype(np.int64)) > 0).all()
