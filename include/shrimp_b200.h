@@ -89,6 +89,30 @@ int shrimp_gpu_sw_vector_batch(shrimp_gpu_ctx *ctx,
                                int32_t *scores_out);
 
 /* ------------------------------------------------------------------------------------------
+ * Genome residency.  Replaces the arrays load_genome builds (gmapper/genome.c:1092-1124,
+ * globals gmapper.h:264-275): takes the reference's own genome_contigs[] (packed letters, one
+ * array per contig), genome_len[] and num_contigs, and derives genome_contigs_rc (util.c:541-598)
+ * and, in colour space, genome_cs_contigs / genome_cs_contigs_rc (fasta.c:586-612) in HBM.
+ * Global coordinates are contig_offsets[cn] + position, as in the reference.
+ * ---------------------------------------------------------------------------------------- */
+int shrimp_gpu_genome_load(shrimp_gpu_ctx *ctx, int num_contigs, const uint32_t *const *genome_contigs,
+                           const uint32_t *genome_len, int colour_space);
+/* which: 0 letters fwd, 1 letters rc, 2 colours fwd, 3 colours rc; global packed coordinates */
+int shrimp_gpu_genome_export(shrimp_gpu_ctx *ctx, int which, uint32_t *out_words, size_t n_words);
+
+/* ------------------------------------------------------------------------------------------
+ * Spaced-seed projection ("genome map").  Replaces the projection loop of load_genome
+ * (genome.c:1138-1166) + KMER_TO_MAPIDX (gmapper.h:323-370) for seeds parsed as add_spaced_seed
+ * does (seeds.c:9-42; masks[sn] bit 0 = rightmost seed character).  hflag = -H hashed k-mers.
+ * Result: per seed a CSR (genomemap_len -> offsets, genomemap lists concatenated, ascending).
+ * shrimp_gpu_index_export returns it in the layout of the reference's -S files (genome.c:37-63).
+ * ---------------------------------------------------------------------------------------- */
+int shrimp_gpu_index_build(shrimp_gpu_ctx *ctx, int n_seeds, const uint64_t *masks, const int32_t *spans,
+                           const int32_t *weights, int hflag);
+int shrimp_gpu_index_nbuckets(shrimp_gpu_ctx *ctx, int sn, uint32_t *nbuckets, uint64_t *total);
+int shrimp_gpu_index_export(shrimp_gpu_ctx *ctx, int sn, uint32_t *lens_out, uint32_t *pos_out, uint64_t *total_out);
+
+/* ------------------------------------------------------------------------------------------
  * Measurement helper (no reference counterpart): integer-pipe peak, in giga thread-level
  * VIADDMNMX.S16x2 instructions per second, measured with a register-resident micro-benchmark.
  * bench.py uses it as the denominator of the sw_vector roofline.

@@ -52,6 +52,16 @@ def lib() -> C.CDLL:
     L.shrimp_gpu_sw_vector_batch.restype = i32
     L.shrimp_gpu_dpx_peak.argtypes = [vp, C.POINTER(C.c_double)]
     L.shrimp_gpu_dpx_peak.restype = i32
+    L.shrimp_gpu_genome_load.argtypes = [vp, i32, vp, vp, i32]
+    L.shrimp_gpu_genome_load.restype = i32
+    L.shrimp_gpu_genome_export.argtypes = [vp, i32, vp, C.c_size_t]
+    L.shrimp_gpu_genome_export.restype = i32
+    L.shrimp_gpu_index_build.argtypes = [vp, i32, vp, vp, vp, i32]
+    L.shrimp_gpu_index_build.restype = i32
+    L.shrimp_gpu_index_nbuckets.argtypes = [vp, i32, C.POINTER(C.c_uint32), C.POINTER(u64)]
+    L.shrimp_gpu_index_nbuckets.restype = i32
+    L.shrimp_gpu_index_export.argtypes = [vp, i32, vp, vp, C.POINTER(u64)]
+    L.shrimp_gpu_index_export.restype = i32
     _lib = L
     return L
 

@@ -140,6 +140,43 @@ class GpuContext:
             "shrimp_gpu_sw_vector_batch")
         return out
 
+    # ---- genome + index ---------------------------------------------------------------------
+    def load_genome(self, contigs_packed: list, genome_len, colour_space: bool = False):
+        """load_genome's arrays (genome.c:1092-1124): packed letter contigs -> HBM (+ rc, colour arrays)."""
+        arrs = [np.ascontiguousarray(c, dtype=np.uint32) for c in contigs_packed]
+        ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+        lens = np.ascontiguousarray(genome_len, dtype=np.uint32)
+        check(self._L.shrimp_gpu_genome_load(self._h, len(arrs), C.cast(ptrs, C.c_void_p), _ptr(lens),
+                                             int(colour_space)), "shrimp_gpu_genome_load")
+        self.genome_len = lens.copy()
+        self.total_len = int(lens.astype(np.int64).sum())
+        self.colour_space = bool(colour_space)
+
+    def genome_export(self, which: int) -> np.ndarray:
+        out = np.zeros((self.total_len + 7) // 8, dtype=np.uint32)
+        check(self._L.shrimp_gpu_genome_export(self._h, which, _ptr(out), out.size), "shrimp_gpu_genome_export")
+        return out
+
+    def build_index(self, seeds, hflag: bool = False):
+        """projection loop of load_genome (genome.c:1138-1166) for seeds from shrimp_b200.seeds."""
+        masks = np.array([s.mask for s in seeds], dtype=np.uint64)
+        spans = np.array([s.span for s in seeds], dtype=np.int32)
+        weights = np.array([s.weight for s in seeds], dtype=np.int32)
+        check(self._L.shrimp_gpu_index_build(self._h, len(seeds), _ptr(masks), _ptr(spans), _ptr(weights),
+                                             int(hflag)), "shrimp_gpu_index_build")
+        self.seeds = list(seeds)
+
+    def export_index(self, sn: int):
+        """(genomemap_len[sn], concatenated genomemap[sn] lists) as in the -S files (genome.c:37-63)."""
+        nb = C.c_uint32()
+        tot = C.c_uint64()
+        check(self._L.shrimp_gpu_index_nbuckets(self._h, sn, C.byref(nb), C.byref(tot)), "shrimp_gpu_index_nbuckets")
+        lens = np.zeros(nb.value, dtype=np.uint32)
+        pos = np.zeros(max(1, tot.value), dtype=np.uint32)
+        check(self._L.shrimp_gpu_index_export(self._h, sn, _ptr(lens), _ptr(pos), C.byref(tot)),
+              "shrimp_gpu_index_export")
+        return lens, pos[: tot.value]
+
     def dpx_peak(self) -> float:
         """Measured integer-pipe peak in G thread-instructions/s (VIADDMNMX.S16x2)."""
         v = C.c_double()
