@@ -113,6 +113,84 @@ int shrimp_gpu_index_nbuckets(shrimp_gpu_ctx *ctx, int sn, uint32_t *nbuckets, u
 int shrimp_gpu_index_export(shrimp_gpu_ctx *ctx, int sn, uint32_t *lens_out, uint32_t *pos_out, uint64_t *total_out);
 
 /* ------------------------------------------------------------------------------------------
+ * Chunk-level mapping.  Replaces handle_read (gmapper/mapping.c:1773-1868) for a whole chunk of
+ * unpaired reads with the default single option set of gmapper.c:2601-2632, i.e. per read:
+ *   read_get_mapidxs :76, read_get_region_counts :459, read_get_anchor_list :1008,
+ *   read_get_hit_list :1232, read_pass1 :1345 (f1_run / sw_vector / sw_gapless),
+ *   read_get_vector_hits :1376, read_pass2 :1631 (hit_run_full_sw -> sw_full_ls / sw_full_cs,
+ *   hit_run_post_sw, read_remove_duplicate_hits, ranking).
+ * What read_output (gmapper/output.c:955) would receive comes back as shrimp_hit records in read
+ * order, then in the order of hits_pass2[].  The caller (the reference's unchanged output.c, or a
+ * test) formats SAM from them.  Field names follow options/globals of gmapper.h:50-141.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct shrimp_map_params {
+  double window_len;            /* -w: > 0 percent of read length, < 0 absolute (util.h:48-53) */
+  double window_overlap;        /* -l */
+  double window_gen_threshold;  /* -r */
+  double sw_vect_threshold;     /* -v */
+  double sw_full_threshold;     /* -h */
+  double score_alpha, score_beta; /* gmapper.c:2559-2568, used by hit_run_post_sw */
+  int32_t match_mode;           /* -n: 1 or 2 (unpaired) */
+  int32_t num_outputs;          /* -o */
+  int32_t num_tmp_outputs;      /* 20 + num_outputs */
+  int32_t gapless;              /* -U / mirna: sw_gapless instead of sw_vector */
+  int32_t hash_filter_calls;    /* 0 with -Z */
+  int32_t use_regions;
+  int32_t region_bits, region_overlap;
+  int32_t Gflag, Tflag;         /* global-in-read alignment; reversed tie-breaks on the rc strand */
+  int32_t strata, max_alignments;
+  int32_t compute_mapping_qualities;
+  uint32_t list_cutoff;         /* -z / automatic (gmapper.c:2811-2837) */
+} shrimp_map_params;
+
+/* One reported alignment: read_hit + sw_full_results (gmapper-definitions.h:125-153,
+ * sw-full-common.h:13-48).  The alignment itself is an edit script in `edits`: one byte per
+ * alignment column, the reference's backtrace codes (sw-full-ls.c:44-46) -- 1 BACK_INSERTION
+ * (genome base against '-'), 2 BACK_DELETION (read base against '-'), 3 BACK_MATCH_MISMATCH;
+ * colour space adds 4 when the column carries a crossover.  dbalign/qralign follow from it. */
+typedef struct shrimp_hit {
+  int32_t read_idx, cn, gen_st, w_len;
+  int64_t g_off;                /* rh->g_off, in the orientation of gen_st */
+  int32_t score_vector, score_full, pass2_key, score_max, matches, sw_score;
+  double  posterior;
+  int32_t read_start, rmapped, genome_start, gmapped;
+  int32_t sfr_matches, mismatches, insertions, deletions, crossovers;
+  int32_t edit_len;
+  int64_t edit_off;
+} shrimp_hit;
+
+/* A read_hit after read_pass1 (stage-level parity with DEBUG_HIT_LIST_PASS1 dumps) */
+typedef struct shrimp_stage_hit {
+  int32_t read_idx, st, cn, w_len;
+  int64_t g_off;                /* g_off_pos_strand */
+  int32_t score_window_gen, matches, score_max, score_vector, pct_score_vector;
+  int32_t ax, ay, alen, awidth;
+} shrimp_stage_hit;
+
+typedef struct shrimp_map_stats {
+  uint64_t list_entries;        /* index positions gathered */
+  uint64_t surviving_entries;   /* after the region filter */
+  uint64_t anchors, hits;
+  uint64_t heap_replays;        /* read strands that needed exact heap-order emulation */
+  uint64_t vector_tasks;        /* windows scored on the device (superset) */
+  uint64_t vector_calls;        /* sw_vector calls the reference makes (pass 1 + pass 2) */
+  uint64_t vector_cells;        /* sum glen*rlen over those calls (sw-vector.c:509) */
+  uint64_t vector_bypassed;     /* f1 cache hits */
+  uint64_t full_calls, full_cells;
+} shrimp_map_stats;
+
+/* initbp: per-read initial base (colour space) or NULL.  hits_cap >= n_reads*num_outputs always
+ * suffices.  Returns SHRIMP_E_NOMEM with *edits_used = required bytes if edits_cap is too small.
+ * stage / stage_cap / n_stage are optional (NULL / 0). */
+int shrimp_gpu_map_reads(shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, int n_reads,
+                         const uint32_t *reads, int read_stride_words, const int32_t *read_len,
+                         const int8_t *initbp,
+                         shrimp_hit *hits, int64_t hits_cap, int32_t *n_hits_per_read,
+                         uint8_t *edits, int64_t edits_cap, int64_t *n_hits, int64_t *edits_used,
+                         shrimp_stage_hit *stage, int64_t stage_cap, int64_t *n_stage,
+                         shrimp_map_stats *stats);
+
+/* ------------------------------------------------------------------------------------------
  * Measurement helper (no reference counterpart): integer-pipe peak, in giga thread-level
  * VIADDMNMX.S16x2 instructions per second, measured with a register-resident micro-benchmark.
  * bench.py uses it as the denominator of the sw_vector roofline.

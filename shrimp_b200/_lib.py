@@ -24,6 +24,40 @@ class SwParams(C.Structure):
         "use_colours", "anchor_width", "indel_taboo_len", "max_read_len", "max_window_len")]
 
 
+class MapParamsC(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("window_len", "window_overlap", "window_gen_threshold", "sw_vect_threshold",
+                                          "sw_full_threshold", "score_alpha", "score_beta")] + \
+               [(n, C.c_int32) for n in ("match_mode", "num_outputs", "num_tmp_outputs", "gapless", "hash_filter_calls",
+                                         "use_regions", "region_bits", "region_overlap", "Gflag", "Tflag", "strata",
+                                         "max_alignments", "compute_mapping_qualities")] + \
+               [("list_cutoff", C.c_uint32)]
+
+
+class HitC(C.Structure):
+    _fields_ = [("read_idx", C.c_int32), ("cn", C.c_int32), ("gen_st", C.c_int32), ("w_len", C.c_int32),
+                ("g_off", C.c_int64),
+                ("score_vector", C.c_int32), ("score_full", C.c_int32), ("pass2_key", C.c_int32),
+                ("score_max", C.c_int32), ("matches", C.c_int32), ("sw_score", C.c_int32),
+                ("posterior", C.c_double),
+                ("read_start", C.c_int32), ("rmapped", C.c_int32), ("genome_start", C.c_int32), ("gmapped", C.c_int32),
+                ("sfr_matches", C.c_int32), ("mismatches", C.c_int32), ("insertions", C.c_int32),
+                ("deletions", C.c_int32), ("crossovers", C.c_int32), ("edit_len", C.c_int32), ("edit_off", C.c_int64)]
+
+
+class StageHitC(C.Structure):
+    _fields_ = [("read_idx", C.c_int32), ("st", C.c_int32), ("cn", C.c_int32), ("w_len", C.c_int32),
+                ("g_off", C.c_int64),
+                ("score_window_gen", C.c_int32), ("matches", C.c_int32), ("score_max", C.c_int32),
+                ("score_vector", C.c_int32), ("pct_score_vector", C.c_int32),
+                ("ax", C.c_int32), ("ay", C.c_int32), ("alen", C.c_int32), ("awidth", C.c_int32)]
+
+
+class MapStatsC(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("list_entries", "surviving_entries", "anchors", "hits", "heap_replays",
+                                          "vector_tasks", "vector_calls", "vector_cells", "vector_bypassed",
+                                          "full_calls", "full_cells")]
+
+
 def lib() -> C.CDLL:
     global _lib
     if _lib is not None:
@@ -62,6 +96,10 @@ def lib() -> C.CDLL:
     L.shrimp_gpu_index_nbuckets.restype = i32
     L.shrimp_gpu_index_export.argtypes = [vp, i32, vp, vp, C.POINTER(u64)]
     L.shrimp_gpu_index_export.restype = i32
+    L.shrimp_gpu_map_reads.argtypes = [vp, C.POINTER(MapParamsC), i32, vp, i32, vp, vp, vp, C.c_int64, vp, vp,
+                                       C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64), vp, C.c_int64,
+                                       C.POINTER(C.c_int64), C.POINTER(MapStatsC)]
+    L.shrimp_gpu_map_reads.restype = i32
     _lib = L
     return L
 

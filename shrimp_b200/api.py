@@ -11,7 +11,9 @@ from dataclasses import dataclass
 
 import numpy as np
 
-from ._lib import SwParams, check, lib
+import math
+
+from ._lib import HitC, MapParamsC, MapStatsC, StageHitC, SwParams, check, lib
 
 # fasta.h:26-42
 _LS_CODE = np.full(256, 255, dtype=np.uint8)
@@ -71,6 +73,66 @@ class Scores:
 # gmapper-defaults.h:45-58
 LS_DEFAULT_SCORES = Scores(10, -15, -33, -7, -33, -3, 0)
 CS_DEFAULT_SCORES = Scores(10, -24, -33, -7, -33, -3, -20)
+
+
+def score_alpha_beta(scores: Scores, colour_space: bool, pr_xover: float = 0.03):
+    """score_alpha / score_beta exactly as gmapper.c:2559-2568 derives them (double, same libm)."""
+    if colour_space:
+        alpha = float(scores.crossover) / (math.log(pr_xover / 3) / math.log(2.0))
+        pr_mismatch = 1.0 / (1.0 + 1.0 / 3.0 * math.pow(2.0, (float(scores.match) - float(scores.mismatch)) / alpha))
+    else:
+        pr_mismatch = .01
+        alpha = (float(scores.match) - float(scores.mismatch)) / (
+            math.log((1 - pr_mismatch) / (pr_mismatch / 3.0)) / math.log(2.0))
+    beta = float(scores.match) - 2 * alpha - alpha * math.log(1 - pr_mismatch) / math.log(2.0)
+    return alpha, beta
+
+
+def auto_list_cutoff(total_genome_len: int, max_seed_weight: int) -> int:
+    """automatic index trimming, gmapper.c:2811-2837: max(1000, 100*L/4^W)"""
+    c = ((100 * total_genome_len) // (4 ** max_seed_weight)) & 0xFFFFFFFF
+    return c if c > 1000 else 1000
+
+
+@dataclass
+class MapParams:
+    """Mapping options with the defaults of gmapper.h:50-141 / gmapper-defaults.h (unpaired)."""
+    window_len: float = 140.0
+    window_overlap: float = 90.0
+    window_gen_threshold: float = 55.0
+    sw_vect_threshold: float = 47.0
+    sw_full_threshold: float = 50.0
+    match_mode: int = 2
+    num_outputs: int = 10
+    num_tmp_outputs: int = 30
+    gapless: bool = False
+    hash_filter_calls: bool = True
+    use_regions: bool = True
+    region_bits: int = 11
+    region_overlap: int = 50
+    Gflag: bool = True
+    Tflag: bool = True
+    strata: bool = False
+    max_alignments: int = 0
+    compute_mapping_qualities: bool = True
+    list_cutoff: int = 0xFFFFFFFF
+
+    def to_c(self, scores: Scores, colour_space: bool) -> MapParamsC:
+        alpha, beta = score_alpha_beta(scores, colour_space)
+        return MapParamsC(self.window_len, self.window_overlap, self.window_gen_threshold, self.sw_vect_threshold,
+                          self.sw_full_threshold, alpha, beta, self.match_mode, self.num_outputs,
+                          self.num_tmp_outputs, int(self.gapless), int(self.hash_filter_calls), int(self.use_regions),
+                          self.region_bits, self.region_overlap, int(self.Gflag), int(self.Tflag), int(self.strata),
+                          self.max_alignments, int(self.compute_mapping_qualities), self.list_cutoff & 0xFFFFFFFF)
+
+
+@dataclass
+class MapResult:
+    hits: np.ndarray            # structured array of shrimp_hit
+    n_hits_per_read: np.ndarray
+    edits: np.ndarray           # uint8 pool
+    stage: np.ndarray | None
+    stats: dict
 
 
 def _ptr(a):
@@ -176,6 +238,38 @@ class GpuContext:
         check(self._L.shrimp_gpu_index_export(self._h, sn, _ptr(lens), _ptr(pos), C.byref(tot)),
               "shrimp_gpu_index_export")
         return lens, pos[: tot.value]
+
+    # ---- chunk mapping ------------------------------------------------------------------------
+    def map_reads(self, params: MapParams, scores: Scores, reads: np.ndarray, read_len, initbp=None,
+                  want_stage: bool = False, stage_cap_per_read: int = 256) -> MapResult:
+        """handle_read (mapping.c:1773) for a chunk: returns what read_output would receive."""
+        reads = np.ascontiguousarray(reads, dtype=np.uint32)
+        read_len = np.ascontiguousarray(read_len, dtype=np.int32)
+        n = reads.shape[0]
+        pc = params.to_c(scores, getattr(self, "colour_space", False))
+        hits = np.zeros(max(1, n * params.num_outputs), dtype=HitC)
+        n_per = np.zeros(max(1, n), dtype=np.int32)
+        max_rl = int(read_len.max()) if n else 0
+        pool_cap = max(1024, n * 3 * max(1, max_rl))
+        if initbp is not None:
+            initbp = np.ascontiguousarray(initbp, dtype=np.int8)
+        stage = np.zeros(max(1, n * stage_cap_per_read), dtype=StageHitC) if want_stage else None
+        while True:
+            edits = np.zeros(pool_cap, dtype=np.uint8)
+            n_hits, e_used, n_stage = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+            st = MapStatsC()
+            rc = self._L.shrimp_gpu_map_reads(
+                self._h, C.byref(pc), n, _ptr(reads), reads.shape[1] if n else 1, _ptr(read_len), _ptr(initbp),
+                _ptr(hits), hits.size, _ptr(n_per), _ptr(edits), pool_cap, C.byref(n_hits), C.byref(e_used),
+                _ptr(stage), stage.size if want_stage else 0, C.byref(n_stage), C.byref(st))
+            if rc == -5 and e_used.value > pool_cap:   # SHRIMP_E_NOMEM: edit pool too small, size is returned
+                pool_cap = int(e_used.value) + 1024
+                continue
+            check(rc, "shrimp_gpu_map_reads")
+            break
+        stats = {k: int(getattr(st, k)) for k, _ in MapStatsC._fields_}
+        return MapResult(hits[: n_hits.value], n_per[:n], edits[: e_used.value],
+                         stage[: n_stage.value] if want_stage else None, stats)
 
     def dpx_peak(self) -> float:
         """Measured integer-pipe peak in G thread-instructions/s (VIADDMNMX.S16x2)."""

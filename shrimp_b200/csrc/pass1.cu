@@ -1,0 +1,197 @@
+// Pass 1 around the vector filter: task construction for sw_vector, the f1 window-cache hash,
+// the sequential replay of read_pass1_per_strand and the bounded top-k heap.
+//
+// The reference scores windows one by one and lets earlier results decide whether later windows
+// are scored at all (overlap skip, mapping.c:1287-1293) or looked up in a lossy 2^20-slot cache
+// (f1-wrapper.h:97-134).  On the device every eligible window is scored first (sw_vector.cu, a
+// superset of what the reference scores); `pass1_select_kernel` then replays the reference's
+// sequential rules per read strand in list order -- skipped windows get score 0, windows whose cache
+// slot was written earlier in the same (read, strand) pass get the writer's score -- and finally
+// emulates extheap_unpaired_pass1 (heap.h:226-307, mapping.c:1376-1411) so that the set AND order of
+// hits handed to pass 2 are the reference's.
+#include "stages.cuh"
+
+namespace shrimp {
+
+
+// hash_accumulate / hash_finalize (common/hash.h:69-92), hash_genome_window (util.h:220-241)
+__device__ __forceinline__ uint32_t hash_genome_window_dev(const uint32_t *genome, uint64_t goff, uint32_t glen) {
+  uint32_t key = 0;
+  for (uint32_t i = 0; i < (glen + 15) / 16; i++) {
+    uint32_t buffer = 0;
+    for (uint32_t j = 0; j < 16 && i * 16 + j < glen; j++) {
+      buffer <<= 2;
+      buffer |= extract4(genome, goff + i * 16 + j) & 3u;
+    }
+    key += (buffer >> 16);
+    uint32_t tmp = ((buffer & 0xFFFFu) << 11) ^ key;
+    key = (key << 16) ^ tmp;
+    key += key >> 11;
+  }
+  key ^= key << 3;
+  key += key >> 5;
+  key ^= key << 4;
+  key += key >> 17;
+  key ^= key << 25;
+  key += key >> 6;
+  return key;
+}
+
+// one thread per read strand: fill the sw_vector task arrays for its hits
+__global__ void build_vec_tasks_kernel(const TaskBuildParams P) {
+  const uint32_t rs = blockIdx.x * blockDim.x + threadIdx.x;
+  if (rs >= 2u * (uint32_t)P.n_reads) return;
+  const uint2 rg = P.rs_range[rs];
+  const int r = (int)(rs >> 1), st = (int)(rs & 1u);
+  const int rl = P.read_len[r];
+  const bool cs = P.M.colour_space != 0;
+  for (uint32_t k = 0; k < rg.y; k++) {
+    const uint32_t hi = rg.x + k;
+    const DevHit h = P.hits[hi];
+    const bool eligible = h.matches >= P.M.min_matches;
+    const uint32_t coff = P.G.contig_off[h.cn];
+    // orientation used by pass 1: letter space always scores read strand st on the forward genome;
+    // colour space scores the forward read and flips strand-1 windows onto the rc genome.
+    const int ori = (cs && st == 1) ? 1 : 0;
+    const uint32_t g = ori ? coff + (P.G.contig_len[h.cn] - h.g_off - (uint32_t)h.w_len) : coff + h.g_off;
+    for (int o = 0; o < (cs ? 2 : 1); o++) {
+      const bool mine = eligible && o == ori;
+      P.goff[o][hi] = g;
+      P.glen[o][hi] = mine ? h.w_len : 0;
+      P.ridx[o][hi] = cs ? (int32_t)(2 * r) : (int32_t)rs;
+      P.rlen[o][hi] = rl;
+      if (cs) P.initbp_out[o][hi] = P.initbp[r];
+    }
+    if (P.slot) {
+      const uint32_t *gen = cs ? (ori ? P.G.cs_rc : P.G.cs) : P.G.ls;
+      P.slot[hi] = eligible ? (hash_genome_window_dev(gen, g, (uint32_t)h.w_len) % 1048576u) : 0xffffffffu;
+    }
+  }
+}
+
+
+// one thread per read: read_pass1 (both strands) + read_get_vector_hits
+__global__ void pass1_select_kernel(const Pass1Params P) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= P.n_reads) return;
+  const MapParamsDev &M = P.M;
+  const int rl = P.read_len[r];
+  const int window_len = (int)(unsigned short)abs_or_pct_d(M.window_len, M.window_len_frac, (double)rl);
+  const unsigned int ovl = (unsigned int)abs_or_pct_d(M.overlap_thr, M.overlap_frac, (double)window_len);
+  const bool cs = M.colour_space != 0;
+  uint32_t calls = 0, bypassed = 0;
+  unsigned long long cells = 0;
+  for (int st = 0; st < 2; st++) {
+    const uint2 rg = P.rs_range[2 * r + st];
+    const int ori = (cs && st == 1) ? 1 : 0;
+    int last_good_cn = -1;
+    unsigned int last_good_g_off = 0;
+    for (uint32_t k = 0; k < rg.y; k++) {
+      const uint32_t hi = rg.x + k;
+      DevHit h = P.hits[hi];
+      P.writer[hi] = 0;
+      if (h.matches < M.min_matches) continue;
+      // window overlap with the last good window (:1287-1293): llint + unsigned  <=  unsigned + int
+      if (last_good_cn >= 0 && h.cn == last_good_cn &&
+          (long long)h.g_off + (long long)ovl <= (long long)(unsigned int)(last_good_g_off + (unsigned int)window_len)) {
+        h.score_vector = 0;
+        h.pct_vector = 0;
+        P.hits[hi].score_vector = 0;
+        P.hits[hi].pct_vector = 0;
+        continue;
+      }
+      int score = P.vtrue[ori][hi];
+      bool hit_in_cache = false;
+      if (M.hash_filter_calls) {
+        const uint32_t sl = P.slot[hi];
+        for (uint32_t q = 0; q < k; q++) {
+          const uint32_t hq = rg.x + q;
+          if (P.writer[hq] && P.slot[hq] == sl) {
+            score = P.vtrue[ori][hq];
+            hit_in_cache = true;
+            break;
+          }
+        }
+        if (!hit_in_cache) P.writer[hi] = 1;
+      }
+      if (hit_in_cache) {
+        bypassed++;
+      } else {
+        calls++;
+        cells += (unsigned long long)h.w_len * (unsigned long long)rl;
+      }
+      const int pct = (1000 * 100 * score) / h.score_max;
+      P.hits[hi].score_vector = score;
+      P.hits[hi].pct_vector = pct;
+      if (score >= (int)abs_or_pct_d(M.vect_thr, M.vect_frac, (double)h.score_max)) {
+        last_good_cn = h.cn;
+        last_good_g_off = h.g_off;
+      }
+    }
+  }
+  // read_get_vector_hits (:1376-1411): min-heap of capacity num_tmp_outputs keyed on pass1_key
+  const bool absolute = M.vect_thr < 0;
+  int32_t *a = P.sel + (size_t)r * M.num_tmp_outputs;
+  int load = 0;
+  // keys of the heap entries are re-read from the hits (score_vector / pct_vector are final now)
+#define P1KEY(slot_) (absolute ? P.hits[slot_].score_vector : P.hits[slot_].pct_vector)
+  for (int st = 0; st < 2; st++) {
+    const uint2 rg = P.rs_range[2 * r + st];
+    for (uint32_t k = 0; k < rg.y; k++) {
+      const int32_t hi = (int32_t)(rg.x + k);
+      const DevHit h = P.hits[hi];
+      if (h.score_vector >= (int)abs_or_pct_d(M.vect_thr, M.vect_frac, (double)h.score_max) &&
+          (load < M.num_tmp_outputs || (absolute ? h.score_vector : h.pct_vector) > P1KEY(a[0]))) {
+        const int key = absolute ? h.score_vector : h.pct_vector;
+        if (load < M.num_tmp_outputs) {  // extheap insert + percolate_up
+          a[load] = hi;
+          load++;
+          int node = load, parent = node / 2;
+          while (node > 1 && key < P1KEY(a[parent - 1])) {
+            // (a[node-1] is the new element while it bubbles up)
+            int32_t tmp = a[parent - 1];
+            a[parent - 1] = a[node - 1];
+            a[node - 1] = tmp;
+            node = parent;
+            parent = node / 2;
+          }
+        } else {  // replace_min + percolate_down
+          a[0] = hi;
+          int node = 1;
+          for (;;) {
+            int left = node * 2, right = left + 1, mn = node;
+            if (left <= load && P1KEY(a[left - 1]) < P1KEY(a[node - 1])) mn = left;
+            if (right <= load && P1KEY(a[right - 1]) < P1KEY(a[mn - 1])) mn = right;
+            if (mn == node) break;
+            int32_t tmp = a[mn - 1];
+            a[mn - 1] = a[node - 1];
+            a[node - 1] = tmp;
+            node = mn;
+          }
+        }
+      }
+    }
+  }
+#undef P1KEY
+  P.n_sel[r] = load;
+  if (calls) atomicAdd(&P.stats[4], calls);
+  if (bypassed) atomicAdd(&P.stats[5], bypassed);
+  if (cells) atomicAdd((unsigned long long *)&P.stats[6], cells);
+}
+
+int launch_build_vec_tasks(shrimp_gpu_ctx *ctx, const TaskBuildParams &P) {
+  const unsigned n = 2u * (unsigned)P.n_reads;
+  build_vec_tasks_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(P);
+  SH_CUDA(cudaGetLastError());
+  SH_LAUNCHED(ctx, ST_PASS1);
+  return SHRIMP_OK;
+}
+
+int launch_pass1_select(shrimp_gpu_ctx *ctx, const Pass1Params &P) {
+  pass1_select_kernel<<<(P.n_reads + 127) / 128, 128, 0, ctx->stream>>>(P);
+  SH_CUDA(cudaGetLastError());
+  SH_LAUNCHED(ctx, ST_PASS1);
+  return SHRIMP_OK;
+}
+
+}  // namespace shrimp

@@ -1,0 +1,732 @@
+// Chunk pipeline: shrimp_gpu_map_reads = handle_read (gmapper/mapping.c:1773-1868) for a whole
+// chunk of reads.  Device stages: read reverse-complement -> seed scan (scan.cu) -> sw_vector over
+// all candidate windows (sw_vector.cu) -> pass-1 replay + top-k (pass1.cu) -> full SW with
+// traceback (sw_full.cu).  Host stage (this file, plain C++ on the few <=30 hits per read that
+// survive): hit_run_post_sw's double arithmetic, the pass-2 threshold, duplicate removal with
+// qsort and the final ranking -- the parts SURVEY section 8 a21 keeps on the host because their
+// tie order is glibc qsort's.
+#include <math.h>
+#include <stdlib.h>
+#include <algorithm>
+#include "stages.cuh"
+
+namespace shrimp {
+
+// ---- entry points of the other translation units -----------------------------------------------
+size_t scan_smem_bytes(int cap, int max_rl, int warps);
+
+int launch_scan(shrimp_gpu_ctx *ctx, ScanParams &P, int warps_per_cta, int n_ctas);
+int launch_build_vec_tasks(shrimp_gpu_ctx *ctx, const TaskBuildParams &P);
+int launch_pass1_select(shrimp_gpu_ctx *ctx, const Pass1Params &P);
+int launch_sw_full_ls(shrimp_gpu_ctx *ctx, const FullParams &P);
+
+__constant__ uint8_t c_cmpl_r[16] = {3, 2, 1, 0, 0, 10, 9, 7, 8, 6, 5, 14, 13, 12, 11, 15};
+
+__device__ __forceinline__ void put4_dev(uint32_t *a, int i, uint32_t v) {
+  uint32_t w = a[i >> 3];
+  w &= ~(0xfu << (4 * (i & 7)));
+  w |= (v & 0xfu) << (4 * (i & 7));
+  a[i >> 3] = w;
+}
+
+// reads_all row 2r = read r as given, row 2r+1 = its reverse complement
+// (reverse_complement_read_ls util.c:541-598; reverse_complement_read_cs util.c:601-618)
+__global__ void revcomp_reads_kernel(const uint32_t *in, uint32_t *out, int stride, int n_reads, const int32_t *read_len,
+                                     const int8_t *initbp, int colour_space) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_reads) return;
+  const uint32_t *src = in + (size_t)r * stride;
+  uint32_t *f = out + (size_t)(2 * r) * stride, *rc = f + stride;
+  for (int w = 0; w < stride; w++) {
+    f[w] = src[w];
+    rc[w] = 0;
+  }
+  const int rl = read_len[r];
+  if (rl <= 0) return;
+  if (!colour_space) {
+    for (int i = 0; i < rl; i++) put4_dev(rc, rl - 1 - i, c_cmpl_r[extract4(src, (uint64_t)i)]);
+  } else {
+    int base = initbp[r];
+    for (int i = 0; i < rl; i++) {
+      const int c = (int)extract4(src, (uint64_t)i);
+      // cstols, util.h:157-180
+      base = (base == 15 || c > 3) ? 15 : ((base % 2 == 0) ? (4 + base + c) % 4 : (4 + base - c) % 4);
+      if (i >= 1) put4_dev(rc, rl - i, (uint32_t)c);
+    }
+    const int ci = c_cmpl_r[initbp[r] & 15];
+    put4_dev(rc, 0, (base > 3 || ci > 3) ? 15u : (uint32_t)(base ^ ci));  // lstocs
+  }
+}
+
+struct SelInfo {
+  int32_t hit_slot, read_idx, st, cn, gen_st, w_len;
+  uint32_t g_off;  // oriented (after reverse_hit)
+  int32_t score_vector, score_max, matches;
+};
+
+struct FullBuildParams {
+  GenomeView G;
+  MapParamsDev M;
+  const DevHit *hits;
+  const uint2 *rs_range;
+  const int32_t *read_len;
+  const int32_t *sel;
+  const int32_t *n_sel;
+  const int32_t *vtrue0;
+  int n_reads;
+  FullTask *tasks;   // [n_reads * num_tmp_outputs]
+  SelInfo *info;
+};
+
+// one thread per (read, selected slot): hit_run_full_sw's orientation logic (mapping.c:353-361,
+// reverse_hit :254-263, anchor_reverse anchors.h:30-34)
+__global__ void build_full_tasks_kernel(const FullBuildParams P) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int NT = P.M.num_tmp_outputs;
+  if (idx >= P.n_reads * NT) return;
+  const int r = idx / NT, k = idx % NT;
+  FullTask T;
+  memset(&T, 0, sizeof(T));
+  SelInfo I;
+  memset(&I, 0, sizeof(I));
+  I.hit_slot = -1;
+  if (k < P.n_sel[r]) {
+    const int hi = P.sel[idx];
+    const DevHit h = P.hits[hi];
+    const uint2 r0 = P.rs_range[2 * r];
+    const int st = ((uint32_t)hi >= r0.x && (uint32_t)hi < r0.x + r0.y) ? 0 : 1;
+    const int rl = P.read_len[r];
+    const uint32_t coff = P.G.contig_off[h.cn], clen = P.G.contig_len[h.cn];
+    uint32_t g_off = h.g_off;
+    int ax = h.ax, ay = h.ay;
+    int gen_st = 0;
+    if (st != 0) {  // reverse_hit: the read is always aligned in its input orientation
+      g_off = clen - h.g_off - (uint32_t)h.w_len;
+      ax = -h.ax + (h.w_len - 1) - (h.alen - 1) - (h.awidth - 1);
+      ay = -h.ay + (rl - 1) - (h.alen - 1) + (h.awidth - 1);
+      gen_st = 1;
+    }
+    T.goff_global = coff + g_off;
+    T.goff_contig = g_off;
+    T.glen = h.w_len;
+    T.rlen = rl;
+    T.ridx = 2 * r;
+    T.ax = ax;
+    T.ay = ay;
+    T.alen = h.alen;
+    T.awidth = h.awidth;
+    T.thresh = (int)abs_or_pct_d(P.M.full_thr, P.M.full_frac, (double)h.score_max);
+    T.gen_st = gen_st;
+    if (!P.M.colour_space) {
+      T.maxscore = P.vtrue0[hi];  // sw_vector re-run of mapping.c:386 (same score on the flipped window)
+      T.run = T.maxscore >= T.thresh;
+    } else {
+      T.maxscore = h.score_vector;
+      T.run = 1;
+    }
+    I.hit_slot = hi;
+    I.read_idx = r;
+    I.st = st;
+    I.cn = h.cn;
+    I.gen_st = gen_st;
+    I.w_len = h.w_len;
+    I.g_off = g_off;
+    I.score_vector = P.M.colour_space ? h.score_vector : T.maxscore;
+    I.score_max = h.score_max;
+    I.matches = h.matches;
+  }
+  P.tasks[idx] = T;
+  P.info[idx] = I;
+}
+
+struct Pipeline {
+  DevBuf d_in, d_reads, d_read_len, d_initbp, d_hits, d_rs_range, d_counters, d_overflow, d_scratch;
+  DevBuf d_task[2], d_vtrue[2], d_slot, d_writer, d_sel, d_nsel;
+  DevBuf d_ftasks, d_finfo, d_fresults, d_frow, d_fbp, d_fops;
+  HostBuf h_info, h_results, h_ops, h_nsel, h_hits, h_range;
+  uint32_t hits_cap = 0;
+};
+
+void free_pipeline(shrimp_gpu_ctx *ctx) {
+  Pipeline *p = (Pipeline *)ctx->pipeline;
+  if (!p) return;
+  DevBuf *bufs[] = {&p->d_in, &p->d_reads, &p->d_read_len, &p->d_initbp, &p->d_hits, &p->d_rs_range, &p->d_counters,
+                    &p->d_overflow, &p->d_scratch, &p->d_task[0], &p->d_task[1], &p->d_vtrue[0], &p->d_vtrue[1],
+                    &p->d_slot, &p->d_writer, &p->d_sel, &p->d_nsel, &p->d_ftasks, &p->d_finfo, &p->d_fresults,
+                    &p->d_frow, &p->d_fbp, &p->d_fops};
+  for (DevBuf *b : bufs) b->release();
+  HostBuf *hb[] = {&p->h_info, &p->h_results, &p->h_ops, &p->h_nsel, &p->h_hits, &p->h_range};
+  for (HostBuf *b : hb) b->release();
+  delete p;
+  ctx->pipeline = nullptr;
+}
+
+// ---- host stage ---------------------------------------------------------------------------------
+struct HostHit {
+  SelInfo info;
+  FullResult res;
+  int score_full;
+  double pct_score_full;
+  int pass2_key;
+  double posterior;
+  int task_idx;
+};
+
+static int cmp_gen_start(const void *e1, const void *e2) {  // mapping.c:1485-1494
+  const HostHit *a = *(HostHit *const *)e1, *b = *(HostHit *const *)e2;
+  if (a->info.cn != b->info.cn) return a->info.cn - b->info.cn;
+  if (a->info.gen_st != b->info.gen_st) return a->info.gen_st - b->info.gen_st;
+  return a->res.genome_start - b->res.genome_start;
+}
+static int cmp_gen_end(const void *e1, const void *e2) {  // mapping.c:1496-1506
+  const HostHit *a = *(HostHit *const *)e1, *b = *(HostHit *const *)e2;
+  if (a->info.cn != b->info.cn) return a->info.cn - b->info.cn;
+  if (a->info.gen_st != b->info.gen_st) return a->info.gen_st - b->info.gen_st;
+  return (-a->res.genome_start - a->res.rmapped + a->res.deletions - a->res.insertions) -
+         (-b->res.genome_start - b->res.rmapped + b->res.deletions - b->res.insertions);
+}
+static int cmp_score(const void *e1, const void *e2) {  // mapping.c:1479-1482
+  return (*(HostHit *const *)e2)->pass2_key - (*(HostHit *const *)e1)->pass2_key;
+}
+static void dedup_pass(HostHit **h, int *n, int (*cmp)(const void *, const void *)) {  // mapping.c:1552-1575
+  qsort(h, *n, sizeof(h[0]), cmp);
+  int i = 0, k = 0;
+  while (i < *n) {
+    int max = h[i]->pass2_key, max_idx = i, j = i + 1;
+    while (j < *n && !cmp(&h[i], &h[j])) {
+      if (h[j]->pass2_key > max) {
+        max = h[j]->pass2_key;
+        max_idx = j;
+      }
+      j++;
+    }
+    if (max_idx != k) h[k] = h[max_idx];
+    k++;
+    i = j;
+  }
+  *n = k;
+}
+
+}  // namespace shrimp
+
+using namespace shrimp;
+
+extern "C" int shrimp_gpu_map_reads(shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, int n_reads,
+                                    const uint32_t *reads, int stride, const int32_t *read_len, const int8_t *initbp,
+                                    shrimp_hit *hits_out, int64_t hits_cap, int32_t *n_hits_per_read, uint8_t *edits,
+                                    int64_t edits_cap, int64_t *n_hits, int64_t *edits_used, shrimp_stage_hit *stage,
+                                    int64_t stage_cap, int64_t *n_stage, shrimp_map_stats *stats) {
+  if (!ctx || !mp || !reads || !read_len || n_reads < 0 || stride <= 0 || !hits_out || !n_hits) {
+    set_error("shrimp_gpu_map_reads: invalid argument");
+    return SHRIMP_E_ARG;
+  }
+  DeviceGenome *g = genome_of(ctx);
+  if (!g || !g->have_index) {
+    set_error("shrimp_gpu_map_reads: genome/index not resident (shrimp_gpu_genome_load + shrimp_gpu_index_build)");
+    return SHRIMP_E_STATE;
+  }
+  if (!ctx->sw.valid) {
+    set_error("shrimp_gpu_map_reads: shrimp_gpu_sw_setup() has not been called");
+    return SHRIMP_E_STATE;
+  }
+  const bool cs = g->colour_space != 0;
+  if (cs != (ctx->sw.use_colours != 0)) {
+    set_error("shrimp_gpu_map_reads: genome and scoring set-up disagree about colour space");
+    return SHRIMP_E_STATE;
+  }
+  if (cs && !initbp) {
+    set_error("shrimp_gpu_map_reads: colour-space reads need initbp");
+    return SHRIMP_E_ARG;
+  }
+  if (mp->gapless) {
+    set_error("shrimp_gpu_map_reads: gapless (-U / mirna) pass 1 is not wired into the chunk pipeline yet");
+    return SHRIMP_E_ARG;
+  }
+  if (cs) {
+    set_error("shrimp_gpu_map_reads: colour-space pass 2 (sw_full_cs) is not on the device yet");
+    return SHRIMP_E_ARG;
+  }
+  if (mp->match_mode != 1 && mp->match_mode != 2) {
+    set_error("shrimp_gpu_map_reads: unpaired match_mode must be 1 or 2");
+    return SHRIMP_E_ARG;
+  }
+  *n_hits = 0;
+  if (edits_used) *edits_used = 0;
+  if (n_stage) *n_stage = 0;
+  if (stats) memset(stats, 0, sizeof(*stats));
+  if (n_hits_per_read) memset(n_hits_per_read, 0, sizeof(int32_t) * (size_t)n_reads);
+  if (n_reads == 0) return SHRIMP_OK;
+  if (hits_cap < (int64_t)n_reads * mp->num_outputs) {
+    set_error("shrimp_gpu_map_reads: hits_cap must be at least n_reads * num_outputs");
+    return SHRIMP_E_ARG;
+  }
+  int max_rl = 0;
+  long long sum_rl = 0;
+  for (int r = 0; r < n_reads; r++) {
+    if (read_len[r] < 0 || read_len[r] > stride * 8) {
+      set_error("shrimp_gpu_map_reads: read %d has length %d (stride holds %d)", r, read_len[r], stride * 8);
+      return SHRIMP_E_ARG;
+    }
+    if (read_len[r] > max_rl) max_rl = read_len[r];
+    sum_rl += read_len[r];
+  }
+  if (max_rl > ctx->sw.max_read_len) {
+    set_error("shrimp_gpu_map_reads: read length %d exceeds the qrlen given at setup (%d)", max_rl,
+              ctx->sw.max_read_len);
+    return SHRIMP_E_ARG;
+  }
+  SH_CUDA(cudaSetDevice(ctx->device));
+  if (!ctx->pipeline) ctx->pipeline = new Pipeline();
+  Pipeline *pl = (Pipeline *)ctx->pipeline;
+  cudaStream_t st = ctx->stream;
+  const SwScores &sw = ctx->sw;
+
+  MapParamsDev M;
+  memset(&M, 0, sizeof(M));
+  M.colour_space = cs;
+  M.match_mode = mp->match_mode;
+  M.gapless = mp->gapless;
+  M.hash_filter_calls = mp->hash_filter_calls;
+  M.use_region_counts = (mp->match_mode == 2 && mp->use_regions) ? 1 : 0;  // gmapper.c:2610-2615
+  M.region_bits = mp->region_bits;
+  M.region_overlap = mp->region_overlap;
+  M.list_cutoff = mp->list_cutoff;
+  M.num_tmp_outputs = mp->num_tmp_outputs;
+  M.min_matches = mp->match_mode;  // gmapper.c:2624
+  M.match = sw.match;
+  M.b_gap_open = -sw.b_open;
+  M.b_gap_ext = -sw.b_ext;
+  M.window_len = mp->window_len;
+  M.window_len_frac = mp->window_len / 100.0;
+  M.wgen_thr = mp->window_gen_threshold;
+  M.wgen_frac = mp->window_gen_threshold / 100.0;
+  M.vect_thr = mp->sw_vect_threshold;
+  M.vect_frac = mp->sw_vect_threshold / 100.0;
+  M.full_thr = mp->sw_full_threshold;
+  M.full_frac = mp->sw_full_threshold / 100.0;
+  M.overlap_thr = mp->window_overlap;
+  M.overlap_frac = mp->window_overlap / 100.0;
+  M.Gflag = mp->Gflag;
+  M.Tflag = mp->Tflag;
+  M.anchor_width = sw.anchor_width;
+  const int max_wl = (int)(unsigned short)abs_or_pct_d(M.window_len, M.window_len_frac, (double)max_rl);
+  if (max_wl > sw.max_window_len) {
+    set_error("shrimp_gpu_map_reads: window length %d exceeds the dblen given at setup (%d)", max_wl,
+              sw.max_window_len);
+    return SHRIMP_E_ARG;
+  }
+
+  GenomeView G;
+  G.ls = g->d_ls.as<uint32_t>();
+  G.ls_rc = g->d_ls_rc.as<uint32_t>();
+  G.cs = g->d_cs.as<uint32_t>();
+  G.cs_rc = g->d_cs_rc.as<uint32_t>();
+  G.contig_off = g->d_off.as<uint32_t>();
+  G.contig_len = g->d_len.as<uint32_t>();
+  G.num_contigs = g->num_contigs;
+  IndexView IV;
+  memset(&IV, 0, sizeof(IV));
+  for (int sn = 0; sn < g->seeds.n_seeds; sn++) {
+    IV.offs[sn] = g->d_offs[sn].as<uint32_t>();
+    IV.pos[sn] = g->d_pos[sn].as<uint32_t>();
+  }
+
+  // ---- upload + reverse complements ------------------------------------------------------------
+  const size_t in_bytes = (size_t)n_reads * stride * 4;
+  SH_TRY(pl->d_in.ensure(in_bytes));
+  SH_TRY(pl->d_reads.ensure(in_bytes * 2));
+  SH_TRY(pl->d_read_len.ensure((size_t)n_reads * 4));
+  SH_CUDA(cudaMemcpyAsync(pl->d_in.p, reads, in_bytes, cudaMemcpyHostToDevice, st));
+  SH_CUDA(cudaMemcpyAsync(pl->d_read_len.p, read_len, (size_t)n_reads * 4, cudaMemcpyHostToDevice, st));
+  if (cs) {
+    SH_TRY(pl->d_initbp.ensure((size_t)n_reads));
+    SH_CUDA(cudaMemcpyAsync(pl->d_initbp.p, initbp, (size_t)n_reads, cudaMemcpyHostToDevice, st));
+  }
+  SH_TRY(pl->d_counters.ensure(64 * 4));
+  SH_TRY(pl->d_rs_range.ensure((size_t)n_reads * 2 * sizeof(uint2)));
+  uint32_t *cnt = pl->d_counters.as<uint32_t>();  // [0] hits_used [1] n_overflow [2] status [8..15] stats [16,17] full cells
+  uint32_t hits_used = 0;
+  {
+    ScopedStage ss(ctx, ST_SCAN);
+    revcomp_reads_kernel<<<(n_reads + 127) / 128, 128, 0, st>>>(pl->d_in.as<uint32_t>(), pl->d_reads.as<uint32_t>(),
+                                                                stride, n_reads, pl->d_read_len.as<int32_t>(),
+                                                                cs ? pl->d_initbp.as<int8_t>() : nullptr, cs);
+    SH_CUDA(cudaGetLastError());
+    SH_LAUNCHED(ctx, ST_SCAN);
+
+    // ---- seed scan -----------------------------------------------------------------------------
+    // slab size from the expected number of list entries per read strand: K(r) * L / 4^W
+    double est = 0;
+    const double avg_rl = (double)sum_rl / n_reads;
+    for (int sn = 0; sn < g->seeds.n_seeds; sn++)
+      est += std::max(0.0, avg_rl - g->seeds.span[sn] + 1) * ((double)g->total[sn] / (double)g->nbuckets[sn]);
+    int cap = 128;
+    while (cap < 2048 && cap < est * 3 + 64) cap <<= 1;
+    const int big_cap = 8192;
+    int k_max = g->seeds.n_seeds * std::max(1, max_rl);
+    if (pl->hits_cap == 0) pl->hits_cap = (uint32_t)std::max<long long>(1 << 20, (long long)n_reads * 2 * 16);
+    for (int attempt = 0;; attempt++) {
+      SH_TRY(pl->d_hits.ensure((size_t)pl->hits_cap * sizeof(DevHit)));
+      SH_TRY(pl->d_overflow.ensure((size_t)n_reads * 2 * 4));
+      SH_CUDA(cudaMemsetAsync(cnt, 0, 64 * 4, st));
+      ScanParams P;
+      memset(&P, 0, sizeof(P));
+      P.G = G;
+      P.I = IV;
+      P.S = g->seeds;
+      P.M = M;
+      P.reads = pl->d_reads.as<uint32_t>();
+      P.stride = stride;
+      P.n_reads = n_reads;
+      P.read_len = pl->d_read_len.as<int32_t>();
+      P.hits = pl->d_hits.as<DevHit>();
+      P.hits_cap = pl->hits_cap;
+      P.hits_used = cnt + 0;
+      P.rs_range = pl->d_rs_range.as<uint2>();
+      P.overflow = pl->d_overflow.as<uint32_t>();
+      P.n_overflow = cnt + 1;
+      P.status = cnt + 2;
+      P.stats = cnt + 8;
+      P.k_max = k_max;
+      P.max_rl = max_rl;
+      // small-slab pass over all read strands
+      P.cap = cap;
+      int warps = SCAN_WARPS_HOST;
+      while (warps > 1 && scan_smem_bytes(cap, max_rl, warps) > 100 * 1024) warps >>= 1;
+      const size_t smem = scan_smem_bytes(cap, max_rl, warps);
+      int ctas_per_sm = (int)std::max<size_t>(1, (size_t)(220 * 1024) / std::max<size_t>(smem, 1));
+      ctas_per_sm = std::min(ctas_per_sm, 2048 / (SCAN_WARPS_HOST * 32));
+      int n_ctas = ctx->sm_count * ctas_per_sm;
+      n_ctas = std::min<long long>(n_ctas, ((long long)n_reads * 2 + warps - 1) / warps);
+      P.scratch_ints = 2 * k_max + 2 * cap;
+      SH_TRY(pl->d_scratch.ensure(std::max((size_t)n_ctas * warps * P.scratch_ints,
+                                           (size_t)ctx->sm_count * (2 * k_max + 2 * big_cap)) * 4));
+      P.scratch = pl->d_scratch.as<int32_t>();
+      SH_TRY(launch_scan(ctx, P, warps, n_ctas));
+      uint32_t h3[3];
+      SH_CUDA(cudaMemcpyAsync(h3, cnt, 12, cudaMemcpyDeviceToHost, st));
+      SH_CUDA(cudaStreamSynchronize(st));
+      if (h3[1] > 0 && !(h3[2] & 1u)) {
+        // overflow pass: one warp per CTA with the big slab
+        P.work = pl->d_overflow.as<uint32_t>();
+        P.n_work = h3[1];
+        P.overflow = nullptr;
+        P.cap = big_cap;
+        P.scratch_ints = 2 * k_max + 2 * big_cap;
+        int ctas = std::min<int>(ctx->sm_count, (int)h3[1]);
+        SH_TRY(launch_scan(ctx, P, 1, ctas));
+        SH_CUDA(cudaMemcpyAsync(h3, cnt, 12, cudaMemcpyDeviceToHost, st));
+        SH_CUDA(cudaStreamSynchronize(st));
+      }
+      if (h3[2] & 2u) {
+        set_error("shrimp_gpu_map_reads: a read strand gathered more than %d index positions; the global-memory "
+                  "scan path for such reads is not implemented yet", big_cap);
+        return SHRIMP_E_RANGE;
+      }
+      if (h3[2] & 1u) {  // hit buffer too small: grow and redo the scan
+        if (attempt > 8) {
+          set_error("shrimp_gpu_map_reads: hit buffer overflow");
+          return SHRIMP_E_NOMEM;
+        }
+        pl->hits_cap *= 4;
+        continue;
+      }
+      hits_used = h3[0];
+      break;
+    }
+  }
+
+  // ---- sw_vector over every eligible window ----------------------------------------------------
+  const size_t HU = std::max<uint32_t>(hits_used, 1);
+  const size_t task_bytes = HU * 4 * 4 + ((HU + 3) & ~(size_t)3);
+  const int n_ori = cs ? 2 : 1;
+  VecTaskArrays VT[2];
+  for (int o = 0; o < n_ori; o++) {
+    SH_TRY(pl->d_task[o].ensure(task_bytes));
+    SH_TRY(pl->d_vtrue[o].ensure(HU * 4));
+    SH_CUDA(cudaMemsetAsync(pl->d_vtrue[o].p, 0xff, HU * 4, st));
+  }
+  SH_TRY(pl->d_slot.ensure(HU * 4));
+  SH_TRY(pl->d_writer.ensure(HU));
+  {
+    ScopedStage ss(ctx, ST_PASS1);
+    TaskBuildParams TB;
+    memset(&TB, 0, sizeof(TB));
+    TB.G = G;
+    TB.M = M;
+    TB.hits = pl->d_hits.as<DevHit>();
+    TB.rs_range = pl->d_rs_range.as<uint2>();
+    TB.read_len = pl->d_read_len.as<int32_t>();
+    TB.n_reads = n_reads;
+    for (int o = 0; o < 2; o++) {
+      char *tb = (char *)pl->d_task[o < n_ori ? o : 0].p;
+      TB.goff[o] = (uint32_t *)tb;
+      TB.glen[o] = (int32_t *)(tb + HU * 4);
+      TB.ridx[o] = (int32_t *)(tb + HU * 8);
+      TB.rlen[o] = (int32_t *)(tb + HU * 12);
+      TB.initbp_out[o] = (int8_t *)(tb + HU * 16);
+      VT[o].goff = TB.goff[o];
+      VT[o].glen = TB.glen[o];
+      VT[o].ridx = TB.ridx[o];
+      VT[o].rlen = TB.rlen[o];
+      VT[o].initbp = cs ? TB.initbp_out[o] : nullptr;
+    }
+    TB.initbp = cs ? pl->d_initbp.as<int8_t>() : nullptr;
+    TB.slot = M.hash_filter_calls ? pl->d_slot.as<uint32_t>() : nullptr;
+    SH_TRY(launch_build_vec_tasks(ctx, TB));
+  }
+  if (hits_used > 0) {
+    ScopedStage ss(ctx, ST_VECTOR);
+    for (int o = 0; o < n_ori; o++) {
+      const uint32_t *gen = cs ? (o ? G.cs_rc : G.cs) : G.ls;
+      const uint32_t *gen_ls = cs ? (o ? G.ls_rc : G.ls) : nullptr;
+      SH_TRY(launch_sw_vector(ctx, gen, gen_ls, pl->d_reads.as<uint32_t>(), stride, (int)hits_used, max_rl, max_wl,
+                              VT[o], pl->d_vtrue[o].as<int32_t>(), ST_VECTOR));
+    }
+  }
+
+  // ---- pass-1 replay + top-k -------------------------------------------------------------------
+  const int NT = mp->num_tmp_outputs;
+  SH_TRY(pl->d_sel.ensure((size_t)n_reads * NT * 4));
+  SH_TRY(pl->d_nsel.ensure((size_t)n_reads * 4));
+  {
+    ScopedStage ss(ctx, ST_PASS1);
+    Pass1Params PP;
+    memset(&PP, 0, sizeof(PP));
+    PP.M = M;
+    PP.hits = pl->d_hits.as<DevHit>();
+    PP.rs_range = pl->d_rs_range.as<uint2>();
+    PP.read_len = pl->d_read_len.as<int32_t>();
+    PP.n_reads = n_reads;
+    PP.vtrue[0] = pl->d_vtrue[0].as<int32_t>();
+    PP.vtrue[1] = pl->d_vtrue[n_ori - 1].as<int32_t>();
+    PP.slot = pl->d_slot.as<uint32_t>();
+    PP.writer = pl->d_writer.as<uint8_t>();
+    PP.sel = pl->d_sel.as<int32_t>();
+    PP.n_sel = pl->d_nsel.as<int32_t>();
+    PP.stats = cnt + 8;
+    SH_TRY(launch_pass1_select(ctx, PP));
+  }
+
+  // ---- stage dump (tests) ---------------------------------------------------------------------
+  if (stage) {
+    SH_TRY(pl->h_hits.ensure(HU * sizeof(DevHit)));
+    SH_TRY(pl->h_range.ensure((size_t)n_reads * 2 * sizeof(uint2)));
+    SH_CUDA(cudaMemcpyAsync(pl->h_hits.p, pl->d_hits.p, (size_t)hits_used * sizeof(DevHit), cudaMemcpyDeviceToHost, st));
+    SH_CUDA(cudaMemcpyAsync(pl->h_range.p, pl->d_rs_range.p, (size_t)n_reads * 2 * sizeof(uint2),
+                            cudaMemcpyDeviceToHost, st));
+    SH_CUDA(cudaStreamSynchronize(st));
+    const DevHit *H = pl->h_hits.as<DevHit>();
+    const uint2 *RG = pl->h_range.as<uint2>();
+    int64_t ns = 0;
+    for (int rs = 0; rs < 2 * n_reads; rs++) {
+      for (uint32_t k = 0; k < RG[rs].y; k++) {
+        if (ns >= stage_cap) {
+          set_error("shrimp_gpu_map_reads: stage_cap too small");
+          return SHRIMP_E_NOMEM;
+        }
+        const DevHit &h = H[RG[rs].x + k];
+        shrimp_stage_hit &s = stage[ns++];
+        s.read_idx = rs >> 1;
+        s.st = rs & 1;
+        s.cn = h.cn;
+        s.w_len = h.w_len;
+        s.g_off = h.g_off;
+        s.score_window_gen = h.wg;
+        s.matches = h.matches;
+        s.score_max = h.score_max;
+        s.score_vector = h.score_vector;
+        s.pct_score_vector = h.pct_vector;
+        s.ax = h.ax;
+        s.ay = h.ay;
+        s.alen = h.alen;
+        s.awidth = h.awidth;
+      }
+    }
+    if (n_stage) *n_stage = ns;
+  }
+
+  // ---- full SW on the selected hits ------------------------------------------------------------
+  const int n_slots = n_reads * NT;
+  SH_TRY(pl->d_ftasks.ensure((size_t)n_slots * sizeof(FullTask)));
+  SH_TRY(pl->d_finfo.ensure((size_t)n_slots * sizeof(SelInfo)));
+  SH_TRY(pl->d_fresults.ensure((size_t)n_slots * sizeof(FullResult)));
+  const size_t ops_stride = (size_t)max_rl + max_wl;
+  {
+    ScopedStage ss(ctx, ST_FULL);
+    FullBuildParams FB;
+    memset(&FB, 0, sizeof(FB));
+    FB.G = G;
+    FB.M = M;
+    FB.hits = pl->d_hits.as<DevHit>();
+    FB.rs_range = pl->d_rs_range.as<uint2>();
+    FB.read_len = pl->d_read_len.as<int32_t>();
+    FB.sel = pl->d_sel.as<int32_t>();
+    FB.n_sel = pl->d_nsel.as<int32_t>();
+    FB.vtrue0 = pl->d_vtrue[0].as<int32_t>();
+    FB.n_reads = n_reads;
+    FB.tasks = pl->d_ftasks.as<FullTask>();
+    FB.info = pl->d_finfo.as<SelInfo>();
+    build_full_tasks_kernel<<<(n_slots + 127) / 128, 128, 0, st>>>(FB);
+    SH_CUDA(cudaGetLastError());
+    SH_LAUNCHED(ctx, ST_FULL);
+
+    // sub-batches sized for ~2 GB of DP scratch
+    const size_t per_task = (size_t)3 * (max_wl + 1) * 4 + (size_t)max_rl * max_wl + ops_stride;
+    int batch = (int)std::min<size_t>((size_t)n_slots, std::max<size_t>(1024, ((size_t)2 << 30) / per_task));
+    batch = (batch + 127) & ~127;
+    SH_TRY(pl->d_frow.ensure((size_t)3 * (max_wl + 1) * 4 * batch));
+    SH_TRY(pl->d_fbp.ensure((size_t)max_rl * max_wl * batch));
+    SH_TRY(pl->d_fops.ensure(ops_stride * (size_t)n_slots));
+    for (int b0 = 0; b0 < n_slots; b0 += batch) {
+      FullParams FP;
+      memset(&FP, 0, sizeof(FP));
+      FP.genome_fwd = G.ls;
+      FP.genome_rc = G.ls_rc;
+      FP.reads = pl->d_reads.as<uint32_t>();
+      FP.stride = stride;
+      FP.tasks = pl->d_ftasks.as<FullTask>() + b0;
+      FP.results = pl->d_fresults.as<FullResult>() + b0;
+      FP.n_tasks = std::min(batch, n_slots - b0);
+      FP.NT = batch;
+      FP.row = pl->d_frow.as<int32_t>();
+      FP.bp = pl->d_fbp.as<uint8_t>();
+      FP.ops = pl->d_fops.as<uint8_t>() + ops_stride * (size_t)b0;
+      FP.max_glen = max_wl;
+      FP.max_rlen = max_rl;
+      FP.match = sw.match;
+      FP.mismatch = sw.mismatch;
+      FP.a_open = sw.a_open;
+      FP.a_ext = sw.a_ext;
+      FP.b_open = sw.b_open;
+      FP.b_ext = sw.b_ext;
+      FP.anchor_width = sw.anchor_width;
+      FP.Tflag = mp->Tflag;
+      FP.local = mp->Gflag ? 0 : 1;
+      FP.cells = (unsigned long long *)(cnt + 16);
+      SH_TRY(launch_sw_full_ls(ctx, FP));
+    }
+  }
+
+  // ---- results back to the host ------------------------------------------------------------------
+  SH_TRY(pl->h_info.ensure((size_t)n_slots * sizeof(SelInfo)));
+  SH_TRY(pl->h_results.ensure((size_t)n_slots * sizeof(FullResult)));
+  SH_TRY(pl->h_ops.ensure(ops_stride * (size_t)n_slots));
+  SH_TRY(pl->h_nsel.ensure((size_t)n_reads * 4 + 64 * 4));
+  SH_CUDA(cudaMemcpyAsync(pl->h_info.p, pl->d_finfo.p, (size_t)n_slots * sizeof(SelInfo), cudaMemcpyDeviceToHost, st));
+  SH_CUDA(cudaMemcpyAsync(pl->h_results.p, pl->d_fresults.p, (size_t)n_slots * sizeof(FullResult),
+                          cudaMemcpyDeviceToHost, st));
+  SH_CUDA(cudaMemcpyAsync(pl->h_ops.p, pl->d_fops.p, ops_stride * (size_t)n_slots, cudaMemcpyDeviceToHost, st));
+  SH_CUDA(cudaMemcpyAsync(pl->h_nsel.p, pl->d_nsel.p, (size_t)n_reads * 4, cudaMemcpyDeviceToHost, st));
+  uint32_t *h_cnt = (uint32_t *)((char *)pl->h_nsel.p + (size_t)n_reads * 4);
+  SH_CUDA(cudaMemcpyAsync(h_cnt, cnt, 64 * 4, cudaMemcpyDeviceToHost, st));
+  SH_CUDA(cudaStreamSynchronize(st));
+
+  // ---- host stage: read_pass2 after the DP (mapping.c:1644-1722) -------------------------------
+  const SelInfo *INFO = pl->h_info.as<SelInfo>();
+  const FullResult *RES = pl->h_results.as<FullResult>();
+  const int32_t *NSEL = pl->h_nsel.as<int32_t>();
+  const uint8_t *OPS = pl->h_ops.as<uint8_t>();
+  std::vector<HostHit> hh((size_t)NT);
+  std::vector<HostHit *> h2((size_t)NT + 1);
+  int64_t n_out = 0, e_used = 0;
+  uint64_t full_calls = 0, pass2_vector_calls = 0, pass2_vector_cells = 0;
+  bool edits_short = false;
+  for (int r = 0; r < n_reads; r++) {
+    const int n1 = NSEL[r];
+    int n2 = 0;
+    for (int k = 0; k < n1; k++) {
+      const int idx = r * NT + k;
+      HostHit &h = hh[k];
+      h.info = INFO[idx];
+      h.res = RES[idx];
+      h.task_idx = idx;
+      h.posterior = 0.0;
+      if (!cs) {
+        pass2_vector_calls++;
+        pass2_vector_cells += (uint64_t)h.info.w_len * (uint64_t)read_len[r];
+      }
+      h.score_full = h.res.score;
+      if (h.res.score > 0 || h.res.ops_len > 0) full_calls++;
+      h.pct_score_full = (1000 * 100 * h.score_full) / h.info.score_max;
+      if (mp->compute_mapping_qualities && h.score_full > 0 && !cs) {  // hit_run_post_sw :1609-1625
+        h.posterior = pow(2.0, ((double)h.res.score - (double)h.res.rmapped * (2.0 * mp->score_alpha + mp->score_beta)) /
+                                   mp->score_alpha);
+        int ps = (int)rint(mp->score_alpha * log(h.posterior) / log(2.0) +
+                           (double)h.res.rmapped * (2.0 * mp->score_alpha + mp->score_beta));
+        if (ps < 0) ps = 0;
+        const int pct = (1000 * 100 * ps) / h.info.score_max;
+        h.score_full = ps;
+        h.pct_score_full = pct;
+      }
+      h.pass2_key = mp->sw_full_threshold < 0 ? h.score_full : (int)h.pct_score_full;
+      const double thr = mp->sw_full_threshold < 0 ? -mp->sw_full_threshold
+                                                   : h.info.score_max * (mp->sw_full_threshold / 100.0);
+      if (h.score_full >= thr) h2[n2++] = &h;
+    }
+    dedup_pass(h2.data(), &n2, cmp_gen_start);
+    dedup_pass(h2.data(), &n2, cmp_gen_end);
+    qsort(h2.data(), n2, sizeof(HostHit *), cmp_score);
+    if (n2 > mp->num_outputs) n2 = mp->num_outputs;
+    if (mp->strata && n2 > 0) {
+      int i;
+      for (i = 1; i < n2 && h2[0]->score_full == h2[i]->score_full; i++)
+        ;
+      n2 = i;
+    }
+    if (n2 > 0 && !(mp->max_alignments == 0 || n2 <= mp->max_alignments)) n2 = 0;
+    for (int i = 0; i < n2; i++) {
+      const HostHit &h = *h2[i];
+      shrimp_hit &o = hits_out[n_out++];
+      o.read_idx = r;
+      o.cn = h.info.cn;
+      o.gen_st = h.info.gen_st;
+      o.w_len = h.info.w_len;
+      o.g_off = h.info.g_off;
+      o.score_vector = h.info.score_vector;
+      o.score_full = h.score_full;
+      o.pass2_key = h.pass2_key;
+      o.score_max = h.info.score_max;
+      o.matches = h.info.matches;
+      o.sw_score = h.res.score;
+      o.posterior = h.posterior;
+      o.read_start = h.res.read_start;
+      o.rmapped = h.res.rmapped;
+      o.genome_start = h.res.genome_start;
+      o.gmapped = h.res.gmapped;
+      o.sfr_matches = h.res.matches;
+      o.mismatches = h.res.mismatches;
+      o.insertions = h.res.insertions;
+      o.deletions = h.res.deletions;
+      o.crossovers = h.res.crossovers;
+      o.edit_len = h.res.ops_len;
+      o.edit_off = e_used;
+      if (edits && e_used + h.res.ops_len <= edits_cap)
+        memcpy(edits + e_used, OPS + ops_stride * (size_t)h.task_idx + h.res.ops_start, (size_t)h.res.ops_len);
+      else if (h.res.ops_len > 0)
+        edits_short = true;
+      e_used += h.res.ops_len;
+    }
+    if (n_hits_per_read) n_hits_per_read[r] = n2;
+  }
+  *n_hits = n_out;
+  if (edits_used) *edits_used = e_used;
+  if (stats) {
+    stats->heap_replays = h_cnt[8 + 0];
+    stats->list_entries = h_cnt[8 + 1];
+    stats->surviving_entries = h_cnt[8 + 2];
+    stats->anchors = h_cnt[8 + 3];
+    stats->hits = hits_used;
+    stats->vector_tasks = hits_used;
+    stats->vector_calls = (uint64_t)h_cnt[8 + 4] + pass2_vector_calls;
+    stats->vector_bypassed = h_cnt[8 + 5];
+    stats->vector_cells = *(unsigned long long *)(h_cnt + 8 + 6) + pass2_vector_cells;
+    stats->full_calls = full_calls;
+    stats->full_cells = *(unsigned long long *)(h_cnt + 16);
+  }
+  if (edits_short && edits) {
+    set_error("shrimp_gpu_map_reads: edits_cap too small, %lld bytes needed", (long long)e_used);
+    return SHRIMP_E_NOMEM;
+  }
+  return SHRIMP_OK;
+}

@@ -1,0 +1,452 @@
+// Seed scan: spaced-seed projection of the reads, index lookup, region filter, anchor merge and
+// candidate-window (hit) generation -- one warp per read strand, everything between the HBM index
+// and the hit list staged in shared memory.
+//
+// Replaces, per read strand (gmapper/mapping.c):
+//   read_get_mapidxs_per_strand :37-70, read_get_region_counts :459-542,
+//   advance_index_in_genomemap :646-805 (unpaired branch), read_get_anchor_list_per_strand :861-1006,
+//   read_get_hit_list_per_strand :1025-1229.
+//
+// The reference marks 2 kb regions in a 4 MB table while walking every index list, then walks the
+// lists again through a k-way heap merge.  Here each list is read ONCE:
+//   1. lanes project the read's k-mers (vectorised over read positions) and fetch bucket bounds;
+//   2. the bucket lists are gathered from HBM into the warp's shared-memory slab as
+//      (position << 32 | k-mer slot) keys;
+//   3. a warp bitonic sort orders them by genome position -- the order the heap merge produces;
+//   4. "region has >= 2 hits" (RG_HAS_2) becomes a neighbour test on the sorted array: a region's
+//      catchment [r*2^11, (r+1)*2^11 + overlap) is contiguous, so another entry falls in it iff the
+//      previous or next sorted entry does;  survivors are compacted in order;
+//   5. equal positions on different read offsets would be popped in binary-heap order by the
+//      reference (SURVEY hard part 3a).  Such warps (about 0.05 % of reads) replay heap_uu
+//      (common/heap.h:43-113) exactly on the surviving entries, lane 0 only;
+//   6. colinear collapse (:957-971) and the hit list run on the shared-memory anchors.
+// Read strands whose lists exceed the slab go to an overflow list served by a second launch with a
+// larger slab (one warp per CTA).
+#include "stages.cuh"
+
+namespace shrimp {
+
+
+
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+
+__device__ __forceinline__ int contig_of_dev(const uint32_t *off, int n, uint32_t p) {
+  int lo = 0, hi = n;
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (off[mid] <= p) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// anchor_join of two unit-width anchors (anchors.c:9-54); a[] = {x, y, length, width}
+__device__ __forceinline__ void anchor_join2(long long x0, long long y0, int l0, int w0, long long x1, long long y1,
+                                             int l1, int w1, int &ox, int &oy, int &olen, int &owidth) {
+  long long nw0 = x0 + y0, sw0 = x0 - y0, ne0 = sw0 + 2 * (w0 - 1), se0 = nw0 + 2 * (l0 - 1);
+  long long nw1 = x1 + y1, sw1 = x1 - y1, ne1 = sw1 + 2 * (w1 - 1), se1 = nw1 + 2 * (l1 - 1);
+  long long nw_min = nw0 < nw1 ? nw0 : nw1, sw_min = sw0 < sw1 ? sw0 : sw1;
+  long long ne_max = ne0 > ne1 ? ne0 : ne1, se_max = se0 > se1 ? se0 : se1;
+  if ((nw_min + sw_min) % 2 != 0) nw_min--;
+  long long dx = (nw_min + sw_min) / 2;
+  ox = (int)dx;
+  oy = (int)(nw_min - dx);
+  if ((ne_max - sw_min) % 2 != 0) ne_max++;
+  owidth = (int)((ne_max - sw_min) / 2 + 1);
+  if ((se_max - nw_min) % 2 != 0) se_max++;
+  olen = (int)((se_max - nw_min) / 2 + 1);
+}
+
+
+__global__ void __launch_bounds__(SCAN_WARPS * 32) scan_kernel(const ScanParams P, int warps_per_cta) {
+  extern __shared__ unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  if (wib >= warps_per_cta) return;
+  const int cap = P.cap;
+  // per-warp slab: ent[cap] u64 | rec[cap] AnchorRec (16 B) | cache[max_rl] i16 | keep[cap/32] u32
+  const size_t per_warp = (size_t)cap * 8 + (size_t)cap * 16 + (((size_t)P.max_rl * 2 + 15) & ~(size_t)15) +
+                          (size_t)(cap / 32 + 1) * 4;
+  unsigned char *base = smem_raw + (((per_warp + 15) & ~(size_t)15)) * wib;
+  unsigned long long *ent = (unsigned long long *)base;
+  AnchorRec *rec = (AnchorRec *)(base + (size_t)cap * 8);
+  int16_t *cache = (int16_t *)(base + (size_t)cap * 24);
+  uint32_t *keep = (uint32_t *)(base + (size_t)cap * 24 + (((size_t)P.max_rl * 2 + 15) & ~(size_t)15));
+
+  const uint32_t gwarp = blockIdx.x * warps_per_cta + wib;
+  const uint32_t n_warps = gridDim.x * warps_per_cta;
+  int32_t *scr = P.scratch + (size_t)gwarp * P.scratch_ints;
+  const uint32_t n_items = P.work ? P.n_work : 2u * (uint32_t)P.n_reads;
+  const SeedTable &S = P.S;
+  const MapParamsDev &M = P.M;
+  const int mkp = M.colour_space ? 1 : 0;  // min_kmer_pos (gmapper.c:478-480)
+  const uint32_t rmask = (1u << M.region_bits) - 1u;
+
+  for (uint32_t item = gwarp; item < n_items; item += n_warps) {
+    const uint32_t rs = P.work ? P.work[item] : item;
+    const int r = (int)(rs >> 1);
+    const int rl = P.read_len[r];
+    const uint32_t *seq = P.reads + (size_t)rs * P.stride;
+    int max_n_kmers = M.colour_space ? rl - S.min_span : rl - S.min_span + 1;  // gmapper.c:473-479
+    if (max_n_kmers < 0) max_n_kmers = 0;
+    if (lane == 0) P.rs_range[rs] = make_uint2(0u, 0u);
+    if (rl <= 0 || max_n_kmers == 0) continue;
+
+    // ---- 1. count list entries -------------------------------------------------------------
+    int total = 0;
+    for (int sn = 0; sn < S.n_seeds; sn++) {
+      const int nk = rl - S.span[sn] + 1 - mkp;
+      for (int i = lane; i < nk; i += 32) {
+        uint32_t m = kmer_to_mapidx(S, sn, seq, (uint64_t)(mkp + i));
+        uint32_t len = P.I.offs[sn][m + 1] - P.I.offs[sn][m];
+        if (len > M.list_cutoff) len = 0;  // mapping.c:497,:889
+        total += (int)len;
+      }
+    }
+    total = warp_sum(total);
+    if (total == 0) continue;
+    if (total > cap) {
+      if (lane == 0) {
+        if (P.overflow) {
+          uint32_t o = atomicAdd(P.n_overflow, 1u);
+          P.overflow[o] = rs;
+        } else {
+          atomicOr(P.status, 2u);
+        }
+      }
+      continue;
+    }
+
+    // ---- 2. gather (position << 32 | k-mer slot) ---------------------------------------------
+    int basepos = 0;
+    for (int sn = 0; sn < S.n_seeds; sn++) {
+      const int nk = rl - S.span[sn] + 1 - mkp;
+      for (int i0 = 0; i0 < nk; i0 += 32) {
+        const int i = i0 + lane;
+        uint32_t start = 0, len = 0;
+        if (i < nk) {
+          uint32_t m = kmer_to_mapidx(S, sn, seq, (uint64_t)(mkp + i));
+          start = P.I.offs[sn][m];
+          len = P.I.offs[sn][m + 1] - start;
+          if (len > M.list_cutoff) len = 0;
+        }
+        const int incl = warp_incl_scan((int)len, lane);
+        const int excl = incl - (int)len;
+        const unsigned long long slot = (unsigned long long)(sn * max_n_kmers + i);
+        const uint32_t *list = P.I.pos[sn] + start;
+        for (uint32_t j = 0; j < len; j++) ent[basepos + excl + (int)j] = ((unsigned long long)__ldg(list + j) << 32) | slot;
+        basepos += __shfl_sync(0xffffffffu, incl, 31);
+      }
+    }
+    int Pn = 32;
+    while (Pn < total) Pn <<= 1;
+    for (int t = total + lane; t < Pn; t += 32) ent[t] = ~0ull;
+    __syncwarp();
+
+    // ---- 3. bitonic sort by position -----------------------------------------------------------
+    for (int k = 2; k <= Pn; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int t = lane; t < (Pn >> 1); t += 32) {
+          const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+          const int l = i | j;
+          const unsigned long long a = ent[i], b = ent[l];
+          const bool up = (i & k) == 0;
+          if ((a > b) == up) {
+            ent[i] = b;
+            ent[l] = a;
+          }
+        }
+        __syncwarp();
+      }
+    }
+
+    // ---- 4. region filter (RG_HAS_2 as a neighbour test) + ordered compaction -----------------
+    int m_surv = total;
+    if (M.use_region_counts) {
+      for (int t0 = 0; t0 < total; t0 += 32) {
+        const int t = t0 + lane;
+        bool kp = false;
+        if (t < total) {
+          const unsigned long long x = ent[t] >> 32;
+          const unsigned long long xl = t > 0 ? (ent[t - 1] >> 32) : 0ull;
+          const unsigned long long xr = t + 1 < total ? (ent[t + 1] >> 32) : ~0ull;
+          const unsigned long long region = x >> M.region_bits;
+          const unsigned long long lo = region << M.region_bits;
+          const unsigned long long hi = ((region + 1) << M.region_bits) + (unsigned long long)M.region_overlap;
+          kp = (t > 0 && xl >= lo) || (t + 1 < total && xr < hi);
+          if (!kp && region > 0 && ((uint32_t)x & rmask) < (uint32_t)M.region_overlap) {
+            const unsigned long long lo2 = (region - 1) << M.region_bits;
+            const unsigned long long hi2 = lo + (unsigned long long)M.region_overlap;
+            kp = (t > 0 && xl >= lo2) || (t + 1 < total && xr < hi2);
+          }
+        }
+        const uint32_t b = __ballot_sync(0xffffffffu, kp);
+        if (lane == 0) keep[t0 >> 5] = b;
+      }
+      __syncwarp();
+      int outn = 0;
+      for (int t0 = 0; t0 < total; t0 += 32) {
+        const uint32_t b = keep[t0 >> 5];
+        const int t = t0 + lane;
+        const unsigned long long v = t < total ? ent[t] : 0ull;
+        __syncwarp();
+        if ((b >> lane) & 1u) ent[outn + __popc(b & ((1u << lane) - 1u))] = v;
+        outn += __popc(b);
+        __syncwarp();
+      }
+      m_surv = outn;
+    }
+    if (lane == 0) {
+      atomicAdd(&P.stats[1], (uint32_t)total);
+      atomicAdd(&P.stats[2], (uint32_t)m_surv);
+    }
+    if (m_surv == 0) continue;
+
+    // ---- 5. equal position on different read offsets -> replay the reference's heap -----------
+    bool tie = false;
+    for (int t = lane; t + 1 < m_surv; t += 32) {
+      const unsigned long long a = ent[t], b = ent[t + 1];
+      if ((a >> 32) == (b >> 32) && ((uint32_t)a % (uint32_t)max_n_kmers) != ((uint32_t)b % (uint32_t)max_n_kmers))
+        tie = true;
+    }
+    tie = __any_sync(0xffffffffu, tie);
+    int32_t *order = nullptr;
+    if (tie) {
+      const int K = S.n_seeds * max_n_kmers;
+      int32_t *first_of = scr;               // [k_max]
+      int32_t *heap = scr + P.k_max;         // [k_max]
+      int32_t *next_same = heap + P.k_max;   // [cap]
+      order = next_same + cap;               // [cap]
+      for (int k = lane; k < K; k += 32) first_of[k] = -1;
+      __syncwarp();
+      if (lane == 0) {
+        atomicAdd(&P.stats[0], 1u);
+        for (int t = m_surv - 1; t >= 0; t--) {
+          const int off = (int)(uint32_t)ent[t];
+          next_same[t] = first_of[off];
+          first_of[off] = t;
+        }
+        // heap_uu on key = position; elements are survivor indices.  Load order: sn-major, i.e.
+        // ascending slot (mapping.c:913-935).
+        int load = 0;
+        for (int off = 0; off < K; off++) {
+          const int t = first_of[off];
+          if (t < 0) continue;
+          heap[load++] = t;
+          int node = load, parent = node / 2;  // percolate_up, heap.h:43-60
+          while (node > 1 && (ent[heap[node - 1]] >> 32) < (ent[heap[parent - 1]] >> 32)) {
+            int tmp = heap[parent - 1];
+            heap[parent - 1] = heap[node - 1];
+            heap[node - 1] = tmp;
+            node = parent;
+            parent = node / 2;
+          }
+        }
+        int outn = 0;
+        while (load > 0) {
+          const int t = heap[0];
+          order[outn++] = t;
+          const int nx = next_same[t];
+          if (nx >= 0) {
+            heap[0] = nx;  // heap_uu_replace_min
+          } else {
+            load--;  // heap_uu_extract_min
+            if (load > 0) heap[0] = heap[load];
+          }
+          if (load > 0) {  // percolate_down, heap.h:62-89
+            int node = 1;
+            for (;;) {
+              int left = node * 2, right = left + 1, mn = node;
+              if (left <= load && (ent[heap[left - 1]] >> 32) < (ent[heap[node - 1]] >> 32)) mn = left;
+              if (right <= load && (ent[heap[right - 1]] >> 32) < (ent[heap[mn - 1]] >> 32)) mn = right;
+              if (mn == node) break;
+              int tmp = heap[mn - 1];
+              heap[mn - 1] = heap[node - 1];
+              heap[node - 1] = tmp;
+              node = mn;
+            }
+          }
+        }
+      }
+      __syncwarp();
+    }
+
+    // ---- 6. anchors: contig lookup in parallel, colinear collapse in pop order ----------------
+    for (int t = lane; t < m_surv; t += 32) {
+      const unsigned long long e = ent[order ? order[t] : t];
+      const uint32_t slot = (uint32_t)e;
+      const int sn = (int)(slot / (uint32_t)max_n_kmers), i = (int)(slot % (uint32_t)max_n_kmers);
+      AnchorRec a;
+      a.x = (uint32_t)(e >> 32);
+      a.y = (int16_t)(mkp + i);
+      a.len = (int16_t)S.span[sn];
+      a.weight = 1;
+      a.cn = contig_of_dev(P.G.contig_off, P.G.num_contigs, a.x);
+      rec[t] = a;
+    }
+    for (int t = lane; t < rl; t += 32) cache[t] = -1;
+    __syncwarp();
+    int n_anch = 0;
+    if (lane == 0) {
+      // read_get_anchor_list_per_strand :941-971 with anchor_uw_join (anchors.c:98-119); entries
+      // arrive in ascending x, so only the "extend to the right" branch of the join can fire.
+      for (int t = 0; t < m_surv; t++) {
+        const AnchorRec a = rec[t];
+        const int slot = (int)(((unsigned long long)a.x + (unsigned long long)rl - (unsigned long long)a.y) %
+                               (unsigned long long)rl);
+        const int j = cache[slot];
+        if (j >= 0 && rec[j].cn == a.cn &&
+            (long long)rec[j].x - rec[j].y == (long long)a.x - a.y) {
+          AnchorRec d = rec[j];
+          if ((long long)a.x + a.len > (long long)d.x + d.len) d.len = (int16_t)((long long)a.x - d.x + a.len);
+          d.weight += 1;
+          rec[j] = d;
+        } else {
+          rec[n_anch] = a;
+          cache[slot] = (int16_t)n_anch;
+          n_anch++;
+        }
+      }
+    }
+    n_anch = __shfl_sync(0xffffffffu, n_anch, 0);
+    __syncwarp();
+
+    // ---- 7. hit list (read_get_hit_list_per_strand) ---------------------------------------------
+    uint32_t out0 = 0;
+    if (lane == 0) {
+      out0 = atomicAdd(P.hits_used, (uint32_t)n_anch);
+      atomicAdd(&P.stats[3], (uint32_t)n_anch);
+    }
+    out0 = __shfl_sync(0xffffffffu, out0, 0);
+    if ((unsigned long long)out0 + (unsigned long long)n_anch > (unsigned long long)P.hits_cap) {
+      if (lane == 0) atomicOr(P.status, 1u);
+      continue;
+    }
+    const int window_len = (int)(unsigned short)abs_or_pct_d(M.window_len, M.window_len_frac, (double)rl);
+    int nh = 0;
+    for (int i0 = 0; i0 < n_anch; i0 += 32) {
+      const int i = i0 + lane;
+      bool emit = false;
+      DevHit h;
+      if (i < n_anch) {
+        const AnchorRec ai = rec[i];
+        const int cn = ai.cn;
+        const long long coff = (long long)P.G.contig_off[cn];
+        const long long glen = (long long)P.G.contig_len[cn];
+        int w_len = window_len;
+        if ((long long)w_len > glen) w_len = (int)glen;
+        long long gend = ((long long)ai.x - coff) + rl - 1 - ai.y, gstart;
+        if (gend > glen - 1) gend = glen - 1;
+        gstart = gend >= window_len ? gend - window_len : 0;
+        int max_idx = i;
+        int max_score = ai.len * M.match;
+        if (!M.gapless) {
+          if (M.match_mode == 2 && ai.weight == 1) max_score = -1;
+          for (int j = i - 1; j >= 0; j--) {
+            const AnchorRec aj = rec[j];
+            if ((long long)aj.x < coff + gstart) break;
+            if (aj.y >= ai.y) continue;
+            int short_len, long_len;
+            if ((long long)ai.x - coff - ai.y > (long long)aj.x - coff - aj.y) {
+              short_len = (int)(ai.y - aj.y) + ai.len;
+              long_len = (int)((long long)ai.x - (long long)aj.x) + ai.len;
+            } else {
+              short_len = (int)((long long)ai.x - (long long)aj.x) + ai.len;
+              long_len = (int)(ai.y - aj.y) + ai.len;
+            }
+            int tmp_score = short_len * M.match;
+            if (long_len > short_len) tmp_score += M.b_gap_open + (long_len - short_len) * M.b_gap_ext;  // :1134
+            if (tmp_score > max_score) {
+              max_idx = j;
+              max_score = tmp_score;
+            }
+          }
+        }
+        const int base_len = rl < w_len ? rl : w_len;
+        const int score_max = base_len * M.match;
+        if (M.gapless || M.match_mode == 1 ||
+            max_score >= (int)abs_or_pct_d(M.wgen_thr, M.wgen_frac, (double)score_max)) {
+          const AnchorRec am = rec[max_idx];
+          const int x_len = (int)((long long)ai.x - (long long)am.x) + ai.len;
+          long long goff;
+          if ((long long)((window_len - x_len) / 2) < (long long)am.x - coff)
+            goff = ((long long)am.x - coff) - (window_len - x_len) / 2;
+          else
+            goff = 0;
+          if (goff + w_len > glen) goff = glen - w_len;
+          const long long rel = coff + goff;
+          if (max_idx < i) {
+            anchor_join2((long long)ai.x - rel, ai.y, ai.len, 1, (long long)am.x - rel, am.y, am.len, 1, h.ax, h.ay,
+                         h.alen, h.awidth);
+          } else {
+            h.ax = (int)((long long)ai.x - rel);
+            h.ay = ai.y;
+            h.alen = ai.len;
+            h.awidth = 1;
+          }
+          h.g_off = (uint32_t)goff;
+          h.cn = cn;
+          h.w_len = w_len;
+          h.wg = max_score;
+          h.matches = (M.gapless || max_idx == i) ? ai.weight : ai.weight + am.weight;
+          h.score_max = score_max;
+          h.score_vector = -1;
+          h.pct_vector = 0;
+          emit = true;
+        }
+      }
+      const uint32_t b = __ballot_sync(0xffffffffu, emit);
+      if (emit) P.hits[out0 + nh + __popc(b & ((1u << lane) - 1u))] = h;
+      nh += __popc(b);
+    }
+    __syncwarp();
+    // stable insertion sort by g_off inside a contig (:1210-1223); the list is almost sorted
+    if (lane == 0) {
+      DevHit *H = P.hits + out0;
+      for (int i = 1; i < nh; i++) {
+        const DevHit cur = H[i];
+        int j = i;
+        while (j >= 1 && H[j - 1].cn == cur.cn && H[j - 1].g_off > cur.g_off) j--;
+        if (j < i) {
+          for (int k = i - 1; k >= j; k--) H[k + 1] = H[k];
+          H[j] = cur;
+        }
+      }
+      P.rs_range[rs] = make_uint2(out0, (uint32_t)nh);
+    }
+    __syncwarp();
+  }
+}
+
+size_t scan_smem_bytes(int cap, int max_rl, int warps) {
+  size_t per_warp = (size_t)cap * 8 + (size_t)cap * 16 + (((size_t)max_rl * 2 + 15) & ~(size_t)15) +
+                    (size_t)(cap / 32 + 1) * 4;
+  per_warp = (per_warp + 15) & ~(size_t)15;
+  return per_warp * warps;
+}
+
+int launch_scan(shrimp_gpu_ctx *ctx, ScanParams &P, int warps_per_cta, int n_ctas) {
+  size_t smem = scan_smem_bytes(P.cap, P.max_rl, warps_per_cta);
+  static size_t configured = 0;
+  if (smem > configured) {
+    SH_CUDA(cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = 227 * 1024;
+  }
+  scan_kernel<<<n_ctas, SCAN_WARPS * 32, smem, ctx->stream>>>(P, warps_per_cta);
+  SH_CUDA(cudaGetLastError());
+  SH_LAUNCHED(ctx, ST_SCAN);
+  return SHRIMP_OK;
+}
+
+}  // namespace shrimp

@@ -1,0 +1,114 @@
+// Parameter blocks of the pipeline stage kernels (scan.cu, pass1.cu, sw_full.cu), shared with the
+// host orchestration in pipeline.cu.
+#pragma once
+#include "pipeline.cuh"
+
+namespace shrimp {
+
+#define SCAN_WARPS 8
+#define SCAN_WARPS_HOST SCAN_WARPS
+
+struct ScanParams {
+  GenomeView G;
+  IndexView I;
+  SeedTable S;
+  MapParamsDev M;
+  const uint32_t *reads;  // [2 * n_reads][stride], row 2*r + st
+  int stride;
+  int n_reads;
+  const int32_t *read_len;
+  // work list: nullptr = all read strands, else explicit list (overflow pass)
+  const uint32_t *work;
+  uint32_t n_work;
+  // outputs
+  DevHit *hits;
+  uint32_t hits_cap;
+  uint32_t *hits_used;     // atomic cursor
+  uint2 *rs_range;         // [2 * n_reads] (first hit, count)
+  uint32_t *overflow;      // list of read strands that did not fit `cap`
+  uint32_t *n_overflow;
+  uint32_t *status;        // bit 0: hits_cap exhausted, bit 1: slab exhausted in the overflow pass
+  uint32_t *stats;         // [0] heap replays, [1] gathered entries, [2] surviving entries, [3] anchors
+  // per-warp global scratch for the heap replay: [n_warps][scratch_ints]
+  int32_t *scratch;
+  int scratch_ints;
+  int k_max;               // n_seeds * max_n_kmers upper bound
+  int cap;                 // slab entries per warp
+  int max_rl;
+};
+
+struct AnchorRec {
+  uint32_t x;      // global position
+  int32_t cn;
+  int16_t y, len;
+  int32_t weight;
+};
+
+struct TaskBuildParams {
+  GenomeView G;
+  MapParamsDev M;
+  const DevHit *hits;
+  const uint2 *rs_range;
+  const int32_t *read_len;
+  int n_reads;
+  // task arrays indexed by hit slot, one set per genome orientation (colour space reverses the
+  // strand-1 hits onto the reverse-complement genome, mapping.c:1303-1312)
+  uint32_t *goff[2];
+  int32_t *glen[2];
+  int32_t *ridx[2];
+  int32_t *rlen[2];
+  int8_t *initbp_out[2];
+  const int8_t *initbp;   // per read (colour space)
+  uint32_t *slot;         // f1 cache slot per hit (hash_filter_calls)
+};
+
+struct Pass1Params {
+  MapParamsDev M;
+  DevHit *hits;
+  const uint2 *rs_range;
+  const int32_t *read_len;
+  int n_reads;
+  const int32_t *vtrue[2];   // true sw_vector scores per hit slot (per orientation launch)
+  const uint32_t *slot;
+  uint8_t *writer;           // scratch flag per hit slot
+  int32_t *sel;              // [n_reads][num_tmp_outputs] hit slots in heap-array order
+  int32_t *n_sel;            // [n_reads]
+  uint32_t *stats;           // [4] vector calls the reference would make, [5] bypassed, [6] cells (lo), [7] cells (hi)
+};
+
+struct FullTask {
+  uint32_t goff_global;  // window start in the chosen orientation array (global nibble coordinate)
+  uint32_t goff_contig;  // same, relative to the contig (what sw_full_ls receives as goff)
+  int32_t glen, rlen;
+  int32_t ridx;          // row of the read in the reads array
+  int32_t ax, ay, alen, awidth;
+  int32_t thresh, maxscore;
+  int32_t gen_st;        // 0 forward genome, 1 reverse-complement genome
+  int32_t run;           // 0: below threshold, result score = 0 without DP (mapping.c:390-398)
+};
+
+struct FullResult {
+  int32_t score;
+  int32_t read_start, rmapped, genome_start, gmapped;
+  int32_t matches, mismatches, insertions, deletions, crossovers;
+  int32_t ops_start, ops_len;   // into this task's ops column
+};
+
+struct FullParams {
+  const uint32_t *genome_fwd, *genome_rc;
+  const uint32_t *reads;
+  int stride;
+  const FullTask *tasks;
+  FullResult *results;
+  int n_tasks;      // in this launch
+  int NT;           // scratch stride (>= n_tasks)
+  int32_t *row;     // [3][max_glen+1][NT]
+  uint8_t *bp;      // [max_rlen*max_glen][NT]
+  uint8_t *ops;     // [NT][max_rlen+max_glen]
+  int max_glen, max_rlen;
+  int match, mismatch, a_open, a_ext, b_open, b_ext;
+  int anchor_width, Tflag, local;
+  unsigned long long *cells;
+};
+
+}  // namespace shrimp

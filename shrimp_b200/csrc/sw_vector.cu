@@ -170,8 +170,9 @@ __global__ void __launch_bounds__(SWV_BLOCK) sw_vector_kernel(const SwvParams P)
       }
     }
   }
-  P.scores[tA] = (int)(int16_t)(best & 0xffffu);
-  if (hasB) P.scores[tB] = (int)(int16_t)(best >> 16);
+  // tasks with glen <= 0 are placeholders (pipeline slots that pass 1 will never read)
+  if (glenA > 0) P.scores[tA] = (int)(int16_t)(best & 0xffffu);
+  if (hasB && glenB > 0) P.scores[tB] = (int)(int16_t)(best >> 16);
 }
 
 template <int T>

@@ -1,0 +1,89 @@
+"""GPU parity of the chunk pipeline (shrimp_gpu_map_reads): post-pass1 hit lists and the reported
+alignments vs (a) golden vectors from the reference gmapper and (b) the CPU oracle on the same inputs."""
+import os
+
+import numpy as np
+import pytest
+
+from mapcases import GOLD, MAP_CASES, LsCase, stage_tuple_array
+from shrimp_b200 import align
+from shrimp_b200.api import MapParams, _pack_codes, auto_list_cutoff
+
+pytestmark = pytest.mark.gpu
+
+
+def run_gpu(ctx, case, **over):
+    ctx.sw_setup(1400, 1000, case.scores, use_colours=False, anchor_width=8)
+    ctx.load_genome([_pack_codes(c.astype(np.uint32)) for c in case.contig_codes], [c.size for c in case.contig_codes])
+    ctx.build_index(case.seeds)
+    params = MapParams(list_cutoff=auto_list_cutoff(case.total_len, max(s.weight for s in case.seeds)), **over)
+    return ctx.map_reads(params, case.scores, case.packed, case.read_len, want_stage=True)
+
+
+def sam_arrays(case, res):
+    rows, cig = [], []
+    for h in res.hits:
+        e = res.edits[int(h["edit_off"]): int(h["edit_off"]) + int(h["edit_len"])]
+        f = align.sam_fields(h, e, int(case.read_len[h["read_idx"]]), int(case.contig_codes[h["cn"]].size))
+        rows.append([int(h["read_idx"]), f[0], f[1], f[2], f[4], f[5]])
+        cig.append(f[3])
+    return np.array(rows, dtype=np.int64).reshape(-1, 6), np.array(cig)
+
+
+@pytest.mark.parametrize("name", sorted(MAP_CASES))
+def test_pipeline_matches_reference_golden(gpu_ctx, name):
+    gold = np.load(os.path.join(GOLD, f"map_{name}.npz"))
+    case = LsCase(name)
+    res = run_gpu(gpu_ctx, case, **MAP_CASES[name]["opts"])
+    got_stage = stage_tuple_array(res.stage)
+    assert got_stage.shape == gold["stage"].shape
+    bad = np.nonzero((got_stage != gold["stage"]).any(axis=1))[0]
+    assert bad.size == 0, (bad[:5], got_stage[bad[:5]], gold["stage"][bad[:5]])
+    sam, cig = sam_arrays(case, res)
+    assert sam.shape == gold["sam"].shape
+    bad = np.nonzero((sam != gold["sam"]).any(axis=1))[0]
+    assert bad.size == 0, (bad[:5], sam[bad[:5]], gold["sam"][bad[:5]])
+    assert np.array_equal(cig, gold["cigars"])
+
+
+def test_pipeline_alignment_strings_match_oracle(gpu_ctx):
+    """dbalign/qralign rebuilt from the edit script equal the oracle's pretty_print strings"""
+    from oracle import pipeline as op
+    from test_oracle_pipeline import run_oracle
+    case = LsCase("c1_small")
+    res = run_gpu(gpu_ctx, case)
+    g, hits, nper, stage, stats = run_oracle(case)
+    assert len(hits) == len(res.hits)
+    cmpl = np.array([3, 2, 1, 0, 0, 10, 9, 7, 8, 6, 5, 14, 13, 12, 11, 15], dtype=np.uint8)
+    for a, b in zip(res.hits[:400], hits[:400]):
+        codes = case.contig_codes[int(a["cn"])]
+        if int(a["gen_st"]) == 1:
+            codes = cmpl[codes[::-1]]
+        e = res.edits[int(a["edit_off"]): int(a["edit_off"]) + int(a["edit_len"])]
+        rcodes = np.frombuffer(case.reads[int(a["read_idx"])][1].tobytes(), dtype=np.uint8)
+        from shrimp_b200.api import _LS_CODE
+        db, qr = align.align_strings(e, codes, int(a["genome_start"]), _LS_CODE[rcodes], int(a["read_start"]))
+        assert db == bytes(b["sfr"]["dbalign"]).split(b"\0")[0]
+        assert qr == bytes(b["sfr"]["qralign"]).split(b"\0")[0]
+        for k in ("read_start", "rmapped", "genome_start", "gmapped", "mismatches", "insertions", "deletions"):
+            assert int(a[k]) == int(b["sfr"][k])
+        assert int(a["sfr_matches"]) == int(b["sfr"]["matches"])
+        assert int(a["sw_score"]) == int(b["sw_score"]) and int(a["score_full"]) == int(b["score_full"])
+    assert res.stats["vector_calls"] == stats["vector_calls"]
+    assert res.stats["vector_cells"] == stats["vector_cells"]
+    assert res.stats["full_cells"] == stats["full_cells"]
+
+
+def test_pipeline_empty_and_tiny_reads(gpu_ctx):
+    case = LsCase("c1_small")
+    gpu_ctx.sw_setup(1400, 1000, case.scores)
+    gpu_ctx.load_genome([_pack_codes(c.astype(np.uint32)) for c in case.contig_codes], [c.size for c in case.contig_codes])
+    gpu_ctx.build_index(case.seeds)
+    params = MapParams(list_cutoff=1000)
+    res = gpu_ctx.map_reads(params, case.scores, case.packed[:0], case.read_len[:0])
+    assert len(res.hits) == 0
+    # reads shorter than every seed map nowhere (gmapper.c:503-507 skips them)
+    rl = case.read_len[:8].copy()
+    rl[:] = 10
+    res = gpu_ctx.map_reads(params, case.scores, case.packed[:8], rl)
+    assert len(res.hits) == 0 and (res.n_hits_per_read == 0).all()
