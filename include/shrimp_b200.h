@@ -177,6 +177,7 @@ typedef struct shrimp_map_stats {
   uint64_t vector_cells;        /* sum glen*rlen over those calls (sw-vector.c:509) */
   uint64_t vector_bypassed;     /* f1 cache hits */
   uint64_t full_calls, full_cells;
+  uint64_t device_vector_cells; /* sum glen*rlen over the windows the device scored */
 } shrimp_map_stats;
 
 /* initbp: per-read initial base (colour space) or NULL.  hits_cap >= n_reads*num_outputs always
@@ -189,6 +190,19 @@ int shrimp_gpu_map_reads(shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, int n
                          uint8_t *edits, int64_t edits_cap, int64_t *n_hits, int64_t *edits_used,
                          shrimp_stage_hit *stage, int64_t stage_cap, int64_t *n_stage,
                          shrimp_map_stats *stats);
+
+/* Measurement entries (no reference counterpart).  shrimp_gpu_map_resident re-runs every device
+ * stage on the reads the previous shrimp_gpu_map_reads call left in HBM and keeps the results on
+ * the device: the "inputs already resident" throughput of bench.py.  shrimp_gpu_last_transfer_bytes
+ * reports the host<->device bytes of the last shrimp_gpu_map_reads call. */
+int shrimp_gpu_map_resident(shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, shrimp_map_stats *stats);
+int shrimp_gpu_last_transfer_bytes(shrimp_gpu_ctx *ctx, uint64_t *h2d, uint64_t *d2h);
+
+/* CUDA-event bracket on the library's stream (which = 0 start, 1 stop) and an L2 flush (writes a
+ * 256 MB buffer), for timing hygiene in bench.py. */
+int shrimp_gpu_event_record(shrimp_gpu_ctx *ctx, int which);
+int shrimp_gpu_event_elapsed_ms(shrimp_gpu_ctx *ctx, float *ms);
+int shrimp_gpu_flush_l2(shrimp_gpu_ctx *ctx);
 
 /* ------------------------------------------------------------------------------------------
  * Measurement helper (no reference counterpart): integer-pipe peak, in giga thread-level

@@ -55,7 +55,7 @@ class StageHitC(C.Structure):
 class MapStatsC(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("list_entries", "surviving_entries", "anchors", "hits", "heap_replays",
                                           "vector_tasks", "vector_calls", "vector_cells", "vector_bypassed",
-                                          "full_calls", "full_cells")]
+                                          "full_calls", "full_cells", "device_vector_cells")]
 
 
 def lib() -> C.CDLL:
@@ -100,6 +100,16 @@ def lib() -> C.CDLL:
                                        C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64), vp, C.c_int64,
                                        C.POINTER(C.c_int64), C.POINTER(MapStatsC)]
     L.shrimp_gpu_map_reads.restype = i32
+    L.shrimp_gpu_map_resident.argtypes = [vp, C.POINTER(MapParamsC), C.POINTER(MapStatsC)]
+    L.shrimp_gpu_map_resident.restype = i32
+    L.shrimp_gpu_last_transfer_bytes.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
+    L.shrimp_gpu_last_transfer_bytes.restype = i32
+    L.shrimp_gpu_event_record.argtypes = [vp, i32]
+    L.shrimp_gpu_event_record.restype = i32
+    L.shrimp_gpu_event_elapsed_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    L.shrimp_gpu_event_elapsed_ms.restype = i32
+    L.shrimp_gpu_flush_l2.argtypes = [vp]
+    L.shrimp_gpu_flush_l2.restype = i32
     _lib = L
     return L
 

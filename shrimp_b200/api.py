@@ -271,6 +271,29 @@ class GpuContext:
         return MapResult(hits[: n_hits.value], n_per[:n], edits[: e_used.value],
                          stage[: n_stage.value] if want_stage else None, stats)
 
+    def map_resident(self, params: MapParams, scores: Scores) -> dict:
+        """Device stages only, on the reads the last map_reads call left in HBM (bench.py `value`)."""
+        pc = params.to_c(scores, getattr(self, "colour_space", False))
+        st = MapStatsC()
+        check(self._L.shrimp_gpu_map_resident(self._h, C.byref(pc), C.byref(st)), "shrimp_gpu_map_resident")
+        return {k: int(getattr(st, k)) for k, _ in MapStatsC._fields_}
+
+    def last_transfer_bytes(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        check(self._L.shrimp_gpu_last_transfer_bytes(self._h, C.byref(a), C.byref(b)), "shrimp_gpu_last_transfer_bytes")
+        return int(a.value), int(b.value)
+
+    def event_record(self, which: int):
+        check(self._L.shrimp_gpu_event_record(self._h, which), "shrimp_gpu_event_record")
+
+    def event_elapsed_ms(self) -> float:
+        v = C.c_float()
+        check(self._L.shrimp_gpu_event_elapsed_ms(self._h, C.byref(v)), "shrimp_gpu_event_elapsed_ms")
+        return float(v.value)
+
+    def flush_l2(self):
+        check(self._L.shrimp_gpu_flush_l2(self._h), "shrimp_gpu_flush_l2")
+
     def dpx_peak(self) -> float:
         """Measured integer-pipe peak in G thread-instructions/s (VIADDMNMX.S16x2)."""
         v = C.c_double()

@@ -145,3 +145,37 @@ extern "C" int shrimp_gpu_sw_setup(shrimp_gpu_ctx *c, const shrimp_sw_params *p)
   c->sw = s;
   return SHRIMP_OK;
 }
+
+// Two user events on the library's stream so a caller can bracket a timed region on the device
+// (bench.py: CUDA-event timing of exactly K steps on the launching stream).
+static cudaEvent_t g_user_ev[2] = {nullptr, nullptr};
+extern "C" int shrimp_gpu_event_record(shrimp_gpu_ctx *c, int which) {
+  if (!c || which < 0 || which > 1) {
+    set_error("shrimp_gpu_event_record: invalid argument");
+    return SHRIMP_E_ARG;
+  }
+  SH_CUDA(cudaSetDevice(c->device));
+  if (!g_user_ev[which]) SH_CUDA(cudaEventCreate(&g_user_ev[which]));
+  SH_CUDA(cudaEventRecord(g_user_ev[which], c->stream));
+  return SHRIMP_OK;
+}
+extern "C" int shrimp_gpu_event_elapsed_ms(shrimp_gpu_ctx *c, float *ms) {
+  if (!c || !ms || !g_user_ev[0] || !g_user_ev[1]) {
+    set_error("shrimp_gpu_event_elapsed_ms: events not recorded");
+    return SHRIMP_E_STATE;
+  }
+  SH_CUDA(cudaEventSynchronize(g_user_ev[1]));
+  SH_CUDA(cudaEventElapsedTime(ms, g_user_ev[0], g_user_ev[1]));
+  return SHRIMP_OK;
+}
+// Writes a buffer larger than L2 (126 MB) on the library's stream: L2 flush between timed steps.
+extern "C" int shrimp_gpu_flush_l2(shrimp_gpu_ctx *c) {
+  if (!c) return SHRIMP_E_ARG;
+  SH_CUDA(cudaSetDevice(c->device));
+  static shrimp::DevBuf flush;
+  const size_t bytes = (size_t)256 << 20;
+  SH_TRY(flush.ensure(bytes));
+  SH_CUDA(cudaMemsetAsync(flush.p, 1, bytes, c->stream));
+  SH_CUDA(cudaStreamSynchronize(c->stream));
+  return SHRIMP_OK;
+}

@@ -45,10 +45,16 @@ __global__ void build_vec_tasks_kernel(const TaskBuildParams P) {
   const int r = (int)(rs >> 1), st = (int)(rs & 1u);
   const int rl = P.read_len[r];
   const bool cs = P.M.colour_space != 0;
+  uint32_t n_elig = 0;
+  unsigned long long elig_cells = 0;
   for (uint32_t k = 0; k < rg.y; k++) {
     const uint32_t hi = rg.x + k;
     const DevHit h = P.hits[hi];
     const bool eligible = h.matches >= P.M.min_matches;
+    if (eligible) {
+      n_elig++;
+      elig_cells += (unsigned long long)h.w_len * (unsigned long long)rl;
+    }
     const uint32_t coff = P.G.contig_off[h.cn];
     // orientation used by pass 1: letter space always scores read strand st on the forward genome;
     // colour space scores the forward read and flips strand-1 windows onto the rc genome.
@@ -66,6 +72,10 @@ __global__ void build_vec_tasks_kernel(const TaskBuildParams P) {
       const uint32_t *gen = cs ? (ori ? P.G.cs_rc : P.G.cs) : P.G.ls;
       P.slot[hi] = eligible ? (hash_genome_window_dev(gen, g, (uint32_t)h.w_len) % 1048576u) : 0xffffffffu;
     }
+  }
+  if (n_elig) {
+    atomicAdd(&P.task_stats[0], n_elig);
+    atomicAdd((unsigned long long *)&P.task_stats[2], elig_cells);
   }
 }
 

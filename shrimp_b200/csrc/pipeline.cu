@@ -8,6 +8,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include <algorithm>
+#include <cub/cub.cuh>
 #include "stages.cuh"
 
 namespace shrimp {
@@ -73,8 +74,9 @@ struct FullBuildParams {
   const int32_t *sel;
   const int32_t *n_sel;
   const int32_t *vtrue0;
+  const int32_t *task_off;  // exclusive prefix sum of n_sel: tasks of read r start at task_off[r]
   int n_reads;
-  FullTask *tasks;   // [n_reads * num_tmp_outputs]
+  FullTask *tasks;   // [sum n_sel], dense
   SelInfo *info;
 };
 
@@ -135,16 +137,24 @@ __global__ void build_full_tasks_kernel(const FullBuildParams P) {
     I.score_max = h.score_max;
     I.matches = h.matches;
   }
-  P.tasks[idx] = T;
-  P.info[idx] = I;
+  else {
+    return;
+  }
+  const int out = P.task_off[r] + k;
+  P.tasks[out] = T;
+  P.info[out] = I;
 }
 
 struct Pipeline {
   DevBuf d_in, d_reads, d_read_len, d_initbp, d_hits, d_rs_range, d_counters, d_overflow, d_scratch;
   DevBuf d_task[2], d_vtrue[2], d_slot, d_writer, d_sel, d_nsel;
-  DevBuf d_ftasks, d_finfo, d_fresults, d_frow, d_fbp, d_fops;
+  DevBuf d_ftasks, d_finfo, d_fresults, d_frow, d_fbp, d_fops, d_taskoff, d_scan_tmp;
   HostBuf h_info, h_results, h_ops, h_nsel, h_hits, h_range;
   uint32_t hits_cap = 0;
+  // reads left resident by the last upload (shrimp_gpu_map_resident)
+  int res_n_reads = 0, res_stride = 0;
+  std::vector<int32_t> res_read_len;
+  size_t h2d_bytes = 0, d2h_bytes = 0;
 };
 
 void free_pipeline(shrimp_gpu_ctx *ctx) {
@@ -153,7 +163,7 @@ void free_pipeline(shrimp_gpu_ctx *ctx) {
   DevBuf *bufs[] = {&p->d_in, &p->d_reads, &p->d_read_len, &p->d_initbp, &p->d_hits, &p->d_rs_range, &p->d_counters,
                     &p->d_overflow, &p->d_scratch, &p->d_task[0], &p->d_task[1], &p->d_vtrue[0], &p->d_vtrue[1],
                     &p->d_slot, &p->d_writer, &p->d_sel, &p->d_nsel, &p->d_ftasks, &p->d_finfo, &p->d_fresults,
-                    &p->d_frow, &p->d_fbp, &p->d_fops};
+                    &p->d_frow, &p->d_fbp, &p->d_fops, &p->d_taskoff, &p->d_scan_tmp};
   for (DevBuf *b : bufs) b->release();
   HostBuf *hb[] = {&p->h_info, &p->h_results, &p->h_ops, &p->h_nsel, &p->h_hits, &p->h_range};
   for (HostBuf *b : hb) b->release();
@@ -211,12 +221,28 @@ static void dedup_pass(HostHit **h, int *n, int (*cmp)(const void *, const void 
 
 using namespace shrimp;
 
-extern "C" int shrimp_gpu_map_reads(shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, int n_reads,
-                                    const uint32_t *reads, int stride, const int32_t *read_len, const int8_t *initbp,
-                                    shrimp_hit *hits_out, int64_t hits_cap, int32_t *n_hits_per_read, uint8_t *edits,
-                                    int64_t edits_cap, int64_t *n_hits, int64_t *edits_used, shrimp_stage_hit *stage,
-                                    int64_t stage_cap, int64_t *n_stage, shrimp_map_stats *stats) {
-  if (!ctx || !mp || !reads || !read_len || n_reads < 0 || stride <= 0 || !hits_out || !n_hits) {
+// resident = reuse the reads uploaded by the previous call (bench: inputs already in HBM);
+// device_only = stop after the last device stage (no D2H of results, no host pass 2).
+static int map_impl(shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, int n_reads, const uint32_t *reads, int stride,
+                    const int32_t *read_len, const int8_t *initbp, shrimp_hit *hits_out, int64_t hits_cap,
+                    int32_t *n_hits_per_read, uint8_t *edits, int64_t edits_cap, int64_t *n_hits, int64_t *edits_used,
+                    shrimp_stage_hit *stage, int64_t stage_cap, int64_t *n_stage, shrimp_map_stats *stats,
+                    bool resident, bool device_only) {
+  int64_t dummy_hits = 0;
+  if (device_only && !n_hits) n_hits = &dummy_hits;
+  if (resident) {
+    Pipeline *pp = ctx ? (Pipeline *)ctx->pipeline : nullptr;
+    if (!pp || pp->res_n_reads <= 0) {
+      set_error("shrimp_gpu_map_resident: no reads resident; call shrimp_gpu_map_reads first");
+      return SHRIMP_E_STATE;
+    }
+    n_reads = pp->res_n_reads;
+    stride = pp->res_stride;
+    read_len = pp->res_read_len.data();
+    reads = (const uint32_t *)1;  // not dereferenced
+    if (genome_of(ctx) && genome_of(ctx)->colour_space) initbp = (const int8_t *)1;
+  }
+  if (!ctx || !mp || !reads || !read_len || n_reads < 0 || stride <= 0 || (!hits_out && !device_only) || !n_hits) {
     set_error("shrimp_gpu_map_reads: invalid argument");
     return SHRIMP_E_ARG;
   }
@@ -256,7 +282,7 @@ extern "C" int shrimp_gpu_map_reads(shrimp_gpu_ctx *ctx, const shrimp_map_params
   if (stats) memset(stats, 0, sizeof(*stats));
   if (n_hits_per_read) memset(n_hits_per_read, 0, sizeof(int32_t) * (size_t)n_reads);
   if (n_reads == 0) return SHRIMP_OK;
-  if (hits_cap < (int64_t)n_reads * mp->num_outputs) {
+  if (!device_only && hits_cap < (int64_t)n_reads * mp->num_outputs) {
     set_error("shrimp_gpu_map_reads: hits_cap must be at least n_reads * num_outputs");
     return SHRIMP_E_ARG;
   }
@@ -336,11 +362,17 @@ extern "C" int shrimp_gpu_map_reads(shrimp_gpu_ctx *ctx, const shrimp_map_params
   SH_TRY(pl->d_in.ensure(in_bytes));
   SH_TRY(pl->d_reads.ensure(in_bytes * 2));
   SH_TRY(pl->d_read_len.ensure((size_t)n_reads * 4));
-  SH_CUDA(cudaMemcpyAsync(pl->d_in.p, reads, in_bytes, cudaMemcpyHostToDevice, st));
-  SH_CUDA(cudaMemcpyAsync(pl->d_read_len.p, read_len, (size_t)n_reads * 4, cudaMemcpyHostToDevice, st));
-  if (cs) {
-    SH_TRY(pl->d_initbp.ensure((size_t)n_reads));
-    SH_CUDA(cudaMemcpyAsync(pl->d_initbp.p, initbp, (size_t)n_reads, cudaMemcpyHostToDevice, st));
+  if (!resident) {
+    SH_CUDA(cudaMemcpyAsync(pl->d_in.p, reads, in_bytes, cudaMemcpyHostToDevice, st));
+    SH_CUDA(cudaMemcpyAsync(pl->d_read_len.p, read_len, (size_t)n_reads * 4, cudaMemcpyHostToDevice, st));
+    if (cs) {
+      SH_TRY(pl->d_initbp.ensure((size_t)n_reads));
+      SH_CUDA(cudaMemcpyAsync(pl->d_initbp.p, initbp, (size_t)n_reads, cudaMemcpyHostToDevice, st));
+    }
+    pl->res_n_reads = n_reads;
+    pl->res_stride = stride;
+    pl->res_read_len.assign(read_len, read_len + n_reads);
+    pl->h2d_bytes = in_bytes + (size_t)n_reads * 4 + (cs ? (size_t)n_reads : 0);
   }
   SH_TRY(pl->d_counters.ensure(64 * 4));
   SH_TRY(pl->d_rs_range.ensure((size_t)n_reads * 2 * sizeof(uint2)));
@@ -443,6 +475,7 @@ extern "C" int shrimp_gpu_map_reads(shrimp_gpu_ctx *ctx, const shrimp_map_params
   VecTaskArrays VT[2];
   for (int o = 0; o < n_ori; o++) {
     SH_TRY(pl->d_task[o].ensure(task_bytes));
+    SH_CUDA(cudaMemsetAsync(pl->d_task[o].p, 0, task_bytes, st));  // hit slots that stay gaps get glen = 0
     SH_TRY(pl->d_vtrue[o].ensure(HU * 4));
     SH_CUDA(cudaMemsetAsync(pl->d_vtrue[o].p, 0xff, HU * 4, st));
   }
@@ -473,6 +506,7 @@ extern "C" int shrimp_gpu_map_reads(shrimp_gpu_ctx *ctx, const shrimp_map_params
     }
     TB.initbp = cs ? pl->d_initbp.as<int8_t>() : nullptr;
     TB.slot = M.hash_filter_calls ? pl->d_slot.as<uint32_t>() : nullptr;
+    TB.task_stats = cnt + 20;
     SH_TRY(launch_build_vec_tasks(ctx, TB));
   }
   if (hits_used > 0) {
@@ -488,7 +522,7 @@ extern "C" int shrimp_gpu_map_reads(shrimp_gpu_ctx *ctx, const shrimp_map_params
   // ---- pass-1 replay + top-k -------------------------------------------------------------------
   const int NT = mp->num_tmp_outputs;
   SH_TRY(pl->d_sel.ensure((size_t)n_reads * NT * 4));
-  SH_TRY(pl->d_nsel.ensure((size_t)n_reads * 4));
+  SH_TRY(pl->d_nsel.ensure(((size_t)n_reads + 1) * 4));
   {
     ScopedStage ss(ctx, ST_PASS1);
     Pass1Params PP;
@@ -547,10 +581,26 @@ extern "C" int shrimp_gpu_map_reads(shrimp_gpu_ctx *ctx, const shrimp_map_params
   }
 
   // ---- full SW on the selected hits ------------------------------------------------------------
-  const int n_slots = n_reads * NT;
-  SH_TRY(pl->d_ftasks.ensure((size_t)n_slots * sizeof(FullTask)));
-  SH_TRY(pl->d_finfo.ensure((size_t)n_slots * sizeof(SelInfo)));
-  SH_TRY(pl->d_fresults.ensure((size_t)n_slots * sizeof(FullResult)));
+  // dense task list: exclusive scan of n_sel (cub, plumbing) -> task offsets per read
+  SH_TRY(pl->d_taskoff.ensure(((size_t)n_reads + 1) * 4));
+  int n_slots = 0;
+  {
+    size_t tmp_bytes = 0;
+    SH_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, pl->d_nsel.as<int32_t>(), pl->d_taskoff.as<int32_t>(),
+                                          n_reads + 1, st));
+    SH_TRY(pl->d_scan_tmp.ensure(tmp_bytes));
+    // n_sel has n_reads entries; entry n_reads of the scan needs a readable (zero) input slot
+    SH_CUDA(cudaMemsetAsync(pl->d_nsel.as<int32_t>() + n_reads, 0, 4, st));
+    SH_CUDA(cub::DeviceScan::ExclusiveSum(pl->d_scan_tmp.p, tmp_bytes, pl->d_nsel.as<int32_t>(),
+                                          pl->d_taskoff.as<int32_t>(), n_reads + 1, st));
+    ctx->launches += 1;
+    SH_CUDA(cudaMemcpyAsync(&n_slots, pl->d_taskoff.as<int32_t>() + n_reads, 4, cudaMemcpyDeviceToHost, st));
+    SH_CUDA(cudaStreamSynchronize(st));
+  }
+  const int n_grid = n_reads * NT;
+  SH_TRY(pl->d_ftasks.ensure((size_t)std::max(n_slots, 1) * sizeof(FullTask)));
+  SH_TRY(pl->d_finfo.ensure((size_t)std::max(n_slots, 1) * sizeof(SelInfo)));
+  SH_TRY(pl->d_fresults.ensure((size_t)std::max(n_slots, 1) * sizeof(FullResult)));
   const size_t ops_stride = (size_t)max_rl + max_wl;
   {
     ScopedStage ss(ctx, ST_FULL);
@@ -564,20 +614,21 @@ extern "C" int shrimp_gpu_map_reads(shrimp_gpu_ctx *ctx, const shrimp_map_params
     FB.sel = pl->d_sel.as<int32_t>();
     FB.n_sel = pl->d_nsel.as<int32_t>();
     FB.vtrue0 = pl->d_vtrue[0].as<int32_t>();
+    FB.task_off = pl->d_taskoff.as<int32_t>();
     FB.n_reads = n_reads;
     FB.tasks = pl->d_ftasks.as<FullTask>();
     FB.info = pl->d_finfo.as<SelInfo>();
-    build_full_tasks_kernel<<<(n_slots + 127) / 128, 128, 0, st>>>(FB);
+    build_full_tasks_kernel<<<(n_grid + 127) / 128, 128, 0, st>>>(FB);
     SH_CUDA(cudaGetLastError());
     SH_LAUNCHED(ctx, ST_FULL);
 
     // sub-batches sized for ~2 GB of DP scratch
     const size_t per_task = (size_t)3 * (max_wl + 1) * 4 + (size_t)max_rl * max_wl + ops_stride;
-    int batch = (int)std::min<size_t>((size_t)n_slots, std::max<size_t>(1024, ((size_t)2 << 30) / per_task));
+    int batch = (int)std::min<size_t>((size_t)std::max(n_slots, 1), std::max<size_t>(1024, ((size_t)2 << 30) / per_task));
     batch = (batch + 127) & ~127;
     SH_TRY(pl->d_frow.ensure((size_t)3 * (max_wl + 1) * 4 * batch));
     SH_TRY(pl->d_fbp.ensure((size_t)max_rl * max_wl * batch));
-    SH_TRY(pl->d_fops.ensure(ops_stride * (size_t)n_slots));
+    SH_TRY(pl->d_fops.ensure(ops_stride * (size_t)std::max(n_slots, 1)));
     for (int b0 = 0; b0 < n_slots; b0 += batch) {
       FullParams FP;
       memset(&FP, 0, sizeof(FP));
@@ -608,7 +659,29 @@ extern "C" int shrimp_gpu_map_reads(shrimp_gpu_ctx *ctx, const shrimp_map_params
     }
   }
 
+  if (device_only) {
+    SH_TRY(pl->h_nsel.ensure((size_t)n_reads * 4 + 64 * 4));
+    uint32_t *hc = (uint32_t *)((char *)pl->h_nsel.p + (size_t)n_reads * 4);
+    SH_CUDA(cudaMemcpyAsync(hc, cnt, 64 * 4, cudaMemcpyDeviceToHost, st));
+    SH_CUDA(cudaStreamSynchronize(st));
+    if (stats) {
+      stats->heap_replays = hc[8 + 0];
+      stats->list_entries = hc[8 + 1];
+      stats->surviving_entries = hc[8 + 2];
+      stats->anchors = hc[8 + 3];
+      stats->hits = hits_used;
+      stats->vector_tasks = hc[20];
+      stats->device_vector_cells = *(unsigned long long *)(hc + 22);
+      stats->vector_calls = hc[8 + 4];
+      stats->vector_bypassed = hc[8 + 5];
+      stats->vector_cells = *(unsigned long long *)(hc + 8 + 6);
+      stats->full_cells = *(unsigned long long *)(hc + 16);
+    }
+    return SHRIMP_OK;
+  }
   // ---- results back to the host ------------------------------------------------------------------
+  pl->d2h_bytes = (size_t)n_slots * (sizeof(SelInfo) + sizeof(FullResult)) + ops_stride * (size_t)n_slots +
+                  (size_t)n_reads * 4 + 64 * 4;
   SH_TRY(pl->h_info.ensure((size_t)n_slots * sizeof(SelInfo)));
   SH_TRY(pl->h_results.ensure((size_t)n_slots * sizeof(FullResult)));
   SH_TRY(pl->h_ops.ensure(ops_stride * (size_t)n_slots));
@@ -632,11 +705,12 @@ extern "C" int shrimp_gpu_map_reads(shrimp_gpu_ctx *ctx, const shrimp_map_params
   int64_t n_out = 0, e_used = 0;
   uint64_t full_calls = 0, pass2_vector_calls = 0, pass2_vector_cells = 0;
   bool edits_short = false;
+  int task_base = 0;
   for (int r = 0; r < n_reads; r++) {
     const int n1 = NSEL[r];
     int n2 = 0;
     for (int k = 0; k < n1; k++) {
-      const int idx = r * NT + k;
+      const int idx = task_base + k;
       HostHit &h = hh[k];
       h.info = INFO[idx];
       h.res = RES[idx];
@@ -708,6 +782,7 @@ extern "C" int shrimp_gpu_map_reads(shrimp_gpu_ctx *ctx, const shrimp_map_params
       e_used += h.res.ops_len;
     }
     if (n_hits_per_read) n_hits_per_read[r] = n2;
+    task_base += n1;
   }
   *n_hits = n_out;
   if (edits_used) *edits_used = e_used;
@@ -717,7 +792,8 @@ extern "C" int shrimp_gpu_map_reads(shrimp_gpu_ctx *ctx, const shrimp_map_params
     stats->surviving_entries = h_cnt[8 + 2];
     stats->anchors = h_cnt[8 + 3];
     stats->hits = hits_used;
-    stats->vector_tasks = hits_used;
+    stats->vector_tasks = h_cnt[20];
+    stats->device_vector_cells = *(unsigned long long *)(h_cnt + 22);
     stats->vector_calls = (uint64_t)h_cnt[8 + 4] + pass2_vector_calls;
     stats->vector_bypassed = h_cnt[8 + 5];
     stats->vector_cells = *(unsigned long long *)(h_cnt + 8 + 6) + pass2_vector_cells;
@@ -728,5 +804,33 @@ extern "C" int shrimp_gpu_map_reads(shrimp_gpu_ctx *ctx, const shrimp_map_params
     set_error("shrimp_gpu_map_reads: edits_cap too small, %lld bytes needed", (long long)e_used);
     return SHRIMP_E_NOMEM;
   }
+  return SHRIMP_OK;
+}
+
+extern "C" int shrimp_gpu_map_reads(shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, int n_reads,
+                                    const uint32_t *reads, int stride, const int32_t *read_len, const int8_t *initbp,
+                                    shrimp_hit *hits_out, int64_t hits_cap, int32_t *n_hits_per_read, uint8_t *edits,
+                                    int64_t edits_cap, int64_t *n_hits, int64_t *edits_used, shrimp_stage_hit *stage,
+                                    int64_t stage_cap, int64_t *n_stage, shrimp_map_stats *stats) {
+  return map_impl(ctx, mp, n_reads, reads, stride, read_len, initbp, hits_out, hits_cap, n_hits_per_read, edits,
+                  edits_cap, n_hits, edits_used, stage, stage_cap, n_stage, stats, false, false);
+}
+
+// Measurement entry: re-runs every device stage on the reads left in HBM by the previous
+// shrimp_gpu_map_reads call; results stay on the device (bench.py's device-resident `value`).
+extern "C" int shrimp_gpu_map_resident(shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, shrimp_map_stats *stats) {
+  return map_impl(ctx, mp, 0, nullptr, 0, nullptr, nullptr, nullptr, 0, nullptr, nullptr, 0, nullptr, nullptr, nullptr,
+                  0, nullptr, stats, true, true);
+}
+
+// Host<->device bytes moved by the last shrimp_gpu_map_reads call.
+extern "C" int shrimp_gpu_last_transfer_bytes(shrimp_gpu_ctx *ctx, uint64_t *h2d, uint64_t *d2h) {
+  Pipeline *pl = ctx ? (Pipeline *)ctx->pipeline : nullptr;
+  if (!pl) {
+    set_error("shrimp_gpu_last_transfer_bytes: no mapping call yet");
+    return SHRIMP_E_STATE;
+  }
+  if (h2d) *h2d = pl->h2d_bytes;
+  if (d2h) *d2h = pl->d2h_bytes;
   return SHRIMP_OK;
 }

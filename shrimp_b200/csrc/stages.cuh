@@ -60,6 +60,7 @@ struct TaskBuildParams {
   int8_t *initbp_out[2];
   const int8_t *initbp;   // per read (colour space)
   uint32_t *slot;         // f1 cache slot per hit (hash_filter_calls)
+  uint32_t *task_stats;   // [0] eligible windows, [2..3] their cells (u64)
 };
 
 struct Pass1Params {

@@ -86,18 +86,22 @@ __global__ void __launch_bounds__(SWV_BLOCK) sw_vector_kernel(const SwvParams P)
   const bool hasB = (tA + 1) < P.n_tasks;
   const int tB = hasB ? tA + 1 : tA;
 
+  // glen <= 0 marks a placeholder slot (pipeline hit slots that are gaps or ineligible): its other
+  // fields may be stale, so they are not read and the lane runs on padding only.
   const int glenA = P.t.glen[tA], glenB = P.t.glen[tB];
-  const int rlenA = P.t.rlen[tA], rlenB = P.t.rlen[tB];
-  const uint64_t goffA = P.t.goff[tA], goffB = P.t.goff[tB];
-  const uint32_t *readA = P.reads + (size_t)P.t.ridx[tA] * P.read_stride;
-  const uint32_t *readB = P.reads + (size_t)P.t.ridx[tB] * P.read_stride;
+  const bool okA = glenA > 0, okB = glenB > 0;
+  if (!okA && !okB) return;
+  const int rlenA = okA ? P.t.rlen[tA] : 0, rlenB = okB ? P.t.rlen[tB] : 0;
+  const uint64_t goffA = okA ? P.t.goff[tA] : 0, goffB = okB ? P.t.goff[tB] : 0;
+  const uint32_t *readA = P.reads + (okA ? (size_t)P.t.ridx[tA] * P.read_stride : 0);
+  const uint32_t *readB = P.reads + (okB ? (size_t)P.t.ridx[tB] * P.read_stride : 0);
   const int ncols = max(glenA, glenB);
   const int sh = P.sh;
   const uint32_t DPAD = 16u << sh, QPAD = 17u << sh;
   int ibA = 0, ibB = 0;
   if (CS) {
-    ibA = P.t.initbp[tA];
-    ibB = P.t.initbp[tB];
+    ibA = okA ? P.t.initbp[tA] : 0;
+    ibB = okB ? P.t.initbp[tB] : 0;
   }
 
   const uint32_t MA1 = P.ma1, MM = P.mm, NAOE = P.naoe, NAE = P.nae, NBOE = P.nboe, NBE = P.nbe;
