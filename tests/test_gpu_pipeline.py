@@ -87,3 +87,45 @@ def test_pipeline_empty_and_tiny_reads(gpu_ctx):
     rl[:] = 10
     res = gpu_ctx.map_reads(params, case.scores, case.packed[:8], rl)
     assert len(res.hits) == 0 and (res.n_hits_per_read == 0).all()
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(os.path.dirname(__file__), "..", "oracle", "_ref", "gmapper-ls")),
+                    reason="prebuilt reference binary (oracle/_ref) not present")
+def test_c1_full_size_matches_reference_binary(gpu_ctx, tmp_path):
+    """BASELINE.json configs[0] at full size (100 k x 50 bp vs 10 Mb): every SAM record's hot-path fields
+    equal the reference gmapper run on this box's CPUs (oracle/_ref/gmapper-ls -N <cores>).  This size has
+    the rare equal-position anchors that need the exact heap replay (SURVEY hard part 3a)."""
+    import subprocess
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+    import bench
+    from oracle import pipeline as op
+    from shrimp_b200 import seeds as S
+    from shrimp_b200.api import LS_DEFAULT_SCORES
+    n = 100_000
+    genome, reads, _, _ = bench.make_workload(n)
+    d = str(tmp_path)
+    bench.write_fasta(os.path.join(d, "genome.fa"), ["contig0"], [genome])
+    bench.write_fasta(os.path.join(d, "reads.fa"), [f"r{i}" for i in range(n)], reads)
+    with open(os.path.join(d, "ref.sam"), "w") as f:
+        subprocess.run([os.path.join(os.path.dirname(__file__), "..", "oracle", "_ref", "gmapper-ls"), "-N",
+                        str(os.cpu_count() or 1), "reads.fa", "genome.fa"], cwd=d, stdout=f,
+                       stderr=subprocess.DEVNULL, check=True)
+    ref = op.parse_sam(os.path.join(d, "ref.sam"))
+    gpu_ctx.sw_setup(1400, 1000, LS_DEFAULT_SCORES)
+    gpu_ctx.load_genome([_pack_codes(genome.astype(np.uint32))], [genome.size])
+    gpu_ctx.build_index(S.load_default_seeds())
+    params = MapParams(list_cutoff=auto_list_cutoff(genome.size, 12))
+    res = gpu_ctx.map_reads(params, LS_DEFAULT_SCORES, bench.pack_rows(reads), np.full(n, 50, np.int32))
+    assert res.stats["heap_replays"] > 0
+    assert len(res.hits) == len(ref)
+    bad = 0
+    for h, rrec in zip(res.hits, ref):
+        e = res.edits[int(h["edit_off"]): int(h["edit_off"]) + int(h["edit_len"])]
+        f = align.sam_fields(h, e, 50, genome.size)
+        mine = (f"r{int(h['read_idx'])}", f[0], "contig0", f[2], f[3], f[4], f[5])
+        if mine != rrec:
+            bad += 1
+            if bad < 5:
+                print("DIFF", mine, rrec)
+    assert bad == 0
