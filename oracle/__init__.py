@@ -101,3 +101,69 @@ class RefSw:
     def sw_gapless(self, genome, glen, read, rlen, g_idx, r_idx, genome_ls=None, initbp=-1) -> int:
         return self.L.ref_sw_gapless(_p(genome), int(glen), _p(read), int(rlen), int(g_idx), int(r_idx),
                                      _p(genome_ls), int(initbp))
+
+
+class OrcSfrC(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("read_start", "rmapped", "genome_start", "gmapped", "matches", "mismatches",
+                                       "insertions", "deletions", "score", "crossovers")] + \
+               [("dbalign", C.c_char * 640), ("qralign", C.c_char * 640)]
+
+
+class RefSfrC(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("read_start", "rmapped", "genome_start", "gmapped", "matches", "mismatches",
+                                       "insertions", "deletions", "score", "crossovers")] + \
+               [("dbalign", C.c_char * 4096), ("qralign", C.c_char * 4096)]
+
+
+def _sfr_tuple(s):
+    return (s.read_start, s.rmapped, s.genome_start, s.gmapped, s.matches, s.mismatches, s.insertions, s.deletions,
+            s.score, s.crossovers, bytes(s.dbalign), bytes(s.qralign))
+
+
+def sw_full_ls(genome, goff, glen, read, rlen, thresh, maxscore, revcmpl, anchor, anchor_width, local, scores):
+    L = oracle_lib()
+    sc = scores_struct(scores)
+    out = OrcSfrC()
+    L.orc_sw_full_ls(_p(genome), int(goff), int(glen), _p(read), int(rlen), int(thresh), int(maxscore), int(revcmpl),
+                     C.c_longlong(anchor[0]), C.c_longlong(anchor[1]), int(anchor[2]), int(anchor[3]),
+                     int(anchor_width), int(local), C.byref(sc), C.byref(out))
+    return _sfr_tuple(out)
+
+
+def sw_full_cs(genome_ls, goff, glen, read, rlen, initbp, thresh, revcmpl, anchor, anchor_width, taboo, local,
+               xover_scores, scores):
+    L = oracle_lib()
+    sc = scores_struct(scores)
+    out = OrcSfrC()
+    L.orc_sw_full_cs(_p(genome_ls), int(goff), int(glen), _p(read), int(rlen), int(initbp), int(thresh), int(revcmpl),
+                     C.c_longlong(anchor[0]), C.c_longlong(anchor[1]), int(anchor[2]), int(anchor[3]),
+                     int(anchor_width), int(taboo), int(local), _p(xover_scores), C.byref(sc), C.byref(out), None)
+    return _sfr_tuple(out)
+
+
+class RefFull:
+    """The reference's sw_full_ls / sw_full_cs through oracle/_ref/libshrimp_ref.so."""
+
+    def __init__(self, dblen, qrlen, scores, anchor_width, colour=False, taboo=0):
+        self.L = ref_lib()
+        if colour:
+            self.L.ref_sw_full_cs_setup(dblen, qrlen, scores.a_gap_open, scores.a_gap_ext, scores.b_gap_open,
+                                        scores.b_gap_ext, scores.match, scores.mismatch, scores.crossover,
+                                        anchor_width, taboo)
+        else:
+            self.L.ref_sw_full_ls_setup(dblen, qrlen, scores.a_gap_open, scores.a_gap_ext, scores.b_gap_open,
+                                        scores.b_gap_ext, scores.match, scores.mismatch, anchor_width)
+
+    def sw_full_ls(self, genome, goff, glen, read, rlen, thresh, maxscore, revcmpl, anchor, local):
+        out = RefSfrC()
+        self.L.ref_sw_full_ls(_p(genome), int(goff), int(glen), _p(read), int(rlen), int(thresh), int(maxscore),
+                              int(revcmpl), C.c_longlong(anchor[0]), C.c_longlong(anchor[1]), int(anchor[2]),
+                              int(anchor[3]), int(local), C.byref(out))
+        return _sfr_tuple(out)
+
+    def sw_full_cs(self, genome_ls, goff, glen, read, rlen, initbp, thresh, revcmpl, anchor, local, xover_scores):
+        out = RefSfrC()
+        self.L.ref_sw_full_cs(_p(genome_ls), int(goff), int(glen), _p(read), int(rlen), int(initbp), int(thresh),
+                              int(revcmpl), C.c_longlong(anchor[0]), C.c_longlong(anchor[1]), int(anchor[2]),
+                              int(anchor[3]), int(local), _p(xover_scores), C.byref(out))
+        return _sfr_tuple(out)

@@ -557,4 +557,249 @@ void orc_sw_full_ls(const uint32_t *genome, int goff, int glen, const uint32_t *
                     sc, out, NULL);
 }
 
+/* =============================================================================================
+ * sw_full_cs (common/sw-full-cs.c): the letter genome against the four letter-space translations
+ * of a colour read ("layers"), with crossovers between layers.
+ * ===========================================================================================*/
+typedef struct o_cscell {
+  int n[4], w[4], nw[4];
+  int8_t bn[4], bw[4], bnw[4]; /* FROM_x(layer, dir) = dir << 2 | layer, sw-full-cs.c:53 */
+} o_cscell;
+#define CSFROM(mat, dir) ((int8_t)(((dir) << 2) | (mat)))
+
+static void o_cs_init_cell(o_cscell *c, int local, int xover, int bo, int ao) { /* init_cell :198-242 */
+  for (int k = 0; k < 4; k++) {
+    if (local) {
+      int add = k == 0 ? 0 : xover;
+      c->nw[k] = add;
+      c->n[k] = -bo + add;
+      c->w[k] = -ao + add;
+    } else {
+      c->nw[k] = c->n[k] = c->w[k] = -INT_MAX / 2;
+    }
+    c->bnw[k] = c->bn[k] = c->bw[k] = 0;
+  }
+}
+
+static int o_full_sw_cs(o_cscell *mat, const int8_t *db, int lena, int8_t *const qr[4], int lenb, int threshscore,
+                        int *iret, int *jret, int *kret, int revcmpl, const o_anchor *anchor, int anchor_width,
+                        int local, const int *crossover_score, int global_xover, int indel_taboo_len,
+                        const orc_scores *sc, uint64_t *cells) {
+  const int ao = -sc->a_gap_open, ae = -sc->a_gap_ext, bo = -sc->b_gap_open, be = -sc->b_gap_ext;
+  const int match = sc->match, mismatch = sc->mismatch;
+  int max_i = 0, max_j = 0, max_k = 0, score = 0;
+  const int W = lena + 1;
+  o_anchor rect;
+  for (int j = 0; j < lena + 1; j++) o_cs_init_cell(&mat[j], 1, global_xover, bo, ao); /* :268-270 */
+  if (anchor != NULL && anchor_width >= 0) {
+    o_anchor_join(anchor, 1, &rect);
+    o_anchor_widen(&rect, anchor_width);
+  } else {
+    o_anchor t[2];
+    memset(t, 0, sizeof(t));
+    t[0].x = 0; t[0].y = (lenb * match - threshscore) / match; t[0].length = 1; t[0].width = 1;
+    t[1].x = lena - 1; t[1].y = lenb - 1 - t[0].y; t[1].length = 1; t[1].width = 1;
+    o_anchor_join(t, 2, &rect);
+  }
+  for (int i = 0; i < lenb; i++) {
+    int x_min, x_max;
+    const int xp = crossover_score == NULL ? global_xover : crossover_score[i];
+    const int nt = i < lenb - indel_taboo_len; /* not in the indel taboo zone */
+    o_anchor_x_range(&rect, lena, lenb, i, &x_min, &x_max);
+    o_cs_init_cell(&mat[(i + 1) * W + x_min], local ? 1 : 0, xp, bo, ao); /* :317-325 */
+    if (cells) *cells += (uint64_t)(x_max - x_min + 1);
+    for (int j = x_min; j <= x_max; j++) {
+      const o_cscell *cnw = &mat[i * W + j], *cn = cnw + 1, *cw = cnw + W;
+      o_cscell *cur = &mat[(i + 1) * W + j + 1];
+      for (int k = 0; k < 4; k++) {
+        const int resetval = k != 0 ? xp : 0;
+        int ms, tmp;
+        int8_t t2;
+        if (db[j] == 15 || qr[k][i] == 15) ms = 0;
+        else ms = (db[j] == qr[k][i]) ? match : mismatch;
+        /* northwest :362-437 */
+        if (!revcmpl) {
+          tmp = cnw->nw[k] + ms; t2 = CSFROM(k, FR_NW_NW);
+          if (nt && cnw->n[k] + ms > tmp) { tmp = cnw->n[k] + ms; t2 = CSFROM(k, FR_NW_N); }
+          if (cnw->w[k] + ms > tmp) { tmp = cnw->w[k] + ms; t2 = CSFROM(k, FR_NW_W); }
+        } else {
+          tmp = cnw->w[k] + ms; t2 = CSFROM(k, FR_NW_W);
+          if (nt && cnw->n[k] + ms > tmp) { tmp = cnw->n[k] + ms; t2 = CSFROM(k, FR_NW_N); }
+          if (cnw->nw[k] + ms > tmp) { tmp = cnw->nw[k] + ms; t2 = CSFROM(k, FR_NW_NW); }
+        }
+        for (int l = 0; l < 4; l++) {
+          if (l == k) continue;
+          if (!revcmpl) {
+            if (cnw->nw[l] + ms + xp > tmp) { tmp = cnw->nw[l] + ms + xp; t2 = CSFROM(l, FR_NW_NW); }
+            if (nt && cnw->n[l] + ms + xp > tmp) { tmp = cnw->n[l] + ms + xp; t2 = CSFROM(l, FR_NW_N); }
+            if (cnw->w[l] + ms + xp > tmp) { tmp = cnw->w[l] + ms + xp; t2 = CSFROM(l, FR_NW_W); }
+          } else {
+            if (cnw->w[l] + ms + xp > tmp) { tmp = cnw->w[l] + ms + xp; t2 = CSFROM(l, FR_NW_W); }
+            if (nt && cnw->n[l] + ms + xp > tmp) { tmp = cnw->n[l] + ms + xp; t2 = CSFROM(l, FR_NW_N); }
+            if (cnw->nw[l] + ms + xp > tmp) { tmp = cnw->nw[l] + ms + xp; t2 = CSFROM(l, FR_NW_NW); }
+          }
+        }
+        if (tmp <= resetval && local) { tmp = resetval; t2 = 0; }
+        cur->nw[k] = tmp; cur->bnw[k] = t2;
+        /* north :447-501 */
+        if (!revcmpl) {
+          tmp = cn->nw[k] - bo - be; t2 = CSFROM(k, FR_N_NW);
+          if (!nt || cn->n[k] - be > tmp) { tmp = cn->n[k] - be; t2 = CSFROM(k, FR_N_N); }
+        } else {
+          tmp = cn->n[k] - be; t2 = CSFROM(k, FR_N_N);
+          if (nt && cn->nw[k] - bo - be > tmp) { tmp = cn->nw[k] - bo - be; t2 = CSFROM(k, FR_N_NW); }
+        }
+        for (int l = 0; l < 4; l++) {
+          if (l == k) continue;
+          if (!revcmpl) {
+            if (nt && cn->nw[l] - bo - be + xp > tmp) { tmp = cn->nw[l] - bo - be + xp; t2 = CSFROM(l, FR_N_NW); }
+            if (cn->n[l] - be + xp > tmp) { tmp = cn->n[l] - be + xp; t2 = CSFROM(l, FR_N_N); }
+          } else {
+            if (cn->n[l] - be + xp > tmp) { tmp = cn->n[l] - be + xp; t2 = CSFROM(l, FR_N_N); }
+            if (nt && cn->nw[l] - bo - be + xp > tmp) { tmp = cn->nw[l] - bo - be + xp; t2 = CSFROM(l, FR_N_NW); }
+          }
+        }
+        if (tmp <= resetval && local) { tmp = resetval; t2 = 0; }
+        cur->n[k] = tmp; cur->bn[k] = t2;
+        /* west :511-545: no crossover on a genomic gap */
+        if (!revcmpl) {
+          tmp = cw->nw[k] - ao - ae; t2 = CSFROM(k, FR_W_NW);
+          if (!nt || cw->w[k] - ae > tmp) { tmp = cw->w[k] - ae; t2 = CSFROM(k, FR_W_W); }
+        } else {
+          tmp = cw->w[k] - ae; t2 = CSFROM(k, FR_W_W);
+          if (nt && cw->nw[k] - ao - ae > tmp) { tmp = cw->nw[k] - ao - ae; t2 = CSFROM(k, FR_W_NW); }
+        }
+        if (tmp <= resetval && local) { tmp = resetval; t2 = 0; }
+        cur->w[k] = tmp; cur->bw[k] = t2;
+        /* max score :552-580 */
+        if (local || i == lenb - 1) {
+          if (!revcmpl) {
+            if (cur->nw[k] > score) { score = cur->nw[k]; max_i = i; max_j = j; max_k = k; }
+            if (cur->n[k] > score) { score = cur->n[k]; max_i = i; max_j = j; max_k = k; }
+            if (cur->w[k] > score) { score = cur->w[k]; max_i = i; max_j = j; max_k = k; }
+          } else {
+            if (cur->w[k] > score) { score = cur->w[k]; max_i = i; max_j = j; max_k = k; }
+            if (cur->n[k] > score) { score = cur->n[k]; max_i = i; max_j = j; max_k = k; }
+            if (cur->nw[k] > score) { score = cur->nw[k]; max_i = i; max_j = j; max_k = k; }
+          }
+        }
+      }
+    }
+    if (i + 1 < lenb) { /* :604-612, still with the crossover penalty of colour i */
+      int nmin, nmax;
+      o_anchor_x_range(&rect, lena, lenb, i + 1, &nmin, &nmax);
+      for (int j = x_max + 1; j <= nmax; j++) o_cs_init_cell(&mat[(i + 1) * W + (j + 1)], local, xp, bo, ao);
+    }
+  }
+  *iret = max_i; *jret = max_j; *kret = max_k;
+  return score;
+}
+
+void orc_sw_full_cs(const uint32_t *genome_ls, int goff, int glen, const uint32_t *read, int rlen, int initbp,
+                    int threshscore, int revcmpl, long long ax, long long ay, int alen, int awidth,
+                    int anchor_width, int indel_taboo_len, int local_alignment, const int *crossover_scores,
+                    const orc_scores *sc, orc_sfr *sfr, uint64_t *cells) {
+  int8_t *db = (int8_t *)malloc(glen);
+  int8_t *qr[4];
+  o_cscell *mat = (o_cscell *)malloc(sizeof(o_cscell) * (size_t)(glen + 1) * (rlen + 1));
+  uint8_t *bt = (uint8_t *)calloc(glen + rlen + 1, 1);
+  o_anchor a;
+  memset(&a, 0, sizeof(a));
+  a.x = ax; a.y = ay; a.length = alen; a.width = awidth; a.weight = 1;
+  for (size_t q = 0; q < (size_t)(glen + 1) * (rlen + 1); q++) o_cs_init_cell(&mat[q], 0, 0, 0, 0);
+  for (int i = 0; i < glen; i++) db[i] = (int8_t)EX4(genome_ls, goff + i);
+  for (int k = 0; k < 4; k++) { /* :1182-1196: layer k starts from letter (k + initbp) % 4 */
+    qr[k] = (int8_t *)malloc(rlen);
+    int letter = (k + initbp) % 4;
+    for (int j = 0; j < rlen; j++) {
+      int base = EX4(read, j);
+      if (base == 15) {
+        qr[k][j] = 15;
+        letter = (k + initbp) % 4;
+      } else {
+        /* cstols, util.h:157-180 */
+        int r = (letter == 15 || base > 3) ? 15 : ((letter % 2 == 0) ? (4 + letter + base) % 4 : (4 + letter - base) % 4);
+        qr[k][j] = (int8_t)r;
+        letter = r;
+      }
+    }
+  }
+  memset(sfr, 0, sizeof(*sfr));
+  int i, j, k;
+  sfr->score = o_full_sw_cs(mat, db, glen, qr, rlen, threshscore, &i, &j, &k, revcmpl, &a, anchor_width,
+                            local_alignment, crossover_scores, sc->crossover, indel_taboo_len, sc, cells);
+  if (sfr->score >= 0 && sfr->score >= threshscore) {
+    /* do_backtrace :633-937 */
+    const int W = glen + 1;
+    const int ie = i, je = j;
+    int off = (glen + rlen) - 1;
+    o_cscell *cell = &mat[(i + 1) * W + j + 1];
+    int from = cell->bnw[k], fromscore = cell->nw[k];
+    if (cell->w[k] > fromscore) { from = cell->bw[k]; fromscore = cell->w[k]; }
+    if (cell->n[k] > fromscore) from = cell->bn[k];
+    if (from != 0) {
+      while (i >= 0 && j >= 0) {
+        const int dir = from >> 2, lay = from & 3;
+        if (dir == FR_N_N || dir == FR_N_NW) {
+          sfr->deletions++; sfr->read_start = i--;
+          bt[off] = (uint8_t)(2 + k); /* BACK_A_DELETION + k */
+        } else if (dir == FR_W_W || dir == FR_W_NW) {
+          sfr->insertions++; sfr->genome_start = j--;
+          bt[off] = 1; /* BACK_INSERTION */
+        } else {
+          if (db[j] == qr[k][i] || db[j] == 15 || qr[k][i] == 15) sfr->matches++; else sfr->mismatches++;
+          sfr->read_start = i--; sfr->genome_start = j--;
+          bt[off] = (uint8_t)(6 + k); /* BACK_A_MATCH_MISMATCH + k */
+        }
+        if (k != lay) { bt[off] |= 0x80; sfr->crossovers++; k = lay; }
+        cell = &mat[(i + 1) * W + j + 1];
+        switch (dir) {
+          case FR_N_N: from = cell->bn[k]; break;
+          case FR_N_NW: from = cell->bnw[k]; break;
+          case FR_W_W: from = cell->bw[k]; break;
+          case FR_W_NW: from = cell->bnw[k]; break;
+          case FR_NW_N: from = cell->bn[k]; break;
+          case FR_NW_NW: from = cell->bnw[k]; break;
+          default: from = cell->bw[k]; break;
+        }
+        off--;
+        if (from == 0) break;
+      }
+    }
+    off++;
+    if (k != 0) { bt[off] |= 0x80; sfr->crossovers++; }
+    /* pretty_print :945-1060 */
+    {
+      char *d = sfr->dbalign, *q = sfr->qralign;
+      int ri = sfr->read_start, gj = sfr->genome_start, n = 0;
+      for (int l = off; l < glen + rlen && n < ORC_ALN_CAP - 1; l++, n++) {
+        const int ty = bt[l] & 0x0f, xo = bt[l] & 0x80;
+        if (ty >= 2 && ty <= 5) {
+          char c = o_ls_letters[qr[ty - 2][ri++] & 15];
+          *d++ = '-';
+          *q++ = xo ? (char)(c | 0x20) : c;
+        } else if (ty == 1) {
+          *d++ = o_ls_letters[db[gj++] & 15];
+          *q++ = '-';
+        } else if (ty >= 6 && ty <= 9) {
+          char c = o_ls_letters[qr[ty - 6][ri++] & 15];
+          *d++ = o_ls_letters[db[gj++] & 15];
+          *q++ = xo ? (char)(c | 0x20) : c;
+          if (*(q - 1) == 'n' || *(q - 1) == 'N') *(q - 1) = xo ? (char)(*(d - 1) | 0x20) : *(d - 1);
+        } else {
+          break;
+        }
+      }
+      *d = *q = 0;
+    }
+    sfr->gmapped = je - sfr->genome_start + 1;
+    sfr->genome_start += goff;
+    sfr->rmapped = ie - sfr->read_start + 1;
+  } else {
+    sfr->score = 0;
+  }
+  for (int q = 0; q < 4; q++) free(qr[q]);
+  free(db); free(mat); free(bt);
+}
+
 #include "oracle_pipeline.inc"

@@ -82,6 +82,11 @@ void orc_sw_full_ls(const uint32_t *genome, int goff, int glen, const uint32_t *
                     long long ax, long long ay, int alen, int awidth, int anchor_width,
                     int local_alignment, const orc_scores *sc, orc_sfr *out);
 
+void orc_sw_full_cs(const uint32_t *genome_ls, int goff, int glen, const uint32_t *read, int rlen, int initbp,
+                    int threshscore, int revcmpl, long long ax, long long ay, int alen, int awidth,
+                    int anchor_width, int indel_taboo_len, int local_alignment, const int *crossover_scores,
+                    const orc_scores *sc, orc_sfr *out, uint64_t *cells);
+
 /* ---------------------------------------------------------------------------------------------
  * The per-read pipeline (gmapper/mapping.c handle_read :1773 with the default unpaired option
  * set of gmapper.c:2601-2632)

@@ -51,9 +51,9 @@ def golden_mapping():
             case.write_fasta(d)
             sam = os.path.join(d, "out.sam")
             with open(sam, "w") as f:
-                subprocess.run([os.path.join(ref_dir, "gmapper-ls"), *spec["args"], "reads.fa", "genome.fa"], cwd=d,
+                subprocess.run([os.path.join(ref_dir, case.binary), *spec["args"], "reads.fa", "genome.fa"], cwd=d,
                                stdout=f, stderr=subprocess.DEVNULL, check=True)
-            dbg = subprocess.run([os.path.join(ref_dir, "dbgbin", "gmapper-ls"), *spec["args"], "reads.fa", "genome.fa"],
+            dbg = subprocess.run([os.path.join(ref_dir, "dbgbin", case.binary), *spec["args"], "reads.fa", "genome.fa"],
                                  cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, check=True, text=True).stderr
             recs = op.parse_sam(sam)
         name2idx = {n: i for i, n in enumerate(case.read_names)}
@@ -72,13 +72,49 @@ def golden_mapping():
                 m = pat.match(line)
                 if m:
                     v = list(map(int, m.groups()))
-                    stage.append((ridx, v[1], v[0], v[3], v[4], v[5], v[6], v[8], v[9], v[10], v[11], v[12]))
+                    st, ax, ay = v[1], v[9], v[10]
+                    if v[2] == 1:
+                        # colour-space pass 1 leaves strand-1 hits reversed (reverse_hit, mapping.c:254-263):
+                        # undo it so the fixture is in positive-strand terms (anchor_reverse is an involution)
+                        st = 1 - st
+                        ax = -ax + (v[4] - 1) - (v[11] - 1) - (v[12] - 1)
+                        ay = -ay + (int(case.read_len[ridx]) - 1) - (v[11] - 1) + (v[12] - 1)
+                    stage.append((ridx, st, v[0], v[3], v[4], v[5], v[6], v[8], ax, ay, v[11], v[12]))
         np.savez_compressed(os.path.join(HERE, f"map_{name}.npz"), sam=sam_int, cigars=cigars,
                             stage=np.array(stage, dtype=np.int64))
         print("wrote map", name, sam_int.shape, len(stage))
 
 
-TARGETS = {"sw_vector": golden_sw_vector, "mapping": golden_mapping}
+def golden_sw_full():
+    """sw_full_ls / sw_full_cs results of the REFERENCE objects on seeded random cases (global mode)."""
+    from fullcases import make_full_cases
+    from shrimp_b200.api import CS_DEFAULT_SCORES, LS_DEFAULT_SCORES
+    for colour in (False, True):
+        sc = CS_DEFAULT_SCORES if colour else LS_DEFAULT_SCORES
+        cases = make_full_cases(seed=500 + colour, n=400, colour=colour, rlen_range=(25, 60))
+        ref = oracle.RefFull(400, 200, sc, 8, colour=colour)
+        refv = oracle.RefSw(400, 200, sc, False)
+        ints, db, qr = [], [], []
+        for c in cases:
+            if colour:
+                thresh = int(c["rlen"] * sc.match * 0.4)
+                r = ref.sw_full_cs(c["genome"], c["goff"], c["glen"], c["read"], c["rlen"], c["initbp"], thresh,
+                                   c["revcmpl"], c["anchor"], 0, None)
+            else:
+                v = refv.sw_vector(c["genome"], c["goff"], c["glen"], c["read"], c["rlen"])
+                thresh = int(c["rlen"] * sc.match * 0.5)
+                if v < thresh:
+                    ints.append((0,) * 10); db.append(b""); qr.append(b"")
+                    continue
+                r = ref.sw_full_ls(c["genome"], c["goff"], c["glen"], c["read"], c["rlen"], thresh, v, c["revcmpl"],
+                                   c["anchor"], 0)
+            ints.append(r[:10]); db.append(r[10].split(b"\0")[0]); qr.append(r[11].split(b"\0")[0])
+        np.savez_compressed(os.path.join(HERE, f"sw_full_{'cs' if colour else 'ls'}.npz"),
+                            ints=np.array(ints, dtype=np.int64), db=np.array(db), qr=np.array(qr))
+        print("wrote sw_full", "cs" if colour else "ls", len(ints))
+
+
+TARGETS = {"sw_vector": golden_sw_vector, "mapping": golden_mapping, "sw_full": golden_sw_full}
 
 if __name__ == "__main__":
     assert oracle.have_ref(), "build oracle/_ref first: make -C oracle ref"

@@ -11,7 +11,7 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 import gen_synth  # noqa: E402
 
 from shrimp_b200 import seeds as S  # noqa: E402
-from shrimp_b200.api import LS_DEFAULT_SCORES, _LS_CODE, _pack_codes  # noqa: E402
+from shrimp_b200.api import CS_DEFAULT_SCORES, LS_DEFAULT_SCORES, _CS_CODE, _LS_CODE, _pack_codes  # noqa: E402
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -19,6 +19,8 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 MAP_CASES = {
     "c1_small": dict(gen="c1_small", args=[], opts={}),
     "c1_repeat": dict(gen="c1_repeat", args=[], opts={}),
+    # colour space: post_sw is not on the path yet, so parity runs with --no-mapping-qualities
+    "c2_small": dict(gen="c2_small", args=["--no-mapping-qualities"], opts={"compute_mapping_qualities": False}),
 }
 
 
@@ -26,16 +28,28 @@ class LsCase:
     def __init__(self, name: str):
         cfg = gen_synth.CONFIGS[MAP_CASES[name]["gen"]]
         self.name = name
+        self.colour = bool(cfg.get("colour"))
+        self.binary = "gmapper-cs" if self.colour else "gmapper-ls"
         self.contigs = gen_synth.make_genome(**cfg["genome"])
-        self.reads = gen_synth.simulate_reads(self.contigs, **cfg["reads"])
         self.contig_codes = [_LS_CODE[s] for _, s in self.contigs]
         self.contig_names = [n for n, _ in self.contigs]
+        if self.colour:
+            self.reads = gen_synth.simulate_cs_reads(self.contigs, **cfg["reads"])
+            seqs = [np.frombuffer(r[1], dtype=np.uint8) for r in self.reads]
+            self.read_len = np.array([s.size - 1 for s in seqs], dtype=np.int32)   # colours (gmapper.c:476)
+            self.initbp = np.array([_LS_CODE[s[0]] for s in seqs], dtype=np.int8)
+            self.stride = int((self.read_len.max() + 7) // 8)
+            self.packed = np.stack([_pack_codes(_CS_CODE[s[1:]].astype(np.uint32), self.stride) for s in seqs])
+            self.scores = CS_DEFAULT_SCORES
+        else:
+            self.reads = gen_synth.simulate_reads(self.contigs, **cfg["reads"])
+            self.read_len = np.array([r[1].size for r in self.reads], dtype=np.int32)
+            self.initbp = None
+            self.stride = int((self.read_len.max() + 7) // 8)
+            self.packed = np.stack([_pack_codes(_LS_CODE[r[1]].astype(np.uint32), self.stride) for r in self.reads])
+            self.scores = LS_DEFAULT_SCORES
         self.read_names = [r[0] for r in self.reads]
-        self.read_len = np.array([r[1].size for r in self.reads], dtype=np.int32)
-        self.stride = int((self.read_len.max() + 7) // 8)
-        self.packed = np.stack([_pack_codes(_LS_CODE[r[1]].astype(np.uint32), self.stride) for r in self.reads])
         self.seeds = S.load_default_seeds()
-        self.scores = LS_DEFAULT_SCORES
         self.total_len = int(sum(c.size for c in self.contig_codes))
 
     def write_fasta(self, d: str):

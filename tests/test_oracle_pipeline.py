@@ -11,18 +11,19 @@ from oracle import pipeline as op
 
 
 def run_oracle(case: LsCase, **over):
-    g = op.Genome(case.contig_codes, False)
+    g = op.Genome(case.contig_codes, case.colour)
     ix = op.Index(g, case.seeds)
-    opts = op.MapOptions(scores=case.scores, list_cutoff=op.auto_list_cutoff(g.total_len, max(s.weight for s in case.seeds)),
-                         **over)
-    hits, nper, stage, stats = op.map_reads(g, ix, opts, case.packed, case.read_len, want_stage=True)
+    opts = op.MapOptions(scores=case.scores, colour_space=case.colour,
+                         list_cutoff=op.auto_list_cutoff(g.total_len, max(s.weight for s in case.seeds)), **over)
+    hits, nper, stage, stats = op.map_reads(g, ix, opts, case.packed, case.read_len, initbp=case.initbp,
+                                            want_stage=True)
     return g, hits, nper, stage, stats
 
 
 def sam_arrays(case, g, hits):
     rows, cig = [], []
     for h in hits:
-        f = op.sam_fields(h, int(case.read_len[h["read_idx"]]), int(g.lens[h["cn"]]))
+        f = op.sam_fields(h, int(case.read_len[h["read_idx"]]), int(g.lens[h["cn"]]), case.colour)
         rows.append([int(h["read_idx"]), f[0], f[1], f[2], f[4], f[5]])
         cig.append(f[3])
     return np.array(rows, dtype=np.int64).reshape(-1, 6), np.array(cig)

@@ -155,6 +155,8 @@ CONFIGS = {
     "c1_repeat": dict(genome=dict(total_len=300_000, n_contigs=2, seed=13, repeat_unit=3000,
                                   repeat_copies=40, repeat_div=0.03),
                       reads=dict(n_reads=2_000, read_len=50, seed=14, sub=0.02)),
+    "c2_small": dict(genome=dict(total_len=200_000, n_contigs=2, seed=17, n_frac=0.002),
+                     reads=dict(n_reads=1_500, read_len=36, seed=18, snp_p=0.3, col_err=0.03), colour=True),
     "c5_small": dict(genome=dict(total_len=200_000, n_contigs=1, seed=15),
                      reads=dict(n_reads=500, read_len=75, seed=16, sub=0.04, indel_p=0.5, max_indel=5)),
 }
@@ -172,7 +174,8 @@ def main():
     rk = dict(cfg["reads"])
     if a.n_reads:
         rk["n_reads"] = a.n_reads
-    reads = simulate_reads(contigs, **rk)
+    rk.pop("colour", None)
+    reads = (simulate_cs_reads if cfg.get("colour") else simulate_reads)(contigs, **rk)
     write_fasta(os.path.join(a.outdir, "genome.fa"), contigs, width=80)
     write_fasta(os.path.join(a.outdir, "reads.fa"), reads)
 
