@@ -55,7 +55,8 @@ void         shrimp_gpu_stage_times_reset(shrimp_gpu_ctx *ctx);
  * ---------------------------------------------------------------------------------------- */
 typedef struct shrimp_sw_params {
   int match;            /* > 0 */
-  int mismatch;         /* < 0; colour space: match + crossover, as gmapper.c:2935 passes it */
+  int mismatch;         /* < 0: mismatch_score as sw_full_*_setup get it.  In colour space the vector
+                           filter scores a colour mismatch as match + crossover (gmapper.c:2935). */
   int a_gap_open;       /* <= 0, gap that consumes genome ("a", SAM D) */
   int a_gap_ext;
   int b_gap_open;       /* <= 0, gap that consumes read ("b", SAM I) */
@@ -146,8 +147,10 @@ typedef struct shrimp_map_params {
 /* One reported alignment: read_hit + sw_full_results (gmapper-definitions.h:125-153,
  * sw-full-common.h:13-48).  The alignment itself is an edit script in `edits`: one byte per
  * alignment column, the reference's backtrace codes (sw-full-ls.c:44-46) -- 1 BACK_INSERTION
- * (genome base against '-'), 2 BACK_DELETION (read base against '-'), 3 BACK_MATCH_MISMATCH;
- * colour space adds 4 when the column carries a crossover.  dbalign/qralign follow from it. */
+ * (genome base against '-'), 2 BACK_DELETION (read base against '-'), 3 BACK_MATCH_MISMATCH in
+ * bits 0-1; colour space sets bit 2 when the column carries a crossover and bits 4-5 to the layer
+ * (letter-space translation starting from (layer + initbp) % 4, sw-full-cs.c:1181-1196) whose
+ * letter pretty_print shows.  dbalign/qralign follow from it. */
 typedef struct shrimp_hit {
   int32_t read_idx, cn, gen_st, w_len;
   int64_t g_off;                /* rh->g_off, in the orientation of gen_st */

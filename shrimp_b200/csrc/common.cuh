@@ -99,7 +99,8 @@ struct StageTimer {
 
 // positive-sign score block used by the kernels
 struct SwScores {
-  int match, mismatch;      // mismatch < 0
+  int match, mismatch;      // mismatch < 0 (full SW)
+  int vec_mismatch;         // what the vector filter uses: colour space = match + crossover (gmapper.c:2935)
   int a_open, a_ext;        // >= 0 (negated CLI values, sw-vector.c:422-425)
   int b_open, b_ext;
   int xover;                // < 0

@@ -123,6 +123,7 @@ extern "C" int shrimp_gpu_sw_setup(shrimp_gpu_ctx *c, const shrimp_sw_params *p)
   SwScores s;
   s.match = p->match;
   s.mismatch = p->mismatch;
+  s.vec_mismatch = p->use_colours ? p->match + p->crossover : p->mismatch;
   s.a_open = -p->a_gap_open;
   s.a_ext = -p->a_gap_ext;
   s.b_open = -p->b_gap_open;
@@ -135,7 +136,11 @@ extern "C" int shrimp_gpu_sw_setup(shrimp_gpu_ctx *c, const shrimp_sw_params *p)
   s.max_window_len = p->max_window_len;
   // smallest shift with 2^shift > match - mismatch; 5-bit codes << shift must stay below 2^15
   int sh = 1;
-  while ((1 << sh) <= p->match - p->mismatch) sh++;
+  if (s.vec_mismatch >= 0) {
+    set_error("shrimp_gpu_sw_setup: colour space needs match + crossover < 0");
+    return SHRIMP_E_ARG;
+  }
+  while ((1 << sh) <= p->match - s.vec_mismatch) sh++;
   if (sh > 9 || s.a_open + s.a_ext >= 16384 || s.b_open + s.b_ext >= 16384) {
     set_error("shrimp_gpu_sw_setup: |match - mismatch| or gap scores too large for the packed int16 kernel");
     return SHRIMP_E_RANGE;

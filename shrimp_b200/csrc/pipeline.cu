@@ -20,6 +20,7 @@ int launch_scan(shrimp_gpu_ctx *ctx, ScanParams &P, int warps_per_cta, int n_cta
 int launch_build_vec_tasks(shrimp_gpu_ctx *ctx, const TaskBuildParams &P);
 int launch_pass1_select(shrimp_gpu_ctx *ctx, const Pass1Params &P);
 int launch_sw_full_ls(shrimp_gpu_ctx *ctx, const FullParams &P);
+int launch_sw_full_cs(shrimp_gpu_ctx *ctx, const FullParams &P);
 
 __constant__ uint8_t c_cmpl_r[16] = {3, 2, 1, 0, 0, 10, 9, 7, 8, 6, 5, 14, 13, 12, 11, 15};
 
@@ -74,6 +75,7 @@ struct FullBuildParams {
   const int32_t *sel;
   const int32_t *n_sel;
   const int32_t *vtrue0;
+  const int8_t *initbp;
   const int32_t *task_off;  // exclusive prefix sum of n_sel: tasks of read r start at task_off[r]
   int n_reads;
   FullTask *tasks;   // [sum n_sel], dense
@@ -125,6 +127,7 @@ __global__ void build_full_tasks_kernel(const FullBuildParams P) {
     } else {
       T.maxscore = h.score_vector;
       T.run = 1;
+      T.initbp = P.initbp[r];
     }
     I.hit_slot = hi;
     I.read_idx = r;
@@ -268,8 +271,10 @@ static int map_impl(shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, int n_read
     set_error("shrimp_gpu_map_reads: gapless (-U / mirna) pass 1 is not wired into the chunk pipeline yet");
     return SHRIMP_E_ARG;
   }
-  if (cs) {
-    set_error("shrimp_gpu_map_reads: colour-space pass 2 (sw_full_cs) is not on the device yet");
+  if (cs && mp->compute_mapping_qualities) {
+    // hit_run_post_sw needs post_sw (common/sw-post.c), which is not on this path yet
+    set_error("shrimp_gpu_map_reads: colour space needs compute_mapping_qualities = 0 (--no-mapping-qualities) "
+              "until post_sw is implemented");
     return SHRIMP_E_ARG;
   }
   if (mp->match_mode != 1 && mp->match_mode != 2) {
@@ -614,6 +619,7 @@ static int map_impl(shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, int n_read
     FB.sel = pl->d_sel.as<int32_t>();
     FB.n_sel = pl->d_nsel.as<int32_t>();
     FB.vtrue0 = pl->d_vtrue[0].as<int32_t>();
+    FB.initbp = cs ? pl->d_initbp.as<int8_t>() : nullptr;
     FB.task_off = pl->d_taskoff.as<int32_t>();
     FB.n_reads = n_reads;
     FB.tasks = pl->d_ftasks.as<FullTask>();
@@ -623,11 +629,12 @@ static int map_impl(shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, int n_read
     SH_LAUNCHED(ctx, ST_FULL);
 
     // sub-batches sized for ~2 GB of DP scratch
-    const size_t per_task = (size_t)3 * (max_wl + 1) * 4 + (size_t)max_rl * max_wl + ops_stride;
+    const size_t states = cs ? 12 : 3;
+    const size_t per_task = states * (max_wl + 1) * 4 + (size_t)max_rl * max_wl * (cs ? 12 : 1) + ops_stride;
     int batch = (int)std::min<size_t>((size_t)std::max(n_slots, 1), std::max<size_t>(1024, ((size_t)2 << 30) / per_task));
     batch = (batch + 127) & ~127;
-    SH_TRY(pl->d_frow.ensure((size_t)3 * (max_wl + 1) * 4 * batch));
-    SH_TRY(pl->d_fbp.ensure((size_t)max_rl * max_wl * batch));
+    SH_TRY(pl->d_frow.ensure(states * (max_wl + 1) * 4 * batch));
+    SH_TRY(pl->d_fbp.ensure((size_t)max_rl * max_wl * (cs ? 12 : 1) * batch));
     SH_TRY(pl->d_fops.ensure(ops_stride * (size_t)std::max(n_slots, 1)));
     for (int b0 = 0; b0 < n_slots; b0 += batch) {
       FullParams FP;
@@ -655,7 +662,15 @@ static int map_impl(shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, int n_read
       FP.Tflag = mp->Tflag;
       FP.local = mp->Gflag ? 0 : 1;
       FP.cells = (unsigned long long *)(cnt + 16);
-      SH_TRY(launch_sw_full_ls(ctx, FP));
+      FP.xover = sw.xover;
+      FP.indel_taboo_len = sw.indel_taboo_len;
+      FP.row_cs = pl->d_frow.as<int32_t>();
+      FP.bp_cs = pl->d_fbp.as<uint8_t>();
+      if (cs) {
+        SH_TRY(launch_sw_full_cs(ctx, FP));
+      } else {
+        SH_TRY(launch_sw_full_ls(ctx, FP));
+      }
     }
   }
 

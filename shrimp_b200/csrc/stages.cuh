@@ -86,6 +86,7 @@ struct FullTask {
   int32_t thresh, maxscore;
   int32_t gen_st;        // 0 forward genome, 1 reverse-complement genome
   int32_t run;           // 0: below threshold, result score = 0 without DP (mapping.c:390-398)
+  int32_t initbp;        // colour space: initial base of the read
 };
 
 struct FullResult {
@@ -110,6 +111,10 @@ struct FullParams {
   int match, mismatch, a_open, a_ext, b_open, b_ext;
   int anchor_width, Tflag, local;
   unsigned long long *cells;
+  // colour space (sw_full_cs.cu)
+  int xover, indel_taboo_len;
+  int32_t *row_cs;  // [12][max_glen+1][NT]
+  uint8_t *bp_cs;   // [max_rlen*max_glen*12][NT]
 };
 
 }  // namespace shrimp

@@ -12,51 +12,13 @@
 //   bp[rlen*glen][NT]   one byte of back-pointers per cell (2 bits per state)
 //   ops[NT][rlen+glen]  edit script per task, filled from the end like the reference's backtrace buffer
 // The reference keeps a full (dblen+1)x(qrlen+1) matrix of 16-byte cells per thread.
-#include "stages.cuh"
+#include "band.cuh"
 
 namespace shrimp {
 
-#define NEG_HALF (-1073741823)  // -INT_MAX/2, init_cell :66-81
 
 
 
-
-struct Rect {
-  long long x, y;
-  int length, width;
-};
-
-__device__ __forceinline__ void rect_x_range(const Rect &a, int x_len, int y, int &x_min, int &x_max) {
-  // anchor_get_x_range, anchors.c:66-95
-  if (y < a.y) x_min = 0;
-  else if (y <= a.y + (a.length - 1)) x_min = (int)(a.x + (y - a.y));
-  else x_min = (int)(a.x + a.length);
-  if (x_min < 0) x_min = 0;
-  if (x_min >= x_len) x_min = x_len - 1;
-  if (y < a.y - (a.width - 1)) x_max = (int)(a.x + (a.width - 1) - 1);
-  else if (y <= a.y - (a.width - 1) + (a.length - 1)) x_max = (int)(a.x + (a.width - 1) + (y - (a.y - (a.width - 1))));
-  else x_max = x_len - 1;
-  if (x_max < 0) x_max = 0;
-  if (x_max >= x_len) x_max = x_len - 1;
-}
-
-__device__ __forceinline__ Rect rect_join2(long long x0, long long y0, int l0, int w0, long long x1, long long y1,
-                                           int l1, int w1) {
-  // anchor_join, anchors.c:9-54
-  long long nw0 = x0 + y0, sw0 = x0 - y0, ne0 = sw0 + 2 * (w0 - 1), se0 = nw0 + 2 * (l0 - 1);
-  long long nw1 = x1 + y1, sw1 = x1 - y1, ne1 = sw1 + 2 * (w1 - 1), se1 = nw1 + 2 * (l1 - 1);
-  long long nw_min = nw0 < nw1 ? nw0 : nw1, sw_min = sw0 < sw1 ? sw0 : sw1;
-  long long ne_max = ne0 > ne1 ? ne0 : ne1, se_max = se0 > se1 ? se0 : se1;
-  Rect r;
-  if ((nw_min + sw_min) % 2 != 0) nw_min--;
-  r.x = (nw_min + sw_min) / 2;
-  r.y = nw_min - r.x;
-  if ((ne_max - sw_min) % 2 != 0) ne_max++;
-  r.width = (int)((ne_max - sw_min) / 2 + 1);
-  if ((se_max - nw_min) % 2 != 0) se_max++;
-  r.length = (int)((se_max - nw_min) / 2 + 1);
-  return r;
-}
 
 // back-pointer byte: bits 0-1 northwest state (0 none, 1 from north, 2 from northwest, 3 from west),
 // bits 2-3 north state (0 none, 1 N<-N, 2 N<-NW), bits 4-5 west state (0 none, 1 W<-NW, 2 W<-W)

@@ -245,7 +245,7 @@ int launch_sw_vector(shrimp_gpu_ctx *ctx, const uint32_t *d_genome, const uint32
   }
   auto pk = [](int v) { return ((uint32_t)v & 0xffffu) * 0x10001u; };
   P.ma1 = pk(s.match + 1);
-  P.mm = pk(s.mismatch);
+  P.mm = pk(s.vec_mismatch);
   P.naoe = pk(-(s.a_open + s.a_ext));
   P.nae = pk(-s.a_ext);
   P.nboe = pk(-(s.b_open + s.b_ext));

@@ -13,18 +13,19 @@ pytestmark = pytest.mark.gpu
 
 
 def run_gpu(ctx, case, **over):
-    ctx.sw_setup(1400, 1000, case.scores, use_colours=False, anchor_width=8)
-    ctx.load_genome([_pack_codes(c.astype(np.uint32)) for c in case.contig_codes], [c.size for c in case.contig_codes])
+    ctx.sw_setup(1400, 1000, case.scores, use_colours=case.colour, anchor_width=8)
+    ctx.load_genome([_pack_codes(c.astype(np.uint32)) for c in case.contig_codes], [c.size for c in case.contig_codes],
+                    colour_space=case.colour)
     ctx.build_index(case.seeds)
     params = MapParams(list_cutoff=auto_list_cutoff(case.total_len, max(s.weight for s in case.seeds)), **over)
-    return ctx.map_reads(params, case.scores, case.packed, case.read_len, want_stage=True)
+    return ctx.map_reads(params, case.scores, case.packed, case.read_len, initbp=case.initbp, want_stage=True)
 
 
 def sam_arrays(case, res):
     rows, cig = [], []
     for h in res.hits:
         e = res.edits[int(h["edit_off"]): int(h["edit_off"]) + int(h["edit_len"])]
-        f = align.sam_fields(h, e, int(case.read_len[h["read_idx"]]), int(case.contig_codes[h["cn"]].size))
+        f = align.sam_fields(h, e, int(case.read_len[h["read_idx"]]), int(case.contig_codes[h["cn"]].size), case.colour)
         rows.append([int(h["read_idx"]), f[0], f[1], f[2], f[4], f[5]])
         cig.append(f[3])
     return np.array(rows, dtype=np.int64).reshape(-1, 6), np.array(cig)
