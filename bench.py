@@ -4,9 +4,9 @@
     python bench.py --gpus N --steps K --warmup W            # this repo (CUDA)
     python bench.py --impl reference --gpus N --steps K ...  # the reference gmapper on the host cores
 
-A step is one pass of the whole hot path (seed scan -> sw_vector -> pass-1 replay -> sw_full_ls) over
-one batch of simulated reads against the HBM-resident index.  Workload: BASELINE.json configs[0]
-shape (letter space, 100 k x 50 bp reads, 2 % substitutions, vs an iid 10 Mb genome, default seeds).
+A step is one pass of the whole hot path (seed scan -> sw_vector -> pass-1 replay -> sw_full_{ls,cs})
+over one batch of simulated reads against the HBM-resident index.  Default workload: BASELINE.json
+configs[1] (colour space, 36-colour reads vs an iid 100 Mb genome); --workload c1 = configs[0].
 Under torchrun every rank maps its own batch (weak scaling, no collective on the data path).
 Prints ONE JSON line on rank 0.
 """
@@ -28,25 +28,90 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 
-READ_LEN = 50
-GENOME_LEN = 10_000_000
-WORKLOAD = "C1 letter-space: 100k x 50bp reads (2% subs) vs iid 10 Mb genome, 3 default seeds w12"
+CMPL = np.array([3, 2, 1, 0], dtype=np.uint8)
+# integer-pipe instructions per band cell of the full-SW kernels (counted from SASS)
+FULL_INSTR_PER_CELL = {"ls": 30.0, "cs": 220.0}
 
 
-# -------------------------------------------------------------------------------------------------
-# synthetic workload (vectorised; same distribution as tools/gen_synth.py config c1)
-# -------------------------------------------------------------------------------------------------
+class Workload:
+    """Seeded synthetic genome + simulated reads of one BASELINE.json config."""
+
+    def __init__(self, key, desc, colour, read_len, contig_len, n_contigs, seed_genome, default_reads, binary, args):
+        self.key, self.desc, self.colour, self.read_len = key, desc, colour, read_len
+        self.contig_len, self.n_contigs, self.seed_genome = contig_len, n_contigs, seed_genome
+        self.genome_len = contig_len * n_contigs
+        self.default_reads, self.binary, self.args = default_reads, binary, args
+        self._genome = None
+
+    def genome(self):
+        if self._genome is None:
+            rng = np.random.default_rng(self.seed_genome)
+            self._genome = rng.integers(0, 4, size=self.genome_len, dtype=np.uint8)
+        return self._genome
+
+    def contig_names(self):
+        return [f"contig{i}" for i in range(self.n_contigs)]
+
+    def contigs(self):
+        g = self.genome()
+        return [g[i * self.contig_len:(i + 1) * self.contig_len] for i in range(self.n_contigs)]
+
+    def reads(self, n_reads, seed):
+        """-> (codes [n, read_len] uint8 (letters, or colours in colour space), initbp or None)"""
+        g, rl = self.genome(), self.read_len
+        rr = np.random.default_rng(seed)
+        cn = rr.integers(0, self.n_contigs, size=n_reads)
+        pos = cn * self.contig_len + rr.integers(0, self.contig_len - rl, size=n_reads)
+        frag = g[pos[:, None] + np.arange(rl)[None, :]].copy()
+        if not self.colour:      # C1: 2 % substitutions
+            sub = rr.random(frag.shape) < 0.02
+            frag[sub] = (frag[sub] + rr.integers(1, 4, size=int(sub.sum()))) % 4
+        else:                    # C2: one SNP in 30 % of the reads
+            snp = np.nonzero(rr.random(n_reads) < 0.3)[0]
+            p = rr.integers(0, rl, size=snp.size)
+            frag[snp, p] = (frag[snp, p] + rr.integers(1, 4, size=snp.size)) % 4
+        rc = rr.random(n_reads) < 0.5
+        frag[rc] = CMPL[frag[rc]][:, ::-1]
+        if not self.colour:
+            return frag, None
+        prev = np.concatenate([np.full((n_reads, 1), 3, dtype=np.uint8), frag[:, :-1]], axis=1)  # primer base T
+        col = frag ^ prev
+        err = rr.random(col.shape) < 0.03    # 3 % colour errors
+        col[err] = (col[err] + rr.integers(1, 4, size=int(err.sum()))) % 4
+        return col, np.full(n_reads, 3, dtype=np.int8)
+
+    def write_reads_fasta(self, path, codes):
+        lut = np.frombuffer(b"0123" if self.colour else b"ACGT", dtype=np.uint8)
+        body = lut[codes]
+        with open(path, "wb") as f:
+            for i in range(body.shape[0]):
+                f.write(b">r%d\n" % i + (b"T" if self.colour else b"") + body[i].tobytes() + b"\n")
+
+    def write_genome_fasta(self, path):
+        lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+        with open(path, "wb") as f:
+            for nm, c in zip(self.contig_names(), self.contigs()):
+                f.write(b">" + nm.encode() + b"\n" + lut[c].tobytes() + b"\n")
+
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: the configuration the metric is quoted on that fits one GPU.  post_sw (colour-space
+    # mapping qualities, SURVEY 8 f1) is not on the path yet, so both arms run with --no-mapping-qualities.
+    "c2": Workload("c2", "C2 colour-space: 36-colour SOLiD reads (SNP in 30%, 3% colour errors) vs iid 100 Mb genome "
+                   "in 10 contigs, 3 default seeds w12, sw_full_cs crossovers, --no-mapping-qualities; one step = "
+                   "one batch of the 10 M-read job", True, 36, 10_000_000, 10, 3, 1_000_000, "gmapper-cs",
+                   ["--no-mapping-qualities"]),
+    # BASELINE.json configs[0]: the reference's own CPU-runnable case
+    "c1": Workload("c1", "C1 letter-space: 100k x 50bp reads (2% subs) vs iid 10 Mb genome, 3 default seeds w12",
+                   False, 50, 10_000_000, 1, 1, 100_000, "gmapper-ls", []),
+}
+
+
 def make_workload(n_reads: int, seed_genome: int = 1, seed_reads: int = 2):
-    rng = np.random.default_rng(seed_genome)
-    genome = rng.integers(0, 4, size=GENOME_LEN, dtype=np.uint8)
-    rr = np.random.default_rng(seed_reads)
-    pos = rr.integers(0, GENOME_LEN - READ_LEN, size=n_reads)
-    reads = genome[pos[:, None] + np.arange(READ_LEN)[None, :]].copy()
-    sub = rr.random(reads.shape) < 0.02
-    reads[sub] = (reads[sub] + rr.integers(1, 4, size=int(sub.sum()))) % 4
-    rc = rr.random(n_reads) < 0.5
-    reads[rc] = (3 - reads[rc])[:, ::-1]
-    return genome, reads, pos, rc
+    """C1 inputs as (genome codes, read codes, None, None) -- kept for tests/test_gpu_pipeline.py"""
+    w = WORKLOADS["c1"]
+    codes, _ = w.reads(n_reads, seed_reads)
+    return w.genome(), codes, None, None
 
 
 def pack_rows(codes: np.ndarray) -> np.ndarray:
@@ -112,18 +177,14 @@ class ClockSampler:
 
 
 # -------------------------------------------------------------------------------------------------
-# the reference's own CPU implementation (oracle/_ref/gmapper, compiled from /root/reference)
+# the reference's own CPU implementation (oracle/_ref/gmapper-{ls,cs}, compiled from /root/reference)
 # -------------------------------------------------------------------------------------------------
-REF_BIN = os.path.join(ROOT, "oracle", "_ref", "gmapper-ls")
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
 
 
-def run_reference(workdir: str, n_threads: int, reads_fa: str, prefix: str | None, genome_fa: str):
-    """returns (reads/s over 'Read Mapping Time', vector GCUPS aggregate, seconds)"""
-    cmd = [REF_BIN, "-N", str(n_threads)]
-    if prefix:
-        cmd += ["-L", prefix, reads_fa]
-    else:
-        cmd += [reads_fa, genome_fa]
+def run_reference(w: Workload, workdir: str, n_threads: int, reads_fa: str, prefix: str):
+    """returns (seconds of 'Read Mapping Time', vector GCUPS aggregate, wall seconds)"""
+    cmd = [os.path.join(REF_DIR, w.binary), "-N", str(n_threads), *w.args, "-L", prefix, reads_fa]
     t0 = time.time()
     r = subprocess.run(cmd, cwd=workdir, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
     wall = time.time() - t0
@@ -139,14 +200,35 @@ def run_reference(workdir: str, n_threads: int, reads_fa: str, prefix: str | Non
     return map_s, gcups, wall
 
 
-def reference_setup(workdir, genome, reads_codes):
-    write_fasta(os.path.join(workdir, "genome.fa"), ["contig0"], [genome])
-    write_fasta(os.path.join(workdir, "reads.fa"), [f"r{i}" for i in range(len(reads_codes))], reads_codes)
-    # project once (gmapper -S), so timed runs load the projection instead of rebuilding it
-    r = subprocess.run([REF_BIN, "-S", "proj", "genome.fa"], cwd=workdir, stdout=subprocess.DEVNULL,
-                       stderr=subprocess.PIPE, text=True)
+def reference_setup(w: Workload, workdir: str, reads_codes, ctx=None):
+    """reads.fa + the projection files `proj.*` that the timed runs load with -L (the reference's
+    "Read Mapping Time" excludes loading).  With a GPU context the projection held in HBM is saved in the
+    -S format (shrimp_gpu_projection_save; tests/test_gpu_index.py checks the files byte for byte against
+    `gmapper -S`); without one the reference projects the genome itself (minutes at 100 Mb)."""
+    w.write_reads_fasta(os.path.join(workdir, "reads.fa"), reads_codes)
+    if ctx is not None:
+        ctx.save_projection(os.path.join(workdir, "proj"), w.contig_names())
+        return "projection saved from HBM in the -S format"
+    w.write_genome_fasta(os.path.join(workdir, "genome.fa"))
+    r = subprocess.run([os.path.join(REF_DIR, w.binary), "-S", "proj", "genome.fa"], cwd=workdir,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
     if r.returncode != 0:
         raise RuntimeError("reference gmapper -S failed: " + r.stderr[-500:])
+    return "projection built by gmapper -S"
+
+
+def build_context(w: Workload, device: int):
+    import shrimp_b200
+    from shrimp_b200 import seeds as S
+    ctx = shrimp_b200.GpuContext(device)
+    scores = shrimp_b200.CS_DEFAULT_SCORES if w.colour else shrimp_b200.LS_DEFAULT_SCORES
+    seeds = S.load_default_seeds()
+    ctx.sw_setup(1400, 1000, scores, use_colours=w.colour)  # dblen/qrlen as gmapper sets them up (longest_read_len 1000)
+    t0 = time.time()
+    ctx.load_genome([shrimp_b200.api._pack_codes(c.astype(np.uint32)) for c in w.contigs()],
+                    [w.contig_len] * w.n_contigs, colour_space=w.colour)
+    ctx.build_index(seeds)
+    return ctx, scores, seeds, time.time() - t0
 
 
 def main():
@@ -155,38 +237,52 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--reads", type=int, default=100_000, help="reads per GPU per step")
-    ap.add_argument("--cpu-sample", type=int, default=100_000, help="reads in the cpu_baseline sample")
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--reads", type=int, default=0, help="reads per GPU per step (0 = the workload's default)")
+    ap.add_argument("--cpu-sample", type=int, default=200_000, help="reads in the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     ncores = os.cpu_count() or 1
+    w = WORKLOADS[a.workload]
+    n_reads = a.reads or w.default_reads
+    ref_bin = os.path.join(REF_DIR, w.binary)
 
     if a.impl == "reference":
         if rank != 0:
             return 0
-        genome, reads, _, _ = make_workload(a.cpu_sample)
+        sample, _ = w.reads(a.cpu_sample, 1000)
+        ctx = None
+        try:
+            import torch
+            if torch.cuda.is_available():
+                ctx = build_context(w, 0)[0]
+        except Exception:  # noqa: BLE001
+            ctx = None
         with tempfile.TemporaryDirectory() as d:
-            reference_setup(d, genome, reads)
+            how = reference_setup(w, d, sample, ctx)
+            if ctx is not None:
+                ctx.close()
             for _ in range(min(a.warmup, 1)):
-                run_reference(d, ncores, "reads.fa", "proj", "genome.fa")
+                run_reference(w, d, ncores, "reads.fa", "proj")
             secs, gc = [], []
             for _ in range(a.steps):
-                s, g, _ = run_reference(d, ncores, "reads.fa", "proj", "genome.fa")
+                s, g, _ = run_reference(w, d, ncores, "reads.fa", "proj")
                 secs.append(s)
                 gc.append(g)
         tot = sum(secs)
         val = a.cpu_sample * a.steps / tot
-        sample = f"{a.cpu_sample} reads of the C1 workload per step, gmapper-ls -N {ncores} -L <projection>"
+        sample_s = (f"{a.cpu_sample} reads of the {w.key.upper()} workload per step, {w.binary} -N {ncores} "
+                    f"{' '.join(w.args)} -L <projection> (Read Mapping Time); {how}")
         line = {"impl": "reference", "metric": "reads_per_sec_mapped", "value": val, "unit": "reads/s",
                 "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * tot / a.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16",
-                "data": "synthetic", "config": {"workload": WORKLOAD, "reads_per_step": a.cpu_sample},
+                "data": "synthetic", "config": {"workload": w.desc, "reads_per_step": a.cpu_sample},
                 "sw_vector_gcups": gc[-1],
                 "cpu_baseline": {"value": val, "unit": "reads/s", "cores": ncores, "kind": "reference",
-                                 "sample": sample},
+                                 "sample": sample_s},
                 "e2e": {"value": val, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return 0
@@ -194,29 +290,20 @@ def main():
     import torch
     import torch.distributed as dist
 
-    import shrimp_b200
-    from shrimp_b200 import seeds as S
     from shrimp_b200.api import MapParams, auto_list_cutoff
 
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
 
-    genome, reads, _, _ = make_workload(a.reads, seed_reads=2 + rank)
-    packed_np = pack_rows(reads)
+    codes, initbp_np = w.reads(n_reads, 2 + rank)
     # pinned host buffers for the end-to-end leg
-    packed = torch.from_numpy(packed_np).pin_memory().numpy()
-    read_len = torch.full((a.reads,), READ_LEN, dtype=torch.int32).pin_memory().numpy()
+    packed = torch.from_numpy(pack_rows(codes)).pin_memory().numpy()
+    read_len = torch.full((n_reads,), w.read_len, dtype=torch.int32).pin_memory().numpy()
+    initbp = torch.from_numpy(initbp_np).pin_memory().numpy() if initbp_np is not None else None
 
-    ctx = shrimp_b200.GpuContext(local_rank)
-    scores = shrimp_b200.LS_DEFAULT_SCORES
-    seeds = S.load_default_seeds()
-    ctx.sw_setup(1400, 1000, scores)  # dblen/qrlen as gmapper sets them up (longest_read_len 1000, window 140%)
-    t0 = time.time()
-    ctx.load_genome([shrimp_b200.api._pack_codes(genome.astype(np.uint32))], [GENOME_LEN])
-    ctx.build_index(seeds)
-    index_s = time.time() - t0
-    params = MapParams(list_cutoff=auto_list_cutoff(GENOME_LEN, 12))
+    ctx, scores, seeds, index_s = build_context(w, local_rank)
+    params = MapParams(list_cutoff=auto_list_cutoff(w.genome_len, 12), compute_mapping_qualities=not w.colour)
 
     def barrier():
         if world > 1:
@@ -224,7 +311,7 @@ def main():
         torch.cuda.synchronize()
 
     # first call uploads the batch and leaves it resident; also the e2e path's warm-up
-    res = ctx.map_reads(params, scores, packed, read_len)
+    res = ctx.map_reads(params, scores, packed, read_len, initbp=initbp)
     n_mapped = int((res.n_hits_per_read > 0).sum())
     for _ in range(a.warmup):
         ctx.map_resident(params, scores)
@@ -251,20 +338,20 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms_max = float(t.item())
-    value = world * a.reads * a.steps / (total_ms_max * 1e-3)
+    value = world * n_reads * a.steps / (total_ms_max * 1e-3)
 
     # ---- end to end through the public API: pinned host buffers in, hits out -----------------------
     barrier()
     t0 = time.perf_counter()
     for _ in range(a.steps):
-        res = ctx.map_reads(params, scores, packed, read_len)
+        res = ctx.map_reads(params, scores, packed, read_len, initbp=initbp)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     h2d, d2h = ctx.last_transfer_bytes()
     t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_val = world * a.reads * a.steps / float(t.item())
+    e2e_val = world * n_reads * a.steps / float(t.item())
 
     if rank != 0:
         if world > 1:
@@ -281,39 +368,51 @@ def main():
     peak_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
     vec_ms = stage["sw_vector"][0] / a.steps
     scan_ms = stage["seed_scan"][0] / a.steps
+    full_ms = stage["sw_full"][0] / a.steps
     # sw_vector: every window the device scores (a superset of the reference's calls), 4 integer-pipe
     # instructions per cell (8 per packed pair of cells), against the measured VIADDMNMX.S16x2 peak
     dev_cells = st["device_vector_cells"]
     vec_gcups = dev_cells / (vec_ms * 1e-3) / 1e9 if vec_ms > 0 else 0.0
     vec_ginstr = vec_gcups * 4.0
-    # seed scan: algorithmic bytes = packed read + 2 table words per k-mer (x2: count and gather passes
-    # recompute the bucket) + 4 B per gathered list entry + 48 B per hit written
-    kmers = 2 * a.reads * sum(READ_LEN - s.span + 1 for s in seeds)
-    scan_bytes = 2 * a.reads * 28 + kmers * 8 * 2 + st["list_entries"] * 4 + st["hits"] * 48
+    # seed scan: algorithmic bytes = packed read (both strands) + 2 table words per k-mer + 4 B per
+    # gathered list entry + 48 B per hit written
+    mkp = 1 if w.colour else 0
+    kmers = 2 * n_reads * sum(max(0, w.read_len - s.span + 1 - mkp) for s in seeds)
+    scan_bytes = 2 * n_reads * 4 * packed.shape[1] + kmers * 8 + st["list_entries"] * 4 + st["hits"] * 48
     scan_gbs = scan_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
+    # full SW: band cells x integer-pipe instructions per cell (counted from SASS)
+    full_ipc = FULL_INSTR_PER_CELL["cs" if w.colour else "ls"]
+    full_gcells = st["full_cells"] / (full_ms * 1e-3) / 1e9 if full_ms > 0 else 0.0
     dominant = max(stage.items(), key=lambda kv: kv[1][0])[0]
-    roof_vec = {"kernel": "sw_vector_kernel", "bound": "int-dpx", "achieved": vec_ginstr, "peak": dpx_peak,
-                "unit": "G thread-instr/s", "frac": vec_ginstr / dpx_peak if dpx_peak else None, "traffic": None,
-                "gcups": vec_gcups, "ms_per_launch": vec_ms,
-                "peak_source": "measured live: register-resident VIADDMNMX.S16x2 chains (shrimp_gpu_dpx_peak)"}
-    roof_scan = {"kernel": "scan_kernel", "bound": "hbm", "achieved": scan_gbs, "peak": hbm_peak, "unit": "GB/s",
-                 "frac": scan_gbs / hbm_peak, "traffic": None, "ms_per_launch": scan_ms, "peak_source": peak_src,
-                 "algorithmic_bytes_per_launch": scan_bytes}
-    roofline = dict(roof_scan if dominant == "seed_scan" else roof_vec)
+    roofs = {
+        "sw_vector": {"kernel": "sw_vector_kernel", "bound": "int-dpx", "achieved": vec_ginstr, "peak": dpx_peak,
+                      "unit": "G thread-instr/s", "frac": vec_ginstr / dpx_peak if dpx_peak else None,
+                      "traffic": None, "gcups": vec_gcups, "ms_per_launch": vec_ms,
+                      "peak_source": "measured live: register-resident VIADDMNMX.S16x2 chains (shrimp_gpu_dpx_peak)"},
+        "seed_scan": {"kernel": "scan_kernel", "bound": "hbm", "achieved": scan_gbs, "peak": hbm_peak, "unit": "GB/s",
+                      "frac": scan_gbs / hbm_peak, "traffic": None, "ms_per_launch": scan_ms, "peak_source": peak_src,
+                      "algorithmic_bytes_per_launch": scan_bytes},
+        "sw_full": {"kernel": "sw_full_cs_kernel" if w.colour else "sw_full_ls_kernel", "bound": "int-alu",
+                    "achieved": full_gcells * full_ipc, "peak": dpx_peak, "unit": "G thread-instr/s",
+                    "frac": full_gcells * full_ipc / dpx_peak if dpx_peak else None, "traffic": None,
+                    "gcells_per_s": full_gcells, "instr_per_cell": full_ipc, "ms_per_step": full_ms,
+                    "peak_source": "measured live: integer-pipe issue peak (shrimp_gpu_dpx_peak)"},
+    }
+    roofline = dict(roofs.get(dominant, roofs["seed_scan"]))
     roofline["dominant_stage"] = dominant
-    roofline["other"] = roof_vec if dominant == "seed_scan" else roof_scan
+    roofline["other"] = {k: v for k, v in roofs.items() if k != dominant}
 
     # ---- CPU baseline: the reference binary on this box's cores, bounded sample ---------------------
     cpu = None
-    if world == 1 and not a.no_cpu_baseline and os.path.exists(REF_BIN):
+    if world == 1 and not a.no_cpu_baseline and os.path.exists(ref_bin):
         try:
-            g2, r2, _, _ = make_workload(a.cpu_sample)
+            sample, _ = w.reads(a.cpu_sample, 1000)
             with tempfile.TemporaryDirectory() as d:
-                reference_setup(d, g2, r2)
-                s, gcu, _ = run_reference(d, ncores, "reads.fa", "proj", "genome.fa")
+                how = reference_setup(w, d, sample, ctx)
+                s, gcu, _ = run_reference(w, d, ncores, "reads.fa", "proj")
             cpu = {"value": a.cpu_sample / s, "unit": "reads/s", "cores": ncores, "kind": "reference",
-                   "sample": f"{a.cpu_sample} reads of the same workload, oracle/_ref/gmapper-ls -N {ncores} -L "
-                             "<projection> (Read Mapping Time, index load excluded)",
+                   "sample": f"{a.cpu_sample} reads of the same workload, oracle/_ref/{w.binary} -N {ncores} "
+                             f"{' '.join(w.args)} -L <projection> (Read Mapping Time, index load excluded); {how}",
                    "sw_vector_gcups": gcu}
         except Exception as e:  # noqa: BLE001
             cpu = {"value": None, "unit": "reads/s", "cores": ncores, "kind": "reference", "sample": f"failed: {e}"}
@@ -322,10 +421,11 @@ def main():
         "metric": "reads_per_sec_mapped", "value": value, "unit": "reads/s", "n_gpus": world, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": total_ms_max / a.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "reads_per_gpu_per_step": a.reads, "read_len": READ_LEN,
-                   "genome_len": GENOME_LEN, "parallelism": f"read-sharded x{world}, replicated index",
-                   "l2": "L2 flushed (256 MB write) before every timed step; index 0.7 GB > L2"},
-        "sw_vector_gcups": vec_gcups, "reads_mapped_frac": n_mapped / a.reads,
+        "config": {"workload": w.desc, "reads_per_gpu_per_step": n_reads, "read_len": w.read_len,
+                   "genome_len": w.genome_len, "parallelism": f"read-sharded x{world}, replicated index",
+                   "l2": "L2 flushed (256 MB write) before every timed step; index > L2"},
+        "sw_vector_gcups": vec_gcups, "sw_full_mcells_per_s": full_gcells * 1e3,
+        "reads_mapped_frac": n_mapped / n_reads,
         "index_build_s": index_s,
         "stage_ms_per_step": {k: v[0] / a.steps for k, v in stage.items()},
         "pipeline_stats": st,

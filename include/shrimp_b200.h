@@ -113,6 +113,12 @@ int shrimp_gpu_index_build(shrimp_gpu_ctx *ctx, int n_seeds, const uint64_t *mas
 int shrimp_gpu_index_nbuckets(shrimp_gpu_ctx *ctx, int sn, uint32_t *nbuckets, uint64_t *total);
 int shrimp_gpu_index_export(shrimp_gpu_ctx *ctx, int sn, uint32_t *lens_out, uint32_t *pos_out, uint64_t *total_out);
 
+/* Projection save.  Replaces save_genome_map / save_genome_map_seed (gmapper/genome.c:185-272,
+ * :15-66): writes <prefix>.genome and <prefix>.seed.N in the layout of `gmapper -S`, uncompressed
+ * (the reference's loader reads through gzread, which passes plain files through), so that
+ * `gmapper -L <prefix>` runs on exactly the projection held in HBM.  contig_names[num_contigs]. */
+int shrimp_gpu_projection_save(shrimp_gpu_ctx *ctx, const char *prefix, const char *const *contig_names);
+
 /* ------------------------------------------------------------------------------------------
  * Chunk-level mapping.  Replaces handle_read (gmapper/mapping.c:1773-1868) for a whole chunk of
  * unpaired reads with the default single option set of gmapper.c:2601-2632, i.e. per read:

@@ -96,6 +96,8 @@ def lib() -> C.CDLL:
     L.shrimp_gpu_index_nbuckets.restype = i32
     L.shrimp_gpu_index_export.argtypes = [vp, i32, vp, vp, C.POINTER(u64)]
     L.shrimp_gpu_index_export.restype = i32
+    L.shrimp_gpu_projection_save.argtypes = [vp, C.c_char_p, vp]
+    L.shrimp_gpu_projection_save.restype = i32
     L.shrimp_gpu_map_reads.argtypes = [vp, C.POINTER(MapParamsC), i32, vp, i32, vp, vp, vp, C.c_int64, vp, vp,
                                        C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64), vp, C.c_int64,
                                        C.POINTER(C.c_int64), C.POINTER(MapStatsC)]

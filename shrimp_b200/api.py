@@ -239,6 +239,12 @@ class GpuContext:
               "shrimp_gpu_index_export")
         return lens, pos[: tot.value]
 
+    def save_projection(self, prefix: str, contig_names):
+        """save_genome_map (genome.c:185-272): <prefix>.genome + <prefix>.seed.N for `gmapper -L <prefix>`."""
+        names = (C.c_char_p * len(contig_names))(*[n.encode() for n in contig_names])
+        check(self._L.shrimp_gpu_projection_save(self._h, prefix.encode(), C.cast(names, C.c_void_p)),
+              "shrimp_gpu_projection_save")
+
     # ---- chunk mapping ------------------------------------------------------------------------
     def map_reads(self, params: MapParams, scores: Scores, reads: np.ndarray, read_len, initbp=None,
                   want_stage: bool = False, stage_cap_per_read: int = 256) -> MapResult:

@@ -93,3 +93,36 @@ def test_hashed_seeds_match_oracle(gpu_ctx):
         lens_g, pos_g = gpu_ctx.export_index(sn)
         assert np.array_equal(lens_g, ix.bucket_lens(sn))
         assert np.array_equal(pos_g, ix.positions(sn))
+
+
+import os  # noqa: E402
+
+_REF = os.path.join(os.path.dirname(__file__), "..", "oracle", "_ref")
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(_REF, "gmapper-ls")), reason="oracle/_ref not built")
+@pytest.mark.parametrize("name", ["c1_small", "c2_small"])
+def test_projection_save_is_byte_identical_to_gmapper_S(gpu_ctx, tmp_path, name):
+    """shrimp_gpu_projection_save vs `gmapper -S` (save_genome_map, genome.c:185-272) on the same genome:
+    every file equal after gunzip, and `gmapper -L` on our files gives the SAM of a from-FASTA run."""
+    import gzip
+    import subprocess
+    case = LsCase(name)
+    d = str(tmp_path)
+    case.write_fasta(d)
+    binary = os.path.join(_REF, case.binary)
+    subprocess.run([binary, "-S", "ref", "genome.fa"], cwd=d, check=True, stdout=subprocess.DEVNULL,
+                   stderr=subprocess.DEVNULL)
+    gpu_ctx.load_genome([_pack_codes(c.astype(np.uint32)) for c in case.contig_codes],
+                        [c.size for c in case.contig_codes], colour_space=case.colour)
+    gpu_ctx.build_index(case.seeds)
+    gpu_ctx.save_projection(os.path.join(d, "mine"), case.contig_names)
+    for suffix in ["genome"] + [f"seed.{sn}" for sn in range(len(case.seeds))]:
+        want = gzip.open(os.path.join(d, f"ref.{suffix}"), "rb").read()
+        got = open(os.path.join(d, f"mine.{suffix}"), "rb").read()
+        assert got == want, suffix
+    args = ["--no-mapping-qualities"] if case.colour else []
+    a = subprocess.run([binary, *args, "-L", "mine", "reads.fa"], cwd=d, check=True, capture_output=True).stdout
+    b = subprocess.run([binary, *args, "reads.fa", "genome.fa"], cwd=d, check=True, capture_output=True).stdout
+    strip = lambda s: [l for l in s.splitlines() if not l.startswith(b"@PG")]  # noqa: E731
+    assert strip(a) == strip(b)
