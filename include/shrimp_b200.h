@@ -90,6 +90,37 @@ int shrimp_gpu_sw_vector_batch(shrimp_gpu_ctx *ctx,
                                int32_t *scores_out);
 
 /* ------------------------------------------------------------------------------------------
+ * Batched full Smith-Waterman with traceback.  Replaces sw_full_ls (common/sw-full-ls.c:637-683) and,
+ * after a colour-space set-up, sw_full_cs (common/sw-full-cs.c:1146-1236), one task per call the
+ * reference would make: read reads[read_idx] (rlen bases / colours, initbp in colour space) against
+ * genome[goff .. goff+glen) of ONE packed letter array, band from the anchor (x, y, length, width;
+ * widened by anchor_width of the set-up, or the threshold band when that is < 0), tie-breaks
+ * reversed when revcmpl.  Letter space: maxscore = the sw_vector score of the window (used by local
+ * mode only).  local_alignment = !Gflag.  Results are the fields of struct sw_full_results
+ * (sw-full-common.h:13-48); the alignment comes back as an edit script (see shrimp_hit below).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct shrimp_full_task {
+  uint32_t goff;
+  int32_t glen, read_idx, rlen;
+  int32_t threshscore, maxscore, revcmpl;
+  int32_t ax, ay, alen, awidth;
+  int32_t initbp;
+} shrimp_full_task;
+
+typedef struct shrimp_full_result {
+  int32_t score, read_start, rmapped, genome_start, gmapped;
+  int32_t matches, mismatches, insertions, deletions, crossovers;
+  int32_t edit_len;
+  int64_t edit_off;
+} shrimp_full_result;
+
+int shrimp_gpu_sw_full_batch(shrimp_gpu_ctx *ctx, const uint32_t *genome, size_t genome_words,
+                             const uint32_t *reads, int read_stride_words, int n_reads, int n_tasks,
+                             const shrimp_full_task *tasks, int local_alignment,
+                             shrimp_full_result *results, uint8_t *edits, int64_t edits_cap,
+                             int64_t *edits_used);
+
+/* ------------------------------------------------------------------------------------------
  * Genome residency.  Replaces the arrays load_genome builds (gmapper/genome.c:1092-1124,
  * globals gmapper.h:264-275): takes the reference's own genome_contigs[] (packed letters, one
  * array per contig), genome_len[] and num_contigs, and derives genome_contigs_rc (util.c:541-598)

@@ -52,6 +52,17 @@ class StageHitC(C.Structure):
                 ("ax", C.c_int32), ("ay", C.c_int32), ("alen", C.c_int32), ("awidth", C.c_int32)]
 
 
+class FullTaskC(C.Structure):
+    _fields_ = [("goff", C.c_uint32)] + [(n, C.c_int32) for n in (
+        "glen", "read_idx", "rlen", "threshscore", "maxscore", "revcmpl", "ax", "ay", "alen", "awidth", "initbp")]
+
+
+class FullResultC(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("score", "read_start", "rmapped", "genome_start", "gmapped", "matches",
+                                         "mismatches", "insertions", "deletions", "crossovers", "edit_len")] + \
+               [("edit_off", C.c_int64)]
+
+
 class MapStatsC(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("list_entries", "surviving_entries", "anchors", "hits", "heap_replays",
                                           "vector_tasks", "vector_calls", "vector_cells", "vector_bypassed",
@@ -84,6 +95,9 @@ def lib() -> C.CDLL:
     L.shrimp_gpu_sw_setup.restype = i32
     L.shrimp_gpu_sw_vector_batch.argtypes = [vp, vp, C.c_size_t, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp]
     L.shrimp_gpu_sw_vector_batch.restype = i32
+    L.shrimp_gpu_sw_full_batch.argtypes = [vp, vp, C.c_size_t, vp, i32, i32, i32, vp, i32, vp, vp, C.c_int64,
+                                           C.POINTER(C.c_int64)]
+    L.shrimp_gpu_sw_full_batch.restype = i32
     L.shrimp_gpu_dpx_peak.argtypes = [vp, C.POINTER(C.c_double)]
     L.shrimp_gpu_dpx_peak.restype = i32
     L.shrimp_gpu_genome_load.argtypes = [vp, i32, vp, vp, i32]

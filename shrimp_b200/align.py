@@ -71,3 +71,54 @@ def sam_fields(hit, edit: np.ndarray, read_len: int, genome_len_cn: int, colour_
                             "H" if colour_space else "S")
     nm = int(hit["mismatches"]) + int(hit["deletions"]) + int(hit["insertions"])
     return (16 if reverse else 0, int(hit["cn"]), pos, cigar, int(hit["score_full"]), nm)
+
+
+def cs_layer_letters(colours: np.ndarray, initbp: int) -> np.ndarray:
+    """[4, n] letter translations of a colour read, layer k starting from letter (k + initbp) % 4; a colour N
+    gives letter N and restarts the layer (sw-full-cs.c:1181-1196, cstols util.h:157-180)."""
+    n = len(colours)
+    out = np.zeros((4, n), dtype=np.uint8)
+    for k in range(4):
+        letter = (k + initbp) % 4
+        for j in range(n):
+            c = int(colours[j])
+            if c == 15:
+                out[k, j] = 15
+                letter = (k + initbp) % 4
+            else:
+                r = 15 if (letter == 15 or c > 3) else ((4 + letter + c) % 4 if letter % 2 == 0 else (4 + letter - c) % 4)
+                out[k, j] = r
+                letter = r
+    return out
+
+
+def align_strings_cs(edit: np.ndarray, genome_codes: np.ndarray, genome_start: int, colours: np.ndarray, initbp: int,
+                     read_start: int):
+    """pretty_print of common/sw-full-cs.c:945-1060 from the edit script: the letter shown is the one of the layer
+    in bits 4-5, lower case on a crossover column; an aligned N takes the genome's letter."""
+    qr = cs_layer_letters(colours, initbp)
+    db, q = bytearray(), bytearray()
+    gi, ri = genome_start, read_start
+    for op in edit:
+        op = int(op)
+        ty, xo, k = op & 3, op & 4, (op >> 4) & 3
+        if ty == 2:
+            c = _LS_LETTERS[int(qr[k, ri]) & 15]
+            ri += 1
+            db += b"-"
+            q.append(c | 0x20 if xo else c)
+        elif ty == 1:
+            db.append(_LS_LETTERS[int(genome_codes[gi]) & 15])
+            q += b"-"
+            gi += 1
+        else:
+            c = _LS_LETTERS[int(qr[k, ri]) & 15]
+            g = _LS_LETTERS[int(genome_codes[gi]) & 15]
+            ri += 1
+            gi += 1
+            db.append(g)
+            c = c | 0x20 if xo else c
+            if c in (ord("n"), ord("N")):
+                c = g | 0x20 if xo else g
+            q.append(c)
+    return bytes(db), bytes(q)

@@ -13,7 +13,7 @@ import numpy as np
 
 import math
 
-from ._lib import HitC, MapParamsC, MapStatsC, StageHitC, SwParams, check, lib
+from ._lib import FullResultC, FullTaskC, HitC, MapParamsC, MapStatsC, StageHitC, SwParams, check, lib
 
 # fasta.h:26-42
 _LS_CODE = np.full(256, 255, dtype=np.uint8)
@@ -201,6 +201,23 @@ class GpuContext:
             n, _ptr(goff), _ptr(glen), _ptr(read_idx), _ptr(rlen), _ptr(initbp), _ptr(out)),
             "shrimp_gpu_sw_vector_batch")
         return out
+
+    # ---- sw_full_ls / sw_full_cs ----------------------------------------------------------------
+    def sw_full(self, genome: np.ndarray, reads: np.ndarray, tasks: np.ndarray, local: bool = False):
+        """Batched sw_full_ls (sw-full-ls.c:637) / sw_full_cs (sw-full-cs.c:1146, after a colour set-up).
+        tasks: structured array of FullTaskC.  Returns (results structured array, edit-script pool)."""
+        genome = np.ascontiguousarray(genome, dtype=np.uint32)
+        reads = np.ascontiguousarray(reads, dtype=np.uint32)
+        tasks = np.ascontiguousarray(tasks, dtype=FullTaskC)
+        n = tasks.size
+        res = np.zeros(max(1, n), dtype=FullResultC)
+        cap = max(1024, int((tasks["glen"].astype(np.int64) + tasks["rlen"]).sum()))
+        edits = np.zeros(cap, dtype=np.uint8)
+        used = C.c_int64(0)
+        check(self._L.shrimp_gpu_sw_full_batch(self._h, _ptr(genome), genome.size, _ptr(reads), reads.shape[1],
+                                               reads.shape[0], n, _ptr(tasks), int(local), _ptr(res), _ptr(edits),
+                                               cap, C.byref(used)), "shrimp_gpu_sw_full_batch")
+        return res[:n], edits[: used.value]
 
     # ---- genome + index ---------------------------------------------------------------------
     def load_genome(self, contigs_packed: list, genome_len, colour_space: bool = False):

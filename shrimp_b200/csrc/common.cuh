@@ -114,10 +114,16 @@ struct SwScores {
 
 }  // namespace shrimp
 
+#define SHRIMP_AUX_STREAMS 4
+
 struct shrimp_gpu_ctx {
   int device = 0;
   int sm_count = 0;
   cudaStream_t stream = nullptr;
+  // side streams + fork/join events: independent launches of one stage (the ring-width classes of the
+  // full SW) run concurrently and join back into `stream`
+  cudaStream_t aux[SHRIMP_AUX_STREAMS] = {nullptr};
+  cudaEvent_t fork_ev = nullptr, join_ev[SHRIMP_AUX_STREAMS] = {nullptr};
   uint64_t launches = 0;
   shrimp::SwScores sw;
   shrimp::StageTimer timers[shrimp::ST_COUNT];

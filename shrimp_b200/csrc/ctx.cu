@@ -52,6 +52,11 @@ extern "C" int shrimp_gpu_create(int device, shrimp_gpu_ctx **out) {
   SH_CUDA(cudaGetDeviceProperties(&prop, device));
   c->sm_count = prop.multiProcessorCount;
   SH_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  SH_CUDA(cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming));
+  for (int i = 0; i < SHRIMP_AUX_STREAMS; i++) {
+    SH_CUDA(cudaStreamCreateWithFlags(&c->aux[i], cudaStreamNonBlocking));
+    SH_CUDA(cudaEventCreateWithFlags(&c->join_ev[i], cudaEventDisableTiming));
+  }
   for (int i = 0; i < ST_COUNT; i++) {
     SH_CUDA(cudaEventCreate(&c->timers[i].ev0));
     SH_CUDA(cudaEventCreate(&c->timers[i].ev1));
@@ -76,6 +81,11 @@ extern "C" void shrimp_gpu_destroy(shrimp_gpu_ctx *c) {
     if (c->timers[i].ev0) cudaEventDestroy(c->timers[i].ev0);
     if (c->timers[i].ev1) cudaEventDestroy(c->timers[i].ev1);
   }
+  for (int i = 0; i < SHRIMP_AUX_STREAMS; i++) {
+    if (c->aux[i]) cudaStreamDestroy(c->aux[i]);
+    if (c->join_ev[i]) cudaEventDestroy(c->join_ev[i]);
+  }
+  if (c->fork_ev) cudaEventDestroy(c->fork_ev);
   cudaStreamDestroy(c->stream);
   delete c;
 }

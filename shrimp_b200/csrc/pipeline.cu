@@ -9,7 +9,7 @@
 #include <stdlib.h>
 #include <algorithm>
 #include <cub/cub.cuh>
-#include "stages.cuh"
+#include "band.cuh"
 
 namespace shrimp {
 
@@ -21,6 +21,8 @@ int launch_build_vec_tasks(shrimp_gpu_ctx *ctx, const TaskBuildParams &P);
 int launch_pass1_select(shrimp_gpu_ctx *ctx, const Pass1Params &P);
 int launch_sw_full_ls(shrimp_gpu_ctx *ctx, const FullParams &P);
 int launch_sw_full_cs(shrimp_gpu_ctx *ctx, const FullParams &P);
+int launch_sw_full_ring(shrimp_gpu_ctx *ctx, const FullParams &P, bool cs);
+bool ring_fits(bool cs, int W);
 
 __constant__ uint8_t c_cmpl_r[16] = {3, 2, 1, 0, 0, 10, 9, 7, 8, 6, 5, 14, 13, 12, 11, 15};
 
@@ -148,10 +150,36 @@ __global__ void build_full_tasks_kernel(const FullBuildParams P) {
   P.info[out] = I;
 }
 
+// Ring-width class of every full-SW task (sw_full_ring.cu): the widest row of its band + the edge cell,
+// rounded up to 32/64/128/256; class RING_CLASSES = wider than any ring that fits shared memory, served by
+// the global-scratch kernels.  perm[c * n + rank] lists the task ids of class c.
+#define RING_CLASSES 4
+__global__ void classify_full_tasks_kernel(const FullTask *tasks, int n, int anchor_width, int match, int local,
+                                           int max_class, int32_t *perm, uint32_t *cls_count) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const FullTask T = tasks[t];
+  int bw = 2;
+  if (T.run) {
+    for (int pass = 0; pass < (local ? 2 : 1); pass++) {  // local mode may redo with the threshold band
+      const Rect rect = task_rect(T, anchor_width, match, pass == 0);
+      for (int i = 0; i < T.rlen; i++) {
+        int x_min, x_max;
+        rect_x_range(rect, T.glen, i, x_min, x_max);
+        bw = max(bw, x_max - x_min + 2);
+      }
+    }
+  }
+  int c = bw <= 32 ? 0 : bw <= 64 ? 1 : bw <= 128 ? 2 : bw <= 256 ? 3 : RING_CLASSES;
+  if (c > max_class) c = RING_CLASSES;
+  const uint32_t rank = atomicAdd(&cls_count[c], 1u);
+  perm[(size_t)c * n + rank] = t;
+}
+
 struct Pipeline {
   DevBuf d_in, d_reads, d_read_len, d_initbp, d_hits, d_rs_range, d_counters, d_overflow, d_scratch;
   DevBuf d_task[2], d_vtrue[2], d_slot, d_writer, d_sel, d_nsel;
-  DevBuf d_ftasks, d_finfo, d_fresults, d_frow, d_fbp, d_fops, d_taskoff, d_scan_tmp;
+  DevBuf d_ftasks, d_finfo, d_fresults, d_frow, d_fbp[RING_CLASSES + 1], d_fops, d_taskoff, d_scan_tmp, d_perm;
   HostBuf h_info, h_results, h_ops, h_nsel, h_hits, h_range;
   uint32_t hits_cap = 0;
   // reads left resident by the last upload (shrimp_gpu_map_resident)
@@ -166,12 +194,86 @@ void free_pipeline(shrimp_gpu_ctx *ctx) {
   DevBuf *bufs[] = {&p->d_in, &p->d_reads, &p->d_read_len, &p->d_initbp, &p->d_hits, &p->d_rs_range, &p->d_counters,
                     &p->d_overflow, &p->d_scratch, &p->d_task[0], &p->d_task[1], &p->d_vtrue[0], &p->d_vtrue[1],
                     &p->d_slot, &p->d_writer, &p->d_sel, &p->d_nsel, &p->d_ftasks, &p->d_finfo, &p->d_fresults,
-                    &p->d_frow, &p->d_fbp, &p->d_fops, &p->d_taskoff, &p->d_scan_tmp};
+                    &p->d_frow, &p->d_fbp[0], &p->d_fbp[1], &p->d_fbp[2], &p->d_fbp[3], &p->d_fbp[4], &p->d_fops,
+                    &p->d_taskoff, &p->d_scan_tmp, &p->d_perm};
   for (DevBuf *b : bufs) b->release();
   HostBuf *hb[] = {&p->h_info, &p->h_results, &p->h_ops, &p->h_nsel, &p->h_hits, &p->h_range};
   for (HostBuf *b : hb) b->release();
   delete p;
   ctx->pipeline = nullptr;
+}
+
+// restores ctx->stream on every exit path of run_full_sw
+struct ctx_stream_guard {
+  shrimp_gpu_ctx *c;
+  cudaStream_t s;
+  ~ctx_stream_guard() { c->stream = s; }
+};
+
+// Full SW over the n tasks of FP.tasks: classify by ring width, one ring launch per class and
+// sub-batch (scratch bounded to ~2 GB of back-pointers), global-scratch kernels for the rest.
+static int run_full_sw(shrimp_gpu_ctx *ctx, DevBuf &d_perm, DevBuf &d_row, DevBuf *d_bp /*[RING_CLASSES+1]*/,
+                       FullParams FP, int n, bool cs, uint32_t *d_cls_count) {
+  if (n <= 0) return SHRIMP_OK;
+  cudaStream_t st = ctx->stream;
+  SH_TRY(d_perm.ensure((size_t)(RING_CLASSES + 1) * n * 4));
+  SH_CUDA(cudaMemsetAsync(d_cls_count, 0, (RING_CLASSES + 1) * 4, st));
+  int max_class = -1;
+  for (int c = 0; c < RING_CLASSES; c++)
+    if (ring_fits(cs, 32 << c)) max_class = c;
+  classify_full_tasks_kernel<<<(n + 127) / 128, 128, 0, st>>>(FP.tasks, n, FP.anchor_width, FP.match, FP.local,
+                                                              max_class, d_perm.as<int32_t>(), d_cls_count);
+  SH_CUDA(cudaGetLastError());
+  SH_LAUNCHED(ctx, ST_FULL);
+  uint32_t cls[RING_CLASSES + 1];
+  SH_CUDA(cudaMemcpyAsync(cls, d_cls_count, sizeof(cls), cudaMemcpyDeviceToHost, st));
+  SH_CUDA(cudaStreamSynchronize(st));
+  // the classes are independent: class c runs on its own stream (class 0, the bulk, on the main one) so the
+  // small wide-band launches, each bounded by the latency of one alignment, overlap the bulk
+  const size_t budget = (size_t)2 << 30;
+  SH_CUDA(cudaEventRecord(ctx->fork_ev, st));
+  ctx_stream_guard guard{ctx, st};
+  for (int c = 0; c <= RING_CLASSES; c++) {
+    if (cls[c] == 0) continue;
+    const int count = (int)cls[c];
+    const bool ring = c < RING_CLASSES;
+    const int W = 32 << c;
+    const size_t states = cs ? 12 : 3;
+    const size_t per_task = ring ? (size_t)FP.max_rlen * W * (cs ? 8 : 1)
+                                 : states * (FP.max_glen + 1) * 4 + (size_t)FP.max_rlen * FP.max_glen * (cs ? 12 : 1);
+    int batch = (int)std::min<size_t>((size_t)count, std::max<size_t>(1024, budget / per_task));
+    batch = (batch + 127) & ~127;
+    if (ring) {
+      SH_TRY(d_bp[c].ensure((size_t)FP.max_rlen * W * (cs ? 8 : 1) * batch));
+    } else {
+      SH_TRY(d_row.ensure(states * (FP.max_glen + 1) * 4 * batch));
+      SH_TRY(d_bp[c].ensure((size_t)FP.max_rlen * FP.max_glen * (cs ? 12 : 1) * batch));
+    }
+    cudaStream_t cst = c == 0 ? st : ctx->aux[(c - 1) % SHRIMP_AUX_STREAMS];
+    if (c > 0) SH_CUDA(cudaStreamWaitEvent(cst, ctx->fork_ev, 0));
+    ctx->stream = cst;  // the launchers use ctx->stream
+    for (int b0 = 0; b0 < count; b0 += batch) {
+      FullParams Q = FP;
+      Q.perm = d_perm.as<int32_t>() + (size_t)c * n + b0;
+      Q.n_tasks = std::min(batch, count - b0);
+      Q.NT = batch;
+      Q.W = W;
+      Q.row = Q.row_cs = d_row.as<int32_t>();
+      Q.bp = Q.bp_cs = d_bp[c].as<uint8_t>();
+      Q.bp64 = d_bp[c].as<unsigned long long>();
+      int rc;
+      if (ring) rc = launch_sw_full_ring(ctx, Q, cs);
+      else if (cs) rc = launch_sw_full_cs(ctx, Q);
+      else rc = launch_sw_full_ls(ctx, Q);
+      if (rc != SHRIMP_OK) return rc;
+    }
+    ctx->stream = st;
+    if (c > 0) {
+      SH_CUDA(cudaEventRecord(ctx->join_ev[(c - 1) % SHRIMP_AUX_STREAMS], cst));
+      SH_CUDA(cudaStreamWaitEvent(st, ctx->join_ev[(c - 1) % SHRIMP_AUX_STREAMS], 0));
+    }
+  }
+  return SHRIMP_OK;
 }
 
 // ---- host stage ---------------------------------------------------------------------------------
@@ -628,50 +730,31 @@ static int map_impl(shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, int n_read
     SH_CUDA(cudaGetLastError());
     SH_LAUNCHED(ctx, ST_FULL);
 
-    // sub-batches sized for ~2 GB of DP scratch
-    const size_t states = cs ? 12 : 3;
-    const size_t per_task = states * (max_wl + 1) * 4 + (size_t)max_rl * max_wl * (cs ? 12 : 1) + ops_stride;
-    int batch = (int)std::min<size_t>((size_t)std::max(n_slots, 1), std::max<size_t>(1024, ((size_t)2 << 30) / per_task));
-    batch = (batch + 127) & ~127;
-    SH_TRY(pl->d_frow.ensure(states * (max_wl + 1) * 4 * batch));
-    SH_TRY(pl->d_fbp.ensure((size_t)max_rl * max_wl * (cs ? 12 : 1) * batch));
     SH_TRY(pl->d_fops.ensure(ops_stride * (size_t)std::max(n_slots, 1)));
-    for (int b0 = 0; b0 < n_slots; b0 += batch) {
-      FullParams FP;
-      memset(&FP, 0, sizeof(FP));
-      FP.genome_fwd = G.ls;
-      FP.genome_rc = G.ls_rc;
-      FP.reads = pl->d_reads.as<uint32_t>();
-      FP.stride = stride;
-      FP.tasks = pl->d_ftasks.as<FullTask>() + b0;
-      FP.results = pl->d_fresults.as<FullResult>() + b0;
-      FP.n_tasks = std::min(batch, n_slots - b0);
-      FP.NT = batch;
-      FP.row = pl->d_frow.as<int32_t>();
-      FP.bp = pl->d_fbp.as<uint8_t>();
-      FP.ops = pl->d_fops.as<uint8_t>() + ops_stride * (size_t)b0;
-      FP.max_glen = max_wl;
-      FP.max_rlen = max_rl;
-      FP.match = sw.match;
-      FP.mismatch = sw.mismatch;
-      FP.a_open = sw.a_open;
-      FP.a_ext = sw.a_ext;
-      FP.b_open = sw.b_open;
-      FP.b_ext = sw.b_ext;
-      FP.anchor_width = sw.anchor_width;
-      FP.Tflag = mp->Tflag;
-      FP.local = mp->Gflag ? 0 : 1;
-      FP.cells = (unsigned long long *)(cnt + 16);
-      FP.xover = sw.xover;
-      FP.indel_taboo_len = sw.indel_taboo_len;
-      FP.row_cs = pl->d_frow.as<int32_t>();
-      FP.bp_cs = pl->d_fbp.as<uint8_t>();
-      if (cs) {
-        SH_TRY(launch_sw_full_cs(ctx, FP));
-      } else {
-        SH_TRY(launch_sw_full_ls(ctx, FP));
-      }
-    }
+    FullParams FP;
+    memset(&FP, 0, sizeof(FP));
+    FP.genome_fwd = G.ls;
+    FP.genome_rc = G.ls_rc;
+    FP.reads = pl->d_reads.as<uint32_t>();
+    FP.stride = stride;
+    FP.tasks = pl->d_ftasks.as<FullTask>();
+    FP.results = pl->d_fresults.as<FullResult>();
+    FP.ops = pl->d_fops.as<uint8_t>();
+    FP.max_glen = max_wl;
+    FP.max_rlen = max_rl;
+    FP.match = sw.match;
+    FP.mismatch = sw.mismatch;
+    FP.a_open = sw.a_open;
+    FP.a_ext = sw.a_ext;
+    FP.b_open = sw.b_open;
+    FP.b_ext = sw.b_ext;
+    FP.anchor_width = sw.anchor_width;
+    FP.Tflag = mp->Tflag;
+    FP.local = mp->Gflag ? 0 : 1;
+    FP.cells = (unsigned long long *)(cnt + 16);
+    FP.xover = sw.xover;
+    FP.indel_taboo_len = sw.indel_taboo_len;
+    SH_TRY(run_full_sw(ctx, pl->d_perm, pl->d_frow, pl->d_fbp, FP, n_slots, cs, cnt + 32));
   }
 
   if (device_only) {
@@ -847,5 +930,136 @@ extern "C" int shrimp_gpu_last_transfer_bytes(shrimp_gpu_ctx *ctx, uint64_t *h2d
   }
   if (h2d) *h2d = pl->h2d_bytes;
   if (d2h) *d2h = pl->d2h_bytes;
+  return SHRIMP_OK;
+}
+
+// Batched sw_full_ls / sw_full_cs (common/sw-full-ls.c:637-683, common/sw-full-cs.c:1146-1236): one
+// task per call the reference would make, against one packed letter genome array.
+extern "C" int shrimp_gpu_sw_full_batch(shrimp_gpu_ctx *ctx, const uint32_t *genome, size_t genome_words,
+                                        const uint32_t *reads, int read_stride_words, int n_reads, int n_tasks,
+                                        const shrimp_full_task *tasks, int local_alignment,
+                                        shrimp_full_result *results, uint8_t *edits, int64_t edits_cap,
+                                        int64_t *edits_used) {
+  if (!ctx || !genome || !reads || !tasks || !results || n_tasks < 0 || n_reads <= 0 || read_stride_words <= 0) {
+    set_error("shrimp_gpu_sw_full_batch: invalid argument");
+    return SHRIMP_E_ARG;
+  }
+  if (!ctx->sw.valid) {
+    set_error("shrimp_gpu_sw_full_batch: shrimp_gpu_sw_setup() has not been called");
+    return SHRIMP_E_STATE;
+  }
+  if (edits_used) *edits_used = 0;
+  if (n_tasks == 0) return SHRIMP_OK;
+  const SwScores &sw = ctx->sw;
+  const bool cs = sw.use_colours != 0;
+  int max_rl = 1, max_gl = 1;
+  std::vector<FullTask> ft((size_t)n_tasks);
+  for (int t = 0; t < n_tasks; t++) {
+    const shrimp_full_task &a = tasks[t];
+    if (a.glen <= 0 || a.rlen <= 0 || a.read_idx < 0 || a.read_idx >= n_reads || a.rlen > read_stride_words * 8 ||
+        (uint64_t)a.goff + (uint64_t)a.glen > (uint64_t)genome_words * 8 || a.rlen > sw.max_read_len ||
+        a.glen > sw.max_window_len) {
+      set_error("shrimp_gpu_sw_full_batch: task %d out of range", t);
+      return SHRIMP_E_ARG;
+    }
+    FullTask &T = ft[t];
+    memset(&T, 0, sizeof(T));
+    T.goff_global = a.goff;
+    T.goff_contig = a.goff;
+    T.glen = a.glen;
+    T.rlen = a.rlen;
+    T.ridx = a.read_idx;
+    T.ax = a.ax;
+    T.ay = a.ay;
+    T.alen = a.alen;
+    T.awidth = a.awidth;
+    T.thresh = a.threshscore;
+    T.maxscore = a.maxscore;
+    T.gen_st = a.revcmpl ? 1 : 0;
+    T.run = 1;
+    T.initbp = a.initbp;
+    max_rl = std::max(max_rl, a.rlen);
+    max_gl = std::max(max_gl, a.glen);
+  }
+  SH_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  DevBuf d_gen, d_reads, d_tasks, d_res, d_ops, d_perm, d_row, d_bp[RING_CLASSES + 1], d_cnt;
+  struct Rel {
+    DevBuf *b[13];
+    ~Rel() {
+      for (DevBuf *x : b) x->release();
+    }
+  } rel{{&d_gen, &d_reads, &d_tasks, &d_res, &d_ops, &d_perm, &d_row, &d_bp[0], &d_bp[1], &d_bp[2], &d_bp[3], &d_bp[4],
+         &d_cnt}};
+  const size_t ops_stride = (size_t)max_rl + max_gl;
+  SH_TRY(d_gen.ensure(genome_words * 4 + 16));
+  SH_TRY(d_reads.ensure((size_t)n_reads * read_stride_words * 4));
+  SH_TRY(d_tasks.ensure((size_t)n_tasks * sizeof(FullTask)));
+  SH_TRY(d_res.ensure((size_t)n_tasks * sizeof(FullResult)));
+  SH_TRY(d_ops.ensure(ops_stride * (size_t)n_tasks));
+  SH_TRY(d_cnt.ensure(64 * 4));
+  SH_CUDA(cudaMemcpyAsync(d_gen.p, genome, genome_words * 4, cudaMemcpyHostToDevice, st));
+  SH_CUDA(cudaMemcpyAsync(d_reads.p, reads, (size_t)n_reads * read_stride_words * 4, cudaMemcpyHostToDevice, st));
+  SH_CUDA(cudaMemcpyAsync(d_tasks.p, ft.data(), (size_t)n_tasks * sizeof(FullTask), cudaMemcpyHostToDevice, st));
+  SH_CUDA(cudaMemsetAsync(d_cnt.p, 0, 64 * 4, st));
+  FullParams FP;
+  memset(&FP, 0, sizeof(FP));
+  FP.genome_fwd = FP.genome_rc = d_gen.as<uint32_t>();
+  FP.reads = d_reads.as<uint32_t>();
+  FP.stride = read_stride_words;
+  FP.tasks = d_tasks.as<FullTask>();
+  FP.results = d_res.as<FullResult>();
+  FP.ops = d_ops.as<uint8_t>();
+  FP.max_glen = max_gl;
+  FP.max_rlen = max_rl;
+  FP.match = sw.match;
+  FP.mismatch = sw.mismatch;
+  FP.a_open = sw.a_open;
+  FP.a_ext = sw.a_ext;
+  FP.b_open = sw.b_open;
+  FP.b_ext = sw.b_ext;
+  FP.anchor_width = sw.anchor_width;
+  FP.Tflag = 1;
+  FP.local = local_alignment ? 1 : 0;
+  FP.cells = (unsigned long long *)(d_cnt.as<uint32_t>() + 16);
+  FP.xover = sw.xover;
+  FP.indel_taboo_len = sw.indel_taboo_len;
+  {
+    ScopedStage ss(ctx, ST_FULL);
+    SH_TRY(run_full_sw(ctx, d_perm, d_row, d_bp, FP, n_tasks, cs, d_cnt.as<uint32_t>() + 32));
+  }
+  std::vector<FullResult> hr((size_t)n_tasks);
+  std::vector<uint8_t> hops(ops_stride * (size_t)n_tasks);
+  SH_CUDA(cudaMemcpyAsync(hr.data(), d_res.p, (size_t)n_tasks * sizeof(FullResult), cudaMemcpyDeviceToHost, st));
+  SH_CUDA(cudaMemcpyAsync(hops.data(), d_ops.p, hops.size(), cudaMemcpyDeviceToHost, st));
+  SH_CUDA(cudaStreamSynchronize(st));
+  int64_t used = 0;
+  bool short_pool = false;
+  for (int t = 0; t < n_tasks; t++) {
+    const FullResult &r = hr[t];
+    shrimp_full_result &o = results[t];
+    o.score = r.score;
+    o.read_start = r.read_start;
+    o.rmapped = r.rmapped;
+    o.genome_start = r.genome_start;
+    o.gmapped = r.gmapped;
+    o.matches = r.matches;
+    o.mismatches = r.mismatches;
+    o.insertions = r.insertions;
+    o.deletions = r.deletions;
+    o.crossovers = r.crossovers;
+    o.edit_len = r.ops_len;
+    o.edit_off = used;
+    if (edits && used + r.ops_len <= edits_cap)
+      memcpy(edits + used, hops.data() + ops_stride * (size_t)t + r.ops_start, (size_t)r.ops_len);
+    else if (r.ops_len > 0)
+      short_pool = true;
+    used += r.ops_len;
+  }
+  if (edits_used) *edits_used = used;
+  if (short_pool && edits) {
+    set_error("shrimp_gpu_sw_full_batch: edits_cap too small, %lld bytes needed", (long long)used);
+    return SHRIMP_E_NOMEM;
+  }
   return SHRIMP_OK;
 }

@@ -115,6 +115,11 @@ struct FullParams {
   int xover, indel_taboo_len;
   int32_t *row_cs;  // [12][max_glen+1][NT]
   uint8_t *bp_cs;   // [max_rlen*max_glen*12][NT]
+  // band-ring kernels (sw_full_ring.cu): task ids of this launch (nullptr = identity), ring width,
+  // packed colour-space back-pointers [max_rlen*W][NT]; `bp` is [max_rlen*W][NT] there
+  const int32_t *perm;
+  int W;
+  unsigned long long *bp64;
 };
 
 }  // namespace shrimp

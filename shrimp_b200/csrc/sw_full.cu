@@ -137,8 +137,9 @@ __device__ int full_sw_ls_dev(const FullParams &P, const FullTask &T, int t, con
 }
 
 __global__ void __launch_bounds__(128) sw_full_ls_kernel(const FullParams P) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= P.n_tasks) return;
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;  // scratch column of this launch
+  if (slot >= P.n_tasks) return;
+  const int t = P.perm ? P.perm[slot] : slot;              // task id
   const FullTask T = P.tasks[t];
   FullResult R;
   memset(&R, 0, sizeof(R));
@@ -151,18 +152,18 @@ __global__ void __launch_bounds__(128) sw_full_ls_kernel(const FullParams P) {
   unsigned long long cells = 0;
   int ei = 0, ej = 0, score, e_n = 0, e_w = 0, e_nw = 0;
   if (P.local) {
-    score = full_sw_ls_dev<true>(P, T, t, genome, read, true, ei, ej, e_n, e_w, e_nw, cells);
+    score = full_sw_ls_dev<true>(P, T, slot, genome, read, true, ei, ej, e_n, e_w, e_nw, cells);
     if (score != T.maxscore) {  // :395-398
       e_n = e_w = e_nw = 0;
-      score = full_sw_ls_dev<true>(P, T, t, genome, read, false, ei, ej, e_n, e_w, e_nw, cells);
+      score = full_sw_ls_dev<true>(P, T, slot, genome, read, false, ei, ej, e_n, e_w, e_nw, cells);
     }
   } else {
-    score = full_sw_ls_dev<false>(P, T, t, genome, read, true, ei, ej, e_n, e_w, e_nw, cells);
+    score = full_sw_ls_dev<false>(P, T, slot, genome, read, true, ei, ej, e_n, e_w, e_nw, cells);
   }
   R.score = score;
   // ---- do_backtrace (:413-516) ----
   const int lena = T.glen, NT = P.NT;
-  const uint8_t *bp = P.bp + t;
+  const uint8_t *bp = P.bp + slot;
   uint8_t *ops = P.ops + (size_t)t * (size_t)(P.max_glen + P.max_rlen);
   int i = ei, j = ej;
   // state of the end cell: northwest unless west is strictly greater, unless north is strictly

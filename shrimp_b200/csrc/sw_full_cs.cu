@@ -195,8 +195,9 @@ __device__ int full_sw_cs_dev(const FullParams &P, const FullTask &T, int t, con
 }
 
 __global__ void __launch_bounds__(128) sw_full_cs_kernel(const FullParams P) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= P.n_tasks) return;
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;  // scratch column of this launch
+  if (slot >= P.n_tasks) return;
+  const int t = P.perm ? P.perm[slot] : slot;              // task id
   const FullTask T = P.tasks[t];
   FullResult R;
   memset(&R, 0, sizeof(R));
@@ -208,8 +209,8 @@ __global__ void __launch_bounds__(128) sw_full_cs_kernel(const FullParams P) {
   const uint32_t *read = P.reads + (size_t)T.ridx * P.stride;
   unsigned long long cells = 0;
   int ei = 0, ej = 0, ek = 0, esc[3] = {0, 0, 0};
-  const int score = P.local ? full_sw_cs_dev<true>(P, T, t, genome, read, ei, ej, ek, esc, cells)
-                            : full_sw_cs_dev<false>(P, T, t, genome, read, ei, ej, ek, esc, cells);
+  const int score = P.local ? full_sw_cs_dev<true>(P, T, slot, genome, read, ei, ej, ek, esc, cells)
+                            : full_sw_cs_dev<false>(P, T, slot, genome, read, ei, ej, ek, esc, cells);
   if (cells) atomicAdd(P.cells, cells);
   if (!(score >= 0 && score >= T.thresh)) {  // sw_full_cs :1216-1226: below threshold -> score 0, no traceback
     P.results[t] = R;
@@ -218,7 +219,7 @@ __global__ void __launch_bounds__(128) sw_full_cs_kernel(const FullParams P) {
   R.score = score;
   // letters of the four layers are needed by the match count: recompute the translation on demand
   const int lena = T.glen, NT = P.NT;
-  const uint8_t *bp = P.bp_cs + t;
+  const uint8_t *bp = P.bp_cs + slot;
   uint8_t *ops = P.ops + (size_t)t * (size_t)(P.max_glen + P.max_rlen);
   // qr[k][i] for all i: walk the read once per layer into the ops scratch tail? -- reads are short;
   // recompute by scanning from the last N (or the start) up to i.
