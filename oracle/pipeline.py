@@ -45,6 +45,13 @@ class OrcHitOut(C.Structure):
                 ("sfr", OrcSfr)]
 
 
+class OrcPairParams(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("pair_mode", "min_insert_size", "max_insert_size", "half_paired")]
+
+
+PAIR_MODES = {"opp-in": 1, "opp-out": 2, "col-fw": 3, "col-bw": 4}
+
+
 class OrcStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("vector_calls", "vector_cells", "vector_bypassed", "full_calls",
                                           "full_cells", "n_anchors", "n_hits", "eq_x_ties")]
@@ -76,7 +83,7 @@ class MapOptions:
     window_len: float = 140.0
     window_overlap: float = 90.0
     window_gen_threshold: float = 55.0
-    sw_vect_threshold: float = 47.0
+    sw_vect_threshold: float | None = None   # None: 47 % in colour space, = sw_full_threshold in letter space (gmapper.c:2464-2466)
     sw_full_threshold: float = 50.0
     match_mode: int = 2
     num_outputs: int = 10
@@ -100,10 +107,13 @@ class MapOptions:
     def to_struct(self) -> OrcParams:
         s = self.scores
         alpha, beta = score_alpha_beta(s, self.colour_space)
+        vect = self.sw_vect_threshold
+        if vect is None:
+            vect = 47.0 if self.colour_space else self.sw_full_threshold
         return OrcParams(OrcScores(s.match, s.mismatch, s.a_gap_open, s.a_gap_ext, s.b_gap_open, s.b_gap_ext,
                                    s.crossover),
                          int(self.colour_space), self.window_len, self.window_overlap, self.window_gen_threshold,
-                         self.sw_vect_threshold, self.sw_full_threshold, self.match_mode, self.num_outputs,
+                         vect, self.sw_full_threshold, self.match_mode, self.num_outputs,
                          self.num_tmp_outputs, self.anchor_width, self.indel_taboo_len, int(self.gapless),
                          int(self.hash_filter_calls), int(self.use_regions), self.region_bits, self.region_overlap,
                          int(self.Gflag), int(self.Tflag), int(self.strata), self.max_alignments,
@@ -200,6 +210,104 @@ def map_reads(genome: Genome, index: Index, opts: MapOptions, reads: np.ndarray,
     return hits, n_per, st, sd
 
 
+def map_pairs(genome: Genome, index: Index, opts: MapOptions, reads: np.ndarray, read_len: np.ndarray,
+              pair_mode: str = "opp-in", min_insert: int = 0, max_insert: int = 1000, half_paired: bool = True,
+              initbp: np.ndarray | None = None):
+    """handle_readpair for pairs (reads 2k, 2k+1).  Returns (pair_hits [n,2] structured, pair_info [n,5]
+    (pair, score, score_max, key, insert_size), n_pairs_per_pair, unpaired hits, n_unp_per_read, stats)."""
+    L = oracle_lib()
+    L.orc_map_pairs.restype = C.c_longlong
+    reads = np.ascontiguousarray(reads, dtype=np.uint32)
+    read_len = np.ascontiguousarray(read_len, dtype=np.int32)
+    n = reads.shape[0]
+    assert n % 2 == 0
+    npairs = n // 2
+    p = opts.to_struct()
+    pp = OrcPairParams(PAIR_MODES[pair_mode], min_insert, max_insert, int(half_paired))
+    pcap = max(1, npairs * opts.num_outputs)
+    pout = (OrcHitOut * (2 * pcap))()
+    pinfo = np.zeros((pcap, 5), dtype=np.int32)
+    nper = np.zeros(max(1, npairs), dtype=np.int32)
+    ucap = max(1, n * opts.num_outputs)
+    uout = (OrcHitOut * ucap)()
+    nunp_per = np.zeros(max(1, n), dtype=np.int32)
+    nunp = C.c_longlong(0)
+    stats = OrcStats()
+    if initbp is not None:
+        initbp = np.ascontiguousarray(initbp, dtype=np.int8)
+    L.orc_map_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_longlong,
+                                C.c_void_p, C.c_void_p, C.c_void_p]
+    rc = L.orc_map_pairs(genome.h, index.h, C.byref(p), C.byref(pp), npairs, _p(reads), reads.shape[1], _p(read_len),
+                         _p(initbp), C.cast(pout, C.c_void_p), _p(pinfo), pcap, _p(nper), C.cast(uout, C.c_void_p),
+                         ucap, _p(nunp_per), C.byref(nunp), C.byref(stats))
+    if rc < 0:
+        raise RuntimeError("oracle capacity too small")
+    ph = np.ctypeslib.as_array(pout)[: 2 * rc].reshape(rc, 2) if rc > 0 else np.ctypeslib.as_array(pout)[:0].reshape(0, 2)
+    uh = np.ctypeslib.as_array(uout)[: nunp.value]
+    sd = {k: int(getattr(stats, k)) for k, _ in OrcStats._fields_}
+    return ph, pinfo[:rc], nper[:npairs], uh, nunp_per[:n], sd
+
+
+def pair_sam_records(pair_hits, pair_of, unp_hits, genome_lens, read_len, fields_of, n_pairs):
+    """The mapped SAM records readpair_output / readpair_output_no_mqv + read_output print for each pair, in print
+    order, as tuples (pair, mate, flag, cn, pos, cigar, mate_cn, mpos, isize, AS, NM) -- gmapper/output.c
+    hit_output :228-700.  fields_of(hit, read_len, contig_len) -> (flag16, cn, pos, cigar, AS, NM, gmapped)."""
+    out = []
+    per_pair = [[] for _ in range(n_pairs)]
+    per_read = [[] for _ in range(2 * n_pairs)]
+    for k, hh in zip(pair_of, pair_hits):
+        per_pair[int(k)].append(hh)
+    for h in unp_hits:
+        per_read[int(h["read_idx"])].append(h)
+
+    def rec(k, mate, h, mp, paired_alignment):
+        f = fields_of(h, int(read_len[int(h["read_idx"])]), int(genome_lens[int(h["cn"])]))
+        rev = f[0] == 16
+        flag = 1 | (2 if paired_alignment else 0) | (16 if rev else 0) | (0x40 if mate == 0 else 0x80)
+        mcn, mpos, isize = -1, 0, 0
+        if mp is None:
+            flag |= 8
+        else:
+            fm = fields_of(mp, int(read_len[int(mp["read_idx"])]), int(genome_lens[int(mp["cn"])]))
+            rev_mp = fm[0] == 16
+            if rev_mp:
+                flag |= 0x20
+            mcn, mpos = fm[1], fm[2]
+            if fm[1] == f[1]:
+                fivep = f[2] + f[6] - 1 if rev else f[2] - 1
+                fivep_mp = fm[2] + fm[6] - 1 if rev_mp else fm[2] - 1
+                isize = fivep_mp - fivep
+        return (k, mate, flag, f[1], f[2], f[3], mcn, mpos, isize, f[4], f[5])
+
+    for k in range(n_pairs):
+        for hh in per_pair[k]:
+            out.append(rec(k, 0, hh[0], hh[1], True))
+            out.append(rec(k, 1, hh[1], hh[0], True))
+        for mate in range(2):
+            for h in per_read[2 * k + mate]:
+                out.append(rec(k, mate, h, None, False))
+    return out
+
+
+def parse_pair_sam(path: str, contig_idx: dict):
+    """mapped records of a paired SAM as the tuples of pair_sam_records (qnames p<k>)."""
+    out = []
+    with open(path) as f:
+        for line in f:
+            if line.startswith("@"):
+                continue
+            t = line.rstrip("\n").split("\t")
+            flag = int(t[1])
+            if flag & 4:
+                continue
+            tags = {x[:2]: x[5:] for x in t[11:]}
+            mcn = -1 if t[6] == "*" else (contig_idx[t[2]] if t[6] == "=" else contig_idx[t[6]])
+            out.append((int(t[0][1:]), 0 if flag & 0x40 else 1, flag, contig_idx[t[2]], int(t[3]), t[5], mcn, int(t[7]),
+                        int(t[8]), int(tags["AS"]), int(tags["NM"])))
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # SAM fields that the hot path determines (gmapper/output.c: make_cigar :15-65, hit_output :470-700)
 # ------------------------------------------------------------------------------------------------
@@ -246,7 +354,7 @@ def sam_fields(hit, read_len: int, genome_len_cn: int, colour_space: bool = Fals
     cigar = cigar_from_alignment(int(sfr["read_start"]), int(sfr["rmapped"]), read_len, qr, db, reverse,
                                  "H" if colour_space else "S")
     nm = int(sfr["mismatches"]) + int(sfr["deletions"]) + int(sfr["insertions"])
-    return (16 if reverse else 0, int(hit["cn"]), pos, cigar, int(hit["score_full"]), nm)
+    return (16 if reverse else 0, int(hit["cn"]), pos, cigar, int(hit["score_full"]), nm, int(sfr["gmapped"]))
 
 
 def parse_sam(path: str):

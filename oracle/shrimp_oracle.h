@@ -115,6 +115,13 @@ typedef struct orc_params {
   double score_alpha, score_beta;
 } orc_params;
 
+/* pairing options (gmapper.h:140-142, gmapper.c:2638-2714); match_mode 4 / default paired set only */
+typedef struct orc_pair_params {
+  int pair_mode;               /* 1 opp-in, 2 opp-out, 3 col-fw, 4 col-bw (gmapper-definitions.h:42-47) */
+  int min_insert_size, max_insert_size;
+  int half_paired;
+} orc_pair_params;
+
 typedef struct orc_stage_hit {   /* a read_hit after read_pass1 (mapping.c:1345) */
   int read_idx, st, cn, w_len;
   long long g_off;               /* g_off_pos_strand */
@@ -144,5 +151,12 @@ long long orc_map_reads(const orc_genome *g, const orc_index *ix, const orc_para
                         const uint32_t *reads, int stride_words, const int *read_len, const int8_t *initbp,
                         orc_hit_out *out, long long out_cap, int *n_out_per_read,
                         orc_stage_hit *stage, long long stage_cap, long long *n_stage, orc_stats *stats);
+
+/* handle_readpair (mapping.c:2504-2650) for n_pairs pairs; reads 2k, 2k+1 are mates. */
+long long orc_map_pairs(const orc_genome *g, const orc_index *ix, const orc_params *p, const orc_pair_params *pp,
+                        int n_pairs, const uint32_t *reads, int stride_words, const int *read_len,
+                        const int8_t *initbp, orc_hit_out *pairs_out, int *pair_info, long long pairs_cap,
+                        int *n_pairs_per_pair, orc_hit_out *unp_out, long long unp_cap, int *n_unp_per_read,
+                        long long *n_unp, orc_stats *stats);
 
 #endif

@@ -100,7 +100,7 @@ class MapParams:
     window_len: float = 140.0
     window_overlap: float = 90.0
     window_gen_threshold: float = 55.0
-    sw_vect_threshold: float = 47.0
+    sw_vect_threshold: float | None = None   # None: 47 % in colour space, = sw_full_threshold in letter space (gmapper.c:2464-2466)
     sw_full_threshold: float = 50.0
     match_mode: int = 2
     num_outputs: int = 10
@@ -119,7 +119,10 @@ class MapParams:
 
     def to_c(self, scores: Scores, colour_space: bool) -> MapParamsC:
         alpha, beta = score_alpha_beta(scores, colour_space)
-        return MapParamsC(self.window_len, self.window_overlap, self.window_gen_threshold, self.sw_vect_threshold,
+        vect = self.sw_vect_threshold
+        if vect is None:
+            vect = 47.0 if colour_space else self.sw_full_threshold
+        return MapParamsC(self.window_len, self.window_overlap, self.window_gen_threshold, vect,
                           self.sw_full_threshold, alpha, beta, self.match_mode, self.num_outputs,
                           self.num_tmp_outputs, int(self.gapless), int(self.hash_filter_calls), int(self.use_regions),
                           self.region_bits, self.region_overlap, int(self.Gflag), int(self.Tflag), int(self.strata),

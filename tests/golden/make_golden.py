@@ -114,7 +114,30 @@ def golden_sw_full():
         print("wrote sw_full", "cs" if colour else "ls", len(ints))
 
 
-TARGETS = {"sw_vector": golden_sw_vector, "mapping": golden_mapping, "sw_full": golden_sw_full}
+def golden_pairs():
+    """Runs the reference gmapper on the small paired configs (default and --no-mapping-qualities) and stores every
+    mapped SAM record's hot-path fields: pair, mate, flag, contig, pos, mate contig, mate pos, isize, AS, NM + CIGAR."""
+    import subprocess
+    import tempfile
+    from mapcases import PAIR_CASES, PairCase
+    from oracle import pipeline as op
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    for name, spec in sorted(PAIR_CASES.items()):
+        case = PairCase(name)
+        with tempfile.TemporaryDirectory() as d:
+            case.write_fasta(d)
+            sam = os.path.join(d, "out.sam")
+            with open(sam, "w") as f:
+                subprocess.run([os.path.join(ref_dir, case.binary), "-1", "m1.fa", "-2", "m2.fa", *spec["args"],
+                                "genome.fa"], cwd=d, stdout=f, stderr=subprocess.DEVNULL, check=True)
+            recs = op.parse_pair_sam(sam, {n: i for i, n in enumerate(case.contig_names)})
+        ints = np.array([[r[0], r[1], r[2], r[3], r[4], r[6], r[7], r[8], r[9], r[10]] for r in recs], dtype=np.int64)
+        cig = np.array([r[5] for r in recs])
+        np.savez_compressed(os.path.join(HERE, f"pairs_{name}.npz"), recs=ints, cigars=cig)
+        print("wrote pairs", name, ints.shape)
+
+
+TARGETS = {"pairs": golden_pairs, "sw_vector": golden_sw_vector, "mapping": golden_mapping, "sw_full": golden_sw_full}
 
 if __name__ == "__main__":
     assert oracle.have_ref(), "build oracle/_ref first: make -C oracle ref"

@@ -65,3 +65,40 @@ def stage_tuple_array(stage) -> np.ndarray:
     if len(stage) == 0:
         return np.zeros((0, len(cols)), dtype=np.int64)
     return np.stack([np.asarray(stage[c], dtype=np.int64) for c in cols], axis=1)
+
+
+# paired configs: name -> (generator config, gmapper options, MapOptions overrides)
+PAIR_CASES = {
+    "c3_small": dict(gen="c3_small", args=["-p", "opp-in", "-I", "0,1000"], opts={}),
+    "c3_small_nomq": dict(gen="c3_small", args=["-p", "opp-in", "-I", "0,1000", "--no-mapping-qualities"],
+                          opts={"compute_mapping_qualities": False}),
+}
+
+
+class PairCase:
+    """reads 2k and 2k+1 are the mates of pair k (files -1 / -2 of gmapper)"""
+
+    def __init__(self, name: str):
+        cfg = gen_synth.CONFIGS[PAIR_CASES[name]["gen"]]
+        self.name = name
+        self.colour = False
+        self.binary = "gmapper-ls"
+        self.contigs = gen_synth.make_genome(**cfg["genome"])
+        self.contig_codes = [_LS_CODE[s] for _, s in self.contigs]
+        self.contig_names = [n for n, _ in self.contigs]
+        self.m1, self.m2 = gen_synth.simulate_pairs(self.contigs, **cfg["reads"])
+        self.n_pairs = len(self.m1)
+        inter = [r for pair in zip(self.m1, self.m2) for r in pair]
+        self.read_len = np.array([r[1].size for r in inter], dtype=np.int32)
+        self.stride = int((self.read_len.max() + 7) // 8)
+        self.packed = np.stack([_pack_codes(_LS_CODE[r[1]].astype(np.uint32), self.stride) for r in inter])
+        self.initbp = None
+        self.scores = LS_DEFAULT_SCORES
+        self.seeds = S.load_default_seeds()
+        self.total_len = int(sum(c.size for c in self.contig_codes))
+
+    def write_fasta(self, d: str):
+        os.makedirs(d, exist_ok=True)
+        gen_synth.write_fasta(os.path.join(d, "genome.fa"), self.contigs, width=80)
+        gen_synth.write_fasta(os.path.join(d, "m1.fa"), self.m1)
+        gen_synth.write_fasta(os.path.join(d, "m2.fa"), self.m2)

@@ -134,6 +134,44 @@ def simulate_cs_reads(contigs, n_reads: int, read_len: int, seed: int, snp_p: fl
     return out
 
 
+def simulate_pairs(contigs, n_pairs: int, read_len: int, seed: int, ins_mean: float = 300.0, ins_sd: float = 30.0,
+                   sub: float = 0.02, indel_p: float = 0.0, max_indel: int = 3, junk_p: float = 0.05,
+                   far_p: float = 0.05):
+    """Opp-in pairs: mate 1 = start of the fragment, mate 2 = reverse complement of its end; the fragment is
+    flipped half of the time.  junk_p: one mate replaced by random sequence; far_p: mates taken 5 kb apart
+    (no proper pairing inside the default 0..1000 insert range).  Returns (mates1, mates2)."""
+    rng = np.random.default_rng(seed)
+    lens = np.array([c[1].size for c in contigs], dtype=np.int64)
+    probs = lens / lens.sum()
+    m1, m2 = [], []
+    for i in range(n_pairs):
+        cn = int(rng.choice(len(contigs), p=probs)) if len(contigs) > 1 else 0
+        g = contigs[cn][1]
+        ins = max(read_len + 5, int(rng.normal(ins_mean, ins_sd)))
+        far = rng.random() < far_p
+        span = ins + (5000 if far else 0)
+        pos = int(rng.integers(0, max(1, g.size - span - 10)))
+        a = g[pos:pos + read_len + 8]
+        b_end = pos + span
+        b = g[b_end - read_len - 8:b_end]
+        a = _mutate(rng, a, sub, indel_p, max_indel)[:read_len]
+        b = _mutate(rng, b, sub, indel_p, max_indel)[-read_len:]
+        r1, r2 = a, revcomp(b)
+        if rng.random() < 0.5:
+            r1, r2 = revcomp(b), a
+        j = rng.random()
+        if j < junk_p:
+            which = int(rng.integers(0, 2))
+            junk = BASES[rng.integers(0, 4, size=read_len, dtype=np.uint8)]
+            if which == 0:
+                r1 = junk
+            else:
+                r2 = junk
+        m1.append((f"p{i}/1", np.ascontiguousarray(r1)))
+        m2.append((f"p{i}/2", np.ascontiguousarray(r2)))
+    return m1, m2
+
+
 def write_fasta(path: str, records, width: int = 0):
     with open(path, "wb") as f:
         for name, seq in records:
@@ -157,6 +195,9 @@ CONFIGS = {
                       reads=dict(n_reads=2_000, read_len=50, seed=14, sub=0.02)),
     "c2_small": dict(genome=dict(total_len=200_000, n_contigs=2, seed=17, n_frac=0.002),
                      reads=dict(n_reads=1_500, read_len=36, seed=18, snp_p=0.3, col_err=0.03), colour=True),
+    "c3_small": dict(genome=dict(total_len=300_000, n_contigs=3, seed=19, n_frac=0.002, repeat_unit=1500,
+                                 repeat_copies=30, repeat_div=0.02),
+                     reads=dict(n_pairs=600, read_len=100, seed=20, sub=0.02, indel_p=0.1), paired=True),
     "c5_small": dict(genome=dict(total_len=200_000, n_contigs=1, seed=15),
                      reads=dict(n_reads=500, read_len=75, seed=16, sub=0.04, indel_p=0.5, max_indel=5)),
 }
