@@ -231,6 +231,39 @@ int shrimp_gpu_map_reads(shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, int n
                          shrimp_stage_hit *stage, int64_t stage_cap, int64_t *n_stage,
                          shrimp_map_stats *stats);
 
+/* ------------------------------------------------------------------------------------------
+ * Chunk-level mapping of read pairs.  Replaces handle_readpair (gmapper/mapping.c:2504-2650) for a chunk
+ * of pairs with the default paired option set of gmapper.c:2638-2714 (mp->match_mode = 4, half-paired):
+ * readpair_compute_mp_ranges :2317, per-read region counts / anchors / hit lists as for unpaired reads in
+ * match mode 2, readpair_pair_up_hits :266, read_pass1 with only_paired :1261, readpair_get_vector_hits
+ * :1877, readpair_pass2 :2181 (hit_run_full_sw at half the full threshold, readpair_remove_duplicate_hits,
+ * ranking), then the half-paired fall-back into handle_read :1773 for both mates (pass 1 + pass 2).
+ * reads rows 2k and 2k+1 are the mates of pair k (gmapper -1 / -2).  What readpair_output
+ * (gmapper/output.c:1071) would receive comes back as:
+ *   pairs[]  final_paired_hits in pair order, each naming its two shrimp_hit records (mate 0, mate 1);
+ *   hits[]   first the members of the pairs, then every read's final_unpaired_hits in read order
+ *            (n_unpaired_per_read[2k + mate]).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct shrimp_pair_params {
+  int32_t pair_mode;            /* 1 opp-in, 2 opp-out, 3 col-fw, 4 col-bw (gmapper-definitions.h:42-47) */
+  int32_t min_insert_size, max_insert_size;   /* -I */
+  int32_t half_paired;          /* must be 1 (the default) for now */
+} shrimp_pair_params;
+
+typedef struct shrimp_pair {    /* struct read_hit_pair, gmapper-definitions.h:155-165 */
+  int32_t pair_idx;
+  int32_t score, score_max, key, insert_size;
+  int32_t hit_idx[2];
+} shrimp_pair;
+
+int shrimp_gpu_map_pairs(shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, const shrimp_pair_params *pp,
+                         int n_pairs, const uint32_t *reads, int read_stride_words, const int32_t *read_len,
+                         const int8_t *initbp,
+                         shrimp_hit *hits, int64_t hits_cap, int64_t *n_hits,
+                         shrimp_pair *pairs, int64_t pairs_cap, int64_t *n_pairs_out,
+                         int32_t *n_pairs_per_pair, int32_t *n_unpaired_per_read,
+                         uint8_t *edits, int64_t edits_cap, int64_t *edits_used, shrimp_map_stats *stats);
+
 /* Measurement entries (no reference counterpart).  shrimp_gpu_map_resident re-runs every device
  * stage on the reads the previous shrimp_gpu_map_reads call left in HBM and keeps the results on
  * the device: the "inputs already resident" throughput of bench.py.  shrimp_gpu_last_transfer_bytes

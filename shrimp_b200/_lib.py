@@ -63,6 +63,15 @@ class FullResultC(C.Structure):
                [("edit_off", C.c_int64)]
 
 
+class PairParamsC(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("pair_mode", "min_insert_size", "max_insert_size", "half_paired")]
+
+
+class PairC(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("pair_idx", "score", "score_max", "key", "insert_size")] + \
+               [("hit_idx", C.c_int32 * 2)]
+
+
 class MapStatsC(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("list_entries", "surviving_entries", "anchors", "hits", "heap_replays",
                                           "vector_tasks", "vector_calls", "vector_cells", "vector_bypassed",
@@ -116,6 +125,10 @@ def lib() -> C.CDLL:
                                        C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64), vp, C.c_int64,
                                        C.POINTER(C.c_int64), C.POINTER(MapStatsC)]
     L.shrimp_gpu_map_reads.restype = i32
+    L.shrimp_gpu_map_pairs.argtypes = [vp, C.POINTER(MapParamsC), C.POINTER(PairParamsC), i32, vp, i32, vp, vp,
+                                       vp, C.c_int64, C.POINTER(C.c_int64), vp, C.c_int64, C.POINTER(C.c_int64),
+                                       vp, vp, vp, C.c_int64, C.POINTER(C.c_int64), C.POINTER(MapStatsC)]
+    L.shrimp_gpu_map_pairs.restype = i32
     L.shrimp_gpu_map_resident.argtypes = [vp, C.POINTER(MapParamsC), C.POINTER(MapStatsC)]
     L.shrimp_gpu_map_resident.restype = i32
     L.shrimp_gpu_last_transfer_bytes.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]

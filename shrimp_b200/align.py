@@ -70,7 +70,7 @@ def sam_fields(hit, edit: np.ndarray, read_len: int, genome_len_cn: int, colour_
     cigar = cigar_from_edit(edit, int(hit["read_start"]), int(hit["rmapped"]), read_len, reverse,
                             "H" if colour_space else "S")
     nm = int(hit["mismatches"]) + int(hit["deletions"]) + int(hit["insertions"])
-    return (16 if reverse else 0, int(hit["cn"]), pos, cigar, int(hit["score_full"]), nm)
+    return (16 if reverse else 0, int(hit["cn"]), pos, cigar, int(hit["score_full"]), nm, int(hit["gmapped"]))
 
 
 def cs_layer_letters(colours: np.ndarray, initbp: int) -> np.ndarray:

@@ -13,7 +13,8 @@ import numpy as np
 
 import math
 
-from ._lib import FullResultC, FullTaskC, HitC, MapParamsC, MapStatsC, StageHitC, SwParams, check, lib
+from ._lib import (FullResultC, FullTaskC, HitC, MapParamsC, MapStatsC, PairC, PairParamsC, StageHitC, SwParams,
+                   check, lib)
 
 # fasta.h:26-42
 _LS_CODE = np.full(256, 255, dtype=np.uint8)
@@ -135,6 +136,20 @@ class MapResult:
     n_hits_per_read: np.ndarray
     edits: np.ndarray           # uint8 pool
     stage: np.ndarray | None
+    stats: dict
+
+
+PAIR_MODES = {"opp-in": 1, "opp-out": 2, "col-fw": 3, "col-bw": 4}
+
+
+@dataclass
+class PairResult:
+    hits: np.ndarray             # shrimp_hit pool: members of the pairs first, then the unpaired hits in read order
+    pairs: np.ndarray            # shrimp_pair records (hit_idx into hits)
+    n_pairs_per_pair: np.ndarray
+    n_unpaired_per_read: np.ndarray
+    n_paired_hits: int           # hits[:n_paired_hits] belong to pairs
+    edits: np.ndarray
     stats: dict
 
 
@@ -296,6 +311,43 @@ class GpuContext:
         stats = {k: int(getattr(st, k)) for k, _ in MapStatsC._fields_}
         return MapResult(hits[: n_hits.value], n_per[:n], edits[: e_used.value],
                          stage[: n_stage.value] if want_stage else None, stats)
+
+    def map_pairs(self, params: MapParams, scores: Scores, reads: np.ndarray, read_len, pair_mode: str = "opp-in",
+                  min_insert: int = 0, max_insert: int = 1000, half_paired: bool = True, initbp=None) -> "PairResult":
+        """handle_readpair (mapping.c:2504) for a chunk of pairs: rows 2k and 2k+1 of `reads` are mates."""
+        reads = np.ascontiguousarray(reads, dtype=np.uint32)
+        read_len = np.ascontiguousarray(read_len, dtype=np.int32)
+        n = reads.shape[0]
+        if n % 2:
+            raise ValueError("map_pairs needs an even number of reads (mates interleaved)")
+        npairs = n // 2
+        pc = params.to_c(scores, getattr(self, "colour_space", False))
+        pp = PairParamsC(PAIR_MODES[pair_mode], min_insert, max_insert, int(half_paired))
+        hits = np.zeros(max(1, npairs * params.num_outputs * 4), dtype=HitC)
+        pairs = np.zeros(max(1, npairs * params.num_outputs), dtype=PairC)
+        n_per_pair = np.zeros(max(1, npairs), dtype=np.int32)
+        n_unp = np.zeros(max(1, n), dtype=np.int32)
+        max_rl = int(read_len.max()) if n else 0
+        pool_cap = max(1024, n * 4 * max(1, max_rl))
+        if initbp is not None:
+            initbp = np.ascontiguousarray(initbp, dtype=np.int8)
+        while True:
+            edits = np.zeros(pool_cap, dtype=np.uint8)
+            n_hits, n_pairs_out, e_used = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+            st = MapStatsC()
+            rc = self._L.shrimp_gpu_map_pairs(
+                self._h, C.byref(pc), C.byref(pp), npairs, _ptr(reads), reads.shape[1] if n else 1, _ptr(read_len),
+                _ptr(initbp), _ptr(hits), hits.size, C.byref(n_hits), _ptr(pairs), pairs.size, C.byref(n_pairs_out),
+                _ptr(n_per_pair), _ptr(n_unp), _ptr(edits), pool_cap, C.byref(e_used), C.byref(st))
+            if rc == -5 and e_used.value > pool_cap:
+                pool_cap = int(e_used.value) + 1024
+                continue
+            check(rc, "shrimp_gpu_map_pairs")
+            break
+        stats = {k: int(getattr(st, k)) for k, _ in MapStatsC._fields_}
+        n_paired_hits = 2 * n_pairs_out.value
+        return PairResult(hits[: n_hits.value], pairs[: n_pairs_out.value], n_per_pair[:npairs], n_unp[:n],
+                          n_paired_hits, edits[: e_used.value], stats)
 
     def map_resident(self, params: MapParams, scores: Scores) -> dict:
         """Device stages only, on the reads the last map_reads call left in HBM (bench.py `value`)."""

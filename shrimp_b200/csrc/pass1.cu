@@ -80,8 +80,10 @@ __global__ void build_vec_tasks_kernel(const TaskBuildParams P) {
 }
 
 
-// one thread per read: read_pass1 (both strands) + read_get_vector_hits
-__global__ void pass1_select_kernel(const Pass1Params P) {
+// one thread per read: read_pass1 (both strands), mapping.c:1261-1366.  Serves the first pass of unpaired
+// reads, the only_paired pass of read pairs (pair_min != nullptr) and the half-paired second pass (saved
+// flags set, hits that already carry a positive score keep it, :1296).
+__global__ void pass1_replay_kernel(const Pass1Params P) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= P.n_reads) return;
   const MapParamsDev &M = P.M;
@@ -100,16 +102,21 @@ __global__ void pass1_select_kernel(const Pass1Params P) {
       const uint32_t hi = rg.x + k;
       DevHit h = P.hits[hi];
       P.writer[hi] = 0;
+      if (P.pair_min && P.pair_min[hi] < 0) continue;  // only_paired (:1272-1274)
       if (h.matches < M.min_matches) continue;
+      if (P.saved && P.saved[hi]) {  // :1281-1285
+        last_good_cn = h.cn;
+        last_good_g_off = h.g_off;
+        continue;
+      }
       // window overlap with the last good window (:1287-1293): llint + unsigned  <=  unsigned + int
       if (last_good_cn >= 0 && h.cn == last_good_cn &&
           (long long)h.g_off + (long long)ovl <= (long long)(unsigned int)(last_good_g_off + (unsigned int)window_len)) {
-        h.score_vector = 0;
-        h.pct_vector = 0;
         P.hits[hi].score_vector = 0;
         P.hits[hi].pct_vector = 0;
         continue;
       }
+      if (h.score_vector > 0) continue;  // :1296, only possible in a second pass
       int score = P.vtrue[ori][hi];
       bool hit_in_cache = false;
       if (M.hash_filter_calls) {
@@ -139,16 +146,25 @@ __global__ void pass1_select_kernel(const Pass1Params P) {
       }
     }
   }
-  // read_get_vector_hits (:1376-1411): min-heap of capacity num_tmp_outputs keyed on pass1_key
+  if (calls) atomicAdd(&P.stats[4], calls);
+  if (bypassed) atomicAdd(&P.stats[5], bypassed);
+  if (cells) atomicAdd((unsigned long long *)&P.stats[6], cells);
+}
+
+// one thread per read: read_get_vector_hits (:1376-1411): min-heap of capacity num_tmp_outputs keyed on pass1_key
+__global__ void select_unpaired_kernel(const Pass1Params P) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= P.n_reads) return;
+  const MapParamsDev &M = P.M;
   const bool absolute = M.vect_thr < 0;
   int32_t *a = P.sel + (size_t)r * M.num_tmp_outputs;
   int load = 0;
-  // keys of the heap entries are re-read from the hits (score_vector / pct_vector are final now)
 #define P1KEY(slot_) (absolute ? P.hits[slot_].score_vector : P.hits[slot_].pct_vector)
   for (int st = 0; st < 2; st++) {
     const uint2 rg = P.rs_range[2 * r + st];
     for (uint32_t k = 0; k < rg.y; k++) {
       const int32_t hi = (int32_t)(rg.x + k);
+      if (P.saved && P.saved[hi]) continue;
       const DevHit h = P.hits[hi];
       if (h.score_vector >= (int)abs_or_pct_d(M.vect_thr, M.vect_frac, (double)h.score_max) &&
           (load < M.num_tmp_outputs || (absolute ? h.score_vector : h.pct_vector) > P1KEY(a[0]))) {
@@ -158,7 +174,6 @@ __global__ void pass1_select_kernel(const Pass1Params P) {
           load++;
           int node = load, parent = node / 2;
           while (node > 1 && key < P1KEY(a[parent - 1])) {
-            // (a[node-1] is the new element while it bubbles up)
             int32_t tmp = a[parent - 1];
             a[parent - 1] = a[node - 1];
             a[node - 1] = tmp;
@@ -184,9 +199,6 @@ __global__ void pass1_select_kernel(const Pass1Params P) {
   }
 #undef P1KEY
   P.n_sel[r] = load;
-  if (calls) atomicAdd(&P.stats[4], calls);
-  if (bypassed) atomicAdd(&P.stats[5], bypassed);
-  if (cells) atomicAdd((unsigned long long *)&P.stats[6], cells);
 }
 
 int launch_build_vec_tasks(shrimp_gpu_ctx *ctx, const TaskBuildParams &P) {
@@ -197,8 +209,15 @@ int launch_build_vec_tasks(shrimp_gpu_ctx *ctx, const TaskBuildParams &P) {
   return SHRIMP_OK;
 }
 
-int launch_pass1_select(shrimp_gpu_ctx *ctx, const Pass1Params &P) {
-  pass1_select_kernel<<<(P.n_reads + 127) / 128, 128, 0, ctx->stream>>>(P);
+int launch_pass1_replay(shrimp_gpu_ctx *ctx, const Pass1Params &P) {
+  pass1_replay_kernel<<<(P.n_reads + 127) / 128, 128, 0, ctx->stream>>>(P);
+  SH_CUDA(cudaGetLastError());
+  SH_LAUNCHED(ctx, ST_PASS1);
+  return SHRIMP_OK;
+}
+
+int launch_select_unpaired(shrimp_gpu_ctx *ctx, const Pass1Params &P) {
+  select_unpaired_kernel<<<(P.n_reads + 127) / 128, 128, 0, ctx->stream>>>(P);
   SH_CUDA(cudaGetLastError());
   SH_LAUNCHED(ctx, ST_PASS1);
   return SHRIMP_OK;

@@ -9,7 +9,7 @@
 #include <stdlib.h>
 #include <algorithm>
 #include <cub/cub.cuh>
-#include "band.cuh"
+#include "chunk.cuh"
 
 namespace shrimp {
 
@@ -18,7 +18,8 @@ size_t scan_smem_bytes(int cap, int max_rl, int warps);
 
 int launch_scan(shrimp_gpu_ctx *ctx, ScanParams &P, int warps_per_cta, int n_ctas);
 int launch_build_vec_tasks(shrimp_gpu_ctx *ctx, const TaskBuildParams &P);
-int launch_pass1_select(shrimp_gpu_ctx *ctx, const Pass1Params &P);
+int launch_pass1_replay(shrimp_gpu_ctx *ctx, const Pass1Params &P);
+int launch_select_unpaired(shrimp_gpu_ctx *ctx, const Pass1Params &P);
 int launch_sw_full_ls(shrimp_gpu_ctx *ctx, const FullParams &P);
 int launch_sw_full_cs(shrimp_gpu_ctx *ctx, const FullParams &P);
 int launch_sw_full_ring(shrimp_gpu_ctx *ctx, const FullParams &P, bool cs);
@@ -62,28 +63,6 @@ __global__ void revcomp_reads_kernel(const uint32_t *in, uint32_t *out, int stri
   }
 }
 
-struct SelInfo {
-  int32_t hit_slot, read_idx, st, cn, gen_st, w_len;
-  uint32_t g_off;  // oriented (after reverse_hit)
-  int32_t score_vector, score_max, matches;
-};
-
-struct FullBuildParams {
-  GenomeView G;
-  MapParamsDev M;
-  const DevHit *hits;
-  const uint2 *rs_range;
-  const int32_t *read_len;
-  const int32_t *sel;
-  const int32_t *n_sel;
-  const int32_t *vtrue0;
-  const int8_t *initbp;
-  const int32_t *task_off;  // exclusive prefix sum of n_sel: tasks of read r start at task_off[r]
-  int n_reads;
-  FullTask *tasks;   // [sum n_sel], dense
-  SelInfo *info;
-};
-
 // one thread per (read, selected slot): hit_run_full_sw's orientation logic (mapping.c:353-361,
 // reverse_hit :254-263, anchor_reverse anchors.h:30-34)
 __global__ void build_full_tasks_kernel(const FullBuildParams P) {
@@ -91,60 +70,10 @@ __global__ void build_full_tasks_kernel(const FullBuildParams P) {
   const int NT = P.M.num_tmp_outputs;
   if (idx >= P.n_reads * NT) return;
   const int r = idx / NT, k = idx % NT;
+  if (k >= P.n_sel[r]) return;
   FullTask T;
-  memset(&T, 0, sizeof(T));
   SelInfo I;
-  memset(&I, 0, sizeof(I));
-  I.hit_slot = -1;
-  if (k < P.n_sel[r]) {
-    const int hi = P.sel[idx];
-    const DevHit h = P.hits[hi];
-    const uint2 r0 = P.rs_range[2 * r];
-    const int st = ((uint32_t)hi >= r0.x && (uint32_t)hi < r0.x + r0.y) ? 0 : 1;
-    const int rl = P.read_len[r];
-    const uint32_t coff = P.G.contig_off[h.cn], clen = P.G.contig_len[h.cn];
-    uint32_t g_off = h.g_off;
-    int ax = h.ax, ay = h.ay;
-    int gen_st = 0;
-    if (st != 0) {  // reverse_hit: the read is always aligned in its input orientation
-      g_off = clen - h.g_off - (uint32_t)h.w_len;
-      ax = -h.ax + (h.w_len - 1) - (h.alen - 1) - (h.awidth - 1);
-      ay = -h.ay + (rl - 1) - (h.alen - 1) + (h.awidth - 1);
-      gen_st = 1;
-    }
-    T.goff_global = coff + g_off;
-    T.goff_contig = g_off;
-    T.glen = h.w_len;
-    T.rlen = rl;
-    T.ridx = 2 * r;
-    T.ax = ax;
-    T.ay = ay;
-    T.alen = h.alen;
-    T.awidth = h.awidth;
-    T.thresh = (int)abs_or_pct_d(P.M.full_thr, P.M.full_frac, (double)h.score_max);
-    T.gen_st = gen_st;
-    if (!P.M.colour_space) {
-      T.maxscore = P.vtrue0[hi];  // sw_vector re-run of mapping.c:386 (same score on the flipped window)
-      T.run = T.maxscore >= T.thresh;
-    } else {
-      T.maxscore = h.score_vector;
-      T.run = 1;
-      T.initbp = P.initbp[r];
-    }
-    I.hit_slot = hi;
-    I.read_idx = r;
-    I.st = st;
-    I.cn = h.cn;
-    I.gen_st = gen_st;
-    I.w_len = h.w_len;
-    I.g_off = g_off;
-    I.score_vector = P.M.colour_space ? h.score_vector : T.maxscore;
-    I.score_max = h.score_max;
-    I.matches = h.matches;
-  }
-  else {
-    return;
-  }
+  make_full_task(P, r, P.sel[idx], T, I);
   const int out = P.task_off[r] + k;
   P.tasks[out] = T;
   P.info[out] = I;
@@ -153,7 +82,6 @@ __global__ void build_full_tasks_kernel(const FullBuildParams P) {
 // Ring-width class of every full-SW task (sw_full_ring.cu): the widest row of its band + the edge cell,
 // rounded up to 32/64/128/256; class RING_CLASSES = wider than any ring that fits shared memory, served by
 // the global-scratch kernels.  perm[c * n + rank] lists the task ids of class c.
-#define RING_CLASSES 4
 __global__ void classify_full_tasks_kernel(const FullTask *tasks, int n, int anchor_width, int match, int local,
                                            int max_class, int32_t *perm, uint32_t *cls_count) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -176,18 +104,6 @@ __global__ void classify_full_tasks_kernel(const FullTask *tasks, int n, int anc
   perm[(size_t)c * n + rank] = t;
 }
 
-struct Pipeline {
-  DevBuf d_in, d_reads, d_read_len, d_initbp, d_hits, d_rs_range, d_counters, d_overflow, d_scratch;
-  DevBuf d_task[2], d_vtrue[2], d_slot, d_writer, d_sel, d_nsel;
-  DevBuf d_ftasks, d_finfo, d_fresults, d_frow, d_fbp[RING_CLASSES + 1], d_fops, d_taskoff, d_scan_tmp, d_perm;
-  HostBuf h_info, h_results, h_ops, h_nsel, h_hits, h_range;
-  uint32_t hits_cap = 0;
-  // reads left resident by the last upload (shrimp_gpu_map_resident)
-  int res_n_reads = 0, res_stride = 0;
-  std::vector<int32_t> res_read_len;
-  size_t h2d_bytes = 0, d2h_bytes = 0;
-};
-
 void free_pipeline(shrimp_gpu_ctx *ctx) {
   Pipeline *p = (Pipeline *)ctx->pipeline;
   if (!p) return;
@@ -195,9 +111,11 @@ void free_pipeline(shrimp_gpu_ctx *ctx) {
                     &p->d_overflow, &p->d_scratch, &p->d_task[0], &p->d_task[1], &p->d_vtrue[0], &p->d_vtrue[1],
                     &p->d_slot, &p->d_writer, &p->d_sel, &p->d_nsel, &p->d_ftasks, &p->d_finfo, &p->d_fresults,
                     &p->d_frow, &p->d_fbp[0], &p->d_fbp[1], &p->d_fbp[2], &p->d_fbp[3], &p->d_fbp[4], &p->d_fops,
-                    &p->d_taskoff, &p->d_scan_tmp, &p->d_perm};
+                    &p->d_taskoff, &p->d_scan_tmp, &p->d_perm, &p->d_pair_min, &p->d_pair_max, &p->d_saved, &p->d_pairsel,
+                    &p->d_npairsel, &p->d_taskof, &p->d_pairoff};
   for (DevBuf *b : bufs) b->release();
-  HostBuf *hb[] = {&p->h_info, &p->h_results, &p->h_ops, &p->h_nsel, &p->h_hits, &p->h_range};
+  HostBuf *hb[] = {&p->h_info, &p->h_results, &p->h_ops, &p->h_nsel, &p->h_hits, &p->h_range,
+                   &p->h_pairsel, &p->h_npairsel, &p->h_saved};
   for (HostBuf *b : hb) b->release();
   delete p;
   ctx->pipeline = nullptr;
@@ -212,7 +130,7 @@ struct ctx_stream_guard {
 
 // Full SW over the n tasks of FP.tasks: classify by ring width, one ring launch per class and
 // sub-batch (scratch bounded to ~2 GB of back-pointers), global-scratch kernels for the rest.
-static int run_full_sw(shrimp_gpu_ctx *ctx, DevBuf &d_perm, DevBuf &d_row, DevBuf *d_bp /*[RING_CLASSES+1]*/,
+int run_full_sw(shrimp_gpu_ctx *ctx, DevBuf &d_perm, DevBuf &d_row, DevBuf *d_bp /*[RING_CLASSES+1]*/,
                        FullParams FP, int n, bool cs, uint32_t *d_cls_count) {
   if (n <= 0) return SHRIMP_OK;
   cudaStream_t st = ctx->stream;
@@ -277,16 +195,6 @@ static int run_full_sw(shrimp_gpu_ctx *ctx, DevBuf &d_perm, DevBuf &d_row, DevBu
 }
 
 // ---- host stage ---------------------------------------------------------------------------------
-struct HostHit {
-  SelInfo info;
-  FullResult res;
-  int score_full;
-  double pct_score_full;
-  int pass2_key;
-  double posterior;
-  int task_idx;
-};
-
 static int cmp_gen_start(const void *e1, const void *e2) {  // mapping.c:1485-1494
   const HostHit *a = *(HostHit *const *)e1, *b = *(HostHit *const *)e2;
   if (a->info.cn != b->info.cn) return a->info.cn - b->info.cn;
@@ -322,23 +230,15 @@ static void dedup_pass(HostHit **h, int *n, int (*cmp)(const void *, const void 
   *n = k;
 }
 
-}  // namespace shrimp
 
-using namespace shrimp;
-
-// resident = reuse the reads uploaded by the previous call (bench: inputs already in HBM);
-// device_only = stop after the last device stage (no D2H of results, no host pass 2).
-static int map_impl(shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, int n_reads, const uint32_t *reads, int stride,
-                    const int32_t *read_len, const int8_t *initbp, shrimp_hit *hits_out, int64_t hits_cap,
-                    int32_t *n_hits_per_read, uint8_t *edits, int64_t edits_cap, int64_t *n_hits, int64_t *edits_used,
-                    shrimp_stage_hit *stage, int64_t stage_cap, int64_t *n_stage, shrimp_map_stats *stats,
-                    bool resident, bool device_only) {
-  int64_t dummy_hits = 0;
-  if (device_only && !n_hits) n_hits = &dummy_hits;
+// ---- chunk stages -------------------------------------------------------------------------------
+// Validation, parameter block, upload of the reads and their reverse complements.
+int chunk_begin(Chunk &C, shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, int n_reads, const uint32_t *reads,
+                int stride, const int32_t *read_len, const int8_t *initbp, bool resident, const char *who) {
   if (resident) {
     Pipeline *pp = ctx ? (Pipeline *)ctx->pipeline : nullptr;
     if (!pp || pp->res_n_reads <= 0) {
-      set_error("shrimp_gpu_map_resident: no reads resident; call shrimp_gpu_map_reads first");
+      set_error("%s: no reads resident; call shrimp_gpu_map_reads first", who);
       return SHRIMP_E_STATE;
     }
     n_reads = pp->res_n_reads;
@@ -347,74 +247,67 @@ static int map_impl(shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, int n_read
     reads = (const uint32_t *)1;  // not dereferenced
     if (genome_of(ctx) && genome_of(ctx)->colour_space) initbp = (const int8_t *)1;
   }
-  if (!ctx || !mp || !reads || !read_len || n_reads < 0 || stride <= 0 || (!hits_out && !device_only) || !n_hits) {
-    set_error("shrimp_gpu_map_reads: invalid argument");
+  if (!ctx || !mp || !reads || !read_len || n_reads < 0 || stride <= 0) {
+    set_error("%s: invalid argument", who);
     return SHRIMP_E_ARG;
   }
   DeviceGenome *g = genome_of(ctx);
   if (!g || !g->have_index) {
-    set_error("shrimp_gpu_map_reads: genome/index not resident (shrimp_gpu_genome_load + shrimp_gpu_index_build)");
+    set_error("%s: genome/index not resident (shrimp_gpu_genome_load + shrimp_gpu_index_build)", who);
     return SHRIMP_E_STATE;
   }
   if (!ctx->sw.valid) {
-    set_error("shrimp_gpu_map_reads: shrimp_gpu_sw_setup() has not been called");
+    set_error("%s: shrimp_gpu_sw_setup() has not been called", who);
     return SHRIMP_E_STATE;
   }
   const bool cs = g->colour_space != 0;
   if (cs != (ctx->sw.use_colours != 0)) {
-    set_error("shrimp_gpu_map_reads: genome and scoring set-up disagree about colour space");
+    set_error("%s: genome and scoring set-up disagree about colour space", who);
     return SHRIMP_E_STATE;
   }
   if (cs && !initbp) {
-    set_error("shrimp_gpu_map_reads: colour-space reads need initbp");
+    set_error("%s: colour-space reads need initbp", who);
     return SHRIMP_E_ARG;
   }
   if (mp->gapless) {
-    set_error("shrimp_gpu_map_reads: gapless (-U / mirna) pass 1 is not wired into the chunk pipeline yet");
+    set_error("%s: gapless (-U / mirna) pass 1 is not wired into the chunk pipeline yet", who);
     return SHRIMP_E_ARG;
   }
   if (cs && mp->compute_mapping_qualities) {
     // hit_run_post_sw needs post_sw (common/sw-post.c), which is not on this path yet
-    set_error("shrimp_gpu_map_reads: colour space needs compute_mapping_qualities = 0 (--no-mapping-qualities) "
-              "until post_sw is implemented");
+    set_error("%s: colour space needs compute_mapping_qualities = 0 (--no-mapping-qualities) until post_sw is "
+              "implemented", who);
     return SHRIMP_E_ARG;
   }
-  if (mp->match_mode != 1 && mp->match_mode != 2) {
-    set_error("shrimp_gpu_map_reads: unpaired match_mode must be 1 or 2");
-    return SHRIMP_E_ARG;
-  }
-  *n_hits = 0;
-  if (edits_used) *edits_used = 0;
-  if (n_stage) *n_stage = 0;
-  if (stats) memset(stats, 0, sizeof(*stats));
-  if (n_hits_per_read) memset(n_hits_per_read, 0, sizeof(int32_t) * (size_t)n_reads);
-  if (n_reads == 0) return SHRIMP_OK;
-  if (!device_only && hits_cap < (int64_t)n_reads * mp->num_outputs) {
-    set_error("shrimp_gpu_map_reads: hits_cap must be at least n_reads * num_outputs");
-    return SHRIMP_E_ARG;
-  }
-  int max_rl = 0;
-  long long sum_rl = 0;
+  C.ctx = ctx;
+  C.g = g;
+  C.mp = mp;
+  C.n_reads = n_reads;
+  C.stride = stride;
+  C.cs = cs;
+  C.read_len = read_len;
+  C.n_ori = cs ? 2 : 1;
+  C.max_rl = 0;
+  C.sum_rl = 0;
   for (int r = 0; r < n_reads; r++) {
     if (read_len[r] < 0 || read_len[r] > stride * 8) {
-      set_error("shrimp_gpu_map_reads: read %d has length %d (stride holds %d)", r, read_len[r], stride * 8);
+      set_error("%s: read %d has length %d (stride holds %d)", who, r, read_len[r], stride * 8);
       return SHRIMP_E_ARG;
     }
-    if (read_len[r] > max_rl) max_rl = read_len[r];
-    sum_rl += read_len[r];
+    if (read_len[r] > C.max_rl) C.max_rl = read_len[r];
+    C.sum_rl += read_len[r];
   }
-  if (max_rl > ctx->sw.max_read_len) {
-    set_error("shrimp_gpu_map_reads: read length %d exceeds the qrlen given at setup (%d)", max_rl,
-              ctx->sw.max_read_len);
+  if (C.max_rl > ctx->sw.max_read_len) {
+    set_error("%s: read length %d exceeds the qrlen given at setup (%d)", who, C.max_rl, ctx->sw.max_read_len);
     return SHRIMP_E_ARG;
   }
   SH_CUDA(cudaSetDevice(ctx->device));
   if (!ctx->pipeline) ctx->pipeline = new Pipeline();
-  Pipeline *pl = (Pipeline *)ctx->pipeline;
+  Pipeline *pl = C.pl = (Pipeline *)ctx->pipeline;
   cudaStream_t st = ctx->stream;
   const SwScores &sw = ctx->sw;
 
-  MapParamsDev M;
+  MapParamsDev &M = C.M;
   memset(&M, 0, sizeof(M));
   M.colour_space = cs;
   M.match_mode = mp->match_mode;
@@ -442,14 +335,14 @@ static int map_impl(shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, int n_read
   M.Gflag = mp->Gflag;
   M.Tflag = mp->Tflag;
   M.anchor_width = sw.anchor_width;
-  const int max_wl = (int)(unsigned short)abs_or_pct_d(M.window_len, M.window_len_frac, (double)max_rl);
-  if (max_wl > sw.max_window_len) {
-    set_error("shrimp_gpu_map_reads: window length %d exceeds the dblen given at setup (%d)", max_wl,
-              sw.max_window_len);
+  C.max_wl = (int)(unsigned short)abs_or_pct_d(M.window_len, M.window_len_frac, (double)C.max_rl);
+  if (C.max_wl > sw.max_window_len) {
+    set_error("%s: window length %d exceeds the dblen given at setup (%d)", who, C.max_wl, sw.max_window_len);
     return SHRIMP_E_ARG;
   }
+  C.ops_stride = (size_t)C.max_rl + C.max_wl;
 
-  GenomeView G;
+  GenomeView &G = C.G;
   G.ls = g->d_ls.as<uint32_t>();
   G.ls_rc = g->d_ls_rc.as<uint32_t>();
   G.cs = g->d_cs.as<uint32_t>();
@@ -457,12 +350,12 @@ static int map_impl(shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, int n_read
   G.contig_off = g->d_off.as<uint32_t>();
   G.contig_len = g->d_len.as<uint32_t>();
   G.num_contigs = g->num_contigs;
-  IndexView IV;
-  memset(&IV, 0, sizeof(IV));
+  memset(&C.IV, 0, sizeof(C.IV));
   for (int sn = 0; sn < g->seeds.n_seeds; sn++) {
-    IV.offs[sn] = g->d_offs[sn].as<uint32_t>();
-    IV.pos[sn] = g->d_pos[sn].as<uint32_t>();
+    C.IV.offs[sn] = g->d_offs[sn].as<uint32_t>();
+    C.IV.pos[sn] = g->d_pos[sn].as<uint32_t>();
   }
+  if (n_reads == 0) return SHRIMP_OK;
 
   // ---- upload + reverse complements ------------------------------------------------------------
   const size_t in_bytes = (size_t)n_reads * stride * 4;
@@ -479,108 +372,122 @@ static int map_impl(shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, int n_read
     pl->res_n_reads = n_reads;
     pl->res_stride = stride;
     pl->res_read_len.assign(read_len, read_len + n_reads);
+    C.read_len = pl->res_read_len.data();
     pl->h2d_bytes = in_bytes + (size_t)n_reads * 4 + (cs ? (size_t)n_reads : 0);
   }
   SH_TRY(pl->d_counters.ensure(64 * 4));
   SH_TRY(pl->d_rs_range.ensure((size_t)n_reads * 2 * sizeof(uint2)));
-  uint32_t *cnt = pl->d_counters.as<uint32_t>();  // [0] hits_used [1] n_overflow [2] status [8..15] stats [16,17] full cells
-  uint32_t hits_used = 0;
-  {
-    ScopedStage ss(ctx, ST_SCAN);
-    revcomp_reads_kernel<<<(n_reads + 127) / 128, 128, 0, st>>>(pl->d_in.as<uint32_t>(), pl->d_reads.as<uint32_t>(),
-                                                                stride, n_reads, pl->d_read_len.as<int32_t>(),
-                                                                cs ? pl->d_initbp.as<int8_t>() : nullptr, cs);
-    SH_CUDA(cudaGetLastError());
-    SH_LAUNCHED(ctx, ST_SCAN);
+  C.cnt = pl->d_counters.as<uint32_t>();  // [0] hits_used [1] n_overflow [2] status [8..15] stats [16,17] full cells
+                                          // [20..23] vector task stats [32..36] ring-class counts
+  return SHRIMP_OK;
+}
 
-    // ---- seed scan -----------------------------------------------------------------------------
-    // slab size from the expected number of list entries per read strand: K(r) * L / 4^W
-    double est = 0;
-    const double avg_rl = (double)sum_rl / n_reads;
-    for (int sn = 0; sn < g->seeds.n_seeds; sn++)
-      est += std::max(0.0, avg_rl - g->seeds.span[sn] + 1) * ((double)g->total[sn] / (double)g->nbuckets[sn]);
-    int cap = 128;
-    while (cap < 2048 && cap < est * 3 + 64) cap <<= 1;
-    const int big_cap = 8192;
-    int k_max = g->seeds.n_seeds * std::max(1, max_rl);
-    if (pl->hits_cap == 0) pl->hits_cap = (uint32_t)std::max<long long>(1 << 20, (long long)n_reads * 2 * 16);
-    for (int attempt = 0;; attempt++) {
-      SH_TRY(pl->d_hits.ensure((size_t)pl->hits_cap * sizeof(DevHit)));
-      SH_TRY(pl->d_overflow.ensure((size_t)n_reads * 2 * 4));
-      SH_CUDA(cudaMemsetAsync(cnt, 0, 64 * 4, st));
-      ScanParams P;
-      memset(&P, 0, sizeof(P));
-      P.G = G;
-      P.I = IV;
-      P.S = g->seeds;
-      P.M = M;
-      P.reads = pl->d_reads.as<uint32_t>();
-      P.stride = stride;
-      P.n_reads = n_reads;
-      P.read_len = pl->d_read_len.as<int32_t>();
-      P.hits = pl->d_hits.as<DevHit>();
-      P.hits_cap = pl->hits_cap;
-      P.hits_used = cnt + 0;
-      P.rs_range = pl->d_rs_range.as<uint2>();
-      P.overflow = pl->d_overflow.as<uint32_t>();
-      P.n_overflow = cnt + 1;
-      P.status = cnt + 2;
-      P.stats = cnt + 8;
-      P.k_max = k_max;
-      P.max_rl = max_rl;
-      // small-slab pass over all read strands
-      P.cap = cap;
-      int warps = SCAN_WARPS_HOST;
-      while (warps > 1 && scan_smem_bytes(cap, max_rl, warps) > 100 * 1024) warps >>= 1;
-      const size_t smem = scan_smem_bytes(cap, max_rl, warps);
-      int ctas_per_sm = (int)std::max<size_t>(1, (size_t)(220 * 1024) / std::max<size_t>(smem, 1));
-      ctas_per_sm = std::min(ctas_per_sm, 2048 / (SCAN_WARPS_HOST * 32));
-      int n_ctas = ctx->sm_count * ctas_per_sm;
-      n_ctas = std::min<long long>(n_ctas, ((long long)n_reads * 2 + warps - 1) / warps);
-      P.scratch_ints = 2 * k_max + 2 * cap;
-      SH_TRY(pl->d_scratch.ensure(std::max((size_t)n_ctas * warps * P.scratch_ints,
-                                           (size_t)ctx->sm_count * (2 * k_max + 2 * big_cap)) * 4));
-      P.scratch = pl->d_scratch.as<int32_t>();
-      SH_TRY(launch_scan(ctx, P, warps, n_ctas));
-      uint32_t h3[3];
+// read reverse complement + seed scan -> hits, rs_range
+int chunk_scan(Chunk &C) {
+  shrimp_gpu_ctx *ctx = C.ctx;
+  Pipeline *pl = C.pl;
+  DeviceGenome *g = C.g;
+  cudaStream_t st = ctx->stream;
+  const int n_reads = C.n_reads, stride = C.stride, max_rl = C.max_rl;
+  uint32_t *cnt = C.cnt;
+  ScopedStage ss(ctx, ST_SCAN);
+  revcomp_reads_kernel<<<(n_reads + 127) / 128, 128, 0, st>>>(pl->d_in.as<uint32_t>(), pl->d_reads.as<uint32_t>(),
+                                                              stride, n_reads, pl->d_read_len.as<int32_t>(),
+                                                              C.cs ? pl->d_initbp.as<int8_t>() : nullptr, C.cs);
+  SH_CUDA(cudaGetLastError());
+  SH_LAUNCHED(ctx, ST_SCAN);
+  // slab size from the expected number of list entries per read strand: K(r) * L / 4^W
+  double est = 0;
+  const double avg_rl = (double)C.sum_rl / n_reads;
+  for (int sn = 0; sn < g->seeds.n_seeds; sn++)
+    est += std::max(0.0, avg_rl - g->seeds.span[sn] + 1) * ((double)g->total[sn] / (double)g->nbuckets[sn]);
+  int cap = 128;
+  while (cap < 2048 && cap < est * 3 + 64) cap <<= 1;
+  const int big_cap = 8192;
+  int k_max = g->seeds.n_seeds * std::max(1, max_rl);
+  if (pl->hits_cap == 0) pl->hits_cap = (uint32_t)std::max<long long>(1 << 20, (long long)n_reads * 2 * 16);
+  for (int attempt = 0;; attempt++) {
+    SH_TRY(pl->d_hits.ensure((size_t)pl->hits_cap * sizeof(DevHit)));
+    SH_TRY(pl->d_overflow.ensure((size_t)n_reads * 2 * 4));
+    SH_CUDA(cudaMemsetAsync(cnt, 0, 64 * 4, st));
+    ScanParams P;
+    memset(&P, 0, sizeof(P));
+    P.G = C.G;
+    P.I = C.IV;
+    P.S = g->seeds;
+    P.M = C.M;
+    P.reads = pl->d_reads.as<uint32_t>();
+    P.stride = stride;
+    P.n_reads = n_reads;
+    P.read_len = pl->d_read_len.as<int32_t>();
+    P.hits = pl->d_hits.as<DevHit>();
+    P.hits_cap = pl->hits_cap;
+    P.hits_used = cnt + 0;
+    P.rs_range = pl->d_rs_range.as<uint2>();
+    P.overflow = pl->d_overflow.as<uint32_t>();
+    P.n_overflow = cnt + 1;
+    P.status = cnt + 2;
+    P.stats = cnt + 8;
+    P.k_max = k_max;
+    P.max_rl = max_rl;
+    // small-slab pass over all read strands
+    P.cap = cap;
+    int warps = SCAN_WARPS_HOST;
+    while (warps > 1 && scan_smem_bytes(cap, max_rl, warps) > 100 * 1024) warps >>= 1;
+    const size_t smem = scan_smem_bytes(cap, max_rl, warps);
+    int ctas_per_sm = (int)std::max<size_t>(1, (size_t)(220 * 1024) / std::max<size_t>(smem, 1));
+    ctas_per_sm = std::min(ctas_per_sm, 2048 / (SCAN_WARPS_HOST * 32));
+    int n_ctas = ctx->sm_count * ctas_per_sm;
+    n_ctas = std::min<long long>(n_ctas, ((long long)n_reads * 2 + warps - 1) / warps);
+    P.scratch_ints = 2 * k_max + 2 * cap;
+    SH_TRY(pl->d_scratch.ensure(std::max((size_t)n_ctas * warps * P.scratch_ints,
+                                         (size_t)ctx->sm_count * (2 * k_max + 2 * big_cap)) * 4));
+    P.scratch = pl->d_scratch.as<int32_t>();
+    SH_TRY(launch_scan(ctx, P, warps, n_ctas));
+    uint32_t h3[3];
+    SH_CUDA(cudaMemcpyAsync(h3, cnt, 12, cudaMemcpyDeviceToHost, st));
+    SH_CUDA(cudaStreamSynchronize(st));
+    if (h3[1] > 0 && !(h3[2] & 1u)) {
+      // overflow pass: one warp per CTA with the big slab
+      P.work = pl->d_overflow.as<uint32_t>();
+      P.n_work = h3[1];
+      P.overflow = nullptr;
+      P.cap = big_cap;
+      P.scratch_ints = 2 * k_max + 2 * big_cap;
+      int ctas = std::min<int>(ctx->sm_count, (int)h3[1]);
+      SH_TRY(launch_scan(ctx, P, 1, ctas));
       SH_CUDA(cudaMemcpyAsync(h3, cnt, 12, cudaMemcpyDeviceToHost, st));
       SH_CUDA(cudaStreamSynchronize(st));
-      if (h3[1] > 0 && !(h3[2] & 1u)) {
-        // overflow pass: one warp per CTA with the big slab
-        P.work = pl->d_overflow.as<uint32_t>();
-        P.n_work = h3[1];
-        P.overflow = nullptr;
-        P.cap = big_cap;
-        P.scratch_ints = 2 * k_max + 2 * big_cap;
-        int ctas = std::min<int>(ctx->sm_count, (int)h3[1]);
-        SH_TRY(launch_scan(ctx, P, 1, ctas));
-        SH_CUDA(cudaMemcpyAsync(h3, cnt, 12, cudaMemcpyDeviceToHost, st));
-        SH_CUDA(cudaStreamSynchronize(st));
-      }
-      if (h3[2] & 2u) {
-        set_error("shrimp_gpu_map_reads: a read strand gathered more than %d index positions; the global-memory "
-                  "scan path for such reads is not implemented yet", big_cap);
-        return SHRIMP_E_RANGE;
-      }
-      if (h3[2] & 1u) {  // hit buffer too small: grow and redo the scan
-        if (attempt > 8) {
-          set_error("shrimp_gpu_map_reads: hit buffer overflow");
-          return SHRIMP_E_NOMEM;
-        }
-        pl->hits_cap *= 4;
-        continue;
-      }
-      hits_used = h3[0];
-      break;
     }
+    if (h3[2] & 2u) {
+      set_error("seed scan: a read strand gathered more than %d index positions; the global-memory scan path for "
+                "such reads is not implemented yet", big_cap);
+      return SHRIMP_E_RANGE;
+    }
+    if (h3[2] & 1u) {  // hit buffer too small: grow and redo the scan
+      if (attempt > 8) {
+        set_error("seed scan: hit buffer overflow");
+        return SHRIMP_E_NOMEM;
+      }
+      pl->hits_cap *= 4;
+      continue;
+    }
+    C.hits_used = h3[0];
+    break;
   }
+  return SHRIMP_OK;
+}
 
-  // ---- sw_vector over every eligible window ----------------------------------------------------
-  const size_t HU = std::max<uint32_t>(hits_used, 1);
+// sw_vector over every eligible window (matches >= min_matches): true scores per hit slot in d_vtrue
+int chunk_vector(Chunk &C) {
+  shrimp_gpu_ctx *ctx = C.ctx;
+  Pipeline *pl = C.pl;
+  cudaStream_t st = ctx->stream;
+  const bool cs = C.cs;
+  const size_t HU = std::max<uint32_t>(C.hits_used, 1);
   const size_t task_bytes = HU * 4 * 4 + ((HU + 3) & ~(size_t)3);
-  const int n_ori = cs ? 2 : 1;
   VecTaskArrays VT[2];
-  for (int o = 0; o < n_ori; o++) {
+  for (int o = 0; o < C.n_ori; o++) {
     SH_TRY(pl->d_task[o].ensure(task_bytes));
     SH_CUDA(cudaMemsetAsync(pl->d_task[o].p, 0, task_bytes, st));  // hit slots that stay gaps get glen = 0
     SH_TRY(pl->d_vtrue[o].ensure(HU * 4));
@@ -592,14 +499,14 @@ static int map_impl(shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, int n_read
     ScopedStage ss(ctx, ST_PASS1);
     TaskBuildParams TB;
     memset(&TB, 0, sizeof(TB));
-    TB.G = G;
-    TB.M = M;
+    TB.G = C.G;
+    TB.M = C.M;
     TB.hits = pl->d_hits.as<DevHit>();
     TB.rs_range = pl->d_rs_range.as<uint2>();
     TB.read_len = pl->d_read_len.as<int32_t>();
-    TB.n_reads = n_reads;
+    TB.n_reads = C.n_reads;
     for (int o = 0; o < 2; o++) {
-      char *tb = (char *)pl->d_task[o < n_ori ? o : 0].p;
+      char *tb = (char *)pl->d_task[o < C.n_ori ? o : 0].p;
       TB.goff[o] = (uint32_t *)tb;
       TB.glen[o] = (int32_t *)(tb + HU * 4);
       TB.ridx[o] = (int32_t *)(tb + HU * 8);
@@ -612,19 +519,298 @@ static int map_impl(shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, int n_read
       VT[o].initbp = cs ? TB.initbp_out[o] : nullptr;
     }
     TB.initbp = cs ? pl->d_initbp.as<int8_t>() : nullptr;
-    TB.slot = M.hash_filter_calls ? pl->d_slot.as<uint32_t>() : nullptr;
-    TB.task_stats = cnt + 20;
+    TB.slot = C.M.hash_filter_calls ? pl->d_slot.as<uint32_t>() : nullptr;
+    TB.task_stats = C.cnt + 20;
     SH_TRY(launch_build_vec_tasks(ctx, TB));
   }
-  if (hits_used > 0) {
+  if (C.hits_used > 0) {
     ScopedStage ss(ctx, ST_VECTOR);
-    for (int o = 0; o < n_ori; o++) {
-      const uint32_t *gen = cs ? (o ? G.cs_rc : G.cs) : G.ls;
-      const uint32_t *gen_ls = cs ? (o ? G.ls_rc : G.ls) : nullptr;
-      SH_TRY(launch_sw_vector(ctx, gen, gen_ls, pl->d_reads.as<uint32_t>(), stride, (int)hits_used, max_rl, max_wl,
-                              VT[o], pl->d_vtrue[o].as<int32_t>(), ST_VECTOR));
+    for (int o = 0; o < C.n_ori; o++) {
+      const uint32_t *gen = cs ? (o ? C.G.cs_rc : C.G.cs) : C.G.ls;
+      const uint32_t *gen_ls = cs ? (o ? C.G.ls_rc : C.G.ls) : nullptr;
+      SH_TRY(launch_sw_vector(ctx, gen, gen_ls, pl->d_reads.as<uint32_t>(), C.stride, (int)C.hits_used, C.max_rl,
+                              C.max_wl, VT[o], pl->d_vtrue[o].as<int32_t>(), ST_VECTOR));
     }
   }
+  return SHRIMP_OK;
+}
+
+Pass1Params chunk_pass1_params(Chunk &C) {
+  Pipeline *pl = C.pl;
+  Pass1Params PP;
+  memset(&PP, 0, sizeof(PP));
+  PP.M = C.M;
+  PP.hits = pl->d_hits.as<DevHit>();
+  PP.rs_range = pl->d_rs_range.as<uint2>();
+  PP.read_len = pl->d_read_len.as<int32_t>();
+  PP.n_reads = C.n_reads;
+  PP.vtrue[0] = pl->d_vtrue[0].as<int32_t>();
+  PP.vtrue[1] = pl->d_vtrue[C.n_ori - 1].as<int32_t>();
+  PP.slot = pl->d_slot.as<uint32_t>();
+  PP.writer = pl->d_writer.as<uint8_t>();
+  PP.sel = pl->d_sel.as<int32_t>();
+  PP.n_sel = pl->d_nsel.as<int32_t>();
+  PP.stats = C.cnt + 8;
+  return PP;
+}
+
+// dense full-SW task list of the hits selected per read (d_sel / d_nsel): exclusive scan (cub, plumbing) ->
+// task offsets -> one FullTask per selected hit, thresholds from full_thr (abs_or_pct form)
+int chunk_full_tasks_unpaired(Chunk &C, double full_thr, int *n_slots_out) {
+  shrimp_gpu_ctx *ctx = C.ctx;
+  Pipeline *pl = C.pl;
+  cudaStream_t st = ctx->stream;
+  const int n_reads = C.n_reads, NT = C.mp->num_tmp_outputs;
+  SH_TRY(pl->d_taskoff.ensure(((size_t)n_reads + 1) * 4));
+  int n_slots = 0;
+  size_t tmp_bytes = 0;
+  SH_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, pl->d_nsel.as<int32_t>(), pl->d_taskoff.as<int32_t>(),
+                                        n_reads + 1, st));
+  SH_TRY(pl->d_scan_tmp.ensure(tmp_bytes));
+  // n_sel has n_reads entries; entry n_reads of the scan needs a readable (zero) input slot
+  SH_CUDA(cudaMemsetAsync(pl->d_nsel.as<int32_t>() + n_reads, 0, 4, st));
+  SH_CUDA(cub::DeviceScan::ExclusiveSum(pl->d_scan_tmp.p, tmp_bytes, pl->d_nsel.as<int32_t>(),
+                                        pl->d_taskoff.as<int32_t>(), n_reads + 1, st));
+  ctx->launches += 1;
+  SH_CUDA(cudaMemcpyAsync(&n_slots, pl->d_taskoff.as<int32_t>() + n_reads, 4, cudaMemcpyDeviceToHost, st));
+  SH_CUDA(cudaStreamSynchronize(st));
+  const int n_grid = n_reads * NT;
+  SH_TRY(pl->d_ftasks.ensure((size_t)std::max(n_slots, 1) * sizeof(FullTask)));
+  SH_TRY(pl->d_finfo.ensure((size_t)std::max(n_slots, 1) * sizeof(SelInfo)));
+  SH_TRY(pl->d_fresults.ensure((size_t)std::max(n_slots, 1) * sizeof(FullResult)));
+  ScopedStage ss(ctx, ST_FULL);
+  FullBuildParams FB;
+  memset(&FB, 0, sizeof(FB));
+  FB.G = C.G;
+  FB.M = C.M;
+  FB.M.full_thr = full_thr;
+  FB.M.full_frac = full_thr / 100.0;
+  FB.hits = pl->d_hits.as<DevHit>();
+  FB.rs_range = pl->d_rs_range.as<uint2>();
+  FB.read_len = pl->d_read_len.as<int32_t>();
+  FB.sel = pl->d_sel.as<int32_t>();
+  FB.n_sel = pl->d_nsel.as<int32_t>();
+  FB.vtrue0 = pl->d_vtrue[0].as<int32_t>();
+  FB.initbp = C.cs ? pl->d_initbp.as<int8_t>() : nullptr;
+  FB.task_off = pl->d_taskoff.as<int32_t>();
+  FB.n_reads = n_reads;
+  FB.tasks = pl->d_ftasks.as<FullTask>();
+  FB.info = pl->d_finfo.as<SelInfo>();
+  build_full_tasks_kernel<<<(n_grid + 127) / 128, 128, 0, st>>>(FB);
+  SH_CUDA(cudaGetLastError());
+  SH_LAUNCHED(ctx, ST_FULL);
+  *n_slots_out = n_slots;
+  return SHRIMP_OK;
+}
+
+// full SW with traceback over d_ftasks[0, n_slots)
+int chunk_run_full(Chunk &C, int n_slots) {
+  shrimp_gpu_ctx *ctx = C.ctx;
+  Pipeline *pl = C.pl;
+  const SwScores &sw = ctx->sw;
+  ScopedStage ss(ctx, ST_FULL);
+  SH_TRY(pl->d_fops.ensure(C.ops_stride * (size_t)std::max(n_slots, 1)));
+  FullParams FP;
+  memset(&FP, 0, sizeof(FP));
+  FP.genome_fwd = C.G.ls;
+  FP.genome_rc = C.G.ls_rc;
+  FP.reads = pl->d_reads.as<uint32_t>();
+  FP.stride = C.stride;
+  FP.tasks = pl->d_ftasks.as<FullTask>();
+  FP.results = pl->d_fresults.as<FullResult>();
+  FP.ops = pl->d_fops.as<uint8_t>();
+  FP.max_glen = C.max_wl;
+  FP.max_rlen = C.max_rl;
+  FP.match = sw.match;
+  FP.mismatch = sw.mismatch;
+  FP.a_open = sw.a_open;
+  FP.a_ext = sw.a_ext;
+  FP.b_open = sw.b_open;
+  FP.b_ext = sw.b_ext;
+  FP.anchor_width = sw.anchor_width;
+  FP.Tflag = C.mp->Tflag;
+  FP.local = C.mp->Gflag ? 0 : 1;
+  FP.cells = (unsigned long long *)(C.cnt + 16);
+  FP.xover = sw.xover;
+  FP.indel_taboo_len = sw.indel_taboo_len;
+  return run_full_sw(ctx, pl->d_perm, pl->d_frow, pl->d_fbp, FP, n_slots, C.cs, C.cnt + 32);
+}
+
+// results of the n_slots full-SW tasks (+ n_sel per read and the counters) back to pinned host memory
+int chunk_fetch_full(Chunk &C, int n_slots, bool with_nsel) {
+  Pipeline *pl = C.pl;
+  cudaStream_t st = C.ctx->stream;
+  const int n_reads = C.n_reads;
+  pl->d2h_bytes += (size_t)n_slots * (sizeof(SelInfo) + sizeof(FullResult)) + C.ops_stride * (size_t)n_slots +
+                   (with_nsel ? (size_t)n_reads * 4 : 0) + 64 * 4;
+  SH_TRY(pl->h_info.ensure((size_t)n_slots * sizeof(SelInfo)));
+  SH_TRY(pl->h_results.ensure((size_t)n_slots * sizeof(FullResult)));
+  SH_TRY(pl->h_ops.ensure(C.ops_stride * (size_t)n_slots));
+  SH_TRY(pl->h_nsel.ensure((size_t)n_reads * 4 + 64 * 4));
+  SH_CUDA(cudaMemcpyAsync(pl->h_info.p, pl->d_finfo.p, (size_t)n_slots * sizeof(SelInfo), cudaMemcpyDeviceToHost, st));
+  SH_CUDA(cudaMemcpyAsync(pl->h_results.p, pl->d_fresults.p, (size_t)n_slots * sizeof(FullResult),
+                          cudaMemcpyDeviceToHost, st));
+  SH_CUDA(cudaMemcpyAsync(pl->h_ops.p, pl->d_fops.p, C.ops_stride * (size_t)n_slots, cudaMemcpyDeviceToHost, st));
+  if (with_nsel)
+    SH_CUDA(cudaMemcpyAsync(pl->h_nsel.p, pl->d_nsel.p, (size_t)n_reads * 4, cudaMemcpyDeviceToHost, st));
+  uint32_t *h_cnt = (uint32_t *)((char *)pl->h_nsel.p + (size_t)n_reads * 4);
+  SH_CUDA(cudaMemcpyAsync(h_cnt, C.cnt, 64 * 4, cudaMemcpyDeviceToHost, st));
+  SH_CUDA(cudaStreamSynchronize(st));
+  return SHRIMP_OK;
+}
+
+void chunk_stats(const Chunk &C, const uint32_t *hc, shrimp_map_stats *stats) {
+  if (!stats) return;
+  stats->heap_replays = hc[8 + 0];
+  stats->list_entries = hc[8 + 1];
+  stats->surviving_entries = hc[8 + 2];
+  stats->anchors = hc[8 + 3];
+  stats->hits = C.hits_used;
+  stats->vector_tasks = hc[20];
+  stats->device_vector_cells = *(const unsigned long long *)(hc + 22);
+  stats->vector_calls = hc[8 + 4];
+  stats->vector_bypassed = hc[8 + 5];
+  stats->vector_cells = *(const unsigned long long *)(hc + 8 + 6);
+  stats->full_cells = *(const unsigned long long *)(hc + 16);
+}
+
+// hit_run_full_sw's scores + hit_run_post_sw (mapping.c:1609-1625, letter space) for task idx
+void host_score_hit(const Chunk &C, int idx, HostHit &h) {
+  const shrimp_map_params *mp = C.mp;
+  h.info = C.pl->h_info.as<SelInfo>()[idx];
+  h.res = C.pl->h_results.as<FullResult>()[idx];
+  h.task_idx = idx;
+  h.posterior = 0.0;
+  h.score_full = h.res.score;
+  h.pct_score_full = (1000 * 100 * h.score_full) / h.info.score_max;
+  if (mp->compute_mapping_qualities && h.score_full > 0 && !C.cs) {
+    h.posterior = pow(2.0, ((double)h.res.score - (double)h.res.rmapped * (2.0 * mp->score_alpha + mp->score_beta)) /
+                               mp->score_alpha);
+    int ps = (int)rint(mp->score_alpha * log(h.posterior) / log(2.0) +
+                       (double)h.res.rmapped * (2.0 * mp->score_alpha + mp->score_beta));
+    if (ps < 0) ps = 0;
+    const int pct = (1000 * 100 * ps) / h.info.score_max;
+    h.score_full = ps;
+    h.pct_score_full = pct;
+  }
+}
+
+void host_fill_hit(const Chunk &C, const HostHit &h, int r, HostOut &O) {
+  if (O.n_out >= O.hits_cap) {
+    O.hits_short = true;
+    return;
+  }
+  shrimp_hit &o = O.hits[O.n_out++];
+  o.read_idx = r;
+  o.cn = h.info.cn;
+  o.gen_st = h.info.gen_st;
+  o.w_len = h.info.w_len;
+  o.g_off = h.info.g_off;
+  o.score_vector = h.info.score_vector;
+  o.score_full = h.score_full;
+  o.pass2_key = h.pass2_key;
+  o.score_max = h.info.score_max;
+  o.matches = h.info.matches;
+  o.sw_score = h.res.score;
+  o.posterior = h.posterior;
+  o.read_start = h.res.read_start;
+  o.rmapped = h.res.rmapped;
+  o.genome_start = h.res.genome_start;
+  o.gmapped = h.res.gmapped;
+  o.sfr_matches = h.res.matches;
+  o.mismatches = h.res.mismatches;
+  o.insertions = h.res.insertions;
+  o.deletions = h.res.deletions;
+  o.crossovers = h.res.crossovers;
+  o.edit_len = h.res.ops_len;
+  o.edit_off = O.e_used;
+  const uint8_t *OPS = C.pl->h_ops.as<uint8_t>();
+  if (O.edits && O.e_used + h.res.ops_len <= O.edits_cap)
+    memcpy(O.edits + O.e_used, OPS + C.ops_stride * (size_t)h.task_idx + h.res.ops_start, (size_t)h.res.ops_len);
+  else if (h.res.ops_len > 0)
+    O.edits_short = true;
+  O.e_used += h.res.ops_len;
+}
+
+// read_pass2 after the DP (mapping.c:1644-1722) for read r: tasks [task_base, task_base + n1).  Returns the
+// number of hits written to O; kept_tasks (optional) receives their task indices.
+int host_pass2_read(const Chunk &C, int r, int n1, int task_base, double full_thr, HostOut &O,
+                    std::vector<int> *kept_tasks) {
+  const shrimp_map_params *mp = C.mp;
+  std::vector<HostHit> hh((size_t)std::max(n1, 1));
+  std::vector<HostHit *> h2((size_t)n1 + 1);
+  int n2 = 0;
+  for (int k = 0; k < n1; k++) {
+    HostHit &h = hh[k];
+    host_score_hit(C, task_base + k, h);
+    if (!C.cs) {
+      O.pass2_vector_calls++;
+      O.pass2_vector_cells += (uint64_t)h.info.w_len * (uint64_t)C.read_len[r];
+    }
+    if (h.res.score > 0 || h.res.ops_len > 0) O.full_calls++;
+    h.pass2_key = full_thr < 0 ? h.score_full : (int)h.pct_score_full;
+    const double thr = full_thr < 0 ? -full_thr : h.info.score_max * (full_thr / 100.0);
+    if (h.score_full >= thr) h2[n2++] = &h;
+  }
+  dedup_pass(h2.data(), &n2, cmp_gen_start);
+  dedup_pass(h2.data(), &n2, cmp_gen_end);
+  qsort(h2.data(), n2, sizeof(HostHit *), cmp_score);
+  if (n2 > mp->num_outputs) n2 = mp->num_outputs;
+  if (mp->strata && n2 > 0) {
+    int i;
+    for (i = 1; i < n2 && h2[0]->score_full == h2[i]->score_full; i++)
+      ;
+    n2 = i;
+  }
+  if (n2 > 0 && !(mp->max_alignments == 0 || n2 <= mp->max_alignments)) n2 = 0;
+  for (int i = 0; i < n2; i++) {
+    host_fill_hit(C, *h2[i], r, O);
+    if (kept_tasks) kept_tasks->push_back(h2[i]->task_idx);
+  }
+  return n2;
+}
+
+}  // namespace shrimp
+
+using namespace shrimp;
+
+// resident = reuse the reads uploaded by the previous call (bench: inputs already in HBM);
+// device_only = stop after the last device stage (no D2H of results, no host pass 2).
+static int map_impl(shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, int n_reads, const uint32_t *reads, int stride,
+                    const int32_t *read_len, const int8_t *initbp, shrimp_hit *hits_out, int64_t hits_cap,
+                    int32_t *n_hits_per_read, uint8_t *edits, int64_t edits_cap, int64_t *n_hits, int64_t *edits_used,
+                    shrimp_stage_hit *stage, int64_t stage_cap, int64_t *n_stage, shrimp_map_stats *stats,
+                    bool resident, bool device_only) {
+  const char *who = resident ? "shrimp_gpu_map_resident" : "shrimp_gpu_map_reads";
+  int64_t dummy_hits = 0;
+  if (device_only && !n_hits) n_hits = &dummy_hits;
+  if ((!hits_out && !device_only) || !n_hits) {
+    set_error("%s: invalid argument", who);
+    return SHRIMP_E_ARG;
+  }
+  if (mp && mp->match_mode != 1 && mp->match_mode != 2) {
+    set_error("%s: unpaired match_mode must be 1 or 2", who);
+    return SHRIMP_E_ARG;
+  }
+  Chunk C;
+  SH_TRY(chunk_begin(C, ctx, mp, n_reads, reads, stride, read_len, initbp, resident, who));
+  n_reads = C.n_reads;
+  read_len = C.read_len;
+  *n_hits = 0;
+  if (edits_used) *edits_used = 0;
+  if (n_stage) *n_stage = 0;
+  if (stats) memset(stats, 0, sizeof(*stats));
+  if (n_hits_per_read) memset(n_hits_per_read, 0, sizeof(int32_t) * (size_t)n_reads);
+  if (n_reads == 0) return SHRIMP_OK;
+  if (!device_only && hits_cap < (int64_t)n_reads * mp->num_outputs) {
+    set_error("%s: hits_cap must be at least n_reads * num_outputs", who);
+    return SHRIMP_E_ARG;
+  }
+  Pipeline *pl = C.pl;
+  cudaStream_t st = ctx->stream;
+  pl->d2h_bytes = 0;
+  SH_TRY(chunk_scan(C));
+  SH_TRY(chunk_vector(C));
 
   // ---- pass-1 replay + top-k -------------------------------------------------------------------
   const int NT = mp->num_tmp_outputs;
@@ -632,28 +818,17 @@ static int map_impl(shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, int n_read
   SH_TRY(pl->d_nsel.ensure(((size_t)n_reads + 1) * 4));
   {
     ScopedStage ss(ctx, ST_PASS1);
-    Pass1Params PP;
-    memset(&PP, 0, sizeof(PP));
-    PP.M = M;
-    PP.hits = pl->d_hits.as<DevHit>();
-    PP.rs_range = pl->d_rs_range.as<uint2>();
-    PP.read_len = pl->d_read_len.as<int32_t>();
-    PP.n_reads = n_reads;
-    PP.vtrue[0] = pl->d_vtrue[0].as<int32_t>();
-    PP.vtrue[1] = pl->d_vtrue[n_ori - 1].as<int32_t>();
-    PP.slot = pl->d_slot.as<uint32_t>();
-    PP.writer = pl->d_writer.as<uint8_t>();
-    PP.sel = pl->d_sel.as<int32_t>();
-    PP.n_sel = pl->d_nsel.as<int32_t>();
-    PP.stats = cnt + 8;
-    SH_TRY(launch_pass1_select(ctx, PP));
+    Pass1Params PP = chunk_pass1_params(C);
+    SH_TRY(launch_pass1_replay(ctx, PP));
+    SH_TRY(launch_select_unpaired(ctx, PP));
   }
 
   // ---- stage dump (tests) ---------------------------------------------------------------------
   if (stage) {
+    const size_t HU = std::max<uint32_t>(C.hits_used, 1);
     SH_TRY(pl->h_hits.ensure(HU * sizeof(DevHit)));
     SH_TRY(pl->h_range.ensure((size_t)n_reads * 2 * sizeof(uint2)));
-    SH_CUDA(cudaMemcpyAsync(pl->h_hits.p, pl->d_hits.p, (size_t)hits_used * sizeof(DevHit), cudaMemcpyDeviceToHost, st));
+    SH_CUDA(cudaMemcpyAsync(pl->h_hits.p, pl->d_hits.p, (size_t)C.hits_used * sizeof(DevHit), cudaMemcpyDeviceToHost, st));
     SH_CUDA(cudaMemcpyAsync(pl->h_range.p, pl->d_rs_range.p, (size_t)n_reads * 2 * sizeof(uint2),
                             cudaMemcpyDeviceToHost, st));
     SH_CUDA(cudaStreamSynchronize(st));
@@ -663,7 +838,7 @@ static int map_impl(shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, int n_read
     for (int rs = 0; rs < 2 * n_reads; rs++) {
       for (uint32_t k = 0; k < RG[rs].y; k++) {
         if (ns >= stage_cap) {
-          set_error("shrimp_gpu_map_reads: stage_cap too small");
+          set_error("%s: stage_cap too small", who);
           return SHRIMP_E_NOMEM;
         }
         const DevHit &h = H[RG[rs].x + k];
@@ -688,218 +863,44 @@ static int map_impl(shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, int n_read
   }
 
   // ---- full SW on the selected hits ------------------------------------------------------------
-  // dense task list: exclusive scan of n_sel (cub, plumbing) -> task offsets per read
-  SH_TRY(pl->d_taskoff.ensure(((size_t)n_reads + 1) * 4));
   int n_slots = 0;
-  {
-    size_t tmp_bytes = 0;
-    SH_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, pl->d_nsel.as<int32_t>(), pl->d_taskoff.as<int32_t>(),
-                                          n_reads + 1, st));
-    SH_TRY(pl->d_scan_tmp.ensure(tmp_bytes));
-    // n_sel has n_reads entries; entry n_reads of the scan needs a readable (zero) input slot
-    SH_CUDA(cudaMemsetAsync(pl->d_nsel.as<int32_t>() + n_reads, 0, 4, st));
-    SH_CUDA(cub::DeviceScan::ExclusiveSum(pl->d_scan_tmp.p, tmp_bytes, pl->d_nsel.as<int32_t>(),
-                                          pl->d_taskoff.as<int32_t>(), n_reads + 1, st));
-    ctx->launches += 1;
-    SH_CUDA(cudaMemcpyAsync(&n_slots, pl->d_taskoff.as<int32_t>() + n_reads, 4, cudaMemcpyDeviceToHost, st));
-    SH_CUDA(cudaStreamSynchronize(st));
-  }
-  const int n_grid = n_reads * NT;
-  SH_TRY(pl->d_ftasks.ensure((size_t)std::max(n_slots, 1) * sizeof(FullTask)));
-  SH_TRY(pl->d_finfo.ensure((size_t)std::max(n_slots, 1) * sizeof(SelInfo)));
-  SH_TRY(pl->d_fresults.ensure((size_t)std::max(n_slots, 1) * sizeof(FullResult)));
-  const size_t ops_stride = (size_t)max_rl + max_wl;
-  {
-    ScopedStage ss(ctx, ST_FULL);
-    FullBuildParams FB;
-    memset(&FB, 0, sizeof(FB));
-    FB.G = G;
-    FB.M = M;
-    FB.hits = pl->d_hits.as<DevHit>();
-    FB.rs_range = pl->d_rs_range.as<uint2>();
-    FB.read_len = pl->d_read_len.as<int32_t>();
-    FB.sel = pl->d_sel.as<int32_t>();
-    FB.n_sel = pl->d_nsel.as<int32_t>();
-    FB.vtrue0 = pl->d_vtrue[0].as<int32_t>();
-    FB.initbp = cs ? pl->d_initbp.as<int8_t>() : nullptr;
-    FB.task_off = pl->d_taskoff.as<int32_t>();
-    FB.n_reads = n_reads;
-    FB.tasks = pl->d_ftasks.as<FullTask>();
-    FB.info = pl->d_finfo.as<SelInfo>();
-    build_full_tasks_kernel<<<(n_grid + 127) / 128, 128, 0, st>>>(FB);
-    SH_CUDA(cudaGetLastError());
-    SH_LAUNCHED(ctx, ST_FULL);
-
-    SH_TRY(pl->d_fops.ensure(ops_stride * (size_t)std::max(n_slots, 1)));
-    FullParams FP;
-    memset(&FP, 0, sizeof(FP));
-    FP.genome_fwd = G.ls;
-    FP.genome_rc = G.ls_rc;
-    FP.reads = pl->d_reads.as<uint32_t>();
-    FP.stride = stride;
-    FP.tasks = pl->d_ftasks.as<FullTask>();
-    FP.results = pl->d_fresults.as<FullResult>();
-    FP.ops = pl->d_fops.as<uint8_t>();
-    FP.max_glen = max_wl;
-    FP.max_rlen = max_rl;
-    FP.match = sw.match;
-    FP.mismatch = sw.mismatch;
-    FP.a_open = sw.a_open;
-    FP.a_ext = sw.a_ext;
-    FP.b_open = sw.b_open;
-    FP.b_ext = sw.b_ext;
-    FP.anchor_width = sw.anchor_width;
-    FP.Tflag = mp->Tflag;
-    FP.local = mp->Gflag ? 0 : 1;
-    FP.cells = (unsigned long long *)(cnt + 16);
-    FP.xover = sw.xover;
-    FP.indel_taboo_len = sw.indel_taboo_len;
-    SH_TRY(run_full_sw(ctx, pl->d_perm, pl->d_frow, pl->d_fbp, FP, n_slots, cs, cnt + 32));
-  }
+  SH_TRY(chunk_full_tasks_unpaired(C, mp->sw_full_threshold, &n_slots));
+  SH_TRY(chunk_run_full(C, n_slots));
 
   if (device_only) {
     SH_TRY(pl->h_nsel.ensure((size_t)n_reads * 4 + 64 * 4));
     uint32_t *hc = (uint32_t *)((char *)pl->h_nsel.p + (size_t)n_reads * 4);
-    SH_CUDA(cudaMemcpyAsync(hc, cnt, 64 * 4, cudaMemcpyDeviceToHost, st));
+    SH_CUDA(cudaMemcpyAsync(hc, C.cnt, 64 * 4, cudaMemcpyDeviceToHost, st));
     SH_CUDA(cudaStreamSynchronize(st));
-    if (stats) {
-      stats->heap_replays = hc[8 + 0];
-      stats->list_entries = hc[8 + 1];
-      stats->surviving_entries = hc[8 + 2];
-      stats->anchors = hc[8 + 3];
-      stats->hits = hits_used;
-      stats->vector_tasks = hc[20];
-      stats->device_vector_cells = *(unsigned long long *)(hc + 22);
-      stats->vector_calls = hc[8 + 4];
-      stats->vector_bypassed = hc[8 + 5];
-      stats->vector_cells = *(unsigned long long *)(hc + 8 + 6);
-      stats->full_cells = *(unsigned long long *)(hc + 16);
-    }
+    chunk_stats(C, hc, stats);
     return SHRIMP_OK;
   }
-  // ---- results back to the host ------------------------------------------------------------------
-  pl->d2h_bytes = (size_t)n_slots * (sizeof(SelInfo) + sizeof(FullResult)) + ops_stride * (size_t)n_slots +
-                  (size_t)n_reads * 4 + 64 * 4;
-  SH_TRY(pl->h_info.ensure((size_t)n_slots * sizeof(SelInfo)));
-  SH_TRY(pl->h_results.ensure((size_t)n_slots * sizeof(FullResult)));
-  SH_TRY(pl->h_ops.ensure(ops_stride * (size_t)n_slots));
-  SH_TRY(pl->h_nsel.ensure((size_t)n_reads * 4 + 64 * 4));
-  SH_CUDA(cudaMemcpyAsync(pl->h_info.p, pl->d_finfo.p, (size_t)n_slots * sizeof(SelInfo), cudaMemcpyDeviceToHost, st));
-  SH_CUDA(cudaMemcpyAsync(pl->h_results.p, pl->d_fresults.p, (size_t)n_slots * sizeof(FullResult),
-                          cudaMemcpyDeviceToHost, st));
-  SH_CUDA(cudaMemcpyAsync(pl->h_ops.p, pl->d_fops.p, ops_stride * (size_t)n_slots, cudaMemcpyDeviceToHost, st));
-  SH_CUDA(cudaMemcpyAsync(pl->h_nsel.p, pl->d_nsel.p, (size_t)n_reads * 4, cudaMemcpyDeviceToHost, st));
-  uint32_t *h_cnt = (uint32_t *)((char *)pl->h_nsel.p + (size_t)n_reads * 4);
-  SH_CUDA(cudaMemcpyAsync(h_cnt, cnt, 64 * 4, cudaMemcpyDeviceToHost, st));
-  SH_CUDA(cudaStreamSynchronize(st));
-
-  // ---- host stage: read_pass2 after the DP (mapping.c:1644-1722) -------------------------------
-  const SelInfo *INFO = pl->h_info.as<SelInfo>();
-  const FullResult *RES = pl->h_results.as<FullResult>();
+  // ---- results back to the host + host stage: read_pass2 after the DP ----------------------------
+  SH_TRY(chunk_fetch_full(C, n_slots, true));
+  const uint32_t *h_cnt = (const uint32_t *)((char *)pl->h_nsel.p + (size_t)n_reads * 4);
   const int32_t *NSEL = pl->h_nsel.as<int32_t>();
-  const uint8_t *OPS = pl->h_ops.as<uint8_t>();
-  std::vector<HostHit> hh((size_t)NT);
-  std::vector<HostHit *> h2((size_t)NT + 1);
-  int64_t n_out = 0, e_used = 0;
-  uint64_t full_calls = 0, pass2_vector_calls = 0, pass2_vector_cells = 0;
-  bool edits_short = false;
+  HostOut O;
+  memset(&O, 0, sizeof(O));
+  O.hits = hits_out;
+  O.hits_cap = hits_cap;
+  O.edits = edits;
+  O.edits_cap = edits_cap;
   int task_base = 0;
   for (int r = 0; r < n_reads; r++) {
-    const int n1 = NSEL[r];
-    int n2 = 0;
-    for (int k = 0; k < n1; k++) {
-      const int idx = task_base + k;
-      HostHit &h = hh[k];
-      h.info = INFO[idx];
-      h.res = RES[idx];
-      h.task_idx = idx;
-      h.posterior = 0.0;
-      if (!cs) {
-        pass2_vector_calls++;
-        pass2_vector_cells += (uint64_t)h.info.w_len * (uint64_t)read_len[r];
-      }
-      h.score_full = h.res.score;
-      if (h.res.score > 0 || h.res.ops_len > 0) full_calls++;
-      h.pct_score_full = (1000 * 100 * h.score_full) / h.info.score_max;
-      if (mp->compute_mapping_qualities && h.score_full > 0 && !cs) {  // hit_run_post_sw :1609-1625
-        h.posterior = pow(2.0, ((double)h.res.score - (double)h.res.rmapped * (2.0 * mp->score_alpha + mp->score_beta)) /
-                                   mp->score_alpha);
-        int ps = (int)rint(mp->score_alpha * log(h.posterior) / log(2.0) +
-                           (double)h.res.rmapped * (2.0 * mp->score_alpha + mp->score_beta));
-        if (ps < 0) ps = 0;
-        const int pct = (1000 * 100 * ps) / h.info.score_max;
-        h.score_full = ps;
-        h.pct_score_full = pct;
-      }
-      h.pass2_key = mp->sw_full_threshold < 0 ? h.score_full : (int)h.pct_score_full;
-      const double thr = mp->sw_full_threshold < 0 ? -mp->sw_full_threshold
-                                                   : h.info.score_max * (mp->sw_full_threshold / 100.0);
-      if (h.score_full >= thr) h2[n2++] = &h;
-    }
-    dedup_pass(h2.data(), &n2, cmp_gen_start);
-    dedup_pass(h2.data(), &n2, cmp_gen_end);
-    qsort(h2.data(), n2, sizeof(HostHit *), cmp_score);
-    if (n2 > mp->num_outputs) n2 = mp->num_outputs;
-    if (mp->strata && n2 > 0) {
-      int i;
-      for (i = 1; i < n2 && h2[0]->score_full == h2[i]->score_full; i++)
-        ;
-      n2 = i;
-    }
-    if (n2 > 0 && !(mp->max_alignments == 0 || n2 <= mp->max_alignments)) n2 = 0;
-    for (int i = 0; i < n2; i++) {
-      const HostHit &h = *h2[i];
-      shrimp_hit &o = hits_out[n_out++];
-      o.read_idx = r;
-      o.cn = h.info.cn;
-      o.gen_st = h.info.gen_st;
-      o.w_len = h.info.w_len;
-      o.g_off = h.info.g_off;
-      o.score_vector = h.info.score_vector;
-      o.score_full = h.score_full;
-      o.pass2_key = h.pass2_key;
-      o.score_max = h.info.score_max;
-      o.matches = h.info.matches;
-      o.sw_score = h.res.score;
-      o.posterior = h.posterior;
-      o.read_start = h.res.read_start;
-      o.rmapped = h.res.rmapped;
-      o.genome_start = h.res.genome_start;
-      o.gmapped = h.res.gmapped;
-      o.sfr_matches = h.res.matches;
-      o.mismatches = h.res.mismatches;
-      o.insertions = h.res.insertions;
-      o.deletions = h.res.deletions;
-      o.crossovers = h.res.crossovers;
-      o.edit_len = h.res.ops_len;
-      o.edit_off = e_used;
-      if (edits && e_used + h.res.ops_len <= edits_cap)
-        memcpy(edits + e_used, OPS + ops_stride * (size_t)h.task_idx + h.res.ops_start, (size_t)h.res.ops_len);
-      else if (h.res.ops_len > 0)
-        edits_short = true;
-      e_used += h.res.ops_len;
-    }
+    const int n2 = host_pass2_read(C, r, NSEL[r], task_base, mp->sw_full_threshold, O, nullptr);
     if (n_hits_per_read) n_hits_per_read[r] = n2;
-    task_base += n1;
+    task_base += NSEL[r];
   }
-  *n_hits = n_out;
-  if (edits_used) *edits_used = e_used;
+  *n_hits = O.n_out;
+  if (edits_used) *edits_used = O.e_used;
   if (stats) {
-    stats->heap_replays = h_cnt[8 + 0];
-    stats->list_entries = h_cnt[8 + 1];
-    stats->surviving_entries = h_cnt[8 + 2];
-    stats->anchors = h_cnt[8 + 3];
-    stats->hits = hits_used;
-    stats->vector_tasks = h_cnt[20];
-    stats->device_vector_cells = *(unsigned long long *)(h_cnt + 22);
-    stats->vector_calls = (uint64_t)h_cnt[8 + 4] + pass2_vector_calls;
-    stats->vector_bypassed = h_cnt[8 + 5];
-    stats->vector_cells = *(unsigned long long *)(h_cnt + 8 + 6) + pass2_vector_cells;
-    stats->full_calls = full_calls;
-    stats->full_cells = *(unsigned long long *)(h_cnt + 16);
+    chunk_stats(C, h_cnt, stats);
+    stats->vector_calls += O.pass2_vector_calls;
+    stats->vector_cells += O.pass2_vector_cells;
+    stats->full_calls = O.full_calls;
   }
-  if (edits_short && edits) {
-    set_error("shrimp_gpu_map_reads: edits_cap too small, %lld bytes needed", (long long)e_used);
+  if (O.edits_short && edits) {
+    set_error("%s: edits_cap too small, %lld bytes needed", who, (long long)O.e_used);
     return SHRIMP_E_NOMEM;
   }
   return SHRIMP_OK;

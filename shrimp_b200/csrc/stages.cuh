@@ -75,6 +75,8 @@ struct Pass1Params {
   int32_t *sel;              // [n_reads][num_tmp_outputs] hit slots in heap-array order
   int32_t *n_sel;            // [n_reads]
   uint32_t *stats;           // [4] vector calls the reference would make, [5] bypassed, [6] cells (lo), [7] cells (hi)
+  const int32_t *pair_min;   // read pairs, only_paired pass: first partner index per hit slot (-1 = none); else nullptr
+  const uint8_t *saved;      // half-paired second pass: hits kept by the paired pass 2; else nullptr
 };
 
 struct FullTask {
