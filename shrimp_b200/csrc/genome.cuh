@@ -5,6 +5,7 @@
 namespace shrimp {
 
 #define SHRIMP_MAX_SEEDS 16
+#define SHRIMP_MAX_RUNS 8
 
 // Seed table handed to kernels by value (the reference keeps `seed[]` as a global, gmapper.h:158).
 struct SeedTable {
@@ -14,6 +15,13 @@ struct SeedTable {
   unsigned long long mask[SHRIMP_MAX_SEEDS];
   int span[SHRIMP_MAX_SEEDS];
   int weight[SHRIMP_MAX_SEEDS];
+  // fast projection (scan.cu): the seed as runs of consecutive care positions, in k-mer order.  Run q takes
+  // run_len bases starting at base run_src of the k-mer and drops them at base run_dst of the bucket id.
+  // n_runs = 0: no fast form (span > 32, more than SHRIMP_MAX_RUNS runs, or -H) -> generic kmer_to_mapidx.
+  unsigned char n_runs[SHRIMP_MAX_SEEDS];
+  unsigned char run_src[SHRIMP_MAX_SEEDS][SHRIMP_MAX_RUNS];
+  unsigned char run_len[SHRIMP_MAX_SEEDS][SHRIMP_MAX_RUNS];
+  unsigned char run_dst[SHRIMP_MAX_SEEDS][SHRIMP_MAX_RUNS];
 };
 
 // HBM layout: every orientation of the genome is ONE packed 4-bit array in global coordinates

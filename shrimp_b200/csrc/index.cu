@@ -228,6 +228,32 @@ extern "C" int shrimp_gpu_index_build(shrimp_gpu_ctx *ctx, int n_seeds, const ui
     S.weight[sn] = weights[sn];
     if (spans[sn] > S.max_span) S.max_span = spans[sn];
     if (spans[sn] < S.min_span) S.min_span = spans[sn];
+    // runs of care positions in k-mer order: k-mer base j pairs with mask bit span-1-j (seeds.c:9-42), and
+    // the first care base lands in the lowest two bits of the bucket id (kmer_to_mapidx_orig, gmapper.h:349-368)
+    S.n_runs[sn] = 0;
+    if (!hflag && spans[sn] <= 32) {
+      int nr = 0, rank = 0;
+      bool ok = true;
+      for (int j = 0; j < spans[sn];) {
+        if (!((masks[sn] >> (spans[sn] - 1 - j)) & 1ull)) {
+          j++;
+          continue;
+        }
+        int e = j;
+        while (e < spans[sn] && ((masks[sn] >> (spans[sn] - 1 - e)) & 1ull)) e++;
+        if (nr == SHRIMP_MAX_RUNS) {
+          ok = false;
+          break;
+        }
+        S.run_src[sn][nr] = (unsigned char)j;
+        S.run_len[sn][nr] = (unsigned char)(e - j);
+        S.run_dst[sn][nr] = (unsigned char)rank;
+        rank += e - j;
+        nr++;
+        j = e;
+      }
+      if (ok) S.n_runs[sn] = (unsigned char)nr;
+    }
   }
   SH_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;

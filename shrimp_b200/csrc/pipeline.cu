@@ -14,7 +14,9 @@
 namespace shrimp {
 
 // ---- entry points of the other translation units -----------------------------------------------
-size_t scan_smem_bytes(int cap, int max_rl, int warps);
+size_t scan_smem_bytes(int cap, int max_rl, int k_cap, int bm_log2, int warps);
+size_t scan_big_smem_bytes(int cap, int max_rl, int k_cap, int bm_log2);
+int launch_scan_big(shrimp_gpu_ctx *ctx, ScanParams &P, int n_ctas);
 
 int launch_scan(shrimp_gpu_ctx *ctx, ScanParams &P, int warps_per_cta, int n_ctas);
 int launch_build_vec_tasks(shrimp_gpu_ctx *ctx, const TaskBuildParams &P);
@@ -396,14 +398,34 @@ int chunk_scan(Chunk &C) {
                                                               C.cs ? pl->d_initbp.as<int8_t>() : nullptr, C.cs);
   SH_CUDA(cudaGetLastError());
   SH_LAUNCHED(ctx, ST_SCAN);
-  // slab size from the expected number of list entries per read strand: K(r) * L / 4^W
+  // expected number of list entries per read strand: K(r) * L / 4^W
   double est = 0;
   const double avg_rl = (double)C.sum_rl / n_reads;
-  for (int sn = 0; sn < g->seeds.n_seeds; sn++)
+  const int mkp = C.cs ? 1 : 0;
+  int K_max = 0;
+  for (int sn = 0; sn < g->seeds.n_seeds; sn++) {
     est += std::max(0.0, avg_rl - g->seeds.span[sn] + 1) * ((double)g->total[sn] / (double)g->nbuckets[sn]);
-  int cap = 128;
-  while (cap < 2048 && cap < est * 3 + 64) cap <<= 1;
-  const int big_cap = 8192;
+    K_max += std::max(0, max_rl - g->seeds.span[sn] + 1 - mkp);
+  }
+  const bool filt = C.M.use_region_counts != 0;
+  // warp kernel: candidate slots after the bitmap filter (or all entries when there is no region filter),
+  // bitmaps of >= 16 bits per expected entry
+  int cap = filt ? 256 : 128;
+  if (!filt)
+    while (cap < 2048 && cap < est * 3 + 64) cap <<= 1;
+  int bm_log2 = 10;
+  if (filt)
+    while (bm_log2 < 15 && (1 << bm_log2) < est * 16) bm_log2++;
+  else
+    bm_log2 = 5;
+  const int k_cap = std::max(32, std::min(K_max, 1024));
+  const bool small_useful = !filt || est * 8 <= (double)(1 << 15);
+  // CTA kernel: 2^19-bit bitmaps, 8192 candidates
+  const int big_cap = 8192, big_bm_log2 = filt ? 19 : 5, big_k_cap = std::max(32, K_max);
+  if (scan_big_smem_bytes(big_cap, max_rl, big_k_cap, big_bm_log2) > 226 * 1024) {
+    set_error("seed scan: reads of %d bases with these seeds need more shared memory than a CTA has", max_rl);
+    return SHRIMP_E_RANGE;
+  }
   int k_max = g->seeds.n_seeds * std::max(1, max_rl);
   if (pl->hits_cap == 0) pl->hits_cap = (uint32_t)std::max<long long>(1 << 20, (long long)n_reads * 2 * 16);
   for (int attempt = 0;; attempt++) {
@@ -430,38 +452,45 @@ int chunk_scan(Chunk &C) {
     P.stats = cnt + 8;
     P.k_max = k_max;
     P.max_rl = max_rl;
-    // small-slab pass over all read strands
-    P.cap = cap;
-    int warps = SCAN_WARPS_HOST;
-    while (warps > 1 && scan_smem_bytes(cap, max_rl, warps) > 100 * 1024) warps >>= 1;
-    const size_t smem = scan_smem_bytes(cap, max_rl, warps);
-    int ctas_per_sm = (int)std::max<size_t>(1, (size_t)(220 * 1024) / std::max<size_t>(smem, 1));
-    ctas_per_sm = std::min(ctas_per_sm, 2048 / (SCAN_WARPS_HOST * 32));
-    int n_ctas = ctx->sm_count * ctas_per_sm;
-    n_ctas = std::min<long long>(n_ctas, ((long long)n_reads * 2 + warps - 1) / warps);
-    P.scratch_ints = 2 * k_max + 2 * cap;
-    SH_TRY(pl->d_scratch.ensure(std::max((size_t)n_ctas * warps * P.scratch_ints,
-                                         (size_t)ctx->sm_count * (2 * k_max + 2 * big_cap)) * 4));
-    P.scratch = pl->d_scratch.as<int32_t>();
-    SH_TRY(launch_scan(ctx, P, warps, n_ctas));
-    uint32_t h3[3];
-    SH_CUDA(cudaMemcpyAsync(h3, cnt, 12, cudaMemcpyDeviceToHost, st));
-    SH_CUDA(cudaStreamSynchronize(st));
-    if (h3[1] > 0 && !(h3[2] & 1u)) {
-      // overflow pass: one warp per CTA with the big slab
-      P.work = pl->d_overflow.as<uint32_t>();
-      P.n_work = h3[1];
-      P.overflow = nullptr;
+    uint32_t h3[3] = {0, 0, 0};
+    const int big_ctas_max = ctx->sm_count;
+    SH_TRY(pl->d_scratch.ensure((size_t)big_ctas_max * (2 * k_max + 2 * big_cap) * 4));
+    if (small_useful) {
+      // warp-per-strand pass over all read strands
+      P.cap = cap;
+      P.k_cap = k_cap;
+      P.bm_log2 = bm_log2;
+      int warps = SCAN_WARPS_HOST;
+      while (warps > 1 && scan_smem_bytes(cap, max_rl, k_cap, bm_log2, warps) > 100 * 1024) warps >>= 1;
+      const size_t smem = scan_smem_bytes(cap, max_rl, k_cap, bm_log2, warps);
+      int ctas_per_sm = (int)std::max<size_t>(1, (size_t)(220 * 1024) / std::max<size_t>(smem, 1));
+      ctas_per_sm = std::min(ctas_per_sm, 2048 / (SCAN_WARPS_HOST * 32));
+      int n_ctas = ctx->sm_count * ctas_per_sm;
+      n_ctas = std::min<long long>(n_ctas, ((long long)n_reads * 2 + warps - 1) / warps);
+      P.scratch_ints = 2 * k_max + 2 * cap;
+      SH_TRY(pl->d_scratch.ensure(std::max((size_t)n_ctas * warps * P.scratch_ints,
+                                           (size_t)big_ctas_max * (2 * k_max + 2 * big_cap)) * 4));
+      P.scratch = pl->d_scratch.as<int32_t>();
+      SH_TRY(launch_scan(ctx, P, warps, n_ctas));
+      SH_CUDA(cudaMemcpyAsync(h3, cnt, 12, cudaMemcpyDeviceToHost, st));
+      SH_CUDA(cudaStreamSynchronize(st));
+    }
+    if ((!small_useful || h3[1] > 0) && !(h3[2] & 1u)) {
+      // CTA-per-strand pass: the strands the warp kernel passed on, or every strand when the lists are long
+      P.work = small_useful ? pl->d_overflow.as<uint32_t>() : nullptr;
+      P.n_work = small_useful ? h3[1] : 2u * (uint32_t)n_reads;
       P.cap = big_cap;
+      P.k_cap = big_k_cap;
+      P.bm_log2 = big_bm_log2;
       P.scratch_ints = 2 * k_max + 2 * big_cap;
-      int ctas = std::min<int>(ctx->sm_count, (int)h3[1]);
-      SH_TRY(launch_scan(ctx, P, 1, ctas));
+      P.scratch = pl->d_scratch.as<int32_t>();
+      int ctas = (int)std::min<uint32_t>((uint32_t)big_ctas_max, P.n_work);
+      SH_TRY(launch_scan_big(ctx, P, ctas));
       SH_CUDA(cudaMemcpyAsync(h3, cnt, 12, cudaMemcpyDeviceToHost, st));
       SH_CUDA(cudaStreamSynchronize(st));
     }
     if (h3[2] & 2u) {
-      set_error("seed scan: a read strand gathered more than %d index positions; the global-memory scan path for "
-                "such reads is not implemented yet", big_cap);
+      set_error("seed scan: a read strand kept more than %d index positions after the region filter", big_cap);
       return SHRIMP_E_RANGE;
     }
     if (h3[2] & 1u) {  // hit buffer too small: grow and redo the scan

@@ -1,32 +1,34 @@
 // Seed scan: spaced-seed projection of the reads, index lookup, region filter, anchor merge and
-// candidate-window (hit) generation -- one warp per read strand, everything between the HBM index
-// and the hit list staged in shared memory.
+// candidate-window (hit) generation, everything between the HBM index and the hit list staged in shared
+// memory.
 //
 // Replaces, per read strand (gmapper/mapping.c):
 //   read_get_mapidxs_per_strand :37-70, read_get_region_counts :459-542,
 //   advance_index_in_genomemap :646-805 (unpaired branch), read_get_anchor_list_per_strand :861-1006,
 //   read_get_hit_list_per_strand :1025-1229.
 //
-// The reference marks 2 kb regions in a 4 MB table while walking every index list, then walks the
-// lists again through a k-way heap merge.  Here each list is read ONCE:
-//   1. lanes project the read's k-mers (vectorised over read positions) and fetch bucket bounds;
-//   2. the bucket lists are gathered from HBM into the warp's shared-memory slab as
-//      (position << 32 | k-mer slot) keys;
-//   3. a warp bitonic sort orders them by genome position -- the order the heap merge produces;
-//   4. "region has >= 2 hits" (RG_HAS_2) becomes a neighbour test on the sorted array: a region's
-//      catchment [r*2^11, (r+1)*2^11 + overlap) is contiguous, so another entry falls in it iff the
-//      previous or next sorted entry does;  survivors are compacted in order;
-//   5. equal positions on different read offsets would be popped in binary-heap order by the
-//      reference (SURVEY hard part 3a).  Such warps (about 0.05 % of reads) replay heap_uu
-//      (common/heap.h:43-113) exactly on the surviving entries, lane 0 only;
+// The reference marks 2 kb regions in a 4 MB table while walking every index list, then walks the lists
+// again through a k-way heap merge.  Here (one warp per read strand; one CTA for the rare strands with
+// very many index hits):
+//   1. the read is recoded to 2 bits per base in shared memory; every k-mer is projected ONCE with a few
+//      shift/mask operations per run of care positions of the seed (SeedTable::run_*), its bucket bounds are
+//      fetched and kept in shared memory with a running prefix sum of the list lengths;
+//   2. pass A streams all list entries, flattened over lanes by a search in the prefix sums so that long
+//      lists coalesce and short ones balance, and marks a hashed region bitmap pair in shared memory
+//      ("touched" / "touched twice") -- the reference's region_map (gmapper.h:284-294) without its 4 MB;
+//   3. pass B streams the same entries again (L1/L2 hits) and keeps only those whose region (or region-1
+//      within the overlap) is marked twice: a superset of the reference's survivors (hash collisions add
+//      false positives, never lose one), a few dozen entries instead of hundreds;
+//   4. the candidates are sorted by position (warp / CTA bitonic sort) -- the order the heap merge produces --
+//      and "region has >= 2 hits" (RG_HAS_2) is decided EXACTLY as a neighbour test on the sorted array: a
+//      region's catchment [r*2^11, (r+1)*2^11 + overlap) is contiguous, every witness of a true survivor is
+//      itself a candidate, so the previous/next candidate tells;
+//   5. equal positions on different read offsets would be popped in binary-heap order by the reference
+//      (SURVEY hard part 3a): such strands (about 0.05 %) replay heap_uu (common/heap.h:43-113) exactly;
 //   6. colinear collapse (:957-971) and the hit list run on the shared-memory anchors.
-// Read strands whose lists exceed the slab go to an overflow list served by a second launch with a
-// larger slab (one warp per CTA).
 #include "stages.cuh"
 
 namespace shrimp {
-
-
 
 __device__ __forceinline__ int warp_sum(int v) {
 #pragma unroll
@@ -69,32 +71,393 @@ __device__ __forceinline__ void anchor_join2(long long x0, long long y0, int l0,
 }
 
 
+
+// ---- projection and lookup helpers ----------------------------------------------------------------
+// 8 bases (4 bits each) -> 16 bits (2 bits each, low two bits of every code as KMER_TO_MAPIDX uses them)
+__device__ __forceinline__ uint32_t squeeze8(uint32_t w) {
+  w &= 0x33333333u;
+  w = (w | (w >> 2)) & 0x0f0f0f0fu;
+  w = (w | (w >> 4)) & 0x00ff00ffu;
+  w = (w | (w >> 8)) & 0x0000ffffu;
+  return w;
+}
+
+// bucket id of the k-mer of seed sn starting at base `start` of the 2-bit read r2 (padded with 2 zero words)
+__device__ __forceinline__ uint32_t mapidx_fast(const SeedTable &S, int sn, const uint32_t *r2, int start) {
+  const int o = 2 * start, w = o >> 5, sh = o & 31;
+  unsigned long long x = ((unsigned long long)r2[w + 1] << 32) | r2[w];
+  x >>= sh;
+  if (sh) x |= (unsigned long long)r2[w + 2] << (64 - sh);
+  uint32_t m = 0;
+  const int nr = S.n_runs[sn];
+  for (int q = 0; q < nr; q++) {
+    const unsigned long long part = (x >> (2 * S.run_src[sn][q])) & ((1ull << (2 * S.run_len[sn][q])) - 1ull);
+    m |= (uint32_t)(part << (2 * S.run_dst[sn][q]));
+  }
+  return m;
+}
+
+struct KmerTables {   // shared memory, per read strand
+  uint32_t *kst;      // [K] list start in pos[sn]
+  uint32_t *kpre;     // [K + 1] exclusive prefix sums of the (cut-off) list lengths
+};
+
+// entry t of the flattened lists -> (position, k-mer slot sn * max_n_kmers + i)
+__device__ __forceinline__ void flat_entry(const ScanParams &P, const KmerTables &T, int K, const int *kbase,
+                                           int max_n_kmers, uint32_t t, uint32_t &x, uint32_t &slot) {
+  int lo = 0, hi = K;  // kpre[lo] <= t < kpre[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (T.kpre[mid] <= t) lo = mid; else hi = mid;
+  }
+  int sn = 0;
+  while (sn + 1 < P.S.n_seeds && kbase[sn + 1] <= lo) sn++;
+  x = __ldg(P.I.pos[sn] + T.kst[lo] + (t - T.kpre[lo]));
+  slot = (uint32_t)(sn * max_n_kmers + (lo - kbase[sn]));
+}
+
+__device__ __forceinline__ uint32_t region_hash(uint32_t region, int bm_log2) {
+  return (region * 2654435761u) >> (32 - bm_log2);
+}
+__device__ __forceinline__ void region_mark(uint32_t *bm1, uint32_t *bm2, uint32_t region, int bm_log2) {
+  const uint32_t h = region_hash(region, bm_log2), bit = 1u << (h & 31);
+  const uint32_t old = atomicOr(&bm1[h >> 5], bit);
+  if (old & bit) atomicOr(&bm2[h >> 5], bit);
+}
+__device__ __forceinline__ bool region_twice(const uint32_t *bm2, uint32_t region, int bm_log2) {
+  const uint32_t h = region_hash(region, bm_log2);
+  return (bm2[h >> 5] >> (h & 31)) & 1u;
+}
+
+// ---- steps 4-7 on the sorted candidates ent[0, total): one warp ---------------------------------------
+__device__ void scan_tail(const ScanParams &P, uint32_t rs, int r, int rl, int max_n_kmers, int total, int gathered,
+                          unsigned long long *ent, AnchorRec *rec, int16_t *cache, uint32_t *keep, int32_t *scr,
+                          int cap, int lane) {
+  const SeedTable &S = P.S;
+  const MapParamsDev &M = P.M;
+  const int mkp = M.colour_space ? 1 : 0;
+  const uint32_t rmask = (1u << M.region_bits) - 1u;
+  // ---- 4. region filter (RG_HAS_2 as a neighbour test) + ordered compaction -----------------
+  int m_surv = total;
+  if (M.use_region_counts) {
+    for (int t0 = 0; t0 < total; t0 += 32) {
+      const int t = t0 + lane;
+      bool kp = false;
+      if (t < total) {
+        const unsigned long long x = ent[t] >> 32;
+        const unsigned long long xl = t > 0 ? (ent[t - 1] >> 32) : 0ull;
+        const unsigned long long xr = t + 1 < total ? (ent[t + 1] >> 32) : ~0ull;
+        const unsigned long long region = x >> M.region_bits;
+        const unsigned long long lo = region << M.region_bits;
+        const unsigned long long hi = ((region + 1) << M.region_bits) + (unsigned long long)M.region_overlap;
+        kp = (t > 0 && xl >= lo) || (t + 1 < total && xr < hi);
+        if (!kp && region > 0 && ((uint32_t)x & rmask) < (uint32_t)M.region_overlap) {
+          const unsigned long long lo2 = (region - 1) << M.region_bits;
+          const unsigned long long hi2 = lo + (unsigned long long)M.region_overlap;
+          kp = (t > 0 && xl >= lo2) || (t + 1 < total && xr < hi2);
+        }
+      }
+      const uint32_t b = __ballot_sync(0xffffffffu, kp);
+      if (lane == 0) keep[t0 >> 5] = b;
+    }
+    __syncwarp();
+    int outn = 0;
+    for (int t0 = 0; t0 < total; t0 += 32) {
+      const uint32_t b = keep[t0 >> 5];
+      const int t = t0 + lane;
+      const unsigned long long v = t < total ? ent[t] : 0ull;
+      __syncwarp();
+      if ((b >> lane) & 1u) ent[outn + __popc(b & ((1u << lane) - 1u))] = v;
+      outn += __popc(b);
+      __syncwarp();
+    }
+    m_surv = outn;
+  }
+  if (lane == 0) {
+    atomicAdd(&P.stats[1], (uint32_t)gathered);
+    atomicAdd(&P.stats[2], (uint32_t)m_surv);
+  }
+  if (m_surv == 0) return;
+
+  // ---- 5. equal position on different read offsets -> replay the reference's heap -----------
+  bool tie = false;
+  for (int t = lane; t + 1 < m_surv; t += 32) {
+    const unsigned long long a = ent[t], b = ent[t + 1];
+    if ((a >> 32) == (b >> 32) && ((uint32_t)a % (uint32_t)max_n_kmers) != ((uint32_t)b % (uint32_t)max_n_kmers))
+      tie = true;
+  }
+  tie = __any_sync(0xffffffffu, tie);
+  int32_t *order = nullptr;
+  if (tie) {
+    const int K = S.n_seeds * max_n_kmers;
+    int32_t *first_of = scr;               // [k_max]
+    int32_t *heap = scr + P.k_max;         // [k_max]
+    int32_t *next_same = heap + P.k_max;   // [cap]
+    order = next_same + cap;               // [cap]
+    for (int k = lane; k < K; k += 32) first_of[k] = -1;
+    __syncwarp();
+    if (lane == 0) {
+      atomicAdd(&P.stats[0], 1u);
+      for (int t = m_surv - 1; t >= 0; t--) {
+        const int off = (int)(uint32_t)ent[t];
+        next_same[t] = first_of[off];
+        first_of[off] = t;
+      }
+      // heap_uu on key = position; elements are survivor indices.  Load order: sn-major, i.e.
+      // ascending slot (mapping.c:913-935).
+      int load = 0;
+      for (int off = 0; off < K; off++) {
+        const int t = first_of[off];
+        if (t < 0) continue;
+        heap[load++] = t;
+        int node = load, parent = node / 2;  // percolate_up, heap.h:43-60
+        while (node > 1 && (ent[heap[node - 1]] >> 32) < (ent[heap[parent - 1]] >> 32)) {
+          int tmp = heap[parent - 1];
+          heap[parent - 1] = heap[node - 1];
+          heap[node - 1] = tmp;
+          node = parent;
+          parent = node / 2;
+        }
+      }
+      int outn = 0;
+      while (load > 0) {
+        const int t = heap[0];
+        order[outn++] = t;
+        const int nx = next_same[t];
+        if (nx >= 0) {
+          heap[0] = nx;  // heap_uu_replace_min
+        } else {
+          load--;  // heap_uu_extract_min
+          if (load > 0) heap[0] = heap[load];
+        }
+        if (load > 0) {  // percolate_down, heap.h:62-89
+          int node = 1;
+          for (;;) {
+            int left = node * 2, right = left + 1, mn = node;
+            if (left <= load && (ent[heap[left - 1]] >> 32) < (ent[heap[node - 1]] >> 32)) mn = left;
+            if (right <= load && (ent[heap[right - 1]] >> 32) < (ent[heap[mn - 1]] >> 32)) mn = right;
+            if (mn == node) break;
+            int tmp = heap[mn - 1];
+            heap[mn - 1] = heap[node - 1];
+            heap[node - 1] = tmp;
+            node = mn;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+
+  // ---- 6. anchors: contig lookup in parallel, colinear collapse in pop order ----------------
+  for (int t = lane; t < m_surv; t += 32) {
+    const unsigned long long e = ent[order ? order[t] : t];
+    const uint32_t slot = (uint32_t)e;
+    const int sn = (int)(slot / (uint32_t)max_n_kmers), i = (int)(slot % (uint32_t)max_n_kmers);
+    AnchorRec a;
+    a.x = (uint32_t)(e >> 32);
+    a.y = (int16_t)(mkp + i);
+    a.len = (int16_t)S.span[sn];
+    a.weight = 1;
+    a.cn = contig_of_dev(P.G.contig_off, P.G.num_contigs, a.x);
+    rec[t] = a;
+  }
+  for (int t = lane; t < rl; t += 32) cache[t] = -1;
+  __syncwarp();
+  int n_anch = 0;
+  if (lane == 0) {
+    // read_get_anchor_list_per_strand :941-971 with anchor_uw_join (anchors.c:98-119); entries
+    // arrive in ascending x, so only the "extend to the right" branch of the join can fire.
+    for (int t = 0; t < m_surv; t++) {
+      const AnchorRec a = rec[t];
+      const int slot = (int)(((unsigned long long)a.x + (unsigned long long)rl - (unsigned long long)a.y) %
+                             (unsigned long long)rl);
+      const int j = cache[slot];
+      if (j >= 0 && rec[j].cn == a.cn &&
+          (long long)rec[j].x - rec[j].y == (long long)a.x - a.y) {
+        AnchorRec d = rec[j];
+        if ((long long)a.x + a.len > (long long)d.x + d.len) d.len = (int16_t)((long long)a.x - d.x + a.len);
+        d.weight += 1;
+        rec[j] = d;
+      } else {
+        rec[n_anch] = a;
+        cache[slot] = (int16_t)n_anch;
+        n_anch++;
+      }
+    }
+  }
+  n_anch = __shfl_sync(0xffffffffu, n_anch, 0);
+  __syncwarp();
+
+  // ---- 7. hit list (read_get_hit_list_per_strand) ---------------------------------------------
+  uint32_t out0 = 0;
+  if (lane == 0) {
+    out0 = atomicAdd(P.hits_used, (uint32_t)n_anch);
+    atomicAdd(&P.stats[3], (uint32_t)n_anch);
+  }
+  out0 = __shfl_sync(0xffffffffu, out0, 0);
+  if ((unsigned long long)out0 + (unsigned long long)n_anch > (unsigned long long)P.hits_cap) {
+    if (lane == 0) atomicOr(P.status, 1u);
+    return;
+  }
+  const int window_len = (int)(unsigned short)abs_or_pct_d(M.window_len, M.window_len_frac, (double)rl);
+  int nh = 0;
+  for (int i0 = 0; i0 < n_anch; i0 += 32) {
+    const int i = i0 + lane;
+    bool emit = false;
+    DevHit h;
+    if (i < n_anch) {
+      const AnchorRec ai = rec[i];
+      const int cn = ai.cn;
+      const long long coff = (long long)P.G.contig_off[cn];
+      const long long glen = (long long)P.G.contig_len[cn];
+      int w_len = window_len;
+      if ((long long)w_len > glen) w_len = (int)glen;
+      long long gend = ((long long)ai.x - coff) + rl - 1 - ai.y, gstart;
+      if (gend > glen - 1) gend = glen - 1;
+      gstart = gend >= window_len ? gend - window_len : 0;
+      int max_idx = i;
+      int max_score = ai.len * M.match;
+      if (!M.gapless) {
+        if (M.match_mode == 2 && ai.weight == 1) max_score = -1;
+        for (int j = i - 1; j >= 0; j--) {
+          const AnchorRec aj = rec[j];
+          if ((long long)aj.x < coff + gstart) break;
+          if (aj.y >= ai.y) continue;
+          int short_len, long_len;
+          if ((long long)ai.x - coff - ai.y > (long long)aj.x - coff - aj.y) {
+            short_len = (int)(ai.y - aj.y) + ai.len;
+            long_len = (int)((long long)ai.x - (long long)aj.x) + ai.len;
+          } else {
+            short_len = (int)((long long)ai.x - (long long)aj.x) + ai.len;
+            long_len = (int)(ai.y - aj.y) + ai.len;
+          }
+          int tmp_score = short_len * M.match;
+          if (long_len > short_len) tmp_score += M.b_gap_open + (long_len - short_len) * M.b_gap_ext;  // :1134
+          if (tmp_score > max_score) {
+            max_idx = j;
+            max_score = tmp_score;
+          }
+        }
+      }
+      const int base_len = rl < w_len ? rl : w_len;
+      const int score_max = base_len * M.match;
+      if (M.gapless || M.match_mode == 1 ||
+          max_score >= (int)abs_or_pct_d(M.wgen_thr, M.wgen_frac, (double)score_max)) {
+        const AnchorRec am = rec[max_idx];
+        const int x_len = (int)((long long)ai.x - (long long)am.x) + ai.len;
+        long long goff;
+        if ((long long)((window_len - x_len) / 2) < (long long)am.x - coff)
+          goff = ((long long)am.x - coff) - (window_len - x_len) / 2;
+        else
+          goff = 0;
+        if (goff + w_len > glen) goff = glen - w_len;
+        const long long rel = coff + goff;
+        if (max_idx < i) {
+          anchor_join2((long long)ai.x - rel, ai.y, ai.len, 1, (long long)am.x - rel, am.y, am.len, 1, h.ax, h.ay,
+                       h.alen, h.awidth);
+        } else {
+          h.ax = (int)((long long)ai.x - rel);
+          h.ay = ai.y;
+          h.alen = ai.len;
+          h.awidth = 1;
+        }
+        h.g_off = (uint32_t)goff;
+        h.cn = cn;
+        h.w_len = w_len;
+        h.wg = max_score;
+        h.matches = (M.gapless || max_idx == i) ? ai.weight : ai.weight + am.weight;
+        h.score_max = score_max;
+        h.score_vector = -1;
+        h.pct_vector = 0;
+        emit = true;
+      }
+    }
+    const uint32_t b = __ballot_sync(0xffffffffu, emit);
+    if (emit) P.hits[out0 + nh + __popc(b & ((1u << lane) - 1u))] = h;
+    nh += __popc(b);
+  }
+  __syncwarp();
+  // stable insertion sort by g_off inside a contig (:1210-1223); the list is almost sorted
+  if (lane == 0) {
+    DevHit *H = P.hits + out0;
+    for (int i = 1; i < nh; i++) {
+      const DevHit cur = H[i];
+      int j = i;
+      while (j >= 1 && H[j - 1].cn == cur.cn && H[j - 1].g_off > cur.g_off) j--;
+      if (j < i) {
+        for (int k = i - 1; k >= j; k--) H[k + 1] = H[k];
+        H[j] = cur;
+      }
+    }
+    P.rs_range[rs] = make_uint2(out0, (uint32_t)nh);
+  }
+  __syncwarp();
+}
+
+// shared memory of one warp of the small kernel / of the CTA of the big kernel
+struct ScanSmem {
+  size_t r2, kst, kpre, bm1, bm2, ent, rec, cache, keep, total;
+};
+__host__ __device__ inline ScanSmem scan_layout(int cap, int max_rl, int k_cap, int bm_log2, bool alias_rec) {
+  ScanSmem L;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t at = o; o += (bytes + 15) & ~(size_t)15; return at; };
+  L.r2 = take(((size_t)max_rl / 16 + 4) * 4);
+  L.kst = take((size_t)k_cap * 4);
+  L.kpre = take(((size_t)k_cap + 1) * 4);
+  L.cache = take((size_t)max_rl * 2);
+  L.keep = take(((size_t)cap / 32 + 1) * 4);
+  L.ent = take((size_t)cap * 8);
+  L.bm1 = take(((size_t)1 << bm_log2) / 8);
+  L.bm2 = take(((size_t)1 << bm_log2) / 8);
+  if (alias_rec) {  // big kernel: the anchors reuse the bitmaps, which are dead after pass B
+    L.rec = L.bm1;
+    if (o - L.bm1 < (size_t)cap * 16) o = L.bm1 + (size_t)cap * 16;
+  } else {
+    L.rec = take((size_t)cap * 16);
+  }
+  L.total = (o + 15) & ~(size_t)15;
+  return L;
+}
+
+// number of k-mers of seed sn on a read strand (gmapper.c:473-480, mapping.c:47-66)
+__device__ __forceinline__ int n_kmers_of(const SeedTable &S, int sn, int rl, int mkp) {
+  const int nk = rl - S.span[sn] + 1 - mkp;
+  return nk > 0 ? nk : 0;
+}
+
+// Steps 1-4 for one warp; returns the number of candidates in ent (sorted), or -1 when the strand needs more
+// than `cap` candidate slots / k_cap k-mers (-> overflow list).
 __global__ void __launch_bounds__(SCAN_WARPS * 32) scan_kernel(const ScanParams P, int warps_per_cta) {
   extern __shared__ unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   if (wib >= warps_per_cta) return;
   const int cap = P.cap;
-  // per-warp slab: ent[cap] u64 | rec[cap] AnchorRec (16 B) | cache[max_rl] i16 | keep[cap/32] u32
-  const size_t per_warp = (size_t)cap * 8 + (size_t)cap * 16 + (((size_t)P.max_rl * 2 + 15) & ~(size_t)15) +
-                          (size_t)(cap / 32 + 1) * 4;
-  unsigned char *base = smem_raw + (((per_warp + 15) & ~(size_t)15)) * wib;
-  unsigned long long *ent = (unsigned long long *)base;
-  AnchorRec *rec = (AnchorRec *)(base + (size_t)cap * 8);
-  int16_t *cache = (int16_t *)(base + (size_t)cap * 24);
-  uint32_t *keep = (uint32_t *)(base + (size_t)cap * 24 + (((size_t)P.max_rl * 2 + 15) & ~(size_t)15));
+  const ScanSmem L = scan_layout(cap, P.max_rl, P.k_cap, P.bm_log2, false);
+  unsigned char *base = smem_raw + L.total * wib;
+  uint32_t *r2 = (uint32_t *)(base + L.r2);
+  KmerTables T;
+  T.kst = (uint32_t *)(base + L.kst);
+  T.kpre = (uint32_t *)(base + L.kpre);
+  uint32_t *bm1 = (uint32_t *)(base + L.bm1), *bm2 = (uint32_t *)(base + L.bm2);
+  unsigned long long *ent = (unsigned long long *)(base + L.ent);
+  AnchorRec *rec = (AnchorRec *)(base + L.rec);
+  int16_t *cache = (int16_t *)(base + L.cache);
+  uint32_t *keep = (uint32_t *)(base + L.keep);
+  const int bm_words = 1 << (P.bm_log2 - 5);
 
   const uint32_t gwarp = blockIdx.x * warps_per_cta + wib;
   const uint32_t n_warps = gridDim.x * warps_per_cta;
   int32_t *scr = P.scratch + (size_t)gwarp * P.scratch_ints;
-  const uint32_t n_items = P.work ? P.n_work : 2u * (uint32_t)P.n_reads;
+  const uint32_t n_items = 2u * (uint32_t)P.n_reads;
   const SeedTable &S = P.S;
   const MapParamsDev &M = P.M;
   const int mkp = M.colour_space ? 1 : 0;  // min_kmer_pos (gmapper.c:478-480)
   const uint32_t rmask = (1u << M.region_bits) - 1u;
 
   for (uint32_t item = gwarp; item < n_items; item += n_warps) {
-    const uint32_t rs = P.work ? P.work[item] : item;
+    const uint32_t rs = item;
     const int r = (int)(rs >> 1);
     const int rl = P.read_len[r];
     const uint32_t *seq = P.reads + (size_t)rs * P.stride;
@@ -102,59 +465,111 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) scan_kernel(const ScanParams 
     if (max_n_kmers < 0) max_n_kmers = 0;
     if (lane == 0) P.rs_range[rs] = make_uint2(0u, 0u);
     if (rl <= 0 || max_n_kmers == 0) continue;
+    __syncwarp();
 
-    // ---- 1. count list entries -------------------------------------------------------------
-    int total = 0;
-    for (int sn = 0; sn < S.n_seeds; sn++) {
-      const int nk = rl - S.span[sn] + 1 - mkp;
-      for (int i = lane; i < nk; i += 32) {
-        uint32_t m = kmer_to_mapidx(S, sn, seq, (uint64_t)(mkp + i));
-        uint32_t len = P.I.offs[sn][m + 1] - P.I.offs[sn][m];
-        if (len > M.list_cutoff) len = 0;  // mapping.c:497,:889
-        total += (int)len;
+    // ---- 1. recode the read, project every k-mer once, fetch bucket bounds --------------------------
+    const int nw2 = (rl + 15) / 16;
+    for (int w = lane; w < nw2 + 3; w += 32) {
+      uint32_t v = 0;
+      if (w < nw2) {
+        v = squeeze8(seq[2 * w]);
+        if (2 * w + 1 < P.stride) v |= squeeze8(seq[2 * w + 1]) << 16;
       }
+      r2[w] = v;
     }
-    total = warp_sum(total);
-    if (total == 0) continue;
-    if (total > cap) {
-      if (lane == 0) {
-        if (P.overflow) {
-          uint32_t o = atomicAdd(P.n_overflow, 1u);
-          P.overflow[o] = rs;
-        } else {
-          atomicOr(P.status, 2u);
-        }
-      }
+    for (int w = lane; w < bm_words; w += 32) {
+      bm1[w] = 0u;
+      bm2[w] = 0u;
+    }
+    __syncwarp();
+    int kbase[SHRIMP_MAX_SEEDS + 1];
+    int K = 0;
+    for (int sn = 0; sn < S.n_seeds; sn++) {
+      kbase[sn] = K;
+      K += n_kmers_of(S, sn, rl, mkp);
+    }
+    kbase[S.n_seeds] = K;
+    if (K > P.k_cap) {  // longer than the shared-memory tables of this launch: CTA kernel
+      if (lane == 0) P.overflow[atomicAdd(P.n_overflow, 1u)] = rs;
       continue;
     }
-
-    // ---- 2. gather (position << 32 | k-mer slot) ---------------------------------------------
-    int basepos = 0;
+    uint32_t total = 0;
     for (int sn = 0; sn < S.n_seeds; sn++) {
-      const int nk = rl - S.span[sn] + 1 - mkp;
+      const int nk = kbase[sn + 1] - kbase[sn];
       for (int i0 = 0; i0 < nk; i0 += 32) {
         const int i = i0 + lane;
         uint32_t start = 0, len = 0;
         if (i < nk) {
-          uint32_t m = kmer_to_mapidx(S, sn, seq, (uint64_t)(mkp + i));
-          start = P.I.offs[sn][m];
-          len = P.I.offs[sn][m + 1] - start;
-          if (len > M.list_cutoff) len = 0;
+          const uint32_t m = S.n_runs[sn] ? mapidx_fast(S, sn, r2, mkp + i) : kmer_to_mapidx(S, sn, seq, (uint64_t)(mkp + i));
+          const uint2 be = make_uint2(__ldg(P.I.offs[sn] + m), __ldg(P.I.offs[sn] + m + 1));
+          start = be.x;
+          len = be.y - be.x;
+          if (len > M.list_cutoff) len = 0;  // mapping.c:497,:889
         }
-        const int incl = warp_incl_scan((int)len, lane);
-        const int excl = incl - (int)len;
-        const unsigned long long slot = (unsigned long long)(sn * max_n_kmers + i);
-        const uint32_t *list = P.I.pos[sn] + start;
-        for (uint32_t j = 0; j < len; j++) ent[basepos + excl + (int)j] = ((unsigned long long)__ldg(list + j) << 32) | slot;
-        basepos += __shfl_sync(0xffffffffu, incl, 31);
+        const uint32_t incl = (uint32_t)warp_incl_scan((int)len, lane);
+        if (i < nk) {
+          T.kst[kbase[sn] + i] = start;
+          T.kpre[kbase[sn] + i] = total + incl - len;
+        }
+        total += __shfl_sync(0xffffffffu, incl, 31);
       }
     }
-    int Pn = 32;
-    while (Pn < total) Pn <<= 1;
-    for (int t = total + lane; t < Pn; t += 32) ent[t] = ~0ull;
+    if (lane == 0) T.kpre[K] = total;
     __syncwarp();
+    if (total == 0) continue;
 
-    // ---- 3. bitonic sort by position -----------------------------------------------------------
+    int ns = (int)total;
+    if (M.use_region_counts) {
+      // ---- 2. pass A: mark regions ------------------------------------------------------------------
+      for (uint32_t t = lane; t < total; t += 32) {
+        uint32_t x, slot;
+        flat_entry(P, T, K, kbase, max_n_kmers, t, x, slot);
+        const uint32_t region = x >> M.region_bits;
+        region_mark(bm1, bm2, region, P.bm_log2);
+        if ((x & rmask) < (uint32_t)M.region_overlap && region > 0) region_mark(bm1, bm2, region - 1, P.bm_log2);
+      }
+      __syncwarp();
+      // ---- 3. pass B: keep the entries of regions marked twice ----------------------------------------
+      ns = 0;
+      for (uint32_t t0 = 0; t0 < total; t0 += 32) {
+        const uint32_t t = t0 + lane;
+        bool kp = false;
+        uint32_t x = 0, slot = 0;
+        if (t < total) {
+          flat_entry(P, T, K, kbase, max_n_kmers, t, x, slot);
+          const uint32_t region = x >> M.region_bits;
+          kp = region_twice(bm2, region, P.bm_log2) ||
+               ((x & rmask) < (uint32_t)M.region_overlap && region > 0 && region_twice(bm2, region - 1, P.bm_log2));
+        }
+        const uint32_t b = __ballot_sync(0xffffffffu, kp);
+        if (kp) {
+          const int at = ns + __popc(b & ((1u << lane) - 1u));
+          if (at < cap) ent[at] = ((unsigned long long)x << 32) | slot;
+        }
+        ns += __popc(b);
+      }
+    } else {
+      if (ns <= cap) {
+        for (uint32_t t = lane; t < total; t += 32) {
+          uint32_t x, slot;
+          flat_entry(P, T, K, kbase, max_n_kmers, t, x, slot);
+          ent[t] = ((unsigned long long)x << 32) | slot;
+        }
+      }
+    }
+    if (ns > cap) {
+      if (lane == 0) P.overflow[atomicAdd(P.n_overflow, 1u)] = rs;
+      continue;
+    }
+    if (ns == 0) {
+      if (lane == 0) atomicAdd(&P.stats[1], total);
+      continue;
+    }
+    int Pn = 32;
+    while (Pn < ns) Pn <<= 1;
+    for (int t = ns + lane; t < Pn; t += 32) ent[t] = ~0ull;
+    __syncwarp();
+    // ---- 4a. bitonic sort by position ---------------------------------------------------------------
     for (int k = 2; k <= Pn; k <<= 1) {
       for (int j = k >> 1; j > 0; j >>= 1) {
         for (int t = lane; t < (Pn >> 1); t += 32) {
@@ -170,280 +585,190 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) scan_kernel(const ScanParams 
         __syncwarp();
       }
     }
-
-    // ---- 4. region filter (RG_HAS_2 as a neighbour test) + ordered compaction -----------------
-    int m_surv = total;
-    if (M.use_region_counts) {
-      for (int t0 = 0; t0 < total; t0 += 32) {
-        const int t = t0 + lane;
-        bool kp = false;
-        if (t < total) {
-          const unsigned long long x = ent[t] >> 32;
-          const unsigned long long xl = t > 0 ? (ent[t - 1] >> 32) : 0ull;
-          const unsigned long long xr = t + 1 < total ? (ent[t + 1] >> 32) : ~0ull;
-          const unsigned long long region = x >> M.region_bits;
-          const unsigned long long lo = region << M.region_bits;
-          const unsigned long long hi = ((region + 1) << M.region_bits) + (unsigned long long)M.region_overlap;
-          kp = (t > 0 && xl >= lo) || (t + 1 < total && xr < hi);
-          if (!kp && region > 0 && ((uint32_t)x & rmask) < (uint32_t)M.region_overlap) {
-            const unsigned long long lo2 = (region - 1) << M.region_bits;
-            const unsigned long long hi2 = lo + (unsigned long long)M.region_overlap;
-            kp = (t > 0 && xl >= lo2) || (t + 1 < total && xr < hi2);
-          }
-        }
-        const uint32_t b = __ballot_sync(0xffffffffu, kp);
-        if (lane == 0) keep[t0 >> 5] = b;
-      }
-      __syncwarp();
-      int outn = 0;
-      for (int t0 = 0; t0 < total; t0 += 32) {
-        const uint32_t b = keep[t0 >> 5];
-        const int t = t0 + lane;
-        const unsigned long long v = t < total ? ent[t] : 0ull;
-        __syncwarp();
-        if ((b >> lane) & 1u) ent[outn + __popc(b & ((1u << lane) - 1u))] = v;
-        outn += __popc(b);
-        __syncwarp();
-      }
-      m_surv = outn;
-    }
-    if (lane == 0) {
-      atomicAdd(&P.stats[1], (uint32_t)total);
-      atomicAdd(&P.stats[2], (uint32_t)m_surv);
-    }
-    if (m_surv == 0) continue;
-
-    // ---- 5. equal position on different read offsets -> replay the reference's heap -----------
-    bool tie = false;
-    for (int t = lane; t + 1 < m_surv; t += 32) {
-      const unsigned long long a = ent[t], b = ent[t + 1];
-      if ((a >> 32) == (b >> 32) && ((uint32_t)a % (uint32_t)max_n_kmers) != ((uint32_t)b % (uint32_t)max_n_kmers))
-        tie = true;
-    }
-    tie = __any_sync(0xffffffffu, tie);
-    int32_t *order = nullptr;
-    if (tie) {
-      const int K = S.n_seeds * max_n_kmers;
-      int32_t *first_of = scr;               // [k_max]
-      int32_t *heap = scr + P.k_max;         // [k_max]
-      int32_t *next_same = heap + P.k_max;   // [cap]
-      order = next_same + cap;               // [cap]
-      for (int k = lane; k < K; k += 32) first_of[k] = -1;
-      __syncwarp();
-      if (lane == 0) {
-        atomicAdd(&P.stats[0], 1u);
-        for (int t = m_surv - 1; t >= 0; t--) {
-          const int off = (int)(uint32_t)ent[t];
-          next_same[t] = first_of[off];
-          first_of[off] = t;
-        }
-        // heap_uu on key = position; elements are survivor indices.  Load order: sn-major, i.e.
-        // ascending slot (mapping.c:913-935).
-        int load = 0;
-        for (int off = 0; off < K; off++) {
-          const int t = first_of[off];
-          if (t < 0) continue;
-          heap[load++] = t;
-          int node = load, parent = node / 2;  // percolate_up, heap.h:43-60
-          while (node > 1 && (ent[heap[node - 1]] >> 32) < (ent[heap[parent - 1]] >> 32)) {
-            int tmp = heap[parent - 1];
-            heap[parent - 1] = heap[node - 1];
-            heap[node - 1] = tmp;
-            node = parent;
-            parent = node / 2;
-          }
-        }
-        int outn = 0;
-        while (load > 0) {
-          const int t = heap[0];
-          order[outn++] = t;
-          const int nx = next_same[t];
-          if (nx >= 0) {
-            heap[0] = nx;  // heap_uu_replace_min
-          } else {
-            load--;  // heap_uu_extract_min
-            if (load > 0) heap[0] = heap[load];
-          }
-          if (load > 0) {  // percolate_down, heap.h:62-89
-            int node = 1;
-            for (;;) {
-              int left = node * 2, right = left + 1, mn = node;
-              if (left <= load && (ent[heap[left - 1]] >> 32) < (ent[heap[node - 1]] >> 32)) mn = left;
-              if (right <= load && (ent[heap[right - 1]] >> 32) < (ent[heap[mn - 1]] >> 32)) mn = right;
-              if (mn == node) break;
-              int tmp = heap[mn - 1];
-              heap[mn - 1] = heap[node - 1];
-              heap[node - 1] = tmp;
-              node = mn;
-            }
-          }
-        }
-      }
-      __syncwarp();
-    }
-
-    // ---- 6. anchors: contig lookup in parallel, colinear collapse in pop order ----------------
-    for (int t = lane; t < m_surv; t += 32) {
-      const unsigned long long e = ent[order ? order[t] : t];
-      const uint32_t slot = (uint32_t)e;
-      const int sn = (int)(slot / (uint32_t)max_n_kmers), i = (int)(slot % (uint32_t)max_n_kmers);
-      AnchorRec a;
-      a.x = (uint32_t)(e >> 32);
-      a.y = (int16_t)(mkp + i);
-      a.len = (int16_t)S.span[sn];
-      a.weight = 1;
-      a.cn = contig_of_dev(P.G.contig_off, P.G.num_contigs, a.x);
-      rec[t] = a;
-    }
-    for (int t = lane; t < rl; t += 32) cache[t] = -1;
-    __syncwarp();
-    int n_anch = 0;
-    if (lane == 0) {
-      // read_get_anchor_list_per_strand :941-971 with anchor_uw_join (anchors.c:98-119); entries
-      // arrive in ascending x, so only the "extend to the right" branch of the join can fire.
-      for (int t = 0; t < m_surv; t++) {
-        const AnchorRec a = rec[t];
-        const int slot = (int)(((unsigned long long)a.x + (unsigned long long)rl - (unsigned long long)a.y) %
-                               (unsigned long long)rl);
-        const int j = cache[slot];
-        if (j >= 0 && rec[j].cn == a.cn &&
-            (long long)rec[j].x - rec[j].y == (long long)a.x - a.y) {
-          AnchorRec d = rec[j];
-          if ((long long)a.x + a.len > (long long)d.x + d.len) d.len = (int16_t)((long long)a.x - d.x + a.len);
-          d.weight += 1;
-          rec[j] = d;
-        } else {
-          rec[n_anch] = a;
-          cache[slot] = (int16_t)n_anch;
-          n_anch++;
-        }
-      }
-    }
-    n_anch = __shfl_sync(0xffffffffu, n_anch, 0);
-    __syncwarp();
-
-    // ---- 7. hit list (read_get_hit_list_per_strand) ---------------------------------------------
-    uint32_t out0 = 0;
-    if (lane == 0) {
-      out0 = atomicAdd(P.hits_used, (uint32_t)n_anch);
-      atomicAdd(&P.stats[3], (uint32_t)n_anch);
-    }
-    out0 = __shfl_sync(0xffffffffu, out0, 0);
-    if ((unsigned long long)out0 + (unsigned long long)n_anch > (unsigned long long)P.hits_cap) {
-      if (lane == 0) atomicOr(P.status, 1u);
-      continue;
-    }
-    const int window_len = (int)(unsigned short)abs_or_pct_d(M.window_len, M.window_len_frac, (double)rl);
-    int nh = 0;
-    for (int i0 = 0; i0 < n_anch; i0 += 32) {
-      const int i = i0 + lane;
-      bool emit = false;
-      DevHit h;
-      if (i < n_anch) {
-        const AnchorRec ai = rec[i];
-        const int cn = ai.cn;
-        const long long coff = (long long)P.G.contig_off[cn];
-        const long long glen = (long long)P.G.contig_len[cn];
-        int w_len = window_len;
-        if ((long long)w_len > glen) w_len = (int)glen;
-        long long gend = ((long long)ai.x - coff) + rl - 1 - ai.y, gstart;
-        if (gend > glen - 1) gend = glen - 1;
-        gstart = gend >= window_len ? gend - window_len : 0;
-        int max_idx = i;
-        int max_score = ai.len * M.match;
-        if (!M.gapless) {
-          if (M.match_mode == 2 && ai.weight == 1) max_score = -1;
-          for (int j = i - 1; j >= 0; j--) {
-            const AnchorRec aj = rec[j];
-            if ((long long)aj.x < coff + gstart) break;
-            if (aj.y >= ai.y) continue;
-            int short_len, long_len;
-            if ((long long)ai.x - coff - ai.y > (long long)aj.x - coff - aj.y) {
-              short_len = (int)(ai.y - aj.y) + ai.len;
-              long_len = (int)((long long)ai.x - (long long)aj.x) + ai.len;
-            } else {
-              short_len = (int)((long long)ai.x - (long long)aj.x) + ai.len;
-              long_len = (int)(ai.y - aj.y) + ai.len;
-            }
-            int tmp_score = short_len * M.match;
-            if (long_len > short_len) tmp_score += M.b_gap_open + (long_len - short_len) * M.b_gap_ext;  // :1134
-            if (tmp_score > max_score) {
-              max_idx = j;
-              max_score = tmp_score;
-            }
-          }
-        }
-        const int base_len = rl < w_len ? rl : w_len;
-        const int score_max = base_len * M.match;
-        if (M.gapless || M.match_mode == 1 ||
-            max_score >= (int)abs_or_pct_d(M.wgen_thr, M.wgen_frac, (double)score_max)) {
-          const AnchorRec am = rec[max_idx];
-          const int x_len = (int)((long long)ai.x - (long long)am.x) + ai.len;
-          long long goff;
-          if ((long long)((window_len - x_len) / 2) < (long long)am.x - coff)
-            goff = ((long long)am.x - coff) - (window_len - x_len) / 2;
-          else
-            goff = 0;
-          if (goff + w_len > glen) goff = glen - w_len;
-          const long long rel = coff + goff;
-          if (max_idx < i) {
-            anchor_join2((long long)ai.x - rel, ai.y, ai.len, 1, (long long)am.x - rel, am.y, am.len, 1, h.ax, h.ay,
-                         h.alen, h.awidth);
-          } else {
-            h.ax = (int)((long long)ai.x - rel);
-            h.ay = ai.y;
-            h.alen = ai.len;
-            h.awidth = 1;
-          }
-          h.g_off = (uint32_t)goff;
-          h.cn = cn;
-          h.w_len = w_len;
-          h.wg = max_score;
-          h.matches = (M.gapless || max_idx == i) ? ai.weight : ai.weight + am.weight;
-          h.score_max = score_max;
-          h.score_vector = -1;
-          h.pct_vector = 0;
-          emit = true;
-        }
-      }
-      const uint32_t b = __ballot_sync(0xffffffffu, emit);
-      if (emit) P.hits[out0 + nh + __popc(b & ((1u << lane) - 1u))] = h;
-      nh += __popc(b);
-    }
-    __syncwarp();
-    // stable insertion sort by g_off inside a contig (:1210-1223); the list is almost sorted
-    if (lane == 0) {
-      DevHit *H = P.hits + out0;
-      for (int i = 1; i < nh; i++) {
-        const DevHit cur = H[i];
-        int j = i;
-        while (j >= 1 && H[j - 1].cn == cur.cn && H[j - 1].g_off > cur.g_off) j--;
-        if (j < i) {
-          for (int k = i - 1; k >= j; k--) H[k + 1] = H[k];
-          H[j] = cur;
-        }
-      }
-      P.rs_range[rs] = make_uint2(out0, (uint32_t)nh);
-    }
+    scan_tail(P, rs, r, rl, max_n_kmers, ns, (int)total, ent, rec, cache, keep, scr, cap, lane);
     __syncwarp();
   }
 }
 
-size_t scan_smem_bytes(int cap, int max_rl, int warps) {
-  size_t per_warp = (size_t)cap * 8 + (size_t)cap * 16 + (((size_t)max_rl * 2 + 15) & ~(size_t)15) +
-                    (size_t)(cap / 32 + 1) * 4;
-  per_warp = (per_warp + 15) & ~(size_t)15;
-  return per_warp * warps;
+// CTA per read strand for the strands the warp kernel passed on (P.work): same steps with the lists streamed
+// by all threads, a CTA-wide sort, and warp 0 finishing steps 4b-7.
+#define SCAN_BIG_THREADS 256
+__global__ void __launch_bounds__(SCAN_BIG_THREADS) scan_big_kernel(const ScanParams P) {
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ uint32_t s_total, s_ns;
+  const int tid = threadIdx.x, lane = tid & 31, nthr = SCAN_BIG_THREADS;
+  const int cap = P.cap;
+  const ScanSmem L = scan_layout(cap, P.max_rl, P.k_cap, P.bm_log2, true);
+  uint32_t *r2 = (uint32_t *)(smem_raw + L.r2);
+  KmerTables T;
+  T.kst = (uint32_t *)(smem_raw + L.kst);
+  T.kpre = (uint32_t *)(smem_raw + L.kpre);
+  uint32_t *bm1 = (uint32_t *)(smem_raw + L.bm1), *bm2 = (uint32_t *)(smem_raw + L.bm2);
+  unsigned long long *ent = (unsigned long long *)(smem_raw + L.ent);
+  AnchorRec *rec = (AnchorRec *)(smem_raw + L.rec);
+  int16_t *cache = (int16_t *)(smem_raw + L.cache);
+  uint32_t *keep = (uint32_t *)(smem_raw + L.keep);
+  const int bm_words = 1 << (P.bm_log2 - 5);
+  int32_t *scr = P.scratch + (size_t)blockIdx.x * P.scratch_ints;
+  const SeedTable &S = P.S;
+  const MapParamsDev &M = P.M;
+  const int mkp = M.colour_space ? 1 : 0;
+  const uint32_t rmask = (1u << M.region_bits) - 1u;
+
+  for (uint32_t item = blockIdx.x; item < P.n_work; item += gridDim.x) {
+    const uint32_t rs = P.work ? P.work[item] : item;
+    const int r = (int)(rs >> 1);
+    const int rl = P.read_len[r];
+    const uint32_t *seq = P.reads + (size_t)rs * P.stride;
+    int max_n_kmers = M.colour_space ? rl - S.min_span : rl - S.min_span + 1;
+    if (max_n_kmers < 0) max_n_kmers = 0;
+    __syncthreads();
+    if (!P.work && tid == 0) P.rs_range[rs] = make_uint2(0u, 0u);
+    if (rl <= 0 || max_n_kmers == 0) continue;
+    const int nw2 = (rl + 15) / 16;
+    for (int w = tid; w < nw2 + 3; w += nthr) {
+      uint32_t v = 0;
+      if (w < nw2) {
+        v = squeeze8(seq[2 * w]);
+        if (2 * w + 1 < P.stride) v |= squeeze8(seq[2 * w + 1]) << 16;
+      }
+      r2[w] = v;
+    }
+    for (int w = tid; w < bm_words; w += nthr) {
+      bm1[w] = 0u;
+      bm2[w] = 0u;
+    }
+    __syncthreads();
+    int kbase[SHRIMP_MAX_SEEDS + 1];
+    int K = 0;
+    for (int sn = 0; sn < S.n_seeds; sn++) {
+      kbase[sn] = K;
+      K += n_kmers_of(S, sn, rl, mkp);
+    }
+    kbase[S.n_seeds] = K;
+    if (K > P.k_cap) {
+      if (tid == 0) atomicOr(P.status, 2u);
+      continue;
+    }
+    if (tid < 32) {  // warp 0 projects (a few hundred k-mers)
+      uint32_t total = 0;
+      for (int sn = 0; sn < S.n_seeds; sn++) {
+        const int nk = kbase[sn + 1] - kbase[sn];
+        for (int i0 = 0; i0 < nk; i0 += 32) {
+          const int i = i0 + lane;
+          uint32_t start = 0, len = 0;
+          if (i < nk) {
+            const uint32_t m = S.n_runs[sn] ? mapidx_fast(S, sn, r2, mkp + i) : kmer_to_mapidx(S, sn, seq, (uint64_t)(mkp + i));
+            start = __ldg(P.I.offs[sn] + m);
+            len = __ldg(P.I.offs[sn] + m + 1) - start;
+            if (len > M.list_cutoff) len = 0;
+          }
+          const uint32_t incl = (uint32_t)warp_incl_scan((int)len, lane);
+          if (i < nk) {
+            T.kst[kbase[sn] + i] = start;
+            T.kpre[kbase[sn] + i] = total + incl - len;
+          }
+          total += __shfl_sync(0xffffffffu, incl, 31);
+        }
+      }
+      if (lane == 0) {
+        T.kpre[K] = total;
+        s_total = total;
+        s_ns = 0;
+      }
+    }
+    __syncthreads();
+    const uint32_t total = s_total;
+    if (total == 0) continue;
+    if (M.use_region_counts) {
+      for (uint32_t t = tid; t < total; t += nthr) {
+        uint32_t x, slot;
+        flat_entry(P, T, K, kbase, max_n_kmers, t, x, slot);
+        const uint32_t region = x >> M.region_bits;
+        region_mark(bm1, bm2, region, P.bm_log2);
+        if ((x & rmask) < (uint32_t)M.region_overlap && region > 0) region_mark(bm1, bm2, region - 1, P.bm_log2);
+      }
+      __syncthreads();
+      for (uint32_t t = tid; t < total; t += nthr) {
+        uint32_t x, slot;
+        flat_entry(P, T, K, kbase, max_n_kmers, t, x, slot);
+        const uint32_t region = x >> M.region_bits;
+        const bool kp = region_twice(bm2, region, P.bm_log2) ||
+                        ((x & rmask) < (uint32_t)M.region_overlap && region > 0 &&
+                         region_twice(bm2, region - 1, P.bm_log2));
+        if (kp) {
+          const uint32_t at = atomicAdd(&s_ns, 1u);
+          if (at < (uint32_t)cap) ent[at] = ((unsigned long long)x << 32) | slot;
+        }
+      }
+    } else {
+      if (total <= (uint32_t)cap)
+        for (uint32_t t = tid; t < total; t += nthr) {
+          uint32_t x, slot;
+          flat_entry(P, T, K, kbase, max_n_kmers, t, x, slot);
+          ent[t] = ((unsigned long long)x << 32) | slot;
+        }
+      if (tid == 0) s_ns = total;
+    }
+    __syncthreads();
+    const int ns = (int)s_ns;
+    if (ns > cap) {  // more candidates than the largest slab
+      if (tid == 0) atomicOr(P.status, 2u);
+      continue;
+    }
+    if (ns == 0) {
+      if (tid == 0) {
+        atomicAdd(&P.stats[1], total);
+        P.rs_range[rs] = make_uint2(0u, 0u);
+      }
+      continue;
+    }
+    int Pn = 32;
+    while (Pn < ns) Pn <<= 1;
+    for (int t = ns + tid; t < Pn; t += nthr) ent[t] = ~0ull;
+    __syncthreads();
+    for (int k = 2; k <= Pn; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int t = tid; t < (Pn >> 1); t += nthr) {
+          const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+          const int l = i | j;
+          const unsigned long long a = ent[i], b = ent[l];
+          const bool up = (i & k) == 0;
+          if ((a > b) == up) {
+            ent[i] = b;
+            ent[l] = a;
+          }
+        }
+        __syncthreads();
+      }
+    }
+    if (tid < 32) {
+      if (lane == 0) P.rs_range[rs] = make_uint2(0u, 0u);
+      scan_tail(P, rs, r, rl, max_n_kmers, ns, (int)total, ent, rec, cache, keep, scr, cap, lane);
+    }
+  }
+}
+
+size_t scan_smem_bytes(int cap, int max_rl, int k_cap, int bm_log2, int warps) {
+  return scan_layout(cap, max_rl, k_cap, bm_log2, false).total * warps;
+}
+size_t scan_big_smem_bytes(int cap, int max_rl, int k_cap, int bm_log2) {
+  return scan_layout(cap, max_rl, k_cap, bm_log2, true).total;
 }
 
 int launch_scan(shrimp_gpu_ctx *ctx, ScanParams &P, int warps_per_cta, int n_ctas) {
-  size_t smem = scan_smem_bytes(P.cap, P.max_rl, warps_per_cta);
-  static size_t configured = 0;
-  if (smem > configured) {
-    SH_CUDA(cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = 227 * 1024;
-  }
+  const size_t smem = scan_smem_bytes(P.cap, P.max_rl, P.k_cap, P.bm_log2, warps_per_cta);
+  SH_CUDA(cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   scan_kernel<<<n_ctas, SCAN_WARPS * 32, smem, ctx->stream>>>(P, warps_per_cta);
+  SH_CUDA(cudaGetLastError());
+  SH_LAUNCHED(ctx, ST_SCAN);
+  return SHRIMP_OK;
+}
+
+int launch_scan_big(shrimp_gpu_ctx *ctx, ScanParams &P, int n_ctas) {
+  const size_t smem = scan_big_smem_bytes(P.cap, P.max_rl, P.k_cap, P.bm_log2);
+  SH_CUDA(cudaFuncSetAttribute(scan_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  scan_big_kernel<<<n_ctas, SCAN_BIG_THREADS, smem, ctx->stream>>>(P);
   SH_CUDA(cudaGetLastError());
   SH_LAUNCHED(ctx, ST_SCAN);
   return SHRIMP_OK;

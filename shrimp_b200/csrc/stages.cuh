@@ -33,8 +33,10 @@ struct ScanParams {
   int32_t *scratch;
   int scratch_ints;
   int k_max;               // n_seeds * max_n_kmers upper bound
-  int cap;                 // slab entries per warp
+  int cap;                 // candidate slots (after the bitmap filter) per warp / per CTA
   int max_rl;
+  int k_cap;               // k-mers per read strand the shared-memory tables hold
+  int bm_log2;             // log2 of the bits of each region bitmap
 };
 
 struct AnchorRec {
