@@ -535,27 +535,330 @@ __global__ void __launch_bounds__(BLOCK) sw_full_cs_ring_kernel(const FullParams
   P.results[t] = R;
 }
 
+// ------------------------------------------------------------------------------------------------
+// colour space, four lanes per alignment (one per layer)
+// ------------------------------------------------------------------------------------------------
+// The thread-per-alignment colour kernel above needs 12 ring rows per thread, which leaves 4 warps per SM and
+// every one of its ~200 instructions per cell exposed to ALU latency.  Here lane k of a quad owns layer k:
+// 3 ring rows per lane (4x the resident warps for the same shared memory), a third of the arithmetic per
+// lane, and the cross-layer candidates (northwest and north moves may cross over) exchanged inside the quad
+// with shuffles of (value << 4 | layer priority | direction).  The "minus infinity" of the global-mode edge cells is -2^26
+// here instead of -INT_MAX/2 so that the packed form fits 32 bits: every value derived from it carries
+// exactly one such term, so all comparisons -- and with them every back-pointer -- come out as in the
+// reference, and such cells can never hold the winning score.
+#define NEG_Q (-(1 << 26))
+#define QUAD_THREADS 128
+
+__device__ __forceinline__ int warp_max_i(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// The eight quads of a warp step through rows and band offsets in LOCKSTEP (trip counts are the warp maxima, a
+// quad outside its own band is predicated off), so the cross-layer exchange can use full-mask shuffles -- a
+// shuffle under a computed sub-warp mask costs a WARPSYNC/collective sequence of ~10 instructions each.
+template <bool LOCAL>
+__device__ int quad_cs_dp(const FullParams &P, const FullTask &T, bool run, int slot, int k, int qbase, int32_t *sm,
+                          const uint32_t *genome, const uint32_t *read, const Rect &rect, int &ret_i, int &ret_j,
+                          int end_sc[3], unsigned long long &cells) {
+  const int W = P.W;
+  const int sstride = W * QUAD_THREADS;  // ints between the ring rows of two states
+  const int lena = T.glen, lenb = run ? T.rlen : 0;
+  const size_t bstride = (size_t)P.NT * 4;  // u16 elements between two band offsets
+  const int ao = P.a_open, ae = P.a_ext, bo = P.b_open, be = P.b_ext;
+  const bool revcmpl = T.gen_st && P.Tflag;
+  unsigned short *bp_task = (unsigned short *)P.bp64 + (size_t)slot * 4 + k;
+  int score = 0, max_i = 0, max_j = 0;
+  int letter = (k + T.initbp) % 4;
+  int pxmin = 0, pxmax = -1;
+  const int xp = P.xover;
+  const int add = k == 0 ? 0 : xp;
+  const int ini_n = LOCAL ? -bo + add : NEG_Q, ini_w = LOCAL ? -ao + add : NEG_Q, ini_nw = LOCAL ? add : NEG_Q;
+  const int resetval = k != 0 ? xp : 0;
+  const int match = P.match, mismatch = P.mismatch;
+  const int nrows_w = warp_max_i(lenb);
+  for (int i = 0; i < nrows_w; i++) {
+    const bool row_on = i < lenb;
+    int x_min = 0, x_max = -1;
+    if (row_on) rect_x_range(rect, lena, i, x_min, x_max);
+    const int width = row_on ? x_max - x_min + 1 : 0;
+    const int wmax = warp_max_i(width);
+    const bool nt = i < lenb - P.indel_taboo_len;
+    int qk = 15;
+    if (row_on) {
+      const int colour = (int)extract4(read, (uint64_t)i);
+      if (colour == 15) {
+        letter = (k + T.initbp) % 4;
+      } else {
+        qk = cstols_r(letter, colour);
+        letter = qk;
+      }
+      if (k == 0) cells += (unsigned long long)width;
+    }
+    // what a cell of the previous row reads as when it lies right of that row's band: the initial cell, or
+    // row -1 itself (local-style init with the global crossover penalty, sw-full-cs.c:268-270)
+    const int r_n = i == 0 ? -bo + add : ini_n, r_w = i == 0 ? -ao + add : ini_w, r_nw = i == 0 ? add : ini_nw;
+    int d_n = r_n, d_w = r_w, d_nw = r_nw;
+    const int delta = x_min - pxmin;
+    if (row_on && i > 0 && x_min - 1 <= pxmax) {
+      const int32_t *p = sm + delta * QUAD_THREADS;
+      d_n = p[0]; d_w = p[sstride]; d_nw = p[2 * sstride];
+    }
+    unsigned short *bp = bp_task + (size_t)i * W * bstride;
+    if (row_on) {
+      sm[0] = ini_n; sm[sstride] = ini_w; sm[2 * sstride] = ini_nw;  // edge cell (i, x_min-1)
+      *bp = 0;
+    }
+    int l_w = ini_w, l_nw = ini_nw;
+    int32_t *cur = sm;                                 // ring slot of offset s
+    const int32_t *prev = sm + delta * QUAD_THREADS;   // ring slot of the previous row's cell in the same column
+    uint32_t gpos = T.goff_global + (uint32_t)x_min;
+    uint32_t gword = genome[gpos >> 3];
+    for (int s = 1; s <= wmax; s++) {
+      const bool on = s <= width;
+      cur += QUAD_THREADS;
+      prev += QUAD_THREADS;
+      bp += bstride;
+      const int j = x_min + s - 1;
+      int u_n = r_n, u_w = r_w, u_nw = r_nw;
+      if (on && j <= pxmax) { u_n = prev[0]; u_w = prev[sstride]; u_nw = prev[2 * sstride]; }
+      if (on && (gpos & 7u) == 0u) gword = genome[gpos >> 3];
+      const int dbj = (int)((gword >> (4u * (gpos & 7u))) & 15u);
+      gpos++;
+      int ms = (dbj == qk) ? match : mismatch;
+      if (dbj == 15 || qk == 15) ms = 0;
+      // own layer: first-max of the diagonal sources (direction - 5) and of the north sources (direction - 1)
+      int mv, md, nv, nd;
+      if (!revcmpl) {
+        mv = d_nw; md = D_NW_NW - 5;
+        if (nt && d_n > mv) { mv = d_n; md = D_NW_N - 5; }
+        if (d_w > mv) { mv = d_w; md = D_NW_W - 5; }
+      } else {
+        mv = d_w; md = D_NW_W - 5;
+        if (nt && d_n > mv) { mv = d_n; md = D_NW_N - 5; }
+        if (d_nw > mv) { mv = d_nw; md = D_NW_NW - 5; }
+      }
+      {
+        const int A = u_nw - bo - be, B = u_n - be;
+        if (!revcmpl) {
+          if (nt) {
+            nv = A; nd = D_N_NW - 1;
+            if (B > nv) { nv = B; nd = D_N_N - 1; }
+          } else {
+            nv = B; nd = D_N_N - 1;
+          }
+        } else {
+          nv = B; nd = D_N_N - 1;
+          if (nt && A > nv) { nv = A; nd = D_N_NW - 1; }
+        }
+      }
+      // best other layer: the reference tries layers in ascending order and replaces on strict > (sw-full-cs.c:
+      // 375-437, :460-501), i.e. maximum value, ties to the lowest layer -- a plain integer max over the keys
+      // (value << 4 | (3 - layer) << 2 | direction) of the three other lanes
+      const int pm = (mv << 4) | ((3 - k) << 2) | md, pn = (nv << 4) | ((3 - k) << 2) | nd;
+      int km = __shfl_sync(0xffffffffu, pm, qbase + ((k + 1) & 3));
+      int kn = __shfl_sync(0xffffffffu, pn, qbase + ((k + 1) & 3));
+      km = max(km, __shfl_sync(0xffffffffu, pm, qbase + ((k + 2) & 3)));
+      kn = max(kn, __shfl_sync(0xffffffffu, pn, qbase + ((k + 2) & 3)));
+      km = max(km, __shfl_sync(0xffffffffu, pm, qbase + ((k + 3) & 3)));
+      kn = max(kn, __shfl_sync(0xffffffffu, pn, qbase + ((k + 3) & 3)));
+      const int ov = km >> 4, ow = kn >> 4;
+      const int oc = (((km & 3) + 5) << 2) | (3 - ((km >> 2) & 3));
+      const int oe = (((kn & 3) + 1) << 2) | (3 - ((kn >> 2) & 3));
+      int tmp, v_n, v_w, v_nw;
+      uint32_t t2, bits;
+      tmp = mv + ms; t2 = CSC(k, md + 5);
+      if (ov + ms + xp > tmp) { tmp = ov + ms + xp; t2 = (uint32_t)oc; }
+      if (LOCAL && tmp <= resetval) { tmp = resetval; t2 = 0; }
+      v_nw = tmp; bits = t2 << 10;
+      tmp = nv; t2 = CSC(k, nd + 1);
+      if (ow + xp > tmp) { tmp = ow + xp; t2 = (uint32_t)oe; }
+      if (LOCAL && tmp <= resetval) { tmp = resetval; t2 = 0; }
+      v_n = tmp; bits |= t2;
+      if (!revcmpl) {  // west (:511-545), same layer only
+        tmp = l_nw - ao - ae; t2 = CSC(k, D_W_NW);
+        if (!nt || l_w - ae > tmp) { tmp = l_w - ae; t2 = CSC(k, D_W_W); }
+      } else {
+        tmp = l_w - ae; t2 = CSC(k, D_W_W);
+        if (nt && l_nw - ao - ae > tmp) { tmp = l_nw - ao - ae; t2 = CSC(k, D_W_NW); }
+      }
+      if (LOCAL && tmp <= resetval) { tmp = resetval; t2 = 0; }
+      v_w = tmp; bits |= t2 << 5;
+      d_n = u_n; d_w = u_w; d_nw = u_nw;
+      l_w = v_w; l_nw = v_nw;
+      if (on) {
+        *bp = (unsigned short)bits;
+        cur[0] = v_n; cur[sstride] = v_w; cur[2 * sstride] = v_nw;
+        if (LOCAL || i == lenb - 1) {  // per-lane first maximum in traversal order; the quad combines at the end
+          int best = v_nw > v_n ? v_nw : v_n;
+          best = best > v_w ? best : v_w;
+          if (best > score) {
+            score = best; max_i = i; max_j = j;
+            end_sc[0] = v_n; end_sc[1] = v_w; end_sc[2] = v_nw;
+          }
+        }
+      }
+    }
+    if (row_on) {
+      pxmin = x_min;
+      pxmax = x_max;
+    }
+  }
+  ret_i = max_i;
+  ret_j = max_j;
+  return score;
+}
+
+__global__ void __launch_bounds__(QUAD_THREADS) sw_full_cs_quad_kernel(const FullParams P) {
+  extern __shared__ int32_t ring_smem[];
+  const int k = threadIdx.x & 3, qbase = (threadIdx.x & 31) & ~3;
+  int slot = blockIdx.x * (QUAD_THREADS / 4) + (threadIdx.x >> 2);
+  const bool live = slot < P.n_tasks;
+  if (!live) slot = P.n_tasks - 1;   // dead quads shadow the last task and stay in the warp's lockstep, switched off
+  const int t = P.perm ? P.perm[slot] : slot;
+  const FullTask T = P.tasks[t];
+  FullResult R;
+  memset(&R, 0, sizeof(R));
+  const bool run = live && T.run;
+  int32_t *sm = ring_smem + threadIdx.x;
+  const uint32_t *genome = T.gen_st ? P.genome_rc : P.genome_fwd;
+  const uint32_t *read = P.reads + (size_t)T.ridx * P.stride;
+  unsigned long long cells = 0;
+  int ei = 0, ej = 0, esc[3] = {0, 0, 0};
+  const Rect rect = task_rect(T, P.anchor_width, P.match, true);
+  int score = P.local ? quad_cs_dp<true>(P, T, run, slot, k, qbase, sm, genome, read, rect, ei, ej, esc, cells)
+                      : quad_cs_dp<false>(P, T, run, slot, k, qbase, sm, genome, read, rect, ei, ej, esc, cells);
+  // the reference scans cells in (i, j, layer) order and keeps the first maximum (sw-full-cs.c:552-580):
+  // every lane gathers the four per-layer candidates and picks the winner
+  int ek = 0;
+  int w_score = 0, w_i = 0, w_j = 0, w_e0 = 0, w_e1 = 0, w_e2 = 0;
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const int os = __shfl_sync(0xffffffffu, score, qbase + q);
+    const int oi = __shfl_sync(0xffffffffu, ei, qbase + q);
+    const int oj = __shfl_sync(0xffffffffu, ej, qbase + q);
+    const int o0 = __shfl_sync(0xffffffffu, esc[0], qbase + q);
+    const int o1 = __shfl_sync(0xffffffffu, esc[1], qbase + q);
+    const int o2 = __shfl_sync(0xffffffffu, esc[2], qbase + q);
+    const bool better = os > w_score || (os == w_score && os > 0 && (oi < w_i || (oi == w_i && oj < w_j)));
+    if (better) { w_score = os; w_i = oi; w_j = oj; ek = q; w_e0 = o0; w_e1 = o1; w_e2 = o2; }
+  }
+  if (k != 0 || !live) return;
+  if (!T.run) {
+    P.results[t] = R;
+    return;
+  }
+  score = w_score; ei = w_i; ej = w_j; esc[0] = w_e0; esc[1] = w_e1; esc[2] = w_e2;
+  if (cells) atomicAdd(P.cells, cells);
+  if (!(score >= 0 && score >= T.thresh)) {  // sw_full_cs :1216-1226
+    P.results[t] = R;
+    return;
+  }
+  R.score = score;
+  const int W = P.W;
+  const size_t NT = (size_t)P.NT;
+  const unsigned short *bp = (const unsigned short *)P.bp64 + (size_t)slot * 4;
+  uint8_t *ops = P.ops + (size_t)t * (size_t)(P.max_glen + P.max_rlen);
+  auto layer_letter = [&](int kk, int i) -> int {
+    int letter = (kk + T.initbp) % 4, out = 15;
+    for (int q = 0; q <= i; q++) {
+      const int colour = (int)extract4(read, (uint64_t)q);
+      if (colour == 15) {
+        out = 15;
+        letter = (kk + T.initbp) % 4;
+      } else {
+        out = cstols_r(letter, colour);
+        letter = out;
+      }
+    }
+    return out;
+  };
+  auto back_of = [&](int ci, int cj, int kk, int state) -> int {  // state: 0 north, 1 west, 2 northwest
+    if (ci < 0 || cj < 0) return 0;
+    int xmn, xmx;
+    rect_x_range(rect, T.glen, ci, xmn, xmx);
+    const int s = cj - xmn + 1;
+    if (s <= 0 || cj > xmx) return 0;
+    return (int)((bp[((size_t)ci * W + s) * NT * 4 + kk] >> (5 * state)) & 31u);
+  };
+  int i = ei, j = ej, kk = ek;
+  int state = 2, fromscore = esc[2];  // do_backtrace :643-652
+  if (esc[1] > fromscore) { state = 1; fromscore = esc[1]; }
+  if (esc[0] > fromscore) state = 0;
+  int from = back_of(i, j, kk, state);
+  int off = (T.glen + T.rlen) - 1;
+  int read_start = 0, genome_start = 0;
+  if (from != 0) {
+    while (i >= 0 && j >= 0) {
+      const int dir = from >> 2, lay = from & 3;
+      uint8_t op;
+      if (dir == D_N_N || dir == D_N_NW) {
+        R.deletions++;
+        read_start = i--;
+        op = (uint8_t)(2 | (kk << 4));
+      } else if (dir == D_W_W || dir == D_W_NW) {
+        R.insertions++;
+        genome_start = j--;
+        op = 1;
+      } else {
+        const int dbj = (int)extract4(genome, (uint64_t)T.goff_global + (uint64_t)j);
+        const int q = layer_letter(kk, i);
+        if (dbj == q || dbj == 15 || q == 15) R.matches++;
+        else R.mismatches++;
+        read_start = i--;
+        genome_start = j--;
+        op = (uint8_t)(3 | (kk << 4));
+      }
+      if (kk != lay) {
+        op |= 4;
+        R.crossovers++;
+        kk = lay;
+      }
+      ops[off] = op;
+      const int nstate = (dir == D_N_N || dir == D_NW_N) ? 0 : (dir == D_W_W || dir == D_NW_W) ? 1 : 2;
+      from = back_of(i, j, kk, nstate);
+      off--;
+      if (from == 0) break;
+    }
+  }
+  off++;
+  if (kk != 0 && off < T.glen + T.rlen) {  // :931-934
+    ops[off] |= 4;
+    R.crossovers++;
+  }
+  R.read_start = read_start;
+  R.gmapped = ej - genome_start + 1;
+  R.genome_start = genome_start + (int)T.goff_contig;
+  R.rmapped = ei - read_start + 1;
+  R.ops_start = off;
+  R.ops_len = (T.glen + T.rlen) - off;
+  P.results[t] = R;
+}
+
 // Shared memory per thread of one ring launch, and the block size chosen for it.
-size_t ring_smem_per_thread(bool cs, int W) { return (size_t)(cs ? 12 : 3) * (size_t)W * 4; }
+// (colour space runs four lanes per alignment, each with the 3 rows of its layer: 3 rows per THREAD either way)
+size_t ring_smem_per_thread(bool cs, int W) { return (size_t)3 * (size_t)W * 4; }
 int ring_block_threads(bool cs, int W) {
+  if (cs) return QUAD_THREADS;
   const size_t per = ring_smem_per_thread(cs, W);
   return per * 64 <= 48 * 1024 ? 64 : 32;
 }
-bool ring_fits(bool cs, int W) { return ring_smem_per_thread(cs, W) * 32 <= 200 * 1024; }
+bool ring_fits(bool cs, int W) { return ring_smem_per_thread(cs, W) * (cs ? QUAD_THREADS : 32) <= 200 * 1024; }
 
 int launch_sw_full_ring(shrimp_gpu_ctx *ctx, const FullParams &P, bool cs) {
   if (P.n_tasks <= 0) return SHRIMP_OK;
   const int block = ring_block_threads(cs, P.W);
   const size_t smem = ring_smem_per_thread(cs, P.W) * block;
-  const int grid = (P.n_tasks + block - 1) / block;
+  const int per_block = cs ? block / 4 : block;
+  const int grid = (P.n_tasks + per_block - 1) / per_block;
 #define RING_LAUNCH(K)                                                                                   \
   do {                                                                                                   \
     SH_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));    \
     K<<<grid, block, smem, ctx->stream>>>(P);                                                            \
   } while (0)
   if (cs) {
-    if (block == 64) RING_LAUNCH(sw_full_cs_ring_kernel<64>);
-    else RING_LAUNCH(sw_full_cs_ring_kernel<32>);
+    RING_LAUNCH(sw_full_cs_quad_kernel);
   } else {
     if (block == 64) RING_LAUNCH(sw_full_ls_ring_kernel<64>);
     else RING_LAUNCH(sw_full_ls_ring_kernel<32>);
