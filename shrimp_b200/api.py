@@ -288,15 +288,15 @@ class GpuContext:
         read_len = np.ascontiguousarray(read_len, dtype=np.int32)
         n = reads.shape[0]
         pc = params.to_c(scores, getattr(self, "colour_space", False))
-        hits = np.zeros(max(1, n * params.num_outputs), dtype=HitC)
+        hits = np.empty(max(1, n * params.num_outputs), dtype=HitC)   # untouched pages cost nothing
         n_per = np.zeros(max(1, n), dtype=np.int32)
         max_rl = int(read_len.max()) if n else 0
         pool_cap = max(1024, n * 3 * max(1, max_rl))
         if initbp is not None:
             initbp = np.ascontiguousarray(initbp, dtype=np.int8)
-        stage = np.zeros(max(1, n * stage_cap_per_read), dtype=StageHitC) if want_stage else None
+        stage = np.empty(max(1, n * stage_cap_per_read), dtype=StageHitC) if want_stage else None
         while True:
-            edits = np.zeros(pool_cap, dtype=np.uint8)
+            edits = np.empty(pool_cap, dtype=np.uint8)
             n_hits, e_used, n_stage = C.c_int64(0), C.c_int64(0), C.c_int64(0)
             st = MapStatsC()
             rc = self._L.shrimp_gpu_map_reads(
@@ -323,8 +323,8 @@ class GpuContext:
         npairs = n // 2
         pc = params.to_c(scores, getattr(self, "colour_space", False))
         pp = PairParamsC(PAIR_MODES[pair_mode], min_insert, max_insert, int(half_paired))
-        hits = np.zeros(max(1, npairs * params.num_outputs * 4), dtype=HitC)
-        pairs = np.zeros(max(1, npairs * params.num_outputs), dtype=PairC)
+        hits = np.empty(max(1, npairs * params.num_outputs * 4), dtype=HitC)
+        pairs = np.empty(max(1, npairs * params.num_outputs), dtype=PairC)
         n_per_pair = np.zeros(max(1, npairs), dtype=np.int32)
         n_unp = np.zeros(max(1, n), dtype=np.int32)
         max_rl = int(read_len.max()) if n else 0
@@ -332,7 +332,7 @@ class GpuContext:
         if initbp is not None:
             initbp = np.ascontiguousarray(initbp, dtype=np.int8)
         while True:
-            edits = np.zeros(pool_cap, dtype=np.uint8)
+            edits = np.empty(pool_cap, dtype=np.uint8)
             n_hits, n_pairs_out, e_used = C.c_int64(0), C.c_int64(0), C.c_int64(0)
             st = MapStatsC()
             rc = self._L.shrimp_gpu_map_pairs(

@@ -146,7 +146,7 @@ struct HostOut {
   bool edits_short, hits_short;
   uint64_t full_calls, pass2_vector_calls, pass2_vector_cells;
 };
-int host_pass2_read(const Chunk &C, int r, int n1, int task_base, double full_thr, HostOut &O, std::vector<int> *kept_tasks);
+int host_pass2_all(const Chunk &C, const int32_t *n_sel, double full_thr, HostOut &O, int32_t *n_per_read);
 void host_fill_hit(const Chunk &C, const HostHit &h, int r, HostOut &O);
 int run_full_sw(shrimp_gpu_ctx *ctx, DevBuf &d_perm, DevBuf &d_row, DevBuf *d_bp, FullParams FP, int n, bool cs,
                 uint32_t *d_cls_count);

@@ -170,6 +170,7 @@ struct VecTaskArrays {
   const int32_t *ridx;    // read index into reads (stride words each)
   const int32_t *rlen;
   const int8_t *initbp;   // colour space only
+  const uint32_t *out;    // optional: scores[out[t]] receives the score of task t (dense task lists); else scores[t]
 };
 int launch_sw_vector(shrimp_gpu_ctx *ctx, const uint32_t *d_genome, const uint32_t *d_genome_ls,
                      const uint32_t *d_reads, int read_stride_words, int n_tasks, int max_rlen, int max_glen,

@@ -551,12 +551,7 @@ extern "C" int shrimp_gpu_map_pairs(shrimp_gpu_ctx *ctx, const shrimp_map_params
   SH_TRY(chunk_fetch_full(C, n_slots_b, true));
   const uint32_t *h_cnt = (const uint32_t *)((char *)pl->h_nsel.p + (size_t)n_reads * 4);
   const int32_t *NSEL = pl->h_nsel.as<int32_t>();
-  task_base = 0;
-  for (int r = 0; r < n_reads; r++) {
-    const int n2 = host_pass2_read(C, r, NSEL[r], task_base, mp->sw_full_threshold, O, nullptr);
-    if (n_unpaired_per_read) n_unpaired_per_read[r] = n2;
-    task_base += NSEL[r];
-  }
+  SH_TRY(host_pass2_all(C, NSEL, mp->sw_full_threshold, O, n_unpaired_per_read));
   *n_hits = O.n_out;
   if (edits_used) *edits_used = O.e_used;
   if (stats) {

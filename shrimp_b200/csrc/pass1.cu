@@ -37,7 +37,10 @@ __device__ __forceinline__ uint32_t hash_genome_window_dev(const uint32_t *genom
   return key;
 }
 
-// one thread per read strand: fill the sw_vector task arrays for its hits
+// one thread per read strand: DENSE sw_vector task lists (one per genome orientation) of its eligible hits.
+// A strand's tasks stay together and in list order, so the two tasks a thread of sw_vector_kernel packs into
+// its 16-bit lanes come from the same read (same length) whenever possible; out[t] names the hit slot the
+// score goes to.
 __global__ void build_vec_tasks_kernel(const TaskBuildParams P) {
   const uint32_t rs = blockIdx.x * blockDim.x + threadIdx.x;
   if (rs >= 2u * (uint32_t)P.n_reads) return;
@@ -45,28 +48,33 @@ __global__ void build_vec_tasks_kernel(const TaskBuildParams P) {
   const int r = (int)(rs >> 1), st = (int)(rs & 1u);
   const int rl = P.read_len[r];
   const bool cs = P.M.colour_space != 0;
+  // orientation used by pass 1: letter space always scores read strand st on the forward genome;
+  // colour space scores the forward read and flips strand-1 windows onto the rc genome.
+  const int ori = (cs && st == 1) ? 1 : 0;
   uint32_t n_elig = 0;
   unsigned long long elig_cells = 0;
+  for (uint32_t k = 0; k < rg.y; k++) {
+    const DevHit h = P.hits[rg.x + k];
+    if (h.matches >= P.M.min_matches) {
+      n_elig++;
+      elig_cells += (unsigned long long)h.w_len * (unsigned long long)rl;
+    }
+  }
+  uint32_t t = n_elig ? atomicAdd(&P.task_stats[4 + ori], n_elig) : 0u;
   for (uint32_t k = 0; k < rg.y; k++) {
     const uint32_t hi = rg.x + k;
     const DevHit h = P.hits[hi];
     const bool eligible = h.matches >= P.M.min_matches;
-    if (eligible) {
-      n_elig++;
-      elig_cells += (unsigned long long)h.w_len * (unsigned long long)rl;
-    }
     const uint32_t coff = P.G.contig_off[h.cn];
-    // orientation used by pass 1: letter space always scores read strand st on the forward genome;
-    // colour space scores the forward read and flips strand-1 windows onto the rc genome.
-    const int ori = (cs && st == 1) ? 1 : 0;
     const uint32_t g = ori ? coff + (P.G.contig_len[h.cn] - h.g_off - (uint32_t)h.w_len) : coff + h.g_off;
-    for (int o = 0; o < (cs ? 2 : 1); o++) {
-      const bool mine = eligible && o == ori;
-      P.goff[o][hi] = g;
-      P.glen[o][hi] = mine ? h.w_len : 0;
-      P.ridx[o][hi] = cs ? (int32_t)(2 * r) : (int32_t)rs;
-      P.rlen[o][hi] = rl;
-      if (cs) P.initbp_out[o][hi] = P.initbp[r];
+    if (eligible) {
+      P.goff[ori][t] = g;
+      P.glen[ori][t] = h.w_len;
+      P.ridx[ori][t] = cs ? (int32_t)(2 * r) : (int32_t)rs;
+      P.rlen[ori][t] = rl;
+      if (cs) P.initbp_out[ori][t] = P.initbp[r];
+      P.out[ori][t] = hi;
+      t++;
     }
     if (P.slot) {
       const uint32_t *gen = cs ? (ori ? P.G.cs_rc : P.G.cs) : P.G.ls;

@@ -8,6 +8,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include <algorithm>
+#include <omp.h>
 #include <cub/cub.cuh>
 #include "chunk.cuh"
 
@@ -507,23 +508,21 @@ int chunk_scan(Chunk &C) {
   return SHRIMP_OK;
 }
 
-// sw_vector over every eligible window (matches >= min_matches): true scores per hit slot in d_vtrue
+// sw_vector over every eligible window (matches >= min_matches): true scores per hit slot in d_vtrue[0]
 int chunk_vector(Chunk &C) {
   shrimp_gpu_ctx *ctx = C.ctx;
   Pipeline *pl = C.pl;
   cudaStream_t st = ctx->stream;
   const bool cs = C.cs;
   const size_t HU = std::max<uint32_t>(C.hits_used, 1);
-  const size_t task_bytes = HU * 4 * 4 + ((HU + 3) & ~(size_t)3);
+  const size_t task_bytes = HU * 4 * 5 + ((HU + 3) & ~(size_t)3);
   VecTaskArrays VT[2];
-  for (int o = 0; o < C.n_ori; o++) {
-    SH_TRY(pl->d_task[o].ensure(task_bytes));
-    SH_CUDA(cudaMemsetAsync(pl->d_task[o].p, 0, task_bytes, st));  // hit slots that stay gaps get glen = 0
-    SH_TRY(pl->d_vtrue[o].ensure(HU * 4));
-    SH_CUDA(cudaMemsetAsync(pl->d_vtrue[o].p, 0xff, HU * 4, st));
-  }
+  for (int o = 0; o < C.n_ori; o++) SH_TRY(pl->d_task[o].ensure(task_bytes));
+  SH_TRY(pl->d_vtrue[0].ensure(HU * 4));
+  SH_CUDA(cudaMemsetAsync(pl->d_vtrue[0].p, 0xff, HU * 4, st));
   SH_TRY(pl->d_slot.ensure(HU * 4));
   SH_TRY(pl->d_writer.ensure(HU));
+  uint32_t n_dense[2] = {0, 0};
   {
     ScopedStage ss(ctx, ST_PASS1);
     TaskBuildParams TB;
@@ -540,25 +539,30 @@ int chunk_vector(Chunk &C) {
       TB.glen[o] = (int32_t *)(tb + HU * 4);
       TB.ridx[o] = (int32_t *)(tb + HU * 8);
       TB.rlen[o] = (int32_t *)(tb + HU * 12);
-      TB.initbp_out[o] = (int8_t *)(tb + HU * 16);
+      TB.out[o] = (uint32_t *)(tb + HU * 16);
+      TB.initbp_out[o] = (int8_t *)(tb + HU * 20);
       VT[o].goff = TB.goff[o];
       VT[o].glen = TB.glen[o];
       VT[o].ridx = TB.ridx[o];
       VT[o].rlen = TB.rlen[o];
+      VT[o].out = TB.out[o];
       VT[o].initbp = cs ? TB.initbp_out[o] : nullptr;
     }
     TB.initbp = cs ? pl->d_initbp.as<int8_t>() : nullptr;
     TB.slot = C.M.hash_filter_calls ? pl->d_slot.as<uint32_t>() : nullptr;
     TB.task_stats = C.cnt + 20;
     SH_TRY(launch_build_vec_tasks(ctx, TB));
+    SH_CUDA(cudaMemcpyAsync(n_dense, C.cnt + 24, 8, cudaMemcpyDeviceToHost, st));
+    SH_CUDA(cudaStreamSynchronize(st));
   }
-  if (C.hits_used > 0) {
+  {
     ScopedStage ss(ctx, ST_VECTOR);
     for (int o = 0; o < C.n_ori; o++) {
+      if (n_dense[o] == 0) continue;
       const uint32_t *gen = cs ? (o ? C.G.cs_rc : C.G.cs) : C.G.ls;
       const uint32_t *gen_ls = cs ? (o ? C.G.ls_rc : C.G.ls) : nullptr;
-      SH_TRY(launch_sw_vector(ctx, gen, gen_ls, pl->d_reads.as<uint32_t>(), C.stride, (int)C.hits_used, C.max_rl,
-                              C.max_wl, VT[o], pl->d_vtrue[o].as<int32_t>(), ST_VECTOR));
+      SH_TRY(launch_sw_vector(ctx, gen, gen_ls, pl->d_reads.as<uint32_t>(), C.stride, (int)n_dense[o], C.max_rl,
+                              C.max_wl, VT[o], pl->d_vtrue[0].as<int32_t>(), ST_VECTOR));
     }
   }
   return SHRIMP_OK;
@@ -573,8 +577,8 @@ Pass1Params chunk_pass1_params(Chunk &C) {
   PP.rs_range = pl->d_rs_range.as<uint2>();
   PP.read_len = pl->d_read_len.as<int32_t>();
   PP.n_reads = C.n_reads;
-  PP.vtrue[0] = pl->d_vtrue[0].as<int32_t>();
-  PP.vtrue[1] = pl->d_vtrue[C.n_ori - 1].as<int32_t>();
+  PP.vtrue[0] = pl->d_vtrue[0].as<int32_t>();   // every hit has one orientation: both launches scatter into one array
+  PP.vtrue[1] = pl->d_vtrue[0].as<int32_t>();
   PP.slot = pl->d_slot.as<uint32_t>();
   PP.writer = pl->d_writer.as<uint8_t>();
   PP.sel = pl->d_sel.as<int32_t>();
@@ -761,29 +765,31 @@ void host_fill_hit(const Chunk &C, const HostHit &h, int r, HostOut &O) {
   O.e_used += h.res.ops_len;
 }
 
-// read_pass2 after the DP (mapping.c:1644-1722) for read r: tasks [task_base, task_base + n1).  Returns the
-// number of hits written to O; kept_tasks (optional) receives their task indices.
-int host_pass2_read(const Chunk &C, int r, int n1, int task_base, double full_thr, HostOut &O,
-                    std::vector<int> *kept_tasks) {
+// read_pass2 after the DP (mapping.c:1644-1722) for one read: tasks [task_base, task_base + n1) -> the hits it
+// keeps, in output order, as (task, scores) records.  hh / h2 are caller-owned scratch of >= n1 entries.
+struct KeptRec {
+  int task_idx, score_full, pass2_key;
+  double posterior;
+};
+static int host_pass2_select(const Chunk &C, int r, int n1, int task_base, double full_thr, HostHit *hh, HostHit **h2,
+                             KeptRec *out, uint64_t &full_calls, uint64_t &vcalls, uint64_t &vcells) {
   const shrimp_map_params *mp = C.mp;
-  std::vector<HostHit> hh((size_t)std::max(n1, 1));
-  std::vector<HostHit *> h2((size_t)n1 + 1);
   int n2 = 0;
   for (int k = 0; k < n1; k++) {
     HostHit &h = hh[k];
     host_score_hit(C, task_base + k, h);
     if (!C.cs) {
-      O.pass2_vector_calls++;
-      O.pass2_vector_cells += (uint64_t)h.info.w_len * (uint64_t)C.read_len[r];
+      vcalls++;
+      vcells += (uint64_t)h.info.w_len * (uint64_t)C.read_len[r];
     }
-    if (h.res.score > 0 || h.res.ops_len > 0) O.full_calls++;
+    if (h.res.score > 0 || h.res.ops_len > 0) full_calls++;
     h.pass2_key = full_thr < 0 ? h.score_full : (int)h.pct_score_full;
     const double thr = full_thr < 0 ? -full_thr : h.info.score_max * (full_thr / 100.0);
     if (h.score_full >= thr) h2[n2++] = &h;
   }
-  dedup_pass(h2.data(), &n2, cmp_gen_start);
-  dedup_pass(h2.data(), &n2, cmp_gen_end);
-  qsort(h2.data(), n2, sizeof(HostHit *), cmp_score);
+  dedup_pass(h2, &n2, cmp_gen_start);
+  dedup_pass(h2, &n2, cmp_gen_end);
+  qsort(h2, n2, sizeof(HostHit *), cmp_score);
   if (n2 > mp->num_outputs) n2 = mp->num_outputs;
   if (mp->strata && n2 > 0) {
     int i;
@@ -793,10 +799,116 @@ int host_pass2_read(const Chunk &C, int r, int n1, int task_base, double full_th
   }
   if (n2 > 0 && !(mp->max_alignments == 0 || n2 <= mp->max_alignments)) n2 = 0;
   for (int i = 0; i < n2; i++) {
-    host_fill_hit(C, *h2[i], r, O);
-    if (kept_tasks) kept_tasks->push_back(h2[i]->task_idx);
+    out[i].task_idx = h2[i]->task_idx;
+    out[i].score_full = h2[i]->score_full;
+    out[i].pass2_key = h2[i]->pass2_key;
+    out[i].posterior = h2[i]->posterior;
   }
   return n2;
+}
+
+// read_pass2 for every read of the chunk (n_sel[r] tasks each, in task order), OpenMP over contiguous blocks
+// of reads: the duplicate removal and ranking stay the reference's qsort-based code, only the
+// loop over reads is parallel.  Appends to O in read order; n_per_read[r] = hits kept for read r.
+int host_pass2_all(const Chunk &C, const int32_t *n_sel, double full_thr, HostOut &O, int32_t *n_per_read) {
+  const int n_reads = C.n_reads, NT = C.mp->num_tmp_outputs, NO = C.mp->num_outputs;
+  const int T = std::max(1, std::min(omp_get_max_threads(), 64));
+  std::vector<std::vector<KeptRec>> kept((size_t)T);
+  std::vector<std::vector<int32_t>> counts((size_t)T);
+  std::vector<int64_t> nh((size_t)T + 1, 0), ne((size_t)T + 1, 0);
+  std::vector<uint64_t> fc((size_t)T, 0), vc((size_t)T, 0), vl((size_t)T, 0);
+  std::vector<int64_t> tb((size_t)T + 1, 0);  // first task of each block
+  {
+    int64_t acc = 0;
+    int t = 0;
+    for (int r = 0; r <= n_reads; r++) {
+      while (t <= T && r == (int)((int64_t)n_reads * t / T)) tb[t++] = acc;
+      if (r < n_reads) acc += n_sel[r];
+    }
+  }
+  const FullResult *RES = C.pl->h_results.as<FullResult>();
+#pragma omp parallel num_threads(T)
+  {
+    const int t = omp_get_thread_num();
+    const int r0 = (int)((int64_t)n_reads * t / T), r1 = (int)((int64_t)n_reads * (t + 1) / T);
+    std::vector<HostHit> hh((size_t)NT + 1);
+    std::vector<HostHit *> h2((size_t)NT + 1);
+    std::vector<KeptRec> tmp((size_t)NO + 1);
+    std::vector<KeptRec> &K = kept[t];
+    counts[t].resize((size_t)(r1 - r0));
+    int64_t task_base = tb[t], e = 0;
+    for (int r = r0; r < r1; r++) {
+      const int n2 = host_pass2_select(C, r, n_sel[r], (int)task_base, full_thr, hh.data(), h2.data(), tmp.data(), fc[t],
+                                       vc[t], vl[t]);
+      for (int i = 0; i < n2; i++) {
+        K.push_back(tmp[i]);
+        e += RES[tmp[i].task_idx].ops_len;
+      }
+      counts[t][r - r0] = n2;
+      task_base += n_sel[r];
+    }
+    nh[t + 1] = (int64_t)K.size();
+    ne[t + 1] = e;
+  }
+  for (int t = 0; t < T; t++) {
+    nh[t + 1] += nh[t];
+    ne[t + 1] += ne[t];
+    O.full_calls += fc[t];
+    O.pass2_vector_calls += vc[t];
+    O.pass2_vector_cells += vl[t];
+  }
+  const int64_t hit_base = O.n_out, edit_base = O.e_used;
+  if (hit_base + nh[T] > O.hits_cap) O.hits_short = true;
+  if (O.edits && edit_base + ne[T] > O.edits_cap) O.edits_short = true;
+  const bool fill = !O.hits_short;
+  const bool fill_edits = O.edits && !O.edits_short;
+  const SelInfo *INFO = C.pl->h_info.as<SelInfo>();
+  const uint8_t *OPS = C.pl->h_ops.as<uint8_t>();
+#pragma omp parallel num_threads(T)
+  {
+    const int t = omp_get_thread_num();
+    const int r0 = (int)((int64_t)n_reads * t / T), r1 = (int)((int64_t)n_reads * (t + 1) / T);
+    int64_t hi = hit_base + nh[t], eo = edit_base + ne[t];
+    size_t q = 0;
+    for (int r = r0; r < r1; r++) {
+      const int n2 = counts[t][r - r0];
+      if (n_per_read) n_per_read[r] = n2;
+      for (int i = 0; i < n2 && fill; i++, q++, hi++) {
+        const KeptRec &kr = kept[t][q];
+        const SelInfo &info = INFO[kr.task_idx];
+        const FullResult &res = RES[kr.task_idx];
+        shrimp_hit &o = O.hits[hi];
+        o.read_idx = r;
+        o.cn = info.cn;
+        o.gen_st = info.gen_st;
+        o.w_len = info.w_len;
+        o.g_off = info.g_off;
+        o.score_vector = info.score_vector;
+        o.score_full = kr.score_full;
+        o.pass2_key = kr.pass2_key;
+        o.score_max = info.score_max;
+        o.matches = info.matches;
+        o.sw_score = res.score;
+        o.posterior = kr.posterior;
+        o.read_start = res.read_start;
+        o.rmapped = res.rmapped;
+        o.genome_start = res.genome_start;
+        o.gmapped = res.gmapped;
+        o.sfr_matches = res.matches;
+        o.mismatches = res.mismatches;
+        o.insertions = res.insertions;
+        o.deletions = res.deletions;
+        o.crossovers = res.crossovers;
+        o.edit_len = res.ops_len;
+        o.edit_off = eo;
+        if (fill_edits) memcpy(O.edits + eo, OPS + C.ops_stride * (size_t)kr.task_idx + res.ops_start, (size_t)res.ops_len);
+        eo += res.ops_len;
+      }
+    }
+  }
+  O.n_out = hit_base + nh[T];
+  O.e_used = edit_base + ne[T];
+  return SHRIMP_OK;
 }
 
 }  // namespace shrimp
@@ -914,12 +1026,7 @@ static int map_impl(shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, int n_read
   O.hits_cap = hits_cap;
   O.edits = edits;
   O.edits_cap = edits_cap;
-  int task_base = 0;
-  for (int r = 0; r < n_reads; r++) {
-    const int n2 = host_pass2_read(C, r, NSEL[r], task_base, mp->sw_full_threshold, O, nullptr);
-    if (n_hits_per_read) n_hits_per_read[r] = n2;
-    task_base += NSEL[r];
-  }
+  SH_TRY(host_pass2_all(C, NSEL, mp->sw_full_threshold, O, n_hits_per_read));
   *n_hits = O.n_out;
   if (edits_used) *edits_used = O.e_used;
   if (stats) {
@@ -927,6 +1034,10 @@ static int map_impl(shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, int n_read
     stats->vector_calls += O.pass2_vector_calls;
     stats->vector_cells += O.pass2_vector_cells;
     stats->full_calls = O.full_calls;
+  }
+  if (O.hits_short) {
+    set_error("%s: hits_cap too small", who);
+    return SHRIMP_E_NOMEM;
   }
   if (O.edits_short && edits) {
     set_error("%s: edits_cap too small, %lld bytes needed", who, (long long)O.e_used);

@@ -53,7 +53,7 @@ struct TaskBuildParams {
   const uint2 *rs_range;
   const int32_t *read_len;
   int n_reads;
-  // task arrays indexed by hit slot, one set per genome orientation (colour space reverses the
+  // dense task arrays, one set per genome orientation (colour space reverses the
   // strand-1 hits onto the reverse-complement genome, mapping.c:1303-1312)
   uint32_t *goff[2];
   int32_t *glen[2];
@@ -61,8 +61,9 @@ struct TaskBuildParams {
   int32_t *rlen[2];
   int8_t *initbp_out[2];
   const int8_t *initbp;   // per read (colour space)
+  uint32_t *out[2];       // hit slot of every dense task
   uint32_t *slot;         // f1 cache slot per hit (hash_filter_calls)
-  uint32_t *task_stats;   // [0] eligible windows, [2..3] their cells (u64)
+  uint32_t *task_stats;   // [0] eligible windows, [2..3] their cells (u64), [4], [5] dense task count per orientation
 };
 
 struct Pass1Params {

@@ -175,8 +175,8 @@ __global__ void __launch_bounds__(SWV_BLOCK) sw_vector_kernel(const SwvParams P)
     }
   }
   // tasks with glen <= 0 are placeholders (pipeline slots that pass 1 will never read)
-  if (glenA > 0) P.scores[tA] = (int)(int16_t)(best & 0xffffu);
-  if (hasB && glenB > 0) P.scores[tB] = (int)(int16_t)(best >> 16);
+  if (glenA > 0) P.scores[P.t.out ? P.t.out[tA] : (uint32_t)tA] = (int)(int16_t)(best & 0xffffu);
+  if (hasB && glenB > 0) P.scores[P.t.out ? P.t.out[tB] : (uint32_t)tB] = (int)(int16_t)(best >> 16);
 }
 
 template <int T>
@@ -337,6 +337,7 @@ extern "C" int shrimp_gpu_sw_vector_batch(shrimp_gpu_ctx *ctx, const uint32_t *g
   t.ridx = (const int32_t *)(tb + n * 8);
   t.rlen = (const int32_t *)(tb + n * 12);
   t.initbp = cs ? (const int8_t *)(tb + n * 16) : nullptr;
+  t.out = nullptr;
   {
     ScopedStage ss(ctx, ST_VECTOR);
     SH_TRY(launch_sw_vector(ctx, ctx->d_genome.as<uint32_t>(), cs ? ctx->d_genome_ls.as<uint32_t>() : nullptr,
