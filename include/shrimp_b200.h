@@ -218,6 +218,7 @@ typedef struct shrimp_map_stats {
   uint64_t vector_bypassed;     /* f1 cache hits */
   uint64_t full_calls, full_cells;
   uint64_t device_vector_cells; /* sum glen*rlen over the windows the device scored */
+  uint64_t scan_big_strands;    /* read strands served by the CTA-per-strand scan kernel (long index lists) */
 } shrimp_map_stats;
 
 /* initbp: per-read initial base (colour space) or NULL.  hits_cap >= n_reads*num_outputs always

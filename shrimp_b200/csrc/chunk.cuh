@@ -122,6 +122,7 @@ struct Chunk {
   const int32_t *read_len = nullptr;   // host
   uint32_t *cnt = nullptr;             // device counters [64]
   uint32_t hits_used = 0;
+  uint32_t scan_big = 0;               // read strands that went through scan_big_kernel
   int n_ori = 1;
   size_t ops_stride = 0;
 };

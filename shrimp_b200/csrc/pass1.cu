@@ -143,7 +143,7 @@ __global__ void pass1_replay_kernel(const Pass1Params P) {
         bypassed++;
       } else {
         calls++;
-        cells += (unsigned long long)h.w_len * (unsigned long long)rl;
+        if (!M.gapless) cells += (unsigned long long)h.w_len * (unsigned long long)rl;
       }
       const int pct = (1000 * 100 * score) / h.score_max;
       P.hits[hi].score_vector = score;
@@ -207,6 +207,40 @@ __global__ void select_unpaired_kernel(const Pass1Params P) {
   }
 #undef P1KEY
   P.n_sel[r] = load;
+}
+
+// one thread per dense task: sw_gapless (common/sw-gapless.c:57-117, letter space) -- best ungapped segment on the
+// diagonal through the hit's anchor, walked over the WHOLE contig/read overlap as f1_run does (f1-wrapper.h:
+// 121-124: genome = contig, glen = contig length, g_idx = g_off + anchor.x, r_idx = anchor.y)
+__global__ void sw_gapless_kernel(const GaplessParams P) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= P.n_tasks) return;
+  const uint32_t hi = P.out[t];
+  const DevHit h = P.hits[hi];
+  const uint32_t *read = P.reads + (size_t)P.ridx[t] * P.stride;
+  const int rlen = P.rlen[t];
+  const uint64_t coff = P.G.contig_off[h.cn];
+  const int glen = (int)P.G.contig_len[h.cn];
+  const int g_idx = (int)h.g_off + h.ax, r_idx = h.ay;
+  int g = g_idx < r_idx ? 0 : g_idx - r_idx;
+  int r = g_idx < r_idx ? r_idx - g_idx : 0;
+  int score = 0, max_score = 0;
+  while (g < glen && r < rlen) {
+    score += (extract4(P.G.ls, coff + (uint64_t)g) == extract4(read, (uint64_t)r)) ? P.match : P.mismatch;
+    if (score > max_score) max_score = score;
+    g++;
+    r++;
+    if (score < 0) score = 0;
+  }
+  P.scores[hi] = max_score;
+}
+
+int launch_sw_gapless(shrimp_gpu_ctx *ctx, const GaplessParams &P) {
+  if (P.n_tasks == 0) return SHRIMP_OK;
+  sw_gapless_kernel<<<(P.n_tasks + 127) / 128, 128, 0, ctx->stream>>>(P);
+  SH_CUDA(cudaGetLastError());
+  SH_LAUNCHED(ctx, ST_VECTOR);
+  return SHRIMP_OK;
 }
 
 int launch_build_vec_tasks(shrimp_gpu_ctx *ctx, const TaskBuildParams &P) {

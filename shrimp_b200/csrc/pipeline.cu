@@ -21,6 +21,7 @@ int launch_scan_big(shrimp_gpu_ctx *ctx, ScanParams &P, int n_ctas);
 
 int launch_scan(shrimp_gpu_ctx *ctx, ScanParams &P, int warps_per_cta, int n_ctas);
 int launch_build_vec_tasks(shrimp_gpu_ctx *ctx, const TaskBuildParams &P);
+int launch_sw_gapless(shrimp_gpu_ctx *ctx, const GaplessParams &P);
 int launch_pass1_replay(shrimp_gpu_ctx *ctx, const Pass1Params &P);
 int launch_select_unpaired(shrimp_gpu_ctx *ctx, const Pass1Params &P);
 int launch_sw_full_ls(shrimp_gpu_ctx *ctx, const FullParams &P);
@@ -272,8 +273,8 @@ int chunk_begin(Chunk &C, shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, int 
     set_error("%s: colour-space reads need initbp", who);
     return SHRIMP_E_ARG;
   }
-  if (mp->gapless) {
-    set_error("%s: gapless (-U / mirna) pass 1 is not wired into the chunk pipeline yet", who);
+  if (mp->gapless && cs) {
+    set_error("%s: gapless (-U / mirna) pass 1 is wired for letter space only", who);
     return SHRIMP_E_ARG;
   }
   if (cs && mp->compute_mapping_qualities) {
@@ -420,7 +421,8 @@ int chunk_scan(Chunk &C) {
   else
     bm_log2 = 5;
   const int k_cap = std::max(32, std::min(K_max, 1024));
-  const bool small_useful = !filt || est * 8 <= (double)(1 << 15);
+  bool small_useful = !filt || est * 8 <= (double)(1 << 15);
+  if (getenv("SHRIMP_SCAN_FORCE_BIG")) small_useful = false;  // test hook: every strand through the CTA kernel
   // CTA kernel: 2^19-bit bitmaps, 8192 candidates
   const int big_cap = 8192, big_bm_log2 = filt ? 19 : 5, big_k_cap = std::max(32, K_max);
   if (scan_big_smem_bytes(big_cap, max_rl, big_k_cap, big_bm_log2) > 226 * 1024) {
@@ -486,6 +488,7 @@ int chunk_scan(Chunk &C) {
       P.scratch_ints = 2 * k_max + 2 * big_cap;
       P.scratch = pl->d_scratch.as<int32_t>();
       int ctas = (int)std::min<uint32_t>((uint32_t)big_ctas_max, P.n_work);
+      C.scan_big = P.n_work;
       SH_TRY(launch_scan_big(ctx, P, ctas));
       SH_CUDA(cudaMemcpyAsync(h3, cnt, 12, cudaMemcpyDeviceToHost, st));
       SH_CUDA(cudaStreamSynchronize(st));
@@ -564,6 +567,25 @@ int chunk_vector(Chunk &C) {
       SH_TRY(launch_sw_vector(ctx, gen, gen_ls, pl->d_reads.as<uint32_t>(), C.stride, (int)n_dense[o], C.max_rl,
                               C.max_wl, VT[o], pl->d_vtrue[0].as<int32_t>(), ST_VECTOR));
     }
+    if (C.M.gapless) {
+      // -U / mirna: pass 1 ranks by sw_gapless; the sw_vector scores above still feed hit_run_full_sw (:386)
+      SH_TRY(pl->d_vtrue[1].ensure(HU * 4));
+      SH_CUDA(cudaMemsetAsync(pl->d_vtrue[1].p, 0xff, HU * 4, st));
+      GaplessParams GP;
+      memset(&GP, 0, sizeof(GP));
+      GP.G = C.G;
+      GP.hits = pl->d_hits.as<DevHit>();
+      GP.reads = pl->d_reads.as<uint32_t>();
+      GP.stride = C.stride;
+      GP.out = VT[0].out;
+      GP.ridx = VT[0].ridx;
+      GP.rlen = VT[0].rlen;
+      GP.n_tasks = n_dense[0];
+      GP.match = ctx->sw.match;
+      GP.mismatch = ctx->sw.mismatch;
+      GP.scores = pl->d_vtrue[1].as<int32_t>();
+      SH_TRY(launch_sw_gapless(ctx, GP));
+    }
   }
   return SHRIMP_OK;
 }
@@ -577,8 +599,8 @@ Pass1Params chunk_pass1_params(Chunk &C) {
   PP.rs_range = pl->d_rs_range.as<uint2>();
   PP.read_len = pl->d_read_len.as<int32_t>();
   PP.n_reads = C.n_reads;
-  PP.vtrue[0] = pl->d_vtrue[0].as<int32_t>();   // every hit has one orientation: both launches scatter into one array
-  PP.vtrue[1] = pl->d_vtrue[0].as<int32_t>();
+  // every hit has one orientation: both sw_vector launches scatter into one array; gapless mode ranks by sw_gapless
+  PP.vtrue[0] = PP.vtrue[1] = (C.M.gapless ? pl->d_vtrue[1] : pl->d_vtrue[0]).as<int32_t>();
   PP.slot = pl->d_slot.as<uint32_t>();
   PP.writer = pl->d_writer.as<uint8_t>();
   PP.sel = pl->d_sel.as<int32_t>();
@@ -705,6 +727,7 @@ void chunk_stats(const Chunk &C, const uint32_t *hc, shrimp_map_stats *stats) {
   stats->vector_bypassed = hc[8 + 5];
   stats->vector_cells = *(const unsigned long long *)(hc + 8 + 6);
   stats->full_cells = *(const unsigned long long *)(hc + 16);
+  stats->scan_big_strands = C.scan_big;
 }
 
 // hit_run_full_sw's scores + hit_run_post_sw (mapping.c:1609-1625, letter space) for task idx

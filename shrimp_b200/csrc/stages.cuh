@@ -66,6 +66,18 @@ struct TaskBuildParams {
   uint32_t *task_stats;   // [0] eligible windows, [2..3] their cells (u64), [4], [5] dense task count per orientation
 };
 
+struct GaplessParams {
+  GenomeView G;
+  const DevHit *hits;
+  const uint32_t *reads;
+  int stride;
+  const uint32_t *out;     // hit slot per dense task
+  const int32_t *ridx, *rlen;
+  uint32_t n_tasks;
+  int match, mismatch;
+  int32_t *scores;         // per hit slot
+};
+
 struct Pass1Params {
   MapParamsDev M;
   DevHit *hits;

@@ -21,6 +21,23 @@ MAP_CASES = {
     "c1_repeat": dict(gen="c1_repeat", args=[], opts={}),
     # colour space: post_sw is not on the path yet, so parity runs with --no-mapping-qualities
     "c2_small": dict(gen="c2_small", args=["--no-mapping-qualities"], opts={"compute_mapping_qualities": False}),
+    # BASELINE.json configs[3]: 22 bp reads vs a miRNA-like database, default options and -M mirna (gmapper.c:
+    # 1498-1515: hashed 5-seed set, gapless pass 1, gap opens -255, no window cache, one seed match, window 100 %,
+    # local full SW, no mapping qualities)
+    "c4_small": dict(gen="c4_small", args=[], opts={}),
+    "c4_small_mirna": dict(gen="c4_small", args=["-M", "mirna"],
+                           opts=dict(match_mode=1, window_len=100.0, gapless=True, hash_filter_calls=False,
+                                     Gflag=False, compute_mapping_qualities=False),
+                           mirna=True, anchor_width=0),
+    # BASELINE.json configs[4], "overly sensitive" mode (README:481-534, letter-space subset): four weight-11 seeds,
+    # one seed match is enough (no region filter, every index position is an anchor), wide windows, threshold band
+    # of the full SW (-a -1), no window cache (-Z), no index trimming (-V)
+    "c5_small": dict(gen="c5_small",
+                     args=["-s", "w11", "-n", "1", "-w", "150%", "-r", "50%", "-l", "40%", "-Z", "-h", "60%", "-a", "-1",
+                           "-V"],
+                     opts=dict(match_mode=1, window_len=150.0, window_gen_threshold=50.0, window_overlap=40.0,
+                               hash_filter_calls=False, sw_full_threshold=60.0),
+                     seeds_weight=11, anchor_width=-1, list_cutoff=0xFFFFFFFF),
 }
 
 
@@ -49,8 +66,20 @@ class LsCase:
             self.packed = np.stack([_pack_codes(_LS_CODE[r[1]].astype(np.uint32), self.stride) for r in self.reads])
             self.scores = LS_DEFAULT_SCORES
         self.read_names = [r[0] for r in self.reads]
-        self.seeds = S.load_default_seeds()
+        spec = MAP_CASES[name]
+        self.hflag = bool(spec.get("mirna"))
+        if self.hflag:
+            self.seeds = S.load_default_mirna_seeds()
+            from shrimp_b200.api import Scores
+            self.scores = Scores(self.scores.match, self.scores.mismatch, -255, self.scores.a_gap_ext, -255,
+                                 self.scores.b_gap_ext, self.scores.crossover)
+        else:
+            self.seeds = S.load_default_seeds(spec.get("seeds_weight", 0))
+        self.anchor_width = spec.get("anchor_width", 8)
         self.total_len = int(sum(c.size for c in self.contig_codes))
+        from shrimp_b200.api import auto_list_cutoff
+        self.list_cutoff = spec.get("list_cutoff", auto_list_cutoff(
+            self.total_len, 12 if self.hflag else max(s.weight for s in self.seeds)))
 
     def write_fasta(self, d: str):
         os.makedirs(d, exist_ok=True)

@@ -13,11 +13,11 @@ pytestmark = pytest.mark.gpu
 
 
 def run_gpu(ctx, case, **over):
-    ctx.sw_setup(1400, 1000, case.scores, use_colours=case.colour, anchor_width=8)
+    ctx.sw_setup(1500, 1000, case.scores, use_colours=case.colour, anchor_width=case.anchor_width)
     ctx.load_genome([_pack_codes(c.astype(np.uint32)) for c in case.contig_codes], [c.size for c in case.contig_codes],
                     colour_space=case.colour)
-    ctx.build_index(case.seeds)
-    params = MapParams(list_cutoff=auto_list_cutoff(case.total_len, max(s.weight for s in case.seeds)), **over)
+    ctx.build_index(case.seeds, hflag=case.hflag)
+    params = MapParams(list_cutoff=case.list_cutoff, **over)
     return ctx.map_reads(params, case.scores, case.packed, case.read_len, initbp=case.initbp, want_stage=True)
 
 
@@ -45,6 +45,29 @@ def test_pipeline_matches_reference_golden(gpu_ctx, name):
     bad = np.nonzero((sam != gold["sam"]).any(axis=1))[0]
     assert bad.size == 0, (bad[:5], sam[bad[:5]], gold["sam"][bad[:5]])
     assert np.array_equal(cig, gold["cigars"])
+
+
+def test_repeats_reach_the_cta_scan_kernel(gpu_ctx):
+    """read strands with more candidates than a warp's slab go through scan_big_kernel (and still match, see the
+    golden test of c1_repeat)"""
+    case = LsCase("c1_repeat")
+    res = run_gpu(gpu_ctx, case)
+    assert res.stats["scan_big_strands"] > 0
+
+
+@pytest.mark.parametrize("name", ["c1_small", "c2_small", "c5_small"])
+def test_cta_scan_kernel_alone_matches_reference_golden(gpu_ctx, name, monkeypatch):
+    """every read strand forced through the CTA-per-strand scan kernel (the path long index lists take at
+    hg18 scale): same hit lists and alignments as the reference"""
+    monkeypatch.setenv("SHRIMP_SCAN_FORCE_BIG", "1")
+    gold = np.load(os.path.join(GOLD, f"map_{name}.npz"))
+    case = LsCase(name)
+    res = run_gpu(gpu_ctx, case, **MAP_CASES[name]["opts"])
+    assert res.stats["scan_big_strands"] == 2 * len(case.read_len)
+    got_stage = stage_tuple_array(res.stage)
+    assert got_stage.shape == gold["stage"].shape and np.array_equal(got_stage, gold["stage"])
+    sam, cig = sam_arrays(case, res)
+    assert np.array_equal(sam, gold["sam"]) and np.array_equal(cig, gold["cigars"])
 
 
 def test_pipeline_alignment_strings_match_oracle(gpu_ctx):

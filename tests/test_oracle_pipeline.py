@@ -12,9 +12,9 @@ from oracle import pipeline as op
 
 def run_oracle(case: LsCase, **over):
     g = op.Genome(case.contig_codes, case.colour)
-    ix = op.Index(g, case.seeds)
-    opts = op.MapOptions(scores=case.scores, colour_space=case.colour,
-                         list_cutoff=op.auto_list_cutoff(g.total_len, max(s.weight for s in case.seeds)), **over)
+    ix = op.Index(g, case.seeds, hflag=case.hflag)
+    opts = op.MapOptions(scores=case.scores, colour_space=case.colour, list_cutoff=case.list_cutoff,
+                         anchor_width=case.anchor_width, **over)
     hits, nper, stage, stats = op.map_reads(g, ix, opts, case.packed, case.read_len, initbp=case.initbp,
                                             want_stage=True)
     return g, hits, nper, stage, stats

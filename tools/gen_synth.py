@@ -198,6 +198,9 @@ CONFIGS = {
     "c3_small": dict(genome=dict(total_len=300_000, n_contigs=3, seed=19, n_frac=0.002, repeat_unit=1500,
                                  repeat_copies=30, repeat_div=0.02),
                      reads=dict(n_pairs=600, read_len=100, seed=20, sub=0.02, indel_p=0.1), paired=True),
+    # BASELINE.json configs[3]: short reads vs a miRNA-like database of many 22 bp contigs
+    "c4_small": dict(genome=dict(total_len=22 * 300, n_contigs=300, seed=21),
+                     reads=dict(n_reads=800, read_len=22, seed=22, sub=0.03)),
     "c5_small": dict(genome=dict(total_len=200_000, n_contigs=1, seed=15),
                      reads=dict(n_reads=500, read_len=75, seed=16, sub=0.04, indel_p=0.5, max_indel=5)),
 }
