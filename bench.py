@@ -36,18 +36,41 @@ FULL_INSTR_PER_CELL = {"ls": 30.0, "cs": 220.0}
 class Workload:
     """Seeded synthetic genome + simulated reads of one BASELINE.json config."""
 
-    def __init__(self, key, desc, colour, read_len, contig_len, n_contigs, seed_genome, default_reads, binary, args):
+    def __init__(self, key, desc, colour, read_len, contig_len, n_contigs, seed_genome, default_reads, binary, args,
+                 paired=False, n_frac=0.0):
         self.key, self.desc, self.colour, self.read_len = key, desc, colour, read_len
         self.contig_len, self.n_contigs, self.seed_genome = contig_len, n_contigs, seed_genome
         self.genome_len = contig_len * n_contigs
         self.default_reads, self.binary, self.args = default_reads, binary, args
+        self.paired, self.n_frac = paired, n_frac
+        self._genome = None
+
+    def resize(self, genome_mb: int):
+        self.contig_len = genome_mb * 1_000_000 // self.n_contigs
+        self.genome_len = self.contig_len * self.n_contigs
+        self.desc += f" [genome scaled to {genome_mb} Mb]"
         self._genome = None
 
     def genome(self):
         if self._genome is None:
             rng = np.random.default_rng(self.seed_genome)
-            self._genome = rng.integers(0, 4, size=self.genome_len, dtype=np.uint8)
+            g = rng.integers(0, 4, size=self.genome_len, dtype=np.uint8)
+            if self.n_frac > 0:     # runs of N (code 15), 1 kb each
+                n_runs = int(self.genome_len * self.n_frac / 1000)
+                for p0 in rng.integers(0, self.genome_len - 1000, size=n_runs):
+                    g[p0:p0 + 1000] = 15
+            self._genome = g
         return self._genome
+
+    def packed_contigs(self):
+        """4 bits per base, 8 per uint32 (util.h:41-42), one array per contig"""
+        out = []
+        for c in self.contigs():
+            n = c.size
+            pad = (-n) % 8
+            cc = np.concatenate([c, np.zeros(pad, dtype=np.uint8)]) if pad else c
+            out.append(np.ascontiguousarray(cc[0::2] | (cc[1::2] << 4)).view(np.uint32))
+        return out
 
     def contig_names(self):
         return [f"contig{i}" for i in range(self.n_contigs)]
@@ -56,8 +79,34 @@ class Workload:
         g = self.genome()
         return [g[i * self.contig_len:(i + 1) * self.contig_len] for i in range(self.n_contigs)]
 
+    def pairs(self, n_pairs, seed):
+        """opp-in pairs, insert N(300, 30), 2 % substitutions; mates interleaved: rows 2k, 2k+1"""
+        g, rl = self.genome(), self.read_len
+        rr = np.random.default_rng(seed)
+        ins = np.maximum(rl + 5, rr.normal(300.0, 30.0, size=n_pairs).astype(np.int64))
+        cn = rr.integers(0, self.n_contigs, size=n_pairs)
+        pos = cn * self.contig_len + rr.integers(0, self.contig_len - 400 - rl, size=n_pairs)
+        idx = np.arange(rl)[None, :]
+        a = g[pos[:, None] + idx].copy()
+        b = g[(pos + ins - rl)[:, None] + idx].copy()
+        for m in (a, b):
+            sub = (rr.random(m.shape) < 0.02) & (m < 4)
+            m[sub] = (m[sub] + rr.integers(1, 4, size=int(sub.sum()))) % 4
+        cm = np.arange(16, dtype=np.uint8)
+        cm[:4] = CMPL
+        brc = cm[b][:, ::-1]
+        flip = rr.random(n_pairs) < 0.5
+        r1 = np.where(flip[:, None], brc, a)
+        r2 = np.where(flip[:, None], a, brc)
+        out = np.empty((2 * n_pairs, rl), dtype=np.uint8)
+        out[0::2] = r1
+        out[1::2] = r2
+        return out, None
+
     def reads(self, n_reads, seed):
         """-> (codes [n, read_len] uint8 (letters, or colours in colour space), initbp or None)"""
+        if self.paired:
+            return self.pairs(n_reads // 2, seed)
         g, rl = self.genome(), self.read_len
         rr = np.random.default_rng(seed)
         cn = rr.integers(0, self.n_contigs, size=n_reads)
@@ -81,14 +130,20 @@ class Workload:
         return col, np.full(n_reads, 3, dtype=np.int8)
 
     def write_reads_fasta(self, path, codes):
-        lut = np.frombuffer(b"0123" if self.colour else b"ACGT", dtype=np.uint8)
+        lut = np.frombuffer(b"0123............" if self.colour else b"ACGTNNNNNNNNNNNN", dtype=np.uint8)
         body = lut[codes]
+        if self.paired:     # path.1 / path.2, mates p<k>/1 and p<k>/2
+            with open(path + ".1", "wb") as f1, open(path + ".2", "wb") as f2:
+                for k in range(body.shape[0] // 2):
+                    f1.write(b">p%d/1\n" % k + body[2 * k].tobytes() + b"\n")
+                    f2.write(b">p%d/2\n" % k + body[2 * k + 1].tobytes() + b"\n")
+            return
         with open(path, "wb") as f:
             for i in range(body.shape[0]):
                 f.write(b">r%d\n" % i + (b"T" if self.colour else b"") + body[i].tobytes() + b"\n")
 
     def write_genome_fasta(self, path):
-        lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+        lut = np.frombuffer(b"ACGTNNNNNNNNNNNN", dtype=np.uint8)
         with open(path, "wb") as f:
             for nm, c in zip(self.contig_names(), self.contigs()):
                 f.write(b">" + nm.encode() + b"\n" + lut[c].tobytes() + b"\n")
@@ -101,6 +156,12 @@ WORKLOADS = {
                    "in 10 contigs, 3 default seeds w12, sw_full_cs crossovers, --no-mapping-qualities; one step = "
                    "one batch of the 10 M-read job", True, 36, 10_000_000, 10, 3, 1_000_000, "gmapper-cs",
                    ["--no-mapping-qualities"]),
+    # BASELINE.json configs[2]: paired-end letter space; the genome is scaled by --genome-mb (default 300 Mb; 3000 =
+    # the hg18-sized configuration, every read strand then goes through the CTA-per-strand scan kernel)
+    "c3": Workload("c3", "C3 paired-end letter-space: 2x100bp opp-in pairs (insert N(300,30), 2% subs) vs iid genome "
+                   "in 24 contigs with 1% N runs, 3 default seeds w12, -p opp-in -I 0,1000; value counts reads "
+                   "(2 per pair)", False, 100, 12_500_000, 24, 5, 400_000, "gmapper-ls",
+                   ["-p", "opp-in", "-I", "0,1000"], paired=True, n_frac=0.01),
     # BASELINE.json configs[0]: the reference's own CPU-runnable case
     "c1": Workload("c1", "C1 letter-space: 100k x 50bp reads (2% subs) vs iid 10 Mb genome, 3 default seeds w12",
                    False, 50, 10_000_000, 1, 1, 100_000, "gmapper-ls", []),
@@ -184,7 +245,8 @@ REF_DIR = os.path.join(ROOT, "oracle", "_ref")
 
 def run_reference(w: Workload, workdir: str, n_threads: int, reads_fa: str, prefix: str):
     """returns (seconds of 'Read Mapping Time', vector GCUPS aggregate, wall seconds)"""
-    cmd = [os.path.join(REF_DIR, w.binary), "-N", str(n_threads), *w.args, "-L", prefix, reads_fa]
+    rd = ["-1", reads_fa + ".1", "-2", reads_fa + ".2"] if w.paired else [reads_fa]
+    cmd = [os.path.join(REF_DIR, w.binary), "-N", str(n_threads), *w.args, "-L", prefix, *rd]
     t0 = time.time()
     r = subprocess.run(cmd, cwd=workdir, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
     wall = time.time() - t0
@@ -210,7 +272,7 @@ def reference_setup(w: Workload, workdir: str, reads_codes, ctx=None):
         ctx.save_projection(os.path.join(workdir, "proj"), w.contig_names())
         return "projection saved from HBM in the -S format"
     w.write_genome_fasta(os.path.join(workdir, "genome.fa"))
-    r = subprocess.run([os.path.join(REF_DIR, w.binary), "-S", "proj", "genome.fa"], cwd=workdir,
+    r = subprocess.run([os.path.join(REF_DIR, w.binary), *(w.args if w.paired else []), "-S", "proj", "genome.fa"], cwd=workdir,
                        stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
     if r.returncode != 0:
         raise RuntimeError("reference gmapper -S failed: " + r.stderr[-500:])
@@ -225,8 +287,7 @@ def build_context(w: Workload, device: int):
     seeds = S.load_default_seeds()
     ctx.sw_setup(1400, 1000, scores, use_colours=w.colour)  # dblen/qrlen as gmapper sets them up (longest_read_len 1000)
     t0 = time.time()
-    ctx.load_genome([shrimp_b200.api._pack_codes(c.astype(np.uint32)) for c in w.contigs()],
-                    [w.contig_len] * w.n_contigs, colour_space=w.colour)
+    ctx.load_genome(w.packed_contigs(), [w.contig_len] * w.n_contigs, colour_space=w.colour)
     ctx.build_index(seeds)
     return ctx, scores, seeds, time.time() - t0
 
@@ -239,6 +300,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--reads", type=int, default=0, help="reads per GPU per step (0 = the workload's default)")
+    ap.add_argument("--genome-mb", type=int, default=0, help="scale the synthetic genome (c3: default 300, 3000 = hg18 size)")
     ap.add_argument("--cpu-sample", type=int, default=200_000, help="reads in the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
@@ -247,6 +309,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     ncores = os.cpu_count() or 1
     w = WORKLOADS[a.workload]
+    if a.genome_mb or w.key == "c3":
+        w.resize(a.genome_mb or 300)
     n_reads = a.reads or w.default_reads
     ref_bin = os.path.join(REF_DIR, w.binary)
 
@@ -303,7 +367,18 @@ def main():
     initbp = torch.from_numpy(initbp_np).pin_memory().numpy() if initbp_np is not None else None
 
     ctx, scores, seeds, index_s = build_context(w, local_rank)
-    params = MapParams(list_cutoff=auto_list_cutoff(w.genome_len, 12), compute_mapping_qualities=not w.colour)
+    params = MapParams(list_cutoff=auto_list_cutoff(w.genome_len, 12), compute_mapping_qualities=not w.colour,
+                       match_mode=4 if w.paired else 2)
+
+    def map_host():
+        if w.paired:
+            return ctx.map_pairs(params, scores, packed, read_len)
+        return ctx.map_reads(params, scores, packed, read_len, initbp=initbp)
+
+    def map_dev():
+        if w.paired:
+            return ctx.map_pairs_resident(params, scores)
+        return ctx.map_resident(params, scores)
 
     def barrier():
         if world > 1:
@@ -311,10 +386,14 @@ def main():
         torch.cuda.synchronize()
 
     # first call uploads the batch and leaves it resident; also the e2e path's warm-up
-    res = ctx.map_reads(params, scores, packed, read_len, initbp=initbp)
-    n_mapped = int((res.n_hits_per_read > 0).sum())
+    res = map_host()
+    if w.paired:
+        n_mapped = int(2 * (res.n_pairs_per_pair > 0).sum() +
+                       ((res.n_unpaired_per_read.reshape(-1, 2) > 0) & (res.n_pairs_per_pair[:, None] == 0)).sum())
+    else:
+        n_mapped = int((res.n_hits_per_read > 0).sum())
     for _ in range(a.warmup):
-        ctx.map_resident(params, scores)
+        map_dev()
 
     # ---- device-resident timed region: exactly K steps -------------------------------------------
     dpx_peak = ctx.dpx_peak()
@@ -326,7 +405,7 @@ def main():
         for _ in range(a.steps):
             ctx.flush_l2()
             ctx.event_record(0)
-            st = ctx.map_resident(params, scores)
+            st = map_dev()
             ctx.event_record(1)
             step_ms.append(ctx.event_elapsed_ms())
         barrier()
@@ -344,7 +423,7 @@ def main():
     barrier()
     t0 = time.perf_counter()
     for _ in range(a.steps):
-        res = ctx.map_reads(params, scores, packed, read_len, initbp=initbp)
+        res = map_host()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     h2d, d2h = ctx.last_transfer_bytes()
@@ -404,7 +483,7 @@ def main():
 
     # ---- CPU baseline: the reference binary on this box's cores, bounded sample ---------------------
     cpu = None
-    if world == 1 and not a.no_cpu_baseline and os.path.exists(ref_bin):
+    if world == 1 and not a.no_cpu_baseline and os.path.exists(ref_bin) and w.genome_len <= 400_000_000:
         try:
             sample, _ = w.reads(a.cpu_sample, 1000)
             with tempfile.TemporaryDirectory() as d:

@@ -270,6 +270,10 @@ int shrimp_gpu_map_pairs(shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, const
  * the device: the "inputs already resident" throughput of bench.py.  shrimp_gpu_last_transfer_bytes
  * reports the host<->device bytes of the last shrimp_gpu_map_reads call. */
 int shrimp_gpu_map_resident(shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, shrimp_map_stats *stats);
+/* same for pairs: maps again the pairs the previous shrimp_gpu_map_pairs call left in HBM; the mid-pipeline host
+ * stage (readpair_pass2) is part of the path and stays inside, the records go to library-owned scratch */
+int shrimp_gpu_map_pairs_resident(shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, const shrimp_pair_params *pp,
+                                  shrimp_map_stats *stats);
 int shrimp_gpu_last_transfer_bytes(shrimp_gpu_ctx *ctx, uint64_t *h2d, uint64_t *d2h);
 
 /* CUDA-event bracket on the library's stream (which = 0 start, 1 stop) and an L2 flush (writes a

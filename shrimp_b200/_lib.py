@@ -129,6 +129,8 @@ def lib() -> C.CDLL:
                                        vp, C.c_int64, C.POINTER(C.c_int64), vp, C.c_int64, C.POINTER(C.c_int64),
                                        vp, vp, vp, C.c_int64, C.POINTER(C.c_int64), C.POINTER(MapStatsC)]
     L.shrimp_gpu_map_pairs.restype = i32
+    L.shrimp_gpu_map_pairs_resident.argtypes = [vp, C.POINTER(MapParamsC), C.POINTER(PairParamsC), C.POINTER(MapStatsC)]
+    L.shrimp_gpu_map_pairs_resident.restype = i32
     L.shrimp_gpu_map_resident.argtypes = [vp, C.POINTER(MapParamsC), C.POINTER(MapStatsC)]
     L.shrimp_gpu_map_resident.restype = i32
     L.shrimp_gpu_last_transfer_bytes.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]

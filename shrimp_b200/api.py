@@ -356,6 +356,16 @@ class GpuContext:
         check(self._L.shrimp_gpu_map_resident(self._h, C.byref(pc), C.byref(st)), "shrimp_gpu_map_resident")
         return {k: int(getattr(st, k)) for k, _ in MapStatsC._fields_}
 
+    def map_pairs_resident(self, params: MapParams, scores: Scores, pair_mode: str = "opp-in", min_insert: int = 0,
+                           max_insert: int = 1000) -> dict:
+        """All stages of map_pairs on the pairs the last map_pairs call left in HBM (bench.py `value`)."""
+        pc = params.to_c(scores, getattr(self, "colour_space", False))
+        pp = PairParamsC(PAIR_MODES[pair_mode], min_insert, max_insert, 1)
+        st = MapStatsC()
+        check(self._L.shrimp_gpu_map_pairs_resident(self._h, C.byref(pc), C.byref(pp), C.byref(st)),
+              "shrimp_gpu_map_pairs_resident")
+        return {k: int(getattr(st, k)) for k, _ in MapStatsC._fields_}
+
     def last_transfer_bytes(self):
         a, b = C.c_uint64(), C.c_uint64()
         check(self._L.shrimp_gpu_last_transfer_bytes(self._h, C.byref(a), C.byref(b)), "shrimp_gpu_last_transfer_bytes")

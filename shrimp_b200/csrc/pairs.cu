@@ -294,13 +294,13 @@ static void push_dominant(HostPair *h, int n, bool absolute, int nip, int (*cmp)
 
 using namespace shrimp;
 
-extern "C" int shrimp_gpu_map_pairs(shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, const shrimp_pair_params *pp,
-                                    int n_pairs, const uint32_t *reads, int stride, const int32_t *read_len,
-                                    const int8_t *initbp, shrimp_hit *hits_out, int64_t hits_cap, int64_t *n_hits,
-                                    shrimp_pair *pairs_out, int64_t pairs_cap, int64_t *n_pairs_out,
-                                    int32_t *n_pairs_per_pair, int32_t *n_unpaired_per_read, uint8_t *edits,
-                                    int64_t edits_cap, int64_t *edits_used, shrimp_map_stats *stats) {
-  const char *who = "shrimp_gpu_map_pairs";
+static int map_pairs_impl(shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, const shrimp_pair_params *pp,
+                          int n_pairs, const uint32_t *reads, int stride, const int32_t *read_len,
+                          const int8_t *initbp, shrimp_hit *hits_out, int64_t hits_cap, int64_t *n_hits,
+                          shrimp_pair *pairs_out, int64_t pairs_cap, int64_t *n_pairs_out,
+                          int32_t *n_pairs_per_pair, int32_t *n_unpaired_per_read, uint8_t *edits,
+                          int64_t edits_cap, int64_t *edits_used, shrimp_map_stats *stats, bool resident) {
+  const char *who = resident ? "shrimp_gpu_map_pairs_resident" : "shrimp_gpu_map_pairs";
   if (!pp || !hits_out || !n_hits || !pairs_out || !n_pairs_out || n_pairs < 0) {
     set_error("%s: invalid argument", who);
     return SHRIMP_E_ARG;
@@ -316,7 +316,7 @@ extern "C" int shrimp_gpu_map_pairs(shrimp_gpu_ctx *ctx, const shrimp_map_params
     return SHRIMP_E_ARG;
   }
   Chunk C;
-  SH_TRY(chunk_begin(C, ctx, mp, 2 * n_pairs, reads, stride, read_len, initbp, false, who));
+  SH_TRY(chunk_begin(C, ctx, mp, 2 * n_pairs, reads, stride, read_len, initbp, resident, who));
   if (C.cs) {
     set_error("%s: colour-space pairs are not wired yet", who);
     return SHRIMP_E_ARG;
@@ -570,4 +570,35 @@ extern "C" int shrimp_gpu_map_pairs(shrimp_gpu_ctx *ctx, const shrimp_map_params
     return SHRIMP_E_NOMEM;
   }
   return SHRIMP_OK;
+}
+
+extern "C" int shrimp_gpu_map_pairs(shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, const shrimp_pair_params *pp,
+                                    int n_pairs, const uint32_t *reads, int stride, const int32_t *read_len,
+                                    const int8_t *initbp, shrimp_hit *hits_out, int64_t hits_cap, int64_t *n_hits,
+                                    shrimp_pair *pairs_out, int64_t pairs_cap, int64_t *n_pairs_out,
+                                    int32_t *n_pairs_per_pair, int32_t *n_unpaired_per_read, uint8_t *edits,
+                                    int64_t edits_cap, int64_t *edits_used, shrimp_map_stats *stats) {
+  return map_pairs_impl(ctx, mp, pp, n_pairs, reads, stride, read_len, initbp, hits_out, hits_cap, n_hits, pairs_out,
+                        pairs_cap, n_pairs_out, n_pairs_per_pair, n_unpaired_per_read, edits, edits_cap, edits_used,
+                        stats, false);
+}
+
+// Measurement entry: maps again the pairs the previous shrimp_gpu_map_pairs call left in HBM (no upload of the
+// reads); the records go to library-owned scratch and only the statistics come back.  The mid-pipeline host
+// stage (readpair_pass2) is part of the path and stays inside.
+extern "C" int shrimp_gpu_map_pairs_resident(shrimp_gpu_ctx *ctx, const shrimp_map_params *mp,
+                                             const shrimp_pair_params *pp, shrimp_map_stats *stats) {
+  Pipeline *pl = ctx ? (Pipeline *)ctx->pipeline : nullptr;
+  if (!pl || pl->res_n_reads <= 0 || (pl->res_n_reads & 1) || !mp) {
+    set_error("shrimp_gpu_map_pairs_resident: no pairs resident; call shrimp_gpu_map_pairs first");
+    return SHRIMP_E_STATE;
+  }
+  const int n_pairs = pl->res_n_reads / 2;
+  static thread_local std::vector<shrimp_hit> hits;
+  static thread_local std::vector<shrimp_pair> pairs;
+  hits.resize((size_t)n_pairs * mp->num_outputs * 4);
+  pairs.resize((size_t)n_pairs * mp->num_outputs);
+  int64_t nh = 0, np = 0, eu = 0;
+  return map_pairs_impl(ctx, mp, pp, n_pairs, nullptr, 0, nullptr, nullptr, hits.data(), (int64_t)hits.size(), &nh,
+                        pairs.data(), (int64_t)pairs.size(), &np, nullptr, nullptr, nullptr, 0, &eu, stats, true);
 }

@@ -15,7 +15,7 @@
 namespace shrimp {
 
 // ---- entry points of the other translation units -----------------------------------------------
-size_t scan_smem_bytes(int cap, int max_rl, int k_cap, int bm_log2, int warps);
+size_t scan_smem_bytes(int cap, int max_rl, int k_cap, int bm_log2, int warps, bool alias_rec);
 size_t scan_big_smem_bytes(int cap, int max_rl, int k_cap, int bm_log2);
 int launch_scan_big(shrimp_gpu_ctx *ctx, ScanParams &P, int n_ctas);
 
@@ -410,18 +410,26 @@ int chunk_scan(Chunk &C) {
     K_max += std::max(0, max_rl - g->seeds.span[sn] + 1 - mkp);
   }
   const bool filt = C.M.use_region_counts != 0;
-  // warp kernel: candidate slots after the bitmap filter (or all entries when there is no region filter),
-  // bitmaps of >= 16 bits per expected entry
-  int cap = filt ? 256 : 128;
-  if (!filt)
-    while (cap < 2048 && cap < est * 3 + 64) cap <<= 1;
-  int bm_log2 = 10;
-  if (filt)
-    while (bm_log2 < 15 && (1 << bm_log2) < est * 16) bm_log2++;
-  else
+  // warp kernel: bitmaps of >= 16 bits per expected entry (up to 2^17 bits) and candidate slots for twice the
+  // expected survivors (true: entries that share a 2 kb region, ~3 region touches each; false: bitmap collisions);
+  // without a region filter every entry is a candidate
+  const double L_total = (double)g->total_len;
+  int bm_log2 = 10, cap = 128;
+  bool small_useful = true;
+  if (filt) {
+    while (bm_log2 < 17 && (1 << bm_log2) < est * 16) bm_log2++;
+    const double s_true = est * std::min(1.0, est * 2100.0 / std::max(L_total, 1.0)) * 3.0;
+    const double s_false = est * std::min(1.0, est * 1.1 / (double)(1 << bm_log2));
+    cap = 256;
+    while (cap < 2048 && cap < 2.0 * (s_true + s_false) + 64) cap <<= 1;
+    small_useful = est * 8 <= (double)(1 << bm_log2) && 2.0 * (s_true + s_false) + 64 <= 2048;
+  } else {
     bm_log2 = 5;
+    while (cap < 2048 && cap < est * 3 + 64) cap <<= 1;
+  }
+  // the anchors (16 B per candidate) reuse the bitmaps once those are at least as large
+  const bool alias_rec = filt && ((size_t)2 << bm_log2) / 8 >= (size_t)cap * 16;
   const int k_cap = std::max(32, std::min(K_max, 1024));
-  bool small_useful = !filt || est * 8 <= (double)(1 << 15);
   if (getenv("SHRIMP_SCAN_FORCE_BIG")) small_useful = false;  // test hook: every strand through the CTA kernel
   // CTA kernel: 2^19-bit bitmaps, 8192 candidates
   const int big_cap = 8192, big_bm_log2 = filt ? 19 : 5, big_k_cap = std::max(32, K_max);
@@ -463,9 +471,11 @@ int chunk_scan(Chunk &C) {
       P.cap = cap;
       P.k_cap = k_cap;
       P.bm_log2 = bm_log2;
+      P.alias_rec = alias_rec ? 1 : 0;
+      P.stream = est >= 8.0 * std::max(1, K_max) ? 1 : 0;   // average list of 8+ positions
       int warps = SCAN_WARPS_HOST;
-      while (warps > 1 && scan_smem_bytes(cap, max_rl, k_cap, bm_log2, warps) > 100 * 1024) warps >>= 1;
-      const size_t smem = scan_smem_bytes(cap, max_rl, k_cap, bm_log2, warps);
+      while (warps > 1 && scan_smem_bytes(cap, max_rl, k_cap, bm_log2, warps, alias_rec) > 100 * 1024) warps >>= 1;
+      const size_t smem = scan_smem_bytes(cap, max_rl, k_cap, bm_log2, warps, alias_rec);
       int ctas_per_sm = (int)std::max<size_t>(1, (size_t)(220 * 1024) / std::max<size_t>(smem, 1));
       ctas_per_sm = std::min(ctas_per_sm, 2048 / (SCAN_WARPS_HOST * 32));
       int n_ctas = ctx->sm_count * ctas_per_sm;

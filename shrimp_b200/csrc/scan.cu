@@ -102,9 +102,9 @@ struct KmerTables {   // shared memory, per read strand
   uint32_t *kpre;     // [K + 1] exclusive prefix sums of the (cut-off) list lengths
 };
 
-// entry t of the flattened lists -> (position, k-mer slot sn * max_n_kmers + i)
-__device__ __forceinline__ void flat_entry(const ScanParams &P, const KmerTables &T, int K, const int *kbase,
-                                           int max_n_kmers, uint32_t t, uint32_t &x, uint32_t &slot) {
+// entry t of the flattened lists -> (address of its position, k-mer slot sn * max_n_kmers + i)
+__device__ __forceinline__ const uint32_t *flat_addr(const ScanParams &P, const KmerTables &T, int K, const int *kbase,
+                                                     int max_n_kmers, uint32_t t, uint32_t &slot) {
   int lo = 0, hi = K;  // kpre[lo] <= t < kpre[hi]
   while (hi - lo > 1) {
     const int mid = (lo + hi) >> 1;
@@ -112,8 +112,51 @@ __device__ __forceinline__ void flat_entry(const ScanParams &P, const KmerTables
   }
   int sn = 0;
   while (sn + 1 < P.S.n_seeds && kbase[sn + 1] <= lo) sn++;
-  x = __ldg(P.I.pos[sn] + T.kst[lo] + (t - T.kpre[lo]));
   slot = (uint32_t)(sn * max_n_kmers + (lo - kbase[sn]));
+  return P.I.pos[sn] + T.kst[lo] + (t - T.kpre[lo]);
+}
+__device__ __forceinline__ void flat_entry(const ScanParams &P, const KmerTables &T, int K, const int *kbase,
+                                           int max_n_kmers, uint32_t t, uint32_t &x, uint32_t &slot) {
+  x = __ldg(flat_addr(P, T, K, kbase, max_n_kmers, t, slot));
+}
+
+// Walks entries [t, tend) of the flattened lists as one contiguous stream per thread: one search for the first
+// k-mer, then list after list with four loads in flight; f(position, k-mer slot) per entry.  A thread's stream
+// reads whole sectors (8 positions each), so the lists still cost one HBM/L2 sector fetch per 32 bytes.
+template <typename F>
+__device__ __forceinline__ void walk_entries(const ScanParams &P, const KmerTables &T, int K, const int *kbase,
+                                             int max_n_kmers, uint32_t t, uint32_t tend, F f) {
+  if (t >= tend) return;
+  int lo = 0, hi = K;  // kpre[lo] <= t < kpre[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (T.kpre[mid] <= t) lo = mid; else hi = mid;
+  }
+  int sn = 0;
+  while (sn + 1 < P.S.n_seeds && kbase[sn + 1] <= lo) sn++;
+  int k = lo;
+  while (t < tend) {
+    const uint32_t kp = T.kpre[k], lend = min(tend, T.kpre[k + 1]);
+    if (lend > t) {
+      const uint32_t *p = P.I.pos[sn] + T.kst[k] + (t - kp);
+      const uint32_t slot = (uint32_t)(sn * max_n_kmers + (k - kbase[sn]));
+      uint32_t n = lend - t;
+      while (n >= 4) {
+        const uint32_t x0 = __ldg(p), x1 = __ldg(p + 1), x2 = __ldg(p + 2), x3 = __ldg(p + 3);
+        f(x0, slot); f(x1, slot); f(x2, slot); f(x3, slot);
+        p += 4;
+        n -= 4;
+      }
+      while (n > 0) {
+        f(__ldg(p), slot);
+        p++;
+        n--;
+      }
+      t = lend;
+    }
+    k++;
+    while (sn + 1 < P.S.n_seeds && k >= kbase[sn + 1]) sn++;
+  }
 }
 
 __device__ __forceinline__ uint32_t region_hash(uint32_t region, int bm_log2) {
@@ -406,7 +449,7 @@ __host__ __device__ inline ScanSmem scan_layout(int cap, int max_rl, int k_cap, 
   L.kst = take((size_t)k_cap * 4);
   L.kpre = take(((size_t)k_cap + 1) * 4);
   L.cache = take((size_t)max_rl * 2);
-  L.keep = take(((size_t)cap / 32 + 1) * 4);
+  L.keep = take(((size_t)cap / 32 + 2) * 4);   // + the candidate counter of the warp kernel
   L.ent = take((size_t)cap * 8);
   L.bm1 = take(((size_t)1 << bm_log2) / 8);
   L.bm2 = take(((size_t)1 << bm_log2) / 8);
@@ -434,7 +477,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) scan_kernel(const ScanParams 
   const int wib = threadIdx.x >> 5;
   if (wib >= warps_per_cta) return;
   const int cap = P.cap;
-  const ScanSmem L = scan_layout(cap, P.max_rl, P.k_cap, P.bm_log2, false);
+  const ScanSmem L = scan_layout(cap, P.max_rl, P.k_cap, P.bm_log2, P.alias_rec != 0);
   unsigned char *base = smem_raw + L.total * wib;
   uint32_t *r2 = (uint32_t *)(base + L.r2);
   KmerTables T;
@@ -445,6 +488,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) scan_kernel(const ScanParams 
   AnchorRec *rec = (AnchorRec *)(base + L.rec);
   int16_t *cache = (int16_t *)(base + L.cache);
   uint32_t *keep = (uint32_t *)(base + L.keep);
+  uint32_t *s_cnt = keep + (cap / 32 + 1);   // candidate counter of pass B
   const int bm_words = 1 << (P.bm_log2 - 5);
 
   const uint32_t gwarp = blockIdx.x * warps_per_cta + wib;
@@ -520,33 +564,59 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) scan_kernel(const ScanParams 
 
     int ns = (int)total;
     if (M.use_region_counts) {
-      // ---- 2. pass A: mark regions ------------------------------------------------------------------
-      for (uint32_t t = lane; t < total; t += 32) {
-        uint32_t x, slot;
-        flat_entry(P, T, K, kbase, max_n_kmers, t, x, slot);
-        const uint32_t region = x >> M.region_bits;
-        region_mark(bm1, bm2, region, P.bm_log2);
-        if ((x & rmask) < (uint32_t)M.region_overlap && region > 0) region_mark(bm1, bm2, region - 1, P.bm_log2);
-      }
-      __syncwarp();
-      // ---- 3. pass B: keep the entries of regions marked twice ----------------------------------------
-      ns = 0;
-      for (uint32_t t0 = 0; t0 < total; t0 += 32) {
-        const uint32_t t = t0 + lane;
-        bool kp = false;
-        uint32_t x = 0, slot = 0;
-        if (t < total) {
+      if (P.stream) {  // long lists: one contiguous stream per lane
+        // ---- 2. pass A: mark regions ------------------------------------------------------------------
+        const uint32_t chunk = (total + 31u) / 32u;
+        const uint32_t tb = min(total, lane * chunk), te = min(total, tb + chunk);
+        walk_entries(P, T, K, kbase, max_n_kmers, tb, te, [&](uint32_t x, uint32_t) {
+          const uint32_t region = x >> M.region_bits;
+          region_mark(bm1, bm2, region, P.bm_log2);
+          if ((x & rmask) < (uint32_t)M.region_overlap && region > 0) region_mark(bm1, bm2, region - 1, P.bm_log2);
+        });
+        if (lane == 0) *s_cnt = 0u;
+        __syncwarp();
+        // ---- 3. pass B: keep the entries of regions marked twice ----------------------------------------
+        walk_entries(P, T, K, kbase, max_n_kmers, tb, te, [&](uint32_t x, uint32_t slot) {
+          const uint32_t region = x >> M.region_bits;
+          const bool kp = region_twice(bm2, region, P.bm_log2) ||
+                          ((x & rmask) < (uint32_t)M.region_overlap && region > 0 &&
+                           region_twice(bm2, region - 1, P.bm_log2));
+          if (kp) {
+            const uint32_t at = atomicAdd(s_cnt, 1u);
+            if (at < (uint32_t)cap) ent[at] = ((unsigned long long)x << 32) | slot;
+          }
+        });
+        __syncwarp();
+        ns = (int)*s_cnt;
+      } else {         // short lists: entries interleaved over the lanes, one search per entry
+        // ---- 2. pass A: mark regions ----------------------------------------------------------------
+        for (uint32_t t = lane; t < total; t += 32) {
+          uint32_t x, slot;
           flat_entry(P, T, K, kbase, max_n_kmers, t, x, slot);
           const uint32_t region = x >> M.region_bits;
-          kp = region_twice(bm2, region, P.bm_log2) ||
-               ((x & rmask) < (uint32_t)M.region_overlap && region > 0 && region_twice(bm2, region - 1, P.bm_log2));
+          region_mark(bm1, bm2, region, P.bm_log2);
+          if ((x & rmask) < (uint32_t)M.region_overlap && region > 0) region_mark(bm1, bm2, region - 1, P.bm_log2);
         }
-        const uint32_t b = __ballot_sync(0xffffffffu, kp);
-        if (kp) {
-          const int at = ns + __popc(b & ((1u << lane) - 1u));
-          if (at < cap) ent[at] = ((unsigned long long)x << 32) | slot;
+        __syncwarp();
+        // ---- 3. pass B: keep the entries of regions marked twice --------------------------------------
+        ns = 0;
+        for (uint32_t t0 = 0; t0 < total; t0 += 32) {
+          const uint32_t t = t0 + lane;
+          bool kp = false;
+          uint32_t x = 0, slot = 0;
+          if (t < total) {
+            flat_entry(P, T, K, kbase, max_n_kmers, t, x, slot);
+            const uint32_t region = x >> M.region_bits;
+            kp = region_twice(bm2, region, P.bm_log2) ||
+                 ((x & rmask) < (uint32_t)M.region_overlap && region > 0 && region_twice(bm2, region - 1, P.bm_log2));
+          }
+          const uint32_t b = __ballot_sync(0xffffffffu, kp);
+          if (kp) {
+            const int at = ns + __popc(b & ((1u << lane) - 1u));
+            if (at < cap) ent[at] = ((unsigned long long)x << 32) | slot;
+          }
+          ns += __popc(b);
         }
-        ns += __popc(b);
       }
     } else {
       if (ns <= cap) {
@@ -681,17 +751,15 @@ __global__ void __launch_bounds__(SCAN_BIG_THREADS) scan_big_kernel(const ScanPa
     const uint32_t total = s_total;
     if (total == 0) continue;
     if (M.use_region_counts) {
-      for (uint32_t t = tid; t < total; t += nthr) {
-        uint32_t x, slot;
-        flat_entry(P, T, K, kbase, max_n_kmers, t, x, slot);
+      const uint32_t chunk = (total + (uint32_t)nthr - 1u) / (uint32_t)nthr;
+      const uint32_t tb = min(total, (uint32_t)tid * chunk), te = min(total, tb + chunk);
+      walk_entries(P, T, K, kbase, max_n_kmers, tb, te, [&](uint32_t x, uint32_t) {
         const uint32_t region = x >> M.region_bits;
         region_mark(bm1, bm2, region, P.bm_log2);
         if ((x & rmask) < (uint32_t)M.region_overlap && region > 0) region_mark(bm1, bm2, region - 1, P.bm_log2);
-      }
+      });
       __syncthreads();
-      for (uint32_t t = tid; t < total; t += nthr) {
-        uint32_t x, slot;
-        flat_entry(P, T, K, kbase, max_n_kmers, t, x, slot);
+      walk_entries(P, T, K, kbase, max_n_kmers, tb, te, [&](uint32_t x, uint32_t slot) {
         const uint32_t region = x >> M.region_bits;
         const bool kp = region_twice(bm2, region, P.bm_log2) ||
                         ((x & rmask) < (uint32_t)M.region_overlap && region > 0 &&
@@ -700,7 +768,7 @@ __global__ void __launch_bounds__(SCAN_BIG_THREADS) scan_big_kernel(const ScanPa
           const uint32_t at = atomicAdd(&s_ns, 1u);
           if (at < (uint32_t)cap) ent[at] = ((unsigned long long)x << 32) | slot;
         }
-      }
+      });
     } else {
       if (total <= (uint32_t)cap)
         for (uint32_t t = tid; t < total; t += nthr) {
@@ -749,15 +817,15 @@ __global__ void __launch_bounds__(SCAN_BIG_THREADS) scan_big_kernel(const ScanPa
   }
 }
 
-size_t scan_smem_bytes(int cap, int max_rl, int k_cap, int bm_log2, int warps) {
-  return scan_layout(cap, max_rl, k_cap, bm_log2, false).total * warps;
+size_t scan_smem_bytes(int cap, int max_rl, int k_cap, int bm_log2, int warps, bool alias_rec) {
+  return scan_layout(cap, max_rl, k_cap, bm_log2, alias_rec).total * warps;
 }
 size_t scan_big_smem_bytes(int cap, int max_rl, int k_cap, int bm_log2) {
   return scan_layout(cap, max_rl, k_cap, bm_log2, true).total;
 }
 
 int launch_scan(shrimp_gpu_ctx *ctx, ScanParams &P, int warps_per_cta, int n_ctas) {
-  const size_t smem = scan_smem_bytes(P.cap, P.max_rl, P.k_cap, P.bm_log2, warps_per_cta);
+  const size_t smem = scan_smem_bytes(P.cap, P.max_rl, P.k_cap, P.bm_log2, warps_per_cta, P.alias_rec != 0);
   SH_CUDA(cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   scan_kernel<<<n_ctas, SCAN_WARPS * 32, smem, ctx->stream>>>(P, warps_per_cta);
   SH_CUDA(cudaGetLastError());

@@ -37,6 +37,8 @@ struct ScanParams {
   int max_rl;
   int k_cap;               // k-mers per read strand the shared-memory tables hold
   int bm_log2;             // log2 of the bits of each region bitmap
+  int alias_rec;           // warp kernel: the anchors reuse the bitmaps (dead after pass B)
+  int stream;              // warp kernel: lists long enough for one contiguous stream per lane
 };
 
 struct AnchorRec {
