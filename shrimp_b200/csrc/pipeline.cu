@@ -421,18 +421,23 @@ int chunk_scan(Chunk &C) {
     const double s_true = est * std::min(1.0, est * 2100.0 / std::max(L_total, 1.0)) * 3.0;
     const double s_false = est * std::min(1.0, est * 1.1 / (double)(1 << bm_log2));
     cap = 256;
-    while (cap < 2048 && cap < 2.0 * (s_true + s_false) + 64) cap <<= 1;
-    small_useful = est * 8 <= (double)(1 << bm_log2) && 2.0 * (s_true + s_false) + 64 <= 2048;
+    // + the read's own locus: every k-mer may hit it
+    const double want = 2.0 * (s_true + s_false) + 1.5 * K_max + 32;
+    cap = 128;
+    while (cap < 2048 && cap < want) cap <<= 1;
+    small_useful = est * 8 <= (double)(1 << bm_log2) && want <= 2048;
   } else {
     bm_log2 = 5;
     while (cap < 2048 && cap < est * 3 + 64) cap <<= 1;
   }
   // the anchors (16 B per candidate) reuse the bitmaps once those are at least as large
   const bool alias_rec = filt && ((size_t)2 << bm_log2) / 8 >= (size_t)cap * 16;
-  const int k_cap = std::max(32, std::min(K_max, 1024));
+  // the k-mer tables double as first_of[] of the tie replay, indexed by slot = sn * max_n_kmers + i
+  const int K_slots = g->seeds.n_seeds * std::max(1, max_rl - g->seeds.min_span + 1);
+  const int k_cap = std::max(32, std::min(std::max(K_max, K_slots), 1024));
   if (getenv("SHRIMP_SCAN_FORCE_BIG")) small_useful = false;  // test hook: every strand through the CTA kernel
   // CTA kernel: 2^19-bit bitmaps, 8192 candidates
-  const int big_cap = 8192, big_bm_log2 = filt ? 19 : 5, big_k_cap = std::max(32, K_max);
+  const int big_cap = 8192, big_bm_log2 = filt ? 19 : 5, big_k_cap = std::max(32, std::max(K_max, K_slots));
   if (scan_big_smem_bytes(big_cap, max_rl, big_k_cap, big_bm_log2) > 226 * 1024) {
     set_error("seed scan: reads of %d bases with these seeds need more shared memory than a CTA has", max_rl);
     return SHRIMP_E_RANGE;
@@ -473,11 +478,20 @@ int chunk_scan(Chunk &C) {
       P.bm_log2 = bm_log2;
       P.alias_rec = alias_rec ? 1 : 0;
       P.stream = est >= 8.0 * std::max(1, K_max) ? 1 : 0;   // average list of 8+ positions
-      int warps = SCAN_WARPS_HOST;
-      while (warps > 1 && scan_smem_bytes(cap, max_rl, k_cap, bm_log2, warps, alias_rec) > 100 * 1024) warps >>= 1;
+      // CTA size that keeps the most warps resident (227 KB of shared memory, 32 CTAs and 64 warps per SM)
+      int warps = 1, ctas_per_sm = 1, best = 0;
+      for (int w = SCAN_WARPS_HOST; w >= 1; w >>= 1) {
+        const size_t sm_w = scan_smem_bytes(cap, max_rl, k_cap, bm_log2, w, alias_rec) + 1024;
+        if (sm_w > 220 * 1024) continue;
+        const int c = (int)std::min<size_t>(std::min<size_t>((size_t)(226 * 1024) / sm_w, 32), (size_t)(64 / w));
+        if (c * w > best) {
+          best = c * w;
+          warps = w;
+          ctas_per_sm = c;
+        }
+      }
       const size_t smem = scan_smem_bytes(cap, max_rl, k_cap, bm_log2, warps, alias_rec);
-      int ctas_per_sm = (int)std::max<size_t>(1, (size_t)(220 * 1024) / std::max<size_t>(smem, 1));
-      ctas_per_sm = std::min(ctas_per_sm, 2048 / (SCAN_WARPS_HOST * 32));
+      (void)smem;
       int n_ctas = ctx->sm_count * ctas_per_sm;
       n_ctas = std::min<long long>(n_ctas, ((long long)n_reads * 2 + warps - 1) / warps);
       P.scratch_ints = 2 * k_max + 2 * cap;

@@ -174,8 +174,8 @@ __device__ __forceinline__ bool region_twice(const uint32_t *bm2, uint32_t regio
 
 // ---- steps 4-7 on the sorted candidates ent[0, total): one warp ---------------------------------------
 __device__ void scan_tail(const ScanParams &P, uint32_t rs, int r, int rl, int max_n_kmers, int total, int gathered,
-                          unsigned long long *ent, AnchorRec *rec, int16_t *cache, uint32_t *keep, int32_t *scr,
-                          int cap, int lane) {
+                          unsigned long long *ent, AnchorRec *rec, int16_t *cache, uint32_t *keep, int32_t *first_of,
+                          unsigned long long *heap64, uint16_t *order16, int lane) {
   const SeedTable &S = P.S;
   const MapParamsDev &M = P.M;
   const int mkp = M.colour_space ? 1 : 0;
@@ -230,20 +230,21 @@ __device__ void scan_tail(const ScanParams &P, uint32_t rs, int r, int rl, int m
       tie = true;
   }
   tie = __any_sync(0xffffffffu, tie);
-  int32_t *order = nullptr;
+  const uint16_t *order = nullptr;
   if (tie) {
+    // everything the emulation touches is in shared memory: first_of[] reuses the k-mer table (dead by now),
+    // the heap holds (position << 32 | survivor index), the per-slot chains live in the spare upper half of
+    // each entry's low word, the pop order goes to order16[]
     const int K = S.n_seeds * max_n_kmers;
-    int32_t *first_of = scr;               // [k_max]
-    int32_t *heap = scr + P.k_max;         // [k_max]
-    int32_t *next_same = heap + P.k_max;   // [cap]
-    order = next_same + cap;               // [cap]
     for (int k = lane; k < K; k += 32) first_of[k] = -1;
     __syncwarp();
     if (lane == 0) {
       atomicAdd(&P.stats[0], 1u);
       for (int t = m_surv - 1; t >= 0; t--) {
-        const int off = (int)(uint32_t)ent[t];
-        next_same[t] = first_of[off];
+        const unsigned long long e = ent[t];
+        const int off = (int)((uint32_t)e & 0xffffu);
+        const uint32_t nx = first_of[off] < 0 ? 0xffffu : (uint32_t)first_of[off];
+        ent[t] = (e & 0xffffffff0000ffffull) | ((unsigned long long)nx << 16);
         first_of[off] = t;
       }
       // heap_uu on key = position; elements are survivor indices.  Load order: sn-major, i.e.
@@ -252,49 +253,58 @@ __device__ void scan_tail(const ScanParams &P, uint32_t rs, int r, int rl, int m
       for (int off = 0; off < K; off++) {
         const int t = first_of[off];
         if (t < 0) continue;
-        heap[load++] = t;
+        heap64[load++] = (ent[t] & 0xffffffff00000000ull) | (unsigned)t;
         int node = load, parent = node / 2;  // percolate_up, heap.h:43-60
-        while (node > 1 && (ent[heap[node - 1]] >> 32) < (ent[heap[parent - 1]] >> 32)) {
-          int tmp = heap[parent - 1];
-          heap[parent - 1] = heap[node - 1];
-          heap[node - 1] = tmp;
+        while (node > 1 && (heap64[node - 1] >> 32) < (heap64[parent - 1] >> 32)) {
+          const unsigned long long tmp = heap64[parent - 1];
+          heap64[parent - 1] = heap64[node - 1];
+          heap64[node - 1] = tmp;
           node = parent;
           parent = node / 2;
         }
       }
       int outn = 0;
       while (load > 0) {
-        const int t = heap[0];
-        order[outn++] = t;
-        const int nx = next_same[t];
-        if (nx >= 0) {
-          heap[0] = nx;  // heap_uu_replace_min
+        const int t = (int)(uint32_t)heap64[0];
+        order16[outn++] = (uint16_t)t;
+        const uint32_t nx = ((uint32_t)ent[t] >> 16) & 0xffffu;
+        if (nx != 0xffffu) {
+          heap64[0] = (ent[nx] & 0xffffffff00000000ull) | nx;  // heap_uu_replace_min
         } else {
           load--;  // heap_uu_extract_min
-          if (load > 0) heap[0] = heap[load];
+          if (load > 0) heap64[0] = heap64[load];
         }
         if (load > 0) {  // percolate_down, heap.h:62-89
           int node = 1;
+          const unsigned long long cur = heap64[0];
           for (;;) {
-            int left = node * 2, right = left + 1, mn = node;
-            if (left <= load && (ent[heap[left - 1]] >> 32) < (ent[heap[node - 1]] >> 32)) mn = left;
-            if (right <= load && (ent[heap[right - 1]] >> 32) < (ent[heap[mn - 1]] >> 32)) mn = right;
+            const int left = node * 2, right = left + 1;
+            int mn = node;
+            unsigned long long mk = cur;
+            if (left <= load) {
+              const unsigned long long lk = heap64[left - 1];
+              if ((lk >> 32) < (mk >> 32)) { mn = left; mk = lk; }
+            }
+            if (right <= load) {
+              const unsigned long long rk = heap64[right - 1];
+              if ((rk >> 32) < (mk >> 32)) { mn = right; mk = rk; }
+            }
             if (mn == node) break;
-            int tmp = heap[mn - 1];
-            heap[mn - 1] = heap[node - 1];
-            heap[node - 1] = tmp;
+            heap64[node - 1] = mk;
+            heap64[mn - 1] = cur;
             node = mn;
           }
         }
       }
     }
     __syncwarp();
+    order = order16;
   }
 
   // ---- 6. anchors: contig lookup in parallel, colinear collapse in pop order ----------------
   for (int t = lane; t < m_surv; t += 32) {
     const unsigned long long e = ent[order ? order[t] : t];
-    const uint32_t slot = (uint32_t)e;
+    const uint32_t slot = (uint32_t)e & 0xffffu;
     const int sn = (int)(slot / (uint32_t)max_n_kmers), i = (int)(slot % (uint32_t)max_n_kmers);
     AnchorRec a;
     a.x = (uint32_t)(e >> 32);
@@ -439,9 +449,9 @@ __device__ void scan_tail(const ScanParams &P, uint32_t rs, int r, int rl, int m
 
 // shared memory of one warp of the small kernel / of the CTA of the big kernel
 struct ScanSmem {
-  size_t r2, kst, kpre, bm1, bm2, ent, rec, cache, keep, total;
+  size_t r2, kst, kpre, bm1, bm2, ent, rec, cache, keep, heap, order, total;
 };
-__host__ __device__ inline ScanSmem scan_layout(int cap, int max_rl, int k_cap, int bm_log2, bool alias_rec) {
+__host__ __device__ inline ScanSmem scan_layout(int cap, int max_rl, int k_cap, int bm_log2, bool /*alias_rec*/) {
   ScanSmem L;
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t at = o; o += (bytes + 15) & ~(size_t)15; return at; };
@@ -450,15 +460,14 @@ __host__ __device__ inline ScanSmem scan_layout(int cap, int max_rl, int k_cap, 
   L.kpre = take(((size_t)k_cap + 1) * 4);
   L.cache = take((size_t)max_rl * 2);
   L.keep = take(((size_t)cap / 32 + 2) * 4);   // + the candidate counter of the warp kernel
+  L.order = take((size_t)cap * 2);      // pop order of the tie replay
   L.ent = take((size_t)cap * 8);
+  // the anchors (16 B per candidate) are born after the bitmaps and the replay heap have died: same bytes
   L.bm1 = take(((size_t)1 << bm_log2) / 8);
   L.bm2 = take(((size_t)1 << bm_log2) / 8);
-  if (alias_rec) {  // big kernel: the anchors reuse the bitmaps, which are dead after pass B
-    L.rec = L.bm1;
-    if (o - L.bm1 < (size_t)cap * 16) o = L.bm1 + (size_t)cap * 16;
-  } else {
-    L.rec = take((size_t)cap * 16);
-  }
+  L.heap = take((size_t)k_cap * 8);
+  L.rec = L.bm1;
+  if (o - L.bm1 < (size_t)cap * 16) o = L.bm1 + (size_t)cap * 16;
   L.total = (o + 15) & ~(size_t)15;
   return L;
 }
@@ -493,7 +502,6 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) scan_kernel(const ScanParams 
 
   const uint32_t gwarp = blockIdx.x * warps_per_cta + wib;
   const uint32_t n_warps = gridDim.x * warps_per_cta;
-  int32_t *scr = P.scratch + (size_t)gwarp * P.scratch_ints;
   const uint32_t n_items = 2u * (uint32_t)P.n_reads;
   const SeedTable &S = P.S;
   const MapParamsDev &M = P.M;
@@ -533,7 +541,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) scan_kernel(const ScanParams 
       K += n_kmers_of(S, sn, rl, mkp);
     }
     kbase[S.n_seeds] = K;
-    if (K > P.k_cap) {  // longer than the shared-memory tables of this launch: CTA kernel
+    if (K > P.k_cap || S.n_seeds * max_n_kmers > P.k_cap) {  // longer than this launch's shared-memory tables: CTA kernel
       if (lane == 0) P.overflow[atomicAdd(P.n_overflow, 1u)] = rs;
       continue;
     }
@@ -655,7 +663,8 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) scan_kernel(const ScanParams 
         __syncwarp();
       }
     }
-    scan_tail(P, rs, r, rl, max_n_kmers, ns, (int)total, ent, rec, cache, keep, scr, cap, lane);
+    scan_tail(P, rs, r, rl, max_n_kmers, ns, (int)total, ent, rec, cache, keep, (int32_t *)T.kst,
+              (unsigned long long *)(base + L.heap), (uint16_t *)(base + L.order), lane);
     __syncwarp();
   }
 }
@@ -679,7 +688,6 @@ __global__ void __launch_bounds__(SCAN_BIG_THREADS) scan_big_kernel(const ScanPa
   int16_t *cache = (int16_t *)(smem_raw + L.cache);
   uint32_t *keep = (uint32_t *)(smem_raw + L.keep);
   const int bm_words = 1 << (P.bm_log2 - 5);
-  int32_t *scr = P.scratch + (size_t)blockIdx.x * P.scratch_ints;
   const SeedTable &S = P.S;
   const MapParamsDev &M = P.M;
   const int mkp = M.colour_space ? 1 : 0;
@@ -716,7 +724,7 @@ __global__ void __launch_bounds__(SCAN_BIG_THREADS) scan_big_kernel(const ScanPa
       K += n_kmers_of(S, sn, rl, mkp);
     }
     kbase[S.n_seeds] = K;
-    if (K > P.k_cap) {
+    if (K > P.k_cap || S.n_seeds * max_n_kmers > P.k_cap) {
       if (tid == 0) atomicOr(P.status, 2u);
       continue;
     }
@@ -812,7 +820,8 @@ __global__ void __launch_bounds__(SCAN_BIG_THREADS) scan_big_kernel(const ScanPa
     }
     if (tid < 32) {
       if (lane == 0) P.rs_range[rs] = make_uint2(0u, 0u);
-      scan_tail(P, rs, r, rl, max_n_kmers, ns, (int)total, ent, rec, cache, keep, scr, cap, lane);
+      scan_tail(P, rs, r, rl, max_n_kmers, ns, (int)total, ent, rec, cache, keep, (int32_t *)T.kst,
+                (unsigned long long *)(smem_raw + L.heap), (uint16_t *)(smem_raw + L.order), lane);
     }
   }
 }
@@ -827,7 +836,7 @@ size_t scan_big_smem_bytes(int cap, int max_rl, int k_cap, int bm_log2) {
 int launch_scan(shrimp_gpu_ctx *ctx, ScanParams &P, int warps_per_cta, int n_ctas) {
   const size_t smem = scan_smem_bytes(P.cap, P.max_rl, P.k_cap, P.bm_log2, warps_per_cta, P.alias_rec != 0);
   SH_CUDA(cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  scan_kernel<<<n_ctas, SCAN_WARPS * 32, smem, ctx->stream>>>(P, warps_per_cta);
+  scan_kernel<<<n_ctas, warps_per_cta * 32, smem, ctx->stream>>>(P, warps_per_cta);
   SH_CUDA(cudaGetLastError());
   SH_LAUNCHED(ctx, ST_SCAN);
   return SHRIMP_OK;
