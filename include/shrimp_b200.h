@@ -129,6 +129,10 @@ int shrimp_gpu_sw_full_batch(shrimp_gpu_ctx *ctx, const uint32_t *genome, size_t
  * ---------------------------------------------------------------------------------------- */
 int shrimp_gpu_genome_load(shrimp_gpu_ctx *ctx, int num_contigs, const uint32_t *const *genome_contigs,
                            const uint32_t *genome_len, int colour_space);
+/* One GPU, several host threads: every thread owns a context (stream, chunk buffers, scoring set-up) and they
+ * share the genome arrays and the projection, as gmapper's -N threads share the globals of gmapper.h:262-275.
+ * dst borrows what is resident in src (same device); src must outlive dst. */
+int shrimp_gpu_share_genome(shrimp_gpu_ctx *dst, shrimp_gpu_ctx *src);
 /* which: 0 letters fwd, 1 letters rc, 2 colours fwd, 3 colours rc; global packed coordinates */
 int shrimp_gpu_genome_export(shrimp_gpu_ctx *ctx, int which, uint32_t *out_words, size_t n_words);
 

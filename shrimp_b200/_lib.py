@@ -111,6 +111,8 @@ def lib() -> C.CDLL:
     L.shrimp_gpu_dpx_peak.restype = i32
     L.shrimp_gpu_genome_load.argtypes = [vp, i32, vp, vp, i32]
     L.shrimp_gpu_genome_load.restype = i32
+    L.shrimp_gpu_share_genome.argtypes = [vp, vp]
+    L.shrimp_gpu_share_genome.restype = i32
     L.shrimp_gpu_genome_export.argtypes = [vp, i32, vp, C.c_size_t]
     L.shrimp_gpu_genome_export.restype = i32
     L.shrimp_gpu_index_build.argtypes = [vp, i32, vp, vp, vp, i32]

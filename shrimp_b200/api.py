@@ -249,6 +249,15 @@ class GpuContext:
         self.total_len = int(lens.astype(np.int64).sum())
         self.colour_space = bool(colour_space)
 
+    def share_genome_from(self, other: "GpuContext"):
+        """Borrow the genome + projection resident in `other` (same GPU): one context per host thread, like
+        gmapper's -N threads sharing the process-wide index."""
+        check(self._L.shrimp_gpu_share_genome(self._h, other._h), "shrimp_gpu_share_genome")
+        self._lender = other           # keep it alive
+        for k in ("genome_len", "total_len", "colour_space", "seeds"):
+            if hasattr(other, k):
+                setattr(self, k, getattr(other, k))
+
     def genome_export(self, which: int) -> np.ndarray:
         out = np.zeros((self.total_len + 7) // 8, dtype=np.uint32)
         check(self._L.shrimp_gpu_genome_export(self._h, which, _ptr(out), out.size), "shrimp_gpu_genome_export")
@@ -281,22 +290,32 @@ class GpuContext:
               "shrimp_gpu_projection_save")
 
     # ---- chunk mapping ------------------------------------------------------------------------
+    def _buf(self, key, n, dtype, reuse):
+        """output buffer; with reuse the same pages serve every call (results are views valid until the next call)"""
+        if not reuse:
+            return np.empty(n, dtype=dtype)
+        cache = self.__dict__.setdefault("_out_bufs", {})
+        b = cache.get(key)
+        if b is None or b.size < n:
+            b = cache[key] = np.empty(n, dtype=dtype)
+        return b[:n]
+
     def map_reads(self, params: MapParams, scores: Scores, reads: np.ndarray, read_len, initbp=None,
-                  want_stage: bool = False, stage_cap_per_read: int = 256) -> MapResult:
+                  want_stage: bool = False, stage_cap_per_read: int = 256, reuse_buffers: bool = False) -> MapResult:
         """handle_read (mapping.c:1773) for a chunk: returns what read_output would receive."""
         reads = np.ascontiguousarray(reads, dtype=np.uint32)
         read_len = np.ascontiguousarray(read_len, dtype=np.int32)
         n = reads.shape[0]
         pc = params.to_c(scores, getattr(self, "colour_space", False))
-        hits = np.empty(max(1, n * params.num_outputs), dtype=HitC)   # untouched pages cost nothing
-        n_per = np.zeros(max(1, n), dtype=np.int32)
+        hits = self._buf("hits", max(1, n * params.num_outputs), HitC, reuse_buffers)   # untouched pages cost nothing
+        n_per = self._buf("n_per", max(1, n), np.int32, reuse_buffers)
         max_rl = int(read_len.max()) if n else 0
         pool_cap = max(1024, n * 3 * max(1, max_rl))
         if initbp is not None:
             initbp = np.ascontiguousarray(initbp, dtype=np.int8)
         stage = np.empty(max(1, n * stage_cap_per_read), dtype=StageHitC) if want_stage else None
         while True:
-            edits = np.empty(pool_cap, dtype=np.uint8)
+            edits = self._buf("edits", pool_cap, np.uint8, reuse_buffers)
             n_hits, e_used, n_stage = C.c_int64(0), C.c_int64(0), C.c_int64(0)
             st = MapStatsC()
             rc = self._L.shrimp_gpu_map_reads(
@@ -313,7 +332,8 @@ class GpuContext:
                          stage[: n_stage.value] if want_stage else None, stats)
 
     def map_pairs(self, params: MapParams, scores: Scores, reads: np.ndarray, read_len, pair_mode: str = "opp-in",
-                  min_insert: int = 0, max_insert: int = 1000, half_paired: bool = True, initbp=None) -> "PairResult":
+                  min_insert: int = 0, max_insert: int = 1000, half_paired: bool = True, initbp=None,
+                  reuse_buffers: bool = False) -> "PairResult":
         """handle_readpair (mapping.c:2504) for a chunk of pairs: rows 2k and 2k+1 of `reads` are mates."""
         reads = np.ascontiguousarray(reads, dtype=np.uint32)
         read_len = np.ascontiguousarray(read_len, dtype=np.int32)
@@ -323,16 +343,16 @@ class GpuContext:
         npairs = n // 2
         pc = params.to_c(scores, getattr(self, "colour_space", False))
         pp = PairParamsC(PAIR_MODES[pair_mode], min_insert, max_insert, int(half_paired))
-        hits = np.empty(max(1, npairs * params.num_outputs * 4), dtype=HitC)
-        pairs = np.empty(max(1, npairs * params.num_outputs), dtype=PairC)
-        n_per_pair = np.zeros(max(1, npairs), dtype=np.int32)
-        n_unp = np.zeros(max(1, n), dtype=np.int32)
+        hits = self._buf("p_hits", max(1, npairs * params.num_outputs * 4), HitC, reuse_buffers)
+        pairs = self._buf("p_pairs", max(1, npairs * params.num_outputs), PairC, reuse_buffers)
+        n_per_pair = self._buf("p_npp", max(1, npairs), np.int32, reuse_buffers)
+        n_unp = self._buf("p_nunp", max(1, n), np.int32, reuse_buffers)
         max_rl = int(read_len.max()) if n else 0
         pool_cap = max(1024, n * 4 * max(1, max_rl))
         if initbp is not None:
             initbp = np.ascontiguousarray(initbp, dtype=np.int8)
         while True:
-            edits = np.empty(pool_cap, dtype=np.uint8)
+            edits = self._buf("p_edits", pool_cap, np.uint8, reuse_buffers)
             n_hits, n_pairs_out, e_used = C.c_int64(0), C.c_int64(0), C.c_int64(0)
             st = MapStatsC()
             rc = self._L.shrimp_gpu_map_pairs(

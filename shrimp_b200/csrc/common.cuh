@@ -131,6 +131,7 @@ struct shrimp_gpu_ctx {
   shrimp::DevBuf d_genome, d_genome_ls, d_reads, d_task, d_scores, d_boundary;
   // opaque owners of the resident genome/index and the chunk pipeline (index.cu / pipeline.cu)
   void *genome = nullptr;
+  bool genome_borrowed = false;   // shared from another context (shrimp_gpu_share_genome): not freed here
   void *pipeline = nullptr;
 };
 

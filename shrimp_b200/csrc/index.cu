@@ -101,6 +101,11 @@ __global__ void csr_offsets_kernel(const uint32_t *key, uint64_t n, uint32_t nbu
 void free_genome(shrimp_gpu_ctx *ctx) {
   DeviceGenome *g = genome_of(ctx);
   if (!g) return;
+  if (ctx->genome_borrowed) {
+    ctx->genome = nullptr;
+    ctx->genome_borrowed = false;
+    return;
+  }
   g->d_off.release();
   g->d_len.release();
   g->d_ls.release();
@@ -303,6 +308,24 @@ extern "C" int shrimp_gpu_index_build(shrimp_gpu_ctx *ctx, int n_seeds, const ui
   g->seeds = S;
   g->have_index = true;
   return rc;
+}
+
+// Several host threads can drive one GPU, each with its own context (stream, chunk buffers, scoring set-up),
+// the way gmapper's -N threads share the genome and the projection (gmapper.h:262-275 are process globals):
+// dst borrows the genome and index resident in src.  src must outlive dst and must not reload meanwhile.
+extern "C" int shrimp_gpu_share_genome(shrimp_gpu_ctx *dst, shrimp_gpu_ctx *src) {
+  if (!dst || !src || dst == src || !genome_of(src)) {
+    set_error("shrimp_gpu_share_genome: invalid argument / nothing resident in src");
+    return SHRIMP_E_ARG;
+  }
+  if (dst->device != src->device) {
+    set_error("shrimp_gpu_share_genome: contexts are on different devices");
+    return SHRIMP_E_ARG;
+  }
+  free_genome(dst);
+  dst->genome = src->genome;
+  dst->genome_borrowed = true;
+  return SHRIMP_OK;
 }
 
 // Copies the projection of seed sn back in the layout of the reference's -S files

@@ -317,10 +317,6 @@ static int map_pairs_impl(shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, cons
   }
   Chunk C;
   SH_TRY(chunk_begin(C, ctx, mp, 2 * n_pairs, reads, stride, read_len, initbp, resident, who));
-  if (C.cs) {
-    set_error("%s: colour-space pairs are not wired yet", who);
-    return SHRIMP_E_ARG;
-  }
   // per-read options of the paired set (gmapper.c:2652-2677)
   C.M.match_mode = 2;
   C.M.min_matches = 2;
@@ -408,6 +404,7 @@ static int map_pairs_impl(shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, cons
     PT.FB.rs_range = pl->d_rs_range.as<uint2>();
     PT.FB.read_len = pl->d_read_len.as<int32_t>();
     PT.FB.vtrue0 = pl->d_vtrue[0].as<int32_t>();
+    PT.FB.initbp = C.cs ? pl->d_initbp.as<int8_t>() : nullptr;
     PT.FB.n_reads = n_reads;
     PT.pairsel = d_pairsel;
     PT.n_pairsel = d_npairsel;
@@ -473,8 +470,10 @@ static int map_pairs_impl(shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, cons
     hh.resize((size_t)std::max(nt, 1));
     for (int t = 0; t < nt; t++) {
       host_score_hit(C, task_base + t, hh[t]);
-      O.pass2_vector_calls++;
-      O.pass2_vector_cells += (uint64_t)hh[t].info.w_len * (uint64_t)read_len[hh[t].info.read_idx];
+      if (!C.cs) {
+        O.pass2_vector_calls++;
+        O.pass2_vector_cells += (uint64_t)hh[t].info.w_len * (uint64_t)read_len[hh[t].info.read_idx];
+      }
       if (hh[t].res.score > 0 || hh[t].res.ops_len > 0) O.full_calls++;
     }
     int n2 = 0;

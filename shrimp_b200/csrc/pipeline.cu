@@ -834,9 +834,11 @@ static int host_pass2_select(const Chunk &C, int r, int n1, int task_base, doubl
     const double thr = full_thr < 0 ? -full_thr : h.info.score_max * (full_thr / 100.0);
     if (h.score_full >= thr) h2[n2++] = &h;
   }
-  dedup_pass(h2, &n2, cmp_gen_start);
-  dedup_pass(h2, &n2, cmp_gen_end);
-  qsort(h2, n2, sizeof(HostHit *), cmp_score);
+  if (n2 > 1) {  // with one survivor the duplicate removal and the ranking are the identity
+    dedup_pass(h2, &n2, cmp_gen_start);
+    dedup_pass(h2, &n2, cmp_gen_end);
+    qsort(h2, n2, sizeof(HostHit *), cmp_score);
+  }
   if (n2 > mp->num_outputs) n2 = mp->num_outputs;
   if (mp->strata && n2 > 0) {
     int i;
@@ -882,11 +884,13 @@ int host_pass2_all(const Chunk &C, const int32_t *n_sel, double full_thr, HostOu
     std::vector<HostHit *> h2((size_t)NT + 1);
     std::vector<KeptRec> tmp((size_t)NO + 1);
     std::vector<KeptRec> &K = kept[t];
+    K.reserve((size_t)(r1 - r0) * 2 + 64);
     counts[t].resize((size_t)(r1 - r0));
     int64_t task_base = tb[t], e = 0;
+    uint64_t my_fc = 0, my_vc = 0, my_vl = 0;  // thread-local: the shared counters would share cache lines
     for (int r = r0; r < r1; r++) {
-      const int n2 = host_pass2_select(C, r, n_sel[r], (int)task_base, full_thr, hh.data(), h2.data(), tmp.data(), fc[t],
-                                       vc[t], vl[t]);
+      const int n2 = host_pass2_select(C, r, n_sel[r], (int)task_base, full_thr, hh.data(), h2.data(), tmp.data(), my_fc,
+                                       my_vc, my_vl);
       for (int i = 0; i < n2; i++) {
         K.push_back(tmp[i]);
         e += RES[tmp[i].task_idx].ops_len;
@@ -896,6 +900,9 @@ int host_pass2_all(const Chunk &C, const int32_t *n_sel, double full_thr, HostOu
     }
     nh[t + 1] = (int64_t)K.size();
     ne[t + 1] = e;
+    fc[t] = my_fc;
+    vc[t] = my_vc;
+    vl[t] = my_vl;
   }
   for (int t = 0; t < T; t++) {
     nh[t + 1] += nh[t];
@@ -1064,7 +1071,10 @@ static int map_impl(shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, int n_read
     return SHRIMP_OK;
   }
   // ---- results back to the host + host stage: read_pass2 after the DP ----------------------------
+  const bool timing = getenv("SHRIMP_TIMING") != nullptr;
+  const double t_f0 = omp_get_wtime();
   SH_TRY(chunk_fetch_full(C, n_slots, true));
+  const double t_f1 = omp_get_wtime();
   const uint32_t *h_cnt = (const uint32_t *)((char *)pl->h_nsel.p + (size_t)n_reads * 4);
   const int32_t *NSEL = pl->h_nsel.as<int32_t>();
   HostOut O;
@@ -1074,6 +1084,9 @@ static int map_impl(shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, int n_read
   O.edits = edits;
   O.edits_cap = edits_cap;
   SH_TRY(host_pass2_all(C, NSEL, mp->sw_full_threshold, O, n_hits_per_read));
+  if (timing)
+    fprintf(stderr, "[shrimp_b200] map_reads: n_slots %d, D2H %.2f ms (%.1f MB), host pass 2 %.2f ms\n", n_slots,
+            1e3 * (t_f1 - t_f0), pl->d2h_bytes / 1e6, 1e3 * (omp_get_wtime() - t_f1));
   *n_hits = O.n_out;
   if (edits_used) *edits_used = O.e_used;
   if (stats) {

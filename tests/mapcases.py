@@ -101,6 +101,9 @@ PAIR_CASES = {
     "c3_small": dict(gen="c3_small", args=["-p", "opp-in", "-I", "0,1000"], opts={}),
     "c3_small_nomq": dict(gen="c3_small", args=["-p", "opp-in", "-I", "0,1000", "--no-mapping-qualities"],
                           opts={"compute_mapping_qualities": False}),
+    # colour-space pairs (post_sw is not on the path: --no-mapping-qualities)
+    "c2p_small": dict(gen="c2p_small", args=["-p", "opp-in", "-I", "0,1000", "--no-mapping-qualities"],
+                      opts={"compute_mapping_qualities": False}),
 }
 
 
@@ -110,19 +113,31 @@ class PairCase:
     def __init__(self, name: str):
         cfg = gen_synth.CONFIGS[PAIR_CASES[name]["gen"]]
         self.name = name
-        self.colour = False
-        self.binary = "gmapper-ls"
+        self.colour = bool(cfg.get("colour"))
+        self.binary = "gmapper-cs" if self.colour else "gmapper-ls"
         self.contigs = gen_synth.make_genome(**cfg["genome"])
         self.contig_codes = [_LS_CODE[s] for _, s in self.contigs]
         self.contig_names = [n for n, _ in self.contigs]
         self.m1, self.m2 = gen_synth.simulate_pairs(self.contigs, **cfg["reads"])
         self.n_pairs = len(self.m1)
+        if self.colour:   # SOLiD encoding of every mate: primer base T + colours
+            rng = np.random.default_rng(99)
+            self.m1 = [(n, np.frombuffer(gen_synth.letters_to_colour_read(s, rng, 0.02), dtype=np.uint8)) for n, s in self.m1]
+            self.m2 = [(n, np.frombuffer(gen_synth.letters_to_colour_read(s, rng, 0.02), dtype=np.uint8)) for n, s in self.m2]
         inter = [r for pair in zip(self.m1, self.m2) for r in pair]
-        self.read_len = np.array([r[1].size for r in inter], dtype=np.int32)
-        self.stride = int((self.read_len.max() + 7) // 8)
-        self.packed = np.stack([_pack_codes(_LS_CODE[r[1]].astype(np.uint32), self.stride) for r in inter])
-        self.initbp = None
-        self.scores = LS_DEFAULT_SCORES
+        if self.colour:
+            seqs = [r[1] for r in inter]
+            self.read_len = np.array([s.size - 1 for s in seqs], dtype=np.int32)
+            self.initbp = np.array([_LS_CODE[s[0]] for s in seqs], dtype=np.int8)
+            self.stride = int((self.read_len.max() + 7) // 8)
+            self.packed = np.stack([_pack_codes(_CS_CODE[s[1:]].astype(np.uint32), self.stride) for s in seqs])
+            self.scores = CS_DEFAULT_SCORES
+        else:
+            self.read_len = np.array([r[1].size for r in inter], dtype=np.int32)
+            self.stride = int((self.read_len.max() + 7) // 8)
+            self.packed = np.stack([_pack_codes(_LS_CODE[r[1]].astype(np.uint32), self.stride) for r in inter])
+            self.initbp = None
+            self.scores = LS_DEFAULT_SCORES
         self.seeds = S.load_default_seeds()
         self.total_len = int(sum(c.size for c in self.contig_codes))
 

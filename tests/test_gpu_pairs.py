@@ -15,11 +15,12 @@ pytestmark = pytest.mark.gpu
 
 
 def run_gpu_pairs(ctx, case, **over):
-    ctx.sw_setup(1400, 1000, case.scores, use_colours=False, anchor_width=8)
-    ctx.load_genome([_pack_codes(c.astype(np.uint32)) for c in case.contig_codes], [c.size for c in case.contig_codes])
+    ctx.sw_setup(1400, 1000, case.scores, use_colours=case.colour, anchor_width=8)
+    ctx.load_genome([_pack_codes(c.astype(np.uint32)) for c in case.contig_codes], [c.size for c in case.contig_codes],
+                    colour_space=case.colour)
     ctx.build_index(case.seeds)
     params = MapParams(list_cutoff=auto_list_cutoff(case.total_len, 12), match_mode=4, **over)
-    return ctx.map_pairs(params, case.scores, case.packed, case.read_len)
+    return ctx.map_pairs(params, case.scores, case.packed, case.read_len, initbp=case.initbp)
 
 
 def gpu_records(case, res):
@@ -27,7 +28,7 @@ def gpu_records(case, res):
 
     def fields(h, rl, gl):
         e = res.edits[int(h["edit_off"]): int(h["edit_off"]) + int(h["edit_len"])]
-        return align.sam_fields(h, e, rl, gl)
+        return align.sam_fields(h, e, rl, gl, case.colour)
 
     pair_hits = [(res.hits[int(p["hit_idx"][0])], res.hits[int(p["hit_idx"][1])]) for p in res.pairs]
     return op.pair_sam_records(pair_hits, res.pairs["pair_idx"], res.hits[res.n_paired_hits:], lens, case.read_len,

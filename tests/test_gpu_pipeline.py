@@ -98,6 +98,34 @@ def test_pipeline_alignment_strings_match_oracle(gpu_ctx):
     assert res.stats["full_cells"] == stats["full_cells"]
 
 
+def test_second_context_shares_the_index(gpu_ctx):
+    """one context per host thread, shared genome + projection (gmapper's -N threads): same results from both,
+    also when they map concurrently"""
+    import threading
+    import shrimp_b200
+    case = LsCase("c1_small")
+    want = run_gpu(gpu_ctx, case)
+    with shrimp_b200.GpuContext(0) as ctx2:
+        ctx2.sw_setup(1500, 1000, case.scores, anchor_width=case.anchor_width)
+        ctx2.share_genome_from(gpu_ctx)
+        params = MapParams(list_cutoff=case.list_cutoff)
+        out = [None, None]
+
+        def go(i, c):
+            out[i] = c.map_reads(params, case.scores, case.packed, case.read_len)
+
+        ths = [threading.Thread(target=go, args=(0, gpu_ctx)), threading.Thread(target=go, args=(1, ctx2))]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+    for res in out:
+        assert np.array_equal(res.n_hits_per_read, want.n_hits_per_read)
+        for k in ("cn", "gen_st", "genome_start", "score_full", "edit_len"):
+            assert np.array_equal(res.hits[k], want.hits[k])
+        assert np.array_equal(res.edits, want.edits)
+
+
 def test_pipeline_empty_and_tiny_reads(gpu_ctx):
     case = LsCase("c1_small")
     gpu_ctx.sw_setup(1400, 1000, case.scores)

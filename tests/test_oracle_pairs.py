@@ -17,12 +17,13 @@ def record_arrays(recs):
 
 
 def run_oracle_pairs(case, **over):
-    g = op.Genome(case.contig_codes, False)
+    g = op.Genome(case.contig_codes, case.colour)
     ix = op.Index(g, case.seeds)
-    opts = op.MapOptions(scores=case.scores, list_cutoff=op.auto_list_cutoff(g.total_len, 12), **over)
-    ph, pinfo, nper, uh, nunp, st = op.map_pairs(g, ix, opts, case.packed, case.read_len)
-    recs = op.pair_sam_records(ph, pinfo[:, 0], uh, g.lens, case.read_len, lambda h, rl, gl: op.sam_fields(h, rl, gl),
-                               case.n_pairs)
+    opts = op.MapOptions(scores=case.scores, colour_space=case.colour,
+                         list_cutoff=op.auto_list_cutoff(g.total_len, 12), **over)
+    ph, pinfo, nper, uh, nunp, st = op.map_pairs(g, ix, opts, case.packed, case.read_len, initbp=case.initbp)
+    recs = op.pair_sam_records(ph, pinfo[:, 0], uh, g.lens, case.read_len,
+                               lambda h, rl, gl: op.sam_fields(h, rl, gl, case.colour), case.n_pairs)
     return recs, (ph, pinfo, nper, uh, nunp, st)
 
 

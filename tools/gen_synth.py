@@ -201,6 +201,10 @@ CONFIGS = {
     # BASELINE.json configs[3]: short reads vs a miRNA-like database of many 22 bp contigs
     "c4_small": dict(genome=dict(total_len=22 * 300, n_contigs=300, seed=21),
                      reads=dict(n_reads=800, read_len=22, seed=22, sub=0.03)),
+    "c2p_small": dict(genome=dict(total_len=300_000, n_contigs=3, seed=23, repeat_unit=1200, repeat_copies=20,
+                                  repeat_div=0.02),
+                      reads=dict(n_pairs=500, read_len=40, seed=24, sub=0.01, ins_mean=250.0, ins_sd=25.0),
+                      paired=True, colour=True),
     "c5_small": dict(genome=dict(total_len=200_000, n_contigs=1, seed=15),
                      reads=dict(n_reads=500, read_len=75, seed=16, sub=0.04, indel_p=0.5, max_indel=5)),
 }
