@@ -75,7 +75,8 @@ class PairC(C.Structure):
 class MapStatsC(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("list_entries", "surviving_entries", "anchors", "hits", "heap_replays",
                                           "vector_tasks", "vector_calls", "vector_cells", "vector_bypassed",
-                                          "full_calls", "full_cells", "device_vector_cells", "scan_big_strands")]
+                                          "full_calls", "full_cells", "device_vector_cells", "scan_big_strands",
+                                          "scan_global_strands")]
 
 
 def lib() -> C.CDLL:

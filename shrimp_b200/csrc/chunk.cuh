@@ -82,7 +82,7 @@ __device__ __forceinline__ void make_full_task(const FullBuildParams &P, int r, 
 #define RING_CLASSES 4
 
 struct Pipeline {
-  DevBuf d_in, d_reads, d_read_len, d_initbp, d_hits, d_rs_range, d_counters, d_overflow, d_scratch;
+  DevBuf d_in, d_reads, d_read_len, d_initbp, d_hits, d_rs_range, d_counters, d_overflow, d_overflow2, d_scan_slab, d_scratch;
   DevBuf d_task[2], d_vtrue[2], d_slot, d_writer, d_sel, d_nsel;
   DevBuf d_ftasks, d_finfo, d_fresults, d_frow, d_fbp[RING_CLASSES + 1], d_fops, d_taskoff, d_scan_tmp, d_perm;
   HostBuf h_info, h_results, h_ops, h_nsel, h_hits, h_range;
@@ -122,7 +122,8 @@ struct Chunk {
   const int32_t *read_len = nullptr;   // host
   uint32_t *cnt = nullptr;             // device counters [64]
   uint32_t hits_used = 0;
-  uint32_t scan_big = 0;               // read strands that went through scan_big_kernel
+  uint32_t scan_big = 0;               // read strands that went through scan_cta_kernel
+  uint32_t scan_global = 0;            // ... of which with their candidate arrays in global slabs
   int n_ori = 1;
   size_t ops_stride = 0;
 };

@@ -16,8 +16,8 @@ namespace shrimp {
 
 // ---- entry points of the other translation units -----------------------------------------------
 size_t scan_smem_bytes(int cap, int max_rl, int k_cap, int bm_log2, int warps, bool alias_rec);
-size_t scan_big_smem_bytes(int cap, int max_rl, int k_cap, int bm_log2);
-int launch_scan_big(shrimp_gpu_ctx *ctx, ScanParams &P, int n_ctas);
+size_t scan_cta_smem_bytes(int cap, int max_rl, int k_cap, int bm_log2, int n_part, bool global_arrays);
+int launch_scan_cta(shrimp_gpu_ctx *ctx, ScanParams &P, int n_ctas, int threads);
 
 int launch_scan(shrimp_gpu_ctx *ctx, ScanParams &P, int warps_per_cta, int n_ctas);
 int launch_build_vec_tasks(shrimp_gpu_ctx *ctx, const TaskBuildParams &P);
@@ -112,7 +112,7 @@ void free_pipeline(shrimp_gpu_ctx *ctx) {
   Pipeline *p = (Pipeline *)ctx->pipeline;
   if (!p) return;
   DevBuf *bufs[] = {&p->d_in, &p->d_reads, &p->d_read_len, &p->d_initbp, &p->d_hits, &p->d_rs_range, &p->d_counters,
-                    &p->d_overflow, &p->d_scratch, &p->d_task[0], &p->d_task[1], &p->d_vtrue[0], &p->d_vtrue[1],
+                    &p->d_overflow, &p->d_overflow2, &p->d_scan_slab, &p->d_scratch, &p->d_task[0], &p->d_task[1], &p->d_vtrue[0], &p->d_vtrue[1],
                     &p->d_slot, &p->d_writer, &p->d_sel, &p->d_nsel, &p->d_ftasks, &p->d_finfo, &p->d_fresults,
                     &p->d_frow, &p->d_fbp[0], &p->d_fbp[1], &p->d_fbp[2], &p->d_fbp[3], &p->d_fbp[4], &p->d_fops,
                     &p->d_taskoff, &p->d_scan_tmp, &p->d_perm, &p->d_pair_min, &p->d_pair_max, &p->d_saved, &p->d_pairsel,
@@ -435,10 +435,36 @@ int chunk_scan(Chunk &C) {
   // the k-mer tables double as first_of[] of the tie replay, indexed by slot = sn * max_n_kmers + i
   const int K_slots = g->seeds.n_seeds * std::max(1, max_rl - g->seeds.min_span + 1);
   const int k_cap = std::max(32, std::min(std::max(K_max, K_slots), 1024));
+  // dense regime (thousands of list entries per strand): every strand through the CTA kernel
+  double cta_min_est = 1500.0;
+  if (const char *e = getenv("SHRIMP_SCAN_CTA_MIN_EST")) cta_min_est = atof(e);
+  if (est >= cta_min_est) small_useful = false;
   if (getenv("SHRIMP_SCAN_FORCE_BIG")) small_useful = false;  // test hook: every strand through the CTA kernel
-  // CTA kernel: 2^19-bit bitmaps, 8192 candidates
-  const int big_cap = 8192, big_bm_log2 = filt ? 19 : 5, big_k_cap = std::max(32, std::max(K_max, K_slots));
-  if (scan_big_smem_bytes(big_cap, max_rl, big_k_cap, big_bm_log2) > 226 * 1024) {
+  // CTA kernel: exact region bitmaps over partitions of 2^cta_bm_log2 regions, candidate slots for twice the
+  // expected survivors
+  const int big_k_cap = std::max(32, std::max(K_max, K_slots));
+  int cta_bm_log2 = 5, cta_n_part = 1, cta_cap = 1024;
+  {
+    const double n_regions = L_total / (double)(1u << C.M.region_bits) + 2.0;
+    if (filt) {
+      int bm_max = 18;
+      if (const char *e = getenv("SHRIMP_SCAN_BM_LOG2")) bm_max = std::max(5, std::min(19, atoi(e)));  // test hook
+      cta_bm_log2 = std::min(10, bm_max);
+      while (cta_bm_log2 < bm_max && (double)(1u << cta_bm_log2) < n_regions) cta_bm_log2++;
+      cta_n_part = (int)std::ceil(n_regions / (double)(1u << cta_bm_log2));
+      const double lam = est / n_regions;   // entries per region
+      const double s_true = est * std::min(1.0, 1.1 * lam);
+      const double want = 2.0 * s_true + 2.0 * K_max + 64;
+      while (cta_cap < 8192 && cta_cap < want) cta_cap <<= 1;
+    } else {
+      while (cta_cap < 8192 && cta_cap < est * 3 + 64) cta_cap <<= 1;
+    }
+    if (const char *e = getenv("SHRIMP_SCAN_CTA_CAP")) cta_cap = std::max(32, atoi(e));  // test hook: global slabs
+    while (cta_cap > 256 && scan_cta_smem_bytes(cta_cap, max_rl, big_k_cap, cta_bm_log2, cta_n_part, false) > 200 * 1024)
+      cta_cap >>= 1;
+  }
+  const int g_cap = 65535;   // global-slab pass: 16-bit candidate indices
+  if (scan_cta_smem_bytes(cta_cap, max_rl, big_k_cap, cta_bm_log2, cta_n_part, false) > 226 * 1024) {
     set_error("seed scan: reads of %d bases with these seeds need more shared memory than a CTA has", max_rl);
     return SHRIMP_E_RANGE;
   }
@@ -469,8 +495,6 @@ int chunk_scan(Chunk &C) {
     P.k_max = k_max;
     P.max_rl = max_rl;
     uint32_t h3[3] = {0, 0, 0};
-    const int big_ctas_max = ctx->sm_count;
-    SH_TRY(pl->d_scratch.ensure((size_t)big_ctas_max * (2 * k_max + 2 * big_cap) * 4));
     if (small_useful) {
       // warp-per-strand pass over all read strands
       P.cap = cap;
@@ -495,8 +519,7 @@ int chunk_scan(Chunk &C) {
       int n_ctas = ctx->sm_count * ctas_per_sm;
       n_ctas = std::min<long long>(n_ctas, ((long long)n_reads * 2 + warps - 1) / warps);
       P.scratch_ints = 2 * k_max + 2 * cap;
-      SH_TRY(pl->d_scratch.ensure(std::max((size_t)n_ctas * warps * P.scratch_ints,
-                                           (size_t)big_ctas_max * (2 * k_max + 2 * big_cap)) * 4));
+      SH_TRY(pl->d_scratch.ensure((size_t)n_ctas * warps * P.scratch_ints * 4));
       P.scratch = pl->d_scratch.as<int32_t>();
       SH_TRY(launch_scan(ctx, P, warps, n_ctas));
       SH_CUDA(cudaMemcpyAsync(h3, cnt, 12, cudaMemcpyDeviceToHost, st));
@@ -504,21 +527,56 @@ int chunk_scan(Chunk &C) {
     }
     if ((!small_useful || h3[1] > 0) && !(h3[2] & 1u)) {
       // CTA-per-strand pass: the strands the warp kernel passed on, or every strand when the lists are long
+      SH_TRY(pl->d_overflow2.ensure((size_t)n_reads * 2 * 4));
       P.work = small_useful ? pl->d_overflow.as<uint32_t>() : nullptr;
       P.n_work = small_useful ? h3[1] : 2u * (uint32_t)n_reads;
-      P.cap = big_cap;
+      P.overflow = pl->d_overflow2.as<uint32_t>();
+      P.n_overflow = cnt + 4;
+      P.work_counter = cnt + 3;
+      P.cap = cta_cap;
       P.k_cap = big_k_cap;
-      P.bm_log2 = big_bm_log2;
-      P.scratch_ints = 2 * k_max + 2 * big_cap;
-      P.scratch = pl->d_scratch.as<int32_t>();
-      int ctas = (int)std::min<uint32_t>((uint32_t)big_ctas_max, P.n_work);
+      P.bm_log2 = cta_bm_log2;
+      P.n_part = cta_n_part;
+      P.g_ent = nullptr;
+      const size_t smem = scan_cta_smem_bytes(cta_cap, max_rl, big_k_cap, cta_bm_log2, cta_n_part, false) + 1024;
+      const int per_sm = (int)std::max<size_t>(1, std::min<size_t>((size_t)(227 * 1024) / smem, 8));
+      int threads = std::max(128, std::min(512, (1024 / per_sm) & ~31));
+      if (const char *e = getenv("SHRIMP_SCAN_CTA_THREADS")) threads = std::max(32, std::min(512, atoi(e) & ~31));
+      int ctas = (int)std::min<uint32_t>((uint32_t)(ctx->sm_count * per_sm), P.n_work);
       C.scan_big = P.n_work;
-      SH_TRY(launch_scan_big(ctx, P, ctas));
-      SH_CUDA(cudaMemcpyAsync(h3, cnt, 12, cudaMemcpyDeviceToHost, st));
+      SH_TRY(launch_scan_cta(ctx, P, ctas, threads));
+      uint32_t h5[5] = {0, 0, 0, 0, 0};
+      SH_CUDA(cudaMemcpyAsync(h5, cnt, 20, cudaMemcpyDeviceToHost, st));
       SH_CUDA(cudaStreamSynchronize(st));
+      h3[0] = h5[0];
+      h3[2] = h5[2];
+      if (h5[4] > 0 && !(h3[2] & 1u)) {
+        // strands with more candidates than the shared-memory slab: candidate arrays in global slabs
+        const int gctas = (int)std::min<uint32_t>((uint32_t)ctx->sm_count, h5[4]);
+        const size_t per_cta = (size_t)(g_cap + 1) * 8 + (size_t)(g_cap + 1) * sizeof(AnchorRec) + (size_t)((g_cap + 15) & ~7) * 2 +
+                               (size_t)(g_cap / 32 + 2) * 4;
+        SH_TRY(pl->d_scan_slab.ensure(per_cta * (size_t)gctas + 64));
+        unsigned char *base = pl->d_scan_slab.as<unsigned char>();
+        P.g_ent = (unsigned long long *)base;
+        base += (size_t)gctas * (g_cap + 1) * 8;
+        P.g_rec = (AnchorRec *)base;
+        base += (size_t)gctas * (g_cap + 1) * sizeof(AnchorRec);
+        P.g_keep = (uint32_t *)base;
+        base += (size_t)gctas * (g_cap / 32 + 2) * 4;
+        P.g_order = (uint16_t *)base;
+        P.g_cap = g_cap;
+        P.work = pl->d_overflow2.as<uint32_t>();
+        P.n_work = h5[4];
+        P.overflow = nullptr;
+        SH_CUDA(cudaMemsetAsync(cnt + 3, 0, 4, st));
+        SH_TRY(launch_scan_cta(ctx, P, gctas, 512));
+        SH_CUDA(cudaMemcpyAsync(h3, cnt, 12, cudaMemcpyDeviceToHost, st));
+        SH_CUDA(cudaStreamSynchronize(st));
+        C.scan_global = h5[4];
+      }
     }
     if (h3[2] & 2u) {
-      set_error("seed scan: a read strand kept more than %d index positions after the region filter", big_cap);
+      set_error("seed scan: a read strand kept more than %d index positions after the region filter", g_cap);
       return SHRIMP_E_RANGE;
     }
     if (h3[2] & 1u) {  // hit buffer too small: grow and redo the scan
@@ -752,6 +810,7 @@ void chunk_stats(const Chunk &C, const uint32_t *hc, shrimp_map_stats *stats) {
   stats->vector_cells = *(const unsigned long long *)(hc + 8 + 6);
   stats->full_cells = *(const unsigned long long *)(hc + 16);
   stats->scan_big_strands = C.scan_big;
+  stats->scan_global_strands = C.scan_global;
 }
 
 // hit_run_full_sw's scores + hit_run_post_sw (mapping.c:1609-1625, letter space) for task idx

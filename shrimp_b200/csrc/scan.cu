@@ -172,6 +172,107 @@ __device__ __forceinline__ bool region_twice(const uint32_t *bm2, uint32_t regio
   return (bm2[h >> 5] >> (h & 31)) & 1u;
 }
 
+
+// ---- hit list helpers (read_get_hit_list_per_strand, mapping.c:1025-1229) ------------------------------
+// Chain search of anchor i (:1058-1158): best predecessor and window-generation score; true = the window passes.
+__device__ __forceinline__ bool hit_chain(const ScanParams &P, const AnchorRec *rec, int i, int rl, int window_len,
+                                          int &max_idx, int &max_score) {
+  const MapParamsDev &M = P.M;
+  const AnchorRec ai = rec[i];
+  const long long coff = (long long)P.G.contig_off[ai.cn];
+  const long long glen = (long long)P.G.contig_len[ai.cn];
+  int w_len = window_len;
+  if ((long long)w_len > glen) w_len = (int)glen;
+  long long gend = ((long long)ai.x - coff) + rl - 1 - ai.y, gstart;
+  if (gend > glen - 1) gend = glen - 1;
+  gstart = gend >= window_len ? gend - window_len : 0;
+  max_idx = i;
+  max_score = ai.len * M.match;
+  if (!M.gapless) {
+    if (M.match_mode == 2 && ai.weight == 1) max_score = -1;
+    for (int j = i - 1; j >= 0; j--) {
+      const AnchorRec aj = rec[j];
+      if ((long long)aj.x < coff + gstart) break;
+      if (aj.y >= ai.y) continue;
+      int short_len, long_len;
+      if ((long long)ai.x - coff - ai.y > (long long)aj.x - coff - aj.y) {
+        short_len = (int)(ai.y - aj.y) + ai.len;
+        long_len = (int)((long long)ai.x - (long long)aj.x) + ai.len;
+      } else {
+        short_len = (int)((long long)ai.x - (long long)aj.x) + ai.len;
+        long_len = (int)(ai.y - aj.y) + ai.len;
+      }
+      int tmp_score = short_len * M.match;
+      if (long_len > short_len) tmp_score += M.b_gap_open + (long_len - short_len) * M.b_gap_ext;  // :1134
+      if (tmp_score > max_score) {
+        max_idx = j;
+        max_score = tmp_score;
+      }
+    }
+  }
+  const int base_len = rl < w_len ? rl : w_len;
+  const int score_max = base_len * M.match;
+  return M.gapless || M.match_mode == 1 ||
+         max_score >= (int)abs_or_pct_d(M.wgen_thr, M.wgen_frac, (double)score_max);
+}
+
+// The window of anchor i chained to max_idx (:1161-1204)
+__device__ __forceinline__ DevHit hit_make(const ScanParams &P, const AnchorRec *rec, int i, int max_idx, int max_score,
+                                           int rl, int window_len) {
+  const MapParamsDev &M = P.M;
+  const AnchorRec ai = rec[i], am = rec[max_idx];
+  const int cn = ai.cn;
+  const long long coff = (long long)P.G.contig_off[cn];
+  const long long glen = (long long)P.G.contig_len[cn];
+  int w_len = window_len;
+  if ((long long)w_len > glen) w_len = (int)glen;
+  const int base_len = rl < w_len ? rl : w_len;
+  DevHit h;
+  const int x_len = (int)((long long)ai.x - (long long)am.x) + ai.len;
+  long long goff;
+  if ((long long)((window_len - x_len) / 2) < (long long)am.x - coff)
+    goff = ((long long)am.x - coff) - (window_len - x_len) / 2;
+  else
+    goff = 0;
+  if (goff + w_len > glen) goff = glen - w_len;
+  const long long rel = coff + goff;
+  if (max_idx < i) {
+    anchor_join2((long long)ai.x - rel, ai.y, ai.len, 1, (long long)am.x - rel, am.y, am.len, 1, h.ax, h.ay, h.alen,
+                 h.awidth);
+  } else {
+    h.ax = (int)((long long)ai.x - rel);
+    h.ay = ai.y;
+    h.alen = ai.len;
+    h.awidth = 1;
+  }
+  h.g_off = (uint32_t)goff;
+  h.cn = cn;
+  h.w_len = w_len;
+  h.wg = max_score;
+  h.matches = (M.gapless || max_idx == i) ? ai.weight : ai.weight + am.weight;
+  h.score_max = base_len * M.match;
+  h.score_vector = -1;
+  h.pct_vector = 0;
+  return h;
+}
+#define HITPACK_EMIT (1ull << 63)
+__device__ __forceinline__ unsigned long long hit_pack(bool emit, int max_idx, int max_score) {
+  return (emit ? HITPACK_EMIT : 0ull) | ((unsigned long long)(uint32_t)max_idx << 32) | (uint32_t)max_score;
+}
+
+// stable insertion sort by g_off inside a contig (:1210-1223); the list is almost sorted
+__device__ __forceinline__ void hit_sort_serial(DevHit *H, int nh) {
+  for (int i = 1; i < nh; i++) {
+    const DevHit cur = H[i];
+    int j = i;
+    while (j >= 1 && H[j - 1].cn == cur.cn && H[j - 1].g_off > cur.g_off) j--;
+    if (j < i) {
+      for (int k = i - 1; k >= j; k--) H[k + 1] = H[k];
+      H[j] = cur;
+    }
+  }
+}
+
 // ---- steps 4-7 on the sorted candidates ent[0, total): one warp ---------------------------------------
 __device__ void scan_tail(const ScanParams &P, uint32_t rs, int r, int rl, int max_n_kmers, int total, int gathered,
                           unsigned long long *ent, AnchorRec *rec, int16_t *cache, uint32_t *keep, int32_t *first_of,
@@ -342,106 +443,44 @@ __device__ void scan_tail(const ScanParams &P, uint32_t rs, int r, int rl, int m
   __syncwarp();
 
   // ---- 7. hit list (read_get_hit_list_per_strand) ---------------------------------------------
-  uint32_t out0 = 0;
-  if (lane == 0) {
-    out0 = atomicAdd(P.hits_used, (uint32_t)n_anch);
-    atomicAdd(&P.stats[3], (uint32_t)n_anch);
-  }
-  out0 = __shfl_sync(0xffffffffu, out0, 0);
-  if ((unsigned long long)out0 + (unsigned long long)n_anch > (unsigned long long)P.hits_cap) {
-    if (lane == 0) atomicOr(P.status, 1u);
-    return;
-  }
+  // chain search per anchor first (results parked in ent[], dead by now), so that only the windows that
+  // pass reserve hit slots
   const int window_len = (int)(unsigned short)abs_or_pct_d(M.window_len, M.window_len_frac, (double)rl);
   int nh = 0;
   for (int i0 = 0; i0 < n_anch; i0 += 32) {
     const int i = i0 + lane;
     bool emit = false;
-    DevHit h;
     if (i < n_anch) {
-      const AnchorRec ai = rec[i];
-      const int cn = ai.cn;
-      const long long coff = (long long)P.G.contig_off[cn];
-      const long long glen = (long long)P.G.contig_len[cn];
-      int w_len = window_len;
-      if ((long long)w_len > glen) w_len = (int)glen;
-      long long gend = ((long long)ai.x - coff) + rl - 1 - ai.y, gstart;
-      if (gend > glen - 1) gend = glen - 1;
-      gstart = gend >= window_len ? gend - window_len : 0;
-      int max_idx = i;
-      int max_score = ai.len * M.match;
-      if (!M.gapless) {
-        if (M.match_mode == 2 && ai.weight == 1) max_score = -1;
-        for (int j = i - 1; j >= 0; j--) {
-          const AnchorRec aj = rec[j];
-          if ((long long)aj.x < coff + gstart) break;
-          if (aj.y >= ai.y) continue;
-          int short_len, long_len;
-          if ((long long)ai.x - coff - ai.y > (long long)aj.x - coff - aj.y) {
-            short_len = (int)(ai.y - aj.y) + ai.len;
-            long_len = (int)((long long)ai.x - (long long)aj.x) + ai.len;
-          } else {
-            short_len = (int)((long long)ai.x - (long long)aj.x) + ai.len;
-            long_len = (int)(ai.y - aj.y) + ai.len;
-          }
-          int tmp_score = short_len * M.match;
-          if (long_len > short_len) tmp_score += M.b_gap_open + (long_len - short_len) * M.b_gap_ext;  // :1134
-          if (tmp_score > max_score) {
-            max_idx = j;
-            max_score = tmp_score;
-          }
-        }
-      }
-      const int base_len = rl < w_len ? rl : w_len;
-      const int score_max = base_len * M.match;
-      if (M.gapless || M.match_mode == 1 ||
-          max_score >= (int)abs_or_pct_d(M.wgen_thr, M.wgen_frac, (double)score_max)) {
-        const AnchorRec am = rec[max_idx];
-        const int x_len = (int)((long long)ai.x - (long long)am.x) + ai.len;
-        long long goff;
-        if ((long long)((window_len - x_len) / 2) < (long long)am.x - coff)
-          goff = ((long long)am.x - coff) - (window_len - x_len) / 2;
-        else
-          goff = 0;
-        if (goff + w_len > glen) goff = glen - w_len;
-        const long long rel = coff + goff;
-        if (max_idx < i) {
-          anchor_join2((long long)ai.x - rel, ai.y, ai.len, 1, (long long)am.x - rel, am.y, am.len, 1, h.ax, h.ay,
-                       h.alen, h.awidth);
-        } else {
-          h.ax = (int)((long long)ai.x - rel);
-          h.ay = ai.y;
-          h.alen = ai.len;
-          h.awidth = 1;
-        }
-        h.g_off = (uint32_t)goff;
-        h.cn = cn;
-        h.w_len = w_len;
-        h.wg = max_score;
-        h.matches = (M.gapless || max_idx == i) ? ai.weight : ai.weight + am.weight;
-        h.score_max = score_max;
-        h.score_vector = -1;
-        h.pct_vector = 0;
-        emit = true;
-      }
+      int max_idx, max_score;
+      emit = hit_chain(P, rec, i, rl, window_len, max_idx, max_score);
+      ent[i] = hit_pack(emit, max_idx, max_score);
     }
-    const uint32_t b = __ballot_sync(0xffffffffu, emit);
-    if (emit) P.hits[out0 + nh + __popc(b & ((1u << lane) - 1u))] = h;
-    nh += __popc(b);
+    nh += __popc(__ballot_sync(0xffffffffu, emit));
   }
   __syncwarp();
-  // stable insertion sort by g_off inside a contig (:1210-1223); the list is almost sorted
+  if (lane == 0) atomicAdd(&P.stats[3], (uint32_t)n_anch);
+  if (nh == 0) return;
+  uint32_t out0 = 0;
+  if (lane == 0) out0 = atomicAdd(P.hits_used, (uint32_t)nh);
+  out0 = __shfl_sync(0xffffffffu, out0, 0);
+  if ((unsigned long long)out0 + (unsigned long long)nh > (unsigned long long)P.hits_cap) {
+    if (lane == 0) atomicOr(P.status, 1u);
+    return;
+  }
+  int at = 0;
+  for (int i0 = 0; i0 < n_anch; i0 += 32) {
+    const int i = i0 + lane;
+    const unsigned long long pk = i < n_anch ? ent[i] : 0ull;
+    const bool emit = (pk & HITPACK_EMIT) != 0;
+    const uint32_t b = __ballot_sync(0xffffffffu, emit);
+    if (emit)
+      P.hits[out0 + at + __popc(b & ((1u << lane) - 1u))] =
+          hit_make(P, rec, i, (int)((pk >> 32) & 0x7fffffffu), (int)(uint32_t)pk, rl, window_len);
+    at += __popc(b);
+  }
+  __syncwarp();
   if (lane == 0) {
-    DevHit *H = P.hits + out0;
-    for (int i = 1; i < nh; i++) {
-      const DevHit cur = H[i];
-      int j = i;
-      while (j >= 1 && H[j - 1].cn == cur.cn && H[j - 1].g_off > cur.g_off) j--;
-      if (j < i) {
-        for (int k = i - 1; k >= j; k--) H[k + 1] = H[k];
-        H[j] = cur;
-      }
-    }
+    hit_sort_serial(P.hits + out0, nh);
     P.rs_range[rs] = make_uint2(out0, (uint32_t)nh);
   }
   __syncwarp();
@@ -669,40 +708,106 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) scan_kernel(const ScanParams 
   }
 }
 
-// CTA per read strand for the strands the warp kernel passed on (P.work): same steps with the lists streamed
-// by all threads, a CTA-wide sort, and warp 0 finishing steps 4b-7.
-#define SCAN_BIG_THREADS 256
-__global__ void __launch_bounds__(SCAN_BIG_THREADS) scan_big_kernel(const ScanParams P) {
+// ---- CTA per read strand: the dense regime (long index lists: large genomes) -----------------------------
+// Same steps as the warp kernel, organised for thousands of list entries per strand:
+//   * every thread projects k-mers; a WARP streams one index list at a time (lane-strided, coalesced 128-byte
+//     requests, four loads in flight per lane), lists handed out through a shared-memory counter;
+//   * the region bitmaps are EXACT (one bit per 2 kb region, no hashing): the genome is cut into partitions of
+//     2^bm_log2 regions, each list is cut once per strand by a binary search (lists ascend), and the partitions are
+//     filtered one after the other with the same two bitmaps.  Entries of the first / last region of a partition
+//     depend on marks across the cut and are kept unconditionally; the exact neighbour test of step 4 decides;
+//   * CTA-wide bitonic sort, neighbour test and compaction; the colinear collapse runs in warp lockstep
+//     (32 candidates per step: predecessors on the same diagonal slot by match_any, merged anchors by atomics);
+//   * the chain search of the hit list runs on all threads; only windows that pass reserve hit slots.
+// Strands with more candidates than the shared-memory slab go to a second launch whose candidate arrays live in
+// a global slab per CTA (P.g_ent != nullptr).
+struct CtaSmem {
+  size_t r2, kst, klen, cuts, cache, keep, order, ent, bm1, bm2, rec, heap, total;
+};
+__host__ __device__ inline CtaSmem cta_layout(int cap, int max_rl, int k_cap, int bm_log2, int n_part, bool global_arrays) {
+  CtaSmem L;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t at = o; o += (bytes + 15) & ~(size_t)15; return at; };
+  const size_t c = global_arrays ? 0 : (size_t)cap;
+  L.r2 = take(((size_t)max_rl / 16 + 4) * 4);
+  L.kst = take((size_t)k_cap * 4);
+  L.klen = take((size_t)k_cap * 4);
+  L.cuts = take((size_t)k_cap * (size_t)(n_part > 1 ? n_part - 1 : 0) * 4);
+  L.cache = take((size_t)max_rl * 4);
+  L.heap = take((size_t)k_cap * 8);
+  L.keep = take((c / 32 + 2) * 4);
+  L.order = take(c * 2 + 16);
+  L.ent = take(c * 8);
+  L.bm1 = take(((size_t)1 << bm_log2) / 8);
+  L.bm2 = take(((size_t)1 << bm_log2) / 8);
+  L.rec = L.bm1;   // anchors: born after the bitmaps have died
+  if (o - L.bm1 < c * 16) o = L.bm1 + c * 16;
+  L.total = (o + 15) & ~(size_t)15;
+  return L;
+}
+
+#define SCAN_CTA_MAX_THREADS 512
+__global__ void __launch_bounds__(SCAN_CTA_MAX_THREADS) scan_cta_kernel(const ScanParams P) {
   extern __shared__ unsigned char smem_raw[];
-  __shared__ uint32_t s_total, s_ns;
-  const int tid = threadIdx.x, lane = tid & 31, nthr = SCAN_BIG_THREADS;
-  const int cap = P.cap;
-  const ScanSmem L = scan_layout(cap, P.max_rl, P.k_cap, P.bm_log2, true);
+  __shared__ uint32_t s_item, s_total, s_ns, s_next, s_cnt, s_out0, s_wsum[SCAN_CTA_MAX_THREADS / 32];
+  __shared__ int s_nanch;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nthr = blockDim.x, nwarps = nthr >> 5;
+  const bool glob = P.g_ent != nullptr;
+  const int cap = glob ? P.g_cap : P.cap;
+  const int n_part = P.n_part;
+  const CtaSmem L = cta_layout(P.cap, P.max_rl, P.k_cap, P.bm_log2, n_part, glob);
   uint32_t *r2 = (uint32_t *)(smem_raw + L.r2);
-  KmerTables T;
-  T.kst = (uint32_t *)(smem_raw + L.kst);
-  T.kpre = (uint32_t *)(smem_raw + L.kpre);
+  uint32_t *kst = (uint32_t *)(smem_raw + L.kst), *klen = (uint32_t *)(smem_raw + L.klen);
+  uint32_t *cuts = (uint32_t *)(smem_raw + L.cuts);
+  int32_t *cache = (int32_t *)(smem_raw + L.cache);
+  unsigned long long *heap64 = (unsigned long long *)(smem_raw + L.heap);
   uint32_t *bm1 = (uint32_t *)(smem_raw + L.bm1), *bm2 = (uint32_t *)(smem_raw + L.bm2);
-  unsigned long long *ent = (unsigned long long *)(smem_raw + L.ent);
-  AnchorRec *rec = (AnchorRec *)(smem_raw + L.rec);
-  int16_t *cache = (int16_t *)(smem_raw + L.cache);
-  uint32_t *keep = (uint32_t *)(smem_raw + L.keep);
+  uint32_t *keep;
+  uint16_t *order16;
+  unsigned long long *ent;
+  AnchorRec *rec;
+  if (glob) {
+    const size_t b = (size_t)blockIdx.x;
+    ent = P.g_ent + b * (size_t)(cap + 1);
+    rec = P.g_rec + b * (size_t)(cap + 1);
+    order16 = P.g_order + b * (size_t)((cap + 15) & ~7);   // 16-byte aligned slabs (kpfx is 32-bit)
+    keep = P.g_keep + b * (size_t)(cap / 32 + 2);
+  } else {
+    ent = (unsigned long long *)(smem_raw + L.ent);
+    rec = (AnchorRec *)(smem_raw + L.rec);
+    order16 = (uint16_t *)(smem_raw + L.order);
+    keep = (uint32_t *)(smem_raw + L.keep);
+  }
+  uint32_t *kpfx = (uint32_t *)order16;   // compaction offsets; the pop order is written later
   const int bm_words = 1 << (P.bm_log2 - 5);
   const SeedTable &S = P.S;
   const MapParamsDev &M = P.M;
   const int mkp = M.colour_space ? 1 : 0;
   const uint32_t rmask = (1u << M.region_bits) - 1u;
+  const bool filt = M.use_region_counts != 0;
+  const uint32_t lt = (1u << lane) - 1u;
 
-  for (uint32_t item = blockIdx.x; item < P.n_work; item += gridDim.x) {
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) {
+      s_item = atomicAdd(P.work_counter, 1u);
+      s_total = 0;
+      s_ns = 0;
+      s_cnt = 0;
+    }
+    __syncthreads();
+    const uint32_t item = s_item;
+    if (item >= P.n_work) break;
     const uint32_t rs = P.work ? P.work[item] : item;
     const int r = (int)(rs >> 1);
     const int rl = P.read_len[r];
     const uint32_t *seq = P.reads + (size_t)rs * P.stride;
     int max_n_kmers = M.colour_space ? rl - S.min_span : rl - S.min_span + 1;
     if (max_n_kmers < 0) max_n_kmers = 0;
-    __syncthreads();
     if (!P.work && tid == 0) P.rs_range[rs] = make_uint2(0u, 0u);
     if (rl <= 0 || max_n_kmers == 0) continue;
+
+    // ---- 1. recode, project, bucket bounds ----------------------------------------------------------------
     const int nw2 = (rl + 15) / 16;
     for (int w = tid; w < nw2 + 3; w += nthr) {
       uint32_t v = 0;
@@ -712,11 +817,6 @@ __global__ void __launch_bounds__(SCAN_BIG_THREADS) scan_big_kernel(const ScanPa
       }
       r2[w] = v;
     }
-    for (int w = tid; w < bm_words; w += nthr) {
-      bm1[w] = 0u;
-      bm2[w] = 0u;
-    }
-    __syncthreads();
     int kbase[SHRIMP_MAX_SEEDS + 1];
     int K = 0;
     for (int sn = 0; sn < S.n_seeds; sn++) {
@@ -728,77 +828,160 @@ __global__ void __launch_bounds__(SCAN_BIG_THREADS) scan_big_kernel(const ScanPa
       if (tid == 0) atomicOr(P.status, 2u);
       continue;
     }
-    if (tid < 32) {  // warp 0 projects (a few hundred k-mers)
-      uint32_t total = 0;
-      for (int sn = 0; sn < S.n_seeds; sn++) {
-        const int nk = kbase[sn + 1] - kbase[sn];
-        for (int i0 = 0; i0 < nk; i0 += 32) {
-          const int i = i0 + lane;
-          uint32_t start = 0, len = 0;
-          if (i < nk) {
-            const uint32_t m = S.n_runs[sn] ? mapidx_fast(S, sn, r2, mkp + i) : kmer_to_mapidx(S, sn, seq, (uint64_t)(mkp + i));
-            start = __ldg(P.I.offs[sn] + m);
-            len = __ldg(P.I.offs[sn] + m + 1) - start;
-            if (len > M.list_cutoff) len = 0;
-          }
-          const uint32_t incl = (uint32_t)warp_incl_scan((int)len, lane);
-          if (i < nk) {
-            T.kst[kbase[sn] + i] = start;
-            T.kpre[kbase[sn] + i] = total + incl - len;
-          }
-          total += __shfl_sync(0xffffffffu, incl, 31);
-        }
+    __syncthreads();
+    {
+      uint32_t mytot = 0;
+      for (int kk = tid; kk < K; kk += nthr) {
+        int sn = 0;
+        while (kk >= kbase[sn + 1]) sn++;
+        const int i = kk - kbase[sn];
+        const uint32_t m = S.n_runs[sn] ? mapidx_fast(S, sn, r2, mkp + i) : kmer_to_mapidx(S, sn, seq, (uint64_t)(mkp + i));
+        const uint32_t start = __ldg(P.I.offs[sn] + m);
+        uint32_t len = __ldg(P.I.offs[sn] + m + 1) - start;
+        if (len > M.list_cutoff) len = 0;  // mapping.c:497,:889
+        kst[kk] = start;
+        klen[kk] = len;
+        mytot += len;
       }
-      if (lane == 0) {
-        T.kpre[K] = total;
-        s_total = total;
-        s_ns = 0;
-      }
+      mytot = (uint32_t)warp_sum((int)mytot);
+      if (lane == 0 && mytot) atomicAdd(&s_total, mytot);
     }
     __syncthreads();
     const uint32_t total = s_total;
     if (total == 0) continue;
-    if (M.use_region_counts) {
-      const uint32_t chunk = (total + (uint32_t)nthr - 1u) / (uint32_t)nthr;
-      const uint32_t tb = min(total, (uint32_t)tid * chunk), te = min(total, tb + chunk);
-      walk_entries(P, T, K, kbase, max_n_kmers, tb, te, [&](uint32_t x, uint32_t) {
-        const uint32_t region = x >> M.region_bits;
-        region_mark(bm1, bm2, region, P.bm_log2);
-        if ((x & rmask) < (uint32_t)M.region_overlap && region > 0) region_mark(bm1, bm2, region - 1, P.bm_log2);
-      });
+    // cut every list at the partition boundaries
+    if (n_part > 1) {
+      const int nc = n_part - 1;
+      for (int q = tid; q < K * nc; q += nthr) {
+        const int kk = q / nc, c = q - kk * nc;
+        int sn = 0;
+        while (kk >= kbase[sn + 1]) sn++;
+        const uint32_t *p = P.I.pos[sn] + kst[kk];
+        const unsigned long long key = (unsigned long long)(c + 1) << (P.bm_log2 + M.region_bits);
+        uint32_t lo = 0, hi = klen[kk];   // first entry >= key
+        if (key > 0xffffffffull) lo = hi;
+        while (lo < hi) {
+          const uint32_t mid = (lo + hi) >> 1;
+          if ((unsigned long long)__ldg(p + mid) < key) lo = mid + 1; else hi = mid;
+        }
+        cuts[q] = lo;
+      }
       __syncthreads();
-      walk_entries(P, T, K, kbase, max_n_kmers, tb, te, [&](uint32_t x, uint32_t slot) {
-        const uint32_t region = x >> M.region_bits;
-        const bool kp = region_twice(bm2, region, P.bm_log2) ||
-                        ((x & rmask) < (uint32_t)M.region_overlap && region > 0 &&
-                         region_twice(bm2, region - 1, P.bm_log2));
-        if (kp) {
-          const uint32_t at = atomicAdd(&s_ns, 1u);
-          if (at < (uint32_t)cap) ent[at] = ((unsigned long long)x << 32) | slot;
-        }
-      });
-    } else {
-      if (total <= (uint32_t)cap)
-        for (uint32_t t = tid; t < total; t += nthr) {
-          uint32_t x, slot;
-          flat_entry(P, T, K, kbase, max_n_kmers, t, x, slot);
-          ent[t] = ((unsigned long long)x << 32) | slot;
-        }
-      if (tid == 0) s_ns = total;
     }
-    __syncthreads();
+
+    // ---- 2./3. per partition: pass A marks the regions, pass B keeps the entries of regions marked twice ----
+    for (int part = 0; part < n_part; part++) {
+      const uint32_t R0 = (uint32_t)part << P.bm_log2;
+      const uint32_t Rlast = R0 + ((1u << P.bm_log2) - 1u);
+      if (filt) {
+        for (int w = tid; w < bm_words; w += nthr) {
+          bm1[w] = 0u;
+          bm2[w] = 0u;
+        }
+        if (tid == 0) s_next = 0;
+        __syncthreads();
+        for (;;) {
+          uint32_t kk = 0;
+          if (lane == 0) kk = atomicAdd(&s_next, 1u);
+          kk = __shfl_sync(0xffffffffu, kk, 0);
+          if (kk >= (uint32_t)K) break;
+          uint32_t a = 0, b = klen[kk];
+          if (n_part > 1) {
+            if (part > 0) a = cuts[kk * (n_part - 1) + part - 1];
+            if (part < n_part - 1) b = cuts[kk * (n_part - 1) + part];
+          }
+          if (a >= b) continue;
+          int sn = 0;
+          while ((int)kk >= kbase[sn + 1]) sn++;
+          const uint32_t *p = P.I.pos[sn] + kst[kk];
+          for (uint32_t base = a; base < b; base += 128) {
+            uint32_t x[4];
+            bool ok[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+              const uint32_t i = base + u * 32 + lane;
+              ok[u] = i < b;
+              x[u] = ok[u] ? __ldg(p + i) : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+              if (ok[u]) {
+                const uint32_t idx = (x[u] >> M.region_bits) - R0;
+                const uint32_t bit = 1u << (idx & 31);
+                const uint32_t old = atomicOr(&bm1[idx >> 5], bit);
+                if (old & bit) atomicOr(&bm2[idx >> 5], bit);
+                if ((x[u] & rmask) < (uint32_t)M.region_overlap && idx > 0) {
+                  const uint32_t bit2 = 1u << ((idx - 1) & 31);
+                  const uint32_t old2 = atomicOr(&bm1[(idx - 1) >> 5], bit2);
+                  if (old2 & bit2) atomicOr(&bm2[(idx - 1) >> 5], bit2);
+                }
+              }
+          }
+        }
+        __syncthreads();
+      }
+      if (tid == 0) s_next = 0;
+      __syncthreads();
+      for (;;) {
+        uint32_t kk = 0;
+        if (lane == 0) kk = atomicAdd(&s_next, 1u);
+        kk = __shfl_sync(0xffffffffu, kk, 0);
+        if (kk >= (uint32_t)K) break;
+        uint32_t a = 0, b = klen[kk];
+        if (n_part > 1) {
+          if (part > 0) a = cuts[kk * (n_part - 1) + part - 1];
+          if (part < n_part - 1) b = cuts[kk * (n_part - 1) + part];
+        }
+        if (a >= b) continue;
+        int sn = 0;
+        while ((int)kk >= kbase[sn + 1]) sn++;
+        const uint32_t *p = P.I.pos[sn] + kst[kk];
+        const uint32_t slot = (uint32_t)(sn * max_n_kmers + ((int)kk - kbase[sn]));
+        for (uint32_t base = a; base < b; base += 128) {
+          uint32_t x[4];
+          bool ok[4];
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const uint32_t i = base + u * 32 + lane;
+            ok[u] = i < b;
+            x[u] = ok[u] ? __ldg(p + i) : 0u;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            bool kp = ok[u];
+            if (kp && filt) {
+              const uint32_t region = x[u] >> M.region_bits, idx = region - R0;
+              kp = ((bm2[idx >> 5] >> (idx & 31)) & 1u) != 0;
+              if (!kp && (x[u] & rmask) < (uint32_t)M.region_overlap && idx > 0)
+                kp = ((bm2[(idx - 1) >> 5] >> ((idx - 1) & 31)) & 1u) != 0;
+              // marks across a partition cut are not seen here: keep, the neighbour test decides
+              if (!kp && n_part > 1 && ((part > 0 && region == R0) || (part < n_part - 1 && region == Rlast))) kp = true;
+            }
+            const uint32_t bal = __ballot_sync(0xffffffffu, kp);
+            if (bal) {
+              uint32_t at = 0;
+              if (lane == 0) at = atomicAdd(&s_ns, (uint32_t)__popc(bal));
+              at = __shfl_sync(0xffffffffu, at, 0) + (uint32_t)__popc(bal & lt);
+              if (kp && at < (uint32_t)cap) ent[at] = ((unsigned long long)x[u] << 32) | slot;
+            }
+          }
+        }
+      }
+      __syncthreads();
+    }
     const int ns = (int)s_ns;
-    if (ns > cap) {  // more candidates than the largest slab
-      if (tid == 0) atomicOr(P.status, 2u);
-      continue;
-    }
-    if (ns == 0) {
+    if (ns > cap) {
       if (tid == 0) {
-        atomicAdd(&P.stats[1], total);
-        P.rs_range[rs] = make_uint2(0u, 0u);
+        if (glob || !P.overflow) atomicOr(P.status, 2u);
+        else P.overflow[atomicAdd(P.n_overflow, 1u)] = rs;
       }
       continue;
     }
+    if (ns == 0) {
+      if (tid == 0) atomicAdd(&P.stats[1], total);
+      continue;
+    }
+    // ---- 4a. CTA bitonic sort by position -------------------------------------------------------------------
     int Pn = 32;
     while (Pn < ns) Pn <<= 1;
     for (int t = ns + tid; t < Pn; t += nthr) ent[t] = ~0ull;
@@ -818,10 +1001,275 @@ __global__ void __launch_bounds__(SCAN_BIG_THREADS) scan_big_kernel(const ScanPa
         __syncthreads();
       }
     }
-    if (tid < 32) {
-      if (lane == 0) P.rs_range[rs] = make_uint2(0u, 0u);
-      scan_tail(P, rs, r, rl, max_n_kmers, ns, (int)total, ent, rec, cache, keep, (int32_t *)T.kst,
-                (unsigned long long *)(smem_raw + L.heap), (uint16_t *)(smem_raw + L.order), lane);
+    // ---- 4b. region filter (RG_HAS_2 as a neighbour test) + ordered compaction ----------------------------
+    int m_surv = ns;
+    if (filt) {
+      const int n_words = (ns + 31) >> 5;
+      for (int t0 = 0; t0 < n_words * 32; t0 += nthr) {
+        const int t = t0 + tid;
+        bool kp = false;
+        if (t < ns) {
+          const unsigned long long x = ent[t] >> 32;
+          const unsigned long long xl = t > 0 ? (ent[t - 1] >> 32) : 0ull;
+          const unsigned long long xr = t + 1 < ns ? (ent[t + 1] >> 32) : ~0ull;
+          const unsigned long long region = x >> M.region_bits;
+          const unsigned long long lo = region << M.region_bits;
+          const unsigned long long hi = ((region + 1) << M.region_bits) + (unsigned long long)M.region_overlap;
+          kp = (t > 0 && xl >= lo) || (t + 1 < ns && xr < hi);
+          if (!kp && region > 0 && ((uint32_t)x & rmask) < (uint32_t)M.region_overlap) {
+            const unsigned long long lo2 = (region - 1) << M.region_bits;
+            const unsigned long long hi2 = lo + (unsigned long long)M.region_overlap;
+            kp = (t > 0 && xl >= lo2) || (t + 1 < ns && xr < hi2);
+          }
+        }
+        const uint32_t b = __ballot_sync(0xffffffffu, kp);
+        if (lane == 0 && (t >> 5) < n_words) keep[t >> 5] = b;
+      }
+      __syncthreads();
+      if (wid == 0) {  // exclusive prefix of the popcounts
+        uint32_t run = 0;
+        for (int w0 = 0; w0 < n_words; w0 += 32) {
+          const int w = w0 + lane;
+          const int c = w < n_words ? __popc(keep[w]) : 0;
+          const int inc = warp_incl_scan(c, lane);
+          if (w < n_words) kpfx[w] = run + (uint32_t)(inc - c);
+          run += (uint32_t)__shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (lane == 0) s_cnt = run;
+      }
+      __syncthreads();
+      m_surv = (int)s_cnt;
+      for (int t0 = 0; t0 < n_words * 32; t0 += nthr) {
+        const int t = t0 + tid;
+        unsigned long long v = 0;
+        uint32_t at = 0;
+        bool kp = false;
+        if (t < ns) {
+          const uint32_t b = keep[t >> 5];
+          kp = (b >> lane) & 1u;
+          v = ent[t];
+          at = kpfx[t >> 5] + (uint32_t)__popc(b & lt);
+        }
+        __syncthreads();
+        if (kp) ent[at] = v;
+        __syncthreads();
+      }
+      if (tid == 0) s_cnt = 0;
+    }
+    if (tid == 0) {
+      atomicAdd(&P.stats[1], total);
+      atomicAdd(&P.stats[2], (uint32_t)m_surv);
+    }
+    if (m_surv == 0) continue;
+    __syncthreads();
+
+    // ---- 5. equal position on different read offsets -> replay the reference's heap (thread 0) -------------
+    bool tie = false;
+    for (int t = tid; t + 1 < m_surv; t += nthr) {
+      const unsigned long long a = ent[t], b = ent[t + 1];
+      if ((a >> 32) == (b >> 32) && ((uint32_t)a % (uint32_t)max_n_kmers) != ((uint32_t)b % (uint32_t)max_n_kmers))
+        tie = true;
+    }
+    tie = __syncthreads_or(tie) != 0;
+    const uint16_t *order = nullptr;
+    if (tie) {
+      int32_t *first_of = (int32_t *)kst;   // the k-mer tables are dead
+      const int Ks = S.n_seeds * max_n_kmers;
+      for (int k = tid; k < Ks; k += nthr) first_of[k] = -1;
+      __syncthreads();
+      if (tid == 0) {
+        atomicAdd(&P.stats[0], 1u);
+        for (int t = m_surv - 1; t >= 0; t--) {
+          const unsigned long long e = ent[t];
+          const int off = (int)((uint32_t)e & 0xffffu);
+          const uint32_t nx = first_of[off] < 0 ? 0xffffu : (uint32_t)first_of[off];
+          ent[t] = (e & 0xffffffff0000ffffull) | ((unsigned long long)nx << 16);
+          first_of[off] = t;
+        }
+        int load = 0;   // heap_uu on key = position, loaded in ascending slot order (mapping.c:913-935)
+        for (int off = 0; off < Ks; off++) {
+          const int t = first_of[off];
+          if (t < 0) continue;
+          heap64[load++] = (ent[t] & 0xffffffff00000000ull) | (unsigned)t;
+          int node = load, parent = node / 2;  // percolate_up, heap.h:43-60
+          while (node > 1 && (heap64[node - 1] >> 32) < (heap64[parent - 1] >> 32)) {
+            const unsigned long long tmp = heap64[parent - 1];
+            heap64[parent - 1] = heap64[node - 1];
+            heap64[node - 1] = tmp;
+            node = parent;
+            parent = node / 2;
+          }
+        }
+        int outn = 0;
+        while (load > 0) {
+          const int t = (int)(uint32_t)heap64[0];
+          order16[outn++] = (uint16_t)t;
+          const uint32_t nx = ((uint32_t)ent[t] >> 16) & 0xffffu;
+          if (nx != 0xffffu) {
+            heap64[0] = (ent[nx] & 0xffffffff00000000ull) | nx;  // heap_uu_replace_min
+          } else {
+            load--;  // heap_uu_extract_min
+            if (load > 0) heap64[0] = heap64[load];
+          }
+          if (load > 0) {  // percolate_down, heap.h:62-89
+            int node = 1;
+            const unsigned long long cur = heap64[0];
+            for (;;) {
+              const int left = node * 2, right = left + 1;
+              int mn = node;
+              unsigned long long mk = cur;
+              if (left <= load) {
+                const unsigned long long lk = heap64[left - 1];
+                if ((lk >> 32) < (mk >> 32)) { mn = left; mk = lk; }
+              }
+              if (right <= load) {
+                const unsigned long long rk = heap64[right - 1];
+                if ((rk >> 32) < (mk >> 32)) { mn = right; mk = rk; }
+              }
+              if (mn == node) break;
+              heap64[node - 1] = mk;
+              heap64[mn - 1] = cur;
+              node = mn;
+            }
+          }
+        }
+      }
+      __syncthreads();
+      order = order16;
+    }
+
+    // ---- 6. anchors in pop order; colinear collapse (:941-971) in warp lockstep ---------------------------
+    for (int t = tid; t < m_surv; t += nthr) {
+      const unsigned long long e = ent[order ? order[t] : t];
+      const uint32_t slot = (uint32_t)e & 0xffffu;
+      const int sn = (int)(slot / (uint32_t)max_n_kmers), i = (int)(slot % (uint32_t)max_n_kmers);
+      AnchorRec a;
+      a.x = (uint32_t)(e >> 32);
+      a.y = (int16_t)(mkp + i);
+      a.len = (int16_t)S.span[sn];
+      a.weight = 1;
+      a.cn = contig_of_dev(P.G.contig_off, P.G.num_contigs, a.x);
+      rec[t] = a;
+    }
+    for (int t = tid; t < rl; t += nthr) cache[t] = -1;
+    __syncthreads();
+    if (wid == 0) {
+      int n_anch = 0;
+      for (int t0 = 0; t0 < m_surv; t0 += 32) {
+        const int t = t0 + lane;
+        const bool valid = t < m_surv;
+        AnchorRec a;
+        a.x = 0; a.cn = 0; a.y = 0; a.len = 0; a.weight = 0;
+        if (valid) a = rec[t];
+        const long long diag = (long long)a.x - a.y;
+        // the reference's cache slot (x + len - y) % len of the diagonal
+        const int slot = valid ? (int)(((unsigned long long)a.x + (unsigned long long)rl - (unsigned long long)a.y) %
+                                       (unsigned long long)rl)
+                               : -1 - lane;
+        const uint32_t grp = __match_any_sync(0xffffffffu, slot);
+        const uint32_t below = grp & lt;
+        const int pl = below ? 31 - __clz(below) : lane;
+        const long long pdiag = __shfl_sync(0xffffffffu, diag, pl);
+        const int pcn = __shfl_sync(0xffffffffu, a.cn, pl);
+        bool head = false;
+        int cached = -1;
+        if (valid) {
+          if (below) {
+            head = !(pdiag == diag && pcn == a.cn);
+          } else {
+            cached = cache[slot];
+            head = !(cached >= 0 && rec[cached].cn == a.cn && (long long)rec[cached].x - rec[cached].y == diag);
+          }
+        }
+        const uint32_t hm = __ballot_sync(0xffffffffu, head);
+        // the anchor this candidate belongs to: the nearest head of its slot at or below it, else the cached one
+        int aid = -1;
+        if (valid) {
+          const uint32_t hb = grp & hm & (lt | (1u << lane));
+          if (hb) {
+            const int hl = 31 - __clz(hb);
+            aid = n_anch + __popc(hm & ((1u << hl) - 1u));
+          } else {
+            // no head below in this step: the chain starts at the lowest lane of the group, which read the cache
+            const int first = __ffs(grp) - 1;
+            aid = -2 - first;   // resolved below
+          }
+        }
+        const int cached_first = __shfl_sync(0xffffffffu, cached, (aid <= -2) ? (-2 - aid) : lane);
+        if (aid <= -2) aid = cached_first;
+        __syncwarp();
+        if (valid && head) rec[aid] = a;   // aid <= t: every slot at or below t0+31 is already in registers
+        __syncwarp();
+        if (valid && !head) {
+          const AnchorRec d = rec[aid];
+          const int newlen = (int)((long long)a.x - (long long)d.x) + a.len;
+          atomicMax((unsigned int *)&rec[aid].y, ((unsigned int)newlen << 16) | (unsigned int)(uint16_t)d.y);
+          atomicAdd(&rec[aid].weight, 1);
+        }
+        if (valid && (grp >> lane) <= 1u) cache[slot] = aid;   // highest lane of the group
+        n_anch += __popc(hm);
+        __syncwarp();
+      }
+      if (lane == 0) s_nanch = n_anch;
+    }
+    __syncthreads();
+    const int n_anch = s_nanch;
+
+    // ---- 7. hit list: chain search on all threads, then ordered emission ------------------------------------
+    const int window_len = (int)(unsigned short)abs_or_pct_d(M.window_len, M.window_len_frac, (double)rl);
+    {
+      int mine = 0;
+      for (int i = tid; i < n_anch; i += nthr) {
+        int max_idx, max_score;
+        const bool emit = hit_chain(P, rec, i, rl, window_len, max_idx, max_score);
+        ent[i] = hit_pack(emit, max_idx, max_score);
+        mine += emit ? 1 : 0;
+      }
+      mine = warp_sum(mine);
+      if (lane == 0 && mine) atomicAdd(&s_cnt, (uint32_t)mine);
+    }
+    __syncthreads();
+    const int nh = (int)s_cnt;
+    if (tid == 0) {
+      atomicAdd(&P.stats[3], (uint32_t)n_anch);
+      uint32_t o = 0;
+      if (nh > 0) {
+        o = atomicAdd(P.hits_used, (uint32_t)nh);
+        if ((unsigned long long)o + (unsigned long long)nh > (unsigned long long)P.hits_cap) {
+          atomicOr(P.status, 1u);
+          o = 0xffffffffu;
+        }
+      }
+      s_out0 = o;
+    }
+    __syncthreads();
+    const uint32_t out0 = s_out0;
+    if (nh == 0 || out0 == 0xffffffffu) continue;
+    uint32_t basepos = 0;
+    for (int i0 = 0; i0 < n_anch; i0 += nthr) {
+      const int i = i0 + tid;
+      const unsigned long long pk = i < n_anch ? ent[i] : 0ull;
+      const bool emit = (pk & HITPACK_EMIT) != 0;
+      const uint32_t b = __ballot_sync(0xffffffffu, emit);
+      if (lane == 0) s_wsum[wid] = (uint32_t)__popc(b);
+      __syncthreads();
+      uint32_t before = 0, all = 0;
+      for (int w = 0; w < nwarps; w++) {
+        const uint32_t c = s_wsum[w];
+        if (w < wid) before += c;
+        all += c;
+      }
+      if (emit)
+        P.hits[out0 + basepos + before + (uint32_t)__popc(b & lt)] =
+            hit_make(P, rec, i, (int)((pk >> 32) & 0x7fffffffu), (int)(uint32_t)pk, rl, window_len);
+      basepos += all;
+      __syncthreads();
+    }
+    __threadfence_block();
+    __syncthreads();
+    if (tid == 0) {
+      hit_sort_serial(P.hits + out0, nh);
+      P.rs_range[rs] = make_uint2(out0, (uint32_t)nh);
     }
   }
 }
@@ -829,8 +1277,8 @@ __global__ void __launch_bounds__(SCAN_BIG_THREADS) scan_big_kernel(const ScanPa
 size_t scan_smem_bytes(int cap, int max_rl, int k_cap, int bm_log2, int warps, bool alias_rec) {
   return scan_layout(cap, max_rl, k_cap, bm_log2, alias_rec).total * warps;
 }
-size_t scan_big_smem_bytes(int cap, int max_rl, int k_cap, int bm_log2) {
-  return scan_layout(cap, max_rl, k_cap, bm_log2, true).total;
+size_t scan_cta_smem_bytes(int cap, int max_rl, int k_cap, int bm_log2, int n_part, bool global_arrays) {
+  return cta_layout(cap, max_rl, k_cap, bm_log2, n_part, global_arrays).total;
 }
 
 int launch_scan(shrimp_gpu_ctx *ctx, ScanParams &P, int warps_per_cta, int n_ctas) {
@@ -842,10 +1290,10 @@ int launch_scan(shrimp_gpu_ctx *ctx, ScanParams &P, int warps_per_cta, int n_cta
   return SHRIMP_OK;
 }
 
-int launch_scan_big(shrimp_gpu_ctx *ctx, ScanParams &P, int n_ctas) {
-  const size_t smem = scan_big_smem_bytes(P.cap, P.max_rl, P.k_cap, P.bm_log2);
-  SH_CUDA(cudaFuncSetAttribute(scan_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  scan_big_kernel<<<n_ctas, SCAN_BIG_THREADS, smem, ctx->stream>>>(P);
+int launch_scan_cta(shrimp_gpu_ctx *ctx, ScanParams &P, int n_ctas, int threads) {
+  const size_t smem = scan_cta_smem_bytes(P.cap, P.max_rl, P.k_cap, P.bm_log2, P.n_part, P.g_ent != nullptr);
+  SH_CUDA(cudaFuncSetAttribute(scan_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  scan_cta_kernel<<<n_ctas, threads, smem, ctx->stream>>>(P);
   SH_CUDA(cudaGetLastError());
   SH_LAUNCHED(ctx, ST_SCAN);
   return SHRIMP_OK;

@@ -8,6 +8,13 @@ namespace shrimp {
 #define SCAN_WARPS 8
 #define SCAN_WARPS_HOST SCAN_WARPS
 
+struct AnchorRec {
+  uint32_t x;      // global position
+  int32_t cn;
+  int16_t y, len;  // one 32-bit word, len in the upper half (the CTA kernel's collapse does atomicMax on it)
+  int32_t weight;
+};
+
 struct ScanParams {
   GenomeView G;
   IndexView I;
@@ -39,13 +46,14 @@ struct ScanParams {
   int bm_log2;             // log2 of the bits of each region bitmap
   int alias_rec;           // warp kernel: the anchors reuse the bitmaps (dead after pass B)
   int stream;              // warp kernel: lists long enough for one contiguous stream per lane
-};
-
-struct AnchorRec {
-  uint32_t x;      // global position
-  int32_t cn;
-  int16_t y, len;
-  int32_t weight;
+  // CTA kernel (scan_cta_kernel)
+  int n_part;              // genome partitions of 2^bm_log2 regions each (exact region bitmaps)
+  uint32_t *work_counter;  // dynamic work distribution
+  unsigned long long *g_ent;   // != nullptr: candidate arrays in a global slab per CTA of g_cap entries
+  AnchorRec *g_rec;
+  uint16_t *g_order;
+  uint32_t *g_keep;
+  int g_cap;
 };
 
 struct TaskBuildParams {

@@ -70,6 +70,32 @@ def test_cta_scan_kernel_alone_matches_reference_golden(gpu_ctx, name, monkeypat
     assert np.array_equal(sam, gold["sam"]) and np.array_equal(cig, gold["cigars"])
 
 
+@pytest.mark.parametrize("name,env", [
+    ("c1_small", {"SHRIMP_SCAN_BM_LOG2": "5"}),                                   # 4 partitions of 32 regions
+    ("c1_repeat", {"SHRIMP_SCAN_BM_LOG2": "6"}),                                  # 3 partitions of 64 regions
+    ("c2_small", {"SHRIMP_SCAN_BM_LOG2": "5", "SHRIMP_SCAN_CTA_THREADS": "64"}),
+    ("c1_repeat", {"SHRIMP_SCAN_CTA_CAP": "32"}),                                  # slab of 32: global-slab pass
+    ("c1_repeat", {"SHRIMP_SCAN_CTA_CAP": "32", "SHRIMP_SCAN_BM_LOG2": "5"}),
+    ("c5_small", {"SHRIMP_SCAN_CTA_CAP": "64"}),                                   # no region filter
+])
+def test_cta_scan_partitions_and_global_slabs(gpu_ctx, name, env, monkeypatch):
+    """the CTA scan kernel with the genome cut into several bitmap partitions (how a 3 Gb genome runs), and with
+    a candidate slab so small that strands fall through to the global-slab launch: same results"""
+    monkeypatch.setenv("SHRIMP_SCAN_FORCE_BIG", "1")
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    gold = np.load(os.path.join(GOLD, f"map_{name}.npz"))
+    case = LsCase(name)
+    res = run_gpu(gpu_ctx, case, **MAP_CASES[name]["opts"])
+    assert res.stats["scan_big_strands"] == 2 * len(case.read_len)
+    if "SHRIMP_SCAN_CTA_CAP" in env:
+        assert res.stats["scan_global_strands"] > 0
+    got_stage = stage_tuple_array(res.stage)
+    assert got_stage.shape == gold["stage"].shape and np.array_equal(got_stage, gold["stage"])
+    sam, cig = sam_arrays(case, res)
+    assert np.array_equal(sam, gold["sam"]) and np.array_equal(cig, gold["cigars"])
+
+
 def test_pipeline_alignment_strings_match_oracle(gpu_ctx):
     """dbalign/qralign rebuilt from the edit script equal the oracle's pretty_print strings"""
     from oracle import pipeline as op
