@@ -18,6 +18,7 @@ namespace shrimp {
 size_t scan_smem_bytes(int cap, int max_rl, int k_cap, int bm_log2, int warps, bool alias_rec);
 size_t scan_cta_smem_bytes(int cap, int max_rl, int k_cap, int bm_log2, int n_part, bool global_arrays);
 int launch_scan_cta(shrimp_gpu_ctx *ctx, ScanParams &P, int n_ctas, int threads);
+int launch_scan_replay(shrimp_gpu_ctx *ctx, ScanParams &P, uint32_t n_rec, int ks_cap);
 
 int launch_scan(shrimp_gpu_ctx *ctx, ScanParams &P, int warps_per_cta, int n_ctas);
 int launch_build_vec_tasks(shrimp_gpu_ctx *ctx, const TaskBuildParams &P);
@@ -112,7 +113,7 @@ void free_pipeline(shrimp_gpu_ctx *ctx) {
   Pipeline *p = (Pipeline *)ctx->pipeline;
   if (!p) return;
   DevBuf *bufs[] = {&p->d_in, &p->d_reads, &p->d_read_len, &p->d_initbp, &p->d_hits, &p->d_rs_range, &p->d_counters,
-                    &p->d_overflow, &p->d_overflow2, &p->d_scan_slab, &p->d_scratch, &p->d_task[0], &p->d_task[1], &p->d_vtrue[0], &p->d_vtrue[1],
+                    &p->d_overflow, &p->d_overflow2, &p->d_scan_slab, &p->d_tie_ent, &p->d_tie_order, &p->d_tie_rec, &p->d_scratch, &p->d_task[0], &p->d_task[1], &p->d_vtrue[0], &p->d_vtrue[1],
                     &p->d_slot, &p->d_writer, &p->d_sel, &p->d_nsel, &p->d_ftasks, &p->d_finfo, &p->d_fresults,
                     &p->d_frow, &p->d_fbp[0], &p->d_fbp[1], &p->d_fbp[2], &p->d_fbp[3], &p->d_fbp[4], &p->d_fops,
                     &p->d_taskoff, &p->d_scan_tmp, &p->d_perm, &p->d_pair_min, &p->d_pair_max, &p->d_saved, &p->d_pairsel,
@@ -454,7 +455,7 @@ int chunk_scan(Chunk &C) {
       cta_n_part = (int)std::ceil(n_regions / (double)(1u << cta_bm_log2));
       const double lam = est / n_regions;   // entries per region
       const double s_true = est * std::min(1.0, 1.1 * lam);
-      const double want = 2.0 * s_true + 2.0 * K_max + 64;
+      const double want = 1.5 * s_true + 1.5 * K_max + 64;
       while (cta_cap < 8192 && cta_cap < want) cta_cap <<= 1;
     } else {
       while (cta_cap < 8192 && cta_cap < est * 3 + 64) cta_cap <<= 1;
@@ -526,53 +527,133 @@ int chunk_scan(Chunk &C) {
       SH_CUDA(cudaStreamSynchronize(st));
     }
     if ((!small_useful || h3[1] > 0) && !(h3[2] & 1u)) {
-      // CTA-per-strand pass: the strands the warp kernel passed on, or every strand when the lists are long
+      // CTA-per-strand passes: the strands the warp kernel passed on, or every strand when the lists are long.
+      // Level 0: slab sized for the expected survivors; level 1: the largest shared-memory slab (repeats,
+      // low-complexity reads); level 2: candidate arrays in global slabs.
       SH_TRY(pl->d_overflow2.ensure((size_t)n_reads * 2 * 4));
-      P.work = small_useful ? pl->d_overflow.as<uint32_t>() : nullptr;
-      P.n_work = small_useful ? h3[1] : 2u * (uint32_t)n_reads;
-      P.overflow = pl->d_overflow2.as<uint32_t>();
-      P.n_overflow = cnt + 4;
-      P.work_counter = cnt + 3;
-      P.cap = cta_cap;
+      uint32_t *lists[2] = {pl->d_overflow.as<uint32_t>(), pl->d_overflow2.as<uint32_t>()};
+      int cur = 0;   // list holding the current work (valid when `have_list`)
+      bool have_list = small_useful;
+      uint32_t n_work = small_useful ? h3[1] : 2u * (uint32_t)n_reads;
+      C.scan_big = n_work;
       P.k_cap = big_k_cap;
       P.bm_log2 = cta_bm_log2;
       P.n_part = cta_n_part;
-      P.g_ent = nullptr;
-      const size_t smem = scan_cta_smem_bytes(cta_cap, max_rl, big_k_cap, cta_bm_log2, cta_n_part, false) + 1024;
-      const int per_sm = (int)std::max<size_t>(1, std::min<size_t>((size_t)(227 * 1024) / smem, 8));
-      int threads = std::max(128, std::min(512, (1024 / per_sm) & ~31));
-      if (const char *e = getenv("SHRIMP_SCAN_CTA_THREADS")) threads = std::max(32, std::min(512, atoi(e) & ~31));
-      int ctas = (int)std::min<uint32_t>((uint32_t)(ctx->sm_count * per_sm), P.n_work);
-      C.scan_big = P.n_work;
-      SH_TRY(launch_scan_cta(ctx, P, ctas, threads));
-      uint32_t h5[5] = {0, 0, 0, 0, 0};
-      SH_CUDA(cudaMemcpyAsync(h5, cnt, 20, cudaMemcpyDeviceToHost, st));
+      // lanes per index list: a warp streams 4 positions per lane and step
+      double avg_list = est / std::max(1, K_max);
+      P.lanes_per_list_log2 = avg_list > 64 ? 5 : avg_list > 32 ? 4 : avg_list > 12 ? 3 : 2;
+      if (const char *e = getenv("SHRIMP_SCAN_LANES_LOG2")) P.lanes_per_list_log2 = std::max(0, std::min(5, atoi(e)));
+      if (pl->tie_cap == 0) pl->tie_cap = (uint32_t)std::max<long long>(1 << 20, (long long)n_reads * 2 * 32);
+      SH_TRY(pl->d_tie_ent.ensure((size_t)pl->tie_cap * 8));
+      SH_TRY(pl->d_tie_order.ensure((size_t)pl->tie_cap * 2));
+      SH_TRY(pl->d_tie_rec.ensure((size_t)n_reads * 2 * sizeof(uint4)));
+      P.tie_ent = pl->d_tie_ent.as<unsigned long long>();
+      P.tie_order = pl->d_tie_order.as<uint16_t>();
+      P.tie_rec = pl->d_tie_rec.as<uint4>();
+      P.tie_used = cnt + 6;
+      P.n_tie = cnt + 5;
+      P.tie_cap = pl->tie_cap;
+      P.tie_rec_cap = 2u * (uint32_t)n_reads;
+      P.resume = 0;
+      uint32_t level_work[3] = {0, 0, 0};
+      int big_slab = 8192;
+      while (big_slab > cta_cap && scan_cta_smem_bytes(big_slab, max_rl, big_k_cap, cta_bm_log2, cta_n_part, false) > 224 * 1024)
+        big_slab >>= 1;
+      for (int level = 0; level < 3 && n_work > 0 && !(h3[2] & 1u); level++) {
+        if (level == 1 && (big_slab <= cta_cap || getenv("SHRIMP_SCAN_CTA_CAP"))) continue;
+        level_work[level] = n_work;
+        P.work = have_list ? lists[cur] : nullptr;
+        P.n_work = n_work;
+        P.overflow = level < 2 ? lists[cur ^ 1] : nullptr;
+        P.n_overflow = cnt + 4;
+        P.work_counter = cnt + 3;
+        SH_CUDA(cudaMemsetAsync(cnt + 3, 0, 8, st));
+        int ctas, threads;
+        if (level < 2) {
+          P.cap = level == 0 ? cta_cap : big_slab;
+          P.g_ent = nullptr;
+          const size_t smem = scan_cta_smem_bytes(P.cap, max_rl, big_k_cap, cta_bm_log2, cta_n_part, false) + 1024;
+          const int per_sm = (int)std::max<size_t>(1, std::min<size_t>((size_t)(227 * 1024) / smem, 8));
+          threads = std::max(128, std::min(768, (1536 / per_sm) & ~31));
+          if (const char *e = getenv("SHRIMP_SCAN_CTA_THREADS")) threads = std::max(32, std::min(768, atoi(e) & ~31));
+          ctas = (int)std::min<uint32_t>((uint32_t)(ctx->sm_count * per_sm), n_work);
+        } else {
+          ctas = (int)std::min<uint32_t>((uint32_t)ctx->sm_count, n_work);
+          threads = 512;
+          const size_t per_cta = (size_t)(g_cap + 1) * 8 + (size_t)(g_cap + 1) * sizeof(AnchorRec) +
+                                 (size_t)((g_cap + 15) & ~7) * 2 + (size_t)(g_cap / 32 + 2) * 4;
+          SH_TRY(pl->d_scan_slab.ensure(per_cta * (size_t)ctas + 64));
+          unsigned char *base = pl->d_scan_slab.as<unsigned char>();
+          P.g_ent = (unsigned long long *)base;
+          base += (size_t)ctas * (g_cap + 1) * 8;
+          P.g_rec = (AnchorRec *)base;
+          base += (size_t)ctas * (g_cap + 1) * sizeof(AnchorRec);
+          P.g_keep = (uint32_t *)base;
+          base += (size_t)ctas * (g_cap / 32 + 2) * 4;
+          P.g_order = (uint16_t *)base;
+          P.g_cap = g_cap;
+          C.scan_global = n_work;
+        }
+        SH_TRY(launch_scan_cta(ctx, P, ctas, threads));
+        uint32_t h5[5] = {0, 0, 0, 0, 0};
+        SH_CUDA(cudaMemcpyAsync(h5, cnt, 20, cudaMemcpyDeviceToHost, st));
+        SH_CUDA(cudaStreamSynchronize(st));
+        h3[0] = h5[0];
+        h3[2] = h5[2];
+        n_work = h5[4];
+        cur ^= 1;
+        have_list = true;
+      }
+      // parked strands: replay the reference's heap order (a warp each), then resume them at the anchor step
+      uint32_t h8[8];
+      SH_CUDA(cudaMemcpyAsync(h8, cnt, 32, cudaMemcpyDeviceToHost, st));
       SH_CUDA(cudaStreamSynchronize(st));
-      h3[0] = h5[0];
-      h3[2] = h5[2];
-      if (h5[4] > 0 && !(h3[2] & 1u)) {
-        // strands with more candidates than the shared-memory slab: candidate arrays in global slabs
-        const int gctas = (int)std::min<uint32_t>((uint32_t)ctx->sm_count, h5[4]);
-        const size_t per_cta = (size_t)(g_cap + 1) * 8 + (size_t)(g_cap + 1) * sizeof(AnchorRec) + (size_t)((g_cap + 15) & ~7) * 2 +
-                               (size_t)(g_cap / 32 + 2) * 4;
-        SH_TRY(pl->d_scan_slab.ensure(per_cta * (size_t)gctas + 64));
-        unsigned char *base = pl->d_scan_slab.as<unsigned char>();
-        P.g_ent = (unsigned long long *)base;
-        base += (size_t)gctas * (g_cap + 1) * 8;
-        P.g_rec = (AnchorRec *)base;
-        base += (size_t)gctas * (g_cap + 1) * sizeof(AnchorRec);
-        P.g_keep = (uint32_t *)base;
-        base += (size_t)gctas * (g_cap / 32 + 2) * 4;
-        P.g_order = (uint16_t *)base;
-        P.g_cap = g_cap;
-        P.work = pl->d_overflow2.as<uint32_t>();
-        P.n_work = h5[4];
+      if ((h8[2] & 4u) && !(h8[2] & 3u)) {  // tie slab too small: the cursor counted what is needed
+        pl->tie_cap = (uint32_t)std::min<unsigned long long>(0xfffffff0ull, (unsigned long long)h8[6] + h8[6] / 4 + 1024);
+        if (attempt > 8) {
+          set_error("seed scan: tie slab overflow");
+          return SHRIMP_E_NOMEM;
+        }
+        continue;
+      }
+      if (h8[5] > 0 && !(h8[2] & 3u)) {
+        const int ks_cap = std::max(32, K_slots);
+        SH_TRY(launch_scan_replay(ctx, P, h8[5], ks_cap));
+        P.resume = 1;
+        P.work = nullptr;
+        P.n_work = h8[5];
         P.overflow = nullptr;
-        SH_CUDA(cudaMemsetAsync(cnt + 3, 0, 4, st));
-        SH_TRY(launch_scan_cta(ctx, P, gctas, 512));
+        for (int level = 0; level < 3; level++) {
+          if (level_work[level] == 0) continue;
+          int ctas, threads;
+          SH_CUDA(cudaMemsetAsync(cnt + 3, 0, 4, st));
+          if (level < 2) {
+            P.cap = level == 0 ? cta_cap : big_slab;
+            P.resume_min = level == 0 ? 0 : cta_cap;
+            P.g_ent = nullptr;
+            const size_t smem = scan_cta_smem_bytes(P.cap, max_rl, big_k_cap, cta_bm_log2, cta_n_part, false) + 1024;
+            const int per_sm = (int)std::max<size_t>(1, std::min<size_t>((size_t)(227 * 1024) / smem, 8));
+            threads = std::max(128, std::min(768, (1536 / per_sm) & ~31));
+            ctas = (int)std::min<uint32_t>((uint32_t)(ctx->sm_count * per_sm), P.n_work);
+          } else {
+            // the global slabs of the level-2 launch above
+            P.resume_min = level_work[1] ? big_slab : cta_cap;
+            ctas = (int)std::min<uint32_t>((uint32_t)ctx->sm_count, level_work[2]);
+            threads = 512;
+            unsigned char *base = pl->d_scan_slab.as<unsigned char>();
+            P.g_ent = (unsigned long long *)base;
+            base += (size_t)ctas * (g_cap + 1) * 8;
+            P.g_rec = (AnchorRec *)base;
+            base += (size_t)ctas * (g_cap + 1) * sizeof(AnchorRec);
+            P.g_keep = (uint32_t *)base;
+            base += (size_t)ctas * (g_cap / 32 + 2) * 4;
+            P.g_order = (uint16_t *)base;
+            P.g_cap = g_cap;
+          }
+          SH_TRY(launch_scan_cta(ctx, P, ctas, threads));
+        }
         SH_CUDA(cudaMemcpyAsync(h3, cnt, 12, cudaMemcpyDeviceToHost, st));
         SH_CUDA(cudaStreamSynchronize(st));
-        C.scan_global = h5[4];
       }
     }
     if (h3[2] & 2u) {

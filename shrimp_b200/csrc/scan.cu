@@ -746,8 +746,8 @@ __host__ __device__ inline CtaSmem cta_layout(int cap, int max_rl, int k_cap, in
   return L;
 }
 
-#define SCAN_CTA_MAX_THREADS 512
-__global__ void __launch_bounds__(SCAN_CTA_MAX_THREADS) scan_cta_kernel(const ScanParams P) {
+#define SCAN_CTA_MAX_THREADS 768
+__global__ void __launch_bounds__(SCAN_CTA_MAX_THREADS, 2) scan_cta_kernel(const ScanParams P) {
   extern __shared__ unsigned char smem_raw[];
   __shared__ uint32_t s_item, s_total, s_ns, s_next, s_cnt, s_out0, s_wsum[SCAN_CTA_MAX_THREADS / 32];
   __shared__ int s_nanch;
@@ -786,6 +786,7 @@ __global__ void __launch_bounds__(SCAN_CTA_MAX_THREADS) scan_cta_kernel(const Sc
   const uint32_t rmask = (1u << M.region_bits) - 1u;
   const bool filt = M.use_region_counts != 0;
   const uint32_t lt = (1u << lane) - 1u;
+  const int glog = P.lanes_per_list_log2, g = 1 << glog, lpw = 32 >> glog, gl = lane & (g - 1);
 
   for (;;) {
     __syncthreads();
@@ -798,15 +799,26 @@ __global__ void __launch_bounds__(SCAN_CTA_MAX_THREADS) scan_cta_kernel(const Sc
     __syncthreads();
     const uint32_t item = s_item;
     if (item >= P.n_work) break;
-    const uint32_t rs = P.work ? P.work[item] : item;
+    const uint32_t rs = P.resume ? P.tie_rec[item].x : P.work ? P.work[item] : item;
     const int r = (int)(rs >> 1);
     const int rl = P.read_len[r];
     const uint32_t *seq = P.reads + (size_t)rs * P.stride;
     int max_n_kmers = M.colour_space ? rl - S.min_span : rl - S.min_span + 1;
     if (max_n_kmers < 0) max_n_kmers = 0;
-    if (!P.work && tid == 0) P.rs_range[rs] = make_uint2(0u, 0u);
+    if (!P.work && !P.resume && tid == 0) P.rs_range[rs] = make_uint2(0u, 0u);
     if (rl <= 0 || max_n_kmers == 0) continue;
 
+    int m_surv = 0;
+    const unsigned long long *esrc = ent;   // candidates in pop order: esrc[order ? order[t] : t]
+    const uint16_t *order = nullptr;
+    if (P.resume) {
+      // strands whose heap order was replayed by scan_replay_kernel: candidates and pop order come from the tie slab
+      const uint4 tr = P.tie_rec[item];
+      m_surv = (int)tr.z;
+      if (m_surv <= P.resume_min || m_surv > cap) continue;
+      esrc = P.tie_ent + tr.y;
+      order = P.tie_order + tr.y;
+    } else {
     // ---- 1. recode, project, bucket bounds ----------------------------------------------------------------
     const int nw2 = (rl + 15) / 16;
     for (int w = tid; w < nw2 + 3; w += nthr) {
@@ -881,25 +893,33 @@ __global__ void __launch_bounds__(SCAN_CTA_MAX_THREADS) scan_cta_kernel(const Sc
         if (tid == 0) s_next = 0;
         __syncthreads();
         for (;;) {
+          // a warp takes 32/g lists at a time, g lanes per list (g = P.lanes_per_list: short lists share a warp)
           uint32_t kk = 0;
-          if (lane == 0) kk = atomicAdd(&s_next, 1u);
+          if (lane == 0) kk = atomicAdd(&s_next, (uint32_t)lpw);
           kk = __shfl_sync(0xffffffffu, kk, 0);
           if (kk >= (uint32_t)K) break;
-          uint32_t a = 0, b = klen[kk];
-          if (n_part > 1) {
-            if (part > 0) a = cuts[kk * (n_part - 1) + part - 1];
-            if (part < n_part - 1) b = cuts[kk * (n_part - 1) + part];
+          kk += (uint32_t)(lane >> glog);
+          uint32_t a = 0, b = 0;
+          const uint32_t *p = nullptr;
+          if (kk < (uint32_t)K) {
+            b = klen[kk];
+            if (n_part > 1) {
+              if (part > 0) a = cuts[kk * (n_part - 1) + part - 1];
+              if (part < n_part - 1) b = cuts[kk * (n_part - 1) + part];
+            }
+            int sn = 0;
+            while ((int)kk >= kbase[sn + 1]) sn++;
+            p = P.I.pos[sn] + kst[kk];
           }
-          if (a >= b) continue;
-          int sn = 0;
-          while ((int)kk >= kbase[sn + 1]) sn++;
-          const uint32_t *p = P.I.pos[sn] + kst[kk];
-          for (uint32_t base = a; base < b; base += 128) {
+          if (b < a) b = a;
+          const uint32_t steps = __reduce_max_sync(0xffffffffu, (b - a + (uint32_t)(4 * g) - 1u) / (uint32_t)(4 * g));
+          for (uint32_t it = 0; it < steps; it++) {
+            const uint32_t base = a + it * (uint32_t)(4 * g) + (uint32_t)gl;
             uint32_t x[4];
             bool ok[4];
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-              const uint32_t i = base + u * 32 + lane;
+              const uint32_t i = base + (uint32_t)(u * g);
               ok[u] = i < b;
               x[u] = ok[u] ? __ldg(p + i) : 0u;
             }
@@ -924,25 +944,32 @@ __global__ void __launch_bounds__(SCAN_CTA_MAX_THREADS) scan_cta_kernel(const Sc
       __syncthreads();
       for (;;) {
         uint32_t kk = 0;
-        if (lane == 0) kk = atomicAdd(&s_next, 1u);
+        if (lane == 0) kk = atomicAdd(&s_next, (uint32_t)lpw);
         kk = __shfl_sync(0xffffffffu, kk, 0);
         if (kk >= (uint32_t)K) break;
-        uint32_t a = 0, b = klen[kk];
-        if (n_part > 1) {
-          if (part > 0) a = cuts[kk * (n_part - 1) + part - 1];
-          if (part < n_part - 1) b = cuts[kk * (n_part - 1) + part];
+        kk += (uint32_t)(lane >> glog);
+        uint32_t a = 0, b = 0, slot = 0;
+        const uint32_t *p = nullptr;
+        if (kk < (uint32_t)K) {
+          b = klen[kk];
+          if (n_part > 1) {
+            if (part > 0) a = cuts[kk * (n_part - 1) + part - 1];
+            if (part < n_part - 1) b = cuts[kk * (n_part - 1) + part];
+          }
+          int sn = 0;
+          while ((int)kk >= kbase[sn + 1]) sn++;
+          p = P.I.pos[sn] + kst[kk];
+          slot = (uint32_t)(sn * max_n_kmers + ((int)kk - kbase[sn]));
         }
-        if (a >= b) continue;
-        int sn = 0;
-        while ((int)kk >= kbase[sn + 1]) sn++;
-        const uint32_t *p = P.I.pos[sn] + kst[kk];
-        const uint32_t slot = (uint32_t)(sn * max_n_kmers + ((int)kk - kbase[sn]));
-        for (uint32_t base = a; base < b; base += 128) {
+        if (b < a) b = a;
+        const uint32_t steps = __reduce_max_sync(0xffffffffu, (b - a + (uint32_t)(4 * g) - 1u) / (uint32_t)(4 * g));
+        for (uint32_t it = 0; it < steps; it++) {
+          const uint32_t base = a + it * (uint32_t)(4 * g) + (uint32_t)gl;
           uint32_t x[4];
           bool ok[4];
 #pragma unroll
           for (int u = 0; u < 4; u++) {
-            const uint32_t i = base + u * 32 + lane;
+            const uint32_t i = base + (uint32_t)(u * g);
             ok[u] = i < b;
             x[u] = ok[u] ? __ldg(p + i) : 0u;
           }
@@ -1002,7 +1029,7 @@ __global__ void __launch_bounds__(SCAN_CTA_MAX_THREADS) scan_cta_kernel(const Sc
       }
     }
     // ---- 4b. region filter (RG_HAS_2 as a neighbour test) + ordered compaction ----------------------------
-    int m_surv = ns;
+    m_surv = ns;
     if (filt) {
       const int n_words = (ns + 31) >> 5;
       for (int t0 = 0; t0 < n_words * 32; t0 += nthr) {
@@ -1071,76 +1098,33 @@ __global__ void __launch_bounds__(SCAN_CTA_MAX_THREADS) scan_cta_kernel(const Sc
         tie = true;
     }
     tie = __syncthreads_or(tie) != 0;
-    const uint16_t *order = nullptr;
     if (tie) {
-      int32_t *first_of = (int32_t *)kst;   // the k-mer tables are dead
-      const int Ks = S.n_seeds * max_n_kmers;
-      for (int k = tid; k < Ks; k += nthr) first_of[k] = -1;
-      __syncthreads();
+      // the pop order of equal positions is the reference's binary heap order (SURVEY hard part 3a): park the
+      // candidates in the tie slab; scan_replay_kernel replays heap_uu for all such strands at once (a warp each),
+      // then this kernel resumes them at step 6
       if (tid == 0) {
+        const uint32_t off = atomicAdd(P.tie_used, (uint32_t)m_surv);
+        uint32_t idx = 0xffffffffu;
+        if ((unsigned long long)off + (unsigned long long)m_surv <= (unsigned long long)P.tie_cap) {
+          idx = atomicAdd(P.n_tie, 1u);
+          if (idx < P.tie_rec_cap) P.tie_rec[idx] = make_uint4(rs, off, (uint32_t)m_surv, 0u);
+          else idx = 0xffffffffu;
+        }
+        if (idx == 0xffffffffu) atomicOr(P.status, 4u);
+        s_out0 = idx == 0xffffffffu ? idx : off;
         atomicAdd(&P.stats[0], 1u);
-        for (int t = m_surv - 1; t >= 0; t--) {
-          const unsigned long long e = ent[t];
-          const int off = (int)((uint32_t)e & 0xffffu);
-          const uint32_t nx = first_of[off] < 0 ? 0xffffu : (uint32_t)first_of[off];
-          ent[t] = (e & 0xffffffff0000ffffull) | ((unsigned long long)nx << 16);
-          first_of[off] = t;
-        }
-        int load = 0;   // heap_uu on key = position, loaded in ascending slot order (mapping.c:913-935)
-        for (int off = 0; off < Ks; off++) {
-          const int t = first_of[off];
-          if (t < 0) continue;
-          heap64[load++] = (ent[t] & 0xffffffff00000000ull) | (unsigned)t;
-          int node = load, parent = node / 2;  // percolate_up, heap.h:43-60
-          while (node > 1 && (heap64[node - 1] >> 32) < (heap64[parent - 1] >> 32)) {
-            const unsigned long long tmp = heap64[parent - 1];
-            heap64[parent - 1] = heap64[node - 1];
-            heap64[node - 1] = tmp;
-            node = parent;
-            parent = node / 2;
-          }
-        }
-        int outn = 0;
-        while (load > 0) {
-          const int t = (int)(uint32_t)heap64[0];
-          order16[outn++] = (uint16_t)t;
-          const uint32_t nx = ((uint32_t)ent[t] >> 16) & 0xffffu;
-          if (nx != 0xffffu) {
-            heap64[0] = (ent[nx] & 0xffffffff00000000ull) | nx;  // heap_uu_replace_min
-          } else {
-            load--;  // heap_uu_extract_min
-            if (load > 0) heap64[0] = heap64[load];
-          }
-          if (load > 0) {  // percolate_down, heap.h:62-89
-            int node = 1;
-            const unsigned long long cur = heap64[0];
-            for (;;) {
-              const int left = node * 2, right = left + 1;
-              int mn = node;
-              unsigned long long mk = cur;
-              if (left <= load) {
-                const unsigned long long lk = heap64[left - 1];
-                if ((lk >> 32) < (mk >> 32)) { mn = left; mk = lk; }
-              }
-              if (right <= load) {
-                const unsigned long long rk = heap64[right - 1];
-                if ((rk >> 32) < (mk >> 32)) { mn = right; mk = rk; }
-              }
-              if (mn == node) break;
-              heap64[node - 1] = mk;
-              heap64[mn - 1] = cur;
-              node = mn;
-            }
-          }
-        }
       }
       __syncthreads();
-      order = order16;
+      const uint32_t off = s_out0;
+      if (off != 0xffffffffu)
+        for (int t = tid; t < m_surv; t += nthr) P.tie_ent[off + t] = ent[t];
+      continue;
     }
+    }  // !P.resume
 
     // ---- 6. anchors in pop order; colinear collapse (:941-971) in warp lockstep ---------------------------
     for (int t = tid; t < m_surv; t += nthr) {
-      const unsigned long long e = ent[order ? order[t] : t];
+      const unsigned long long e = esrc[order ? order[t] : t];
       const uint32_t slot = (uint32_t)e & 0xffffu;
       const int sn = (int)(slot / (uint32_t)max_n_kmers), i = (int)(slot % (uint32_t)max_n_kmers);
       AnchorRec a;
@@ -1277,6 +1261,112 @@ __global__ void __launch_bounds__(SCAN_CTA_MAX_THREADS) scan_cta_kernel(const Sc
 size_t scan_smem_bytes(int cap, int max_rl, int k_cap, int bm_log2, int warps, bool alias_rec) {
   return scan_layout(cap, max_rl, k_cap, bm_log2, alias_rec).total * warps;
 }
+// ---- heap-order replay for the strands with equal positions on different read offsets -------------------------
+// One warp per parked strand.  The k-way merge of the reference pops equal keys in binary-heap order
+// (read_get_anchor_list_per_strand, mapping.c:913-1006; heap_uu, common/heap.h:43-113): lanes build the per-list
+// chains in parallel (match_any), lane 0 replays the heap in shared memory.  A heap element is the candidate word with
+// its slot field replaced by the candidate's index: position << 32 | next-in-list << 16 | index.
+#define REPLAY_WARPS 8
+__global__ void __launch_bounds__(REPLAY_WARPS * 32) scan_replay_kernel(const ScanParams P, uint32_t n_rec, int ks_cap) {
+  extern __shared__ unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint32_t w = blockIdx.x * REPLAY_WARPS + wib;
+  if (w >= n_rec) return;
+  unsigned char *base = smem_raw + (size_t)wib * (((size_t)ks_cap * 18 + 47) & ~(size_t)15);
+  unsigned long long *heap = (unsigned long long *)base;
+  unsigned long long *stage = heap + ks_cap;
+  uint16_t *first_of = (uint16_t *)(stage + ks_cap);
+  const uint4 tr = P.tie_rec[w];
+  const uint32_t rs = tr.x;
+  const int m = (int)tr.z;
+  unsigned long long *ent = P.tie_ent + tr.y;
+  uint16_t *order = P.tie_order + tr.y;
+  const int rl = P.read_len[rs >> 1];
+  int max_n_kmers = P.M.colour_space ? rl - P.S.min_span : rl - P.S.min_span + 1;
+  const int Ks = P.S.n_seeds * max_n_kmers;
+  const uint32_t lt = (1u << lane) - 1u;
+  for (int k = lane; k < Ks; k += 32) first_of[k] = 0xffffu;
+  __syncwarp();
+  // chains: next candidate of the same list, built from the back
+  for (int t0 = ((m - 1) >> 5) << 5; t0 >= 0; t0 -= 32) {
+    const int t = t0 + lane;
+    const bool valid = t < m;
+    const unsigned long long e = valid ? ent[t] : 0ull;
+    const uint32_t slot = valid ? ((uint32_t)e & 0xffffu) : (0x10000u + (uint32_t)lane);
+    const uint32_t grp = __match_any_sync(0xffffffffu, slot);
+    const uint32_t above = grp & ~(lt | (1u << lane));
+    uint32_t nx = 0xffffu;
+    if (valid) nx = above ? (uint32_t)(t0 + __ffs(above) - 1) : (uint32_t)first_of[slot];
+    __syncwarp();
+    if (valid && !(grp & lt)) first_of[slot] = (uint16_t)t;
+    if (valid) ent[t] = (e & 0xffffffff0000ffffull) | ((unsigned long long)nx << 16);
+    __syncwarp();
+  }
+  // heads of the lists, in ascending slot order (the load order of mapping.c:913-935)
+  for (int k = lane; k < Ks; k += 32) {
+    const uint32_t t = first_of[k];
+    stage[k] = t == 0xffffu ? ~0ull : ((ent[t] & 0xffffffffffff0000ull) | t);
+  }
+  __syncwarp();
+  if (lane != 0) return;
+  int load = 0;
+  for (int k = 0; k < Ks; k++) {
+    const unsigned long long el = stage[k];
+    if (el == ~0ull) continue;
+    heap[load++] = el;
+    int node = load, parent = node / 2;  // percolate_up, heap.h:43-60
+    while (node > 1 && (heap[node - 1] >> 32) < (heap[parent - 1] >> 32)) {
+      const unsigned long long tmp = heap[parent - 1];
+      heap[parent - 1] = heap[node - 1];
+      heap[node - 1] = tmp;
+      node = parent;
+      parent = node / 2;
+    }
+  }
+  int outn = 0;
+  while (load > 0) {
+    const unsigned long long root = heap[0];
+    order[outn++] = (uint16_t)((uint32_t)root & 0xffffu);
+    const uint32_t nx = ((uint32_t)root >> 16) & 0xffffu;
+    if (nx != 0xffffu) {
+      heap[0] = (ent[nx] & 0xffffffffffff0000ull) | nx;  // heap_uu_replace_min
+    } else {
+      load--;  // heap_uu_extract_min
+      if (load > 0) heap[0] = heap[load];
+    }
+    if (load > 0) {  // percolate_down, heap.h:62-89
+      int node = 1;
+      const unsigned long long cur = heap[0];
+      for (;;) {
+        const int left = node * 2, right = left + 1;
+        int mn = node;
+        unsigned long long mk = cur;
+        if (left <= load) {
+          const unsigned long long lk = heap[left - 1];
+          if ((lk >> 32) < (mk >> 32)) { mn = left; mk = lk; }
+        }
+        if (right <= load) {
+          const unsigned long long rk = heap[right - 1];
+          if ((rk >> 32) < (mk >> 32)) { mn = right; mk = rk; }
+        }
+        if (mn == node) break;
+        heap[node - 1] = mk;
+        heap[mn - 1] = cur;
+        node = mn;
+      }
+    }
+  }
+}
+
+int launch_scan_replay(shrimp_gpu_ctx *ctx, ScanParams &P, uint32_t n_rec, int ks_cap) {
+  const size_t smem = (size_t)REPLAY_WARPS * (((size_t)ks_cap * 18 + 47) & ~(size_t)15);
+  SH_CUDA(cudaFuncSetAttribute(scan_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  scan_replay_kernel<<<(n_rec + REPLAY_WARPS - 1) / REPLAY_WARPS, REPLAY_WARPS * 32, smem, ctx->stream>>>(P, n_rec, ks_cap);
+  SH_CUDA(cudaGetLastError());
+  SH_LAUNCHED(ctx, ST_SCAN);
+  return SHRIMP_OK;
+}
+
 size_t scan_cta_smem_bytes(int cap, int max_rl, int k_cap, int bm_log2, int n_part, bool global_arrays) {
   return cta_layout(cap, max_rl, k_cap, bm_log2, n_part, global_arrays).total;
 }

@@ -54,6 +54,14 @@ struct ScanParams {
   uint16_t *g_order;
   uint32_t *g_keep;
   int g_cap;
+  // strands with equal positions on different read offsets: parked for scan_replay_kernel, resumed at step 6
+  unsigned long long *tie_ent;   // candidate slab
+  uint16_t *tie_order;           // pop order per parked strand (same offsets as tie_ent)
+  uint4 *tie_rec;                // (read strand, slab offset, candidates, 0)
+  uint32_t *tie_used, *n_tie;    // atomic cursors
+  uint32_t tie_cap, tie_rec_cap;
+  int resume, resume_min;        // resume launch: strands with resume_min < candidates <= cap
+  int lanes_per_list_log2; // lanes that share one index list (2..5): short lists are streamed several per warp
 };
 
 struct TaskBuildParams {
