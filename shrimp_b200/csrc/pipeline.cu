@@ -16,7 +16,7 @@ namespace shrimp {
 
 // ---- entry points of the other translation units -----------------------------------------------
 size_t scan_smem_bytes(int cap, int max_rl, int k_cap, int bm_log2, int warps, bool alias_rec);
-size_t scan_cta_smem_bytes(int cap, int max_rl, int k_cap, int bm_log2, int n_part, bool global_arrays);
+size_t scan_cta_smem_bytes(int cap, int max_rl, int k_cap, int bm_log2, int n_part, int win, bool global_arrays);
 int launch_scan_cta(shrimp_gpu_ctx *ctx, ScanParams &P, int n_ctas, int threads);
 int launch_scan_replay(shrimp_gpu_ctx *ctx, ScanParams &P, uint32_t n_rec, int ks_cap);
 
@@ -113,7 +113,7 @@ void free_pipeline(shrimp_gpu_ctx *ctx) {
   Pipeline *p = (Pipeline *)ctx->pipeline;
   if (!p) return;
   DevBuf *bufs[] = {&p->d_in, &p->d_reads, &p->d_read_len, &p->d_initbp, &p->d_hits, &p->d_rs_range, &p->d_counters,
-                    &p->d_overflow, &p->d_overflow2, &p->d_scan_slab, &p->d_tie_ent, &p->d_tie_order, &p->d_tie_rec, &p->d_scratch, &p->d_task[0], &p->d_task[1], &p->d_vtrue[0], &p->d_vtrue[1],
+                    &p->d_overflow, &p->d_overflow2, &p->d_scan_slab, &p->d_tie_ent, &p->d_tie_order, &p->d_tie_rec, &p->d_prof, &p->d_scratch, &p->d_task[0], &p->d_task[1], &p->d_vtrue[0], &p->d_vtrue[1],
                     &p->d_slot, &p->d_writer, &p->d_sel, &p->d_nsel, &p->d_ftasks, &p->d_finfo, &p->d_fresults,
                     &p->d_frow, &p->d_fbp[0], &p->d_fbp[1], &p->d_fbp[2], &p->d_fbp[3], &p->d_fbp[4], &p->d_fops,
                     &p->d_taskoff, &p->d_scan_tmp, &p->d_perm, &p->d_pair_min, &p->d_pair_max, &p->d_saved, &p->d_pairsel,
@@ -444,28 +444,50 @@ int chunk_scan(Chunk &C) {
   // CTA kernel: exact region bitmaps over partitions of 2^cta_bm_log2 regions, candidate slots for twice the
   // expected survivors
   const int big_k_cap = std::max(32, std::max(K_max, K_slots));
-  int cta_bm_log2 = 5, cta_n_part = 1, cta_cap = 1024;
+  int cta_bm_log2 = 5, cta_n_part = 1, cta_cap = 512, cta_win = 1024;
+  bool cta_hashed = false;
   {
     const double n_regions = L_total / (double)(1u << C.M.region_bits) + 2.0;
     if (filt) {
+      int exact_log2 = 5;
+      while (exact_log2 < 31 && (double)(1u << exact_log2) < n_regions) exact_log2++;
+      // exact bitmaps (one bit per 2 kb region, partitions of at most 2^18 regions) unless they would be far
+      // larger than the strand's entries call for: then hashed bitmaps of >= 8 bits per expected entry, whose
+      // false candidates the exact neighbour test removes
+      cta_hashed = (double)(1u << exact_log2) > 16.0 * std::max(est, 64.0);
+      if (const char *e = getenv("SHRIMP_SCAN_HASHED")) cta_hashed = atoi(e) != 0;
       int bm_max = 18;
-      if (const char *e = getenv("SHRIMP_SCAN_BM_LOG2")) bm_max = std::max(5, std::min(19, atoi(e)));  // test hook
-      cta_bm_log2 = std::min(10, bm_max);
-      while (cta_bm_log2 < bm_max && (double)(1u << cta_bm_log2) < n_regions) cta_bm_log2++;
-      cta_n_part = (int)std::ceil(n_regions / (double)(1u << cta_bm_log2));
+      if (const char *e = getenv("SHRIMP_SCAN_BM_LOG2")) {  // test hook
+        bm_max = std::max(5, std::min(19, atoi(e)));
+        if (!getenv("SHRIMP_SCAN_HASHED")) cta_hashed = false;
+      }
+      double s_false = 0;
+      if (cta_hashed) {
+        cta_bm_log2 = 10;
+        while (cta_bm_log2 < bm_max && (double)(1u << cta_bm_log2) < 8.0 * est) cta_bm_log2++;
+        if (getenv("SHRIMP_SCAN_BM_LOG2")) cta_bm_log2 = bm_max;
+        s_false = est * std::min(1.0, 1.1 * est / (double)(1u << cta_bm_log2));
+      } else {
+        cta_bm_log2 = std::min(10, bm_max);
+        while (cta_bm_log2 < bm_max && (double)(1u << cta_bm_log2) < n_regions) cta_bm_log2++;
+        cta_n_part = (int)std::ceil(n_regions / (double)(1u << cta_bm_log2));
+      }
       const double lam = est / n_regions;   // entries per region
       const double s_true = est * std::min(1.0, 1.1 * lam);
-      const double want = 1.5 * s_true + 1.5 * K_max + 64;
+      const double want = 1.3 * (s_true + s_false) + K_max + 64;
       while (cta_cap < 8192 && cta_cap < want) cta_cap <<= 1;
     } else {
       while (cta_cap < 8192 && cta_cap < est * 3 + 64) cta_cap <<= 1;
     }
+    // staging window: about half of a partition's entries, 1024..4096
+    while (cta_win < 4096 && cta_win < 0.4 * est / cta_n_part) cta_win <<= 1;
+    if (const char *e = getenv("SHRIMP_SCAN_WIN")) cta_win = std::max(64, atoi(e));  // test hook: several windows
     if (const char *e = getenv("SHRIMP_SCAN_CTA_CAP")) cta_cap = std::max(32, atoi(e));  // test hook: global slabs
-    while (cta_cap > 256 && scan_cta_smem_bytes(cta_cap, max_rl, big_k_cap, cta_bm_log2, cta_n_part, false) > 200 * 1024)
+    while (cta_cap > 256 && scan_cta_smem_bytes(cta_cap, max_rl, big_k_cap, cta_bm_log2, cta_n_part, cta_win, false) > 200 * 1024)
       cta_cap >>= 1;
   }
   const int g_cap = 65535;   // global-slab pass: 16-bit candidate indices
-  if (scan_cta_smem_bytes(cta_cap, max_rl, big_k_cap, cta_bm_log2, cta_n_part, false) > 226 * 1024) {
+  if (scan_cta_smem_bytes(cta_cap, max_rl, big_k_cap, cta_bm_log2, cta_n_part, cta_win, false) > 226 * 1024) {
     set_error("seed scan: reads of %d bases with these seeds need more shared memory than a CTA has", max_rl);
     return SHRIMP_E_RANGE;
   }
@@ -539,6 +561,8 @@ int chunk_scan(Chunk &C) {
       P.k_cap = big_k_cap;
       P.bm_log2 = cta_bm_log2;
       P.n_part = cta_n_part;
+      P.win = cta_win;
+      P.bm_hashed = cta_hashed ? 1 : 0;
       // lanes per index list: a warp streams 4 positions per lane and step
       double avg_list = est / std::max(1, K_max);
       P.lanes_per_list_log2 = avg_list > 64 ? 5 : avg_list > 32 ? 4 : avg_list > 12 ? 3 : 2;
@@ -555,9 +579,15 @@ int chunk_scan(Chunk &C) {
       P.tie_cap = pl->tie_cap;
       P.tie_rec_cap = 2u * (uint32_t)n_reads;
       P.resume = 0;
+      P.prof = nullptr;
+      if (getenv("SHRIMP_SCAN_PROF")) {
+        SH_TRY(pl->d_prof.ensure(16 * 8));
+        SH_CUDA(cudaMemsetAsync(pl->d_prof.p, 0, 16 * 8, st));
+        P.prof = pl->d_prof.as<unsigned long long>();
+      }
       uint32_t level_work[3] = {0, 0, 0};
       int big_slab = 8192;
-      while (big_slab > cta_cap && scan_cta_smem_bytes(big_slab, max_rl, big_k_cap, cta_bm_log2, cta_n_part, false) > 224 * 1024)
+      while (big_slab > cta_cap && scan_cta_smem_bytes(big_slab, max_rl, big_k_cap, cta_bm_log2, cta_n_part, cta_win, false) > 224 * 1024)
         big_slab >>= 1;
       for (int level = 0; level < 3 && n_work > 0 && !(h3[2] & 1u); level++) {
         if (level == 1 && (big_slab <= cta_cap || getenv("SHRIMP_SCAN_CTA_CAP"))) continue;
@@ -572,7 +602,7 @@ int chunk_scan(Chunk &C) {
         if (level < 2) {
           P.cap = level == 0 ? cta_cap : big_slab;
           P.g_ent = nullptr;
-          const size_t smem = scan_cta_smem_bytes(P.cap, max_rl, big_k_cap, cta_bm_log2, cta_n_part, false) + 1024;
+          const size_t smem = scan_cta_smem_bytes(P.cap, max_rl, big_k_cap, cta_bm_log2, cta_n_part, cta_win, false) + 1024;
           const int per_sm = (int)std::max<size_t>(1, std::min<size_t>((size_t)(227 * 1024) / smem, 8));
           threads = std::max(128, std::min(768, (1536 / per_sm) & ~31));
           if (const char *e = getenv("SHRIMP_SCAN_CTA_THREADS")) threads = std::max(32, std::min(768, atoi(e) & ~31));
@@ -604,6 +634,17 @@ int chunk_scan(Chunk &C) {
         cur ^= 1;
         have_list = true;
       }
+      if (P.prof) {
+        unsigned long long hp[16];
+        SH_CUDA(cudaMemcpyAsync(hp, P.prof, sizeof(hp), cudaMemcpyDeviceToHost, st));
+        SH_CUDA(cudaStreamSynchronize(st));
+        unsigned long long tot = 0;
+        for (int i = 0; i < 16; i++) tot += hp[i];
+        fprintf(stderr, "scan_cta phases (%% of CTA cycles):");
+        for (int i = 0; i < 16; i++) if (hp[i]) fprintf(stderr, " [%d] %.1f", i, 100.0 * (double)hp[i] / (double)tot);
+        fprintf(stderr, "\n");
+        P.prof = nullptr;
+      }
       // parked strands: replay the reference's heap order (a warp each), then resume them at the anchor step
       uint32_t h8[8];
       SH_CUDA(cudaMemcpyAsync(h8, cnt, 32, cudaMemcpyDeviceToHost, st));
@@ -631,7 +672,7 @@ int chunk_scan(Chunk &C) {
             P.cap = level == 0 ? cta_cap : big_slab;
             P.resume_min = level == 0 ? 0 : cta_cap;
             P.g_ent = nullptr;
-            const size_t smem = scan_cta_smem_bytes(P.cap, max_rl, big_k_cap, cta_bm_log2, cta_n_part, false) + 1024;
+            const size_t smem = scan_cta_smem_bytes(P.cap, max_rl, big_k_cap, cta_bm_log2, cta_n_part, cta_win, false) + 1024;
             const int per_sm = (int)std::max<size_t>(1, std::min<size_t>((size_t)(227 * 1024) / smem, 8));
             threads = std::max(128, std::min(768, (1536 / per_sm) & ~31));
             ctas = (int)std::min<uint32_t>((uint32_t)(ctx->sm_count * per_sm), P.n_work);

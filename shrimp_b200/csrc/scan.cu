@@ -722,9 +722,10 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) scan_kernel(const ScanParams 
 // Strands with more candidates than the shared-memory slab go to a second launch whose candidate arrays live in
 // a global slab per CTA (P.g_ent != nullptr).
 struct CtaSmem {
-  size_t r2, kst, klen, cuts, cache, keep, order, ent, bm1, bm2, rec, heap, total;
+  size_t r2, kst, klen, kA, kpre, cuts, cache, keep, order, ent, bm1, bm2, rec, heap, buf, bslot, total;
 };
-__host__ __device__ inline CtaSmem cta_layout(int cap, int max_rl, int k_cap, int bm_log2, int n_part, bool global_arrays) {
+__host__ __device__ inline CtaSmem cta_layout(int cap, int max_rl, int k_cap, int bm_log2, int n_part, int win,
+                                              bool global_arrays) {
   CtaSmem L;
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t at = o; o += (bytes + 15) & ~(size_t)15; return at; };
@@ -732,6 +733,10 @@ __host__ __device__ inline CtaSmem cta_layout(int cap, int max_rl, int k_cap, in
   L.r2 = take(((size_t)max_rl / 16 + 4) * 4);
   L.kst = take((size_t)k_cap * 4);
   L.klen = take((size_t)k_cap * 4);
+  L.kA = take((size_t)k_cap * 4);
+  L.kpre = take(((size_t)k_cap + 1) * 4);
+  L.buf = take((size_t)win * 4);
+  L.bslot = take((size_t)win * 2);
   L.cuts = take((size_t)k_cap * (size_t)(n_part > 1 ? n_part - 1 : 0) * 4);
   L.cache = take((size_t)max_rl * 4);
   L.heap = take((size_t)k_cap * 8);
@@ -747,37 +752,42 @@ __host__ __device__ inline CtaSmem cta_layout(int cap, int max_rl, int k_cap, in
 }
 
 #define SCAN_CTA_MAX_THREADS 768
+// phase timing (P.prof != nullptr): thread 0 adds the cycles since the previous mark to prof[phase]
+#define PROF_MARK(ph)                                                   \
+  do {                                                                  \
+    if (P.prof && tid == 0) {                                           \
+      const long long _now = clock64();                                 \
+      atomicAdd(&P.prof[ph], (unsigned long long)(_now - prof_t));      \
+      prof_t = _now;                                                    \
+    }                                                                   \
+  } while (0)
+// GLOB: candidate arrays in global slabs (else in shared memory: the template keeps the address space static)
+template <bool GLOB>
 __global__ void __launch_bounds__(SCAN_CTA_MAX_THREADS, 2) scan_cta_kernel(const ScanParams P) {
   extern __shared__ unsigned char smem_raw[];
-  __shared__ uint32_t s_item, s_total, s_ns, s_next, s_cnt, s_out0, s_wsum[SCAN_CTA_MAX_THREADS / 32];
-  __shared__ int s_nanch;
+  __shared__ uint32_t s_item_next, s_total, s_ns, s_next, s_cnt, s_out0, s_wsum[SCAN_CTA_MAX_THREADS / 32];
+  __shared__ int s_nanch, kbase[SHRIMP_MAX_SEEDS + 1];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nthr = blockDim.x, nwarps = nthr >> 5;
-  const bool glob = P.g_ent != nullptr;
+  constexpr bool glob = GLOB;
   const int cap = glob ? P.g_cap : P.cap;
   const int n_part = P.n_part;
-  const CtaSmem L = cta_layout(P.cap, P.max_rl, P.k_cap, P.bm_log2, n_part, glob);
+  const CtaSmem L = cta_layout(P.cap, P.max_rl, P.k_cap, P.bm_log2, n_part, P.win, glob);
+  const int win = P.win;
+  uint32_t *kA = (uint32_t *)(smem_raw + L.kA), *kpre = (uint32_t *)(smem_raw + L.kpre);
+  uint32_t *buf = (uint32_t *)(smem_raw + L.buf);
+  uint16_t *bslot = (uint16_t *)(smem_raw + L.bslot);
   uint32_t *r2 = (uint32_t *)(smem_raw + L.r2);
   uint32_t *kst = (uint32_t *)(smem_raw + L.kst), *klen = (uint32_t *)(smem_raw + L.klen);
   uint32_t *cuts = (uint32_t *)(smem_raw + L.cuts);
   int32_t *cache = (int32_t *)(smem_raw + L.cache);
   unsigned long long *heap64 = (unsigned long long *)(smem_raw + L.heap);
   uint32_t *bm1 = (uint32_t *)(smem_raw + L.bm1), *bm2 = (uint32_t *)(smem_raw + L.bm2);
-  uint32_t *keep;
-  uint16_t *order16;
-  unsigned long long *ent;
-  AnchorRec *rec;
-  if (glob) {
-    const size_t b = (size_t)blockIdx.x;
-    ent = P.g_ent + b * (size_t)(cap + 1);
-    rec = P.g_rec + b * (size_t)(cap + 1);
-    order16 = P.g_order + b * (size_t)((cap + 15) & ~7);   // 16-byte aligned slabs (kpfx is 32-bit)
-    keep = P.g_keep + b * (size_t)(cap / 32 + 2);
-  } else {
-    ent = (unsigned long long *)(smem_raw + L.ent);
-    rec = (AnchorRec *)(smem_raw + L.rec);
-    order16 = (uint16_t *)(smem_raw + L.order);
-    keep = (uint32_t *)(smem_raw + L.keep);
-  }
+  const size_t slab = (size_t)blockIdx.x;
+  // 16-byte aligned slabs (kpfx is 32-bit)
+  unsigned long long *const ent = glob ? P.g_ent + slab * (size_t)(cap + 1) : (unsigned long long *)(smem_raw + L.ent);
+  AnchorRec *const rec = glob ? P.g_rec + slab * (size_t)(cap + 1) : (AnchorRec *)(smem_raw + L.rec);
+  uint16_t *const order16 = glob ? P.g_order + slab * (size_t)((cap + 15) & ~7) : (uint16_t *)(smem_raw + L.order);
+  uint32_t *const keep = glob ? P.g_keep + slab * (size_t)(cap / 32 + 2) : (uint32_t *)(smem_raw + L.keep);
   uint32_t *kpfx = (uint32_t *)order16;   // compaction offsets; the pop order is written later
   const int bm_words = 1 << (P.bm_log2 - 5);
   const SeedTable &S = P.S;
@@ -785,20 +795,25 @@ __global__ void __launch_bounds__(SCAN_CTA_MAX_THREADS, 2) scan_cta_kernel(const
   const int mkp = M.colour_space ? 1 : 0;
   const uint32_t rmask = (1u << M.region_bits) - 1u;
   const bool filt = M.use_region_counts != 0;
+  const bool hashed = P.bm_hashed != 0;   // hashed bitmaps (one partition): false positives only add candidates
   const uint32_t lt = (1u << lane) - 1u;
   const int glog = P.lanes_per_list_log2, g = 1 << glog, lpw = 32 >> glog, gl = lane & (g - 1);
 
+  long long prof_t = clock64();
+  if (tid == 0) s_item_next = atomicAdd(P.work_counter, 1u);
   for (;;) {
     __syncthreads();
+    PROF_MARK(15);
+    const uint32_t item = s_item_next;
+    __syncthreads();
+    if (item >= P.n_work) break;
     if (tid == 0) {
-      s_item = atomicAdd(P.work_counter, 1u);
       s_total = 0;
       s_ns = 0;
       s_cnt = 0;
     }
-    __syncthreads();
-    const uint32_t item = s_item;
-    if (item >= P.n_work) break;
+    // the next strand's ticket travels while this one is processed (the last warp waits for it at its next barrier)
+    if (tid == nthr - 1) s_item_next = atomicAdd(P.work_counter, 1u);
     const uint32_t rs = P.resume ? P.tie_rec[item].x : P.work ? P.work[item] : item;
     const int r = (int)(rs >> 1);
     const int rl = P.read_len[r];
@@ -819,6 +834,7 @@ __global__ void __launch_bounds__(SCAN_CTA_MAX_THREADS, 2) scan_cta_kernel(const
       esrc = P.tie_ent + tr.y;
       order = P.tie_order + tr.y;
     } else {
+    PROF_MARK(0);
     // ---- 1. recode, project, bucket bounds ----------------------------------------------------------------
     const int nw2 = (rl + 15) / 16;
     for (int w = tid; w < nw2 + 3; w += nthr) {
@@ -829,13 +845,12 @@ __global__ void __launch_bounds__(SCAN_CTA_MAX_THREADS, 2) scan_cta_kernel(const
       }
       r2[w] = v;
     }
-    int kbase[SHRIMP_MAX_SEEDS + 1];
     int K = 0;
     for (int sn = 0; sn < S.n_seeds; sn++) {
-      kbase[sn] = K;
+      if (tid == 0) kbase[sn] = K;   // shared: the previous strand's readers passed the barrier at the loop top
       K += n_kmers_of(S, sn, rl, mkp);
     }
-    kbase[S.n_seeds] = K;
+    if (tid == 0) kbase[S.n_seeds] = K;
     if (K > P.k_cap || S.n_seeds * max_n_kmers > P.k_cap) {
       if (tid == 0) atomicOr(P.status, 2u);
       continue;
@@ -861,6 +876,7 @@ __global__ void __launch_bounds__(SCAN_CTA_MAX_THREADS, 2) scan_cta_kernel(const
     __syncthreads();
     const uint32_t total = s_total;
     if (total == 0) continue;
+    PROF_MARK(1);
     // cut every list at the partition boundaries
     if (n_part > 1) {
       const int nc = n_part - 1;
@@ -881,120 +897,135 @@ __global__ void __launch_bounds__(SCAN_CTA_MAX_THREADS, 2) scan_cta_kernel(const
       __syncthreads();
     }
 
-    // ---- 2./3. per partition: pass A marks the regions, pass B keeps the entries of regions marked twice ----
+    PROF_MARK(2);
+    // ---- 2./3. per partition: the list entries are staged in shared memory (asynchronous 4-byte copies, several
+    // lists per warp), then pass A marks the regions and pass B keeps the entries of regions marked twice as flat
+    // loops over the staged window.  A partition with more entries than the window is staged window by window,
+    // twice (the second time from L2).
     for (int part = 0; part < n_part; part++) {
       const uint32_t R0 = (uint32_t)part << P.bm_log2;
       const uint32_t Rlast = R0 + ((1u << P.bm_log2) - 1u);
-      if (filt) {
-        for (int w = tid; w < bm_words; w += nthr) {
-          bm1[w] = 0u;
-          bm2[w] = 0u;
-        }
-        if (tid == 0) s_next = 0;
-        __syncthreads();
-        for (;;) {
-          // a warp takes 32/g lists at a time, g lanes per list (g = P.lanes_per_list: short lists share a warp)
-          uint32_t kk = 0;
-          if (lane == 0) kk = atomicAdd(&s_next, (uint32_t)lpw);
-          kk = __shfl_sync(0xffffffffu, kk, 0);
-          if (kk >= (uint32_t)K) break;
-          kk += (uint32_t)(lane >> glog);
+      // sub-range of every list in this partition and the prefix sums of their lengths
+      if (wid == 0) {
+        uint32_t run = 0;
+        for (int k0 = 0; k0 < K; k0 += 32) {
+          const int kk = k0 + lane;
           uint32_t a = 0, b = 0;
-          const uint32_t *p = nullptr;
-          if (kk < (uint32_t)K) {
+          if (kk < K) {
             b = klen[kk];
             if (n_part > 1) {
               if (part > 0) a = cuts[kk * (n_part - 1) + part - 1];
               if (part < n_part - 1) b = cuts[kk * (n_part - 1) + part];
             }
-            int sn = 0;
-            while ((int)kk >= kbase[sn + 1]) sn++;
-            p = P.I.pos[sn] + kst[kk];
+            if (b < a) b = a;
           }
-          if (b < a) b = a;
-          const uint32_t steps = __reduce_max_sync(0xffffffffu, (b - a + (uint32_t)(4 * g) - 1u) / (uint32_t)(4 * g));
-          for (uint32_t it = 0; it < steps; it++) {
-            const uint32_t base = a + it * (uint32_t)(4 * g) + (uint32_t)gl;
-            uint32_t x[4];
-            bool ok[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-              const uint32_t i = base + (uint32_t)(u * g);
-              ok[u] = i < b;
-              x[u] = ok[u] ? __ldg(p + i) : 0u;
+          const uint32_t len = b - a;
+          const uint32_t inc = (uint32_t)warp_incl_scan((int)len, lane);
+          if (kk < K) {
+            kA[kk] = a;
+            kpre[kk] = run + inc - len;
+          }
+          run += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (lane == 0) kpre[K] = run;
+      }
+      if (filt)
+        for (int w = tid; w < bm_words; w += nthr) {
+          bm1[w] = 0u;
+          bm2[w] = 0u;
+        }
+      __syncthreads();
+      const uint32_t total_p = kpre[K];
+      if (total_p == 0) continue;
+      const bool one_window = total_p <= (uint32_t)win;
+      for (int pass = filt ? 0 : 1; pass < 2; pass++) {
+        for (uint32_t w0 = 0; w0 < total_p; w0 += (uint32_t)win) {
+          const uint32_t w1 = min(w0 + (uint32_t)win, total_p), n = w1 - w0;
+          if (!(pass == 1 && one_window && filt)) {
+            // ---- stage the window: lists [klo, ...) whose flat range meets [w0, w1)
+            int klo = 0;
+            if (w0 > 0) {
+              int hi = K;  // kpre[klo] <= w0 < kpre[hi]
+              while (hi - klo > 1) {
+                const int mid = (klo + hi) >> 1;
+                if (kpre[mid] <= w0) klo = mid; else hi = mid;
+              }
             }
-#pragma unroll
-            for (int u = 0; u < 4; u++)
-              if (ok[u]) {
-                const uint32_t idx = (x[u] >> M.region_bits) - R0;
-                const uint32_t bit = 1u << (idx & 31);
-                const uint32_t old = atomicOr(&bm1[idx >> 5], bit);
-                if (old & bit) atomicOr(&bm2[idx >> 5], bit);
-                if ((x[u] & rmask) < (uint32_t)M.region_overlap && idx > 0) {
-                  const uint32_t bit2 = 1u << ((idx - 1) & 31);
-                  const uint32_t old2 = atomicOr(&bm1[(idx - 1) >> 5], bit2);
-                  if (old2 & bit2) atomicOr(&bm2[(idx - 1) >> 5], bit2);
+            __syncthreads();   // the previous window's readers are done with buf
+            if (tid == 0) s_next = (uint32_t)klo;
+            __syncthreads();
+            for (;;) {
+              uint32_t kk = 0;
+              if (lane == 0) kk = atomicAdd(&s_next, (uint32_t)lpw);
+              kk = __shfl_sync(0xffffffffu, kk, 0);
+              if (kk >= (uint32_t)K || kpre[kk] >= w1) break;
+              kk += (uint32_t)(lane >> glog);
+              if (kk >= (uint32_t)K) continue;
+              const uint32_t f0 = kpre[kk], lo = max(f0, w0), hi = min(kpre[kk + 1], w1);
+              if (lo >= hi) continue;
+              int sn = 0;
+              while ((int)kk >= kbase[sn + 1]) sn++;
+              const uint32_t *p = P.I.pos[sn] + kst[kk] + kA[kk];
+              const uint16_t slot = (uint16_t)(sn * max_n_kmers + ((int)kk - kbase[sn]));
+              for (uint32_t f = lo + (uint32_t)gl; f < hi; f += (uint32_t)g) {
+                const uint32_t d = f - w0;
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(buf + d);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst), "l"(p + (f - f0)) : "memory");
+                bslot[d] = slot;
+              }
+            }
+            asm volatile("cp.async.wait_all;\n" ::: "memory");
+            __syncthreads();
+          }
+          if (pass == 0) {
+            // ---- pass A: mark
+            for (uint32_t t = tid; t < n; t += nthr) {
+              const uint32_t x = buf[t];
+              const uint32_t region = x >> M.region_bits;
+              const uint32_t idx = hashed ? region_hash(region, P.bm_log2) : region - R0;
+              const uint32_t bit = 1u << (idx & 31);
+              const uint32_t old = atomicOr(&bm1[idx >> 5], bit);
+              if (old & bit) atomicOr(&bm2[idx >> 5], bit);
+              if ((x & rmask) < (uint32_t)M.region_overlap && (hashed ? region > 0 : idx > 0)) {
+                const uint32_t idx2 = hashed ? region_hash(region - 1, P.bm_log2) : idx - 1;
+                const uint32_t bit2 = 1u << (idx2 & 31);
+                const uint32_t old2 = atomicOr(&bm1[idx2 >> 5], bit2);
+                if (old2 & bit2) atomicOr(&bm2[idx2 >> 5], bit2);
+              }
+            }
+          } else {
+            // ---- pass B: keep
+            for (uint32_t t0 = 0; t0 < n; t0 += nthr) {
+              const uint32_t t = t0 + tid;
+              bool kp = t < n;
+              uint32_t x = 0;
+              if (kp) {
+                x = buf[t];
+                if (filt) {
+                  const uint32_t region = x >> M.region_bits;
+                  const uint32_t idx = hashed ? region_hash(region, P.bm_log2) : region - R0;
+                  kp = ((bm2[idx >> 5] >> (idx & 31)) & 1u) != 0;
+                  if (!kp && (x & rmask) < (uint32_t)M.region_overlap && (hashed ? region > 0 : idx > 0)) {
+                    const uint32_t idx2 = hashed ? region_hash(region - 1, P.bm_log2) : idx - 1;
+                    kp = ((bm2[idx2 >> 5] >> (idx2 & 31)) & 1u) != 0;
+                  }
+                  // marks across a partition cut are not seen here: keep, the neighbour test decides
+                  if (!kp && n_part > 1 && ((part > 0 && region == R0) || (part < n_part - 1 && region == Rlast))) kp = true;
                 }
               }
-          }
-        }
-        __syncthreads();
-      }
-      if (tid == 0) s_next = 0;
-      __syncthreads();
-      for (;;) {
-        uint32_t kk = 0;
-        if (lane == 0) kk = atomicAdd(&s_next, (uint32_t)lpw);
-        kk = __shfl_sync(0xffffffffu, kk, 0);
-        if (kk >= (uint32_t)K) break;
-        kk += (uint32_t)(lane >> glog);
-        uint32_t a = 0, b = 0, slot = 0;
-        const uint32_t *p = nullptr;
-        if (kk < (uint32_t)K) {
-          b = klen[kk];
-          if (n_part > 1) {
-            if (part > 0) a = cuts[kk * (n_part - 1) + part - 1];
-            if (part < n_part - 1) b = cuts[kk * (n_part - 1) + part];
-          }
-          int sn = 0;
-          while ((int)kk >= kbase[sn + 1]) sn++;
-          p = P.I.pos[sn] + kst[kk];
-          slot = (uint32_t)(sn * max_n_kmers + ((int)kk - kbase[sn]));
-        }
-        if (b < a) b = a;
-        const uint32_t steps = __reduce_max_sync(0xffffffffu, (b - a + (uint32_t)(4 * g) - 1u) / (uint32_t)(4 * g));
-        for (uint32_t it = 0; it < steps; it++) {
-          const uint32_t base = a + it * (uint32_t)(4 * g) + (uint32_t)gl;
-          uint32_t x[4];
-          bool ok[4];
-#pragma unroll
-          for (int u = 0; u < 4; u++) {
-            const uint32_t i = base + (uint32_t)(u * g);
-            ok[u] = i < b;
-            x[u] = ok[u] ? __ldg(p + i) : 0u;
-          }
-#pragma unroll
-          for (int u = 0; u < 4; u++) {
-            bool kp = ok[u];
-            if (kp && filt) {
-              const uint32_t region = x[u] >> M.region_bits, idx = region - R0;
-              kp = ((bm2[idx >> 5] >> (idx & 31)) & 1u) != 0;
-              if (!kp && (x[u] & rmask) < (uint32_t)M.region_overlap && idx > 0)
-                kp = ((bm2[(idx - 1) >> 5] >> ((idx - 1) & 31)) & 1u) != 0;
-              // marks across a partition cut are not seen here: keep, the neighbour test decides
-              if (!kp && n_part > 1 && ((part > 0 && region == R0) || (part < n_part - 1 && region == Rlast))) kp = true;
-            }
-            const uint32_t bal = __ballot_sync(0xffffffffu, kp);
-            if (bal) {
-              uint32_t at = 0;
-              if (lane == 0) at = atomicAdd(&s_ns, (uint32_t)__popc(bal));
-              at = __shfl_sync(0xffffffffu, at, 0) + (uint32_t)__popc(bal & lt);
-              if (kp && at < (uint32_t)cap) ent[at] = ((unsigned long long)x[u] << 32) | slot;
+              const uint32_t bal = __ballot_sync(0xffffffffu, kp);
+              if (bal) {
+                uint32_t at = 0;
+                if (lane == 0) at = atomicAdd(&s_ns, (uint32_t)__popc(bal));
+                at = __shfl_sync(0xffffffffu, at, 0) + (uint32_t)__popc(bal & lt);
+                if (kp && at < (uint32_t)cap) ent[at] = ((unsigned long long)x << 32) | bslot[t];
+              }
             }
           }
         }
+        __syncthreads();   // all marks are in before pass B tests them
+        PROF_MARK(3 + pass);
       }
-      __syncthreads();
     }
     const int ns = (int)s_ns;
     if (ns > cap) {
@@ -1028,6 +1059,7 @@ __global__ void __launch_bounds__(SCAN_CTA_MAX_THREADS, 2) scan_cta_kernel(const
         __syncthreads();
       }
     }
+    PROF_MARK(5);
     // ---- 4b. region filter (RG_HAS_2 as a neighbour test) + ordered compaction ----------------------------
     m_surv = ns;
     if (filt) {
@@ -1090,6 +1122,7 @@ __global__ void __launch_bounds__(SCAN_CTA_MAX_THREADS, 2) scan_cta_kernel(const
     if (m_surv == 0) continue;
     __syncthreads();
 
+    PROF_MARK(6);
     // ---- 5. equal position on different read offsets -> replay the reference's heap (thread 0) -------------
     bool tie = false;
     for (int t = tid; t + 1 < m_surv; t += nthr) {
@@ -1122,6 +1155,7 @@ __global__ void __launch_bounds__(SCAN_CTA_MAX_THREADS, 2) scan_cta_kernel(const
     }
     }  // !P.resume
 
+    PROF_MARK(7);
     // ---- 6. anchors in pop order; colinear collapse (:941-971) in warp lockstep ---------------------------
     for (int t = tid; t < m_surv; t += nthr) {
       const unsigned long long e = esrc[order ? order[t] : t];
@@ -1137,6 +1171,7 @@ __global__ void __launch_bounds__(SCAN_CTA_MAX_THREADS, 2) scan_cta_kernel(const
     }
     for (int t = tid; t < rl; t += nthr) cache[t] = -1;
     __syncthreads();
+    PROF_MARK(8);
     if (wid == 0) {
       int n_anch = 0;
       for (int t0 = 0; t0 < m_surv; t0 += 32) {
@@ -1199,6 +1234,7 @@ __global__ void __launch_bounds__(SCAN_CTA_MAX_THREADS, 2) scan_cta_kernel(const
     __syncthreads();
     const int n_anch = s_nanch;
 
+    PROF_MARK(9);
     // ---- 7. hit list: chain search on all threads, then ordered emission ------------------------------------
     const int window_len = (int)(unsigned short)abs_or_pct_d(M.window_len, M.window_len_frac, (double)rl);
     {
@@ -1213,6 +1249,7 @@ __global__ void __launch_bounds__(SCAN_CTA_MAX_THREADS, 2) scan_cta_kernel(const
       if (lane == 0 && mine) atomicAdd(&s_cnt, (uint32_t)mine);
     }
     __syncthreads();
+    PROF_MARK(10);
     const int nh = (int)s_cnt;
     if (tid == 0) {
       atomicAdd(&P.stats[3], (uint32_t)n_anch);
@@ -1255,6 +1292,7 @@ __global__ void __launch_bounds__(SCAN_CTA_MAX_THREADS, 2) scan_cta_kernel(const
       hit_sort_serial(P.hits + out0, nh);
       P.rs_range[rs] = make_uint2(out0, (uint32_t)nh);
     }
+    PROF_MARK(11);
   }
 }
 
@@ -1367,8 +1405,8 @@ int launch_scan_replay(shrimp_gpu_ctx *ctx, ScanParams &P, uint32_t n_rec, int k
   return SHRIMP_OK;
 }
 
-size_t scan_cta_smem_bytes(int cap, int max_rl, int k_cap, int bm_log2, int n_part, bool global_arrays) {
-  return cta_layout(cap, max_rl, k_cap, bm_log2, n_part, global_arrays).total;
+size_t scan_cta_smem_bytes(int cap, int max_rl, int k_cap, int bm_log2, int n_part, int win, bool global_arrays) {
+  return cta_layout(cap, max_rl, k_cap, bm_log2, n_part, win, global_arrays).total;
 }
 
 int launch_scan(shrimp_gpu_ctx *ctx, ScanParams &P, int warps_per_cta, int n_ctas) {
@@ -1381,9 +1419,14 @@ int launch_scan(shrimp_gpu_ctx *ctx, ScanParams &P, int warps_per_cta, int n_cta
 }
 
 int launch_scan_cta(shrimp_gpu_ctx *ctx, ScanParams &P, int n_ctas, int threads) {
-  const size_t smem = scan_cta_smem_bytes(P.cap, P.max_rl, P.k_cap, P.bm_log2, P.n_part, P.g_ent != nullptr);
-  SH_CUDA(cudaFuncSetAttribute(scan_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  scan_cta_kernel<<<n_ctas, threads, smem, ctx->stream>>>(P);
+  const size_t smem = scan_cta_smem_bytes(P.cap, P.max_rl, P.k_cap, P.bm_log2, P.n_part, P.win, P.g_ent != nullptr);
+  if (P.g_ent) {
+    SH_CUDA(cudaFuncSetAttribute(scan_cta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    scan_cta_kernel<true><<<n_ctas, threads, smem, ctx->stream>>>(P);
+  } else {
+    SH_CUDA(cudaFuncSetAttribute(scan_cta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    scan_cta_kernel<false><<<n_ctas, threads, smem, ctx->stream>>>(P);
+  }
   SH_CUDA(cudaGetLastError());
   SH_LAUNCHED(ctx, ST_SCAN);
   return SHRIMP_OK;

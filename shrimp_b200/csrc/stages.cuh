@@ -61,6 +61,9 @@ struct ScanParams {
   uint32_t *tie_used, *n_tie;    // atomic cursors
   uint32_t tie_cap, tie_rec_cap;
   int resume, resume_min;        // resume launch: strands with resume_min < candidates <= cap
+  unsigned long long *prof;      // optional phase cycle counters [16] (SHRIMP_SCAN_PROF)
+  int bm_hashed;                 // CTA kernel: hashed region bitmaps (one partition) instead of exact partitions
+  int win;                       // entries of the shared-memory staging window
   int lanes_per_list_log2; // lanes that share one index list (2..5): short lists are streamed several per warp
 };
 
