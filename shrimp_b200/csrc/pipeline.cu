@@ -454,7 +454,7 @@ int chunk_scan(Chunk &C) {
       // exact bitmaps (one bit per 2 kb region, partitions of at most 2^18 regions) unless they would be far
       // larger than the strand's entries call for: then hashed bitmaps of >= 8 bits per expected entry, whose
       // false candidates the exact neighbour test removes
-      cta_hashed = (double)(1u << exact_log2) > 16.0 * std::max(est, 64.0);
+      cta_hashed = (double)(1u << exact_log2) > 16.0 * std::max(est, 64.0) && 8.0 * est <= (double)(1u << 17);
       if (const char *e = getenv("SHRIMP_SCAN_HASHED")) cta_hashed = atoi(e) != 0;
       int bm_max = 18;
       if (const char *e = getenv("SHRIMP_SCAN_BM_LOG2")) {  // test hook
@@ -515,6 +515,7 @@ int chunk_scan(Chunk &C) {
     P.n_overflow = cnt + 1;
     P.status = cnt + 2;
     P.stats = cnt + 8;
+    P.stats64 = (unsigned long long *)(cnt + 40);
     P.k_max = k_max;
     P.max_rl = max_rl;
     uint32_t h3[3] = {0, 0, 0};
@@ -921,9 +922,9 @@ int chunk_fetch_full(Chunk &C, int n_slots, bool with_nsel) {
 void chunk_stats(const Chunk &C, const uint32_t *hc, shrimp_map_stats *stats) {
   if (!stats) return;
   stats->heap_replays = hc[8 + 0];
-  stats->list_entries = hc[8 + 1];
-  stats->surviving_entries = hc[8 + 2];
-  stats->anchors = hc[8 + 3];
+  stats->list_entries = *(const unsigned long long *)(hc + 40);
+  stats->surviving_entries = *(const unsigned long long *)(hc + 42);
+  stats->anchors = *(const unsigned long long *)(hc + 44);
   stats->hits = C.hits_used;
   stats->vector_tasks = hc[20];
   stats->device_vector_cells = *(const unsigned long long *)(hc + 22);

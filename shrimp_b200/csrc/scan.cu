@@ -318,8 +318,8 @@ __device__ void scan_tail(const ScanParams &P, uint32_t rs, int r, int rl, int m
     m_surv = outn;
   }
   if (lane == 0) {
-    atomicAdd(&P.stats[1], (uint32_t)gathered);
-    atomicAdd(&P.stats[2], (uint32_t)m_surv);
+    atomicAdd(&P.stats64[0], (unsigned long long)gathered);
+    atomicAdd(&P.stats64[1], (unsigned long long)m_surv);
   }
   if (m_surv == 0) return;
 
@@ -458,7 +458,7 @@ __device__ void scan_tail(const ScanParams &P, uint32_t rs, int r, int rl, int m
     nh += __popc(__ballot_sync(0xffffffffu, emit));
   }
   __syncwarp();
-  if (lane == 0) atomicAdd(&P.stats[3], (uint32_t)n_anch);
+  if (lane == 0) atomicAdd(&P.stats64[2], (unsigned long long)n_anch);
   if (nh == 0) return;
   uint32_t out0 = 0;
   if (lane == 0) out0 = atomicAdd(P.hits_used, (uint32_t)nh);
@@ -679,7 +679,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) scan_kernel(const ScanParams 
       continue;
     }
     if (ns == 0) {
-      if (lane == 0) atomicAdd(&P.stats[1], total);
+      if (lane == 0) atomicAdd(&P.stats64[0], (unsigned long long)total);
       continue;
     }
     int Pn = 32;
@@ -1036,7 +1036,7 @@ __global__ void __launch_bounds__(SCAN_CTA_MAX_THREADS, 2) scan_cta_kernel(const
       continue;
     }
     if (ns == 0) {
-      if (tid == 0) atomicAdd(&P.stats[1], total);
+      if (tid == 0) atomicAdd(&P.stats64[0], (unsigned long long)total);
       continue;
     }
     // ---- 4a. CTA bitonic sort by position -------------------------------------------------------------------
@@ -1116,8 +1116,8 @@ __global__ void __launch_bounds__(SCAN_CTA_MAX_THREADS, 2) scan_cta_kernel(const
       if (tid == 0) s_cnt = 0;
     }
     if (tid == 0) {
-      atomicAdd(&P.stats[1], total);
-      atomicAdd(&P.stats[2], (uint32_t)m_surv);
+      atomicAdd(&P.stats64[0], (unsigned long long)total);
+      atomicAdd(&P.stats64[1], (unsigned long long)m_surv);
     }
     if (m_surv == 0) continue;
     __syncthreads();
@@ -1252,7 +1252,7 @@ __global__ void __launch_bounds__(SCAN_CTA_MAX_THREADS, 2) scan_cta_kernel(const
     PROF_MARK(10);
     const int nh = (int)s_cnt;
     if (tid == 0) {
-      atomicAdd(&P.stats[3], (uint32_t)n_anch);
+      atomicAdd(&P.stats64[2], (unsigned long long)n_anch);
       uint32_t o = 0;
       if (nh > 0) {
         o = atomicAdd(P.hits_used, (uint32_t)nh);

@@ -35,7 +35,8 @@ struct ScanParams {
   uint32_t *overflow;      // list of read strands that did not fit `cap`
   uint32_t *n_overflow;
   uint32_t *status;        // bit 0: hits_cap exhausted, bit 1: slab exhausted in the overflow pass
-  uint32_t *stats;         // [0] heap replays, [1] gathered entries, [2] surviving entries, [3] anchors
+  uint32_t *stats;         // [0] heap replays
+  unsigned long long *stats64;   // [0] gathered entries, [1] surviving entries, [2] anchors
   // per-warp global scratch for the heap replay: [n_warps][scratch_ints]
   int32_t *scratch;
   int scratch_ints;
