@@ -414,10 +414,8 @@ def main():
     clocks = clk.summary()
     stage = ctx.stage_times()
     total_ms = float(sum(step_ms))
-    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms_max = float(t.item())
+    from shrimp_b200 import shard
+    total_ms_max = shard.max_over_ranks(total_ms, world, device="cuda")   # the slowest rank's timed region
     value = world * n_reads * a.steps / (total_ms_max * 1e-3)
 
     # ---- end to end through the public API: pinned host buffers in, hits out -----------------------
@@ -461,10 +459,7 @@ def main():
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     h2d, d2h = ctx.last_transfer_bytes()
-    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_val = world * n_reads * a.steps / float(t.item())
+    e2e_val = world * n_reads * a.steps / shard.max_over_ranks(e2e_s, world, device="cuda")
 
     if rank != 0:
         if world > 1:
