@@ -172,7 +172,7 @@ typedef struct shrimp_map_params {
   double sw_vect_threshold;     /* -v */
   double sw_full_threshold;     /* -h */
   double score_alpha, score_beta; /* gmapper.c:2559-2568, used by hit_run_post_sw */
-  int32_t match_mode;           /* -n: 1 or 2 (unpaired) */
+  int32_t match_mode;           /* -n: 1 or 2 (unpaired); 2, 3 or 4 (pairs, default 4) */
   int32_t num_outputs;          /* -o */
   int32_t num_tmp_outputs;      /* 20 + num_outputs */
   int32_t gapless;              /* -U / mirna: sw_gapless instead of sw_vector */
@@ -239,11 +239,12 @@ int shrimp_gpu_map_reads(shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, int n
 
 /* ------------------------------------------------------------------------------------------
  * Chunk-level mapping of read pairs.  Replaces handle_readpair (gmapper/mapping.c:2504-2650) for a chunk
- * of pairs with the default paired option set of gmapper.c:2638-2714 (mp->match_mode = 4, half-paired):
- * readpair_compute_mp_ranges :2317, per-read region counts / anchors / hit lists as for unpaired reads in
- * match mode 2, readpair_pair_up_hits :266, read_pass1 with only_paired :1261, readpair_get_vector_hits
+ * of pairs with the paired option sets of gmapper.c:2638-2714: mp->match_mode 4 (default), 3 or 2, with or without
+ * half-pairing.  readpair_compute_mp_ranges :2317; per-read region counts; for -n 3 and for --no-half-paired the
+ * mate-pair region counts (read_get_mp_region_counts :546, the paired rules of advance_index_in_genomemap :667-728,
+ * hit-list mode 3 :1082-1094); anchors / hit lists; readpair_pair_up_hits :266, read_pass1 with only_paired :1261, readpair_get_vector_hits
  * :1877, readpair_pass2 :2181 (hit_run_full_sw at half the full threshold, readpair_remove_duplicate_hits,
- * ranking), then the half-paired fall-back into handle_read :1773 for both mates (pass 1 + pass 2).
+ * ranking), then (half_paired) the half-paired fall-back into handle_read :1773 for both mates (pass 1 + pass 2).
  * reads rows 2k and 2k+1 are the mates of pair k (gmapper -1 / -2).  What readpair_output
  * (gmapper/output.c:1071) would receive comes back as:
  *   pairs[]  final_paired_hits in pair order, each naming its two shrimp_hit records (mate 0, mate 1);
@@ -253,7 +254,7 @@ int shrimp_gpu_map_reads(shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, int n
 typedef struct shrimp_pair_params {
   int32_t pair_mode;            /* 1 opp-in, 2 opp-out, 3 col-fw, 4 col-bw (gmapper-definitions.h:42-47) */
   int32_t min_insert_size, max_insert_size;   /* -I */
-  int32_t half_paired;          /* must be 1 (the default) for now */
+  int32_t half_paired;          /* 1 (default) / 0 = --no-half-paired */
 } shrimp_pair_params;
 
 typedef struct shrimp_pair {    /* struct read_hit_pair, gmapper-definitions.h:155-165 */

@@ -82,11 +82,12 @@ __device__ __forceinline__ void make_full_task(const FullBuildParams &P, int r, 
 #define RING_CLASSES 4
 
 struct Pipeline {
-  DevBuf d_in, d_reads, d_read_len, d_initbp, d_hits, d_rs_range, d_counters, d_overflow, d_overflow2, d_scan_slab, d_tie_ent, d_tie_order, d_tie_rec, d_prof, d_scratch;
+  DevBuf d_in, d_reads, d_read_len, d_initbp, d_hits, d_rs_range, d_counters, d_overflow, d_overflow2, d_scan_slab, d_tie_ent, d_tie_order, d_tie_rec, d_prof, d_mp_tab, d_mp_epoch, d_scratch;
   DevBuf d_task[2], d_vtrue[2], d_slot, d_writer, d_sel, d_nsel;
   DevBuf d_ftasks, d_finfo, d_fresults, d_frow, d_fbp[RING_CLASSES + 1], d_fops, d_taskoff, d_scan_tmp, d_perm;
   HostBuf h_info, h_results, h_ops, h_nsel, h_hits, h_range;
   uint32_t hits_cap = 0, tie_cap = 0;
+  size_t mp_tab_ints = 0;   // size the region tables were zeroed for
   // reads left resident by the last upload (shrimp_gpu_map_resident)
   int res_n_reads = 0, res_stride = 0;
   std::vector<int32_t> res_read_len;
@@ -125,6 +126,8 @@ struct Chunk {
   uint32_t scan_big = 0;               // read strands that went through scan_cta_kernel
   uint32_t scan_global = 0;            // ... of which with their candidate arrays in global slabs
   int n_ori = 1;
+  // paired option sets that look at the mate's region counts (pairs.cu sets these; 0 = off)
+  int mp_mode = 0, pair_mode = 0, min_insert = 0, max_insert = 0;
   size_t ops_stride = 0;
 };
 

@@ -309,18 +309,23 @@ static int map_pairs_impl(shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, cons
     set_error("%s: pair_mode must be 1 (opp-in) .. 4 (col-bw)", who);
     return SHRIMP_E_ARG;
   }
-  if (mp && (mp->match_mode != 4 || !pp->half_paired)) {
-    // match modes 3 and 4 without half-paired need the mate-pair region counts (read_get_mp_region_counts,
-    // mapping.c:546-608), which are not on the device yet
-    set_error("%s: only the default paired option set is supported (match_mode 4, half-paired)", who);
+  if (mp && (mp->match_mode < 2 || mp->match_mode > 4)) {
+    set_error("%s: paired match_mode must be 2, 3 or 4 (gmapper.c:2495-2499)", who);
     return SHRIMP_E_ARG;
   }
   Chunk C;
   SH_TRY(chunk_begin(C, ctx, mp, 2 * n_pairs, reads, stride, read_len, initbp, resident, who));
-  // per-read options of the paired set (gmapper.c:2652-2677)
-  C.M.match_mode = 2;
-  C.M.min_matches = 2;
-  C.M.use_region_counts = mp->use_regions ? 1 : 0;
+  // per-read options of the paired set (gmapper.c:2652-2677): region counts unless -n 2; the mate-pair region
+  // counts by match mode and half-pairing; hit-list mode 2 / 3 / 1 and pass-1 min_matches 2 / 1 / 1 for -n 4 / 3 / 2
+  const int pmm = mp->match_mode;
+  C.M.match_mode = pmm == 4 ? 2 : pmm == 3 ? 3 : 1;
+  C.M.min_matches = pmm == 4 ? 2 : 1;
+  C.M.use_region_counts = (mp->use_regions && pmm != 2) ? 1 : 0;
+  C.mp_mode = !mp->use_regions ? 0 : (pmm == 4 && !pp->half_paired) ? 1 : (pmm == 3 && pp->half_paired) ? 2 :
+              (pmm == 3 && !pp->half_paired) ? 3 : 0;
+  C.pair_mode = pp->pair_mode;
+  C.min_insert = pp->min_insert_size;
+  C.max_insert = pp->max_insert_size;
   const int n_reads = C.n_reads;
   read_len = C.read_len;
   *n_hits = 0;
@@ -534,23 +539,27 @@ static int map_pairs_impl(shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, cons
   uint32_t cntA[64];
   memcpy(cntA, (const char *)pl->h_nsel.p + (size_t)n_reads * 4, sizeof(cntA));
 
-  // ---- half-paired fall-back: handle_read for every mate, pass 1 + pass 2 only (gmapper.c:2694-2714) ----
-  SH_CUDA(cudaMemcpyAsync(pl->d_saved.p, saved, HU, cudaMemcpyHostToDevice, st));
-  pl->h2d_bytes += HU;
-  {
-    ScopedStage ss(ctx, ST_PASS1);
-    Pass1Params P1 = chunk_pass1_params(C);
-    P1.saved = pl->d_saved.as<uint8_t>();
-    SH_TRY(launch_pass1_replay(ctx, P1));
-    SH_TRY(launch_select_unpaired(ctx, P1));
-  }
-  int n_slots_b = 0;
-  SH_TRY(chunk_full_tasks_unpaired(C, mp->sw_full_threshold, &n_slots_b));
-  SH_TRY(chunk_run_full(C, n_slots_b));
-  SH_TRY(chunk_fetch_full(C, n_slots_b, true));
   const uint32_t *h_cnt = (const uint32_t *)((char *)pl->h_nsel.p + (size_t)n_reads * 4);
-  const int32_t *NSEL = pl->h_nsel.as<int32_t>();
-  SH_TRY(host_pass2_all(C, NSEL, mp->sw_full_threshold, O, n_unpaired_per_read));
+  if (pp->half_paired) {
+    // ---- half-paired fall-back: handle_read for every mate, pass 1 + pass 2 only (gmapper.c:2694-2714;
+    // stop_threshold 101 % means no pair ever stops it, :2686-2687) ----
+    SH_CUDA(cudaMemcpyAsync(pl->d_saved.p, saved, HU, cudaMemcpyHostToDevice, st));
+    pl->h2d_bytes += HU;
+    {
+      ScopedStage ss(ctx, ST_PASS1);
+      Pass1Params P1 = chunk_pass1_params(C);
+      P1.M.min_matches = 2;   // unpaired_mapping_options[.][0].pass1.min_matches, gmapper.c:2705
+      P1.saved = pl->d_saved.as<uint8_t>();
+      SH_TRY(launch_pass1_replay(ctx, P1));
+      SH_TRY(launch_select_unpaired(ctx, P1));
+    }
+    int n_slots_b = 0;
+    SH_TRY(chunk_full_tasks_unpaired(C, mp->sw_full_threshold, &n_slots_b));
+    SH_TRY(chunk_run_full(C, n_slots_b));
+    SH_TRY(chunk_fetch_full(C, n_slots_b, true));
+    const int32_t *NSEL = pl->h_nsel.as<int32_t>();
+    SH_TRY(host_pass2_all(C, NSEL, mp->sw_full_threshold, O, n_unpaired_per_read));
+  }
   *n_hits = O.n_out;
   if (edits_used) *edits_used = O.e_used;
   if (stats) {

@@ -113,7 +113,7 @@ void free_pipeline(shrimp_gpu_ctx *ctx) {
   Pipeline *p = (Pipeline *)ctx->pipeline;
   if (!p) return;
   DevBuf *bufs[] = {&p->d_in, &p->d_reads, &p->d_read_len, &p->d_initbp, &p->d_hits, &p->d_rs_range, &p->d_counters,
-                    &p->d_overflow, &p->d_overflow2, &p->d_scan_slab, &p->d_tie_ent, &p->d_tie_order, &p->d_tie_rec, &p->d_prof, &p->d_scratch, &p->d_task[0], &p->d_task[1], &p->d_vtrue[0], &p->d_vtrue[1],
+                    &p->d_overflow, &p->d_overflow2, &p->d_scan_slab, &p->d_tie_ent, &p->d_tie_order, &p->d_tie_rec, &p->d_prof, &p->d_mp_tab, &p->d_mp_epoch, &p->d_scratch, &p->d_task[0], &p->d_task[1], &p->d_vtrue[0], &p->d_vtrue[1],
                     &p->d_slot, &p->d_writer, &p->d_sel, &p->d_nsel, &p->d_ftasks, &p->d_finfo, &p->d_fresults,
                     &p->d_frow, &p->d_fbp[0], &p->d_fbp[1], &p->d_fbp[2], &p->d_fbp[3], &p->d_fbp[4], &p->d_fops,
                     &p->d_taskoff, &p->d_scan_tmp, &p->d_perm, &p->d_pair_min, &p->d_pair_max, &p->d_saved, &p->d_pairsel,
@@ -441,6 +441,7 @@ int chunk_scan(Chunk &C) {
   if (const char *e = getenv("SHRIMP_SCAN_CTA_MIN_EST")) cta_min_est = atof(e);
   if (est >= cta_min_est) small_useful = false;
   if (getenv("SHRIMP_SCAN_FORCE_BIG")) small_useful = false;  // test hook: every strand through the CTA kernel
+  if (C.mp_mode) small_useful = false;   // mate-pair region counts live in the CTA kernel
   // CTA kernel: exact region bitmaps over partitions of 2^cta_bm_log2 regions, candidate slots for twice the
   // expected survivors
   const int big_k_cap = std::max(32, std::max(K_max, K_slots));
@@ -448,7 +449,12 @@ int chunk_scan(Chunk &C) {
   bool cta_hashed = false;
   {
     const double n_regions = L_total / (double)(1u << C.M.region_bits) + 2.0;
-    if (filt) {
+    if (filt && C.mp_mode) {
+      // exact region tables in global memory: no bitmaps; every candidate is a survivor
+      const double lam = est / n_regions;
+      const double want = 3.0 * est * std::min(1.0, 1.1 * lam) + 2.0 * K_max + 64;
+      while (cta_cap < 8192 && cta_cap < want) cta_cap <<= 1;
+    } else if (filt) {
       int exact_log2 = 5;
       while (exact_log2 < 31 && (double)(1u << exact_log2) < n_regions) exact_log2++;
       // exact bitmaps (one bit per 2 kb region, partitions of at most 2^18 regions) unless they would be far
@@ -557,8 +563,8 @@ int chunk_scan(Chunk &C) {
       uint32_t *lists[2] = {pl->d_overflow.as<uint32_t>(), pl->d_overflow2.as<uint32_t>()};
       int cur = 0;   // list holding the current work (valid when `have_list`)
       bool have_list = small_useful;
-      uint32_t n_work = small_useful ? h3[1] : 2u * (uint32_t)n_reads;
-      C.scan_big = n_work;
+      uint32_t n_work = small_useful ? h3[1] : C.mp_mode ? (uint32_t)n_reads / 2u : 2u * (uint32_t)n_reads;
+      C.scan_big = small_useful ? h3[1] : 2u * (uint32_t)n_reads;
       P.k_cap = big_k_cap;
       P.bm_log2 = cta_bm_log2;
       P.n_part = cta_n_part;
@@ -580,6 +586,30 @@ int chunk_scan(Chunk &C) {
       P.tie_cap = pl->tie_cap;
       P.tie_rec_cap = 2u * (uint32_t)n_reads;
       P.resume = 0;
+      P.mp_mode = C.mp_mode;
+      P.pair_mode = C.pair_mode;
+      P.min_insert = C.min_insert;
+      P.max_insert = C.max_insert;
+      if (C.mp_mode) {
+        // four region tables per CTA, (epoch << 8) | flags per 2 kb region; zeroed when (re)allocated, epochs persist
+        const int mp_regions = (int)(L_total / (double)(1u << C.M.region_bits)) + 2;
+        const size_t ctas_max = (size_t)ctx->sm_count * 8;
+        const size_t ints = ctas_max * 4 * (size_t)mp_regions;
+        if (pl->mp_tab_ints != ints) {
+          SH_TRY(pl->d_mp_tab.ensure(ints * 4));
+          SH_TRY(pl->d_mp_epoch.ensure(ctas_max * 4));
+          SH_CUDA(cudaMemsetAsync(pl->d_mp_tab.p, 0, ints * 4, st));
+          SH_CUDA(cudaMemsetAsync(pl->d_mp_epoch.p, 0, ctas_max * 4, st));
+          pl->mp_tab_ints = ints;
+        }
+        P.mp_tab = pl->d_mp_tab.as<uint32_t>();
+        P.mp_epoch = pl->d_mp_epoch.as<uint32_t>();
+        P.mp_regions = mp_regions;
+        if (K_slots >= 0x8000) {
+          set_error("seed scan: reads too long for the paired match modes that use mate-pair region counts");
+          return SHRIMP_E_RANGE;
+        }
+      }
       P.prof = nullptr;
       if (getenv("SHRIMP_SCAN_PROF")) {
         SH_TRY(pl->d_prof.ensure(16 * 8));

@@ -188,8 +188,11 @@ __device__ __forceinline__ bool hit_chain(const ScanParams &P, const AnchorRec *
   gstart = gend >= window_len ? gend - window_len : 0;
   max_idx = i;
   max_score = ai.len * M.match;
+  // hit-list mode 3 (paired -n 3): a window whose mate has two k-mer hits in range passes on one match (:1082-1094);
+  // the flag rides in bit 30 of the head's weight
+  const bool heavy_mp = M.match_mode == 3 && ((ai.weight >> 30) & 1);
   if (!M.gapless) {
-    if (M.match_mode == 2 && ai.weight == 1) max_score = -1;
+    if ((M.match_mode == 2 || (M.match_mode == 3 && !heavy_mp)) && (ai.weight & 0x3fffffff) == 1) max_score = -1;
     for (int j = i - 1; j >= 0; j--) {
       const AnchorRec aj = rec[j];
       if ((long long)aj.x < coff + gstart) break;
@@ -212,7 +215,7 @@ __device__ __forceinline__ bool hit_chain(const ScanParams &P, const AnchorRec *
   }
   const int base_len = rl < w_len ? rl : w_len;
   const int score_max = base_len * M.match;
-  return M.gapless || M.match_mode == 1 ||
+  return M.gapless || M.match_mode == 1 || heavy_mp ||
          max_score >= (int)abs_or_pct_d(M.wgen_thr, M.wgen_frac, (double)score_max);
 }
 
@@ -249,7 +252,7 @@ __device__ __forceinline__ DevHit hit_make(const ScanParams &P, const AnchorRec 
   h.cn = cn;
   h.w_len = w_len;
   h.wg = max_score;
-  h.matches = (M.gapless || max_idx == i) ? ai.weight : ai.weight + am.weight;
+  h.matches = (M.gapless || max_idx == i) ? (ai.weight & 0x3fffffff) : (ai.weight & 0x3fffffff) + (am.weight & 0x3fffffff);
   h.score_max = base_len * M.match;
   h.score_vector = -1;
   h.pct_vector = 0;
@@ -801,6 +804,7 @@ __global__ void __launch_bounds__(SCAN_CTA_MAX_THREADS, 2) scan_cta_kernel(const
 
   long long prof_t = clock64();
   if (tid == 0) s_item_next = atomicAdd(P.work_counter, 1u);
+  uint32_t mp_epoch = (P.mp_mode && !P.resume) ? P.mp_epoch[blockIdx.x] : 0u;
   for (;;) {
     __syncthreads();
     PROF_MARK(15);
@@ -814,14 +818,80 @@ __global__ void __launch_bounds__(SCAN_CTA_MAX_THREADS, 2) scan_cta_kernel(const
     }
     // the next strand's ticket travels while this one is processed (the last warp waits for it at its next barrier)
     if (tid == nthr - 1) s_item_next = atomicAdd(P.work_counter, 1u);
-    const uint32_t rs = P.resume ? P.tie_rec[item].x : P.work ? P.work[item] : item;
+    // Mate-pair region counts (P.mp_mode): a work item is a read PAIR.  Its four strands first mark
+    // this CTA's exact region tables in global memory (sub-steps 0-3: read_get_region_counts), then each strand
+    // keeps the entries that pass the paired rule of advance_index_in_genomemap (sub-steps 4-7), with the mate's
+    // count taken over the region interval the insert-size limits allow (read_get_mp_region_counts).
+    const bool mp = P.mp_mode != 0 && !P.resume;
+    // with a work list (strands that overflowed a smaller slab) the pair's tables are rebuilt and one strand is kept
+    const int n_sub = mp ? (P.work ? 5 : 8) : 1;
+    const uint32_t mp_pair = mp ? (P.work ? P.work[item] >> 2 : item) : 0u;
+    if (mp) mp_epoch++;
+    for (int sub = 0; sub < n_sub; sub++) {
+    if (sub > 0) {
+      __syncthreads();
+      if (tid == 0) {
+        s_total = 0;
+        s_ns = 0;
+        s_cnt = 0;
+      }
+    }
+    const bool mp_mark = mp && sub < 4;
+    const int q = mp_mark ? sub : (P.work ? (int)(P.work[item] & 3u) : sub - 4);   // mp: strand of the pair, 2 * mate + strand
+    const uint32_t rs = mp ? 4u * mp_pair + (uint32_t)q : P.resume ? P.tie_rec[item].x : P.work ? P.work[item] : item;
     const int r = (int)(rs >> 1);
     const int rl = P.read_len[r];
     const uint32_t *seq = P.reads + (size_t)rs * P.stride;
     int max_n_kmers = M.colour_space ? rl - S.min_span : rl - S.min_span + 1;
     if (max_n_kmers < 0) max_n_kmers = 0;
-    if (!P.work && !P.resume && tid == 0) P.rs_range[rs] = make_uint2(0u, 0u);
+    if (!P.work && !P.resume && !mp_mark && tid == 0) P.rs_range[rs] = make_uint2(0u, 0u);
     if (rl <= 0 || max_n_kmers == 0) continue;
+    uint32_t *tab_self = nullptr;
+    const uint32_t *tab_mate = nullptr;
+    int dr_min = 0, dr_max = 0;
+    if (mp) {
+      tab_self = P.mp_tab + ((size_t)blockIdx.x * 4 + (size_t)q) * (size_t)P.mp_regions;
+      tab_mate = P.mp_tab + ((size_t)blockIdx.x * 4 + (size_t)(3 - q)) * (size_t)P.mp_regions;
+      // readpair_compute_mp_ranges (mapping.c:2317-2430) for this mate and strand
+      const int nip = (q >> 1) & 1, st = q & 1;
+      const int rl1 = P.read_len[(rs >> 2) * 2], rl2 = P.read_len[(rs >> 2) * 2 + 1];
+      const int wl1 = (int)(unsigned short)abs_or_pct_d(M.window_len, M.window_len_frac, (double)rl1);
+      const int wl2 = (int)(unsigned short)abs_or_pct_d(M.window_len, M.window_len_frac, (double)rl2);
+      int d1min[2], d1max[2];
+      d1min[0] = P.min_insert - wl2;
+      d1max[0] = P.max_insert + (wl1 - rl1) - rl2;
+      d1min[1] = -P.max_insert + rl1 + (rl2 - wl2);
+      d1max[1] = -P.min_insert + wl1;
+      const int sh = P.pair_mode == 2 ? rl1 + rl2 : P.pair_mode == 3 ? rl2 : P.pair_mode == 4 ? rl1 : 0;
+      d1min[0] += sh; d1max[0] += sh; d1min[1] -= sh; d1max[1] -= sh;
+      int lo, hi;
+      if (nip == 0) {
+        lo = d1min[st]; hi = d1max[st];
+      } else if (P.pair_mode == 1 || P.pair_mode == 2) {
+        lo = -d1max[1 - st]; hi = -d1min[1 - st];
+      } else {
+        lo = -d1max[st]; hi = -d1min[st];
+      }
+      const int rsz = 1 << M.region_bits;
+      dr_min = lo >= 0 ? lo / rsz : -1 - (-lo - 1) / rsz;
+      dr_max = hi > 0 ? 1 + (hi - 1) / rsz : -(-hi / rsz);
+    }
+    // the paired keep rule for one region (mapping.c:704-712); also the hit list's heavy_mp (:1082-1094)
+    auto mp_count = [&](uint32_t region) -> int {
+      int first = (int)region + dr_min, last = (int)region + dr_max, mx = 0;
+      if (first < 0) first = 0;
+      if (last > P.mp_regions - 1) last = P.mp_regions - 1;
+      for (int k = first; k <= last && mx < 2; k++) {
+        const uint32_t c = tab_mate[k];
+        if ((c >> 8) == mp_epoch) mx = (c & 2u) ? 2 : 1;
+      }
+      return mx;
+    };
+    auto mp_pass = [&](uint32_t region) -> bool {
+      const int count_main = (tab_self[region] & 2u) ? 2 : 1, count_mp = mp_count(region);
+      return (P.mp_mode == 1 && count_main >= 2 && count_mp >= 2) || (P.mp_mode == 2 && (count_main >= 2 || count_mp >= 2)) ||
+             (P.mp_mode == 3 && count_mp >= 1 && count_main + count_mp >= 3);
+    };
 
     int m_surv = 0;
     const unsigned long long *esrc = ent;   // candidates in pop order: esrc[order ? order[t] : t]
@@ -938,10 +1008,10 @@ __global__ void __launch_bounds__(SCAN_CTA_MAX_THREADS, 2) scan_cta_kernel(const
       const uint32_t total_p = kpre[K];
       if (total_p == 0) continue;
       const bool one_window = total_p <= (uint32_t)win;
-      for (int pass = filt ? 0 : 1; pass < 2; pass++) {
+      for (int pass = mp ? (mp_mark ? 0 : 1) : filt ? 0 : 1; pass < (mp_mark ? 1 : 2); pass++) {
         for (uint32_t w0 = 0; w0 < total_p; w0 += (uint32_t)win) {
           const uint32_t w1 = min(w0 + (uint32_t)win, total_p), n = w1 - w0;
-          if (!(pass == 1 && one_window && filt)) {
+          if (!(pass == 1 && one_window && filt && !mp)) {
             // ---- stage the window: lists [klo, ...) whose flat range meets [w0, w1)
             int klo = 0;
             if (w0 > 0) {
@@ -979,6 +1049,20 @@ __global__ void __launch_bounds__(SCAN_CTA_MAX_THREADS, 2) scan_cta_kernel(const
           }
           if (pass == 0) {
             // ---- pass A: mark
+            if (mp) {   // exact per-(mate, strand) tables in global memory: (epoch << 8) | has2 << 1 | touched
+              const uint32_t fresh = (mp_epoch << 8) | 1u;
+              for (uint32_t t = tid; t < n; t += nthr) {
+                const uint32_t x = buf[t];
+                uint32_t region = x >> M.region_bits;
+                uint32_t old = atomicMax(&tab_self[region], fresh);
+                if ((old >> 8) == mp_epoch) atomicOr(&tab_self[region], 2u);
+                if ((x & rmask) < (uint32_t)M.region_overlap && region > 0) {
+                  region--;
+                  old = atomicMax(&tab_self[region], fresh);
+                  if ((old >> 8) == mp_epoch) atomicOr(&tab_self[region], 2u);
+                }
+              }
+            } else
             for (uint32_t t = tid; t < n; t += nthr) {
               const uint32_t x = buf[t];
               const uint32_t region = x >> M.region_bits;
@@ -1001,7 +1085,10 @@ __global__ void __launch_bounds__(SCAN_CTA_MAX_THREADS, 2) scan_cta_kernel(const
               uint32_t x = 0;
               if (kp) {
                 x = buf[t];
-                if (filt) {
+                if (mp) {
+                  const uint32_t region = x >> M.region_bits;
+                  kp = mp_pass(region) || ((x & rmask) < (uint32_t)M.region_overlap && region > 0 && mp_pass(region - 1));
+                } else if (filt) {
                   const uint32_t region = x >> M.region_bits;
                   const uint32_t idx = hashed ? region_hash(region, P.bm_log2) : region - R0;
                   kp = ((bm2[idx >> 5] >> (idx & 31)) & 1u) != 0;
@@ -1018,7 +1105,16 @@ __global__ void __launch_bounds__(SCAN_CTA_MAX_THREADS, 2) scan_cta_kernel(const
                 uint32_t at = 0;
                 if (lane == 0) at = atomicAdd(&s_ns, (uint32_t)__popc(bal));
                 at = __shfl_sync(0xffffffffu, at, 0) + (uint32_t)__popc(bal & lt);
-                if (kp && at < (uint32_t)cap) ent[at] = ((unsigned long long)x << 32) | bslot[t];
+                if (kp && at < (uint32_t)cap) {
+                  uint32_t lowword = bslot[t];
+                  if (mp && M.match_mode == 3) {   // heavy_mp of the anchor this entry may head, bit 15 of the slot field
+                    const uint32_t region = x >> M.region_bits;
+                    if (mp_count(region) >= 2 ||
+                        ((x & rmask) < (uint32_t)M.region_overlap && region > 0 && mp_count(region - 1) >= 2))
+                      lowword |= 0x8000u;
+                  }
+                  ent[at] = ((unsigned long long)x << 32) | lowword;
+                }
               }
             }
           }
@@ -1027,6 +1123,7 @@ __global__ void __launch_bounds__(SCAN_CTA_MAX_THREADS, 2) scan_cta_kernel(const
         PROF_MARK(3 + pass);
       }
     }
+    if (mp_mark) continue;
     const int ns = (int)s_ns;
     if (ns > cap) {
       if (tid == 0) {
@@ -1062,7 +1159,7 @@ __global__ void __launch_bounds__(SCAN_CTA_MAX_THREADS, 2) scan_cta_kernel(const
     PROF_MARK(5);
     // ---- 4b. region filter (RG_HAS_2 as a neighbour test) + ordered compaction ----------------------------
     m_surv = ns;
-    if (filt) {
+    if (filt && !mp) {
       const int n_words = (ns + 31) >> 5;
       for (int t0 = 0; t0 < n_words * 32; t0 += nthr) {
         const int t = t0 + tid;
@@ -1127,7 +1224,8 @@ __global__ void __launch_bounds__(SCAN_CTA_MAX_THREADS, 2) scan_cta_kernel(const
     bool tie = false;
     for (int t = tid; t + 1 < m_surv; t += nthr) {
       const unsigned long long a = ent[t], b = ent[t + 1];
-      if ((a >> 32) == (b >> 32) && ((uint32_t)a % (uint32_t)max_n_kmers) != ((uint32_t)b % (uint32_t)max_n_kmers))
+      if ((a >> 32) == (b >> 32) &&
+          (((uint32_t)a & 0x7fffu) % (uint32_t)max_n_kmers) != (((uint32_t)b & 0x7fffu) % (uint32_t)max_n_kmers))
         tie = true;
     }
     tie = __syncthreads_or(tie) != 0;
@@ -1159,13 +1257,13 @@ __global__ void __launch_bounds__(SCAN_CTA_MAX_THREADS, 2) scan_cta_kernel(const
     // ---- 6. anchors in pop order; colinear collapse (:941-971) in warp lockstep ---------------------------
     for (int t = tid; t < m_surv; t += nthr) {
       const unsigned long long e = esrc[order ? order[t] : t];
-      const uint32_t slot = (uint32_t)e & 0xffffu;
+      const uint32_t slot = (uint32_t)e & 0x7fffu;
       const int sn = (int)(slot / (uint32_t)max_n_kmers), i = (int)(slot % (uint32_t)max_n_kmers);
       AnchorRec a;
       a.x = (uint32_t)(e >> 32);
       a.y = (int16_t)(mkp + i);
       a.len = (int16_t)S.span[sn];
-      a.weight = 1;
+      a.weight = 1 | (int)(((uint32_t)e >> 15) & 1u) << 30;
       a.cn = contig_of_dev(P.G.contig_off, P.G.num_contigs, a.x);
       rec[t] = a;
     }
@@ -1293,7 +1391,9 @@ __global__ void __launch_bounds__(SCAN_CTA_MAX_THREADS, 2) scan_cta_kernel(const
       P.rs_range[rs] = make_uint2(out0, (uint32_t)nh);
     }
     PROF_MARK(11);
+    }  // sub-steps
   }
+  if (P.mp_mode && !P.resume && tid == 0) P.mp_epoch[blockIdx.x] = mp_epoch;
 }
 
 size_t scan_smem_bytes(int cap, int max_rl, int k_cap, int bm_log2, int warps, bool alias_rec) {
@@ -1330,7 +1430,7 @@ __global__ void __launch_bounds__(REPLAY_WARPS * 32) scan_replay_kernel(const Sc
     const int t = t0 + lane;
     const bool valid = t < m;
     const unsigned long long e = valid ? ent[t] : 0ull;
-    const uint32_t slot = valid ? ((uint32_t)e & 0xffffu) : (0x10000u + (uint32_t)lane);
+    const uint32_t slot = valid ? ((uint32_t)e & 0x7fffu) : (0x10000u + (uint32_t)lane);   // bit 15: heavy_mp flag
     const uint32_t grp = __match_any_sync(0xffffffffu, slot);
     const uint32_t above = grp & ~(lt | (1u << lane));
     uint32_t nx = 0xffffu;

@@ -63,6 +63,12 @@ struct ScanParams {
   uint32_t tie_cap, tie_rec_cap;
   int resume, resume_min;        // resume launch: strands with resume_min < candidates <= cap
   unsigned long long *prof;      // optional phase cycle counters [16] (SHRIMP_SCAN_PROF)
+  // mate-pair region counts (paired option sets that look at the mate)
+  int mp_mode;                   // anchor_list.use_mp_region_counts: 0 off, 1, 2, 3 (gmapper.c:2659-2662); work item = pair
+  int pair_mode, min_insert, max_insert;
+  uint32_t *mp_tab;              // [n_ctas][4][mp_regions] region tables, zeroed once
+  uint32_t *mp_epoch;            // [n_ctas] table epochs
+  int mp_regions;
   int bm_hashed;                 // CTA kernel: hashed region bitmaps (one partition) instead of exact partitions
   int win;                       // entries of the shared-memory staging window
   int lanes_per_list_log2; // lanes that share one index list (2..5): short lists are streamed several per warp
