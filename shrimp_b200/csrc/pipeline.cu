@@ -84,11 +84,15 @@ __global__ void build_full_tasks_kernel(const FullBuildParams P) {
   P.info[out] = I;
 }
 
-// Ring-width class of every full-SW task (sw_full_ring.cu): the widest row of its band + the edge cell,
-// rounded up to 32/64/128/256; class RING_CLASSES = wider than any ring that fits shared memory, served by
-// the global-scratch kernels.  perm[c * n + rank] lists the task ids of class c.
+// Class of every full-SW task (sw_full_ring.cu): the widest row of its band + the edge cell, rounded up to
+// 32/64/128/256 (class RING_CLASSES = wider than any ring that fits shared memory, served by the global-scratch
+// kernels); then whether the alignment runs with the reverse-complement tie order (gen_st && Tflag: a
+// compile-time variant of the kernels), then the band width in sixteenths of the ring -- the alignments of a
+// warp run in lockstep over the widest band among them, so neighbours in the task order should look alike.
+// key = class * 32 + revcmpl * 16 + width bucket.
+#define FULL_KEYS ((RING_CLASSES + 1) * 32)
 __global__ void classify_full_tasks_kernel(const FullTask *tasks, int n, int anchor_width, int match, int local,
-                                           int max_class, int32_t *perm, uint32_t *cls_count) {
+                                           int Tflag, int max_class, uint32_t *key, uint32_t *key_count) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
   const FullTask T = tasks[t];
@@ -105,8 +109,24 @@ __global__ void classify_full_tasks_kernel(const FullTask *tasks, int n, int anc
   }
   int c = bw <= 32 ? 0 : bw <= 64 ? 1 : bw <= 128 ? 2 : bw <= 256 ? 3 : RING_CLASSES;
   if (c > max_class) c = RING_CLASSES;
-  const uint32_t rank = atomicAdd(&cls_count[c], 1u);
-  perm[(size_t)c * n + rank] = t;
+  const int W = 32 << c;
+  const int bucket = c < RING_CLASSES ? min(15, (bw * 16 - 1) / W) : 0;
+  const uint32_t k = (uint32_t)(c * 32 + ((T.gen_st && Tflag) ? 16 : 0) + bucket);
+  key[t] = k;
+  atomicAdd(&key_count[k], 1u);
+}
+// exclusive prefix of the key counts -> first slot of every key in perm (one thread: FULL_KEYS values)
+__global__ void full_key_offsets_kernel(const uint32_t *key_count, uint32_t *key_off) {
+  uint32_t run = 0;
+  for (int k = 0; k < FULL_KEYS; k++) {
+    key_off[k] = run;
+    run += key_count[k];
+  }
+}
+__global__ void group_full_tasks_kernel(const uint32_t *key, int n, uint32_t *key_off, int32_t *perm) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  perm[atomicAdd(&key_off[key[t]], 1u)] = t;
 }
 
 void free_pipeline(shrimp_gpu_ctx *ctx) {
@@ -139,18 +159,40 @@ int run_full_sw(shrimp_gpu_ctx *ctx, DevBuf &d_perm, DevBuf &d_row, DevBuf *d_bp
                        FullParams FP, int n, bool cs, uint32_t *d_cls_count) {
   if (n <= 0) return SHRIMP_OK;
   cudaStream_t st = ctx->stream;
-  SH_TRY(d_perm.ensure((size_t)(RING_CLASSES + 1) * n * 4));
-  SH_CUDA(cudaMemsetAsync(d_cls_count, 0, (RING_CLASSES + 1) * 4, st));
+  // d_perm: perm[n] grouped by key | key[n] | key counts | key offsets
+  SH_TRY(d_perm.ensure(((size_t)2 * n + 2 * FULL_KEYS) * 4));
+  int32_t *perm = d_perm.as<int32_t>();
+  uint32_t *d_key = (uint32_t *)perm + n, *d_key_count = d_key + n, *d_key_off = d_key_count + FULL_KEYS;
+  (void)d_cls_count;
+  SH_CUDA(cudaMemsetAsync(d_key_count, 0, FULL_KEYS * 4, st));
   int max_class = -1;
   for (int c = 0; c < RING_CLASSES; c++)
     if (ring_fits(cs, 32 << c)) max_class = c;
-  classify_full_tasks_kernel<<<(n + 127) / 128, 128, 0, st>>>(FP.tasks, n, FP.anchor_width, FP.match, FP.local,
-                                                              max_class, d_perm.as<int32_t>(), d_cls_count);
+  classify_full_tasks_kernel<<<(n + 127) / 128, 128, 0, st>>>(FP.tasks, n, FP.anchor_width, FP.match, FP.local, FP.Tflag,
+                                                              max_class, d_key, d_key_count);
   SH_CUDA(cudaGetLastError());
   SH_LAUNCHED(ctx, ST_FULL);
-  uint32_t cls[RING_CLASSES + 1];
-  SH_CUDA(cudaMemcpyAsync(cls, d_cls_count, sizeof(cls), cudaMemcpyDeviceToHost, st));
+  full_key_offsets_kernel<<<1, 1, 0, st>>>(d_key_count, d_key_off);
+  group_full_tasks_kernel<<<(n + 127) / 128, 128, 0, st>>>(d_key, n, d_key_off, perm);
+  SH_CUDA(cudaGetLastError());
+  SH_LAUNCHED(ctx, ST_FULL);
+  SH_LAUNCHED(ctx, ST_FULL);
+  uint32_t kc[FULL_KEYS];
+  SH_CUDA(cudaMemcpyAsync(kc, d_key_count, sizeof(kc), cudaMemcpyDeviceToHost, st));
   SH_CUDA(cudaStreamSynchronize(st));
+  uint32_t cls[RING_CLASSES + 1], cls_rev0[RING_CLASSES + 1], cls_first[RING_CLASSES + 1];
+  {
+    uint32_t run = 0;
+    for (int c = 0; c <= RING_CLASSES; c++) {
+      cls_first[c] = run;
+      cls[c] = cls_rev0[c] = 0;
+      for (int k = 0; k < 32; k++) {
+        cls[c] += kc[c * 32 + k];
+        if (k < 16) cls_rev0[c] += kc[c * 32 + k];
+      }
+      run += cls[c];
+    }
+  }
   // the classes are independent: class c runs on its own stream (class 0, the bulk, on the main one) so the
   // small wide-band launches, each bounded by the latency of one alignment, overlap the bulk
   const size_t budget = (size_t)2 << 30;
@@ -175,10 +217,14 @@ int run_full_sw(shrimp_gpu_ctx *ctx, DevBuf &d_perm, DevBuf &d_row, DevBuf *d_bp
     cudaStream_t cst = c == 0 ? st : ctx->aux[(c - 1) % SHRIMP_AUX_STREAMS];
     if (c > 0) SH_CUDA(cudaStreamWaitEvent(cst, ctx->fork_ev, 0));
     ctx->stream = cst;  // the launchers use ctx->stream
-    for (int b0 = 0; b0 < count; b0 += batch) {
+    // the forward-order tasks first, then the reverse-complement-order ones: a launch holds one kind
+    for (int rev = 0; rev < 2; rev++) {
+    const int r0 = rev ? (int)cls_rev0[c] : 0, r1 = rev ? count : (int)cls_rev0[c];
+    for (int b0 = r0; b0 < r1; b0 += batch) {
       FullParams Q = FP;
-      Q.perm = d_perm.as<int32_t>() + (size_t)c * n + b0;
-      Q.n_tasks = std::min(batch, count - b0);
+      Q.perm = perm + cls_first[c] + b0;
+      Q.n_tasks = std::min(batch, r1 - b0);
+      Q.rev = rev;
       Q.NT = batch;
       Q.W = W;
       Q.row = Q.row_cs = d_row.as<int32_t>();
@@ -189,6 +235,7 @@ int run_full_sw(shrimp_gpu_ctx *ctx, DevBuf &d_perm, DevBuf &d_row, DevBuf *d_bp
       else if (cs) rc = launch_sw_full_cs(ctx, Q);
       else rc = launch_sw_full_ls(ctx, Q);
       if (rc != SHRIMP_OK) return rc;
+    }
     }
     ctx->stream = st;
     if (c > 0) {

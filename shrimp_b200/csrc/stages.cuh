@@ -163,6 +163,7 @@ struct FullParams {
   // band-ring kernels (sw_full_ring.cu): task ids of this launch (nullptr = identity), ring width,
   // packed colour-space back-pointers [max_rlen*W][NT]; `bp` is [max_rlen*W][NT] there
   const int32_t *perm;
+  int rev;          // every task of this launch has gen_st && Tflag == rev (the tasks are grouped by it)
   int W;
   unsigned long long *bp64;
 };

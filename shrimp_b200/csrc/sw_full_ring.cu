@@ -558,7 +558,7 @@ __device__ __forceinline__ int warp_max_i(int v) {
 // The eight quads of a warp step through rows and band offsets in LOCKSTEP (trip counts are the warp maxima, a
 // quad outside its own band is predicated off), so the cross-layer exchange can use full-mask shuffles -- a
 // shuffle under a computed sub-warp mask costs a WARPSYNC/collective sequence of ~10 instructions each.
-template <bool LOCAL>
+template <bool LOCAL, bool REV, bool TABOO>
 __device__ int quad_cs_dp(const FullParams &P, const FullTask &T, bool run, int slot, int k, int qbase, int32_t *sm,
                           const uint32_t *genome, const uint32_t *read, const Rect &rect, int &ret_i, int &ret_j,
                           int end_sc[3], unsigned long long &cells) {
@@ -567,7 +567,7 @@ __device__ int quad_cs_dp(const FullParams &P, const FullTask &T, bool run, int 
   const int lena = T.glen, lenb = run ? T.rlen : 0;
   const size_t bstride = (size_t)P.NT * 4;  // u16 elements between two band offsets
   const int ao = P.a_open, ae = P.a_ext, bo = P.b_open, be = P.b_ext;
-  const bool revcmpl = T.gen_st && P.Tflag;
+  constexpr bool revcmpl = REV;   // T.gen_st && P.Tflag of every task of the launch (the tasks are grouped by it)
   unsigned short *bp_task = (unsigned short *)P.bp64 + (size_t)slot * 4 + k;
   int score = 0, max_i = 0, max_j = 0;
   int letter = (k + T.initbp) % 4;
@@ -584,7 +584,7 @@ __device__ int quad_cs_dp(const FullParams &P, const FullTask &T, bool run, int 
     if (row_on) rect_x_range(rect, lena, i, x_min, x_max);
     const int width = row_on ? x_max - x_min + 1 : 0;
     const int wmax = warp_max_i(width);
-    const bool nt = i < lenb - P.indel_taboo_len;
+    const bool nt = TABOO ? i < lenb - P.indel_taboo_len : true;   // rows past lenb are switched off anyway
     int qk = 15;
     if (row_on) {
       const int colour = (int)extract4(read, (uint64_t)i);
@@ -710,6 +710,7 @@ __device__ int quad_cs_dp(const FullParams &P, const FullTask &T, bool run, int 
   return score;
 }
 
+template <bool REV, bool TABOO>
 __global__ void __launch_bounds__(QUAD_THREADS) sw_full_cs_quad_kernel(const FullParams P) {
   extern __shared__ int32_t ring_smem[];
   const int k = threadIdx.x & 3, qbase = (threadIdx.x & 31) & ~3;
@@ -727,8 +728,8 @@ __global__ void __launch_bounds__(QUAD_THREADS) sw_full_cs_quad_kernel(const Ful
   unsigned long long cells = 0;
   int ei = 0, ej = 0, esc[3] = {0, 0, 0};
   const Rect rect = task_rect(T, P.anchor_width, P.match, true);
-  int score = P.local ? quad_cs_dp<true>(P, T, run, slot, k, qbase, sm, genome, read, rect, ei, ej, esc, cells)
-                      : quad_cs_dp<false>(P, T, run, slot, k, qbase, sm, genome, read, rect, ei, ej, esc, cells);
+  int score = P.local ? quad_cs_dp<true, REV, TABOO>(P, T, run, slot, k, qbase, sm, genome, read, rect, ei, ej, esc, cells)
+                      : quad_cs_dp<false, REV, TABOO>(P, T, run, slot, k, qbase, sm, genome, read, rect, ei, ej, esc, cells);
   // the reference scans cells in (i, j, layer) order and keeps the first maximum (sw-full-cs.c:552-580):
   // every lane gathers the four per-layer candidates and picks the winner
   int ek = 0;
@@ -858,7 +859,14 @@ int launch_sw_full_ring(shrimp_gpu_ctx *ctx, const FullParams &P, bool cs) {
     K<<<grid, block, smem, ctx->stream>>>(P);                                                            \
   } while (0)
   if (cs) {
-    RING_LAUNCH(sw_full_cs_quad_kernel);
+    const bool taboo = P.indel_taboo_len != 0;
+    if (P.rev) {
+      if (taboo) RING_LAUNCH((sw_full_cs_quad_kernel<true, true>));
+      else RING_LAUNCH((sw_full_cs_quad_kernel<true, false>));
+    } else {
+      if (taboo) RING_LAUNCH((sw_full_cs_quad_kernel<false, true>));
+      else RING_LAUNCH((sw_full_cs_quad_kernel<false, false>));
+    }
   } else {
     if (block == 64) RING_LAUNCH(sw_full_ls_ring_kernel<64>);
     else RING_LAUNCH(sw_full_ls_ring_kernel<32>);
