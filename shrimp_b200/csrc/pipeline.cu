@@ -15,7 +15,7 @@
 namespace shrimp {
 
 // ---- entry points of the other translation units -----------------------------------------------
-size_t scan_smem_bytes(int cap, int max_rl, int k_cap, int bm_log2, int warps, bool alias_rec);
+size_t scan_smem_bytes(int cap, int max_rl, int k_cap, int bm_log2, int warps, int stash);
 size_t scan_cta_smem_bytes(int cap, int max_rl, int k_cap, int bm_log2, int n_part, int win, bool global_arrays);
 int launch_scan_cta(shrimp_gpu_ctx *ctx, ScanParams &P, int n_ctas, int threads);
 int launch_scan_replay(shrimp_gpu_ctx *ctx, ScanParams &P, uint32_t n_rec, int ks_cap);
@@ -579,10 +579,19 @@ int chunk_scan(Chunk &C) {
       P.bm_log2 = bm_log2;
       P.alias_rec = alias_rec ? 1 : 0;
       P.stream = est >= 8.0 * std::max(1, K_max) ? 1 : 0;   // average list of 8+ positions
+      // staging slab for the strand's list entries: the expected random entries + one per k-mer for the read's own
+      // locus, 128..2048 (strands with more take the two-pass path)
+      int stash = 0;
+      if (filt) {
+        stash = 128;
+        while (stash < 2048 && stash < 1.2 * est + K_max) stash <<= 1;
+      }
+      if (const char *e = getenv("SHRIMP_SCAN_STASH")) stash = std::max(0, std::min(4096, atoi(e)));
+      P.stash = stash;
       // CTA size that keeps the most warps resident (227 KB of shared memory, 32 CTAs and 64 warps per SM)
       int warps = 1, ctas_per_sm = 1, best = 0;
       for (int w = SCAN_WARPS_HOST; w >= 1; w >>= 1) {
-        const size_t sm_w = scan_smem_bytes(cap, max_rl, k_cap, bm_log2, w, alias_rec) + 1024;
+        const size_t sm_w = scan_smem_bytes(cap, max_rl, k_cap, bm_log2, w, stash) + 1024;
         if (sm_w > 220 * 1024) continue;
         const int c = (int)std::min<size_t>(std::min<size_t>((size_t)(226 * 1024) / sm_w, 32), (size_t)(64 / w));
         if (c * w > best) {
@@ -591,7 +600,7 @@ int chunk_scan(Chunk &C) {
           ctas_per_sm = c;
         }
       }
-      const size_t smem = scan_smem_bytes(cap, max_rl, k_cap, bm_log2, warps, alias_rec);
+      const size_t smem = scan_smem_bytes(cap, max_rl, k_cap, bm_log2, warps, stash);
       (void)smem;
       int n_ctas = ctx->sm_count * ctas_per_sm;
       n_ctas = std::min<long long>(n_ctas, ((long long)n_reads * 2 + warps - 1) / warps);

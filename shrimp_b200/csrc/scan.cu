@@ -276,9 +276,74 @@ __device__ __forceinline__ void hit_sort_serial(DevHit *H, int nh) {
   }
 }
 
+// Colinear collapse (read_get_anchor_list_per_strand :941-971 with anchor_uw_join, anchors.c:98-119) of the
+// candidates rec[0, m_surv) -- in pop order, ascending x, so only the "extend to the right" branch of the join can
+// fire -- by one warp in lockstep, 32 candidates per step: a candidate merges into the anchor of the previous
+// candidate with the same cache slot (diagonal mod read length) iff that one lies on the same diagonal of the same
+// contig; predecessors inside the step come from match_any, earlier ones from the cache; merged anchors take their
+// length and weight by atomics.  Anchors are written back in place (anchor id <= candidate index).  Returns n_anch.
+__device__ __forceinline__ int collapse_lockstep(AnchorRec *rec, int32_t *cache, int m_surv, int rl, int lane) {
+  const uint32_t lt = (1u << lane) - 1u;
+  int n_anch = 0;
+  for (int t0 = 0; t0 < m_surv; t0 += 32) {
+    const int t = t0 + lane;
+    const bool valid = t < m_surv;
+    AnchorRec a;
+    a.x = 0; a.cn = 0; a.y = 0; a.len = 0; a.weight = 0;
+    if (valid) a = rec[t];
+    const long long diag = (long long)a.x - a.y;
+    // the reference's cache slot (x + len - y) % len of the diagonal, in 32-bit arithmetic (y < len)
+    const int slot = valid ? (int)((a.x % (uint32_t)rl + (uint32_t)rl - (uint32_t)a.y) % (uint32_t)rl) : -1 - lane;
+    const uint32_t grp = __match_any_sync(0xffffffffu, slot);
+    const uint32_t below = grp & lt;
+    const int pl = below ? 31 - __clz(below) : lane;
+    const long long pdiag = __shfl_sync(0xffffffffu, diag, pl);
+    const int pcn = __shfl_sync(0xffffffffu, a.cn, pl);
+    bool head = false;
+    int cached = -1;
+    if (valid) {
+      if (below) {
+        head = !(pdiag == diag && pcn == a.cn);
+      } else {
+        cached = cache[slot];
+        head = !(cached >= 0 && rec[cached].cn == a.cn && (long long)rec[cached].x - rec[cached].y == diag);
+      }
+    }
+    const uint32_t hm = __ballot_sync(0xffffffffu, head);
+    // the anchor this candidate belongs to: the nearest head of its slot at or below it, else the cached one
+    int aid = -1;
+    if (valid) {
+      const uint32_t hb = grp & hm & (lt | (1u << lane));
+      if (hb) {
+        const int hl = 31 - __clz(hb);
+        aid = n_anch + __popc(hm & ((1u << hl) - 1u));
+      } else {
+        // no head below in this step: the chain starts at the lowest lane of the group, which read the cache
+        const int first = __ffs(grp) - 1;
+        aid = -2 - first;   // resolved below
+      }
+    }
+    const int cached_first = __shfl_sync(0xffffffffu, cached, (aid <= -2) ? (-2 - aid) : lane);
+    if (aid <= -2) aid = cached_first;
+    __syncwarp();
+    if (valid && head) rec[aid] = a;   // aid <= t: every slot at or below t0+31 is already in registers
+    __syncwarp();
+    if (valid && !head) {
+      const AnchorRec d = rec[aid];
+      const int newlen = (int)((long long)a.x - (long long)d.x) + a.len;
+      atomicMax((unsigned int *)&rec[aid].y, ((unsigned int)newlen << 16) | (unsigned int)(uint16_t)d.y);
+      atomicAdd(&rec[aid].weight, 1);
+    }
+    if (valid && (grp >> lane) <= 1u) cache[slot] = aid;   // highest lane of the group
+    n_anch += __popc(hm);
+    __syncwarp();
+  }
+  return n_anch;
+}
+
 // ---- steps 4-7 on the sorted candidates ent[0, total): one warp ---------------------------------------
 __device__ void scan_tail(const ScanParams &P, uint32_t rs, int r, int rl, int max_n_kmers, int total, int gathered,
-                          unsigned long long *ent, AnchorRec *rec, int16_t *cache, uint32_t *keep, int32_t *first_of,
+                          unsigned long long *ent, AnchorRec *rec, int32_t *cache, uint32_t *keep, int32_t *first_of,
                           unsigned long long *heap64, uint16_t *order16, int lane) {
   const SeedTable &S = P.S;
   const MapParamsDev &M = P.M;
@@ -420,29 +485,7 @@ __device__ void scan_tail(const ScanParams &P, uint32_t rs, int r, int rl, int m
   }
   for (int t = lane; t < rl; t += 32) cache[t] = -1;
   __syncwarp();
-  int n_anch = 0;
-  if (lane == 0) {
-    // read_get_anchor_list_per_strand :941-971 with anchor_uw_join (anchors.c:98-119); entries
-    // arrive in ascending x, so only the "extend to the right" branch of the join can fire.
-    for (int t = 0; t < m_surv; t++) {
-      const AnchorRec a = rec[t];
-      const int slot = (int)(((unsigned long long)a.x + (unsigned long long)rl - (unsigned long long)a.y) %
-                             (unsigned long long)rl);
-      const int j = cache[slot];
-      if (j >= 0 && rec[j].cn == a.cn &&
-          (long long)rec[j].x - rec[j].y == (long long)a.x - a.y) {
-        AnchorRec d = rec[j];
-        if ((long long)a.x + a.len > (long long)d.x + d.len) d.len = (int16_t)((long long)a.x - d.x + a.len);
-        d.weight += 1;
-        rec[j] = d;
-      } else {
-        rec[n_anch] = a;
-        cache[slot] = (int16_t)n_anch;
-        n_anch++;
-      }
-    }
-  }
-  n_anch = __shfl_sync(0xffffffffu, n_anch, 0);
+  const int n_anch = collapse_lockstep(rec, cache, m_surv, rl, lane);
   __syncwarp();
 
   // ---- 7. hit list (read_get_hit_list_per_strand) ---------------------------------------------
@@ -491,18 +534,20 @@ __device__ void scan_tail(const ScanParams &P, uint32_t rs, int r, int rl, int m
 
 // shared memory of one warp of the small kernel / of the CTA of the big kernel
 struct ScanSmem {
-  size_t r2, kst, kpre, bm1, bm2, ent, rec, cache, keep, heap, order, total;
+  size_t r2, kst, kpre, bm1, bm2, ent, rec, cache, keep, heap, order, stash, sslot, total;
 };
-__host__ __device__ inline ScanSmem scan_layout(int cap, int max_rl, int k_cap, int bm_log2, bool /*alias_rec*/) {
+__host__ __device__ inline ScanSmem scan_layout(int cap, int max_rl, int k_cap, int bm_log2, int stash) {
   ScanSmem L;
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t at = o; o += (bytes + 15) & ~(size_t)15; return at; };
   L.r2 = take(((size_t)max_rl / 16 + 4) * 4);
   L.kst = take((size_t)k_cap * 4);
   L.kpre = take(((size_t)k_cap + 1) * 4);
-  L.cache = take((size_t)max_rl * 2);
+  L.cache = take((size_t)max_rl * 4);
   L.keep = take(((size_t)cap / 32 + 2) * 4);   // + the candidate counter of the warp kernel
   L.order = take((size_t)cap * 2);      // pop order of the tie replay
+  L.stash = take((size_t)stash * 4);    // the strand's list entries, staged once (warp kernel, short lists)
+  L.sslot = take((size_t)stash * 2);
   L.ent = take((size_t)cap * 8);
   // the anchors (16 B per candidate) are born after the bitmaps and the replay heap have died: same bytes
   L.bm1 = take(((size_t)1 << bm_log2) / 8);
@@ -528,7 +573,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) scan_kernel(const ScanParams 
   const int wib = threadIdx.x >> 5;
   if (wib >= warps_per_cta) return;
   const int cap = P.cap;
-  const ScanSmem L = scan_layout(cap, P.max_rl, P.k_cap, P.bm_log2, P.alias_rec != 0);
+  const ScanSmem L = scan_layout(cap, P.max_rl, P.k_cap, P.bm_log2, P.stash);
   unsigned char *base = smem_raw + L.total * wib;
   uint32_t *r2 = (uint32_t *)(base + L.r2);
   KmerTables T;
@@ -537,7 +582,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) scan_kernel(const ScanParams 
   uint32_t *bm1 = (uint32_t *)(base + L.bm1), *bm2 = (uint32_t *)(base + L.bm2);
   unsigned long long *ent = (unsigned long long *)(base + L.ent);
   AnchorRec *rec = (AnchorRec *)(base + L.rec);
-  int16_t *cache = (int16_t *)(base + L.cache);
+  int32_t *cache = (int32_t *)(base + L.cache);
   uint32_t *keep = (uint32_t *)(base + L.keep);
   uint32_t *s_cnt = keep + (cap / 32 + 1);   // candidate counter of pass B
   const int bm_words = 1 << (P.bm_log2 - 5);
@@ -613,7 +658,73 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) scan_kernel(const ScanParams 
     if (total == 0) continue;
 
     int ns = (int)total;
-    if (M.use_region_counts) {
+    if (M.use_region_counts && total <= (uint32_t)P.stash) {
+      // short lists: every entry is fetched ONCE, by an asynchronous 4-byte copy into shared memory (all the
+      // strand's loads in flight together), then both passes run on the staged copy
+      uint32_t *stash = (uint32_t *)(base + L.stash);
+      uint16_t *sslot = (uint16_t *)(base + L.sslot);
+      // a lane per list (the lists are a handful of entries each); lists of more than 32 entries are copied by
+      // the whole warp afterwards
+      for (int k0 = 0; k0 < K; k0 += 32) {
+        const int kk = k0 + lane;
+        uint32_t f0 = 0, n = 0, slot = 0;
+        const uint32_t *p = nullptr;
+        if (kk < K) {
+          f0 = T.kpre[kk];
+          n = T.kpre[kk + 1] - f0;
+          int sn = 0;
+          while (sn + 1 < S.n_seeds && kbase[sn + 1] <= kk) sn++;
+          p = P.I.pos[sn] + T.kst[kk];
+          slot = (uint32_t)(sn * max_n_kmers + (kk - kbase[sn]));
+        }
+        if (n <= 32u)
+          for (uint32_t j = 0; j < n; j++) {
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(stash + f0 + j);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst), "l"(p + j) : "memory");
+            sslot[f0 + j] = (uint16_t)slot;
+          }
+        uint32_t big = __ballot_sync(0xffffffffu, n > 32u);
+        while (big) {
+          const int src = __ffs(big) - 1;
+          big &= big - 1;
+          const uint32_t bf0 = __shfl_sync(0xffffffffu, f0, src), bn = __shfl_sync(0xffffffffu, n, src);
+          const uint32_t bslot = __shfl_sync(0xffffffffu, slot, src);
+          const unsigned long long bp = __shfl_sync(0xffffffffu, (unsigned long long)p, src);
+          for (uint32_t j = lane; j < bn; j += 32) {
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(stash + bf0 + j);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst), "l"((const uint32_t *)bp + j) : "memory");
+            sslot[bf0 + j] = (uint16_t)bslot;
+          }
+        }
+      }
+      asm volatile("cp.async.wait_all;\n" ::: "memory");
+      __syncwarp();
+      for (uint32_t t = lane; t < total; t += 32) {   // pass A: mark regions
+        const uint32_t x = stash[t];
+        const uint32_t region = x >> M.region_bits;
+        region_mark(bm1, bm2, region, P.bm_log2);
+        if ((x & rmask) < (uint32_t)M.region_overlap && region > 0) region_mark(bm1, bm2, region - 1, P.bm_log2);
+      }
+      __syncwarp();
+      ns = 0;
+      for (uint32_t t0 = 0; t0 < total; t0 += 32) {   // pass B: keep the entries of regions marked twice
+        const uint32_t t = t0 + lane;
+        bool kp = false;
+        uint32_t x = 0;
+        if (t < total) {
+          x = stash[t];
+          const uint32_t region = x >> M.region_bits;
+          kp = region_twice(bm2, region, P.bm_log2) ||
+               ((x & rmask) < (uint32_t)M.region_overlap && region > 0 && region_twice(bm2, region - 1, P.bm_log2));
+        }
+        const uint32_t b = __ballot_sync(0xffffffffu, kp);
+        if (kp) {
+          const int at = ns + __popc(b & ((1u << lane) - 1u));
+          if (at < cap) ent[at] = ((unsigned long long)x << 32) | sslot[t];
+        }
+        ns += __popc(b);
+      }
+    } else if (M.use_region_counts) {
       if (P.stream) {  // long lists: one contiguous stream per lane
         // ---- 2. pass A: mark regions ------------------------------------------------------------------
         const uint32_t chunk = (total + 31u) / 32u;
@@ -1271,62 +1382,7 @@ __global__ void __launch_bounds__(SCAN_CTA_MAX_THREADS, 2) scan_cta_kernel(const
     __syncthreads();
     PROF_MARK(8);
     if (wid == 0) {
-      int n_anch = 0;
-      for (int t0 = 0; t0 < m_surv; t0 += 32) {
-        const int t = t0 + lane;
-        const bool valid = t < m_surv;
-        AnchorRec a;
-        a.x = 0; a.cn = 0; a.y = 0; a.len = 0; a.weight = 0;
-        if (valid) a = rec[t];
-        const long long diag = (long long)a.x - a.y;
-        // the reference's cache slot (x + len - y) % len of the diagonal
-        const int slot = valid ? (int)(((unsigned long long)a.x + (unsigned long long)rl - (unsigned long long)a.y) %
-                                       (unsigned long long)rl)
-                               : -1 - lane;
-        const uint32_t grp = __match_any_sync(0xffffffffu, slot);
-        const uint32_t below = grp & lt;
-        const int pl = below ? 31 - __clz(below) : lane;
-        const long long pdiag = __shfl_sync(0xffffffffu, diag, pl);
-        const int pcn = __shfl_sync(0xffffffffu, a.cn, pl);
-        bool head = false;
-        int cached = -1;
-        if (valid) {
-          if (below) {
-            head = !(pdiag == diag && pcn == a.cn);
-          } else {
-            cached = cache[slot];
-            head = !(cached >= 0 && rec[cached].cn == a.cn && (long long)rec[cached].x - rec[cached].y == diag);
-          }
-        }
-        const uint32_t hm = __ballot_sync(0xffffffffu, head);
-        // the anchor this candidate belongs to: the nearest head of its slot at or below it, else the cached one
-        int aid = -1;
-        if (valid) {
-          const uint32_t hb = grp & hm & (lt | (1u << lane));
-          if (hb) {
-            const int hl = 31 - __clz(hb);
-            aid = n_anch + __popc(hm & ((1u << hl) - 1u));
-          } else {
-            // no head below in this step: the chain starts at the lowest lane of the group, which read the cache
-            const int first = __ffs(grp) - 1;
-            aid = -2 - first;   // resolved below
-          }
-        }
-        const int cached_first = __shfl_sync(0xffffffffu, cached, (aid <= -2) ? (-2 - aid) : lane);
-        if (aid <= -2) aid = cached_first;
-        __syncwarp();
-        if (valid && head) rec[aid] = a;   // aid <= t: every slot at or below t0+31 is already in registers
-        __syncwarp();
-        if (valid && !head) {
-          const AnchorRec d = rec[aid];
-          const int newlen = (int)((long long)a.x - (long long)d.x) + a.len;
-          atomicMax((unsigned int *)&rec[aid].y, ((unsigned int)newlen << 16) | (unsigned int)(uint16_t)d.y);
-          atomicAdd(&rec[aid].weight, 1);
-        }
-        if (valid && (grp >> lane) <= 1u) cache[slot] = aid;   // highest lane of the group
-        n_anch += __popc(hm);
-        __syncwarp();
-      }
+      const int n_anch = collapse_lockstep(rec, cache, m_surv, rl, lane);
       if (lane == 0) s_nanch = n_anch;
     }
     __syncthreads();
@@ -1396,8 +1452,8 @@ __global__ void __launch_bounds__(SCAN_CTA_MAX_THREADS, 2) scan_cta_kernel(const
   if (P.mp_mode && !P.resume && tid == 0) P.mp_epoch[blockIdx.x] = mp_epoch;
 }
 
-size_t scan_smem_bytes(int cap, int max_rl, int k_cap, int bm_log2, int warps, bool alias_rec) {
-  return scan_layout(cap, max_rl, k_cap, bm_log2, alias_rec).total * warps;
+size_t scan_smem_bytes(int cap, int max_rl, int k_cap, int bm_log2, int warps, int stash) {
+  return scan_layout(cap, max_rl, k_cap, bm_log2, stash).total * warps;
 }
 // ---- heap-order replay for the strands with equal positions on different read offsets -------------------------
 // One warp per parked strand.  The k-way merge of the reference pops equal keys in binary-heap order
@@ -1510,7 +1566,7 @@ size_t scan_cta_smem_bytes(int cap, int max_rl, int k_cap, int bm_log2, int n_pa
 }
 
 int launch_scan(shrimp_gpu_ctx *ctx, ScanParams &P, int warps_per_cta, int n_ctas) {
-  const size_t smem = scan_smem_bytes(P.cap, P.max_rl, P.k_cap, P.bm_log2, warps_per_cta, P.alias_rec != 0);
+  const size_t smem = scan_smem_bytes(P.cap, P.max_rl, P.k_cap, P.bm_log2, warps_per_cta, P.stash);
   SH_CUDA(cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   scan_kernel<<<n_ctas, warps_per_cta * 32, smem, ctx->stream>>>(P, warps_per_cta);
   SH_CUDA(cudaGetLastError());

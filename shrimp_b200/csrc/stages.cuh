@@ -47,6 +47,7 @@ struct ScanParams {
   int bm_log2;             // log2 of the bits of each region bitmap
   int alias_rec;           // warp kernel: the anchors reuse the bitmaps (dead after pass B)
   int stream;              // warp kernel: lists long enough for one contiguous stream per lane
+  int stash;               // warp kernel: list entries staged per strand in shared memory (0 = off)
   // CTA kernel (scan_cta_kernel)
   int n_part;              // genome partitions of 2^bm_log2 regions each (exact region bitmaps)
   uint32_t *work_counter;  // dynamic work distribution
