@@ -217,25 +217,42 @@ int run_full_sw(shrimp_gpu_ctx *ctx, DevBuf &d_perm, DevBuf &d_row, DevBuf *d_bp
     cudaStream_t cst = c == 0 ? st : ctx->aux[(c - 1) % SHRIMP_AUX_STREAMS];
     if (c > 0) SH_CUDA(cudaStreamWaitEvent(cst, ctx->fork_ev, 0));
     ctx->stream = cst;  // the launchers use ctx->stream
-    // the forward-order tasks first, then the reverse-complement-order ones: a launch holds one kind
+    // the forward-order tasks first, then the reverse-complement-order ones: a launch holds one kind.  Within a
+    // kind the tasks are ordered by band width; runs of width buckets (at least 8192 tasks each) get a ring just wide
+    // enough for them -- the ring is what limits the resident warps of these kernels.
     for (int rev = 0; rev < 2; rev++) {
-    const int r0 = rev ? (int)cls_rev0[c] : 0, r1 = rev ? count : (int)cls_rev0[c];
-    for (int b0 = r0; b0 < r1; b0 += batch) {
-      FullParams Q = FP;
-      Q.perm = perm + cls_first[c] + b0;
-      Q.n_tasks = std::min(batch, r1 - b0);
-      Q.rev = rev;
-      Q.NT = batch;
-      Q.W = W;
-      Q.row = Q.row_cs = d_row.as<int32_t>();
-      Q.bp = Q.bp_cs = d_bp[c].as<uint8_t>();
-      Q.bp64 = d_bp[c].as<unsigned long long>();
-      int rc;
-      if (ring) rc = launch_sw_full_ring(ctx, Q, cs);
-      else if (cs) rc = launch_sw_full_cs(ctx, Q);
-      else rc = launch_sw_full_ls(ctx, Q);
-      if (rc != SHRIMP_OK) return rc;
-    }
+      int seg0 = rev ? (int)cls_rev0[c] : 0;
+      int acc = 0, kmax = -1;
+      for (int k = 0; k < 16; k++) {
+        const int nk = (int)kc[c * 32 + rev * 16 + k];
+        if (nk > 0) kmax = k;
+        acc += nk;
+        if (acc == 0 || ((acc < 8192 || !cs) && k < 15)) continue;   // letter space: one run (thread-per-alignment rings are cheap)
+        const int Wl = (ring && cs) ? std::max(4, (kmax + 1) * W / 16) : W;
+        const size_t per_task_l = ring ? (size_t)FP.max_rlen * Wl * (cs ? 8 : 1) : per_task;
+        int batch_l = ring ? (int)std::min<size_t>((size_t)acc, std::max<size_t>(1024, budget / per_task_l)) : batch;
+        batch_l = (batch_l + 127) & ~127;
+        if (ring && (size_t)batch_l * per_task_l > (size_t)batch * per_task) batch_l = batch;
+        for (int b0 = seg0; b0 < seg0 + acc; b0 += batch_l) {
+          FullParams Q = FP;
+          Q.perm = perm + cls_first[c] + b0;
+          Q.n_tasks = std::min(batch_l, seg0 + acc - b0);
+          Q.rev = rev;
+          Q.NT = batch_l;
+          Q.W = Wl;
+          Q.row = Q.row_cs = d_row.as<int32_t>();
+          Q.bp = Q.bp_cs = d_bp[c].as<uint8_t>();
+          Q.bp64 = d_bp[c].as<unsigned long long>();
+          int rc;
+          if (ring) rc = launch_sw_full_ring(ctx, Q, cs);
+          else if (cs) rc = launch_sw_full_cs(ctx, Q);
+          else rc = launch_sw_full_ls(ctx, Q);
+          if (rc != SHRIMP_OK) return rc;
+        }
+        seg0 += acc;
+        acc = 0;
+        kmax = -1;
+      }
     }
     ctx->stream = st;
     if (c > 0) {
