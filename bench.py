@@ -304,6 +304,7 @@ def main():
     ap.add_argument("--genome-mb", type=int, default=0, help="scale the synthetic genome (c3: default 300, 3000 = hg18 size)")
     ap.add_argument("--cpu-sample", type=int, default=200_000, help="reads in the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-threads", type=int, default=3, help="host threads (one context each) of the end-to-end leg")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -419,25 +420,30 @@ def main():
     value = world * n_reads * a.steps / (total_ms_max * 1e-3)
 
     # ---- end to end through the public API: pinned host buffers in, hits out -----------------------
-    # Two host threads per GPU, one context each (own stream and chunk buffers, shared index), the way
+    # A few host threads per GPU (--e2e-threads), one context each (own stream and chunk buffers, shared index), the way
     # gmapper's -N threads share the projection: the host half of a step (read_pass2 on the host cores, D2H)
     # overlaps the device half of the other thread's step.  Every step still uploads its reads and
     # downloads its records; K steps in total.
     import shrimp_b200
-    ctx2 = shrimp_b200.GpuContext(local_rank)
-    ctx2.sw_setup(1400, 1000, scores, use_colours=w.colour)
-    ctx2.share_genome_from(ctx)
-    codes2, initbp2_np = w.reads(n_reads, 1002 + rank)
-    packed2 = torch.from_numpy(pack_rows(codes2)).pin_memory().numpy()
-    initbp2 = torch.from_numpy(initbp2_np).pin_memory().numpy() if initbp2_np is not None else None
+    n_host = max(1, min(a.e2e_threads, a.steps))
+    workers = [map_host]
+    extra_ctx = []
+    for i in range(1, n_host):
+        cx = shrimp_b200.GpuContext(local_rank)
+        cx.sw_setup(1400, 1000, scores, use_colours=w.colour)
+        cx.share_genome_from(ctx)
+        codes_i, initbp_i_np = w.reads(n_reads, 1001 + i + 10 * rank)
+        packed_i = torch.from_numpy(pack_rows(codes_i)).pin_memory().numpy()
+        initbp_i = torch.from_numpy(initbp_i_np).pin_memory().numpy() if initbp_i_np is not None else None
 
-    def map_host2():
-        if w.paired:
-            return ctx2.map_pairs(params, scores, packed2, read_len, reuse_buffers=True)
-        return ctx2.map_reads(params, scores, packed2, read_len, initbp=initbp2, reuse_buffers=True)
+        def map_host_i(cx=cx, packed_i=packed_i, initbp_i=initbp_i):
+            if w.paired:
+                return cx.map_pairs(params, scores, packed_i, read_len, reuse_buffers=True)
+            return cx.map_reads(params, scores, packed_i, read_len, initbp=initbp_i, reuse_buffers=True)
 
-    map_host2()   # warm-up of the second context's buffers
-    workers = [map_host, map_host2]
+        map_host_i()   # warm-up of this context's buffers
+        workers.append(map_host_i)
+        extra_ctx.append(cx)
     todo = list(range(a.steps))
     lock = threading.Lock()
 
@@ -451,7 +457,7 @@ def main():
 
     barrier()
     t0 = time.perf_counter()
-    ths = [threading.Thread(target=work, args=(fn,)) for fn in workers[:max(1, min(2, a.steps))]]
+    ths = [threading.Thread(target=work, args=(fn,)) for fn in workers]
     for th in ths:
         th.start()
     for th in ths:
@@ -540,7 +546,7 @@ def main():
         "pipeline_stats": st,
         "clocks": clocks,
         "e2e": {"value": e2e_val, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "host_threads_per_gpu": 2},
+                "host_threads_per_gpu": n_host},
         "gpu_launches": launches,
         "roofline": roofline,
         "cpu_baseline": cpu,
