@@ -209,9 +209,11 @@ __global__ void select_unpaired_kernel(const Pass1Params P) {
   P.n_sel[r] = load;
 }
 
-// one thread per dense task: sw_gapless (common/sw-gapless.c:57-117, letter space) -- best ungapped segment on the
-// diagonal through the hit's anchor, walked over the WHOLE contig/read overlap as f1_run does (f1-wrapper.h:
-// 121-124: genome = contig, glen = contig length, g_idx = g_off + anchor.x, r_idx = anchor.y)
+// one thread per dense task: sw_gapless (common/sw-gapless.c:57-117) -- best ungapped segment on the diagonal
+// through the hit's anchor, walked over the WHOLE contig/read overlap as f1_run does (f1-wrapper.h:121-124: genome =
+// contig, glen = contig length, g_idx = g_off + anchor.x, r_idx = anchor.y).  Colour space (mapping.c:1297-1318):
+// strand-1 hits are reversed onto the reverse-complement arrays (reverse_hit :254-263), the read is the input-strand
+// one, and the first colour of the read is forced through the LETTER genome and the initial base (:83-93).
 __global__ void sw_gapless_kernel(const GaplessParams P) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= P.n_tasks) return;
@@ -221,12 +223,29 @@ __global__ void sw_gapless_kernel(const GaplessParams P) {
   const int rlen = P.rlen[t];
   const uint64_t coff = P.G.contig_off[h.cn];
   const int glen = (int)P.G.contig_len[h.cn];
-  const int g_idx = (int)h.g_off + h.ax, r_idx = h.ay;
+  int g_off = (int)h.g_off, ax = h.ax, ay = h.ay;
+  if (P.ori) {
+    g_off = glen - (int)h.g_off - h.w_len;
+    ax = -h.ax + (h.w_len - 1) - (h.alen - 1) - (h.awidth - 1);
+    ay = -h.ay + (rlen - 1) - (h.alen - 1) + (h.awidth - 1);
+  }
+  const uint32_t *genome = !P.cs ? P.G.ls : P.ori ? P.G.cs_rc : P.G.cs;
+  const int g_idx = g_off + ax, r_idx = ay;
   int g = g_idx < r_idx ? 0 : g_idx - r_idx;
   int r = g_idx < r_idx ? r_idx - g_idx : 0;
-  int score = 0, max_score = 0;
+  int score = 0;
+  if (P.cs && r == 0) {  // forcefully match the first colour of the read
+    const uint32_t *genome_ls = P.ori ? P.G.ls_rc : P.G.ls;
+    const uint32_t letter = extract4(genome_ls, coff + (uint64_t)g);
+    const int ib = P.initbp[t];
+    const uint32_t real_colour = (letter > 3u || (uint32_t)ib > 3u) ? 15u : (letter ^ (uint32_t)ib);  // lstocs
+    if (real_colour == extract4(read, 0)) score = P.match;
+    r++;
+    g++;
+  }
+  int max_score = score;
   while (g < glen && r < rlen) {
-    score += (extract4(P.G.ls, coff + (uint64_t)g) == extract4(read, (uint64_t)r)) ? P.match : P.mismatch;
+    score += (extract4(genome, coff + (uint64_t)g) == extract4(read, (uint64_t)r)) ? P.match : P.mismatch;
     if (score > max_score) max_score = score;
     g++;
     r++;

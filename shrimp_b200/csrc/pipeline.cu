@@ -338,10 +338,6 @@ int chunk_begin(Chunk &C, shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, int 
     set_error("%s: colour-space reads need initbp", who);
     return SHRIMP_E_ARG;
   }
-  if (mp->gapless && cs) {
-    set_error("%s: gapless (-U / mirna) pass 1 is wired for letter space only", who);
-    return SHRIMP_E_ARG;
-  }
   if (cs && mp->compute_mapping_qualities) {
     // hit_run_post_sw needs post_sw (common/sw-post.c), which is not on this path yet
     set_error("%s: colour space needs compute_mapping_qualities = 0 (--no-mapping-qualities) until post_sw is "
@@ -879,20 +875,25 @@ int chunk_vector(Chunk &C) {
       // -U / mirna: pass 1 ranks by sw_gapless; the sw_vector scores above still feed hit_run_full_sw (:386)
       SH_TRY(pl->d_vtrue[1].ensure(HU * 4));
       SH_CUDA(cudaMemsetAsync(pl->d_vtrue[1].p, 0xff, HU * 4, st));
-      GaplessParams GP;
-      memset(&GP, 0, sizeof(GP));
-      GP.G = C.G;
-      GP.hits = pl->d_hits.as<DevHit>();
-      GP.reads = pl->d_reads.as<uint32_t>();
-      GP.stride = C.stride;
-      GP.out = VT[0].out;
-      GP.ridx = VT[0].ridx;
-      GP.rlen = VT[0].rlen;
-      GP.n_tasks = n_dense[0];
-      GP.match = ctx->sw.match;
-      GP.mismatch = ctx->sw.mismatch;
-      GP.scores = pl->d_vtrue[1].as<int32_t>();
-      SH_TRY(launch_sw_gapless(ctx, GP));
+      for (int o = 0; o < C.n_ori; o++) {
+        GaplessParams GP;
+        memset(&GP, 0, sizeof(GP));
+        GP.G = C.G;
+        GP.hits = pl->d_hits.as<DevHit>();
+        GP.reads = pl->d_reads.as<uint32_t>();
+        GP.stride = C.stride;
+        GP.out = VT[o].out;
+        GP.ridx = VT[o].ridx;
+        GP.rlen = VT[o].rlen;
+        GP.initbp = VT[o].initbp;
+        GP.n_tasks = n_dense[o];
+        GP.match = ctx->sw.match;
+        GP.mismatch = cs ? ctx->sw.vec_mismatch : ctx->sw.mismatch;
+        GP.cs = cs ? 1 : 0;
+        GP.ori = o;
+        GP.scores = pl->d_vtrue[1].as<int32_t>();
+        SH_TRY(launch_sw_gapless(ctx, GP));
+      }
     }
   }
   return SHRIMP_OK;

@@ -102,8 +102,10 @@ struct GaplessParams {
   int stride;
   const uint32_t *out;     // hit slot per dense task
   const int32_t *ridx, *rlen;
+  const int8_t *initbp;    // colour space: per dense task
   uint32_t n_tasks;
   int match, mismatch;
+  int cs, ori;             // colour space; orientation of this launch's tasks (1: reversed onto the rc arrays)
   int32_t *scores;         // per hit slot
 };
 

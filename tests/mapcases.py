@@ -24,6 +24,12 @@ MAP_CASES = {
     # BASELINE.json configs[3]: 22 bp reads vs a miRNA-like database, default options and -M mirna (gmapper.c:
     # 1498-1515: hashed 5-seed set, gapless pass 1, gap opens -255, no window cache, one seed match, window 100 %,
     # local full SW, no mapping qualities)
+    # -U (ungapped) in colour space: sw_gapless with the first colour forced through the letter genome
+    # (sw-gapless.c:83-93), gap opens -255, anchor_width 0, no window cache; -U needs local mode (gmapper.c:2330)
+    "c2_small_ungapped": dict(gen="c2_small", args=["--no-mapping-qualities", "-U", "--local"],
+                              opts=dict(gapless=True, hash_filter_calls=False, Gflag=False,
+                                        compute_mapping_qualities=False),
+                              gap_open=-255, anchor_width=0),
     "c4_small": dict(gen="c4_small", args=[], opts={}),
     "c4_small_mirna": dict(gen="c4_small", args=["-M", "mirna"],
                            opts=dict(match_mode=1, window_len=100.0, gapless=True, hash_filter_calls=False,
@@ -75,6 +81,10 @@ class LsCase:
                                  self.scores.b_gap_ext, self.scores.crossover)
         else:
             self.seeds = S.load_default_seeds(spec.get("seeds_weight", 0))
+            if "gap_open" in spec:
+                from shrimp_b200.api import Scores
+                self.scores = Scores(self.scores.match, self.scores.mismatch, spec["gap_open"], self.scores.a_gap_ext,
+                                     spec["gap_open"], self.scores.b_gap_ext, self.scores.crossover)
         self.anchor_width = spec.get("anchor_width", 8)
         self.total_len = int(sum(c.size for c in self.contig_codes))
         from shrimp_b200.api import auto_list_cutoff
