@@ -183,6 +183,10 @@ typedef struct shrimp_map_params {
   int32_t strata, max_alignments;
   int32_t compute_mapping_qualities;
   uint32_t list_cutoff;         /* -z / automatic (gmapper.c:2811-2837) */
+  /* colour-space reads with qualities (-Q without --ignore-qvs): read_entry::crossover_score of every read
+   * (gmapper.c:532-543), rows of crossover_stride ints; NULL = the global crossover score for every position */
+  const int32_t *crossover_scores;
+  int32_t crossover_stride;
 } shrimp_map_params;
 
 /* One reported alignment: read_hit + sw_full_results (gmapper-definitions.h:125-153,

@@ -177,10 +177,17 @@ class Index:
 
 
 def map_reads(genome: Genome, index: Index, opts: MapOptions, reads: np.ndarray, read_len: np.ndarray,
-              initbp: np.ndarray | None = None, want_stage: bool = False, stage_cap_per_read: int = 256):
-    """Returns (hits structured array, n_out_per_read, stage array or None, stats dict)."""
+              initbp: np.ndarray | None = None, want_stage: bool = False, stage_cap_per_read: int = 256,
+              crossover_scores: np.ndarray | None = None):
+    """Returns (hits structured array, n_out_per_read, stage array or None, stats dict).  crossover_scores [n, w]
+    int32: read_entry::crossover_score of colour-space reads with qualities (gmapper.c:532-543)."""
     L = oracle_lib()
     L.orc_map_reads.restype = C.c_longlong
+    L.orc_set_crossover_scores.argtypes = [C.c_void_p, C.c_int]
+    L.orc_set_crossover_scores.restype = None
+    if crossover_scores is not None:
+        crossover_scores = np.ascontiguousarray(crossover_scores, dtype=np.int32)
+        L.orc_set_crossover_scores(_p(crossover_scores), int(crossover_scores.shape[1]))
     reads = np.ascontiguousarray(reads, dtype=np.uint32)
     read_len = np.ascontiguousarray(read_len, dtype=np.int32)
     n = reads.shape[0]
@@ -200,6 +207,7 @@ def map_reads(genome: Genome, index: Index, opts: MapOptions, reads: np.ndarray,
     rc = L.orc_map_reads(genome.h, index.h, C.byref(p), n, _p(reads), reads.shape[1], _p(read_len), _p(initbp),
                          C.cast(out, C.c_void_p), len(out), _p(n_per),
                          C.cast(stage, C.c_void_p) if want_stage else None, cap, C.byref(n_stage), C.byref(stats))
+    L.orc_set_crossover_scores(None, 0)
     if rc < 0:
         raise RuntimeError("oracle capacity too small")
     hits = np.ctypeslib.as_array(out)[:rc] if rc > 0 else np.ctypeslib.as_array(out)[:0]

@@ -89,6 +89,21 @@ def score_alpha_beta(scores: Scores, colour_space: bool, pr_xover: float = 0.03)
     return alpha, beta
 
 
+def crossover_scores_from_quals(quals, scores: Scores, qual_delta: int = 33, pr_xover: float = 0.03) -> np.ndarray:
+    """read_entry::crossover_score from the quality strings of colour-space reads, exactly as gmapper.c:532-543
+    (double arithmetic, same libm): (int)(alpha * log(pr_err(q) / 3) / log 2), clamped to [2 * crossover, -1]."""
+    alpha, _ = score_alpha_beta(scores, True, pr_xover)
+    width = max(len(q) for q in quals)
+    out = np.zeros((len(quals), width), dtype=np.int32)
+    for r, q in enumerate(quals):
+        for j, ch in enumerate(q):
+            qv = int(ch) - qual_delta
+            pr = .99999999 if qv <= 0 else 1e-25 if qv >= 250 else math.pow(10.0, -float(qv) / 10.0)   # util.h:285-293
+            v = int(alpha * math.log(pr / 3.0) / math.log(2.0))
+            out[r, j] = -1 if v > -1 else max(v, 2 * scores.crossover)
+    return out
+
+
 def auto_list_cutoff(total_genome_len: int, max_seed_weight: int) -> int:
     """automatic index trimming, gmapper.c:2811-2837: max(1000, 100*L/4^W)"""
     c = ((100 * total_genome_len) // (4 ** max_seed_weight)) & 0xFFFFFFFF
@@ -118,7 +133,7 @@ class MapParams:
     compute_mapping_qualities: bool = True
     list_cutoff: int = 0xFFFFFFFF
 
-    def to_c(self, scores: Scores, colour_space: bool) -> MapParamsC:
+    def to_c(self, scores: Scores, colour_space: bool, crossover_scores: np.ndarray | None = None) -> MapParamsC:
         alpha, beta = score_alpha_beta(scores, colour_space)
         vect = self.sw_vect_threshold
         if vect is None:
@@ -127,7 +142,9 @@ class MapParams:
                           self.sw_full_threshold, alpha, beta, self.match_mode, self.num_outputs,
                           self.num_tmp_outputs, int(self.gapless), int(self.hash_filter_calls), int(self.use_regions),
                           self.region_bits, self.region_overlap, int(self.Gflag), int(self.Tflag), int(self.strata),
-                          self.max_alignments, int(self.compute_mapping_qualities), self.list_cutoff & 0xFFFFFFFF)
+                          self.max_alignments, int(self.compute_mapping_qualities), self.list_cutoff & 0xFFFFFFFF,
+                          crossover_scores.ctypes.data if crossover_scores is not None else None,
+                          int(crossover_scores.shape[1]) if crossover_scores is not None else 0)
 
 
 @dataclass
@@ -301,12 +318,16 @@ class GpuContext:
         return b[:n]
 
     def map_reads(self, params: MapParams, scores: Scores, reads: np.ndarray, read_len, initbp=None,
-                  want_stage: bool = False, stage_cap_per_read: int = 256, reuse_buffers: bool = False) -> MapResult:
-        """handle_read (mapping.c:1773) for a chunk: returns what read_output would receive."""
+                  want_stage: bool = False, stage_cap_per_read: int = 256, reuse_buffers: bool = False,
+                  crossover_scores: np.ndarray | None = None) -> MapResult:
+        """handle_read (mapping.c:1773) for a chunk: returns what read_output would receive.  crossover_scores
+        [n, >= max read length] int32: read_entry::crossover_score of colour-space reads that came with qualities."""
         reads = np.ascontiguousarray(reads, dtype=np.uint32)
         read_len = np.ascontiguousarray(read_len, dtype=np.int32)
         n = reads.shape[0]
-        pc = params.to_c(scores, getattr(self, "colour_space", False))
+        if crossover_scores is not None:
+            crossover_scores = np.ascontiguousarray(crossover_scores, dtype=np.int32)
+        pc = params.to_c(scores, getattr(self, "colour_space", False), crossover_scores)
         hits = self._buf("hits", max(1, n * params.num_outputs), HitC, reuse_buffers)   # untouched pages cost nothing
         n_per = self._buf("n_per", max(1, n), np.int32, reuse_buffers)
         max_rl = int(read_len.max()) if n else 0

@@ -133,13 +133,13 @@ void free_pipeline(shrimp_gpu_ctx *ctx) {
   Pipeline *p = (Pipeline *)ctx->pipeline;
   if (!p) return;
   DevBuf *bufs[] = {&p->d_in, &p->d_reads, &p->d_read_len, &p->d_initbp, &p->d_hits, &p->d_rs_range, &p->d_counters,
-                    &p->d_overflow, &p->d_overflow2, &p->d_scan_slab, &p->d_tie_ent, &p->d_tie_order, &p->d_tie_rec, &p->d_prof, &p->d_mp_tab, &p->d_mp_epoch, &p->d_scratch, &p->d_task[0], &p->d_task[1], &p->d_vtrue[0], &p->d_vtrue[1],
+                    &p->d_overflow, &p->d_overflow2, &p->d_scan_slab, &p->d_tie_ent, &p->d_tie_order, &p->d_tie_rec, &p->d_prof, &p->d_mp_tab, &p->d_mp_epoch, &p->d_xover, &p->d_scratch, &p->d_task[0], &p->d_task[1], &p->d_vtrue[0], &p->d_vtrue[1],
                     &p->d_slot, &p->d_writer, &p->d_sel, &p->d_nsel, &p->d_ftasks, &p->d_finfo, &p->d_fresults,
                     &p->d_frow, &p->d_fbp[0], &p->d_fbp[1], &p->d_fbp[2], &p->d_fbp[3], &p->d_fbp[4], &p->d_fops,
                     &p->d_taskoff, &p->d_scan_tmp, &p->d_perm, &p->d_pair_min, &p->d_pair_max, &p->d_saved, &p->d_pairsel,
                     &p->d_npairsel, &p->d_taskof, &p->d_pairoff};
   for (DevBuf *b : bufs) b->release();
-  HostBuf *hb[] = {&p->h_info, &p->h_results, &p->h_ops, &p->h_nsel, &p->h_hits, &p->h_range,
+  HostBuf *hb[] = {&p->h_info, &p->h_results, &p->h_ops, &p->h_nsel, &p->h_hits, &p->h_range, &p->h_xover,
                    &p->h_pairsel, &p->h_npairsel, &p->h_saved};
   for (HostBuf *b : hb) b->release();
   delete p;
@@ -433,6 +433,20 @@ int chunk_begin(Chunk &C, shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, int 
     if (cs) {
       SH_TRY(pl->d_initbp.ensure((size_t)n_reads));
       SH_CUDA(cudaMemcpyAsync(pl->d_initbp.p, initbp, (size_t)n_reads, cudaMemcpyHostToDevice, st));
+    }
+    pl->xover_stride = 0;
+    if (cs && mp->crossover_scores && mp->crossover_stride > 0) {
+      // per-position crossover scores (reads with qualities): 16 bits each on the device
+      const int xs = mp->crossover_stride;
+      SH_TRY(pl->h_xover.ensure((size_t)n_reads * xs * 2));
+      int16_t *hx = pl->h_xover.as<int16_t>();
+      for (size_t q = 0; q < (size_t)n_reads * xs; q++) {
+        const int32_t v = mp->crossover_scores[q];
+        hx[q] = (int16_t)(v < -32768 ? -32768 : v > 0 ? 0 : v);
+      }
+      SH_TRY(pl->d_xover.ensure((size_t)n_reads * xs * 2));
+      SH_CUDA(cudaMemcpyAsync(pl->d_xover.p, hx, (size_t)n_reads * xs * 2, cudaMemcpyHostToDevice, st));
+      pl->xover_stride = xs;
     }
     pl->res_n_reads = n_reads;
     pl->res_stride = stride;
@@ -996,6 +1010,8 @@ int chunk_run_full(Chunk &C, int n_slots) {
   FP.local = C.mp->Gflag ? 0 : 1;
   FP.cells = (unsigned long long *)(C.cnt + 16);
   FP.xover = sw.xover;
+  FP.xover_pos = pl->xover_stride ? pl->d_xover.as<int16_t>() : nullptr;
+  FP.xover_stride = pl->xover_stride;
   FP.indel_taboo_len = sw.indel_taboo_len;
   return run_full_sw(ctx, pl->d_perm, pl->d_frow, pl->d_fbp, FP, n_slots, C.cs, C.cnt + 32);
 }

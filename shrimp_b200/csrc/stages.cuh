@@ -161,6 +161,8 @@ struct FullParams {
   unsigned long long *cells;
   // colour space (sw_full_cs.cu)
   int xover, indel_taboo_len;
+  const int16_t *xover_pos;   // per read position crossover scores [n_reads][xover_stride] (reads with qualities), or nullptr
+  int xover_stride;
   int32_t *row_cs;  // [12][max_glen+1][NT]
   uint8_t *bp_cs;   // [max_rlen*max_glen*12][NT]
   // band-ring kernels (sw_full_ring.cu): task ids of this launch (nullptr = identity), ring width,

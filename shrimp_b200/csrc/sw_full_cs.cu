@@ -47,7 +47,8 @@ __device__ int full_sw_cs_dev(const FullParams &P, const FullTask &T, int t, con
   for (int i = 0; i < lenb; i++) {
     int x_min, x_max;
     rect_x_range(rect, lena, i, x_min, x_max);
-    const int xp = P.xover;  // FASTA reads: global crossover penalty (per-position scores need qualities)
+    // global crossover penalty, or the read position's when the read came with qualities (sw-full-cs.c:312)
+    const int xp = P.xover_pos ? (int)P.xover_pos[(size_t)(T.ridx >> 1) * (size_t)P.xover_stride + i] : P.xover;
     const bool nt = i < lenb - P.indel_taboo_len;
     const int colour = (int)extract4(read, (uint64_t)i);
     int qk[4];

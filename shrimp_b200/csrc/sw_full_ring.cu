@@ -572,10 +572,9 @@ __device__ int quad_cs_dp(const FullParams &P, const FullTask &T, bool run, int 
   int score = 0, max_i = 0, max_j = 0;
   int letter = (k + T.initbp) % 4;
   int pxmin = 0, pxmax = -1;
-  const int xp = P.xover;
-  const int add = k == 0 ? 0 : xp;
-  const int ini_n = LOCAL ? -bo + add : NEG_Q, ini_w = LOCAL ? -ao + add : NEG_Q, ini_nw = LOCAL ? add : NEG_Q;
-  const int resetval = k != 0 ? xp : 0;
+  // crossover penalty: global, or per read position when the read came with qualities (sw-full-cs.c:312)
+  const int16_t *xrow = P.xover_pos ? P.xover_pos + (size_t)(T.ridx >> 1) * (size_t)P.xover_stride : nullptr;
+  int add_prev = k == 0 ? 0 : P.xover;   // what row -1 was initialised with: the global penalty (:268-270)
   const int match = P.match, mismatch = P.mismatch;
   const int nrows_w = warp_max_i(lenb);
   for (int i = 0; i < nrows_w; i++) {
@@ -596,9 +595,14 @@ __device__ int quad_cs_dp(const FullParams &P, const FullTask &T, bool run, int 
       }
       if (k == 0) cells += (unsigned long long)width;
     }
-    // what a cell of the previous row reads as when it lies right of that row's band: the initial cell, or
-    // row -1 itself (local-style init with the global crossover penalty, sw-full-cs.c:268-270)
-    const int r_n = i == 0 ? -bo + add : ini_n, r_w = i == 0 ? -ao + add : ini_w, r_nw = i == 0 ? add : ini_nw;
+    const int xp = (xrow && row_on) ? (int)xrow[i] : P.xover;
+    const int add = k == 0 ? 0 : xp;
+    const int ini_n = LOCAL ? -bo + add : NEG_Q, ini_w = LOCAL ? -ao + add : NEG_Q, ini_nw = LOCAL ? add : NEG_Q;
+    const int resetval = k != 0 ? xp : 0;
+    // what a cell of the previous row reads as when it lies right of that row's band: the initial cell written
+    // with that row's penalty (:604-612), or row -1 itself (local-style init with the global crossover penalty)
+    const int r_n = (i == 0 || LOCAL) ? -bo + add_prev : NEG_Q, r_w = (i == 0 || LOCAL) ? -ao + add_prev : NEG_Q,
+              r_nw = (i == 0 || LOCAL) ? add_prev : NEG_Q;
     int d_n = r_n, d_w = r_w, d_nw = r_nw;
     const int delta = x_min - pxmin;
     if (row_on && i > 0 && x_min - 1 <= pxmax) {
@@ -703,6 +707,7 @@ __device__ int quad_cs_dp(const FullParams &P, const FullTask &T, bool run, int 
     if (row_on) {
       pxmin = x_min;
       pxmax = x_max;
+      add_prev = add;
     }
   }
   ret_i = max_i;

@@ -30,6 +30,12 @@ MAP_CASES = {
                               opts=dict(gapless=True, hash_filter_calls=False, Gflag=False,
                                         compute_mapping_qualities=False),
                               gap_open=-255, anchor_width=0),
+    # colour-space reads WITH qualities (-Q): per-position crossover scores in sw_full_cs (gmapper.c:532-543,
+    # sw-full-cs.c:312); qualities are seeded, 2..40, PHRED+33
+    "c2_small_fastq": dict(gen="c2_small", args=["-Q", "--no-mapping-qualities"],
+                           opts={"compute_mapping_qualities": False}, fastq=True),
+    "c2_small_fastq_local": dict(gen="c2_small", args=["-Q", "--no-mapping-qualities", "--local"],
+                                 opts={"compute_mapping_qualities": False, "Gflag": False}, fastq=True),
     "c4_small": dict(gen="c4_small", args=[], opts={}),
     "c4_small_mirna": dict(gen="c4_small", args=["-M", "mirna"],
                            opts=dict(match_mode=1, window_len=100.0, gapless=True, hash_filter_calls=False,
@@ -86,6 +92,13 @@ class LsCase:
                 self.scores = Scores(self.scores.match, self.scores.mismatch, spec["gap_open"], self.scores.a_gap_ext,
                                      spec["gap_open"], self.scores.b_gap_ext, self.scores.crossover)
         self.anchor_width = spec.get("anchor_width", 8)
+        self.quals = None
+        self.crossover_scores = None
+        if spec.get("fastq"):
+            from shrimp_b200.api import crossover_scores_from_quals
+            rq = np.random.default_rng(4242)
+            self.quals = [(33 + rq.integers(2, 41, size=int(n))).astype(np.uint8) for n in self.read_len]
+            self.crossover_scores = crossover_scores_from_quals(self.quals, self.scores, qual_delta=33)
         self.total_len = int(sum(c.size for c in self.contig_codes))
         from shrimp_b200.api import auto_list_cutoff
         self.list_cutoff = spec.get("list_cutoff", auto_list_cutoff(
@@ -94,7 +107,12 @@ class LsCase:
     def write_fasta(self, d: str):
         os.makedirs(d, exist_ok=True)
         gen_synth.write_fasta(os.path.join(d, "genome.fa"), self.contigs, width=80)
-        gen_synth.write_fasta(os.path.join(d, "reads.fa"), self.reads)
+        if self.quals is None:
+            gen_synth.write_fasta(os.path.join(d, "reads.fa"), self.reads)
+        else:   # FASTQ (gmapper -Q); colour-space reads carry one quality per colour, none for the primer base
+            with open(os.path.join(d, "reads.fa"), "wb") as f:
+                for (name, seq), q in zip(self.reads, self.quals):
+                    f.write(b"@" + name.encode() + b"\n" + bytes(seq) + b"\n+\n" + bytes(q) + b"\n")
 
 
 def stage_tuple_array(stage) -> np.ndarray:

@@ -18,7 +18,8 @@ def run_gpu(ctx, case, **over):
                     colour_space=case.colour)
     ctx.build_index(case.seeds, hflag=case.hflag)
     params = MapParams(list_cutoff=case.list_cutoff, **over)
-    return ctx.map_reads(params, case.scores, case.packed, case.read_len, initbp=case.initbp, want_stage=True)
+    return ctx.map_reads(params, case.scores, case.packed, case.read_len, initbp=case.initbp, want_stage=True,
+                         crossover_scores=case.crossover_scores)
 
 
 def sam_arrays(case, res):
