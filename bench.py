@@ -369,6 +369,9 @@ def main():
     initbp = torch.from_numpy(initbp_np).pin_memory().numpy() if initbp_np is not None else None
 
     ctx, scores, seeds, index_s = build_context(w, local_rank)
+    # torchrun exports OMP_NUM_THREADS=1: give every rank its share of the host cores for the host stages
+    from shrimp_b200.api import set_host_threads
+    set_host_threads(max(1, ncores // max(1, world)))
     params = MapParams(list_cutoff=auto_list_cutoff(w.genome_len, 12), compute_mapping_qualities=not w.colour,
                        match_mode=4 if w.paired else 2)
 

@@ -299,6 +299,10 @@ int shrimp_gpu_flush_l2(shrimp_gpu_ctx *ctx);
  * ---------------------------------------------------------------------------------------- */
 int shrimp_gpu_dpx_peak(shrimp_gpu_ctx *ctx, double *ginstr_per_s);
 
+/* Host threads of the stages that stay on the CPU as in the reference (read_pass2's duplicate removal and ranking,
+ * the -N threads of gmapper.c:2907): n > 0 fixes the count, 0 = the OpenMP default. Process-wide. */
+int shrimp_gpu_set_host_threads(int n);
+
 #ifdef __cplusplus
 }
 #endif

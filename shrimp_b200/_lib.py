@@ -110,6 +110,8 @@ def lib() -> C.CDLL:
     L.shrimp_gpu_sw_full_batch.restype = i32
     L.shrimp_gpu_dpx_peak.argtypes = [vp, C.POINTER(C.c_double)]
     L.shrimp_gpu_dpx_peak.restype = i32
+    L.shrimp_gpu_set_host_threads.argtypes = [C.c_int]
+    L.shrimp_gpu_set_host_threads.restype = i32
     L.shrimp_gpu_genome_load.argtypes = [vp, i32, vp, vp, i32]
     L.shrimp_gpu_genome_load.restype = i32
     L.shrimp_gpu_share_genome.argtypes = [vp, vp]

@@ -104,6 +104,12 @@ def crossover_scores_from_quals(quals, scores: Scores, qual_delta: int = 33, pr_
     return out
 
 
+def set_host_threads(n: int) -> None:
+    """host threads of the stages the reference also runs on the CPU (read_pass2 ranking); 0 = OpenMP default"""
+    from ._lib import lib
+    lib().shrimp_gpu_set_host_threads(int(n))
+
+
 def auto_list_cutoff(total_genome_len: int, max_seed_weight: int) -> int:
     """automatic index trimming, gmapper.c:2811-2837: max(1000, 100*L/4^W)"""
     c = ((100 * total_genome_len) // (4 ** max_seed_weight)) & 0xFFFFFFFF

@@ -9,6 +9,7 @@
 #include <stdlib.h>
 #include <algorithm>
 #include <omp.h>
+#include <atomic>
 #include <cub/cub.cuh>
 #include "chunk.cuh"
 
@@ -1158,12 +1159,20 @@ static int host_pass2_select(const Chunk &C, int r, int n1, int task_base, doubl
   return n2;
 }
 
+// host threads of the OpenMP stages; 0 = omp_get_max_threads() (launchers such as torchrun set OMP_NUM_THREADS=1)
+static std::atomic<int> g_host_threads{0};
+extern "C" int shrimp_gpu_set_host_threads(int n) {
+  g_host_threads.store(n < 0 ? 0 : n);
+  return SHRIMP_OK;
+}
+
 // read_pass2 for every read of the chunk (n_sel[r] tasks each, in task order), OpenMP over contiguous blocks
 // of reads: the duplicate removal and ranking stay the reference's qsort-based code, only the
 // loop over reads is parallel.  Appends to O in read order; n_per_read[r] = hits kept for read r.
 int host_pass2_all(const Chunk &C, const int32_t *n_sel, double full_thr, HostOut &O, int32_t *n_per_read) {
   const int n_reads = C.n_reads, NT = C.mp->num_tmp_outputs, NO = C.mp->num_outputs;
-  const int T = std::max(1, std::min(omp_get_max_threads(), 64));
+  const int want_T = g_host_threads.load() > 0 ? g_host_threads.load() : omp_get_max_threads();
+  const int T = std::max(1, std::min(want_T, 64));
   std::vector<std::vector<KeptRec>> kept((size_t)T);
   std::vector<std::vector<int32_t>> counts((size_t)T);
   std::vector<int64_t> nh((size_t)T + 1, 0), ne((size_t)T + 1, 0);
