@@ -34,7 +34,7 @@ __device__ __forceinline__ int cstols_r(int first_letter, int colour) {  // util
 // ------------------------------------------------------------------------------------------------
 // letter space
 // ------------------------------------------------------------------------------------------------
-template <bool LOCAL, int BLOCK>
+template <bool LOCAL, int BLOCK, bool REV>
 __device__ int ring_ls_dp(const FullParams &P, const FullTask &T, int slot, int32_t *sm, const uint32_t *genome,
                           const uint32_t *read, const Rect &rect, int &ret_i, int &ret_j, int &end_n, int &end_w,
                           int &end_nw, unsigned long long &cells) {
@@ -43,7 +43,7 @@ __device__ int ring_ls_dp(const FullParams &P, const FullTask &T, int slot, int3
   const int lena = T.glen, lenb = T.rlen;
   const size_t NT = (size_t)P.NT;
   const int ao = P.a_open, ae = P.a_ext, bo = P.b_open, be = P.b_ext;
-  const bool revcmpl = T.gen_st && P.Tflag;
+  constexpr bool revcmpl = REV;   // T.gen_st && P.Tflag of every task of the launch (the tasks are grouped by it)
   uint8_t *bp = P.bp + slot;
   int score = 0, max_i = 0, max_j = 0;
   const int init_nw = LOCAL ? 0 : NEG_HALF, init_n = LOCAL ? -bo : NEG_HALF, init_w = LOCAL ? -ao : NEG_HALF;
@@ -122,7 +122,7 @@ __device__ int ring_ls_dp(const FullParams &P, const FullTask &T, int slot, int3
   return score;
 }
 
-template <int BLOCK>
+template <int BLOCK, bool REV>
 __global__ void __launch_bounds__(BLOCK) sw_full_ls_ring_kernel(const FullParams P) {
   extern __shared__ int32_t ring_smem[];
   const int slot = blockIdx.x * BLOCK + threadIdx.x;
@@ -142,14 +142,14 @@ __global__ void __launch_bounds__(BLOCK) sw_full_ls_ring_kernel(const FullParams
   int ei = 0, ej = 0, score, e_n = 0, e_w = 0, e_nw = 0;
   Rect rect = task_rect(T, P.anchor_width, P.match, true);
   if (P.local) {
-    score = ring_ls_dp<true, BLOCK>(P, T, slot, sm, genome, read, rect, ei, ej, e_n, e_w, e_nw, cells);
+    score = ring_ls_dp<true, BLOCK, REV>(P, T, slot, sm, genome, read, rect, ei, ej, e_n, e_w, e_nw, cells);
     if (score != T.maxscore) {  // sw-full-ls.c:395-398: redo with the threshold band
       e_n = e_w = e_nw = 0;
       rect = task_rect(T, P.anchor_width, P.match, false);
-      score = ring_ls_dp<true, BLOCK>(P, T, slot, sm, genome, read, rect, ei, ej, e_n, e_w, e_nw, cells);
+      score = ring_ls_dp<true, BLOCK, REV>(P, T, slot, sm, genome, read, rect, ei, ej, e_n, e_w, e_nw, cells);
     }
   } else {
-    score = ring_ls_dp<false, BLOCK>(P, T, slot, sm, genome, read, rect, ei, ej, e_n, e_w, e_nw, cells);
+    score = ring_ls_dp<false, BLOCK, REV>(P, T, slot, sm, genome, read, rect, ei, ej, e_n, e_w, e_nw, cells);
   }
   R.score = score;
   // ---- do_backtrace (sw-full-ls.c:413-516) ----
@@ -873,8 +873,13 @@ int launch_sw_full_ring(shrimp_gpu_ctx *ctx, const FullParams &P, bool cs) {
       else RING_LAUNCH((sw_full_cs_quad_kernel<false, false>));
     }
   } else {
-    if (block == 64) RING_LAUNCH(sw_full_ls_ring_kernel<64>);
-    else RING_LAUNCH(sw_full_ls_ring_kernel<32>);
+    if (P.rev) {
+      if (block == 64) RING_LAUNCH((sw_full_ls_ring_kernel<64, true>));
+      else RING_LAUNCH((sw_full_ls_ring_kernel<32, true>));
+    } else {
+      if (block == 64) RING_LAUNCH((sw_full_ls_ring_kernel<64, false>));
+      else RING_LAUNCH((sw_full_ls_ring_kernel<32, false>));
+    }
   }
 #undef RING_LAUNCH
   SH_CUDA(cudaGetLastError());
