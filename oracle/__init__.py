@@ -106,7 +106,7 @@ class RefSw:
 class OrcSfrC(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("read_start", "rmapped", "genome_start", "gmapped", "matches", "mismatches",
                                        "insertions", "deletions", "score", "crossovers")] + \
-               [("dbalign", C.c_char * 640), ("qralign", C.c_char * 640)]
+               [("dbalign", C.c_char * 640), ("qralign", C.c_char * 640), ("qual", C.c_char * 640)]
 
 
 class RefSfrC(C.Structure):

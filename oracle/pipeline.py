@@ -16,7 +16,7 @@ ALN_CAP = 640
 class OrcSfr(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("read_start", "rmapped", "genome_start", "gmapped", "matches", "mismatches",
                                        "insertions", "deletions", "score", "crossovers")] + \
-               [("dbalign", C.c_char * ALN_CAP), ("qralign", C.c_char * ALN_CAP)]
+               [("dbalign", C.c_char * ALN_CAP), ("qralign", C.c_char * ALN_CAP), ("qual", C.c_char * ALN_CAP)]
 
 
 class OrcParams(C.Structure):
@@ -178,7 +178,7 @@ class Index:
 
 def map_reads(genome: Genome, index: Index, opts: MapOptions, reads: np.ndarray, read_len: np.ndarray,
               initbp: np.ndarray | None = None, want_stage: bool = False, stage_cap_per_read: int = 256,
-              crossover_scores: np.ndarray | None = None):
+              crossover_scores: np.ndarray | None = None, quals=None, qual_delta: int = 33):
     """Returns (hits structured array, n_out_per_read, stage array or None, stats dict).  crossover_scores [n, w]
     int32: read_entry::crossover_score of colour-space reads with qualities (gmapper.c:532-543)."""
     L = oracle_lib()
@@ -188,6 +188,15 @@ def map_reads(genome: Genome, index: Index, opts: MapOptions, reads: np.ndarray,
     if crossover_scores is not None:
         crossover_scores = np.ascontiguousarray(crossover_scores, dtype=np.int32)
         L.orc_set_crossover_scores(_p(crossover_scores), int(crossover_scores.shape[1]))
+    L.orc_set_read_quals.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.orc_set_read_quals.restype = None
+    qbuf = None
+    if quals is not None:   # post_sw reads re->qual (gmapper -Q)
+        w = max(len(q) for q in quals) + 1
+        qbuf = np.zeros((len(quals), w), dtype=np.uint8)
+        for r, q in enumerate(quals):
+            qbuf[r, :len(q)] = np.frombuffer(bytes(q), dtype=np.uint8)
+        L.orc_set_read_quals(_p(qbuf), w, qual_delta, 0, 1)
     reads = np.ascontiguousarray(reads, dtype=np.uint32)
     read_len = np.ascontiguousarray(read_len, dtype=np.int32)
     n = reads.shape[0]
@@ -208,6 +217,7 @@ def map_reads(genome: Genome, index: Index, opts: MapOptions, reads: np.ndarray,
                          C.cast(out, C.c_void_p), len(out), _p(n_per),
                          C.cast(stage, C.c_void_p) if want_stage else None, cap, C.byref(n_stage), C.byref(stats))
     L.orc_set_crossover_scores(None, 0)
+    L.orc_set_read_quals(None, 0, 33, 0, 1)
     if rc < 0:
         raise RuntimeError("oracle capacity too small")
     hits = np.ctypeslib.as_array(out)[:rc] if rc > 0 else np.ctypeslib.as_array(out)[:0]

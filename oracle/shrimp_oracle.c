@@ -1,4 +1,5 @@
 /* TEST INFRASTRUCTURE ONLY -- see shrimp_oracle.h. */
+#include <ctype.h>
 #include <limits.h>
 #include <math.h>
 #include <stdint.h>

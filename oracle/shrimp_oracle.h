@@ -75,6 +75,7 @@ typedef struct orc_sfr {
   int matches, mismatches, insertions, deletions, score, crossovers;
   char dbalign[ORC_ALN_CAP];
   char qralign[ORC_ALN_CAP];
+  char qual[ORC_ALN_CAP];      /* sfrp->qual: base qualities from post_sw (colour space with mapping qualities) */
 } orc_sfr;
 
 void orc_sw_full_ls(const uint32_t *genome, int goff, int glen, const uint32_t *read, int rlen,

@@ -36,6 +36,9 @@ MAP_CASES = {
                            opts={"compute_mapping_qualities": False}, fastq=True),
     "c2_small_fastq_local": dict(gen="c2_small", args=["-Q", "--no-mapping-qualities", "--local"],
                                  opts={"compute_mapping_qualities": False, "Gflag": False}, fastq=True),
+    # colour space with mapping qualities (the reference's default): post_sw (sw-post.c) rescoring every alignment
+    "c2_small_mq": dict(gen="c2_small", args=[], opts={}),
+    "c2_small_fastq_mq": dict(gen="c2_small", args=["-Q"], opts={}, fastq=True),
     "c4_small": dict(gen="c4_small", args=[], opts={}),
     "c4_small_mirna": dict(gen="c4_small", args=["-M", "mirna"],
                            opts=dict(match_mode=1, window_len=100.0, gapless=True, hash_filter_calls=False,

@@ -16,7 +16,7 @@ def run_oracle(case: LsCase, **over):
     opts = op.MapOptions(scores=case.scores, colour_space=case.colour, list_cutoff=case.list_cutoff,
                          anchor_width=case.anchor_width, **over)
     hits, nper, stage, stats = op.map_reads(g, ix, opts, case.packed, case.read_len, initbp=case.initbp,
-                                            want_stage=True, crossover_scores=case.crossover_scores)
+                                            want_stage=True, crossover_scores=case.crossover_scores, quals=case.quals)
     return g, hits, nper, stage, stats
 
 
