@@ -375,6 +375,37 @@ def sam_fields(hit, read_len: int, genome_len_cn: int, colour_space: bool = Fals
     return (16 if reverse else 0, int(hit["cn"]), pos, cigar, int(hit["score_full"]), nm, int(sfr["gmapped"]))
 
 
+def parse_sam_seq_qual(path: str):
+    """[(SEQ, QUAL)] of the mapped records, in file order (colour space with mapping qualities: the corrected base
+    calls and base qualities of post_sw, gmapper/output.c:483-640)."""
+    out = []
+    with open(path) as f:
+        for line in f:
+            if line.startswith("@"):
+                continue
+            t = line.rstrip("\n").split("\t")
+            if int(t[1]) & 4:
+                continue
+            out.append((t[9], t[10]))
+    return out
+
+
+_RC = bytes.maketrans(b"ACGTacgt", b"TGCAtgca")
+
+
+def seq_qual_of_alignment(qralign: bytes, qual: bytes, reverse: bool, have_quals: bool):
+    """SEQ / QUAL columns hit_output prints for a colour-space alignment with mapping qualities (output.c:486-546,
+    :607-616, :626-628): the letters of qralign upper-cased (reverse-complemented on the reverse strand), and
+    sfrp->qual (reversed there) when the reads came with qualities, else '*'."""
+    seq = bytes(c for c in qralign if c != ord("-")).upper()
+    q = bytes(qual) if have_quals else b"*"
+    if reverse:
+        seq = seq.translate(_RC)[::-1]
+        if have_quals:
+            q = q[::-1]
+    return seq.decode(), q.decode()
+
+
 def parse_sam(path: str):
     """[(qname, flag, rname, pos, cigar, AS, NM)] for mapped records, in file order."""
     out = []

@@ -56,6 +56,7 @@ def golden_mapping():
             dbg = subprocess.run([os.path.join(ref_dir, "dbgbin", case.binary), *spec["args"], "reads.fa", "genome.fa"],
                                  cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, check=True, text=True).stderr
             recs = op.parse_sam(sam)
+            seq_qual = op.parse_sam_seq_qual(sam) if name.endswith("_mq") else None
         name2idx = {n: i for i, n in enumerate(case.read_names)}
         cn2idx = {n: i for i, n in enumerate(case.contig_names)}
         sam_int = np.array([[name2idx[r[0]], r[1], cn2idx[r[2]], r[3], r[5], r[6]] for r in recs], dtype=np.int64)
@@ -80,8 +81,11 @@ def golden_mapping():
                         ax = -ax + (v[4] - 1) - (v[11] - 1) - (v[12] - 1)
                         ay = -ay + (int(case.read_len[ridx]) - 1) - (v[11] - 1) + (v[12] - 1)
                     stage.append((ridx, st, v[0], v[3], v[4], v[5], v[6], v[8], ax, ay, v[11], v[12]))
+        extra = {}
+        if seq_qual is not None:
+            extra = dict(seq=np.array([a for a, _ in seq_qual]), qual=np.array([b for _, b in seq_qual]))
         np.savez_compressed(os.path.join(HERE, f"map_{name}.npz"), sam=sam_int, cigars=cigars,
-                            stage=np.array(stage, dtype=np.int64))
+                            stage=np.array(stage, dtype=np.int64), **extra)
         print("wrote map", name, sam_int.shape, len(stage))
 
 

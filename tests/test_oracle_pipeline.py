@@ -39,6 +39,12 @@ def test_oracle_pipeline_matches_reference_golden(name):
     assert np.array_equal(sam, gold["sam"])
     assert np.array_equal(cig, gold["cigars"])
     assert np.array_equal(stage_tuple_array(stage), gold["stage"])
+    if "seq" in gold:   # colour space with mapping qualities: post_sw's corrected base calls and base qualities
+        sq = [op.seq_qual_of_alignment(bytes(h["sfr"]["qralign"]).split(b"\0")[0],
+                                       bytes(h["sfr"]["qual"]).split(b"\0")[0], int(h["gen_st"]) == 1,
+                                       case.quals is not None) for h in hits]
+        assert [a for a, _ in sq] == gold["seq"].tolist()
+        assert [b for _, b in sq] == gold["qual"].tolist()
 
 
 def test_oracle_index_is_sorted_csr():
