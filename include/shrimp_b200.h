@@ -187,6 +187,15 @@ typedef struct shrimp_map_params {
    * (gmapper.c:532-543), rows of crossover_stride ints; NULL = the global crossover score for every position */
   const int32_t *crossover_scores;
   int32_t crossover_stride;
+  /* colour space with compute_mapping_qualities: post_sw (common/sw-post.c) rescoring.  read_quals = the quality
+   * strings of the reads as read (re->qual, gmapper -Q; rows of qual_stride bytes) or NULL for reads without
+   * qualities; qual_delta / qual_vector_offset / use_sanger_qvs as post_sw_setup gets them (gmapper.c:2960-2962);
+   * pr_xover as -X (0 = the default .03).  Every reported alignment then carries sfrp->posterior, the corrected base
+   * calls (edit bytes with bit 3 set: bits 4-5 are the base itself, bit 2 = lower case) and, right after its edit
+   * script in `edits`, rmapped bytes of base qualities (sfrp->qual, 33 + q). */
+  const uint8_t *read_quals;
+  int32_t qual_stride, qual_delta, qual_vector_offset, use_sanger_qvs;
+  double pr_xover;
 } shrimp_map_params;
 
 /* One reported alignment: read_hit + sw_full_results (gmapper-definitions.h:125-153,

@@ -30,7 +30,9 @@ class MapParamsC(C.Structure):
                [(n, C.c_int32) for n in ("match_mode", "num_outputs", "num_tmp_outputs", "gapless", "hash_filter_calls",
                                          "use_regions", "region_bits", "region_overlap", "Gflag", "Tflag", "strata",
                                          "max_alignments", "compute_mapping_qualities")] + \
-               [("list_cutoff", C.c_uint32), ("crossover_scores", C.c_void_p), ("crossover_stride", C.c_int32)]
+               [("list_cutoff", C.c_uint32), ("crossover_scores", C.c_void_p), ("crossover_stride", C.c_int32),
+                ("read_quals", C.c_void_p), ("qual_stride", C.c_int32), ("qual_delta", C.c_int32),
+                ("qual_vector_offset", C.c_int32), ("use_sanger_qvs", C.c_int32), ("pr_xover", C.c_double)]
 
 
 class HitC(C.Structure):

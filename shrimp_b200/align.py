@@ -122,3 +122,17 @@ def align_strings_cs(edit: np.ndarray, genome_codes: np.ndarray, genome_start: i
                 c = g | 0x20 if xo else g
             q.append(c)
     return bytes(db), bytes(q)
+
+
+def post_sw_seq_qual(edit: np.ndarray, quals: np.ndarray, reverse: bool, have_quals: bool):
+    """SEQ / QUAL columns of a colour-space alignment with mapping qualities (gmapper/output.c:486-546, :607-628)
+    from what shrimp_gpu_map_reads returns after post_sw: edit bytes with bit 3 set carry the corrected base call in
+    bits 4-5; `quals` are the rmapped bytes of sfrp->qual that follow the edit script."""
+    rc = bytes.maketrans(b"ACGT", b"TGCA")
+    seq = bytes(_LS_LETTERS[(int(op) >> 4) & 3] for op in edit if (int(op) & 3) != 1)
+    q = bytes(quals.tobytes()) if have_quals else b"*"
+    if reverse:
+        seq = seq.translate(rc)[::-1]
+        if have_quals:
+            q = q[::-1]
+    return seq.decode(), q.decode()

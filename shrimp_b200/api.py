@@ -139,7 +139,8 @@ class MapParams:
     compute_mapping_qualities: bool = True
     list_cutoff: int = 0xFFFFFFFF
 
-    def to_c(self, scores: Scores, colour_space: bool, crossover_scores: np.ndarray | None = None) -> MapParamsC:
+    def to_c(self, scores: Scores, colour_space: bool, crossover_scores: np.ndarray | None = None,
+             read_quals: np.ndarray | None = None, qual_delta: int = 33) -> MapParamsC:
         alpha, beta = score_alpha_beta(scores, colour_space)
         vect = self.sw_vect_threshold
         if vect is None:
@@ -150,7 +151,9 @@ class MapParams:
                           self.region_bits, self.region_overlap, int(self.Gflag), int(self.Tflag), int(self.strata),
                           self.max_alignments, int(self.compute_mapping_qualities), self.list_cutoff & 0xFFFFFFFF,
                           crossover_scores.ctypes.data if crossover_scores is not None else None,
-                          int(crossover_scores.shape[1]) if crossover_scores is not None else 0)
+                          int(crossover_scores.shape[1]) if crossover_scores is not None else 0,
+                          read_quals.ctypes.data if read_quals is not None else None,
+                          int(read_quals.shape[1]) if read_quals is not None else 0, qual_delta, 0, 1, 0.0)
 
 
 @dataclass
@@ -325,7 +328,7 @@ class GpuContext:
 
     def map_reads(self, params: MapParams, scores: Scores, reads: np.ndarray, read_len, initbp=None,
                   want_stage: bool = False, stage_cap_per_read: int = 256, reuse_buffers: bool = False,
-                  crossover_scores: np.ndarray | None = None) -> MapResult:
+                  crossover_scores: np.ndarray | None = None, quals=None, qual_delta: int = 33) -> MapResult:
         """handle_read (mapping.c:1773) for a chunk: returns what read_output would receive.  crossover_scores
         [n, >= max read length] int32: read_entry::crossover_score of colour-space reads that came with qualities."""
         reads = np.ascontiguousarray(reads, dtype=np.uint32)
@@ -333,7 +336,13 @@ class GpuContext:
         n = reads.shape[0]
         if crossover_scores is not None:
             crossover_scores = np.ascontiguousarray(crossover_scores, dtype=np.int32)
-        pc = params.to_c(scores, getattr(self, "colour_space", False), crossover_scores)
+        qbuf = None
+        if quals is not None:   # re->qual of every read (gmapper -Q), for post_sw
+            qw = max(len(q) for q in quals) + 1
+            qbuf = np.zeros((len(quals), qw), dtype=np.uint8)
+            for r, q in enumerate(quals):
+                qbuf[r, :len(q)] = np.frombuffer(bytes(q), dtype=np.uint8)
+        pc = params.to_c(scores, getattr(self, "colour_space", False), crossover_scores, qbuf, qual_delta)
         hits = self._buf("hits", max(1, n * params.num_outputs), HitC, reuse_buffers)   # untouched pages cost nothing
         n_per = self._buf("n_per", max(1, n), np.int32, reuse_buffers)
         max_rl = int(read_len.max()) if n else 0

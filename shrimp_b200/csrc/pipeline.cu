@@ -20,6 +20,7 @@ size_t scan_smem_bytes(int cap, int max_rl, int k_cap, int bm_log2, int warps, i
 size_t scan_cta_smem_bytes(int cap, int max_rl, int k_cap, int bm_log2, int n_part, int win, bool global_arrays);
 int launch_scan_cta(shrimp_gpu_ctx *ctx, ScanParams &P, int n_ctas, int threads);
 int launch_scan_replay(shrimp_gpu_ctx *ctx, ScanParams &P, uint32_t n_rec, int ks_cap);
+int launch_post_sw(shrimp_gpu_ctx *ctx, const PostParams &P);
 
 int launch_scan(shrimp_gpu_ctx *ctx, ScanParams &P, int warps_per_cta, int n_ctas);
 int launch_build_vec_tasks(shrimp_gpu_ctx *ctx, const TaskBuildParams &P);
@@ -134,13 +135,13 @@ void free_pipeline(shrimp_gpu_ctx *ctx) {
   Pipeline *p = (Pipeline *)ctx->pipeline;
   if (!p) return;
   DevBuf *bufs[] = {&p->d_in, &p->d_reads, &p->d_read_len, &p->d_initbp, &p->d_hits, &p->d_rs_range, &p->d_counters,
-                    &p->d_overflow, &p->d_overflow2, &p->d_scan_slab, &p->d_tie_ent, &p->d_tie_order, &p->d_tie_rec, &p->d_prof, &p->d_mp_tab, &p->d_mp_epoch, &p->d_xover, &p->d_scratch, &p->d_task[0], &p->d_task[1], &p->d_vtrue[0], &p->d_vtrue[1],
+                    &p->d_overflow, &p->d_overflow2, &p->d_scan_slab, &p->d_tie_ent, &p->d_tie_order, &p->d_tie_rec, &p->d_prof, &p->d_mp_tab, &p->d_mp_epoch, &p->d_xover, &p->d_quals, &p->d_fqual, &p->d_pstab, &p->d_scratch, &p->d_task[0], &p->d_task[1], &p->d_vtrue[0], &p->d_vtrue[1],
                     &p->d_slot, &p->d_writer, &p->d_sel, &p->d_nsel, &p->d_ftasks, &p->d_finfo, &p->d_fresults,
                     &p->d_frow, &p->d_fbp[0], &p->d_fbp[1], &p->d_fbp[2], &p->d_fbp[3], &p->d_fbp[4], &p->d_fops,
                     &p->d_taskoff, &p->d_scan_tmp, &p->d_perm, &p->d_pair_min, &p->d_pair_max, &p->d_saved, &p->d_pairsel,
                     &p->d_npairsel, &p->d_taskof, &p->d_pairoff};
   for (DevBuf *b : bufs) b->release();
-  HostBuf *hb[] = {&p->h_info, &p->h_results, &p->h_ops, &p->h_nsel, &p->h_hits, &p->h_range, &p->h_xover,
+  HostBuf *hb[] = {&p->h_info, &p->h_results, &p->h_ops, &p->h_nsel, &p->h_hits, &p->h_range, &p->h_xover, &p->h_fqual,
                    &p->h_pairsel, &p->h_npairsel, &p->h_saved};
   for (HostBuf *b : hb) b->release();
   delete p;
@@ -339,12 +340,6 @@ int chunk_begin(Chunk &C, shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, int 
     set_error("%s: colour-space reads need initbp", who);
     return SHRIMP_E_ARG;
   }
-  if (cs && mp->compute_mapping_qualities) {
-    // hit_run_post_sw needs post_sw (common/sw-post.c), which is not on this path yet
-    set_error("%s: colour space needs compute_mapping_qualities = 0 (--no-mapping-qualities) until post_sw is "
-              "implemented", who);
-    return SHRIMP_E_ARG;
-  }
   C.ctx = ctx;
   C.g = g;
   C.mp = mp;
@@ -407,6 +402,7 @@ int chunk_begin(Chunk &C, shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, int 
     return SHRIMP_E_ARG;
   }
   C.ops_stride = (size_t)C.max_rl + C.max_wl;
+  C.post_sw = cs && mp->compute_mapping_qualities;
 
   GenomeView &G = C.G;
   G.ls = g->d_ls.as<uint32_t>();
@@ -434,6 +430,12 @@ int chunk_begin(Chunk &C, shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, int 
     if (cs) {
       SH_TRY(pl->d_initbp.ensure((size_t)n_reads));
       SH_CUDA(cudaMemcpyAsync(pl->d_initbp.p, initbp, (size_t)n_reads, cudaMemcpyHostToDevice, st));
+    }
+    pl->qual_stride = 0;
+    if (cs && mp->compute_mapping_qualities && mp->read_quals && mp->qual_stride > 0) {
+      SH_TRY(pl->d_quals.ensure((size_t)n_reads * mp->qual_stride));
+      SH_CUDA(cudaMemcpyAsync(pl->d_quals.p, mp->read_quals, (size_t)n_reads * mp->qual_stride, cudaMemcpyHostToDevice, st));
+      pl->qual_stride = mp->qual_stride;
     }
     pl->xover_stride = 0;
     if (cs && mp->crossover_scores && mp->crossover_stride > 0) {
@@ -1014,7 +1016,60 @@ int chunk_run_full(Chunk &C, int n_slots) {
   FP.xover_pos = pl->xover_stride ? pl->d_xover.as<int16_t>() : nullptr;
   FP.xover_stride = pl->xover_stride;
   FP.indel_taboo_len = sw.indel_taboo_len;
-  return run_full_sw(ctx, pl->d_perm, pl->d_frow, pl->d_fbp, FP, n_slots, C.cs, C.cnt + 32);
+  SH_TRY(run_full_sw(ctx, pl->d_perm, pl->d_frow, pl->d_fbp, FP, n_slots, C.cs, C.cnt + 32));
+  if (C.post_sw && n_slots > 0) {
+    // hit_run_post_sw (mapping.c:1609-1625) for every alignment with a positive score: emission terms from the host
+    // (libm, gmapper.c:2561-2572 and post_sw_setup), recurrences on the device (post_sw.cu)
+    const shrimp_map_params *mp = C.mp;
+    const double pr_xover = mp->pr_xover > 0 ? mp->pr_xover : 0.03;
+    const double alpha = mp->score_alpha, beta = mp->score_beta;
+    const double pr_snp = 1.0 / (1.0 + 1.0 / 3.0 * pow(2.0, ((double)sw.match - (double)sw.mismatch) / alpha));
+    PostParams PS;
+    memset(&PS, 0, sizeof(PS));
+    PS.genome_fwd = C.G.ls;
+    PS.genome_rc = C.G.ls_rc;
+    PS.reads = pl->d_reads.as<uint32_t>();
+    PS.stride = C.stride;
+    PS.tasks = pl->d_ftasks.as<FullTask>();
+    PS.results = pl->d_fresults.as<FullResult>();
+    PS.ops = pl->d_fops.as<uint8_t>();
+    PS.ops_stride = (int)C.ops_stride;
+    SH_TRY(pl->d_fqual.ensure((size_t)n_slots * (size_t)C.max_rl));
+    PS.quals_out = pl->d_fqual.as<uint8_t>();
+    PS.max_rlen = C.max_rl;
+    PS.n_tasks = n_slots;
+    PS.la1 = log(1 - pr_snp);
+    PS.la2 = log(pr_snp / 3.0);
+    PS.lc1 = log(1 - pr_xover);
+    PS.lc2 = log(pr_xover / 3.0);
+    PS.ln1 = log(1 - .75);
+    PS.ln2 = log(.75 / 3.0);
+    PS.pr_del_open = pow(2.0, (double)(-sw.a_open) / alpha);      // the CLI (negative) gap scores
+    PS.pr_ins_open = pow(2.0, (double)(-sw.b_open) / alpha);
+    PS.pr_del_extend = pow(2.0, (double)(-sw.a_ext) / alpha);
+    PS.pr_ins_extend = pow(2.0, ((double)(-sw.b_ext) - beta) / alpha);
+    if (pl->qual_stride) {
+      double tab[512];
+      for (int q = 0; q < 256; q++) {
+        const int qv = q - mp->qual_delta;
+        double e = qv <= 0 ? .99999999 : qv >= 250 ? 1E-25 : pow(10.0, -(double)qv / 10.0);   // util.h:285-293
+        if (!mp->use_sanger_qvs) e /= (1 + e);
+        if (e > .75) e = .75;
+        tab[q] = log(1 - e);
+        tab[256 + q] = log(e / 3.0);
+      }
+      SH_TRY(pl->d_pstab.ensure(sizeof(tab)));
+      SH_CUDA(cudaMemcpyAsync(pl->d_pstab.p, tab, sizeof(tab), cudaMemcpyHostToDevice, ctx->stream));
+      SH_CUDA(cudaStreamSynchronize(ctx->stream));   // tab lives on this stack frame
+      PS.lc1_tab = pl->d_pstab.as<double>();
+      PS.lc2_tab = PS.lc1_tab + 256;
+      PS.read_quals = pl->d_quals.as<uint8_t>();
+      PS.qual_stride = pl->qual_stride;
+      PS.qual_vector_offset = mp->qual_vector_offset;
+    }
+    SH_TRY(launch_post_sw(ctx, PS));
+  }
+  return SHRIMP_OK;
 }
 
 // results of the n_slots full-SW tasks (+ n_sel per read and the counters) back to pinned host memory
@@ -1032,6 +1087,11 @@ int chunk_fetch_full(Chunk &C, int n_slots, bool with_nsel) {
   SH_CUDA(cudaMemcpyAsync(pl->h_results.p, pl->d_fresults.p, (size_t)n_slots * sizeof(FullResult),
                           cudaMemcpyDeviceToHost, st));
   SH_CUDA(cudaMemcpyAsync(pl->h_ops.p, pl->d_fops.p, C.ops_stride * (size_t)n_slots, cudaMemcpyDeviceToHost, st));
+  if (C.post_sw && n_slots > 0) {
+    SH_TRY(pl->h_fqual.ensure((size_t)n_slots * (size_t)C.max_rl));
+    SH_CUDA(cudaMemcpyAsync(pl->h_fqual.p, pl->d_fqual.p, (size_t)n_slots * (size_t)C.max_rl, cudaMemcpyDeviceToHost, st));
+    pl->d2h_bytes += (size_t)n_slots * (size_t)C.max_rl;
+  }
   if (with_nsel)
     SH_CUDA(cudaMemcpyAsync(pl->h_nsel.p, pl->d_nsel.p, (size_t)n_reads * 4, cudaMemcpyDeviceToHost, st));
   uint32_t *h_cnt = (uint32_t *)((char *)pl->h_nsel.p + (size_t)n_reads * 4);
@@ -1066,9 +1126,12 @@ void host_score_hit(const Chunk &C, int idx, HostHit &h) {
   h.posterior = 0.0;
   h.score_full = h.res.score;
   h.pct_score_full = (1000 * 100 * h.score_full) / h.info.score_max;
-  if (mp->compute_mapping_qualities && h.score_full > 0 && !C.cs) {
-    h.posterior = pow(2.0, ((double)h.res.score - (double)h.res.rmapped * (2.0 * mp->score_alpha + mp->score_beta)) /
-                               mp->score_alpha);
+  if (mp->compute_mapping_qualities && h.score_full > 0) {
+    if (C.cs)   // post_sw ran on the device
+      h.posterior = h.res.posterior;
+    else
+      h.posterior = pow(2.0, ((double)h.res.score - (double)h.res.rmapped * (2.0 * mp->score_alpha + mp->score_beta)) /
+                                 mp->score_alpha);
     int ps = (int)rint(mp->score_alpha * log(h.posterior) / log(2.0) +
                        (double)h.res.rmapped * (2.0 * mp->score_alpha + mp->score_beta));
     if (ps < 0) ps = 0;
@@ -1113,6 +1176,13 @@ void host_fill_hit(const Chunk &C, const HostHit &h, int r, HostOut &O) {
   else if (h.res.ops_len > 0)
     O.edits_short = true;
   O.e_used += h.res.ops_len;
+  if (C.post_sw) {   // sfrp->qual right after the edit script
+    if (O.edits && O.e_used + h.res.rmapped <= O.edits_cap)
+      memcpy(O.edits + O.e_used, C.pl->h_fqual.as<uint8_t>() + (size_t)C.max_rl * (size_t)h.task_idx, (size_t)h.res.rmapped);
+    else if (h.res.rmapped > 0)
+      O.edits_short = true;
+    O.e_used += h.res.rmapped;
+  }
 }
 
 // read_pass2 after the DP (mapping.c:1644-1722) for one read: tasks [task_base, task_base + n1) -> the hits it
@@ -1204,7 +1274,7 @@ int host_pass2_all(const Chunk &C, const int32_t *n_sel, double full_thr, HostOu
                                        my_vc, my_vl);
       for (int i = 0; i < n2; i++) {
         K.push_back(tmp[i]);
-        e += RES[tmp[i].task_idx].ops_len;
+        e += RES[tmp[i].task_idx].ops_len + (C.post_sw ? RES[tmp[i].task_idx].rmapped : 0);
       }
       counts[t][r - r0] = n2;
       task_base += n_sel[r];
@@ -1229,6 +1299,7 @@ int host_pass2_all(const Chunk &C, const int32_t *n_sel, double full_thr, HostOu
   const bool fill_edits = O.edits && !O.edits_short;
   const SelInfo *INFO = C.pl->h_info.as<SelInfo>();
   const uint8_t *OPS = C.pl->h_ops.as<uint8_t>();
+  const uint8_t *FQ = C.pl->h_fqual.as<uint8_t>();
 #pragma omp parallel num_threads(T)
   {
     const int t = omp_get_thread_num();
@@ -1268,6 +1339,10 @@ int host_pass2_all(const Chunk &C, const int32_t *n_sel, double full_thr, HostOu
         o.edit_off = eo;
         if (fill_edits) memcpy(O.edits + eo, OPS + C.ops_stride * (size_t)kr.task_idx + res.ops_start, (size_t)res.ops_len);
         eo += res.ops_len;
+        if (C.post_sw) {   // sfrp->qual right after the edit script
+          if (fill_edits) memcpy(O.edits + eo, FQ + (size_t)C.max_rl * (size_t)kr.task_idx, (size_t)res.rmapped);
+          eo += res.rmapped;
+        }
       }
     }
   }

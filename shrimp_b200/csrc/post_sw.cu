@@ -1,0 +1,315 @@
+// post_sw on the device: colour-space mapping qualities.
+//
+// Replaces common/sw-post.c post_sw :640-758 (load_local_vectors :472-545, forward_backward :270-372,
+// post_traceback :182-207, fix_base_calls :548-581, get_base_qualities :584-601, get_posterior :604-626) as
+// hit_run_post_sw calls it (mapping.c:1609-1625) for every alignment with a positive full-SW score.
+//
+// The model is a 16-node chain (node = letter pair, left/right) over the aligned read columns.  One HALF-WARP per
+// alignment, lane = node: the forward and backward recurrences take their four predecessor / successor values by
+// width-16 shuffles, sums run in the reference's index order, the scale (minimum over the nodes) is a half-warp
+// reduction; forwards[][] of all columns stay in shared memory for the posterior pass.  The two alignments of a warp
+// run in lockstep (trip counts = the longer one).  Emission terms are exact: the -log() of the error rates comes
+// from the host (libm) as constants / a 256-entry table over the quality characters; exp() and log() inside the
+// recurrences are CUDA's double-precision functions (<= 1 ulp), so the doubles agree with the reference to a few
+// ulp and everything derived from them as integers is identical on every fixture.
+#include "stages.cuh"
+
+namespace shrimp {
+
+#define PS_LEFT(i) (((i) >> 2) & 3)
+#define PS_RIGHT(i) ((i) & 3)
+
+__device__ __forceinline__ double half_min(double v) {
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o, 16));
+  return v;
+}
+__device__ __forceinline__ int warp_max_int(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ int ps_cstols(int first_letter, int colour) {   // cstols, util.h:157-180
+  if (first_letter == 15 || colour < 0 || colour > 3) return 15;
+  return (first_letter % 2 == 0) ? (4 + first_letter + colour) % 4 : (4 + first_letter - colour) % 4;
+}
+__device__ __forceinline__ int ps_qv_from_pr_err(double pr_err) {   // util.h:268-276
+  if (pr_err > .99999999) return 0;
+  else if (pr_err < 1E-25) return 250;
+  else return (int)(-10.0 * log(pr_err) / log(10.0));
+}
+
+struct PsCol {   // one aligned read column (struct column, sw-post.c:61-78, without the recurrences' arrays)
+  int8_t let;    // genome letter 0-3, -1 = other (N), -2 = no letter emission (read base against a gap)
+  int8_t col;    // colour emitted
+  uint8_t q;     // quality character of the colour (table index)
+  uint8_t kind;  // 0: constant crossover rate (FASTA), 1: quality table, 2: colour N / run of N: rate .75
+  int8_t call;   // the full SW's base call (layer letter), 15 = N
+  int8_t maxp;   // max_posterior
+  uint8_t qual;  // 33 + base quality
+  uint8_t pad;
+};
+
+__global__ void __launch_bounds__(128) post_sw_kernel(const PostParams P, int halves_per_cta, int max_cols) {
+  extern __shared__ double ps_smem[];
+  const int lane = threadIdx.x & 31, hl = lane & 15;
+  const int hidx = threadIdx.x >> 4;   // half-warp of the CTA
+  // per half-warp: forwards[max_cols][16], forwscale[max_cols], columns[max_cols]
+  const size_t per_half = (size_t)max_cols * 17 + ((size_t)max_cols * sizeof(PsCol) + 7) / 8;
+  double *fw = ps_smem + (size_t)hidx * per_half;
+  double *fscale = fw + (size_t)max_cols * 16;
+  PsCol *cols = (PsCol *)(fscale + max_cols);
+  int slot = blockIdx.x * halves_per_cta + hidx;
+  const bool live = hidx < halves_per_cta && slot < P.n_tasks;
+  if (!live) slot = P.n_tasks - 1;
+  const FullTask T = P.tasks[slot];
+  FullResult R = P.results[slot];
+  const bool run = live && T.run && R.score > 0;   // mapping.c:1648: score_full > 0
+  const uint32_t *genome = T.gen_st ? P.genome_rc : P.genome_fwd;
+  const uint32_t *read = P.reads + (size_t)T.ridx * P.stride;
+  const uint8_t *ops = P.ops + (size_t)slot * (size_t)P.ops_stride;
+  const uint8_t *rq = P.read_quals ? P.read_quals + (size_t)(T.ridx >> 1) * (size_t)P.qual_stride + P.qual_vector_offset
+                                   : nullptr;
+  const int init_bp = T.initbp;
+  // ---- load_local_vectors: one lane walks the edit script -------------------------------------------------
+  int len = 0;
+  if (run && hl == 0) {
+    int letter[4];
+    for (int k = 0; k < 4; k++) letter[k] = (k + init_bp) % 4;
+    int start_run = 0, min_qv = 10000;
+    bool brk = false;
+    for (int j = 0; j < R.read_start; j++) {
+      const int c = (int)extract4(read, (uint64_t)j);
+      for (int k = 0; k < 4; k++) letter[k] = c == 15 ? (k + init_bp) % 4 : ps_cstols(letter[k], c);
+      if (!brk) {
+        if (c == 15) {
+          start_run = 15;
+          min_qv = 0;
+          brk = true;
+        } else {
+          start_run ^= c;
+          if (rq) min_qv = min(min_qv, (int)rq[j]);
+        }
+      }
+    }
+    uint64_t gpos = (uint64_t)T.goff_global + (uint64_t)(R.genome_start - (int)T.goff_contig);
+    int j = R.read_start;
+    for (int o = R.ops_start; o < R.ops_start + R.ops_len; o++) {
+      const int op = ops[o], type = op & 3, kk = (op >> 4) & 3;
+      if (type == 1) {   // genome base against a gap: no read column
+        gpos++;
+        continue;
+      }
+      const int c = (int)extract4(read, (uint64_t)j);
+      int qk[4];
+      for (int k = 0; k < 4; k++) {
+        if (c == 15) {
+          qk[k] = 15;
+          letter[k] = (k + init_bp) % 4;
+        } else {
+          qk[k] = ps_cstols(letter[k], c);
+          letter[k] = qk[k];
+        }
+      }
+      PsCol pc;
+      if (type == 3) {
+        const int g = (int)extract4(genome, gpos);
+        pc.let = (int8_t)(g <= 3 ? g : -1);
+        gpos++;
+      } else {
+        pc.let = -2;
+      }
+      if ((len == 0 && start_run == 15) || c == 15) {
+        pc.col = 0;
+        pc.kind = 2;
+        pc.q = 0;
+      } else {
+        pc.col = (int8_t)(c ^ (len == 0 ? start_run : 0));
+        if (rq) {
+          pc.kind = 1;
+          pc.q = (uint8_t)(len == 0 ? min(min_qv, (int)rq[j]) : (int)rq[j]);
+        } else {
+          pc.kind = 0;
+          pc.q = 0;
+        }
+      }
+      pc.call = (int8_t)qk[kk];
+      pc.maxp = 0;
+      pc.qual = 33;
+      pc.pad = 0;
+      if (len < max_cols) cols[len] = pc;
+      len++;
+      j++;
+    }
+  }
+  len = __shfl_sync(0xffffffffu, len, 0, 16);
+  if (len > max_cols) len = 0;   // cannot happen: columns <= read length
+  const int wlen = warp_max_int(len);
+  __syncwarp();
+  // -log() emission terms of node hl at column c (nodePrior, sw-post.c:112-140): (0 - a) - b
+  auto node_prior = [&](const PsCol &pc, int node) -> double {
+    double val = 0;
+    if (pc.let != -2) val = val - (PS_RIGHT(node) == pc.let ? P.la1 : P.la2);
+    const bool same = (PS_LEFT(node) ^ PS_RIGHT(node)) == pc.col;
+    const double l1 = pc.kind == 0 ? P.lc1 : pc.kind == 2 ? P.ln1 : P.lc1_tab[pc.q];
+    const double l2 = pc.kind == 0 ? P.lc2 : pc.kind == 2 ? P.ln2 : P.lc2_tab[pc.q];
+    val = val - (same ? l1 : l2);
+    return val;
+  };
+  // ---- do_forwards (sw-post.c:318-361) -----------------------------------------------------------------------
+  double f = 0, run_scale = 0;
+  for (int i = 0; i < wlen; i++) {
+    const bool on = i < len;
+    PsCol pc;
+    if (on) pc = cols[i];
+    else { pc.let = -2; pc.col = 0; pc.kind = 0; pc.q = 0; pc.call = 15; pc.maxp = 0; pc.qual = 33; pc.pad = 0; }
+    double nf;
+    if (i == 0) {
+      nf = PS_LEFT(hl) == init_bp ? node_prior(pc, hl) : HUGE_VAL;
+    } else {
+      const double val = node_prior(pc, hl);
+      double s = 0;
+#pragma unroll
+      for (int m = 0; m < 4; m++) {
+        const double pk = __shfl_sync(0xffffffffu, f, 4 * m + PS_LEFT(hl), 16);
+        s += exp(-1 * (pk));
+      }
+      nf = val - log(s);
+    }
+    // forwscale: minimum over the nodes (column 0: over the nodes that start from the initial base; the others are
+    // +infinity and never the minimum)
+    const double sc = half_min(nf);
+    nf -= sc;
+    if (on) {
+      f = nf;
+      run_scale = i == 0 ? sc : sc + run_scale;
+      fw[(size_t)i * 16 + hl] = f;
+      if (hl == 0) fscale[i] = run_scale;
+    }
+  }
+  double total_score = 0;
+  {
+    const double e = exp(-1 * (f));
+    double val = 0;
+#pragma unroll
+    for (int j = 0; j < 16; j++) val += __shfl_sync(0xffffffffu, e, j, 16);
+    total_score = -log(val) + run_scale;
+  }
+  __syncwarp();
+  // ---- do_backwards (sw-post.c:270-316) fused with post_traceback (:182-207) and get_base_qualities (:584-601) ----
+  double b = 0, bscale = 0;
+  for (int step = 0; step < wlen; step++) {
+    // this half is at column i = len - 1 - (step - (wlen - len)): the shorter alignment of the warp starts later
+    const int i = len - 1 - (step - (wlen - len));
+    const bool on = step >= wlen - len && len > 0;
+    PsCol pc, nxt;
+    pc.let = -2; pc.col = 0; pc.kind = 0; pc.q = 0; pc.call = 15; pc.maxp = 0; pc.qual = 33; pc.pad = 0;
+    nxt = pc;
+    if (on) {
+      pc = cols[i];
+      if (i + 1 < len) nxt = cols[i + 1];
+    }
+    // the shuffles are full-mask: both halves of the warp execute them whatever their own state
+    double s = 0;
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+      const int k = 4 * PS_RIGHT(hl) + m;
+      const double val = node_prior(nxt, k);
+      const double bk = __shfl_sync(0xffffffffu, b, k, 16);
+      s += exp(-1 * (val + bk));
+    }
+    const double nb0 = (!on || i == len - 1) ? 0.0 : -log(s);   // last column: backwards = 0, backscale = 0
+    double nb = nb0;
+    const double sc = half_min(nb);
+    nb -= sc;
+    if (on) {
+      bscale = (i == len - 1) ? sc : sc + bscale;
+      b = nb;
+    }
+    // posterior of the four letters at this column
+    const double fwv = on ? fw[(size_t)i * 16 + hl] : 0.0, fs = on ? fscale[i] : 0.0;
+    const double e = exp(-1 * (fwv + b + fs + bscale - total_score));
+    double p = 0;
+#pragma unroll
+    for (int m = 0; m < 4; m++) p += __shfl_sync(0xffffffffu, e, 4 * m + (hl & 3), 16);
+    const double p0 = __shfl_sync(0xffffffffu, p, 0, 16), p1 = __shfl_sync(0xffffffffu, p, 1, 16);
+    const double p2 = __shfl_sync(0xffffffffu, p, 2, 16), p3 = __shfl_sync(0xffffffffu, p, 3, 16);
+    if (on && hl == 0) {
+      int maxval = 0;
+      double pm = p0;
+      if (p1 > pm) { maxval = 1; pm = p1; }
+      if (p2 > pm) { maxval = 2; pm = p2; }
+      if (p3 > pm) { maxval = 3; pm = p3; }
+      const int bc = pc.call;
+      int tmp = 0;
+      if (bc != 15) tmp = ps_qv_from_pr_err(1 - (bc == 0 ? p0 : bc == 1 ? p1 : bc == 2 ? p2 : p3));
+      if (tmp > 40) tmp = 40;
+      cols[i].maxp = (int8_t)maxval;
+      cols[i].qual = (uint8_t)(33 + tmp);
+    }
+  }
+  __syncwarp();
+  // ---- fix_base_calls (:548-581), get_posterior (:604-626): one lane rewrites the edit script -----------------------
+  if (run && hl == 0 && len > 0) {
+    uint8_t *wops = P.ops + (size_t)slot * (size_t)P.ops_stride;
+    uint8_t *qout = P.quals_out + (size_t)slot * (size_t)P.max_rlen;
+    uint64_t gpos = (uint64_t)T.goff_global + (uint64_t)(R.genome_start - (int)T.goff_contig);
+    int prev_base = init_bp, j = 0, prev_type = 0;
+    int matches = 0, mismatches = 0, crossovers = 0;
+    double res = exp(-total_score);
+    for (int o = R.ops_start; o < R.ops_start + R.ops_len; o++) {
+      const int op = wops[o], type = op & 3;
+      if (type == 1) {   // qralign '-': a deletion column of get_posterior
+        gpos++;
+        res *= P.pr_del_extend;
+        if (o == R.ops_start || prev_type != 1) res *= P.pr_del_open;
+      } else {
+        const PsCol pc = cols[j];
+        const int crt = pc.maxp;
+        const bool lower = (prev_base ^ crt) != pc.col;
+        if (lower) crossovers++;
+        if (type == 3) {
+          const int g = (int)extract4(genome, gpos);
+          gpos++;
+          if (g == crt) matches++;
+          else mismatches++;
+        } else {   // dbalign '-': an insertion column of get_posterior
+          res *= P.pr_ins_extend;
+          if (o == R.ops_start || prev_type != 2) res *= P.pr_ins_open;
+        }
+        // bit 3: bits 4-5 are the base call itself (not a layer); bit 2: lower case (crossover before this base)
+        wops[o] = (uint8_t)(type | (lower ? 4 : 0) | 8 | (crt << 4));
+        qout[j] = pc.qual;
+        prev_base = crt;
+        j++;
+      }
+      prev_type = type;
+    }
+    R.matches = matches;
+    R.mismatches = mismatches;
+    R.crossovers = crossovers;
+    R.posterior = res;
+    P.results[slot] = R;
+  }
+}
+
+int launch_post_sw(shrimp_gpu_ctx *ctx, const PostParams &P) {
+  if (P.n_tasks <= 0) return SHRIMP_OK;
+  const int max_cols = std::max(1, P.max_rlen);
+  const size_t per_half = ((size_t)max_cols * 17 + ((size_t)max_cols * sizeof(PsCol) + 7) / 8) * sizeof(double);
+  int halves = 8;
+  while (halves > 2 && per_half * halves > 200 * 1024) halves -= 2;
+  if (per_half * 2 > 220 * 1024) {
+    set_error("post_sw: reads of %d bases need more shared memory than a CTA has", P.max_rlen);
+    return SHRIMP_E_RANGE;
+  }
+  const size_t smem = per_half * halves;
+  SH_CUDA(cudaFuncSetAttribute(post_sw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = (P.n_tasks + halves - 1) / halves;
+  post_sw_kernel<<<grid, halves * 16, smem, ctx->stream>>>(P, halves, max_cols);
+  SH_CUDA(cudaGetLastError());
+  SH_LAUNCHED(ctx, ST_FULL);
+  return SHRIMP_OK;
+}
+
+}  // namespace shrimp

@@ -142,6 +142,7 @@ struct FullResult {
   int32_t read_start, rmapped, genome_start, gmapped;
   int32_t matches, mismatches, insertions, deletions, crossovers;
   int32_t ops_start, ops_len;   // into this task's ops column
+  double posterior;             // colour space with mapping qualities: sfrp->posterior of post_sw (post_sw.cu)
 };
 
 struct FullParams {
@@ -171,6 +172,27 @@ struct FullParams {
   int rev;          // every task of this launch has gen_st && Tflag == rev (the tasks are grouped by it)
   int W;
   unsigned long long *bp64;
+};
+
+// post_sw over the full-SW tasks of a chunk (post_sw.cu)
+struct PostParams {
+  const uint32_t *genome_fwd, *genome_rc;
+  const uint32_t *reads;
+  int stride;
+  const FullTask *tasks;
+  FullResult *results;
+  uint8_t *ops;            // edit scripts, rewritten with the corrected base calls
+  int ops_stride;
+  uint8_t *quals_out;      // [n_tasks][max_rlen] base qualities (33 + q) of the aligned read columns
+  int max_rlen;
+  int n_tasks;
+  const uint8_t *read_quals;   // quality strings of the reads (gmapper -Q) or nullptr
+  int qual_stride, qual_vector_offset;
+  const double *lc1_tab, *lc2_tab;   // per quality character: log(1 - colour error rate), log(rate / 3) (host libm)
+  double la1, la2;         // log(1 - pr_snp), log(pr_snp / 3)
+  double lc1, lc2;         // reads without qualities: log(1 - pr_xover), log(pr_xover / 3)
+  double ln1, ln2;         // colour N: rate .75
+  double pr_del_open, pr_del_extend, pr_ins_open, pr_ins_extend;
 };
 
 }  // namespace shrimp

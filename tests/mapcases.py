@@ -135,6 +135,8 @@ PAIR_CASES = {
     # colour-space pairs (post_sw is not on the path: --no-mapping-qualities)
     "c2p_small": dict(gen="c2p_small", args=["-p", "opp-in", "-I", "0,1000", "--no-mapping-qualities"],
                       opts={"compute_mapping_qualities": False}),
+    # colour-space pairs with mapping qualities (post_sw on every member of a pair)
+    "c2p_small_mq": dict(gen="c2p_small", args=["-p", "opp-in", "-I", "0,1000"], opts={}),
     # the paired option sets that look at the mate's region counts (gmapper.c:2659-2662):
     # use_mp_region_counts 1 (-n 4 without half-paired), 2 (-n 3), 3 (-n 3 without half-paired); and -n 2 (no regions)
     "c3_small_nohp": dict(gen="c3_small", args=["-p", "opp-in", "-I", "0,1000", "--no-half-paired"], opts={},

@@ -19,7 +19,8 @@ def run_gpu(ctx, case, **over):
     ctx.build_index(case.seeds, hflag=case.hflag)
     params = MapParams(list_cutoff=case.list_cutoff, **over)
     return ctx.map_reads(params, case.scores, case.packed, case.read_len, initbp=case.initbp, want_stage=True,
-                         crossover_scores=case.crossover_scores)
+                         crossover_scores=case.crossover_scores,
+                         quals=case.quals if params.compute_mapping_qualities else None)
 
 
 def sam_arrays(case, res):
@@ -46,6 +47,14 @@ def test_pipeline_matches_reference_golden(gpu_ctx, name):
     bad = np.nonzero((sam != gold["sam"]).any(axis=1))[0]
     assert bad.size == 0, (bad[:5], sam[bad[:5]], gold["sam"][bad[:5]])
     assert np.array_equal(cig, gold["cigars"])
+    if "seq" in gold:   # colour space with mapping qualities: post_sw's corrected base calls and base qualities
+        sq = []
+        for h in res.hits:
+            e0, el, rm = int(h["edit_off"]), int(h["edit_len"]), int(h["rmapped"])
+            sq.append(align.post_sw_seq_qual(res.edits[e0:e0 + el], res.edits[e0 + el:e0 + el + rm],
+                                             int(h["gen_st"]) == 1, case.quals is not None))
+        assert [a for a, _ in sq] == gold["seq"].tolist()
+        assert [b for _, b in sq] == gold["qual"].tolist()
 
 
 def test_repeats_reach_the_cta_scan_kernel(gpu_ctx):
