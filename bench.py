@@ -151,12 +151,17 @@ class Workload:
 
 
 WORKLOADS = {
-    # BASELINE.json configs[1]: the configuration the metric is quoted on that fits one GPU.  post_sw (colour-space
-    # mapping qualities) is not on the path yet, so both arms run with --no-mapping-qualities.
+    # BASELINE.json configs[1]: the configuration the metric is quoted on that fits one GPU, with gmapper-cs's default
+    # options (mapping qualities on: post_sw rescoring of every alignment); c2nomq = the same with
+    # --no-mapping-qualities
     "c2": Workload("c2", "C2 colour-space: 36-colour SOLiD reads (SNP in 30%, 3% colour errors) vs iid 100 Mb genome "
-                   "in 10 contigs, 3 default seeds w12, sw_full_cs crossovers, --no-mapping-qualities; one step = "
-                   "one batch of the 10 M-read job", True, 36, 10_000_000, 10, 3, 1_000_000, "gmapper-cs",
-                   ["--no-mapping-qualities"]),
+                   "in 10 contigs, 3 default seeds w12, sw_full_cs crossovers, mapping qualities (post_sw) on as by "
+                   "default; one step = one batch of the 10 M-read job", True, 36, 10_000_000, 10, 3, 1_000_000,
+                   "gmapper-cs", []),
+    "c2nomq": Workload("c2nomq", "C2 colour-space without mapping qualities: 36-colour SOLiD reads (SNP in 30%, 3% "
+                       "colour errors) vs iid 100 Mb genome in 10 contigs, 3 default seeds w12, sw_full_cs crossovers, "
+                       "--no-mapping-qualities; one step = one batch of the 10 M-read job", True, 36, 10_000_000, 10, 3,
+                       1_000_000, "gmapper-cs", ["--no-mapping-qualities"]),
     # BASELINE.json configs[2]: paired-end letter space; the genome is scaled by --genome-mb (default 300 Mb; 3000 =
     # the hg18-sized configuration, every read strand then goes through the CTA-per-strand scan kernel)
     "c3": Workload("c3", "C3 paired-end letter-space: 2x100bp opp-in pairs (insert N(300,30), 2% subs) vs iid genome "
@@ -372,7 +377,7 @@ def main():
     # torchrun exports OMP_NUM_THREADS=1: give every rank its share of the host cores for the host stages
     from shrimp_b200.api import set_host_threads
     set_host_threads(max(1, ncores // max(1, world)))
-    params = MapParams(list_cutoff=auto_list_cutoff(w.genome_len, 12), compute_mapping_qualities=not w.colour,
+    params = MapParams(list_cutoff=auto_list_cutoff(w.genome_len, 12), compute_mapping_qualities="--no-mapping-qualities" not in w.args,
                        match_mode=4 if w.paired else 2)
 
     def map_host():

@@ -312,6 +312,10 @@ int shrimp_gpu_dpx_peak(shrimp_gpu_ctx *ctx, double *ginstr_per_s);
  * the -N threads of gmapper.c:2907): n > 0 fixes the count, 0 = the OpenMP default. Process-wide. */
 int shrimp_gpu_set_host_threads(int n);
 
+/* Diagnostic: exp() and log() of n doubles as post_sw's kernel computes them (a transcription of the libm the
+ * reference runs on), so that a test can compare them bit for bit with the host's libm. */
+int shrimp_gpu_glibc_explog(shrimp_gpu_ctx *ctx, const double *x, int n, double *exp_out, double *log_out);
+
 #ifdef __cplusplus
 }
 #endif

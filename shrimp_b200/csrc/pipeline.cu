@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <omp.h>
 #include <atomic>
+#include "glibc_tables.inc"
 #include <cub/cub.cuh>
 #include "chunk.cuh"
 
@@ -135,7 +136,7 @@ void free_pipeline(shrimp_gpu_ctx *ctx) {
   Pipeline *p = (Pipeline *)ctx->pipeline;
   if (!p) return;
   DevBuf *bufs[] = {&p->d_in, &p->d_reads, &p->d_read_len, &p->d_initbp, &p->d_hits, &p->d_rs_range, &p->d_counters,
-                    &p->d_overflow, &p->d_overflow2, &p->d_scan_slab, &p->d_tie_ent, &p->d_tie_order, &p->d_tie_rec, &p->d_prof, &p->d_mp_tab, &p->d_mp_epoch, &p->d_xover, &p->d_quals, &p->d_fqual, &p->d_pstab, &p->d_scratch, &p->d_task[0], &p->d_task[1], &p->d_vtrue[0], &p->d_vtrue[1],
+                    &p->d_overflow, &p->d_overflow2, &p->d_scan_slab, &p->d_tie_ent, &p->d_tie_order, &p->d_tie_rec, &p->d_prof, &p->d_mp_tab, &p->d_mp_epoch, &p->d_xover, &p->d_quals, &p->d_fqual, &p->d_pstab, &p->d_gmtab, &p->d_scratch, &p->d_task[0], &p->d_task[1], &p->d_vtrue[0], &p->d_vtrue[1],
                     &p->d_slot, &p->d_writer, &p->d_sel, &p->d_nsel, &p->d_ftasks, &p->d_finfo, &p->d_fresults,
                     &p->d_frow, &p->d_fbp[0], &p->d_fbp[1], &p->d_fbp[2], &p->d_fbp[3], &p->d_fbp[4], &p->d_fops,
                     &p->d_taskoff, &p->d_scan_tmp, &p->d_perm, &p->d_pair_min, &p->d_pair_max, &p->d_saved, &p->d_pairsel,
@@ -1048,6 +1049,19 @@ int chunk_run_full(Chunk &C, int n_slots) {
     PS.pr_ins_open = pow(2.0, (double)(-sw.b_open) / alpha);
     PS.pr_del_extend = pow(2.0, (double)(-sw.a_ext) / alpha);
     PS.pr_ins_extend = pow(2.0, ((double)(-sw.b_ext) - beta) / alpha);
+    {   // tables of the libm transcription, once per context
+      if (!pl->gm_tab_ready) {
+        std::vector<unsigned long long> gm(8 + 256 + 18 + 256);
+        memcpy(gm.data(), GLIBC_EXP_CONST, 8 * 8);
+        memcpy(gm.data() + 8, GLIBC_EXP_TAB, 256 * 8);
+        memcpy(gm.data() + 8 + 256, GLIBC_LOG_CONST, 18 * 8);
+        memcpy(gm.data() + 8 + 256 + 18, GLIBC_LOG_TAB, 256 * 8);
+        SH_TRY(pl->d_gmtab.ensure(gm.size() * 8));
+        SH_CUDA(cudaMemcpy(pl->d_gmtab.p, gm.data(), gm.size() * 8, cudaMemcpyHostToDevice));
+        pl->gm_tab_ready = true;
+      }
+      PS.gm_tab = pl->d_gmtab.as<unsigned long long>();
+    }
     if (pl->qual_stride) {
       double tab[512];
       for (int q = 0; q < 256; q++) {

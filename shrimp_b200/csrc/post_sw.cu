@@ -8,11 +8,14 @@
 // alignment, lane = node: the forward and backward recurrences take their four predecessor / successor values by
 // width-16 shuffles, sums run in the reference's index order, the scale (minimum over the nodes) is a half-warp
 // reduction; forwards[][] of all columns stay in shared memory for the posterior pass.  The two alignments of a warp
-// run in lockstep (trip counts = the longer one).  Emission terms are exact: the -log() of the error rates comes
-// from the host (libm) as constants / a 256-entry table over the quality characters; exp() and log() inside the
-// recurrences are CUDA's double-precision functions (<= 1 ulp), so the doubles agree with the reference to a few
-// ulp and everything derived from them as integers is identical on every fixture.
+// run in lockstep (trip counts = the longer one).  Every double is the reference's, bit for bit: the -log() emission
+// terms come from the host (libm) as constants / a 256-entry table over the quality characters, and exp() / log()
+// inside the recurrences are glibc_math.cuh -- the libm algorithms operation by operation -- because equally likely
+// alternatives (two colour errors of the same quality) tie exactly and the last bit of a sum decides the base call.
+// Compiled with -fmad=false: only the fused multiply-adds the transcription names are fused.
 #include "stages.cuh"
+#include "glibc_math.cuh"
+#include <vector>
 
 namespace shrimp {
 
@@ -33,10 +36,10 @@ __device__ __forceinline__ int ps_cstols(int first_letter, int colour) {   // cs
   if (first_letter == 15 || colour < 0 || colour > 3) return 15;
   return (first_letter % 2 == 0) ? (4 + first_letter + colour) % 4 : (4 + first_letter - colour) % 4;
 }
-__device__ __forceinline__ int ps_qv_from_pr_err(double pr_err) {   // util.h:268-276
+__device__ __forceinline__ int ps_qv_from_pr_err(double pr_err, const glibc_math::Tables &GT) {   // util.h:268-276
   if (pr_err > .99999999) return 0;
   else if (pr_err < 1E-25) return 250;
-  else return (int)(-10.0 * log(pr_err) / log(10.0));
+  else return (int)(-10.0 * glibc_math::log_glibc(pr_err, GT) / glibc_math::log_glibc(10.0, GT));
 }
 
 struct PsCol {   // one aligned read column (struct column, sw-post.c:61-78, without the recurrences' arrays)
@@ -71,6 +74,9 @@ __global__ void __launch_bounds__(128) post_sw_kernel(const PostParams P, int ha
   const uint8_t *rq = P.read_quals ? P.read_quals + (size_t)(T.ridx >> 1) * (size_t)P.qual_stride + P.qual_vector_offset
                                    : nullptr;
   const int init_bp = T.initbp;
+  const glibc_math::Tables GT = {P.gm_tab, P.gm_tab + 8, P.gm_tab + 8 + 256, P.gm_tab + 8 + 256 + 18};
+#define PS_EXP(x) glibc_math::exp_glibc((x), GT)
+#define PS_LOG(x) glibc_math::log_glibc((x), GT)
   // ---- load_local_vectors: one lane walks the edit script -------------------------------------------------
   int len = 0;
   if (run && hl == 0) {
@@ -172,9 +178,9 @@ __global__ void __launch_bounds__(128) post_sw_kernel(const PostParams P, int ha
 #pragma unroll
       for (int m = 0; m < 4; m++) {
         const double pk = __shfl_sync(0xffffffffu, f, 4 * m + PS_LEFT(hl), 16);
-        s += exp(-1 * (pk));
+        s += PS_EXP(-1 * (pk));
       }
-      nf = val - log(s);
+      nf = val - PS_LOG(s);
     }
     // forwscale: minimum over the nodes (column 0: over the nodes that start from the initial base; the others are
     // +infinity and never the minimum)
@@ -189,11 +195,11 @@ __global__ void __launch_bounds__(128) post_sw_kernel(const PostParams P, int ha
   }
   double total_score = 0;
   {
-    const double e = exp(-1 * (f));
+    const double e = PS_EXP(-1 * (f));
     double val = 0;
 #pragma unroll
     for (int j = 0; j < 16; j++) val += __shfl_sync(0xffffffffu, e, j, 16);
-    total_score = -log(val) + run_scale;
+    total_score = -PS_LOG(val) + run_scale;
   }
   __syncwarp();
   // ---- do_backwards (sw-post.c:270-316) fused with post_traceback (:182-207) and get_base_qualities (:584-601) ----
@@ -216,9 +222,9 @@ __global__ void __launch_bounds__(128) post_sw_kernel(const PostParams P, int ha
       const int k = 4 * PS_RIGHT(hl) + m;
       const double val = node_prior(nxt, k);
       const double bk = __shfl_sync(0xffffffffu, b, k, 16);
-      s += exp(-1 * (val + bk));
+      s += PS_EXP(-1 * (val + bk));
     }
-    const double nb0 = (!on || i == len - 1) ? 0.0 : -log(s);   // last column: backwards = 0, backscale = 0
+    const double nb0 = (!on || i == len - 1) ? 0.0 : -PS_LOG(s);   // last column: backwards = 0, backscale = 0
     double nb = nb0;
     const double sc = half_min(nb);
     nb -= sc;
@@ -228,7 +234,7 @@ __global__ void __launch_bounds__(128) post_sw_kernel(const PostParams P, int ha
     }
     // posterior of the four letters at this column
     const double fwv = on ? fw[(size_t)i * 16 + hl] : 0.0, fs = on ? fscale[i] : 0.0;
-    const double e = exp(-1 * (fwv + b + fs + bscale - total_score));
+    const double e = PS_EXP(-1 * (fwv + b + fs + bscale - total_score));
     double p = 0;
 #pragma unroll
     for (int m = 0; m < 4; m++) p += __shfl_sync(0xffffffffu, e, 4 * m + (hl & 3), 16);
@@ -242,7 +248,7 @@ __global__ void __launch_bounds__(128) post_sw_kernel(const PostParams P, int ha
       if (p3 > pm) { maxval = 3; pm = p3; }
       const int bc = pc.call;
       int tmp = 0;
-      if (bc != 15) tmp = ps_qv_from_pr_err(1 - (bc == 0 ? p0 : bc == 1 ? p1 : bc == 2 ? p2 : p3));
+      if (bc != 15) tmp = ps_qv_from_pr_err(1 - (bc == 0 ? p0 : bc == 1 ? p1 : bc == 2 ? p2 : p3), GT);
       if (tmp > 40) tmp = 40;
       cols[i].maxp = (int8_t)maxval;
       cols[i].qual = (uint8_t)(33 + tmp);
@@ -256,7 +262,7 @@ __global__ void __launch_bounds__(128) post_sw_kernel(const PostParams P, int ha
     uint64_t gpos = (uint64_t)T.goff_global + (uint64_t)(R.genome_start - (int)T.goff_contig);
     int prev_base = init_bp, j = 0, prev_type = 0;
     int matches = 0, mismatches = 0, crossovers = 0;
-    double res = exp(-total_score);
+    double res = PS_EXP(-total_score);
     for (int o = R.ops_start; o < R.ops_start + R.ops_len; o++) {
       const int op = wops[o], type = op & 3;
       if (type == 1) {   // qralign '-': a deletion column of get_posterior
@@ -312,4 +318,47 @@ int launch_post_sw(shrimp_gpu_ctx *ctx, const PostParams &P) {
   return SHRIMP_OK;
 }
 
+__global__ void glibc_explog_kernel(const double *x, int n, const unsigned long long *gm_tab, double *e, double *l) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const glibc_math::Tables GT = {gm_tab, gm_tab + 8, gm_tab + 8 + 256, gm_tab + 8 + 256 + 18};
+  e[i] = glibc_math::exp_glibc(x[i], GT);
+  l[i] = glibc_math::log_glibc(x[i], GT);
+}
+
 }  // namespace shrimp
+
+// Diagnostic entry: exp() and log() of n doubles as the device computes them in post_sw (glibc_math.cuh), for the
+// test that compares them bit for bit with the host's libm.
+extern "C" int shrimp_gpu_glibc_explog(shrimp_gpu_ctx *ctx, const double *x, int n, double *exp_out, double *log_out) {
+  using namespace shrimp;
+  if (!ctx || !x || !exp_out || !log_out || n < 0) {
+    set_error("shrimp_gpu_glibc_explog: invalid argument");
+    return SHRIMP_E_ARG;
+  }
+  if (n == 0) return SHRIMP_OK;
+  std::vector<unsigned long long> gm(8 + 256 + 18 + 256);
+  memcpy(gm.data(), GLIBC_EXP_CONST, 8 * 8);
+  memcpy(gm.data() + 8, GLIBC_EXP_TAB, 256 * 8);
+  memcpy(gm.data() + 8 + 256, GLIBC_LOG_CONST, 18 * 8);
+  memcpy(gm.data() + 8 + 256 + 18, GLIBC_LOG_TAB, 256 * 8);
+  DevBuf dt, dx, de, dl;
+  int rc = SHRIMP_OK;
+  if ((rc = dt.ensure(gm.size() * 8)) == SHRIMP_OK && (rc = dx.ensure((size_t)n * 8)) == SHRIMP_OK &&
+      (rc = de.ensure((size_t)n * 8)) == SHRIMP_OK && (rc = dl.ensure((size_t)n * 8)) == SHRIMP_OK) {
+    cudaMemcpyAsync(dt.p, gm.data(), gm.size() * 8, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(dx.p, x, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream);
+    glibc_explog_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(dx.as<double>(), n, dt.as<unsigned long long>(),
+                                                                   de.as<double>(), dl.as<double>());
+    ctx->launches++;
+    cudaMemcpyAsync(exp_out, de.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaMemcpyAsync(log_out, dl.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    const cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+      set_error("shrimp_gpu_glibc_explog: %s", cudaGetErrorString(e));
+      rc = SHRIMP_E_CUDA;
+    }
+  }
+  dt.release(); dx.release(); de.release(); dl.release();
+  return rc;
+}

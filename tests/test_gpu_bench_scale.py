@@ -34,7 +34,7 @@ def _reference_sam(bench, w, d, codes, ctx):
 
 def test_c2_sample_matches_reference_binary(tmp_path):
     import bench
-    w = bench.WORKLOADS["c2"]
+    w = bench.WORKLOADS["c2nomq"]
     n = 60_000
     codes, initbp = w.reads(n, 77)
     ctx, scores, seeds, _ = bench.build_context(w, 0)
@@ -55,6 +55,38 @@ def test_c2_sample_matches_reference_binary(tmp_path):
             bad += 1
             if bad < 5:
                 print("DIFF", mine, rrec)
+    assert bad == 0
+
+
+def test_c2_mapping_qualities_sample_matches_reference_binary(tmp_path):
+    """gmapper-cs with its default options: post_sw (device) rescoring -- AS, NM, position, CIGAR and the corrected
+    base calls (SEQ) of every record equal the reference's"""
+    import bench
+    w = bench.WORKLOADS["c2"]
+    n = 40_000
+    codes, initbp = w.reads(n, 79)
+    ctx, scores, seeds, _ = bench.build_context(w, 0)
+    try:
+        sam_path = _reference_sam(bench, w, str(tmp_path), codes, ctx)
+        ref = op.parse_sam(sam_path)
+        ref_sq = op.parse_sam_seq_qual(sam_path)
+        params = MapParams(list_cutoff=auto_list_cutoff(w.genome_len, 12), compute_mapping_qualities=True)
+        res = ctx.map_reads(params, scores, bench.pack_rows(codes), np.full(n, w.read_len, np.int32), initbp=initbp)
+    finally:
+        ctx.close()
+    names = w.contig_names()
+    assert len(res.hits) == len(ref) and len(ref) > n // 2
+    bad = 0
+    for h, rrec, (rseq, rqual) in zip(res.hits, ref, ref_sq):
+        e0, el, rm = int(h["edit_off"]), int(h["edit_len"]), int(h["rmapped"])
+        e = res.edits[e0:e0 + el]
+        f = align.sam_fields(h, e, w.read_len, w.contig_len, True)
+        seq, _ = align.post_sw_seq_qual(e, res.edits[e0 + el:e0 + el + rm], int(h["gen_st"]) == 1, False)
+        mine = (f"r{int(h['read_idx'])}", f[0], names[f[1]], f[2], f[3], f[4], f[5])
+        if mine != rrec or seq != rseq or rqual != "*":
+            bad += 1
+            if bad < 5:
+                print("DIFF", mine, rrec, seq, rseq)
     assert bad == 0
 
 

@@ -15,7 +15,7 @@ packed = torch.from_numpy(bench.pack_rows(codes)).pin_memory().numpy()
 read_len = torch.full((n,), w.read_len, dtype=torch.int32).pin_memory().numpy()
 initbp = torch.from_numpy(initbp_np).pin_memory().numpy() if initbp_np is not None else None
 ctx, scores, seeds, _ = bench.build_context(w, 0)
-params = MapParams(list_cutoff=auto_list_cutoff(w.genome_len, 12), compute_mapping_qualities=not w.colour,
+params = MapParams(list_cutoff=auto_list_cutoff(w.genome_len, 12), compute_mapping_qualities="--no-mapping-qualities" not in w.args,
                    match_mode=4 if w.paired else 2)
 f = (lambda: ctx.map_pairs(params, scores, packed, read_len, reuse_buffers=True)) if w.paired else \
     (lambda: ctx.map_reads(params, scores, packed, read_len, initbp=initbp, reuse_buffers=True))

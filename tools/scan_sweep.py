@@ -35,7 +35,7 @@ def main():
     initbp = torch.from_numpy(initbp_np).pin_memory().numpy() if initbp_np is not None else None
     ctx, scores, seeds, index_s = bench.build_context(w, 0)
     print("index built in %.1f s" % index_s, flush=True)
-    params = MapParams(list_cutoff=auto_list_cutoff(w.genome_len, 12), compute_mapping_qualities=not w.colour,
+    params = MapParams(list_cutoff=auto_list_cutoff(w.genome_len, 12), compute_mapping_qualities="--no-mapping-qualities" not in w.args,
                        match_mode=4 if w.paired else 2)
     if w.paired:
         ctx.map_pairs(params, scores, packed, read_len, reuse_buffers=True)
