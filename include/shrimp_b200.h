@@ -237,6 +237,7 @@ typedef struct shrimp_map_stats {
   uint64_t device_vector_cells; /* sum glen*rlen over the windows the device scored */
   uint64_t scan_big_strands;    /* read strands served by the CTA-per-strand scan kernel (long index lists) */
   uint64_t scan_global_strands; /* ... of which needed candidate arrays in global memory (more than a shared-memory slab) */
+  uint64_t post_sw_columns;     /* aligned read columns post_sw ran its 16-node forward-backward over */
 } shrimp_map_stats;
 
 /* initbp: per-read initial base (colour space) or NULL.  hits_cap >= n_reads*num_outputs always

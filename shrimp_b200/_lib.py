@@ -78,7 +78,7 @@ class MapStatsC(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("list_entries", "surviving_entries", "anchors", "hits", "heap_replays",
                                           "vector_tasks", "vector_calls", "vector_cells", "vector_bypassed",
                                           "full_calls", "full_cells", "device_vector_cells", "scan_big_strands",
-                                          "scan_global_strands")]
+                                          "scan_global_strands", "post_sw_columns")]
 
 
 def lib() -> C.CDLL:

@@ -87,6 +87,7 @@ enum Stage {
   ST_VECTOR,
   ST_PASS1,
   ST_FULL,
+  ST_POST,
   ST_OTHER,
   ST_COUNT
 };

@@ -92,7 +92,7 @@ extern "C" void shrimp_gpu_destroy(shrimp_gpu_ctx *c) {
 
 extern "C" uint64_t shrimp_gpu_launch_count(const shrimp_gpu_ctx *c) { return c ? c->launches : 0; }
 
-static const char *k_stage_names[ST_COUNT] = {"index_build", "seed_scan", "sw_vector", "pass1_select", "sw_full", "other"};
+static const char *k_stage_names[ST_COUNT] = {"index_build", "seed_scan", "sw_vector", "pass1_select", "sw_full", "post_sw", "other"};
 
 extern "C" int shrimp_gpu_stage_times(shrimp_gpu_ctx *c, const char **names, float *ms, uint64_t *launches, int max_n) {
   if (!c) return 0;

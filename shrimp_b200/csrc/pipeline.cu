@@ -990,7 +990,6 @@ int chunk_run_full(Chunk &C, int n_slots) {
   shrimp_gpu_ctx *ctx = C.ctx;
   Pipeline *pl = C.pl;
   const SwScores &sw = ctx->sw;
-  ScopedStage ss(ctx, ST_FULL);
   SH_TRY(pl->d_fops.ensure(C.ops_stride * (size_t)std::max(n_slots, 1)));
   FullParams FP;
   memset(&FP, 0, sizeof(FP));
@@ -1017,8 +1016,12 @@ int chunk_run_full(Chunk &C, int n_slots) {
   FP.xover_pos = pl->xover_stride ? pl->d_xover.as<int16_t>() : nullptr;
   FP.xover_stride = pl->xover_stride;
   FP.indel_taboo_len = sw.indel_taboo_len;
-  SH_TRY(run_full_sw(ctx, pl->d_perm, pl->d_frow, pl->d_fbp, FP, n_slots, C.cs, C.cnt + 32));
+  {
+    ScopedStage ss(ctx, ST_FULL);
+    SH_TRY(run_full_sw(ctx, pl->d_perm, pl->d_frow, pl->d_fbp, FP, n_slots, C.cs, C.cnt + 32));
+  }
   if (C.post_sw && n_slots > 0) {
+    ScopedStage ss(ctx, ST_POST);
     // hit_run_post_sw (mapping.c:1609-1625) for every alignment with a positive score: emission terms from the host
     // (libm, gmapper.c:2561-2572 and post_sw_setup), recurrences on the device (post_sw.cu)
     const shrimp_map_params *mp = C.mp;
@@ -1039,6 +1042,7 @@ int chunk_run_full(Chunk &C, int n_slots) {
     PS.quals_out = pl->d_fqual.as<uint8_t>();
     PS.max_rlen = C.max_rl;
     PS.n_tasks = n_slots;
+    PS.columns = (unsigned long long *)(C.cnt + 46);
     PS.la1 = log(1 - pr_snp);
     PS.la2 = log(pr_snp / 3.0);
     PS.lc1 = log(1 - pr_xover);
@@ -1127,6 +1131,7 @@ void chunk_stats(const Chunk &C, const uint32_t *hc, shrimp_map_stats *stats) {
   stats->vector_bypassed = hc[8 + 5];
   stats->vector_cells = *(const unsigned long long *)(hc + 8 + 6);
   stats->full_cells = *(const unsigned long long *)(hc + 16);
+  stats->post_sw_columns = *(const unsigned long long *)(hc + 46);
   stats->scan_big_strands = C.scan_big;
   stats->scan_global_strands = C.scan_global;
 }

@@ -150,6 +150,7 @@ __global__ void __launch_bounds__(128) post_sw_kernel(const PostParams P, int ha
   }
   len = __shfl_sync(0xffffffffu, len, 0, 16);
   if (len > max_cols) len = 0;   // cannot happen: columns <= read length
+  if (hl == 0 && len > 0 && P.columns) atomicAdd(P.columns, (unsigned long long)len);
   const int wlen = warp_max_int(len);
   __syncwarp();
   // -log() emission terms of node hl at column c (nodePrior, sw-post.c:112-140): (0 - a) - b
@@ -314,7 +315,7 @@ int launch_post_sw(shrimp_gpu_ctx *ctx, const PostParams &P) {
   const int grid = (P.n_tasks + halves - 1) / halves;
   post_sw_kernel<<<grid, halves * 16, smem, ctx->stream>>>(P, halves, max_cols);
   SH_CUDA(cudaGetLastError());
-  SH_LAUNCHED(ctx, ST_FULL);
+  SH_LAUNCHED(ctx, ST_POST);
   return SHRIMP_OK;
 }
 

@@ -188,6 +188,7 @@ struct PostParams {
   int n_tasks;
   const uint8_t *read_quals;   // quality strings of the reads (gmapper -Q) or nullptr
   int qual_stride, qual_vector_offset;
+  unsigned long long *columns;       // statistics: aligned read columns processed
   const unsigned long long *gm_tab;  // glibc exp/log tables (glibc_math.cuh): exp consts[8], exp tab[256], log consts[18], log tab[256]
   const double *lc1_tab, *lc2_tab;   // per quality character: log(1 - colour error rate), log(rate / 3) (host libm)
   double la1, la2;         // log(1 - pr_snp), log(pr_snp / 3)
