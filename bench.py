@@ -523,10 +523,10 @@ def main():
     }
     post_ms = stage.get("post_sw", (0.0, 0))[0] / a.steps
     if post_ms > 0:
-        # post_sw: per aligned column 16 nodes x (9 exp + 2 log), 11 / 20 FP64 instructions each in the libm
-        # transcription (glibc_math.cuh); against the nominal FP64 issue rate (64 lanes per clock and SM at the
-        # measured SM clock -- MEASURED_PEAKS.json has no FP64 figure)
-        fp64_instr = st["post_sw_columns"] * 16.0 * (9 * 11 + 2 * 20)
+        # post_sw: per aligned column 16 nodes x (3 exp + 2 log: forward, backward, posterior), 11 / 20 FP64
+        # instructions each in the libm transcription (glibc_math.cuh); against the nominal FP64 issue rate (64 lanes
+        # per clock and SM at the measured SM clock -- MEASURED_PEAKS.json has no FP64 figure)
+        fp64_instr = st["post_sw_columns"] * 16.0 * (3 * 11 + 2 * 20)
         sm_mhz = clocks.get("sm_mhz") or 1965.0
         fp64_peak = 148 * 64 * sm_mhz * 1e6 / 1e9
         roofs["post_sw"] = {"kernel": "post_sw_kernel", "bound": "fp64", "achieved": fp64_instr / (post_ms * 1e-3) / 1e9,

@@ -174,13 +174,13 @@ __global__ void __launch_bounds__(128) post_sw_kernel(const PostParams P, int ha
     if (i == 0) {
       nf = PS_LEFT(hl) == init_bp ? node_prior(pc, hl) : HUGE_VAL;
     } else {
+      // exp(-forwards[i-1][k]) depends on k only: every lane takes the exponential of its own node once and the
+      // sums pick their four terms by shuffle, in the reference's order of k
       const double val = node_prior(pc, hl);
+      const double ef = PS_EXP(-1 * (f));
       double s = 0;
 #pragma unroll
-      for (int m = 0; m < 4; m++) {
-        const double pk = __shfl_sync(0xffffffffu, f, 4 * m + PS_LEFT(hl), 16);
-        s += PS_EXP(-1 * (pk));
-      }
+      for (int m = 0; m < 4; m++) s += __shfl_sync(0xffffffffu, ef, 4 * m + PS_LEFT(hl), 16);
       nf = val - PS_LOG(s);
     }
     // forwscale: minimum over the nodes (column 0: over the nodes that start from the initial base; the others are
@@ -217,14 +217,11 @@ __global__ void __launch_bounds__(128) post_sw_kernel(const PostParams P, int ha
       if (i + 1 < len) nxt = cols[i + 1];
     }
     // the shuffles are full-mask: both halves of the warp execute them whatever their own state
+    // exp(-(nodePrior(i+1, k) + backwards[i+1][k])) depends on k only: one exponential per lane, four shuffles per sum
+    const double eb = PS_EXP(-1 * (node_prior(nxt, hl) + b));
     double s = 0;
 #pragma unroll
-    for (int m = 0; m < 4; m++) {
-      const int k = 4 * PS_RIGHT(hl) + m;
-      const double val = node_prior(nxt, k);
-      const double bk = __shfl_sync(0xffffffffu, b, k, 16);
-      s += PS_EXP(-1 * (val + bk));
-    }
+    for (int m = 0; m < 4; m++) s += __shfl_sync(0xffffffffu, eb, 4 * PS_RIGHT(hl) + m, 16);
     const double nb0 = (!on || i == len - 1) ? 0.0 : -PS_LOG(s);   // last column: backwards = 0, backscale = 0
     double nb = nb0;
     const double sc = half_min(nb);
