@@ -80,13 +80,14 @@ __global__ void __launch_bounds__(128) post_sw_kernel(const PostParams P, int ha
   // ---- load_local_vectors: one lane walks the edit script -------------------------------------------------
   int len = 0;
   if (run && hl == 0) {
-    int letter[4];
-    for (int k = 0; k < 4; k++) letter[k] = (k + init_bp) % 4;
-    int start_run = 0, min_qv = 10000;
+    // The full SW's base call at read position j on layer kk is the layer's start letter (kk + initbp) % 4 XORed with
+    // the colours since the last N (cstols, util.h:157-180, is XOR on the 2-bit codes; a colour N gives letter N and
+    // restarts the layer, sw-full-cs.c:1181-1196): one running XOR instead of four letter chains.
+    int px = 0, start_run = 0, min_qv = 10000;
     bool brk = false;
     for (int j = 0; j < R.read_start; j++) {
       const int c = (int)extract4(read, (uint64_t)j);
-      for (int k = 0; k < 4; k++) letter[k] = c == 15 ? (k + init_bp) % 4 : ps_cstols(letter[k], c);
+      px = c == 15 ? 0 : px ^ c;
       if (!brk) {
         if (c == 15) {
           start_run = 15;
@@ -107,16 +108,7 @@ __global__ void __launch_bounds__(128) post_sw_kernel(const PostParams P, int ha
         continue;
       }
       const int c = (int)extract4(read, (uint64_t)j);
-      int qk[4];
-      for (int k = 0; k < 4; k++) {
-        if (c == 15) {
-          qk[k] = 15;
-          letter[k] = (k + init_bp) % 4;
-        } else {
-          qk[k] = ps_cstols(letter[k], c);
-          letter[k] = qk[k];
-        }
-      }
+      px = c == 15 ? 0 : px ^ c;
       PsCol pc;
       if (type == 3) {
         const int g = (int)extract4(genome, gpos);
@@ -139,7 +131,7 @@ __global__ void __launch_bounds__(128) post_sw_kernel(const PostParams P, int ha
           pc.q = 0;
         }
       }
-      pc.call = (int8_t)qk[kk];
+      pc.call = (int8_t)(c == 15 ? 15 : (((kk + init_bp) & 3) ^ px));
       pc.maxp = 0;
       pc.qual = 33;
       pc.pad = 0;
