@@ -77,70 +77,106 @@ __global__ void __launch_bounds__(128) post_sw_kernel(const PostParams P, int ha
   const glibc_math::Tables GT = {P.gm_tab, P.gm_tab + 8, P.gm_tab + 8 + 256, P.gm_tab + 8 + 256 + 18};
 #define PS_EXP(x) glibc_math::exp_glibc((x), GT)
 #define PS_LOG(x) glibc_math::log_glibc((x), GT)
-  // ---- load_local_vectors: one lane walks the edit script -------------------------------------------------
-  int len = 0;
-  if (run && hl == 0) {
-    // The full SW's base call at read position j on layer kk is the layer's start letter (kk + initbp) % 4 XORed with
-    // the colours since the last N (cstols, util.h:157-180, is XOR on the 2-bit codes; a colour N gives letter N and
-    // restarts the layer, sw-full-cs.c:1181-1196): one running XOR instead of four letter chains.
-    int px = 0, start_run = 0, min_qv = 10000;
-    bool brk = false;
-    for (int j = 0; j < R.read_start; j++) {
-      const int c = (int)extract4(read, (uint64_t)j);
-      px = c == 15 ? 0 : px ^ c;
-      if (!brk) {
-        if (c == 15) {
-          start_run = 15;
-          min_qv = 0;
-          brk = true;
-        } else {
-          start_run ^= c;
-          if (rq) min_qv = min(min_qv, (int)rq[j]);
+  // ---- load_local_vectors (sw-post.c:472-545) on all 16 lanes ------------------------------------------------
+  // The full SW's base call at read position j on layer kk is the layer's start letter (kk + initbp) % 4 XORed with
+  // the colours since the last N (cstols, util.h:157-180, is XOR on the 2-bit codes; a colour N gives letter N and
+  // restarts the layer, sw-full-cs.c:1181-1196): a segmented XOR scan over the read.  Column index, read position and
+  // genome position of every edit operation are prefix sums over the script.
+  uint8_t *pxs = (uint8_t *)fw;   // per read position; dead before the forward pass writes fw
+  const int rlen_t = run ? T.rlen : 0, n_ops = run ? R.ops_len : 0;
+  const int w_rlen = warp_max_int(rlen_t), w_ops = warp_max_int(n_ops);
+  const int hshift = (lane >> 4) << 4;
+  int start_run = 0, min_qv = 10000;
+  {
+    int carry = 0, any_n = 0;
+    for (int p0 = 0; p0 < w_rlen; p0 += 16) {
+      const int p = p0 + hl;
+      const bool in = p < rlen_t;
+      const int c = in ? (int)extract4(read, (uint64_t)p) : 15;
+      int v = c != 15 ? c : 0, f = c == 15 ? 1 : 0;
+#pragma unroll
+      for (int d = 1; d < 16; d <<= 1) {
+        const int v2 = __shfl_up_sync(0xffffffffu, v, d, 16), f2 = __shfl_up_sync(0xffffffffu, f, d, 16);
+        if (hl >= d) {
+          if (!f) v ^= v2;
+          f |= f2;
         }
       }
+      if (!f) v ^= carry;
+      if (in) pxs[p] = (uint8_t)v;
+      carry = __shfl_sync(0xffffffffu, v, 15, 16);
+      // the colours before the alignment (:484-496): their XOR, or N as soon as one of them is N
+      const bool pre = in && p < R.read_start;
+      any_n |= (int)((__ballot_sync(0xffffffffu, pre && c == 15) >> hshift) & 0xffffu);
+      int x = (pre && c != 15) ? c : 0, mq = (pre && rq) ? (int)rq[p] : 10000;
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) {
+        x ^= __shfl_xor_sync(0xffffffffu, x, o, 16);
+        mq = min(mq, __shfl_xor_sync(0xffffffffu, mq, o, 16));
+      }
+      start_run ^= x;
+      min_qv = min(min_qv, mq);
     }
-    uint64_t gpos = (uint64_t)T.goff_global + (uint64_t)(R.genome_start - (int)T.goff_contig);
-    int j = R.read_start;
-    for (int o = R.ops_start; o < R.ops_start + R.ops_len; o++) {
-      const int op = ops[o], type = op & 3, kk = (op >> 4) & 3;
-      if (type == 1) {   // genome base against a gap: no read column
-        gpos++;
-        continue;
-      }
-      const int c = (int)extract4(read, (uint64_t)j);
-      px = c == 15 ? 0 : px ^ c;
-      PsCol pc;
-      if (type == 3) {
-        const int g = (int)extract4(genome, gpos);
-        pc.let = (int8_t)(g <= 3 ? g : -1);
-        gpos++;
-      } else {
-        pc.let = -2;
-      }
-      if ((len == 0 && start_run == 15) || c == 15) {
-        pc.col = 0;
-        pc.kind = 2;
-        pc.q = 0;
-      } else {
-        pc.col = (int8_t)(c ^ (len == 0 ? start_run : 0));
-        if (rq) {
-          pc.kind = 1;
-          pc.q = (uint8_t)(len == 0 ? min(min_qv, (int)rq[j]) : (int)rq[j]);
-        } else {
-          pc.kind = 0;
-          pc.q = 0;
-        }
-      }
-      pc.call = (int8_t)(c == 15 ? 15 : (((kk + init_bp) & 3) ^ px));
-      pc.maxp = 0;
-      pc.qual = 33;
-      pc.pad = 0;
-      if (len < max_cols) cols[len] = pc;
-      len++;
-      j++;
+    if (any_n) {
+      start_run = 15;
+      min_qv = 0;
     }
   }
-  len = __shfl_sync(0xffffffffu, len, 0, 16);
+  __syncwarp();
+  int len = 0;
+  {
+    int colbase = 0, genbase = 0;
+    const uint64_t g0 = (uint64_t)T.goff_global + (uint64_t)(R.genome_start - (int)T.goff_contig);
+    for (int q0 = 0; q0 < w_ops; q0 += 16) {
+      const int q = q0 + hl;
+      const bool in = q < n_ops;
+      const int op = in ? (int)ops[R.ops_start + q] : 0, type = op & 3, kk = (op >> 4) & 3;
+      const int isread = (in && type != 1) ? 1 : 0, isgen = (in && type != 2) ? 1 : 0;
+      int ir = isread, ig = isgen;
+#pragma unroll
+      for (int d = 1; d < 16; d <<= 1) {
+        const int r2 = __shfl_up_sync(0xffffffffu, ir, d, 16), g2 = __shfl_up_sync(0xffffffffu, ig, d, 16);
+        if (hl >= d) {
+          ir += r2;
+          ig += g2;
+        }
+      }
+      const int col = colbase + ir - isread;
+      if (isread && col < max_cols) {
+        const int j = R.read_start + col;
+        const int c = (int)extract4(read, (uint64_t)j);
+        PsCol pc;
+        if (type == 3) {
+          const int g = (int)extract4(genome, g0 + (uint64_t)(genbase + ig - isgen));
+          pc.let = (int8_t)(g <= 3 ? g : -1);
+        } else {
+          pc.let = -2;
+        }
+        if ((col == 0 && start_run == 15) || c == 15) {
+          pc.col = 0;
+          pc.kind = 2;
+          pc.q = 0;
+        } else {
+          pc.col = (int8_t)(c ^ (col == 0 ? start_run : 0));
+          if (rq) {
+            pc.kind = 1;
+            pc.q = (uint8_t)(col == 0 ? min(min_qv, (int)rq[j]) : (int)rq[j]);
+          } else {
+            pc.kind = 0;
+            pc.q = 0;
+          }
+        }
+        pc.call = (int8_t)(c == 15 ? 15 : (((kk + init_bp) & 3) ^ (int)pxs[j]));
+        pc.maxp = 0;
+        pc.qual = 33;
+        pc.pad = 0;
+        cols[col] = pc;
+      }
+      colbase += __shfl_sync(0xffffffffu, ir, 15, 16);
+      genbase += __shfl_sync(0xffffffffu, ig, 15, 16);
+    }
+    len = colbase;
+  }
   if (len > max_cols) len = 0;   // cannot happen: columns <= read length
   if (hl == 0 && len > 0 && P.columns) atomicAdd(P.columns, (unsigned long long)len);
   const int wlen = warp_max_int(len);
