@@ -36,10 +36,10 @@ __device__ __forceinline__ int ps_cstols(int first_letter, int colour) {   // cs
   if (first_letter == 15 || colour < 0 || colour > 3) return 15;
   return (first_letter % 2 == 0) ? (4 + first_letter + colour) % 4 : (4 + first_letter - colour) % 4;
 }
-__device__ __forceinline__ int ps_qv_from_pr_err(double pr_err, const glibc_math::Tables &GT) {   // util.h:268-276
+__device__ __forceinline__ int ps_qv_from_pr_err(double pr_err, double log10v, const glibc_math::Tables &GT) {   // util.h:268-276
   if (pr_err > .99999999) return 0;
   else if (pr_err < 1E-25) return 250;
-  else return (int)(-10.0 * glibc_math::log_glibc(pr_err, GT) / glibc_math::log_glibc(10.0, GT));
+  else return (int)(-10.0 * glibc_math::log_glibc(pr_err, GT) / log10v);
 }
 
 struct PsCol {   // one aligned read column (struct column, sw-post.c:61-78, without the recurrences' arrays)
@@ -272,12 +272,21 @@ __global__ void __launch_bounds__(128) post_sw_kernel(const PostParams P, int ha
       if (p1 > pm) { maxval = 1; pm = p1; }
       if (p2 > pm) { maxval = 2; pm = p2; }
       if (p3 > pm) { maxval = 3; pm = p3; }
+      // the base quality needs a log(): park 1 - posterior[base call] in the column's forwscale slot (dead from
+      // here on) and take the logarithms of all columns together afterwards, a lane per column
       const int bc = pc.call;
-      int tmp = 0;
-      if (bc != 15) tmp = ps_qv_from_pr_err(1 - (bc == 0 ? p0 : bc == 1 ? p1 : bc == 2 ? p2 : p3), GT);
-      if (tmp > 40) tmp = 40;
+      fscale[i] = bc != 15 ? 1 - (bc == 0 ? p0 : bc == 1 ? p1 : bc == 2 ? p2 : p3) : 2.0;
       cols[i].maxp = (int8_t)maxval;
-      cols[i].qual = (uint8_t)(33 + tmp);
+    }
+  }
+  __syncwarp();
+  {   // get_base_qualities (sw-post.c:584-601)
+    const double log10v = PS_LOG(10.0);
+    for (int c = hl; c < len; c += 16) {
+      const double pe = fscale[c];
+      int tmp = pe == 2.0 ? 0 : ps_qv_from_pr_err(pe, log10v, GT);
+      if (tmp > 40) tmp = 40;
+      cols[c].qual = (uint8_t)(33 + tmp);
     }
   }
   __syncwarp();
