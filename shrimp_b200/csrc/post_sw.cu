@@ -290,47 +290,82 @@ __global__ void __launch_bounds__(128) post_sw_kernel(const PostParams P, int ha
     }
   }
   __syncwarp();
-  // ---- fix_base_calls (:548-581), get_posterior (:604-626): one lane rewrites the edit script -----------------------
-  if (run && hl == 0 && len > 0) {
+  // ---- fix_base_calls (:548-581) on all lanes, get_posterior (:604-626) by one lane over the gap columns only ----
+  {
     uint8_t *wops = P.ops + (size_t)slot * (size_t)P.ops_stride;
     uint8_t *qout = P.quals_out + (size_t)slot * (size_t)P.max_rlen;
-    uint64_t gpos = (uint64_t)T.goff_global + (uint64_t)(R.genome_start - (int)T.goff_contig);
-    int prev_base = init_bp, j = 0, prev_type = 0;
+    const uint64_t g0 = (uint64_t)T.goff_global + (uint64_t)(R.genome_start - (int)T.goff_contig);
+    const bool doit = run && len > 0;
+    const int n_ops3 = doit ? n_ops : 0;
     int matches = 0, mismatches = 0, crossovers = 0;
-    double res = PS_EXP(-total_score);
-    for (int o = R.ops_start; o < R.ops_start + R.ops_len; o++) {
-      const int op = wops[o], type = op & 3;
-      if (type == 1) {   // qralign '-': a deletion column of get_posterior
-        gpos++;
-        res *= P.pr_del_extend;
-        if (o == R.ops_start || prev_type != 1) res *= P.pr_del_open;
-      } else {
-        const PsCol pc = cols[j];
+    int colbase = 0, genbase = 0, last_type = 0;
+    double res = (doit && hl == 0) ? PS_EXP(-total_score) : 0.0;
+    for (int q0 = 0; q0 < w_ops; q0 += 16) {
+      const int q = q0 + hl;
+      const bool in = q < n_ops3;
+      const int op = in ? (int)wops[R.ops_start + q] : 0, type = in ? (op & 3) : 0;
+      const int isread = (in && type != 1) ? 1 : 0, isgen = (in && type != 2) ? 1 : 0;
+      int ir = isread, ig = isgen;
+#pragma unroll
+      for (int d = 1; d < 16; d <<= 1) {
+        const int r2 = __shfl_up_sync(0xffffffffu, ir, d, 16), g2 = __shfl_up_sync(0xffffffffu, ig, d, 16);
+        if (hl >= d) {
+          ir += r2;
+          ig += g2;
+        }
+      }
+      // type of the previous column (for the gap-open test)
+      int ptype = __shfl_up_sync(0xffffffffu, type, 1, 16);
+      if (hl == 0) ptype = last_type;
+      const int col = colbase + ir - isread;
+      if (isread) {
+        const PsCol pc = cols[col];
         const int crt = pc.maxp;
+        const int prev_base = col == 0 ? init_bp : (int)cols[col - 1].maxp;
         const bool lower = (prev_base ^ crt) != pc.col;
         if (lower) crossovers++;
         if (type == 3) {
-          const int g = (int)extract4(genome, gpos);
-          gpos++;
+          const int g = (int)extract4(genome, g0 + (uint64_t)(genbase + ig - isgen));
           if (g == crt) matches++;
           else mismatches++;
-        } else {   // dbalign '-': an insertion column of get_posterior
-          res *= P.pr_ins_extend;
-          if (o == R.ops_start || prev_type != 2) res *= P.pr_ins_open;
         }
         // bit 3: bits 4-5 are the base call itself (not a layer); bit 2: lower case (crossover before this base)
-        wops[o] = (uint8_t)(type | (lower ? 4 : 0) | 8 | (crt << 4));
-        qout[j] = pc.qual;
-        prev_base = crt;
-        j++;
+        wops[R.ops_start + q] = (uint8_t)(type | (lower ? 4 : 0) | 8 | (crt << 4));
+        qout[col] = pc.qual;
       }
-      prev_type = type;
+      // gap columns, in script order: a genome base against a gap multiplies by the deletion terms, a read base
+      // against a gap by the insertion terms; the open term when the previous column was not the same kind of gap
+      const bool gap = in && type != 3;
+      const bool opens = gap && (q == 0 || ptype != type);
+      uint32_t gm = (__ballot_sync(0xffffffffu, gap) >> hshift) & 0xffffu;
+      const uint32_t dm = (__ballot_sync(0xffffffffu, gap && type == 1) >> hshift) & 0xffffu;
+      const uint32_t om = (__ballot_sync(0xffffffffu, opens) >> hshift) & 0xffffu;
+      if (hl == 0)
+        while (gm) {
+          const int bpos = __ffs(gm) - 1;
+          gm &= gm - 1;
+          const bool del = (dm >> bpos) & 1u;
+          res *= del ? P.pr_del_extend : P.pr_ins_extend;
+          if ((om >> bpos) & 1u) res *= del ? P.pr_del_open : P.pr_ins_open;
+        }
+      colbase += __shfl_sync(0xffffffffu, ir, 15, 16);
+      genbase += __shfl_sync(0xffffffffu, ig, 15, 16);
+      const int lt_ = __shfl_sync(0xffffffffu, type, 15, 16);
+      last_type = lt_;
     }
-    R.matches = matches;
-    R.mismatches = mismatches;
-    R.crossovers = crossovers;
-    R.posterior = res;
-    P.results[slot] = R;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+      matches += __shfl_xor_sync(0xffffffffu, matches, o, 16);
+      mismatches += __shfl_xor_sync(0xffffffffu, mismatches, o, 16);
+      crossovers += __shfl_xor_sync(0xffffffffu, crossovers, o, 16);
+    }
+    if (doit && hl == 0) {
+      R.matches = matches;
+      R.mismatches = mismatches;
+      R.crossovers = crossovers;
+      R.posterior = res;
+      P.results[slot] = R;
+    }
   }
 }
 
