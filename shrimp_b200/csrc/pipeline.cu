@@ -565,6 +565,7 @@ int chunk_scan(Chunk &C) {
     }
     // staging window: about half of a partition's entries, 1024..4096
     while (cta_win < 4096 && cta_win < 0.4 * est / cta_n_part) cta_win <<= 1;
+    if (est / cta_n_part > 6000.0) cta_win = 8192;   // hg18 scale: a partition in one window, staged once for both passes
     if (const char *e = getenv("SHRIMP_SCAN_WIN")) cta_win = std::max(64, atoi(e));  // test hook: several windows
     if (const char *e = getenv("SHRIMP_SCAN_CTA_CAP")) cta_cap = std::max(32, atoi(e));  // test hook: global slabs
     while (cta_cap > 256 && scan_cta_smem_bytes(cta_cap, max_rl, big_k_cap, cta_bm_log2, cta_n_part, cta_win, false) > 200 * 1024)
