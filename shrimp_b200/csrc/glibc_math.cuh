@@ -19,6 +19,24 @@
 
 namespace glibc_math {
 
+// The scalar constants: operands straight from the constant bank in device code (a 64-bit immediate costs two moves,
+// a global load a round trip), literals on the host
+#ifdef __CUDACC__
+static __constant__ unsigned long long GM_DEV_EXP[8] = {GLIBC_EXP_CONST_0, GLIBC_EXP_CONST_1, GLIBC_EXP_CONST_2, GLIBC_EXP_CONST_3,
+                                                        GLIBC_EXP_CONST_4, GLIBC_EXP_CONST_5, GLIBC_EXP_CONST_6, GLIBC_EXP_CONST_7};
+static __constant__ unsigned long long GM_DEV_LOG[18] = {
+    GLIBC_LOG_CONST_0,  GLIBC_LOG_CONST_1,  GLIBC_LOG_CONST_2,  GLIBC_LOG_CONST_3,  GLIBC_LOG_CONST_4,  GLIBC_LOG_CONST_5,
+    GLIBC_LOG_CONST_6,  GLIBC_LOG_CONST_7,  GLIBC_LOG_CONST_8,  GLIBC_LOG_CONST_9,  GLIBC_LOG_CONST_10, GLIBC_LOG_CONST_11,
+    GLIBC_LOG_CONST_12, GLIBC_LOG_CONST_13, GLIBC_LOG_CONST_14, GLIBC_LOG_CONST_15, GLIBC_LOG_CONST_16, GLIBC_LOG_CONST_17};
+#endif
+#ifdef __CUDA_ARCH__
+#define GM_EC(i) gm_asdouble(GM_DEV_EXP[i])
+#define GM_LC(i) gm_asdouble(GM_DEV_LOG[i])
+#else
+#define GM_EC(i) gm_asdouble(GLIBC_EXP_CONST_##i)
+#define GM_LC(i) gm_asdouble(GLIBC_LOG_CONST_##i)
+#endif
+
 GM_HD double gm_asdouble(unsigned long long u) {
 #ifdef __CUDA_ARCH__
   return __longlong_as_double((long long)u);
@@ -76,10 +94,9 @@ GM_HD double exp_glibc(double x, const Tables &T) {
     }
     abstop = 0;   // 512 <= |x| < 1024: handled below with the special scaling
   }
-  const double InvLn2N = gm_asdouble(T.exp_const[0]), Shift = gm_asdouble(T.exp_const[1]);
-  const double NegLn2hiN = gm_asdouble(T.exp_const[2]), NegLn2loN = gm_asdouble(T.exp_const[3]);
-  const double C2 = gm_asdouble(T.exp_const[4]), C3 = gm_asdouble(T.exp_const[5]);
-  const double C4 = gm_asdouble(T.exp_const[6]), C5 = gm_asdouble(T.exp_const[7]);
+  // only the 2^(j/128) table is read through the pointer
+  const double InvLn2N = GM_EC(0), Shift = GM_EC(1), NegLn2hiN = GM_EC(2), NegLn2loN = GM_EC(3);
+  const double C2 = GM_EC(4), C3 = GM_EC(5), C4 = GM_EC(6), C5 = GM_EC(7);
   double kd = fma(x, InvLn2N, Shift);
   const unsigned long long ki = gm_asuint64(kd);
   kd = kd - Shift;
@@ -102,7 +119,6 @@ GM_HD double exp_glibc(double x, const Tables &T) {
 
 GM_HD double log_glibc(double x, const Tables &T) {
   unsigned long long ix = gm_asuint64(x);
-#define GM_LC(i) gm_asdouble(T.log_const[i])
   if (ix + 0xc012000000000000ull <= 0x308ffffffffffull) {   // 1 - 0x1p-4 <= x < 1 + 0x1.09p-4
     if (ix == 0x3ff0000000000000ull) return 0.0;
     const double B0 = GM_LC(7), B1 = GM_LC(8), B2 = GM_LC(9), B3 = GM_LC(10), B4 = GM_LC(11), B5 = GM_LC(12),
@@ -162,7 +178,6 @@ GM_HD double log_glibc(double x, const Tables &T) {
   const double pC = fma(pB, r2, pA);
   const double y0 = fma(r3, pC, lo);
   return y0 + hi;
-#undef GM_LC
 }
 
 }  // namespace glibc_math

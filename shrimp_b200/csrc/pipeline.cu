@@ -21,7 +21,7 @@ size_t scan_smem_bytes(int cap, int max_rl, int k_cap, int bm_log2, int warps, i
 size_t scan_cta_smem_bytes(int cap, int max_rl, int k_cap, int bm_log2, int n_part, int win, bool global_arrays);
 int launch_scan_cta(shrimp_gpu_ctx *ctx, ScanParams &P, int n_ctas, int threads);
 int launch_scan_replay(shrimp_gpu_ctx *ctx, ScanParams &P, uint32_t n_rec, int ks_cap);
-int launch_post_sw(shrimp_gpu_ctx *ctx, const PostParams &P);
+int launch_post_sw(shrimp_gpu_ctx *ctx, const PostParams &P, DevBuf &scratch);
 
 int launch_scan(shrimp_gpu_ctx *ctx, ScanParams &P, int warps_per_cta, int n_ctas);
 int launch_build_vec_tasks(shrimp_gpu_ctx *ctx, const TaskBuildParams &P);
@@ -1086,7 +1086,7 @@ int chunk_run_full(Chunk &C, int n_slots) {
       PS.qual_stride = pl->qual_stride;
       PS.qual_vector_offset = mp->qual_vector_offset;
     }
-    SH_TRY(launch_post_sw(ctx, PS));
+    SH_TRY(launch_post_sw(ctx, PS, pl->d_scratch));   // the scan scratch is dead by now
   }
   return SHRIMP_OK;
 }

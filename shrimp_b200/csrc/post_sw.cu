@@ -7,8 +7,11 @@
 // The model is a 16-node chain (node = letter pair, left/right) over the aligned read columns.  One HALF-WARP per
 // alignment, lane = node: the forward and backward recurrences take their four predecessor / successor values by
 // width-16 shuffles, sums run in the reference's index order, the scale (minimum over the nodes) is a half-warp
-// reduction; forwards[][] of all columns stay in shared memory for the posterior pass.  The two alignments of a warp
-// run in lockstep (trip counts = the longer one).  Every double is the reference's, bit for bit: the -log() emission
+// reduction; forwards[][] of all columns wait for the posterior pass in a global scratch row per resident half-warp
+// (written and read back by the same lane, 128 contiguous bytes per column: it lives in L2), so that shared memory
+// holds only the columns and the scales and the register file bounds the occupancy.  The kernel is persistent: a
+// CTA takes groups of alignments grid-stride.  The two alignments of a warp run in lockstep (trip counts = the
+// longer one).  Every double is the reference's, bit for bit: the -log() emission
 // terms come from the host (libm) as constants / a 256-entry table over the quality characters, and exp() / log()
 // inside the recurrences are glibc_math.cuh -- the libm algorithms operation by operation -- because equally likely
 // alternatives (two colour errors of the same quality) tie exactly and the last bit of a sum decides the base call.
@@ -19,6 +22,7 @@
 
 namespace shrimp {
 
+#define PS_CTAS_PER_SM 8
 #define PS_LEFT(i) (((i) >> 2) & 3)
 #define PS_RIGHT(i) ((i) & 3)
 
@@ -28,9 +32,9 @@ __device__ __forceinline__ double half_min(double v) {
   return v;
 }
 __device__ __forceinline__ int warp_max_int(int v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
+  // redux.sync leaves its result in a uniform register: the loops bounded by it are known to be warp-uniform and
+  // the shuffles inside need no reconvergence code
+  return __reduce_max_sync(0xffffffffu, v);
 }
 __device__ __forceinline__ int ps_cstols(int first_letter, int colour) {   // cstols, util.h:157-180
   if (first_letter == 15 || colour < 0 || colour > 3) return 15;
@@ -53,16 +57,24 @@ struct PsCol {   // one aligned read column (struct column, sw-post.c:61-78, wit
   uint8_t pad;
 };
 
-__global__ void __launch_bounds__(128) post_sw_kernel(const PostParams P, int halves_per_cta, int max_cols) {
+__host__ __device__ inline size_t ps_smem_doubles_per_half(int max_cols) {
+  // forwscale[max_cols], columns[max_cols], the segmented XOR scan of the read (one byte per position)
+  return (size_t)max_cols + ((size_t)max_cols * sizeof(PsCol) + 7) / 8 + ((size_t)max_cols + 7) / 8;
+}
+
+__global__ void __launch_bounds__(128, PS_CTAS_PER_SM) post_sw_kernel(const PostParams P, int halves_per_cta, int max_cols,
+                                                                      int n_groups, double *fw_scratch) {
   extern __shared__ double ps_smem[];
   const int lane = threadIdx.x & 31, hl = lane & 15;
   const int hidx = threadIdx.x >> 4;   // half-warp of the CTA
-  // per half-warp: forwards[max_cols][16], forwscale[max_cols], columns[max_cols]
-  const size_t per_half = (size_t)max_cols * 17 + ((size_t)max_cols * sizeof(PsCol) + 7) / 8;
-  double *fw = ps_smem + (size_t)hidx * per_half;
-  double *fscale = fw + (size_t)max_cols * 16;
+  double *fscale = ps_smem + (size_t)hidx * ps_smem_doubles_per_half(max_cols);
   PsCol *cols = (PsCol *)(fscale + max_cols);
-  int slot = blockIdx.x * halves_per_cta + hidx;
+  uint8_t *pxs = (uint8_t *)(cols + max_cols);   // per read position
+  // forwards[max_cols][16] of this half-warp
+  double *fw = fw_scratch + ((size_t)blockIdx.x * halves_per_cta + hidx) * (size_t)max_cols * 16;
+  const glibc_math::Tables GT = {P.gm_tab, P.gm_tab + 8, P.gm_tab + 8 + 256, P.gm_tab + 8 + 256 + 18};
+  for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+  int slot = grp * halves_per_cta + hidx;
   const bool live = hidx < halves_per_cta && slot < P.n_tasks;
   if (!live) slot = P.n_tasks - 1;
   const FullTask T = P.tasks[slot];
@@ -74,7 +86,6 @@ __global__ void __launch_bounds__(128) post_sw_kernel(const PostParams P, int ha
   const uint8_t *rq = P.read_quals ? P.read_quals + (size_t)(T.ridx >> 1) * (size_t)P.qual_stride + P.qual_vector_offset
                                    : nullptr;
   const int init_bp = T.initbp;
-  const glibc_math::Tables GT = {P.gm_tab, P.gm_tab + 8, P.gm_tab + 8 + 256, P.gm_tab + 8 + 256 + 18};
 #define PS_EXP(x) glibc_math::exp_glibc((x), GT)
 #define PS_LOG(x) glibc_math::log_glibc((x), GT)
   // ---- load_local_vectors (sw-post.c:472-545) on all 16 lanes ------------------------------------------------
@@ -82,7 +93,6 @@ __global__ void __launch_bounds__(128) post_sw_kernel(const PostParams P, int ha
   // the colours since the last N (cstols, util.h:157-180, is XOR on the 2-bit codes; a colour N gives letter N and
   // restarts the layer, sw-full-cs.c:1181-1196): a segmented XOR scan over the read.  Column index, read position and
   // genome position of every edit operation are prefix sums over the script.
-  uint8_t *pxs = (uint8_t *)fw;   // per read position; dead before the forward pass writes fw
   const int rlen_t = run ? T.rlen : 0, n_ops = run ? R.ops_len : 0;
   const int w_rlen = warp_max_int(rlen_t), w_ops = warp_max_int(n_ops);
   const int hshift = (lane >> 4) << 4;
@@ -367,22 +377,29 @@ __global__ void __launch_bounds__(128) post_sw_kernel(const PostParams P, int ha
       P.results[slot] = R;
     }
   }
+  __syncwarp();   // the next group reuses the columns
+  }
 }
 
-int launch_post_sw(shrimp_gpu_ctx *ctx, const PostParams &P) {
+int launch_post_sw(shrimp_gpu_ctx *ctx, const PostParams &P, DevBuf &scratch) {
   if (P.n_tasks <= 0) return SHRIMP_OK;
   const int max_cols = std::max(1, P.max_rlen);
-  const size_t per_half = ((size_t)max_cols * 17 + ((size_t)max_cols * sizeof(PsCol) + 7) / 8) * sizeof(double);
-  int halves = 8;
-  while (halves > 2 && per_half * halves > 200 * 1024) halves -= 2;
-  if (per_half * 2 > 220 * 1024) {
+  const size_t per_half = ps_smem_doubles_per_half(max_cols) * sizeof(double);
+  const int halves = 8;
+  if (per_half * halves > 200 * 1024) {
     set_error("post_sw: reads of %d bases need more shared memory than a CTA has", P.max_rlen);
     return SHRIMP_E_RANGE;
   }
   const size_t smem = per_half * halves;
-  SH_CUDA(cudaFuncSetAttribute(post_sw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = (P.n_tasks + halves - 1) / halves;
-  post_sw_kernel<<<grid, halves * 16, smem, ctx->stream>>>(P, halves, max_cols);
+  auto kern = post_sw_kernel;
+  SH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  SH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, halves * 16, smem));
+  if (per_sm < 1) per_sm = 1;
+  const int n_groups = (P.n_tasks + halves - 1) / halves;
+  const int grid = std::min(n_groups, ctx->sm_count * per_sm);
+  SH_TRY(scratch.ensure((size_t)grid * halves * (size_t)max_cols * 16 * sizeof(double)));
+  kern<<<grid, halves * 16, smem, ctx->stream>>>(P, halves, max_cols, n_groups, scratch.as<double>());
   SH_CUDA(cudaGetLastError());
   SH_LAUNCHED(ctx, ST_POST);
   return SHRIMP_OK;
