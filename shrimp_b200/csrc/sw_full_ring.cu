@@ -766,19 +766,27 @@ __global__ void __launch_bounds__(QUAD_THREADS) sw_full_cs_quad_kernel(const Ful
   const size_t NT = (size_t)P.NT;
   const unsigned short *bp = (const unsigned short *)P.bp64 + (size_t)slot * 4;
   uint8_t *ops = P.ops + (size_t)t * (size_t)(P.max_glen + P.max_rlen);
+  // Letter of layer kk at read row i: the layer's start letter XORed with the colours since the last N (cstols,
+  // util.h:157-180, is XOR on the 2-bit codes; a colour N restarts the layer, sw-full-cs.c:1181-1196).  The
+  // traceback asks for rows in descending order, so the XOR is carried from row to row (one colour per step) and
+  // only recomputed from the start of the read at the first use and after crossing an N.
+  int lx_row = -1, lx_val = 0;
   auto layer_letter = [&](int kk, int i) -> int {
-    int letter = (kk + T.initbp) % 4, out = 15;
-    for (int q = 0; q <= i; q++) {
-      const int colour = (int)extract4(read, (uint64_t)q);
-      if (colour == 15) {
-        out = 15;
-        letter = (kk + T.initbp) % 4;
-      } else {
-        out = cstols_r(letter, colour);
-        letter = out;
-      }
+    if ((int)extract4(read, (uint64_t)i) == 15) return 15;
+    while (lx_row > i) {   // lx_val is the XOR at lx_row (colour there is not N)
+      lx_val ^= (int)extract4(read, (uint64_t)lx_row);
+      lx_row--;
+      if ((int)extract4(read, (uint64_t)lx_row) == 15) lx_row = -1;
     }
-    return out;
+    if (lx_row != i) {
+      lx_val = 0;
+      for (int q = 0; q <= i; q++) {
+        const int colour = (int)extract4(read, (uint64_t)q);
+        lx_val = colour == 15 ? 0 : lx_val ^ colour;
+      }
+      lx_row = i;
+    }
+    return ((kk + T.initbp) & 3) ^ lx_val;
   };
   auto back_of = [&](int ci, int cj, int kk, int state) -> int {  // state: 0 north, 1 west, 2 northwest
     if (ci < 0 || cj < 0) return 0;
