@@ -317,6 +317,11 @@ int shrimp_gpu_set_host_threads(int n);
  * reference runs on), so that a test can compare them bit for bit with the host's libm. */
 int shrimp_gpu_glibc_explog(shrimp_gpu_ctx *ctx, const double *x, int n, double *exp_out, double *log_out);
 
+/* Diagnostic: hash_genome_window (common/util.h:220-241, the key of the f1 window cache, f1-wrapper.h:97-134) of n
+ * windows [goff, goff + glen) of a packed genome (8 four-bit codes per word, host memory) as the device computes it. */
+int shrimp_gpu_hash_windows(shrimp_gpu_ctx *ctx, const uint32_t *genome_words, uint64_t n_words, const uint32_t *goff,
+                            const int32_t *glen, int n, uint32_t *hash_out);
+
 #ifdef __cplusplus
 }
 #endif

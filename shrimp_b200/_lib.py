@@ -116,6 +116,8 @@ def lib() -> C.CDLL:
     L.shrimp_gpu_set_host_threads.restype = i32
     L.shrimp_gpu_glibc_explog.argtypes = [vp, vp, C.c_int, vp, vp]
     L.shrimp_gpu_glibc_explog.restype = i32
+    L.shrimp_gpu_hash_windows.argtypes = [vp, vp, u64, vp, vp, C.c_int, vp]
+    L.shrimp_gpu_hash_windows.restype = i32
     L.shrimp_gpu_genome_load.argtypes = [vp, i32, vp, vp, i32]
     L.shrimp_gpu_genome_load.restype = i32
     L.shrimp_gpu_share_genome.argtypes = [vp, vp]

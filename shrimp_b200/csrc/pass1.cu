@@ -15,18 +15,36 @@ namespace shrimp {
 
 
 // hash_accumulate / hash_finalize (common/hash.h:69-92), hash_genome_window (util.h:220-241)
+// The window is read a word (8 codes) at a time: a group of 16 codes is two words at the window's fixed
+// misalignment, squeezed to 2 bits per code and reversed pairwise (the reference shifts the codes in first-to-last,
+// so the first code ends up most significant; a short last group is right-aligned).
+__device__ __forceinline__ uint32_t squeeze8_pairs(uint32_t w) {   // 8 codes -> 16 bits, code j at bits 2j
+  w &= 0x33333333u;
+  w = (w | (w >> 2)) & 0x0f0f0f0fu;
+  w = (w | (w >> 4)) & 0x00ff00ffu;
+  w = (w | (w >> 8)) & 0x0000ffffu;
+  return w;
+}
 __device__ __forceinline__ uint32_t hash_genome_window_dev(const uint32_t *genome, uint64_t goff, uint32_t glen) {
   uint32_t key = 0;
+  const uint32_t *wp = genome + (goff >> 3);
+  const uint32_t sh = (uint32_t)(goff & 7u), shb = 4u * sh;
+  uint32_t w0 = glen ? wp[0] : 0u;
   for (uint32_t i = 0; i < (glen + 15) / 16; i++) {
-    uint32_t buffer = 0;
-    for (uint32_t j = 0; j < 16 && i * 16 + j < glen; j++) {
-      buffer <<= 2;
-      buffer |= extract4(genome, goff + i * 16 + j) & 3u;
-    }
+    const uint32_t cnt = min(16u, glen - i * 16u), need = sh + cnt;   // codes of this group, codes from wp[2i] on
+    const uint32_t w1 = need > 8u ? wp[2 * i + 1] : 0u, w2 = need > 16u ? wp[2 * i + 2] : 0u;
+    const uint32_t lo = __funnelshift_r(w0, w1, shb), hi = __funnelshift_r(w1, w2, shb);
+    uint32_t v = squeeze8_pairs(lo) | (squeeze8_pairs(hi) << 16);    // code j of the group at bits 2j
+    if (cnt < 16u) v &= (1u << (2u * cnt)) - 1u;
+    v = __brev(v);
+    v = ((v & 0x55555555u) << 1) | ((v >> 1) & 0x55555555u);         // code j at bits 2 (15 - j)
+    const uint32_t buffer = v >> (2u * (16u - cnt));
     key += (buffer >> 16);
     uint32_t tmp = ((buffer & 0xFFFFu) << 11) ^ key;
     key = (key << 16) ^ tmp;
     key += key >> 11;
+    w0 = w2;
+    if (sh == 0u && i * 16u + 16u < glen) w0 = wp[2 * i + 2];
   }
   key ^= key << 3;
   key += key >> 5;
@@ -43,10 +61,11 @@ __device__ __forceinline__ uint32_t hash_genome_window_dev(const uint32_t *genom
 // score goes to.
 __global__ void build_vec_tasks_kernel(const TaskBuildParams P) {
   const uint32_t rs = blockIdx.x * blockDim.x + threadIdx.x;
-  if (rs >= 2u * (uint32_t)P.n_reads) return;
-  const uint2 rg = P.rs_range[rs];
+  const bool live = rs < 2u * (uint32_t)P.n_reads;
+  const int lane = threadIdx.x & 31;
+  const uint2 rg = live ? P.rs_range[rs] : make_uint2(0u, 0u);
   const int r = (int)(rs >> 1), st = (int)(rs & 1u);
-  const int rl = P.read_len[r];
+  const int rl = live ? P.read_len[r] : 0;
   const bool cs = P.M.colour_space != 0;
   // orientation used by pass 1: letter space always scores read strand st on the forward genome;
   // colour space scores the forward read and flips strand-1 windows onto the rc genome.
@@ -60,31 +79,65 @@ __global__ void build_vec_tasks_kernel(const TaskBuildParams P) {
       elig_cells += (unsigned long long)h.w_len * (unsigned long long)rl;
     }
   }
-  uint32_t t = n_elig ? atomicAdd(&P.task_stats[4 + ori], n_elig) : 0u;
+  // dense slots: one atomic per warp and orientation (millions of per-strand atomics on one counter serialise),
+  // the strands of a warp in lane order behind it
+  uint32_t t = 0;
+#pragma unroll
+  for (int o = 0; o < 2; o++) {
+    const uint32_t mine = ori == o ? n_elig : 0u;
+    uint32_t incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += v;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    uint32_t base = 0;
+    if (lane == 31 && total) base = atomicAdd(&P.task_stats[4 + o], total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    if (ori == o) t = base + incl - mine;
+    if (o == 0) {   // statistics of the whole warp
+      uint32_t ne = n_elig;
+      unsigned long long ec = elig_cells;
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) {
+        ne += __shfl_xor_sync(0xffffffffu, ne, d);
+        ec += __shfl_xor_sync(0xffffffffu, ec, d);
+      }
+      if (lane == 0 && ne) {
+        atomicAdd(&P.task_stats[0], ne);
+        atomicAdd((unsigned long long *)&P.task_stats[2], ec);
+      }
+    }
+  }
   for (uint32_t k = 0; k < rg.y; k++) {
     const uint32_t hi = rg.x + k;
     const DevHit h = P.hits[hi];
-    const bool eligible = h.matches >= P.M.min_matches;
+    if (h.matches < P.M.min_matches) continue;
     const uint32_t coff = P.G.contig_off[h.cn];
     const uint32_t g = ori ? coff + (P.G.contig_len[h.cn] - h.g_off - (uint32_t)h.w_len) : coff + h.g_off;
-    if (eligible) {
-      P.goff[ori][t] = g;
-      P.glen[ori][t] = h.w_len;
-      P.ridx[ori][t] = cs ? (int32_t)(2 * r) : (int32_t)rs;
-      P.rlen[ori][t] = rl;
-      if (cs) P.initbp_out[ori][t] = P.initbp[r];
-      P.out[ori][t] = hi;
-      t++;
-    }
-    if (P.slot) {
-      const uint32_t *gen = cs ? (ori ? P.G.cs_rc : P.G.cs) : P.G.ls;
-      P.slot[hi] = eligible ? (hash_genome_window_dev(gen, g, (uint32_t)h.w_len) % 1048576u) : 0xffffffffu;
-    }
+    P.goff[ori][t] = g;
+    P.glen[ori][t] = h.w_len;
+    P.ridx[ori][t] = cs ? (int32_t)(2 * r) : (int32_t)rs;
+    P.rlen[ori][t] = rl;
+    if (cs) P.initbp_out[ori][t] = P.initbp[r];
+    P.out[ori][t] = hi;
+    t++;
   }
-  if (n_elig) {
-    atomicAdd(&P.task_stats[0], n_elig);
-    atomicAdd((unsigned long long *)&P.task_stats[2], elig_cells);
-  }
+}
+
+// f1 cache slot (f1-wrapper.h:97-134: hash_genome_window % 2^20) of every dense task's window, a thread per task;
+// the slots of the hits without a task stay 0xffffffff (the caller's memset)
+__global__ void window_slots_kernel(const uint32_t *genome, const uint32_t *goff, const int32_t *glen, const uint32_t *out,
+                                    uint32_t n_tasks, uint32_t *slot) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tasks) return;
+  slot[out[t]] = hash_genome_window_dev(genome, goff[t], (uint32_t)glen[t]) % 1048576u;
+}
+
+__global__ void window_hash_kernel(const uint32_t *genome, const uint32_t *goff, const int32_t *glen, uint32_t n, uint32_t *hash) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) hash[t] = hash_genome_window_dev(genome, goff[t], (uint32_t)glen[t]);
 }
 
 
@@ -270,6 +323,15 @@ int launch_build_vec_tasks(shrimp_gpu_ctx *ctx, const TaskBuildParams &P) {
   return SHRIMP_OK;
 }
 
+int launch_window_slots(shrimp_gpu_ctx *ctx, const uint32_t *genome, const uint32_t *goff, const int32_t *glen,
+                        const uint32_t *out, uint32_t n_tasks, uint32_t *slot) {
+  if (n_tasks == 0) return SHRIMP_OK;
+  window_slots_kernel<<<(n_tasks + 255) / 256, 256, 0, ctx->stream>>>(genome, goff, glen, out, n_tasks, slot);
+  SH_CUDA(cudaGetLastError());
+  SH_LAUNCHED(ctx, ST_PASS1);
+  return SHRIMP_OK;
+}
+
 int launch_pass1_replay(shrimp_gpu_ctx *ctx, const Pass1Params &P) {
   pass1_replay_kernel<<<(P.n_reads + 127) / 128, 128, 0, ctx->stream>>>(P);
   SH_CUDA(cudaGetLastError());
@@ -285,3 +347,39 @@ int launch_select_unpaired(shrimp_gpu_ctx *ctx, const Pass1Params &P) {
 }
 
 }  // namespace shrimp
+
+// Diagnostic: hash_genome_window (util.h:220-241) of n windows of a packed genome (8 codes per word) as the device
+// computes it for the f1 window cache, for the test that compares it with the reference's.
+extern "C" int shrimp_gpu_hash_windows(shrimp_gpu_ctx *ctx, const uint32_t *genome_words, uint64_t n_words,
+                                       const uint32_t *goff, const int32_t *glen, int n, uint32_t *hash_out) {
+  using namespace shrimp;
+  if (!ctx || !genome_words || !goff || !glen || !hash_out || n < 0) {
+    set_error("shrimp_gpu_hash_windows: invalid argument");
+    return SHRIMP_E_ARG;
+  }
+  if (n == 0) return SHRIMP_OK;
+  for (int t = 0; t < n; t++)
+    if (glen[t] < 0 || (uint64_t)goff[t] + (uint64_t)glen[t] > n_words * 8) {
+      set_error("shrimp_gpu_hash_windows: window %d outside the genome", t);
+      return SHRIMP_E_RANGE;
+    }
+  DevBuf dg, do_, dl, dh;
+  int rc = SHRIMP_OK;
+  if ((rc = dg.ensure(n_words * 4)) == SHRIMP_OK && (rc = do_.ensure((size_t)n * 4)) == SHRIMP_OK &&
+      (rc = dl.ensure((size_t)n * 4)) == SHRIMP_OK && (rc = dh.ensure((size_t)n * 4)) == SHRIMP_OK) {
+    cudaMemcpyAsync(dg.p, genome_words, n_words * 4, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(do_.p, goff, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(dl.p, glen, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream);
+    window_hash_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(dg.as<uint32_t>(), do_.as<uint32_t>(), dl.as<int32_t>(),
+                                                                  (uint32_t)n, dh.as<uint32_t>());
+    ctx->launches++;
+    cudaMemcpyAsync(hash_out, dh.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    const cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+      set_error("shrimp_gpu_hash_windows: %s", cudaGetErrorString(e));
+      rc = SHRIMP_E_CUDA;
+    }
+  }
+  dg.release(); do_.release(); dl.release(); dh.release();
+  return rc;
+}

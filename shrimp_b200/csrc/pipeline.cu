@@ -25,6 +25,8 @@ int launch_post_sw(shrimp_gpu_ctx *ctx, const PostParams &P, DevBuf &scratch);
 
 int launch_scan(shrimp_gpu_ctx *ctx, ScanParams &P, int warps_per_cta, int n_ctas);
 int launch_build_vec_tasks(shrimp_gpu_ctx *ctx, const TaskBuildParams &P);
+int launch_window_slots(shrimp_gpu_ctx *ctx, const uint32_t *genome, const uint32_t *goff, const int32_t *glen,
+                        const uint32_t *out, uint32_t n_tasks, uint32_t *slot);
 int launch_sw_gapless(shrimp_gpu_ctx *ctx, const GaplessParams &P);
 int launch_pass1_replay(shrimp_gpu_ctx *ctx, const Pass1Params &P);
 int launch_select_unpaired(shrimp_gpu_ctx *ctx, const Pass1Params &P);
@@ -116,7 +118,9 @@ __global__ void classify_full_tasks_kernel(const FullTask *tasks, int n, int anc
   const int bucket = c < RING_CLASSES ? min(15, (bw * 16 - 1) / W) : 0;
   const uint32_t k = (uint32_t)(c * 32 + ((T.gen_st && Tflag) ? 16 : 0) + bucket);
   key[t] = k;
-  atomicAdd(&key_count[k], 1u);
+  // one atomic per warp and key: the counters are few and every task hits one of them
+  const uint32_t peers = __match_any_sync(__activemask(), k);
+  if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&key_count[k], (uint32_t)__popc(peers));
 }
 // exclusive prefix of the key counts -> first slot of every key in perm (one thread: FULL_KEYS values)
 __global__ void full_key_offsets_kernel(const uint32_t *key_count, uint32_t *key_off) {
@@ -129,7 +133,13 @@ __global__ void full_key_offsets_kernel(const uint32_t *key_count, uint32_t *key
 __global__ void group_full_tasks_kernel(const uint32_t *key, int n, uint32_t *key_off, int32_t *perm) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
-  perm[atomicAdd(&key_off[key[t]], 1u)] = t;
+  const uint32_t k = key[t];
+  const uint32_t peers = __match_any_sync(__activemask(), k);
+  const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+  uint32_t base = 0;
+  if (lane == leader) base = atomicAdd(&key_off[k], (uint32_t)__popc(peers));
+  base = __shfl_sync(peers, base, leader);
+  perm[base + (uint32_t)__popc(peers & ((1u << lane) - 1u))] = t;
 }
 
 void free_pipeline(shrimp_gpu_ctx *ctx) {
@@ -879,7 +889,12 @@ int chunk_vector(Chunk &C) {
     TB.task_stats = C.cnt + 20;
     SH_TRY(launch_build_vec_tasks(ctx, TB));
     SH_CUDA(cudaMemcpyAsync(n_dense, C.cnt + 24, 8, cudaMemcpyDeviceToHost, st));
+    if (TB.slot) SH_CUDA(cudaMemsetAsync(TB.slot, 0xff, (size_t)HU * 4, st));   // hits without a task: no cache slot
     SH_CUDA(cudaStreamSynchronize(st));
+    if (TB.slot)
+      for (int o = 0; o < C.n_ori; o++)
+        SH_TRY(launch_window_slots(ctx, cs ? (o ? C.G.cs_rc : C.G.cs) : C.G.ls, VT[o].goff, (const int32_t *)VT[o].glen,
+                                   VT[o].out, (uint32_t)n_dense[o], TB.slot));
   }
   {
     ScopedStage ss(ctx, ST_VECTOR);
