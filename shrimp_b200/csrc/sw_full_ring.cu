@@ -542,11 +542,11 @@ __global__ void __launch_bounds__(BLOCK) sw_full_cs_ring_kernel(const FullParams
 // every one of its ~200 instructions per cell exposed to ALU latency.  Here lane k of a quad owns layer k:
 // 3 ring rows per lane (4x the resident warps for the same shared memory), a third of the arithmetic per
 // lane, and the cross-layer candidates (northwest and north moves may cross over) exchanged inside the quad
-// with shuffles of (value << 4 | layer priority | direction).  The "minus infinity" of the global-mode edge cells is -2^26
+// with shuffles of (value << 7 | layer priority | back-pointer code).  The "minus infinity" of the global-mode edge cells is -2^22
 // here instead of -INT_MAX/2 so that the packed form fits 32 bits: every value derived from it carries
 // exactly one such term, so all comparisons -- and with them every back-pointer -- come out as in the
 // reference, and such cells can never hold the winning score.
-#define NEG_Q (-(1 << 26))
+#define NEG_Q (-(1 << 22))
 #define QUAD_THREADS 128
 
 __device__ __forceinline__ int warp_max_i(int v) {
@@ -576,6 +576,7 @@ __device__ int quad_cs_dp(const FullParams &P, const FullTask &T, bool run, int 
   const int16_t *xrow = P.xover_pos ? P.xover_pos + (size_t)(T.ridx >> 1) * (size_t)P.xover_stride : nullptr;
   int add_prev = k == 0 ? 0 : P.xover;   // what row -1 was initialised with: the global penalty (:268-270)
   const int match = P.match, mismatch = P.mismatch;
+  const int kprio = (3 - k) << 5;   // tie order of the cross-layer maximum: lowest layer first
   const int nrows_w = warp_max_i(lenb);
   for (int i = 0; i < nrows_w; i++) {
     const bool row_on = i < lenb;
@@ -632,51 +633,49 @@ __device__ int quad_cs_dp(const FullParams &P, const FullTask &T, bool run, int 
       gpos++;
       int ms = (dbj == qk) ? match : mismatch;
       if (dbj == 15 || qk == 15) ms = 0;
-      // own layer: first-max of the diagonal sources (direction - 5) and of the north sources (direction - 1)
+      // own layer: first-max of the diagonal sources and of the north sources; md / nd hold the back-pointer code
+      // of the choice (direction << 2 | own layer, CSC)
       int mv, md, nv, nd;
       if (!revcmpl) {
-        mv = d_nw; md = D_NW_NW - 5;
-        if (nt && d_n > mv) { mv = d_n; md = D_NW_N - 5; }
-        if (d_w > mv) { mv = d_w; md = D_NW_W - 5; }
+        mv = d_nw; md = CSC(k, D_NW_NW);
+        if (nt && d_n > mv) { mv = d_n; md = CSC(k, D_NW_N); }
+        if (d_w > mv) { mv = d_w; md = CSC(k, D_NW_W); }
       } else {
-        mv = d_w; md = D_NW_W - 5;
-        if (nt && d_n > mv) { mv = d_n; md = D_NW_N - 5; }
-        if (d_nw > mv) { mv = d_nw; md = D_NW_NW - 5; }
+        mv = d_w; md = CSC(k, D_NW_W);
+        if (nt && d_n > mv) { mv = d_n; md = CSC(k, D_NW_N); }
+        if (d_nw > mv) { mv = d_nw; md = CSC(k, D_NW_NW); }
       }
       {
         const int A = u_nw - bo - be, B = u_n - be;
         if (!revcmpl) {
           if (nt) {
-            nv = A; nd = D_N_NW - 1;
-            if (B > nv) { nv = B; nd = D_N_N - 1; }
+            nv = A; nd = CSC(k, D_N_NW);
+            if (B > nv) { nv = B; nd = CSC(k, D_N_N); }
           } else {
-            nv = B; nd = D_N_N - 1;
+            nv = B; nd = CSC(k, D_N_N);
           }
         } else {
-          nv = B; nd = D_N_N - 1;
-          if (nt && A > nv) { nv = A; nd = D_N_NW - 1; }
+          nv = B; nd = CSC(k, D_N_N);
+          if (nt && A > nv) { nv = A; nd = CSC(k, D_N_NW); }
         }
       }
       // best other layer: the reference tries layers in ascending order and replaces on strict > (sw-full-cs.c:
       // 375-437, :460-501), i.e. maximum value, ties to the lowest layer -- a plain integer max over the keys
-      // (value << 4 | (3 - layer) << 2 | direction) of the three other lanes
-      const int pm = (mv << 4) | ((3 - k) << 2) | md, pn = (nv << 4) | ((3 - k) << 2) | nd;
-      int km = __shfl_sync(0xffffffffu, pm, qbase + ((k + 1) & 3));
-      int kn = __shfl_sync(0xffffffffu, pn, qbase + ((k + 1) & 3));
-      km = max(km, __shfl_sync(0xffffffffu, pm, qbase + ((k + 2) & 3)));
-      kn = max(kn, __shfl_sync(0xffffffffu, pn, qbase + ((k + 2) & 3)));
-      km = max(km, __shfl_sync(0xffffffffu, pm, qbase + ((k + 3) & 3)));
-      kn = max(kn, __shfl_sync(0xffffffffu, pn, qbase + ((k + 3) & 3)));
-      const int ov = km >> 4, ow = kn >> 4;
-      const int oc = (((km & 3) + 5) << 2) | (3 - ((km >> 2) & 3));
-      const int oe = (((kn & 3) + 1) << 2) | (3 - ((kn >> 2) & 3));
+      // (value << 7 | (3 - layer) << 5 | back-pointer code) of the three other lanes: the partner lane's key and
+      // the maximum of the other pair, two xor-shuffles per key
+      const int pm = (mv << 7) | kprio | md, pn = (nv << 7) | kprio | nd;
+      const int xm = __shfl_xor_sync(0xffffffffu, pm, 1), xn = __shfl_xor_sync(0xffffffffu, pn, 1);
+      const int ym = __shfl_xor_sync(0xffffffffu, max(pm, xm), 2), yn = __shfl_xor_sync(0xffffffffu, max(pn, xn), 2);
+      const int km = max(xm, ym), kn = max(xn, yn);
+      const int ov = km >> 7, ow = kn >> 7;
+      const int oc = km & 31, oe = kn & 31;
       int tmp, v_n, v_w, v_nw;
       uint32_t t2, bits;
-      tmp = mv + ms; t2 = CSC(k, md + 5);
+      tmp = mv + ms; t2 = (uint32_t)md;
       if (ov + ms + xp > tmp) { tmp = ov + ms + xp; t2 = (uint32_t)oc; }
       if (LOCAL && tmp <= resetval) { tmp = resetval; t2 = 0; }
       v_nw = tmp; bits = t2 << 10;
-      tmp = nv; t2 = CSC(k, nd + 1);
+      tmp = nv; t2 = (uint32_t)nd;
       if (ow + xp > tmp) { tmp = ow + xp; t2 = (uint32_t)oe; }
       if (LOCAL && tmp <= resetval) { tmp = resetval; t2 = 0; }
       v_n = tmp; bits |= t2;
