@@ -28,7 +28,13 @@ namespace shrimp {
 
 __device__ __forceinline__ double half_min(double v) {
 #pragma unroll
-  for (int o = 8; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o, 16));
+  for (int o = 8; o > 0; o >>= 1) {
+    // the values are never NaN: a compare-and-select (the reference's own `<` scan, sw-post.c:343-347) instead of
+    // fmin's NaN handling.  Which zero a tie of +0 and -0 yields does not matter: the scale is only subtracted and
+    // summed, and x - (+-0) = x, exp(+-0) = 1
+    const double w = __shfl_xor_sync(0xffffffffu, v, o, 16);
+    v = w < v ? w : v;
+  }
   return v;
 }
 __device__ __forceinline__ int warp_max_int(int v) {
