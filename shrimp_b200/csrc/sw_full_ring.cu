@@ -563,7 +563,8 @@ __device__ int quad_cs_dp(const FullParams &P, const FullTask &T, bool run, int 
                           const uint32_t *genome, const uint32_t *read, const Rect &rect, int &ret_i, int &ret_j,
                           int end_sc[3], unsigned long long &cells) {
   const int W = P.W;
-  const int sstride = W * QUAD_THREADS;  // ints between the ring rows of two states
+  // ring layout [band offset][state][thread]: the three states of a cell sit at compile-time offsets of one pointer
+  constexpr int sstride = QUAD_THREADS, slotstride = 3 * QUAD_THREADS;
   const int lena = T.glen, lenb = run ? T.rlen : 0;
   const size_t bstride = (size_t)P.NT * 4;  // u16 elements between two band offsets
   const int ao = P.a_open, ae = P.a_ext, bo = P.b_open, be = P.b_ext;
@@ -607,7 +608,7 @@ __device__ int quad_cs_dp(const FullParams &P, const FullTask &T, bool run, int 
     int d_n = r_n, d_w = r_w, d_nw = r_nw;
     const int delta = x_min - pxmin;
     if (row_on && i > 0 && x_min - 1 <= pxmax) {
-      const int32_t *p = sm + delta * QUAD_THREADS;
+      const int32_t *p = sm + delta * slotstride;
       d_n = p[0]; d_w = p[sstride]; d_nw = p[2 * sstride];
     }
     unsigned short *bp = bp_task + (size_t)i * W * bstride;
@@ -617,13 +618,13 @@ __device__ int quad_cs_dp(const FullParams &P, const FullTask &T, bool run, int 
     }
     int l_w = ini_w, l_nw = ini_nw;
     int32_t *cur = sm;                                 // ring slot of offset s
-    const int32_t *prev = sm + delta * QUAD_THREADS;   // ring slot of the previous row's cell in the same column
+    const int32_t *prev = sm + delta * slotstride;   // ring slot of the previous row's cell in the same column
     uint32_t gpos = T.goff_global + (uint32_t)x_min;
     uint32_t gword = genome[gpos >> 3];
     for (int s = 1; s <= wmax; s++) {
       const bool on = s <= width;
-      cur += QUAD_THREADS;
-      prev += QUAD_THREADS;
+      cur += slotstride;
+      prev += slotstride;
       bp += bstride;
       const int j = x_min + s - 1;
       int u_n = r_n, u_w = r_w, u_nw = r_nw;
