@@ -39,7 +39,7 @@ __device__ int ring_ls_dp(const FullParams &P, const FullTask &T, int slot, int3
                           const uint32_t *read, const Rect &rect, int &ret_i, int &ret_j, int &end_n, int &end_w,
                           int &end_nw, unsigned long long &cells) {
   const int W = P.W;
-#define SMR(st, s) sm[((st) * W + (s)) * BLOCK]
+#define SMR(st, s) sm[((s) * 3 + (st)) * BLOCK]   // [band offset][state][thread]: one pointer, constant state offsets
   const int lena = T.glen, lenb = T.rlen;
   const size_t NT = (size_t)P.NT;
   const int ao = P.a_open, ae = P.a_ext, bo = P.b_open, be = P.b_ext;
@@ -63,13 +63,17 @@ __device__ int ring_ls_dp(const FullParams &P, const FullTask &T, int slot, int3
     bp[((size_t)i * W) * NT] = 0;
     int l_nw = init_nw, l_w = init_w;
     const int delta = x_min - pxmin;
+    uint32_t gpos = T.goff_global + (uint32_t)x_min;
+    uint32_t gword = genome[gpos >> 3];
     for (int j = x_min; j <= x_max; j++) {
       const int s = j - x_min + 1;
       int u_nw, u_n, u_w;  // cell (i-1, j)
       if (i == 0) { u_nw = 0; u_n = -bo; u_w = -ao; }
       else if (j > pxmax) { u_nw = init_nw; u_n = init_n; u_w = init_w; }
       else { const int sp = s + delta; u_nw = SMR(0, sp); u_n = SMR(1, sp); u_w = SMR(2, sp); }
-      const uint32_t d = extract4(genome, (uint64_t)T.goff_global + (uint64_t)j);
+      if ((gpos & 7u) == 0u) gword = genome[gpos >> 3];
+      const uint32_t d = (gword >> (4u * (gpos & 7u))) & 15u;
+      gpos++;
       const int ms = (d == q) ? P.match : P.mismatch;
       int tmp, v_nw, v_n, v_w;
       uint32_t b_nw, b_n, b_w;
