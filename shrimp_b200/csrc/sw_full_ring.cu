@@ -601,6 +601,7 @@ __device__ int quad_cs_dp(const FullParams &P, const FullTask &T, bool run, int 
       }
       if (k == 0) cells += (unsigned long long)width;
     }
+    const int m_eq = qk == 15 ? 0 : match, m_ne = qk == 15 ? 0 : mismatch;
     const int xp = (xrow && row_on) ? (int)xrow[i] : P.xover;
     const int add = k == 0 ? 0 : xp;
     const int ini_n = LOCAL ? -bo + add : NEG_Q, ini_w = LOCAL ? -ao + add : NEG_Q, ini_nw = LOCAL ? add : NEG_Q;
@@ -625,6 +626,7 @@ __device__ int quad_cs_dp(const FullParams &P, const FullTask &T, bool run, int 
     const int32_t *prev = sm + delta * slotstride;   // ring slot of the previous row's cell in the same column
     uint32_t gpos = T.goff_global + (uint32_t)x_min;
     uint32_t gword = genome[gpos >> 3];
+#pragma unroll 2
     for (int s = 1; s <= wmax; s++) {
       const bool on = s <= width;
       cur += slotstride;
@@ -636,8 +638,7 @@ __device__ int quad_cs_dp(const FullParams &P, const FullTask &T, bool run, int 
       if (on && (gpos & 7u) == 0u) gword = genome[gpos >> 3];
       const int dbj = (int)((gword >> (4u * (gpos & 7u))) & 15u);
       gpos++;
-      int ms = (dbj == qk) ? match : mismatch;
-      if (dbj == 15 || qk == 15) ms = 0;
+      const int ms = dbj == qk ? m_eq : (dbj == 15 ? 0 : m_ne);   // N on either side scores 0
       // own layer: first-max of the diagonal sources and of the north sources; md / nd hold the back-pointer code
       // of the choice (direction << 2 | own layer, CSC)
       int mv, md, nv, nd;
