@@ -7,9 +7,10 @@
 // The model is a 16-node chain (node = letter pair, left/right) over the aligned read columns.  One HALF-WARP per
 // alignment, lane = node: the forward and backward recurrences take their four predecessor / successor values by
 // width-16 shuffles, sums run in the reference's index order, the scale (minimum over the nodes) is a half-warp
-// reduction; forwards[][] of all columns wait for the posterior pass in a global scratch row per resident half-warp
-// (written and read back by the same lane, 128 contiguous bytes per column: it lives in L2), so that shared memory
-// holds only the columns and the scales and the register file bounds the occupancy.  The kernel is persistent: a
+// reduction.  The forward and the backward recurrence advance in the same loop (two independent chains, one shared
+// logarithm per lane); forwards[][] and backwards[][] of all columns wait for the posterior pass in a global scratch
+// row per resident half-warp (written and read back by the same lane, 128 contiguous bytes per column: it lives in
+// L2), so that shared memory holds only the columns and the scales and the register file bounds the occupancy.  The kernel is persistent: a
 // CTA takes groups of alignments grid-stride.  The two alignments of a warp run in lockstep (trip counts = the
 // longer one).  Every double is the reference's, bit for bit: the -log() emission
 // terms come from the host (libm) as constants / a 256-entry table over the quality characters, and exp() / log()
@@ -22,7 +23,7 @@
 
 namespace shrimp {
 
-#define PS_CTAS_PER_SM 8
+#define PS_CTAS_PER_SM 7
 #define PS_LEFT(i) (((i) >> 2) & 3)
 #define PS_RIGHT(i) ((i) & 3)
 
@@ -64,8 +65,8 @@ struct PsCol {   // one aligned read column (struct column, sw-post.c:61-78, wit
 };
 
 __host__ __device__ inline size_t ps_smem_doubles_per_half(int max_cols) {
-  // forwscale[max_cols], columns[max_cols], the segmented XOR scan of the read (one byte per position)
-  return (size_t)max_cols + ((size_t)max_cols * sizeof(PsCol) + 7) / 8 + ((size_t)max_cols + 7) / 8;
+  // forwscale[max_cols], backscale[max_cols], columns[max_cols], the segmented XOR scan of the read (one byte per position)
+  return 2 * (size_t)max_cols + ((size_t)max_cols * sizeof(PsCol) + 7) / 8 + ((size_t)max_cols + 7) / 8;
 }
 
 __global__ void __launch_bounds__(128, PS_CTAS_PER_SM) post_sw_kernel(const PostParams P, int halves_per_cta, int max_cols,
@@ -74,10 +75,12 @@ __global__ void __launch_bounds__(128, PS_CTAS_PER_SM) post_sw_kernel(const Post
   const int lane = threadIdx.x & 31, hl = lane & 15;
   const int hidx = threadIdx.x >> 4;   // half-warp of the CTA
   double *fscale = ps_smem + (size_t)hidx * ps_smem_doubles_per_half(max_cols);
-  PsCol *cols = (PsCol *)(fscale + max_cols);
+  double *bsc = fscale + max_cols;
+  PsCol *cols = (PsCol *)(bsc + max_cols);
   uint8_t *pxs = (uint8_t *)(cols + max_cols);   // per read position
-  // forwards[max_cols][16] of this half-warp
-  double *fw = fw_scratch + ((size_t)blockIdx.x * halves_per_cta + hidx) * (size_t)max_cols * 16;
+  // forwards[max_cols][16] and backwards[max_cols][16] of this half-warp
+  double *fw = fw_scratch + ((size_t)blockIdx.x * halves_per_cta + hidx) * (size_t)max_cols * 32;
+  double *bw = fw + (size_t)max_cols * 16;
   const glibc_math::Tables GT = {P.gm_tab, P.gm_tab + 8, P.gm_tab + 8 + 256, P.gm_tab + 8 + 256 + 18};
   for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
   int slot = grp * halves_per_cta + hidx;
@@ -207,35 +210,61 @@ __global__ void __launch_bounds__(128, PS_CTAS_PER_SM) post_sw_kernel(const Post
     val = val - (same ? l1 : l2);
     return val;
   };
-  // ---- do_forwards (sw-post.c:318-361) -----------------------------------------------------------------------
-  double f = 0, run_scale = 0;
-  for (int i = 0; i < wlen; i++) {
-    const bool on = i < len;
-    PsCol pc;
-    if (on) pc = cols[i];
-    else { pc.let = -2; pc.col = 0; pc.kind = 0; pc.q = 0; pc.call = 15; pc.maxp = 0; pc.qual = 33; pc.pad = 0; }
-    double nf;
-    if (i == 0) {
+  // ---- do_forwards (sw-post.c:318-361) and do_backwards (:270-316) in ONE loop --------------------------------
+  // Iteration t advances the forward recurrence to column t and the backward recurrence to column len - 1 - t: two
+  // independent dependency chains per warp, and -- since the logarithm of a forward sum depends on the node's left
+  // letter only and that of a backward sum on its right letter only (four distinct values each) -- ONE logarithm
+  // per lane serves both: lanes 0-7 of the half-warp take the forward sums, lanes 8-15 the backward sums, and every
+  // node fetches its two results by shuffle.  exp(-forwards[i-1][k]) and exp(-(nodePrior(i+1, k) + backwards[i+1][k]))
+  // depend on k only: one exponential each per lane, the sums pick their four terms by shuffle in the reference's
+  // order of k.  All shuffles are full-mask and unconditional: both halves of the warp execute them whatever their
+  // own state.
+  double f = 0, run_scale = 0, b = 0, bscale = 0;
+  const bool fwd_lane = hl < 8;
+  const int q4 = hl & 3;
+  PsCol blank;
+  blank.let = -2; blank.col = 0; blank.kind = 0; blank.q = 0; blank.call = 15; blank.maxp = 0; blank.qual = 33; blank.pad = 0;
+  for (int t = 0; t < wlen; t++) {
+    const bool on = t < len;
+    const int c = len - 1 - t;   // backward column
+    const PsCol pc = on ? cols[t] : blank;
+    double nf, nb;
+    if (t == 0) {
       nf = PS_LEFT(hl) == init_bp ? node_prior(pc, hl) : HUGE_VAL;
+      nb = 0.0;   // last column: backwards = 0, backscale = 0
     } else {
-      // exp(-forwards[i-1][k]) depends on k only: every lane takes the exponential of its own node once and the
-      // sums pick their four terms by shuffle, in the reference's order of k
+      const PsCol nxt = on ? cols[c + 1] : blank;
       const double val = node_prior(pc, hl);
       const double ef = PS_EXP(-1 * (f));
+      const double eb = PS_EXP(-1 * (node_prior(nxt, hl) + b));
       double s = 0;
 #pragma unroll
-      for (int m = 0; m < 4; m++) s += __shfl_sync(0xffffffffu, ef, 4 * m + PS_LEFT(hl), 16);
-      nf = val - PS_LOG(s);
+      for (int m = 0; m < 4; m++) {
+        const int src = fwd_lane ? 4 * m + q4 : 4 * q4 + m;
+        const double xf = __shfl_sync(0xffffffffu, ef, src, 16), xb = __shfl_sync(0xffffffffu, eb, src, 16);
+        s += fwd_lane ? xf : xb;
+      }
+      const double lg = PS_LOG(s);
+      const double lf = __shfl_sync(0xffffffffu, lg, PS_LEFT(hl), 16), lb = __shfl_sync(0xffffffffu, lg, 8 + PS_RIGHT(hl), 16);
+      nf = val - lf;
+      nb = on ? -lb : 0.0;
     }
-    // forwscale: minimum over the nodes (column 0: over the nodes that start from the initial base; the others are
-    // +infinity and never the minimum)
-    const double sc = half_min(nf);
-    nf -= sc;
+    // forwscale / backscale: minimum over the nodes (column 0: over the nodes that start from the initial base; the
+    // others are +infinity and never the minimum)
+    const double scf = half_min(nf), scb = half_min(nb);
+    nf -= scf;
+    nb -= scb;
     if (on) {
       f = nf;
-      run_scale = i == 0 ? sc : sc + run_scale;
-      fw[(size_t)i * 16 + hl] = f;
-      if (hl == 0) fscale[i] = run_scale;
+      run_scale = t == 0 ? scf : scf + run_scale;
+      fw[(size_t)t * 16 + hl] = f;
+      b = nb;
+      bscale = t == 0 ? scb : scb + bscale;
+      bw[(size_t)c * 16 + hl] = b;
+      if (hl == 0) {
+        fscale[t] = run_scale;
+        bsc[c] = bscale;
+      }
     }
   }
   double total_score = 0;
@@ -247,36 +276,14 @@ __global__ void __launch_bounds__(128, PS_CTAS_PER_SM) post_sw_kernel(const Post
     total_score = -PS_LOG(val) + run_scale;
   }
   __syncwarp();
-  // ---- do_backwards (sw-post.c:270-316) fused with post_traceback (:182-207) and get_base_qualities (:584-601) ----
-  double b = 0, bscale = 0;
-  for (int step = 0; step < wlen; step++) {
-    // this half is at column i = len - 1 - (step - (wlen - len)): the shorter alignment of the warp starts later
-    const int i = len - 1 - (step - (wlen - len));
-    const bool on = step >= wlen - len && len > 0;
-    PsCol pc, nxt;
-    pc.let = -2; pc.col = 0; pc.kind = 0; pc.q = 0; pc.call = 15; pc.maxp = 0; pc.qual = 33; pc.pad = 0;
-    nxt = pc;
-    if (on) {
-      pc = cols[i];
-      if (i + 1 < len) nxt = cols[i + 1];
-    }
-    // the shuffles are full-mask: both halves of the warp execute them whatever their own state
-    // exp(-(nodePrior(i+1, k) + backwards[i+1][k])) depends on k only: one exponential per lane, four shuffles per sum
-    const double eb = PS_EXP(-1 * (node_prior(nxt, hl) + b));
-    double s = 0;
-#pragma unroll
-    for (int m = 0; m < 4; m++) s += __shfl_sync(0xffffffffu, eb, 4 * PS_RIGHT(hl) + m, 16);
-    const double nb0 = (!on || i == len - 1) ? 0.0 : -PS_LOG(s);   // last column: backwards = 0, backscale = 0
-    double nb = nb0;
-    const double sc = half_min(nb);
-    nb -= sc;
-    if (on) {
-      bscale = (i == len - 1) ? sc : sc + bscale;
-      b = nb;
-    }
-    // posterior of the four letters at this column
-    const double fwv = on ? fw[(size_t)i * 16 + hl] : 0.0, fs = on ? fscale[i] : 0.0;
-    const double e = PS_EXP(-1 * (fwv + b + fs + bscale - total_score));
+  // ---- posteriors of the four letters per column, post_traceback (:182-207), get_base_qualities (:584-601) -------
+  // no dependency between the columns: the loads of the next ones overlap the exponential of this one
+  for (int i = 0; i < wlen; i++) {
+    const bool on = i < len;
+    const double fwv = on ? fw[(size_t)i * 16 + hl] : 0.0, bwv = on ? bw[(size_t)i * 16 + hl] : 0.0;
+    const double fs = on ? fscale[i] : 0.0, bs = on ? bsc[i] : 0.0;
+    const int bc = on ? (int)cols[i].call : 15;
+    const double e = PS_EXP(-1 * (fwv + bwv + fs + bs - total_score));
     double p = 0;
 #pragma unroll
     for (int m = 0; m < 4; m++) p += __shfl_sync(0xffffffffu, e, 4 * m + (hl & 3), 16);
@@ -289,8 +296,8 @@ __global__ void __launch_bounds__(128, PS_CTAS_PER_SM) post_sw_kernel(const Post
       if (p2 > pm) { maxval = 2; pm = p2; }
       if (p3 > pm) { maxval = 3; pm = p3; }
       // the base quality needs a log(): park 1 - posterior[base call] in the column's forwscale slot (dead from
-      // here on) and take the logarithms of all columns together afterwards, a lane per column
-      const int bc = pc.call;
+      // here on: the shuffles above come after every lane's read) and take the logarithms of all columns together
+      // afterwards, a lane per column
       fscale[i] = bc != 15 ? 1 - (bc == 0 ? p0 : bc == 1 ? p1 : bc == 2 ? p2 : p3) : 2.0;
       cols[i].maxp = (int8_t)maxval;
     }
@@ -404,7 +411,7 @@ int launch_post_sw(shrimp_gpu_ctx *ctx, const PostParams &P, DevBuf &scratch) {
   if (per_sm < 1) per_sm = 1;
   const int n_groups = (P.n_tasks + halves - 1) / halves;
   const int grid = std::min(n_groups, ctx->sm_count * per_sm);
-  SH_TRY(scratch.ensure((size_t)grid * halves * (size_t)max_cols * 16 * sizeof(double)));
+  SH_TRY(scratch.ensure((size_t)grid * halves * (size_t)max_cols * 32 * sizeof(double)));
   kern<<<grid, halves * 16, smem, ctx->stream>>>(P, halves, max_cols, n_groups, scratch.as<double>());
   SH_CUDA(cudaGetLastError());
   SH_LAUNCHED(ctx, ST_POST);
