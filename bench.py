@@ -578,7 +578,7 @@ def main():
         roofs["seed_scan"]["traffic"] = 28.27e9
         roofs["seed_scan"]["traffic_source"] = "profiles/r01e_ncu_full_c2_top_raw.csv"
         if "post_sw" in roofs:
-            roofs["post_sw"]["traffic"] = 745.4e6
+            roofs["post_sw"]["traffic"] = 4.08e9
             roofs["post_sw"]["traffic_source"] = "profiles/r01f_ncu_full_post_sw_raw.csv"
     roofline = dict(roofs.get(dominant, roofs["seed_scan"]))
     roofline["dominant_stage"] = dominant
