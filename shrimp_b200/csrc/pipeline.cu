@@ -512,8 +512,10 @@ int chunk_scan(Chunk &C) {
     cap = 256;
     // + the read's own locus: every k-mer may hit it
     const double want = 2.0 * (s_true + s_false) + 1.5 * K_max + 32;
+    // in steps of 64: the slab decides how many warps an SM holds.  (The bitonic sort pads to the next power of two
+    // of the survivors, possibly past `cap`: the bytes behind ent are the bitmaps, dead by then, scan_layout.)
     cap = 128;
-    while (cap < 2048 && cap < want) cap <<= 1;
+    while (cap < 2048 && cap < want) cap += 64;
     small_useful = est * 8 <= (double)(1 << bm_log2) && want <= 2048;
   } else {
     bm_log2 = 5;
