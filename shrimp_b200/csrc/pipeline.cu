@@ -628,7 +628,7 @@ int chunk_scan(Chunk &C) {
       int stash = 0;
       if (filt) {
         stash = 128;
-        while (stash < 2048 && stash < 1.2 * est + K_max) stash <<= 1;
+        while (stash < 2048 && stash < 1.2 * est + K_max) stash += 32;
       }
       if (const char *e = getenv("SHRIMP_SCAN_STASH")) stash = std::max(0, std::min(4096, atoi(e)));
       P.stash = stash;

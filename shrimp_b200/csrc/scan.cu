@@ -545,16 +545,19 @@ __host__ __device__ inline ScanSmem scan_layout(int cap, int max_rl, int k_cap, 
   L.kpre = take(((size_t)k_cap + 1) * 4);
   L.cache = take((size_t)max_rl * 4);
   L.keep = take(((size_t)cap / 32 + 2) * 4);   // + the candidate counter of the warp kernel
-  L.order = take((size_t)cap * 2);      // pop order of the tie replay
-  L.stash = take((size_t)stash * 4);    // the strand's list entries, staged once (warp kernel, short lists)
-  L.sslot = take((size_t)stash * 2);
+  // Lifetimes: stash / sslot (the strand's list entries, staged once: warp kernel, short lists) and the bitmaps die
+  // with pass B; the replay heap dies with the tie replay, which leaves `order`; the anchors (16 B per candidate)
+  // are born after that from ent + order.  So `order` lives in the stash, and the anchors overlay sslot, the
+  // bitmaps and the heap.  The sort pads ent to a power of two, possibly past `cap`: into sslot, dead by then.
+  L.stash = take((size_t)stash * 4 > (size_t)cap * 2 ? (size_t)stash * 4 : (size_t)cap * 2);
+  L.order = L.stash;                    // pop order of the tie replay
   L.ent = take((size_t)cap * 8);
-  // the anchors (16 B per candidate) are born after the bitmaps and the replay heap have died: same bytes
+  L.sslot = take((size_t)stash * 2);
   L.bm1 = take(((size_t)1 << bm_log2) / 8);
   L.bm2 = take(((size_t)1 << bm_log2) / 8);
   L.heap = take((size_t)k_cap * 8);
-  L.rec = L.bm1;
-  if (o - L.bm1 < (size_t)cap * 16) o = L.bm1 + (size_t)cap * 16;
+  L.rec = L.sslot;
+  if (o - L.rec < (size_t)cap * 16) o = L.rec + (size_t)cap * 16;
   L.total = (o + 15) & ~(size_t)15;
   return L;
 }
