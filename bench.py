@@ -573,10 +573,10 @@ def main():
                             "columns_per_s": st["post_sw_columns"] / (post_ms * 1e-3), "ms_per_step": post_ms,
                             "peak_source": "nominal: 148 SMs x 64 FP64 lanes x the SM clock sampled during the run"}
     # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture per launch; only for the
-    # configuration the capture was taken on (profiles/r01e_ncu_full_c2_top_raw.csv, r01f_ncu_full_post_sw_raw.csv: C2, 1 M reads per launch)
+    # configuration the capture was taken on (profiles/r01h_ncu_full_scan_kernel_raw.csv, r01f_ncu_full_post_sw_raw.csv: C2, 1 M reads per launch)
     if w.key in ("c2", "c2nomq") and n_reads == 1_000_000:
-        roofs["seed_scan"]["traffic"] = 28.27e9
-        roofs["seed_scan"]["traffic_source"] = "profiles/r01e_ncu_full_c2_top_raw.csv"
+        roofs["seed_scan"]["traffic"] = 28.42e9
+        roofs["seed_scan"]["traffic_source"] = "profiles/r01h_ncu_full_scan_kernel_raw.csv"
         if "post_sw" in roofs:
             roofs["post_sw"]["traffic"] = 4.08e9
             roofs["post_sw"]["traffic_source"] = "profiles/r01f_ncu_full_post_sw_raw.csv"
