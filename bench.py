@@ -325,7 +325,7 @@ def build_context(w: Workload, device: int):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
@@ -333,7 +333,8 @@ def main():
     ap.add_argument("--genome-mb", type=int, default=0, help="scale the synthetic genome (c3: default 300, 3000 = hg18 size)")
     ap.add_argument("--cpu-sample", type=int, default=200_000, help="reads in the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-threads", type=int, default=3, help="host threads (one context each) of the end-to-end leg")
+    ap.add_argument("--e2e-threads", type=int, default=0,
+                    help="host threads (one context each) of the end-to-end leg; 0 = 4 on one GPU, 3 per GPU on several")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -471,7 +472,7 @@ def main():
     # overlaps the device half of the other thread's step.  Every step still uploads its reads and
     # downloads its records; K steps in total.
     import shrimp_b200
-    n_host = max(1, min(a.e2e_threads, a.steps))
+    n_host = max(1, min(a.e2e_threads or (4 if world == 1 else 3), a.steps))
     workers = [map_host]
     extra_ctx = []
     for i in range(1, n_host):
