@@ -626,7 +626,7 @@ __device__ int quad_cs_dp(const FullParams &P, const FullTask &T, bool run, int 
     const int32_t *prev = sm + delta * slotstride;   // ring slot of the previous row's cell in the same column
     uint32_t gpos = T.goff_global + (uint32_t)x_min;
     uint32_t gword = genome[gpos >> 3];
-#pragma unroll 2
+#pragma unroll 4
     for (int s = 1; s <= wmax; s++) {
       const bool on = s <= width;
       cur += slotstride;
