@@ -65,6 +65,7 @@ __device__ int ring_ls_dp(const FullParams &P, const FullTask &T, int slot, int3
     const int delta = x_min - pxmin;
     uint32_t gpos = T.goff_global + (uint32_t)x_min;
     uint32_t gword = genome[gpos >> 3];
+#pragma unroll 4
     for (int j = x_min; j <= x_max; j++) {
       const int s = j - x_min + 1;
       int u_nw, u_n, u_w;  // cell (i-1, j)
