@@ -84,7 +84,7 @@ __device__ __forceinline__ void make_full_task(const FullBuildParams &P, int r, 
 struct Pipeline {
   DevBuf d_in, d_reads, d_read_len, d_initbp, d_hits, d_rs_range, d_counters, d_overflow, d_overflow2, d_scan_slab, d_tie_ent, d_tie_order, d_tie_rec, d_prof, d_mp_tab, d_mp_epoch, d_xover, d_quals, d_fqual, d_pstab, d_gmtab, d_scratch;
   DevBuf d_task[2], d_vtrue[2], d_slot, d_writer, d_sel, d_nsel;
-  DevBuf d_ftasks, d_finfo, d_fresults, d_frow, d_fbp[RING_CLASSES + 1], d_fops, d_taskoff, d_scan_tmp, d_perm;
+  DevBuf d_ftasks, d_finfo, d_fresults, d_frow, d_fbp[RING_CLASSES + 2], d_fops, d_taskoff, d_scan_tmp, d_perm;
   HostBuf h_info, h_results, h_ops, h_nsel, h_hits, h_range, h_xover, h_fqual;
   bool gm_tab_ready = false;
   int qual_stride = 0;      // quality strings of the resident chunk (0 = none)

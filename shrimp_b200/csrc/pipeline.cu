@@ -148,7 +148,7 @@ void free_pipeline(shrimp_gpu_ctx *ctx) {
   DevBuf *bufs[] = {&p->d_in, &p->d_reads, &p->d_read_len, &p->d_initbp, &p->d_hits, &p->d_rs_range, &p->d_counters,
                     &p->d_overflow, &p->d_overflow2, &p->d_scan_slab, &p->d_tie_ent, &p->d_tie_order, &p->d_tie_rec, &p->d_prof, &p->d_mp_tab, &p->d_mp_epoch, &p->d_xover, &p->d_quals, &p->d_fqual, &p->d_pstab, &p->d_gmtab, &p->d_scratch, &p->d_task[0], &p->d_task[1], &p->d_vtrue[0], &p->d_vtrue[1],
                     &p->d_slot, &p->d_writer, &p->d_sel, &p->d_nsel, &p->d_ftasks, &p->d_finfo, &p->d_fresults,
-                    &p->d_frow, &p->d_fbp[0], &p->d_fbp[1], &p->d_fbp[2], &p->d_fbp[3], &p->d_fbp[4], &p->d_fops,
+                    &p->d_frow, &p->d_fbp[0], &p->d_fbp[1], &p->d_fbp[2], &p->d_fbp[3], &p->d_fbp[4], &p->d_fbp[5], &p->d_fops,
                     &p->d_taskoff, &p->d_scan_tmp, &p->d_perm, &p->d_pair_min, &p->d_pair_max, &p->d_saved, &p->d_pairsel,
                     &p->d_npairsel, &p->d_taskof, &p->d_pairoff};
   for (DevBuf *b : bufs) b->release();
@@ -168,7 +168,7 @@ struct ctx_stream_guard {
 
 // Full SW over the n tasks of FP.tasks: classify by ring width, one ring launch per class and
 // sub-batch (scratch bounded to ~2 GB of back-pointers), global-scratch kernels for the rest.
-int run_full_sw(shrimp_gpu_ctx *ctx, DevBuf &d_perm, DevBuf &d_row, DevBuf *d_bp /*[RING_CLASSES+1]*/,
+int run_full_sw(shrimp_gpu_ctx *ctx, DevBuf &d_perm, DevBuf &d_row, DevBuf *d_bp /*[RING_CLASSES+2], the last for short runs*/,
                        FullParams FP, int n, bool cs, uint32_t *d_cls_count) {
   if (n <= 0) return SHRIMP_OK;
   cudaStream_t st = ctx->stream;
@@ -211,6 +211,8 @@ int run_full_sw(shrimp_gpu_ctx *ctx, DevBuf &d_perm, DevBuf &d_row, DevBuf *d_bp
   const size_t budget = (size_t)2 << 30;
   SH_CUDA(cudaEventRecord(ctx->fork_ev, st));
   ctx_stream_guard guard{ctx, st};
+  cudaStream_t side_st = ctx->aux[SHRIMP_AUX_STREAMS - 1];
+  bool side_used = false;
   for (int c = 0; c <= RING_CLASSES; c++) {
     if (cls[c] == 0) continue;
     const int count = (int)cls[c];
@@ -246,6 +248,16 @@ int run_full_sw(shrimp_gpu_ctx *ctx, DevBuf &d_perm, DevBuf &d_row, DevBuf *d_bp
         int batch_l = ring ? (int)std::min<size_t>((size_t)acc, std::max<size_t>(1024, budget / per_task_l)) : batch;
         batch_l = (batch_l + 127) & ~127;
         if (ring && (size_t)batch_l * per_task_l > (size_t)batch * per_task) batch_l = batch;
+        // a short run (the widest bands of a kind: a handful of alignments, a launch bounded by the latency of one)
+        // goes to a side stream with back-pointers of its own and overlaps the bulk
+        const bool side = ring && cs && acc < 8192 && acc <= batch_l;
+        DevBuf &bpbuf = side ? d_bp[RING_CLASSES + 1] : d_bp[c];
+        if (side) {
+          SH_TRY(bpbuf.ensure((size_t)batch_l * per_task_l));   // grows only: earlier short runs in flight keep their bytes
+          if (!side_used) SH_CUDA(cudaStreamWaitEvent(side_st, ctx->fork_ev, 0));
+          side_used = true;
+          ctx->stream = side_st;
+        }
         for (int b0 = seg0; b0 < seg0 + acc; b0 += batch_l) {
           FullParams Q = FP;
           Q.perm = perm + cls_first[c] + b0;
@@ -254,14 +266,15 @@ int run_full_sw(shrimp_gpu_ctx *ctx, DevBuf &d_perm, DevBuf &d_row, DevBuf *d_bp
           Q.NT = batch_l;
           Q.W = Wl;
           Q.row = Q.row_cs = d_row.as<int32_t>();
-          Q.bp = Q.bp_cs = d_bp[c].as<uint8_t>();
-          Q.bp64 = d_bp[c].as<unsigned long long>();
+          Q.bp = Q.bp_cs = bpbuf.as<uint8_t>();
+          Q.bp64 = bpbuf.as<unsigned long long>();
           int rc;
           if (ring) rc = launch_sw_full_ring(ctx, Q, cs);
           else if (cs) rc = launch_sw_full_cs(ctx, Q);
           else rc = launch_sw_full_ls(ctx, Q);
           if (rc != SHRIMP_OK) return rc;
         }
+        if (side) ctx->stream = cst;
         seg0 += acc;
         acc = 0;
         kmax = -1;
@@ -272,6 +285,10 @@ int run_full_sw(shrimp_gpu_ctx *ctx, DevBuf &d_perm, DevBuf &d_row, DevBuf *d_bp
       SH_CUDA(cudaEventRecord(ctx->join_ev[(c - 1) % SHRIMP_AUX_STREAMS], cst));
       SH_CUDA(cudaStreamWaitEvent(st, ctx->join_ev[(c - 1) % SHRIMP_AUX_STREAMS], 0));
     }
+  }
+  if (side_used) {
+    SH_CUDA(cudaEventRecord(ctx->join_ev[SHRIMP_AUX_STREAMS - 1], side_st));
+    SH_CUDA(cudaStreamWaitEvent(st, ctx->join_ev[SHRIMP_AUX_STREAMS - 1], 0));
   }
   return SHRIMP_OK;
 }
@@ -1607,14 +1624,14 @@ extern "C" int shrimp_gpu_sw_full_batch(shrimp_gpu_ctx *ctx, const uint32_t *gen
   }
   SH_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
-  DevBuf d_gen, d_reads, d_tasks, d_res, d_ops, d_perm, d_row, d_bp[RING_CLASSES + 1], d_cnt;
+  DevBuf d_gen, d_reads, d_tasks, d_res, d_ops, d_perm, d_row, d_bp[RING_CLASSES + 2], d_cnt;
   struct Rel {
-    DevBuf *b[13];
+    DevBuf *b[14];
     ~Rel() {
       for (DevBuf *x : b) x->release();
     }
   } rel{{&d_gen, &d_reads, &d_tasks, &d_res, &d_ops, &d_perm, &d_row, &d_bp[0], &d_bp[1], &d_bp[2], &d_bp[3], &d_bp[4],
-         &d_cnt}};
+         &d_bp[5], &d_cnt}};
   const size_t ops_stride = (size_t)max_rl + max_gl;
   SH_TRY(d_gen.ensure(genome_words * 4 + 16));
   SH_TRY(d_reads.ensure((size_t)n_reads * read_stride_words * 4));
