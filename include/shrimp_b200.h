@@ -90,6 +90,24 @@ int shrimp_gpu_sw_vector_batch(shrimp_gpu_ctx *ctx,
                                int32_t *scores_out);
 
 /* ------------------------------------------------------------------------------------------
+ * Batched gapless filter.  Replaces sw_gapless (common/sw-gapless.c:57-117), one call per task: the best
+ * ungapped segment score on the diagonal through (g_idx[t], r_idx[t]) of the genome piece genome[goff[t] ..
+ * goff[t] + glen[t]) (f1_run passes a whole contig, f1-wrapper.h:121-124) against reads[read_idx[t]].  Scores are
+ * the match / vector mismatch of the set-up (sw_gapless_setup gets the same two, f1-wrapper.h:56).  Colour space:
+ * genome_ls + initbp[t] force the first colour of the read (:83-93); letter space: NULL, NULL.
+ * ---------------------------------------------------------------------------------------- */
+int shrimp_gpu_sw_gapless_batch(shrimp_gpu_ctx *ctx,
+                                const uint32_t *genome, size_t genome_words,
+                                const uint32_t *genome_ls,
+                                const uint32_t *reads, int read_stride_words, int n_reads,
+                                int n_tasks,
+                                const uint32_t *goff, const int32_t *glen,
+                                const int32_t *read_idx, const int32_t *rlen,
+                                const int32_t *g_idx, const int32_t *r_idx,
+                                const int8_t *initbp,
+                                int32_t *scores_out);
+
+/* ------------------------------------------------------------------------------------------
  * Batched full Smith-Waterman with traceback.  Replaces sw_full_ls (common/sw-full-ls.c:637-683) and,
  * after a colour-space set-up, sw_full_cs (common/sw-full-cs.c:1146-1236), one task per call the
  * reference would make: read reads[read_idx] (rlen bases / colours, initbp in colour space) against
@@ -119,6 +137,14 @@ int shrimp_gpu_sw_full_batch(shrimp_gpu_ctx *ctx, const uint32_t *genome, size_t
                              const shrimp_full_task *tasks, int local_alignment,
                              shrimp_full_result *results, uint8_t *edits, int64_t edits_cap,
                              int64_t *edits_used);
+/* ... with sw_full_cs's last argument (sw-full-cs.c:1149, read_entry::crossover_score of reads with qualities):
+ * row read_idx of crossover_scores[n_reads][crossover_stride], or NULL for the global crossover score. */
+int shrimp_gpu_sw_full_batch_xover(shrimp_gpu_ctx *ctx, const uint32_t *genome, size_t genome_words,
+                                   const uint32_t *reads, int read_stride_words, int n_reads, int n_tasks,
+                                   const shrimp_full_task *tasks, int local_alignment,
+                                   const int32_t *crossover_scores, int crossover_stride,
+                                   shrimp_full_result *results, uint8_t *edits, int64_t edits_cap,
+                                   int64_t *edits_used);
 
 /* ------------------------------------------------------------------------------------------
  * Genome residency.  Replaces the arrays load_genome builds (gmapper/genome.c:1092-1124,
@@ -214,6 +240,13 @@ typedef struct shrimp_hit {
   int32_t sfr_matches, mismatches, insertions, deletions, crossovers;
   int32_t edit_len;
   int64_t edit_off;
+  /* identity of the read_hit inside the chunk (its slot in the chunk's hit lists): two records with the same
+   * hit_slot are the SAME struct read_hit in the reference -- readpair_save_final_hits (mapping.c:2446-2500) pools
+   * the members of the pairs by that identity before compute_paired_mqv (output.c:811-941) sums over them.
+   * st = the read strand the hit was found on before hit_run_full_sw re-oriented it (mapping.c:349-351). */
+  int32_t hit_slot, st;
+  int32_t score_window_gen;     /* rh->score_window_gen (mapping.c:1185), the ZR field of --extra-sam-fields */
+  int32_t reserved;
 } shrimp_hit;
 
 /* A read_hit after read_pass1 (stage-level parity with DEBUG_HIT_LIST_PASS1 dumps) */

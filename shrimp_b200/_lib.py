@@ -43,7 +43,8 @@ class HitC(C.Structure):
                 ("posterior", C.c_double),
                 ("read_start", C.c_int32), ("rmapped", C.c_int32), ("genome_start", C.c_int32), ("gmapped", C.c_int32),
                 ("sfr_matches", C.c_int32), ("mismatches", C.c_int32), ("insertions", C.c_int32),
-                ("deletions", C.c_int32), ("crossovers", C.c_int32), ("edit_len", C.c_int32), ("edit_off", C.c_int64)]
+                ("deletions", C.c_int32), ("crossovers", C.c_int32), ("edit_len", C.c_int32), ("edit_off", C.c_int64),
+                ("hit_slot", C.c_int32), ("st", C.c_int32), ("score_window_gen", C.c_int32), ("reserved", C.c_int32)]
 
 
 class StageHitC(C.Structure):
@@ -107,9 +108,14 @@ def lib() -> C.CDLL:
     L.shrimp_gpu_sw_setup.restype = i32
     L.shrimp_gpu_sw_vector_batch.argtypes = [vp, vp, C.c_size_t, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp]
     L.shrimp_gpu_sw_vector_batch.restype = i32
+    L.shrimp_gpu_sw_gapless_batch.argtypes = [vp, vp, C.c_size_t, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.shrimp_gpu_sw_gapless_batch.restype = i32
     L.shrimp_gpu_sw_full_batch.argtypes = [vp, vp, C.c_size_t, vp, i32, i32, i32, vp, i32, vp, vp, C.c_int64,
                                            C.POINTER(C.c_int64)]
     L.shrimp_gpu_sw_full_batch.restype = i32
+    L.shrimp_gpu_sw_full_batch_xover.argtypes = [vp, vp, C.c_size_t, vp, i32, i32, i32, vp, i32, vp, i32, vp, vp,
+                                                 C.c_int64, C.POINTER(C.c_int64)]
+    L.shrimp_gpu_sw_full_batch_xover.restype = i32
     L.shrimp_gpu_dpx_peak.argtypes = [vp, C.POINTER(C.c_double)]
     L.shrimp_gpu_dpx_peak.restype = i32
     L.shrimp_gpu_set_host_threads.argtypes = [C.c_int]

@@ -246,6 +246,25 @@ class GpuContext:
             "shrimp_gpu_sw_vector_batch")
         return out
 
+    # ---- sw_gapless ---------------------------------------------------------------------------
+    def sw_gapless(self, genome: np.ndarray, goff, glen, reads: np.ndarray, read_idx, rlen, g_idx, r_idx,
+                   genome_ls: np.ndarray | None = None, initbp=None) -> np.ndarray:
+        """Batched sw_gapless(genome, glen, read, rlen, g_idx, r_idx, genome_ls, init_bp) (sw-gapless.c:57); the
+        genome piece of task t starts at nibble goff[t] of `genome`."""
+        genome = np.ascontiguousarray(genome, dtype=np.uint32)
+        reads = np.ascontiguousarray(reads, dtype=np.uint32)
+        arrs = [np.ascontiguousarray(a, dtype=np.int32) for a in (glen, read_idx, rlen, g_idx, r_idx)]
+        goff = np.ascontiguousarray(goff, dtype=np.uint32)
+        n = goff.size
+        if genome_ls is not None:
+            genome_ls = np.ascontiguousarray(genome_ls, dtype=np.uint32)
+            initbp = np.ascontiguousarray(initbp, dtype=np.int8)
+        out = np.empty(n, dtype=np.int32)
+        check(self._L.shrimp_gpu_sw_gapless_batch(
+            self._h, _ptr(genome), genome.size, _ptr(genome_ls), _ptr(reads), reads.shape[1], reads.shape[0], n,
+            _ptr(goff), *[_ptr(a) for a in arrs], _ptr(initbp), _ptr(out)), "shrimp_gpu_sw_gapless_batch")
+        return out
+
     # ---- sw_full_ls / sw_full_cs ----------------------------------------------------------------
     def sw_full(self, genome: np.ndarray, reads: np.ndarray, tasks: np.ndarray, local: bool = False):
         """Batched sw_full_ls (sw-full-ls.c:637) / sw_full_cs (sw-full-cs.c:1146, after a colour set-up).

@@ -10,6 +10,7 @@ struct SelInfo {
   int32_t sort_idx;  // read_hit::sort_idx (mapping.c:1243-1246): index in the read's hit lists, strand 0 first
   uint32_t g_off;  // oriented (after reverse_hit)
   int32_t score_vector, score_max, matches;
+  int32_t wg;  // read_hit::score_window_gen
 };
 
 struct FullBuildParams {
@@ -77,6 +78,7 @@ __device__ __forceinline__ void make_full_task(const FullBuildParams &P, int r, 
   I.score_vector = P.M.colour_space ? h.score_vector : T.maxscore;
   I.score_max = h.score_max;
   I.matches = h.matches;
+  I.wg = h.wg;
 }
 
 #define RING_CLASSES 4

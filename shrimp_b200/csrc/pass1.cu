@@ -346,7 +346,101 @@ int launch_select_unpaired(shrimp_gpu_ctx *ctx, const Pass1Params &P) {
   return SHRIMP_OK;
 }
 
+// sw_gapless (common/sw-gapless.c:57-117), one thread per independent task of the batch entry below: the best
+// ungapped segment on the diagonal through (g_idx, r_idx) of a `glen`-long genome piece that starts at nibble goff.
+__global__ void sw_gapless_batch_kernel(const uint32_t *genome, const uint32_t *genome_ls, const uint32_t *reads,
+                                        int stride, const uint32_t *goff, const int32_t *glen, const int32_t *ridx,
+                                        const int32_t *rlen, const int32_t *g_idx, const int32_t *r_idx,
+                                        const int8_t *initbp, uint32_t n_tasks, int match, int mismatch,
+                                        int32_t *scores) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tasks) return;
+  const uint32_t *read = reads + (size_t)ridx[t] * stride;
+  const uint64_t g0 = goff[t];
+  const int gl = glen[t], rl = rlen[t];
+  int g = g_idx[t] < r_idx[t] ? 0 : g_idx[t] - r_idx[t];
+  int r = g_idx[t] < r_idx[t] ? r_idx[t] - g_idx[t] : 0;
+  int score = 0;
+  if (genome_ls != nullptr && r == 0) {  // forcefully match the first colour of the read (:83-93)
+    const uint32_t letter = extract4(genome_ls, g0 + (uint64_t)g);
+    const int ib = initbp[t];
+    const uint32_t real_colour = (letter > 3u || (uint32_t)ib > 3u) ? 15u : (letter ^ (uint32_t)ib);  // lstocs
+    if (real_colour == extract4(read, 0)) score = match;
+    r++;
+    g++;
+  }
+  int max_score = score;
+  while (g < gl && r < rl) {
+    score += (extract4(genome, g0 + (uint64_t)g) == extract4(read, (uint64_t)r)) ? match : mismatch;
+    if (score > max_score) max_score = score;
+    g++;
+    r++;
+    if (score < 0) score = 0;
+  }
+  scores[t] = max_score;
+}
+
 }  // namespace shrimp
+
+// sw_gapless (sw-gapless.c:57) for a batch of independent tasks, host buffers in, scores out.
+extern "C" int shrimp_gpu_sw_gapless_batch(shrimp_gpu_ctx *ctx, const uint32_t *genome, size_t genome_words,
+                                           const uint32_t *genome_ls, const uint32_t *reads, int read_stride_words,
+                                           int n_reads, int n_tasks, const uint32_t *goff, const int32_t *glen,
+                                           const int32_t *read_idx, const int32_t *rlen, const int32_t *g_idx,
+                                           const int32_t *r_idx, const int8_t *initbp, int32_t *scores_out) {
+  using namespace shrimp;
+  if (!ctx || !genome || !reads || !goff || !glen || !read_idx || !rlen || !g_idx || !r_idx || !scores_out ||
+      n_tasks < 0 || n_reads <= 0 || read_stride_words <= 0 || (genome_ls && !initbp)) {
+    set_error("shrimp_gpu_sw_gapless_batch: invalid argument");
+    return SHRIMP_E_ARG;
+  }
+  if (!ctx->sw.valid) {
+    set_error("shrimp_gpu_sw_gapless_batch: shrimp_gpu_sw_setup() has not been called");
+    return SHRIMP_E_STATE;
+  }
+  if (n_tasks == 0) return SHRIMP_OK;
+  for (int i = 0; i < n_tasks; i++)
+    if (glen[i] < 0 || rlen[i] < 0 || read_idx[i] < 0 || read_idx[i] >= n_reads || g_idx[i] < 0 || r_idx[i] < 0 ||
+        (uint64_t)goff[i] + (uint64_t)glen[i] > (uint64_t)genome_words * 8 || rlen[i] > read_stride_words * 8) {
+      set_error("shrimp_gpu_sw_gapless_batch: task %d out of range", i);
+      return SHRIMP_E_ARG;
+    }
+  SH_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const size_t gbytes = genome_words * sizeof(uint32_t);
+  SH_TRY(ctx->d_genome.ensure(gbytes + 16));
+  SH_CUDA(cudaMemsetAsync((char *)ctx->d_genome.p + gbytes, 0, 16, st));
+  SH_CUDA(cudaMemcpyAsync(ctx->d_genome.p, genome, gbytes, cudaMemcpyHostToDevice, st));
+  if (genome_ls) {
+    SH_TRY(ctx->d_genome_ls.ensure(gbytes + 16));
+    SH_CUDA(cudaMemsetAsync((char *)ctx->d_genome_ls.p + gbytes, 0, 16, st));
+    SH_CUDA(cudaMemcpyAsync(ctx->d_genome_ls.p, genome_ls, gbytes, cudaMemcpyHostToDevice, st));
+  }
+  const size_t rbytes = (size_t)n_reads * read_stride_words * sizeof(uint32_t);
+  SH_TRY(ctx->d_reads.ensure(rbytes));
+  SH_CUDA(cudaMemcpyAsync(ctx->d_reads.p, reads, rbytes, cudaMemcpyHostToDevice, st));
+  // task arrays packed in one buffer: goff | glen | ridx | rlen | g_idx | r_idx | initbp
+  const size_t n = (size_t)n_tasks;
+  SH_TRY(ctx->d_task.ensure(n * 4 * 6 + ((n + 3) & ~(size_t)3)));
+  char *tb = (char *)ctx->d_task.p;
+  const void *src[6] = {goff, glen, read_idx, rlen, g_idx, r_idx};
+  for (int k = 0; k < 6; k++) SH_CUDA(cudaMemcpyAsync(tb + n * 4 * k, src[k], n * 4, cudaMemcpyHostToDevice, st));
+  if (genome_ls) SH_CUDA(cudaMemcpyAsync(tb + n * 24, initbp, n, cudaMemcpyHostToDevice, st));
+  SH_TRY(ctx->d_scores.ensure(n * 4));
+  {
+    ScopedStage ss(ctx, ST_VECTOR);
+    sw_gapless_batch_kernel<<<(n_tasks + 127) / 128, 128, 0, st>>>(
+        ctx->d_genome.as<uint32_t>(), genome_ls ? ctx->d_genome_ls.as<uint32_t>() : nullptr, ctx->d_reads.as<uint32_t>(),
+        read_stride_words, (const uint32_t *)tb, (const int32_t *)(tb + n * 4), (const int32_t *)(tb + n * 8),
+        (const int32_t *)(tb + n * 12), (const int32_t *)(tb + n * 16), (const int32_t *)(tb + n * 20),
+        (const int8_t *)(tb + n * 24), (uint32_t)n_tasks, ctx->sw.match, ctx->sw.vec_mismatch, ctx->d_scores.as<int32_t>());
+    SH_CUDA(cudaGetLastError());
+    SH_LAUNCHED(ctx, ST_VECTOR);
+  }
+  SH_CUDA(cudaMemcpyAsync(scores_out, ctx->d_scores.p, n * 4, cudaMemcpyDeviceToHost, st));
+  SH_CUDA(cudaStreamSynchronize(st));
+  return SHRIMP_OK;
+}
 
 // Diagnostic: hash_genome_window (util.h:220-241) of n windows of a packed genome (8 codes per word) as the device
 // computes it for the f1 window cache, for the test that compares it with the reference's.

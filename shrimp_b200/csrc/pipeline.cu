@@ -1224,6 +1224,10 @@ void host_fill_hit(const Chunk &C, const HostHit &h, int r, HostOut &O) {
   o.crossovers = h.res.crossovers;
   o.edit_len = h.res.ops_len;
   o.edit_off = O.e_used;
+  o.hit_slot = h.info.hit_slot;
+  o.st = h.info.st;
+  o.score_window_gen = h.info.wg;
+  o.reserved = 0;
   const uint8_t *OPS = C.pl->h_ops.as<uint8_t>();
   if (O.edits && O.e_used + h.res.ops_len <= O.edits_cap)
     memcpy(O.edits + O.e_used, OPS + C.ops_stride * (size_t)h.task_idx + h.res.ops_start, (size_t)h.res.ops_len);
@@ -1311,9 +1315,10 @@ int host_pass2_all(const Chunk &C, const int32_t *n_sel, double full_thr, HostOu
     }
   }
   const FullResult *RES = C.pl->h_results.as<FullResult>();
-#pragma omp parallel num_threads(T)
-  {
-    const int t = omp_get_thread_num();
+  // the block index is the loop variable, never the team size: inside gmapper's own parallel region (nested
+  // parallelism off) or under OMP_THREAD_LIMIT the team has fewer than T threads and one thread takes several blocks
+#pragma omp parallel for schedule(static, 1) num_threads(T)
+  for (int t = 0; t < T; t++) {
     const int r0 = (int)((int64_t)n_reads * t / T), r1 = (int)((int64_t)n_reads * (t + 1) / T);
     std::vector<HostHit> hh((size_t)NT + 1);
     std::vector<HostHit *> h2((size_t)NT + 1);
@@ -1354,9 +1359,8 @@ int host_pass2_all(const Chunk &C, const int32_t *n_sel, double full_thr, HostOu
   const SelInfo *INFO = C.pl->h_info.as<SelInfo>();
   const uint8_t *OPS = C.pl->h_ops.as<uint8_t>();
   const uint8_t *FQ = C.pl->h_fqual.as<uint8_t>();
-#pragma omp parallel num_threads(T)
-  {
-    const int t = omp_get_thread_num();
+#pragma omp parallel for schedule(static, 1) num_threads(T)
+  for (int t = 0; t < T; t++) {
     const int r0 = (int)((int64_t)n_reads * t / T), r1 = (int)((int64_t)n_reads * (t + 1) / T);
     int64_t hi = hit_base + nh[t], eo = edit_base + ne[t];
     size_t q = 0;
@@ -1391,6 +1395,10 @@ int host_pass2_all(const Chunk &C, const int32_t *n_sel, double full_thr, HostOu
         o.crossovers = res.crossovers;
         o.edit_len = res.ops_len;
         o.edit_off = eo;
+        o.hit_slot = info.hit_slot;
+        o.st = info.st;
+        o.score_window_gen = info.wg;
+        o.reserved = 0;
         if (fill_edits) memcpy(O.edits + eo, OPS + C.ops_stride * (size_t)kr.task_idx + res.ops_start, (size_t)res.ops_len);
         eo += res.ops_len;
         if (C.post_sw) {   // sfrp->qual right after the edit script
@@ -1581,7 +1589,20 @@ extern "C" int shrimp_gpu_sw_full_batch(shrimp_gpu_ctx *ctx, const uint32_t *gen
                                         const shrimp_full_task *tasks, int local_alignment,
                                         shrimp_full_result *results, uint8_t *edits, int64_t edits_cap,
                                         int64_t *edits_used) {
-  if (!ctx || !genome || !reads || !tasks || !results || n_tasks < 0 || n_reads <= 0 || read_stride_words <= 0) {
+  return shrimp_gpu_sw_full_batch_xover(ctx, genome, genome_words, reads, read_stride_words, n_reads, n_tasks, tasks,
+                                        local_alignment, nullptr, 0, results, edits, edits_cap, edits_used);
+}
+
+// ... with the per-position crossover scores sw_full_cs takes as its last argument (sw-full-cs.c:1149): row
+// read_idx of crossover_scores[n_reads][crossover_stride], or NULL for the global score of the set-up.
+extern "C" int shrimp_gpu_sw_full_batch_xover(shrimp_gpu_ctx *ctx, const uint32_t *genome, size_t genome_words,
+                                              const uint32_t *reads, int read_stride_words, int n_reads, int n_tasks,
+                                              const shrimp_full_task *tasks, int local_alignment,
+                                              const int32_t *crossover_scores, int crossover_stride,
+                                              shrimp_full_result *results, uint8_t *edits, int64_t edits_cap,
+                                              int64_t *edits_used) {
+  if (!ctx || !genome || !reads || !tasks || !results || n_tasks < 0 || n_reads <= 0 || read_stride_words <= 0 ||
+      (crossover_scores && crossover_stride <= 0)) {
     set_error("shrimp_gpu_sw_full_batch: invalid argument");
     return SHRIMP_E_ARG;
   }
@@ -1594,9 +1615,17 @@ extern "C" int shrimp_gpu_sw_full_batch(shrimp_gpu_ctx *ctx, const uint32_t *gen
   const SwScores &sw = ctx->sw;
   const bool cs = sw.use_colours != 0;
   int max_rl = 1, max_gl = 1;
+  // the kernels find a read's crossover row at ridx >> 1 (the chunk layout: row 2r = read r, 2r + 1 = its reverse
+  // complement), so with crossover rows the reads of the batch go to the even rows
+  const bool xpos = cs && crossover_scores != nullptr && crossover_stride > 0;
+  const int rmul = xpos ? 2 : 1;
   std::vector<FullTask> ft((size_t)n_tasks);
   for (int t = 0; t < n_tasks; t++) {
     const shrimp_full_task &a = tasks[t];
+    if (xpos && a.rlen > crossover_stride) {
+      set_error("shrimp_gpu_sw_full_batch: task %d is longer than a crossover row", t);
+      return SHRIMP_E_ARG;
+    }
     if (a.glen <= 0 || a.rlen <= 0 || a.read_idx < 0 || a.read_idx >= n_reads || a.rlen > read_stride_words * 8 ||
         (uint64_t)a.goff + (uint64_t)a.glen > (uint64_t)genome_words * 8 || a.rlen > sw.max_read_len ||
         a.glen > sw.max_window_len) {
@@ -1609,7 +1638,7 @@ extern "C" int shrimp_gpu_sw_full_batch(shrimp_gpu_ctx *ctx, const uint32_t *gen
     T.goff_contig = a.goff;
     T.glen = a.glen;
     T.rlen = a.rlen;
-    T.ridx = a.read_idx;
+    T.ridx = a.read_idx * rmul;
     T.ax = a.ax;
     T.ay = a.ay;
     T.alen = a.alen;
@@ -1624,23 +1653,35 @@ extern "C" int shrimp_gpu_sw_full_batch(shrimp_gpu_ctx *ctx, const uint32_t *gen
   }
   SH_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
-  DevBuf d_gen, d_reads, d_tasks, d_res, d_ops, d_perm, d_row, d_bp[RING_CLASSES + 2], d_cnt;
+  DevBuf d_gen, d_reads, d_tasks, d_res, d_ops, d_perm, d_row, d_bp[RING_CLASSES + 2], d_cnt, d_xo;
   struct Rel {
-    DevBuf *b[14];
+    DevBuf *b[15];
     ~Rel() {
       for (DevBuf *x : b) x->release();
     }
   } rel{{&d_gen, &d_reads, &d_tasks, &d_res, &d_ops, &d_perm, &d_row, &d_bp[0], &d_bp[1], &d_bp[2], &d_bp[3], &d_bp[4],
-         &d_bp[5], &d_cnt}};
+         &d_bp[5], &d_cnt, &d_xo}};
   const size_t ops_stride = (size_t)max_rl + max_gl;
   SH_TRY(d_gen.ensure(genome_words * 4 + 16));
-  SH_TRY(d_reads.ensure((size_t)n_reads * read_stride_words * 4));
+  SH_TRY(d_reads.ensure((size_t)n_reads * rmul * read_stride_words * 4));
   SH_TRY(d_tasks.ensure((size_t)n_tasks * sizeof(FullTask)));
   SH_TRY(d_res.ensure((size_t)n_tasks * sizeof(FullResult)));
   SH_TRY(d_ops.ensure(ops_stride * (size_t)n_tasks));
   SH_TRY(d_cnt.ensure(64 * 4));
+  SH_CUDA(cudaMemsetAsync((char *)d_gen.p + genome_words * 4, 0, 16, st));
   SH_CUDA(cudaMemcpyAsync(d_gen.p, genome, genome_words * 4, cudaMemcpyHostToDevice, st));
-  SH_CUDA(cudaMemcpyAsync(d_reads.p, reads, (size_t)n_reads * read_stride_words * 4, cudaMemcpyHostToDevice, st));
+  SH_CUDA(cudaMemcpy2DAsync(d_reads.p, (size_t)rmul * read_stride_words * 4, reads, (size_t)read_stride_words * 4,
+                            (size_t)read_stride_words * 4, (size_t)n_reads, cudaMemcpyHostToDevice, st));
+  std::vector<int16_t> hx;
+  if (xpos) {
+    hx.resize((size_t)n_reads * crossover_stride);
+    for (size_t q = 0; q < hx.size(); q++) {
+      const int32_t v = crossover_scores[q];
+      hx[q] = (int16_t)(v < -32768 ? -32768 : v > 0 ? 0 : v);
+    }
+    SH_TRY(d_xo.ensure(hx.size() * 2));
+    SH_CUDA(cudaMemcpyAsync(d_xo.p, hx.data(), hx.size() * 2, cudaMemcpyHostToDevice, st));
+  }
   SH_CUDA(cudaMemcpyAsync(d_tasks.p, ft.data(), (size_t)n_tasks * sizeof(FullTask), cudaMemcpyHostToDevice, st));
   SH_CUDA(cudaMemsetAsync(d_cnt.p, 0, 64 * 4, st));
   FullParams FP;
@@ -1665,6 +1706,8 @@ extern "C" int shrimp_gpu_sw_full_batch(shrimp_gpu_ctx *ctx, const uint32_t *gen
   FP.cells = (unsigned long long *)(d_cnt.as<uint32_t>() + 16);
   FP.xover = sw.xover;
   FP.indel_taboo_len = sw.indel_taboo_len;
+  FP.xover_pos = xpos ? d_xo.as<int16_t>() : nullptr;
+  FP.xover_stride = xpos ? crossover_stride : 0;
   {
     ScopedStage ss(ctx, ST_FULL);
     SH_TRY(run_full_sw(ctx, d_perm, d_row, d_bp, FP, n_tasks, cs, d_cnt.as<uint32_t>() + 32));

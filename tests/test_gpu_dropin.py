@@ -1,0 +1,119 @@
+"""The linked drop-in (integration/): the reference's UNCHANGED gmapper.c / genome.c / output.c / fasta.c objects
+linked with the shims + libshrimp_b200.so, run FASTA -> SAM, and diffed byte for byte (minus the @PG line, which
+carries the command line) against the reference binary on the same files and options.  This pins everything the
+SAM body shows: MAPQ, Z0..Z6, mate fields, TLEN, SEQ/QUAL, XX:Z, CM:i, AS, NM.
+
+Both binaries are prebuilt here (oracle/_ref, integration/_build) and travel to the GPU box."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from mapcases import MAP_CASES, PAIR_CASES, LsCase, PairCase  # noqa: E402
+
+REF = os.path.join(ROOT, "oracle", "_ref")
+NEW = os.path.join(ROOT, "integration", "_build")
+
+needs_bins = pytest.mark.skipif(
+    not (os.path.exists(os.path.join(REF, "gmapper-ls")) and os.path.exists(os.path.join(NEW, "gmapper-ls"))),
+    reason="prebuilt reference / drop-in binaries not present")
+
+
+def run_sam(bindir, binary, args, cwd, threads, extra=()):
+    cmd = [os.path.join(bindir, binary), "-N", str(threads), *extra, *args]
+    r = subprocess.run(cmd, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=1200)
+    assert r.returncode == 0, (cmd, r.stderr.decode(errors="replace")[-3000:])
+    body = [ln for ln in r.stdout.split(b"\n") if not ln.startswith(b"@PG")]
+    return body, r.stderr.decode(errors="replace")
+
+
+def assert_same_sam(ref, new):
+    assert len(ref) == len(new), (len(ref), len(new))
+    bad = [i for i, (a, b) in enumerate(zip(ref, new)) if a != b]
+    assert not bad, (len(bad), [(ref[i], new[i]) for i in bad[:3]])
+
+
+@needs_bins
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(MAP_CASES))
+def test_unpaired_sam_identical(name, tmp_path):
+    case = LsCase(name)
+    case.write_fasta(str(tmp_path))
+    args = [*MAP_CASES[name]["args"], "reads.fa", "genome.fa"]
+    ref, _ = run_sam(REF, case.binary, args, str(tmp_path), 4)
+    # -K 700: several chunks per thread, so the look-ahead batches start in the middle of the file too
+    new, err = run_sam(NEW, case.binary, args, str(tmp_path), 2, ["-K", "700"])
+    assert_same_sam(ref, new)
+    assert sum(1 for ln in new if ln and not ln.startswith(b"@")) > 100
+
+
+@needs_bins
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(PAIR_CASES))
+def test_paired_sam_identical(name, tmp_path):
+    case = PairCase(name)
+    case.write_fasta(str(tmp_path))
+    args = [*PAIR_CASES[name]["args"], "-1", "m1.fa", "-2", "m2.fa", "genome.fa"]
+    ref, _ = run_sam(REF, case.binary, args, str(tmp_path), 4)
+    new, err = run_sam(NEW, case.binary, args, str(tmp_path), 2, ["-K", "300"])
+    assert_same_sam(ref, new)
+    assert sum(1 for ln in new if ln and not ln.startswith(b"@")) > 100
+
+
+@needs_bins
+@pytest.mark.gpu
+@pytest.mark.parametrize("extra", [["--sam-unaligned"], ["--single-best-mapping"], ["--strata"], ["-o", "3"],
+                                   ["--extra-sam-fields"], ["--all-contigs"], ["--trim-front", "3", "--trim-end", "2"]])
+def test_output_options_c1(extra, tmp_path):
+    """options that only touch the unchanged output code or the loop of gmapper.c the look-ahead has to predict"""
+    case = LsCase("c1_small")
+    case.write_fasta(str(tmp_path))
+    args = [*extra, "reads.fa", "genome.fa"]
+    ref, _ = run_sam(REF, case.binary, args, str(tmp_path), 4)
+    new, _ = run_sam(NEW, case.binary, args, str(tmp_path), 2, ["-K", "700"])
+    assert_same_sam(ref, new)
+
+
+@needs_bins
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["opp-out", "col-fw", "col-bw"])
+def test_pair_modes(mode, tmp_path):
+    """the pair orientations that reverse a mate before mapping (pair_reverse, gmapper-defaults.h:184-191)"""
+    case = PairCase("c3_small")
+    case.write_fasta(str(tmp_path))
+    args = ["-p", mode, "-I", "0,1000", "-1", "m1.fa", "-2", "m2.fa", "genome.fa"]
+    ref, _ = run_sam(REF, case.binary, args, str(tmp_path), 4)
+    new, _ = run_sam(NEW, case.binary, args, str(tmp_path), 2, ["-K", "300"])
+    assert_same_sam(ref, new)
+
+
+def test_dropin_exports_the_reference_symbols():
+    """nm: the mangled names mapping.o / sw-vector.o / sw-gapless.o / sw-full-ls.o / sw-full-cs.o export in the
+    reference are all defined by the shims"""
+    objs = [os.path.join(NEW, "mapping_shim.o"), os.path.join(NEW, "sw_shims.o")]
+    if not all(os.path.exists(o) for o in objs):
+        pytest.skip("integration/_build not built")
+    out = subprocess.run(["nm", "--defined-only", *objs], stdout=subprocess.PIPE, check=True).stdout.decode()
+    have = {ln.split()[-1] for ln in out.splitlines() if " T " in ln}
+    want = ["_Z15sw_vector_setupiiiiiiiiib", "_Z9sw_vectorPjiiS_iS_ib", "_Z15sw_vector_statsPmS_Pd",
+            "_Z17sw_vector_cleanupv", "_Z16sw_gapless_setupiib", "_Z10sw_gaplessPjiS_iiiS_ib",
+            "_Z16sw_gapless_statsPmS_S_", "_Z16sw_full_ls_setupiiiiiiiibi",
+            "_Z10sw_full_lsPjiiS_iiiP15sw_full_resultsbP6anchorii", "_Z16sw_full_ls_statsPmS_Pd",
+            "_Z18sw_full_ls_cleanupv", "_Z16sw_full_cs_setupiiiiiiiiibii",
+            "_Z10sw_full_csPjiiS_iiiP15sw_full_resultsbbP6anchoriiPi", "_Z16sw_full_cs_statsPmS_Pd",
+            "_Z18sw_full_cs_cleanupv", "_Z11handle_readP10read_entryP22read_mapping_options_ti",
+            "_Z15handle_readpairP10pair_entryP26readpair_mapping_options_ti", "_Z15get_insert_sizeP8read_hitS0_"]
+    missing = [w for w in want if w not in have]
+    assert not missing, missing
+    # and they are the reference's names: the reference objects define the very same symbols
+    ref_objs = [os.path.join(REF, "obj", f"{n}.o") for n in ("gmapper_mapping", "common_sw-vector", "common_sw-gapless",
+                                                             "common_sw-full-ls", "common_sw-full-cs")]
+    if all(os.path.exists(o) for o in ref_objs):
+        rout = subprocess.run(["nm", "--defined-only", *ref_objs], stdout=subprocess.PIPE, check=True).stdout.decode()
+        rhave = {ln.split()[-1] for ln in rout.splitlines() if " T " in ln}
+        assert set(want) <= rhave, sorted(set(want) - rhave)
+        assert rhave <= have, sorted(rhave - have)
