@@ -38,13 +38,40 @@ class Workload:
     """Seeded synthetic genome + simulated reads of one BASELINE.json config."""
 
     def __init__(self, key, desc, colour, read_len, contig_len, n_contigs, seed_genome, default_reads, binary, args,
-                 paired=False, n_frac=0.0):
+                 paired=False, n_frac=0.0, opts=None, seeds_weight=0, mirna=False, anchor_width=8, gap_open=None,
+                 list_cutoff=None, kind=None, cpu_sample=200_000):
         self.key, self.desc, self.colour, self.read_len = key, desc, colour, read_len
         self.contig_len, self.n_contigs, self.seed_genome = contig_len, n_contigs, seed_genome
         self.genome_len = contig_len * n_contigs
         self.default_reads, self.binary, self.args = default_reads, binary, args
         self.paired, self.n_frac = paired, n_frac
+        # option set of the gmapper command line `args` as MapParams overrides (tests/mapcases.py has the same table)
+        self.opts, self.seeds_weight, self.mirna = dict(opts or {}), seeds_weight, mirna
+        self.anchor_width, self.gap_open, self.fixed_cutoff = anchor_width, gap_open, list_cutoff
+        self.kind = kind or key
+        self.cpu_sample = cpu_sample
         self._genome = None
+
+    def seeds(self):
+        from shrimp_b200 import seeds as S
+        return S.load_default_mirna_seeds() if self.mirna else S.load_default_seeds(self.seeds_weight)
+
+    def scores(self):
+        import shrimp_b200
+        from shrimp_b200.api import Scores
+        sc = shrimp_b200.CS_DEFAULT_SCORES if self.colour else shrimp_b200.LS_DEFAULT_SCORES
+        if self.gap_open is not None:
+            sc = Scores(sc.match, sc.mismatch, self.gap_open, sc.a_gap_ext, self.gap_open, sc.b_gap_ext, sc.crossover)
+        return sc
+
+    def map_params(self):
+        from shrimp_b200.api import MapParams, auto_list_cutoff
+        cutoff = self.fixed_cutoff if self.fixed_cutoff is not None else auto_list_cutoff(
+            self.genome_len, 12 if self.mirna else max(s.weight for s in self.seeds()))
+        kw = dict(list_cutoff=cutoff, compute_mapping_qualities="--no-mapping-qualities" not in self.args,
+                  match_mode=4 if self.paired else 2)
+        kw.update(self.opts)
+        return MapParams(**kw)
 
     def resize(self, genome_mb: int):
         self.contig_len = genome_mb * 1_000_000 // self.n_contigs
@@ -111,9 +138,30 @@ class Workload:
         g, rl = self.genome(), self.read_len
         rr = np.random.default_rng(seed)
         cn = rr.integers(0, self.n_contigs, size=n_reads)
-        pos = cn * self.contig_len + rr.integers(0, self.contig_len - rl, size=n_reads)
-        frag = g[pos[:, None] + np.arange(rl)[None, :]].copy()
-        if not self.colour:      # C1: 2 % substitutions
+        room = self.contig_len - rl - (6 if self.kind == "c5" else 0)
+        pos = cn * self.contig_len + (rr.integers(0, room, size=n_reads) if room > 0 else 0)
+        if self.kind == "c5":    # C5: 4 % substitutions, half of the reads with one indel of 1..5 bases
+            frag = g[pos[:, None] + np.arange(rl + 6)[None, :]].copy()
+            sub = rr.random(frag.shape) < 0.04
+            frag[sub] = (frag[sub] + rr.integers(1, 4, size=int(sub.sum()))) % 4
+            out = frag[:, :rl].copy()
+            for i in np.nonzero(rr.random(n_reads) < 0.5)[0]:
+                k, at = int(rr.integers(1, 6)), int(rr.integers(5, rl - 10))
+                if rr.random() < 0.5:    # the read skips k genome bases
+                    out[i, at:] = frag[i, at + k:at + k + rl - at]
+                else:                    # k extra bases in the read
+                    out[i, at:at + k] = rr.integers(0, 4, size=k)
+                    out[i, at + k:] = frag[i, at:rl - k]
+            frag = out
+        else:
+            frag = g[pos[:, None] + np.arange(rl)[None, :]].copy()
+        if self.kind == "c5":
+            pass
+        elif self.kind == "c4":  # C4: one substitution in half of the reads
+            m = np.nonzero(rr.random(n_reads) < 0.5)[0]
+            p = rr.integers(0, rl, size=m.size)
+            frag[m, p] = (frag[m, p] + rr.integers(1, 4, size=m.size)) % 4
+        elif not self.colour:      # C1: 2 % substitutions
             sub = rr.random(frag.shape) < 0.02
             frag[sub] = (frag[sub] + rr.integers(1, 4, size=int(sub.sum()))) % 4
         else:                    # C2: one SNP in 30 % of the reads
@@ -171,6 +219,25 @@ WORKLOADS = {
     # BASELINE.json configs[0]: the reference's own CPU-runnable case
     "c1": Workload("c1", "C1 letter-space: 100k x 50bp reads (2% subs) vs iid 10 Mb genome, 3 default seeds w12",
                    False, 50, 10_000_000, 1, 1, 100_000, "gmapper-ls", []),
+    # BASELINE.json configs[3]: 22 bp reads vs a miRNA-like database of 2,000 x 22 bp contigs (short targets, many
+    # windows), with gmapper-ls's default options and with -M mirna (gmapper.c:1498-1515: hashed 5-seed set, gapless
+    # pass 1, gap opens -255, no window cache, one seed match, window 100 %, local full SW, no mapping qualities)
+    "c4": Workload("c4", "C4 miRNA: 22bp reads (one substitution in half of them) vs 2,000 x 22bp contigs, default "
+                   "options", False, 22, 22, 2000, 7, 1_000_000, "gmapper-ls", [], kind="c4"),
+    "c4mirna": Workload("c4mirna", "C4 miRNA with -M mirna: 22bp reads vs 2,000 x 22bp contigs, hashed 5-seed set, "
+                        "gapless pass 1, local full SW", False, 22, 22, 2000, 7, 1_000_000, "gmapper-ls", ["-M", "mirna"],
+                        opts=dict(match_mode=1, window_len=100.0, gapless=True, hash_filter_calls=False, Gflag=False,
+                                  compute_mapping_qualities=False), mirna=True, anchor_width=0, gap_open=-255, kind="c4"),
+    # BASELINE.json configs[4]: the "overly sensitive" mode (README:481-534, letter-space subset): four weight-11
+    # seeds, one seed match, wide windows, threshold band (-a -1), no window cache (-Z), no index trimming (-V):
+    # about a thousand sw_vector calls per read in the reference -- the DPX kernel's real test
+    "c5": Workload("c5", "C5 overly sensitive: 75bp reads (4% subs, one indel of 1-5 bp in half of them) vs iid 10 Mb "
+                   "genome, -s w11 -n 1 -w 150% -r 50% -l 40% -Z -h 60% -a -1 -V", False, 75, 10_000_000, 1, 1, 200_000,
+                   "gmapper-ls", ["-s", "w11", "-n", "1", "-w", "150%", "-r", "50%", "-l", "40%", "-Z", "-h", "60%", "-a",
+                                  "-1", "-V"],
+                   opts=dict(match_mode=1, window_len=150.0, window_gen_threshold=50.0, window_overlap=40.0,
+                             hash_filter_calls=False, sw_full_threshold=60.0), seeds_weight=11, anchor_width=-1,
+                   list_cutoff=0xFFFFFFFF, kind="c5", cpu_sample=4_000),
 }
 
 
@@ -293,9 +360,9 @@ def run_oracle_port(w: Workload, n_sample: int):
     import shrimp_b200
     n = min(n_sample, 20_000) & ~1
     codes, initbp = w.reads(n, 1000)
-    scores = shrimp_b200.CS_DEFAULT_SCORES if w.colour else shrimp_b200.LS_DEFAULT_SCORES
+    scores = w.scores()
     g = op.Genome(w.contigs(), w.colour)
-    ix = op.Index(g, S.load_default_seeds())
+    ix = op.Index(g, w.seeds())
     opts = op.MapOptions(scores=scores, colour_space=w.colour, list_cutoff=op.auto_list_cutoff(w.genome_len, 12),
                          compute_mapping_qualities="--no-mapping-qualities" not in w.args,
                          match_mode=4 if w.paired else 2)
@@ -309,101 +376,37 @@ def run_oracle_port(w: Workload, n_sample: int):
     return n / dt, f"{n} reads of the same workload through the C oracle port (oracle/shrimp_oracle.c), 1 host thread"
 
 
+def bench_config(w: Workload, n_reads: int, world: int):
+    """the `config` of the JSON line, the same for both arms"""
+    return {"workload": w.desc, "reads_per_gpu_per_step": n_reads, "read_len": w.read_len, "genome_len": w.genome_len,
+            "parallelism": f"read-sharded x{world}, replicated index",
+            "l2": "L2 flushed (256 MB write) before every timed step; index > L2"}
+
+
 def build_context(w: Workload, device: int):
     import shrimp_b200
     from shrimp_b200 import seeds as S
     ctx = shrimp_b200.GpuContext(device)
-    scores = shrimp_b200.CS_DEFAULT_SCORES if w.colour else shrimp_b200.LS_DEFAULT_SCORES
-    seeds = S.load_default_seeds()
-    ctx.sw_setup(1400, 1000, scores, use_colours=w.colour)  # dblen/qrlen as gmapper sets them up (longest_read_len 1000)
+    scores = w.scores()
+    seeds = w.seeds()
+    # dblen/qrlen as gmapper sets them up (longest_read_len 1000, window 140 % / 150 %)
+    ctx.sw_setup(1500, 1000, scores, use_colours=w.colour, anchor_width=w.anchor_width)
     t0 = time.time()
     ctx.load_genome(w.packed_contigs(), [w.contig_len] * w.n_contigs, colour_space=w.colour)
-    ctx.build_index(seeds)
+    ctx.build_index(seeds, hflag=w.mirna)
     return ctx, scores, seeds, time.time() - t0
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--reads", type=int, default=0, help="reads per GPU per step (0 = the workload's default)")
-    ap.add_argument("--genome-mb", type=int, default=0, help="scale the synthetic genome (c3: default 300, 3000 = hg18 size)")
-    ap.add_argument("--cpu-sample", type=int, default=200_000, help="reads in the cpu_baseline sample")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-threads", type=int, default=0,
-                    help="host threads (one context each) of the end-to-end leg; 0 = 4 on one GPU, 3 per GPU on several")
-    a = ap.parse_args()
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    ncores = os.cpu_count() or 1
-    w = WORKLOADS[a.workload]
-    if a.genome_mb or w.key == "c3":
-        w.resize(a.genome_mb or 300)
-    n_reads = a.reads or w.default_reads
+def measure(a, w, n_reads, rank, world, local_rank, ncores, compact=False):
+    """One workload on this rank's GPU: device-resident value, end to end through the C ABI, per-stage rooflines, the
+    reference on the host cores (rank 0, one GPU) and the drop-in binary FASTA -> SAM.  Returns the JSON line (rank 0).
+    compact: a short leg for the `workloads` block of the default run."""
     ref_bin = os.path.join(REF_DIR, w.binary)
-
-    if a.impl == "reference":
-        if rank != 0:
-            return 0
-        if not os.path.exists(ref_bin):   # the compiled reference did not travel: time the oracle port instead
-            vals = []
-            for _ in range(max(1, min(a.steps, 2))):
-                v, sample_s = run_oracle_port(w, a.cpu_sample)
-                vals.append(v)
-            val = sum(vals) / len(vals)
-            print(json.dumps({"impl": "reference", "metric": "reads_per_sec_mapped", "value": val, "unit": "reads/s",
-                              "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": None,
-                              "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16",
-                              "data": "synthetic", "config": {"workload": w.desc},
-                              "cpu_baseline": {"value": val, "unit": "reads/s", "cores": 1, "kind": "port",
-                                               "sample": sample_s},
-                              "e2e": {"value": val, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
-            return 0
-        sample, _ = w.reads(a.cpu_sample, 1000)
-        ctx = None
-        try:
-            import torch
-            if torch.cuda.is_available():
-                ctx = build_context(w, 0)[0]
-        except Exception:  # noqa: BLE001
-            ctx = None
-        with tempfile.TemporaryDirectory() as d:
-            how = reference_setup(w, d, sample, ctx)
-            if ctx is not None:
-                ctx.close()
-            for _ in range(min(a.warmup, 1)):
-                run_reference(w, d, ncores, "reads.fa", "proj")
-            secs, gc = [], []
-            for _ in range(a.steps):
-                s, g, _ = run_reference(w, d, ncores, "reads.fa", "proj")
-                secs.append(s)
-                gc.append(g)
-        tot = sum(secs)
-        val = a.cpu_sample * a.steps / tot
-        sample_s = (f"{a.cpu_sample} reads of the {w.key.upper()} workload per step, {w.binary} -N {ncores} "
-                    f"{' '.join(w.args)} -L <projection> (Read Mapping Time); {how}")
-        line = {"impl": "reference", "metric": "reads_per_sec_mapped", "value": val, "unit": "reads/s",
-                "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * tot / a.steps,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16",
-                "data": "synthetic", "config": {"workload": w.desc, "reads_per_step": a.cpu_sample},
-                "sw_vector_gcups": gc[-1],
-                "cpu_baseline": {"value": val, "unit": "reads/s", "cores": ncores, "kind": "reference",
-                                 "sample": sample_s},
-                "e2e": {"value": val, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
-        return 0
-
     import torch
     import torch.distributed as dist
 
     from shrimp_b200.api import MapParams, auto_list_cutoff
 
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
 
     codes, initbp_np = w.reads(n_reads, 2 + rank)
@@ -416,8 +419,7 @@ def main():
     # torchrun exports OMP_NUM_THREADS=1: give every rank its share of the host cores for the host stages
     from shrimp_b200.api import set_host_threads
     set_host_threads(max(1, ncores // max(1, world)))
-    params = MapParams(list_cutoff=auto_list_cutoff(w.genome_len, 12), compute_mapping_qualities="--no-mapping-qualities" not in w.args,
-                       match_mode=4 if w.paired else 2)
+    params = w.map_params()
 
     def map_host():
         if w.paired:
@@ -515,9 +517,10 @@ def main():
     e2e_val = world * n_reads * a.steps / shard.max_over_ranks(e2e_s, world, device="cuda")
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return 0
+        for cx in extra_ctx:
+            cx.close()
+        ctx.close()
+        return None
 
     # ---- roofline of the dominant kernels ----------------------------------------------------------
     peaks = {}
@@ -550,7 +553,7 @@ def main():
                       "unit": "G thread-instr/s", "frac": vec_ginstr / dpx_peak if dpx_peak else None,
                       "traffic": None, "gcups": vec_gcups, "ms_per_launch": vec_ms,
                       "peak_source": "measured live: register-resident VIADDMNMX.S16x2 chains (shrimp_gpu_dpx_peak)"},
-        "seed_scan": {"kernel": "scan_kernel", "bound": "hbm", "achieved": scan_gbs, "peak": hbm_peak, "unit": "GB/s",
+        "seed_scan": {"kernel": "scan_cta_kernel" if st["scan_big_strands"] > n_reads else "scan_kernel", "bound": "hbm", "achieved": scan_gbs, "peak": hbm_peak, "unit": "GB/s",
                       "frac": scan_gbs / hbm_peak, "traffic": None, "ms_per_launch": scan_ms, "peak_source": peak_src,
                       "algorithmic_bytes_per_launch": scan_bytes},
         "sw_full": {"kernel": "sw_full_cs_quad_kernel" if w.colour else "sw_full_ls_ring_kernel", "bound": "int-alu",
@@ -585,34 +588,55 @@ def main():
     roofline["dominant_stage"] = dominant
     roofline["other"] = {k: v for k, v in roofs.items() if k != dominant}
 
-    # ---- CPU baseline: the reference binary on this box's cores, bounded sample ---------------------
+    # ---- CPU baseline: the reference binary on this box's cores, bounded sample; and the drop-in binary
+    # (integration/_build: the reference's unchanged gmapper.c / output.c / fasta.c objects + the shims + the library)
+    # FASTA -> SAM on the same kind of files, each by its own "Read Mapping Time" ---------------------------------
     cpu = None
+    e2e_sam = None
+    n_cpu = min(a.cpu_sample, w.cpu_sample) & ~1
     if world == 1 and not a.no_cpu_baseline and not os.path.exists(ref_bin) and w.genome_len <= 400_000_000:
         try:
-            v, sample_s = run_oracle_port(w, a.cpu_sample)
+            v, sample_s = run_oracle_port(w, n_cpu)
             cpu = {"value": v, "unit": "reads/s", "cores": 1, "kind": "port", "sample": sample_s}
         except Exception as e:  # noqa: BLE001
             cpu = {"value": None, "unit": "reads/s", "cores": 1, "kind": "port", "sample": f"failed: {e}"}
     if world == 1 and not a.no_cpu_baseline and os.path.exists(ref_bin) and w.genome_len <= 400_000_000:
         try:
-            sample, _ = w.reads(a.cpu_sample, 1000)
+            sample, _ = w.reads(n_cpu, 1000)
             with tempfile.TemporaryDirectory() as d:
                 how = reference_setup(w, d, sample, ctx)
                 s, gcu, _ = run_reference(w, d, ncores, "reads.fa", "proj")
-            cpu = {"value": a.cpu_sample / s, "unit": "reads/s", "cores": ncores, "kind": "reference",
-                   "sample": f"{a.cpu_sample} reads of the same workload, oracle/_ref/{w.binary} -N {ncores} "
-                             f"{' '.join(w.args)} -L <projection> (Read Mapping Time, index load excluded); {how}",
-                   "sw_vector_gcups": gcu}
+                cpu = {"value": n_cpu / s, "unit": "reads/s", "cores": ncores, "kind": "reference",
+                       "sample": f"{n_cpu} reads of the same workload, oracle/_ref/{w.binary} -N {ncores} "
+                                 f"{' '.join(w.args)} -L <projection> (Read Mapping Time, index load excluded); {how}",
+                       "sw_vector_gcups": gcu}
+                dropin = os.path.join(ROOT, "integration", "_build", w.binary)
+                if os.path.exists(dropin):
+                    n_sam = (n_reads if compact else 2 * n_reads) & ~1
+                    big, _ = w.reads(n_sam, 1001)
+                    w.write_reads_fasta(os.path.join(d, "big.fa"), big)
+                    th, ck = min(ncores, 16), max(2000, min(125_000, n_sam // 8)) & ~1
+                    rd = ["-1", "big.fa.1", "-2", "big.fa.2"] if w.paired else ["big.fa"]
+                    r = subprocess.run([dropin, "-N", str(th), "-K", str(ck), *w.args, "-L", "proj", *rd], cwd=d,
+                                       stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
+                    m = re.search(r"Read Mapping Time:\s+([0-9.]+) seconds", r.stderr)
+                    if r.returncode == 0 and m and float(m.group(1)) > 0:
+                        e2e_sam = {"value": n_sam / float(m.group(1)), "unit": "reads/s", "reads": n_sam,
+                                   "reference_value": cpu["value"],
+                                   "how": f"integration/_build/{w.binary} -N {th} -K {ck} {' '.join(w.args)} -L <projection> "
+                                          "<reads.fa>: FASTA in, SAM out, the reference's own Read Mapping Time; its "
+                                          "unchanged serial FASTA parser (fasta.c:316, inside an omp critical section, "
+                                          "gmapper.c:339) and output.c bound it, not the device"}
+                    else:
+                        e2e_sam = {"value": None, "unit": "reads/s", "how": "failed: " + r.stderr[-300:]}
         except Exception as e:  # noqa: BLE001
-            cpu = {"value": None, "unit": "reads/s", "cores": ncores, "kind": "reference", "sample": f"failed: {e}"}
+            cpu = cpu or {"value": None, "unit": "reads/s", "cores": ncores, "kind": "reference", "sample": f"failed: {e}"}
 
     line = {
         "metric": "reads_per_sec_mapped", "value": value, "unit": "reads/s", "n_gpus": world, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": total_ms_max / a.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int16", "data": "synthetic",
-        "config": {"workload": w.desc, "reads_per_gpu_per_step": n_reads, "read_len": w.read_len,
-                   "genome_len": w.genome_len, "parallelism": f"read-sharded x{world}, replicated index",
-                   "l2": "L2 flushed (256 MB write) before every timed step; index > L2"},
+        "config": bench_config(w, n_reads, world),
         "sw_vector_gcups": vec_gcups, "sw_full_mcells_per_s": full_gcells * 1e3,
         "reads_mapped_frac": n_mapped / n_reads,
         "index_build_s": index_s,
@@ -624,8 +648,143 @@ def main():
         "gpu_launches": launches,
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "e2e_sam": e2e_sam,
     }
-    print(json.dumps(line))
+    if compact:   # the short form that goes into the `workloads` block of the default run
+        line = {"value": value, "unit": "reads/s", "ms_per_step": total_ms_max / a.steps, "steps": a.steps,
+                "reads_per_step": n_reads, "genome_len": w.genome_len, "reads_mapped_frac": n_mapped / n_reads,
+                "e2e": line["e2e"], "e2e_sam": e2e_sam, "cpu_baseline": cpu, "index_build_s": index_s,
+                "stage_ms_per_step": line["stage_ms_per_step"], "sw_vector_gcups": vec_gcups,
+                "sw_full_mcells_per_s": full_gcells * 1e3,
+                "roofline": {k: {kk: v.get(kk) for kk in ("kernel", "bound", "achieved", "peak", "unit", "frac")}
+                             for k, v in roofs.items()},
+                "dominant_stage": dominant, "gpu_launches": launches, "config": w.desc}
+    for cx in extra_ctx:
+        cx.close()
+    ctx.close()
+    return line
+
+
+def other_workloads(a, ncores):
+    """The other BASELINE.json configs next to the headline one, a few steps each (one GPU): C1, C3 at 300 Mb and at
+    hg18 size (100 k reads per step), C4 with default options and with -M mirna, C5."""
+    import copy
+    out = {}
+    legs = [("c1", "c1", 0, 0), ("c3_300mb", "c3", 300, 0), ("c3_3gb", "c3", 3000, 100_000), ("c4", "c4", 0, 0),
+            ("c4mirna", "c4mirna", 0, 0), ("c5", "c5", 0, 0)]
+    for name, key, mb, n in legs:
+        w = copy.copy(WORKLOADS[key])
+        w._genome = None
+        if mb:
+            w.resize(mb)
+        b = copy.copy(a)
+        b.steps, b.warmup, b.e2e_threads = 3, 3, 2
+        try:
+            if mb >= 3000:
+                import psutil
+                if psutil.virtual_memory().available < 40e9:
+                    raise RuntimeError("less than 40 GB of host memory free for the 3 Gb genome")
+            out[name] = measure(b, w, n or w.default_reads, 0, 1, 0, ncores, compact=True)
+        except Exception as e:  # noqa: BLE001
+            out[name] = {"value": None, "error": str(e)[-300:]}
+        w._genome = None
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--reads", type=int, default=0, help="reads per GPU per step (0 = the workload's default)")
+    ap.add_argument("--genome-mb", type=int, default=0, help="scale the synthetic genome (c3: default 300, 3000 = hg18 size)")
+    ap.add_argument("--cpu-sample", type=int, default=200_000, help="reads in the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-workloads-block", action="store_true",
+                    help="skip the compact C1 / C3 / C4 / C5 legs the default C2 run appends")
+    ap.add_argument("--e2e-threads", type=int, default=0,
+                    help="host threads (one context each) of the end-to-end leg; 0 = 4 on one GPU, 3 per GPU on several")
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    ncores = os.cpu_count() or 1
+    w = WORKLOADS[a.workload]
+    if a.genome_mb or w.key == "c3":
+        w.resize(a.genome_mb or 300)
+    n_reads = a.reads or w.default_reads
+    ref_bin = os.path.join(REF_DIR, w.binary)
+
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        if not os.path.exists(ref_bin):   # the compiled reference did not travel: time the oracle port instead
+            vals = []
+            for _ in range(max(1, min(a.steps, 2))):
+                v, sample_s = run_oracle_port(w, a.cpu_sample)
+                vals.append(v)
+            val = sum(vals) / len(vals)
+            print(json.dumps({"impl": "reference", "metric": "reads_per_sec_mapped", "value": val, "unit": "reads/s",
+                              "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": None,
+                              "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16",
+                              "data": "synthetic", "config": {"workload": w.desc},
+                              "cpu_baseline": {"value": val, "unit": "reads/s", "cores": 1, "kind": "port",
+                                               "sample": sample_s},
+                              "e2e": {"value": val, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+            return 0
+        n_cpu = min(a.cpu_sample, w.cpu_sample) & ~1
+        sample, _ = w.reads(n_cpu, 1000)
+        # the projection the timed runs load with -L is the reference's own (gmapper -S, minutes at 100 Mb, untimed),
+        # kept under /tmp for the other invocations on this box; nothing of this repo's library runs in this arm
+        cache = os.path.join(tempfile.gettempdir(), f"shrimp_ref_proj_{w.key}_{w.genome_len}")
+        os.makedirs(cache, exist_ok=True)
+        if not os.path.exists(os.path.join(cache, "proj.genome")):
+            w.write_genome_fasta(os.path.join(cache, "genome.fa"))
+            r = subprocess.run([ref_bin, *[x for x in w.args if x in ("-s", "w11", "-M", "mirna")], "-S", "proj.tmp",
+                                "genome.fa"], cwd=cache, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
+            if r.returncode != 0:
+                raise RuntimeError("reference gmapper -S failed: " + r.stderr[-500:])
+            for f in sorted(os.listdir(cache)):
+                if f.startswith("proj.tmp"):
+                    os.rename(os.path.join(cache, f), os.path.join(cache, "proj" + f[len("proj.tmp"):]))
+            os.remove(os.path.join(cache, "genome.fa"))
+        how = "projection built by the reference itself (gmapper -S)"
+        with tempfile.TemporaryDirectory() as d:
+            w.write_reads_fasta(os.path.join(d, "reads.fa"), sample)
+            prefix = os.path.join(cache, "proj")
+            for _ in range(min(a.warmup, 1)):
+                run_reference(w, d, ncores, "reads.fa", prefix)
+            secs, gc = [], []
+            for _ in range(a.steps):
+                s_, g, _ = run_reference(w, d, ncores, "reads.fa", prefix)
+                secs.append(s_)
+                gc.append(g)
+        tot = sum(secs)
+        val = n_cpu * a.steps / tot
+        sample_s = (f"{n_cpu} reads of the {w.key.upper()} workload per step, {w.binary} -N {ncores} "
+                    f"{' '.join(w.args)} -L <projection> (Read Mapping Time: FASTA parsing and SAM printing included); {how}")
+        line = {"impl": "reference", "metric": "reads_per_sec_mapped", "value": val, "unit": "reads/s",
+                "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * tot / a.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16",
+                "data": "synthetic", "config": bench_config(w, n_reads, a.gpus),
+                "sw_vector_gcups": gc[-1],
+                "cpu_baseline": {"value": val, "unit": "reads/s", "cores": ncores, "kind": "reference",
+                                 "sample": sample_s},
+                "e2e": {"value": val, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    line = measure(a, w, n_reads, rank, world, local_rank, ncores)
+    if rank == 0:
+        if world == 1 and a.workload == "c2" and not a.no_workloads_block and not a.genome_mb and not a.reads:
+            line["workloads"] = other_workloads(a, ncores)
+        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0

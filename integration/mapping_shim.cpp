@@ -64,7 +64,12 @@ static std::once_flag g_ndev_once;
 
 static thread_local shrimp_gpu_ctx *t_ctx;
 static shrimp_gpu_ctx *ctx_if_any() { return t_ctx; }
-static const bool g_hooked = ((chunk_ctx_hook = ctx_if_any), true);
+shrimp_gpu_ctx *thread_ctx();
+static void init_thread_ctx() {
+  // only once the genome is in memory and this is a mapping run (gmapper -S exits before the set-up calls)
+  if (genome_contigs != NULL && num_contigs > 0 && n_seeds > 0) thread_ctx();
+}
+static const bool g_hooked = ((chunk_ctx_hook = ctx_if_any), (chunk_init_hook = init_thread_ctx), true);
 
 static shrimp_sw_params sw_params_from_globals() {
   shrimp_sw_params sp;
@@ -88,6 +93,8 @@ static shrimp_sw_params sw_params_from_globals() {
 shrimp_gpu_ctx *thread_ctx() {
   if (t_ctx) return t_ctx;
   std::call_once(g_ndev_once, [] {
+    // every kernel of the library is loaded when the context is created (in the set-up phase), not at its first launch
+    setenv("CUDA_MODULE_LOADING", "EAGER", 0);
     g_ndev = shrimp_gpu_device_count();
     if (const char *e = getenv("SHRIMP_B200_GPUS")) g_ndev = std::min(g_ndev, std::max(1, atoi(e)));
     if (g_ndev > 64) g_ndev = 64;
@@ -337,6 +344,7 @@ static void fill_row(Batch &B, int row, const Prep &p) {
 static void run_batch(Batch &B, const std::vector<Prep> &preps) {
   const bool cs = shrimp_mode == MODE_COLOUR_SPACE;
   shrimp_gpu_ctx *ctx = thread_ctx();
+  const double t0 = omp_get_wtime();
   int max_len = 1;
   B.n_rows = 0;
   B.row_of.assign(B.n_entries, -1);
@@ -373,6 +381,9 @@ static void run_batch(Batch &B, const std::vector<Prep> &preps) {
   memset(&st, 0, sizeof(st));
   int64_t n_hits = 0, e_used = 0;
   const int n = B.n_rows;
+  const double t1 = omp_get_wtime();
+  tstats.t_prep += t1 - t0;
+  tstats.reads += (uint64_t)n;
   B.first_unp.assign((size_t)n + 1, 0);
   B.n_unp.assign((size_t)std::max(n, 1), 0);
   size_t e_cap = std::max<size_t>(B.edits.size(), std::max<size_t>(4096, (size_t)n * 2 * (size_t)max_len));
@@ -419,6 +430,7 @@ static void run_batch(Batch &B, const std::vector<Prep> &preps) {
     for (int r = 0; r < n; r++) B.first_unp[r + 1] = B.first_unp[r] + B.n_unp[r];
   }
   tstats.add(st);
+  tstats.t_device += omp_get_wtime() - t1;
 }
 
 // entries [re, re + ahead) of the chunk that are loaded; `step` entries per unit (2 in paired mode)
@@ -565,7 +577,10 @@ static void emit_unpaired(const Batch &B, int row, read_entry *re, bool save_out
   if (n <= 0) return;
   const shrimp_hit *h = &B.hits[(size_t)B.first_unp[row]];
   read_hit *rh = (read_hit *)my_malloc((size_t)n * sizeof(read_hit), &mem_mapping, "final_unpaired_hits [%s]", re->name);
+  const double t0 = omp_get_wtime();
   for (int i = 0; i < n; i++) build_hit(B, h[i], re, &rh[i]);
+  tstats.t_build += omp_get_wtime() - t0;
+  tstats.records += (uint64_t)n;
   re->final_matches += n;
 #pragma omp atomic
   total_reads_matched++;
@@ -577,7 +592,9 @@ static void emit_unpaired(const Batch &B, int row, read_entry *re, bool save_out
   } else {
     std::vector<read_hit *> ptr((size_t)n);
     for (int i = 0; i < n; i++) ptr[i] = &rh[i];
+    const double t1 = omp_get_wtime();
     read_output(re, ptr.data(), n);
+    tstats.t_output += omp_get_wtime() - t1;
     free_hits(re, rh, n);
     my_free(rh, (size_t)n * sizeof(read_hit), &mem_mapping, "final_unpaired_hits [%s]", re->name);
   }
@@ -715,7 +732,9 @@ void handle_readpair(pair_entry *pe, struct readpair_mapping_options_t *options,
   t_drop_snapshot = (total_reads_dropped + total_pairs_dropped) - t_own_drops;
 
   // OUTPUT, mapping.c:2613-2636
+  const double t_out = omp_get_wtime();
   readpair_output(pe);
+  tstats.t_output += omp_get_wtime() - t_out;
   if (aligned_reads_file != NULL && (pe->mapped || re1->mapped || re2->mapped)) {
 #pragma omp critical(aligned_reads_file)
     {

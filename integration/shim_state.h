@@ -14,7 +14,8 @@ struct ThreadStats {
   uint64_t vector_calls = 0, vector_cells = 0, vector_bypassed = 0;   /* sw-vector.c:507-509, f1-wrapper.h:110 */
   uint64_t full_calls = 0, full_cells = 0;                            /* sw-full-ls.c:237, :662 */
   uint64_t post_columns = 0;
-  uint64_t batches = 0, mispredicted = 0;
+  uint64_t batches = 0, mispredicted = 0, reads = 0, records = 0;
+  double t_prep = 0, t_device = 0, t_build = 0, t_output = 0;   /* host seconds of this thread, SHRIMP_B200_VERBOSE */
   void add(const shrimp_map_stats &s) {
     vector_calls += s.vector_calls;
     vector_cells += s.vector_cells;
@@ -31,6 +32,11 @@ shrimp_gpu_ctx *thread_ctx();
 /* set by mapping_shim.cpp: the calling thread's chunk-path context if it exists (NULL otherwise), so that the
  * *_stats functions of sw_shims.cpp can read its device stage times; sw_shims.cpp also links on its own */
 extern shrimp_gpu_ctx *(*chunk_ctx_hook)();
+/* set by mapping_shim.cpp: creates the calling thread's chunk-path context.  gmapper.c calls sw_full_{ls,cs}_setup
+ * from every -N thread after load_genome and before the mapping clock starts (gmapper.c:2907-2965), which is where
+ * the reference allocates its per-thread DP state; the device state (genome upload, projection build) is set up at the
+ * same point, so that "Read Mapping Time" (gmapper.c:3015-3021) covers mapping only, as it does in the reference. */
+extern void (*chunk_init_hook)();
 
 }  // namespace shrimp_shim
 

@@ -36,6 +36,7 @@ namespace shrimp_shim {
 
 thread_local ThreadStats tstats;
 shrimp_gpu_ctx *(*chunk_ctx_hook)() = nullptr;
+void (*chunk_init_hook)() = nullptr;
 
 struct CallState {
   shrimp_gpu_ctx *ctx = nullptr;
@@ -122,6 +123,12 @@ int sw_vector_setup(int dblen, int qrlen, int a_gap_open, int a_gap_ext, int b_g
 
 int sw_vector_cleanup(void) {   // sw-vector.c:379
   S.vector_set = false;
+  if (getenv("SHRIMP_B200_VERBOSE") && tstats.batches)
+    fprintf(stderr,
+            "[gmapper-b200] thread: %llu reads in %llu device batches (%llu re-mapped alone), %llu records; host seconds: "
+            "look-ahead %.3f, device calls %.3f, record rebuild %.3f, output.c %.3f\n",
+            (unsigned long long)tstats.reads, (unsigned long long)tstats.batches, (unsigned long long)tstats.mispredicted,
+            (unsigned long long)tstats.records, tstats.t_prep, tstats.t_device, tstats.t_build, tstats.t_output);
   return 0;
 }
 
@@ -210,6 +217,7 @@ int sw_full_ls_setup(int dblen, int qrlen, int a_gap_open, int a_gap_ext, int b_
   S.p.anchor_width = anchor_width;
   if (reset_stats) S.ls_invocs = 0;
   S.full_ls_set = true;
+  if (chunk_init_hook) chunk_init_hook();
   return 0;
 }
 
@@ -229,6 +237,7 @@ int sw_full_cs_setup(int dblen, int qrlen, int a_gap_open, int a_gap_ext, int b_
   S.p.indel_taboo_len = indel_taboo_len;
   if (reset_stats) S.cs_invocs = 0;
   S.full_cs_set = true;
+  if (chunk_init_hook) chunk_init_hook();
   return 0;
 }
 

@@ -42,7 +42,8 @@ __device__ __forceinline__ void make_full_task(const FullBuildParams &P, int r, 
   uint32_t g_off = h.g_off;
   int ax = h.ax, ay = h.ay;
   int gen_st = 0;
-  if (st != 0) {  // reverse_hit: the read is always aligned in its input orientation
+  const int in_st = P.M.rev_mate[r & 1];   // re->input_strand
+  if (st != in_st) {  // reverse_hit: the read is always aligned in its input orientation
     g_off = clen - h.g_off - (uint32_t)h.w_len;
     ax = -h.ax + (h.w_len - 1) - (h.alen - 1) - (h.awidth - 1);
     ay = -h.ay + (rl - 1) - (h.alen - 1) + (h.awidth - 1);
@@ -52,7 +53,7 @@ __device__ __forceinline__ void make_full_task(const FullBuildParams &P, int r, 
   T.goff_contig = g_off;
   T.glen = h.w_len;
   T.rlen = rl;
-  T.ridx = 2 * r;
+  T.ridx = 2 * r + in_st;
   T.ax = ax;
   T.ay = ay;
   T.alen = h.alen;

@@ -324,6 +324,8 @@ static int map_pairs_impl(shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, cons
   C.mp_mode = !mp->use_regions ? 0 : (pmm == 4 && !pp->half_paired) ? 1 : (pmm == 3 && pp->half_paired) ? 2 :
               (pmm == 3 && !pp->half_paired) ? 3 : 0;
   C.pair_mode = pp->pair_mode;
+  C.M.rev_mate[0] = (pp->pair_mode == 2 || pp->pair_mode == 4) ? 1 : 0;   // pair_reverse, gmapper-defaults.h:184-191
+  C.M.rev_mate[1] = (pp->pair_mode == 2 || pp->pair_mode == 3) ? 1 : 0;
   C.min_insert = pp->min_insert_size;
   C.max_insert = pp->max_insert_size;
   const int n_reads = C.n_reads;

@@ -69,7 +69,8 @@ __global__ void build_vec_tasks_kernel(const TaskBuildParams P) {
   const bool cs = P.M.colour_space != 0;
   // orientation used by pass 1: letter space always scores read strand st on the forward genome;
   // colour space scores the forward read and flips strand-1 windows onto the rc genome.
-  const int ori = (cs && st == 1) ? 1 : 0;
+  const int in_st = live ? P.M.rev_mate[r & 1] : 0;   // re->input_strand (mapping.c:1303)
+  const int ori = (cs && st != in_st) ? 1 : 0;
   uint32_t n_elig = 0;
   unsigned long long elig_cells = 0;
   for (uint32_t k = 0; k < rg.y; k++) {
@@ -118,7 +119,7 @@ __global__ void build_vec_tasks_kernel(const TaskBuildParams P) {
     const uint32_t g = ori ? coff + (P.G.contig_len[h.cn] - h.g_off - (uint32_t)h.w_len) : coff + h.g_off;
     P.goff[ori][t] = g;
     P.glen[ori][t] = h.w_len;
-    P.ridx[ori][t] = cs ? (int32_t)(2 * r) : (int32_t)rs;
+    P.ridx[ori][t] = cs ? (int32_t)(2 * r + in_st) : (int32_t)rs;
     P.rlen[ori][t] = rl;
     if (cs) P.initbp_out[ori][t] = P.initbp[r];
     P.out[ori][t] = hi;
@@ -156,7 +157,7 @@ __global__ void pass1_replay_kernel(const Pass1Params P) {
   unsigned long long cells = 0;
   for (int st = 0; st < 2; st++) {
     const uint2 rg = P.rs_range[2 * r + st];
-    const int ori = (cs && st == 1) ? 1 : 0;
+    const int ori = (cs && st != M.rev_mate[r & 1]) ? 1 : 0;
     int last_good_cn = -1;
     unsigned int last_good_g_off = 0;
     for (uint32_t k = 0; k < rg.y; k++) {

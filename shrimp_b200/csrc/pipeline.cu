@@ -47,11 +47,15 @@ __device__ __forceinline__ void put4_dev(uint32_t *a, int i, uint32_t v) {
 // reads_all row 2r = read r as given, row 2r+1 = its reverse complement
 // (reverse_complement_read_ls util.c:541-598; reverse_complement_read_cs util.c:601-618)
 __global__ void revcomp_reads_kernel(const uint32_t *in, uint32_t *out, int stride, int n_reads, const int32_t *read_len,
-                                     const int8_t *initbp, int colour_space) {
+                                     const int8_t *initbp, int colour_space, int rev_even, int rev_odd) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n_reads) return;
   const uint32_t *src = in + (size_t)r * stride;
   uint32_t *f = out + (size_t)(2 * r) * stride, *rc = f + stride;
+  if ((r & 1) ? rev_odd : rev_even) {  // read_reverse: the two strands trade places
+    rc = f;
+    f = rc + stride;
+  }
   for (int w = 0; w < stride; w++) {
     f[w] = src[w];
     rc[w] = 0;
@@ -503,7 +507,8 @@ int chunk_scan(Chunk &C) {
   ScopedStage ss(ctx, ST_SCAN);
   revcomp_reads_kernel<<<(n_reads + 127) / 128, 128, 0, st>>>(pl->d_in.as<uint32_t>(), pl->d_reads.as<uint32_t>(),
                                                               stride, n_reads, pl->d_read_len.as<int32_t>(),
-                                                              C.cs ? pl->d_initbp.as<int8_t>() : nullptr, C.cs);
+                                                              C.cs ? pl->d_initbp.as<int8_t>() : nullptr, C.cs,
+                                                              C.M.rev_mate[0], C.M.rev_mate[1]);
   SH_CUDA(cudaGetLastError());
   SH_LAUNCHED(ctx, ST_SCAN);
   // expected number of list entries per read strand: K(r) * L / 4^W
@@ -1436,6 +1441,8 @@ static int map_impl(shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, int n_read
     return SHRIMP_E_ARG;
   }
   Chunk C;
+  const bool timing = getenv("SHRIMP_TIMING") != nullptr;
+  const double t_b0 = omp_get_wtime();
   SH_TRY(chunk_begin(C, ctx, mp, n_reads, reads, stride, read_len, initbp, resident, who));
   n_reads = C.n_reads;
   read_len = C.read_len;
@@ -1452,8 +1459,11 @@ static int map_impl(shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, int n_read
   Pipeline *pl = C.pl;
   cudaStream_t st = ctx->stream;
   pl->d2h_bytes = 0;
+  const double t_b1 = omp_get_wtime();
   SH_TRY(chunk_scan(C));
+  const double t_b2 = omp_get_wtime();
   SH_TRY(chunk_vector(C));
+  const double t_b3 = omp_get_wtime();
 
   // ---- pass-1 replay + top-k -------------------------------------------------------------------
   const int NT = mp->num_tmp_outputs;
@@ -1519,7 +1529,6 @@ static int map_impl(shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, int n_read
     return SHRIMP_OK;
   }
   // ---- results back to the host + host stage: read_pass2 after the DP ----------------------------
-  const bool timing = getenv("SHRIMP_TIMING") != nullptr;
   const double t_f0 = omp_get_wtime();
   SH_TRY(chunk_fetch_full(C, n_slots, true));
   const double t_f1 = omp_get_wtime();
@@ -1533,8 +1542,9 @@ static int map_impl(shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, int n_read
   O.edits_cap = edits_cap;
   SH_TRY(host_pass2_all(C, NSEL, mp->sw_full_threshold, O, n_hits_per_read));
   if (timing)
-    fprintf(stderr, "[shrimp_b200] map_reads: n_slots %d, D2H %.2f ms (%.1f MB), host pass 2 %.2f ms\n", n_slots,
-            1e3 * (t_f1 - t_f0), pl->d2h_bytes / 1e6, 1e3 * (omp_get_wtime() - t_f1));
+    fprintf(stderr, "[shrimp_b200] map_reads: %d reads, n_slots %d: begin %.2f, scan %.2f, vector %.2f, pass 1 + full SW %.2f, "
+            "D2H %.2f ms (%.1f MB), host pass 2 %.2f ms\n", n_reads, n_slots, 1e3 * (t_b1 - t_b0), 1e3 * (t_b2 - t_b1),
+            1e3 * (t_b3 - t_b2), 1e3 * (t_f0 - t_b3), 1e3 * (t_f1 - t_f0), pl->d2h_bytes / 1e6, 1e3 * (omp_get_wtime() - t_f1));
   *n_hits = O.n_out;
   if (edits_used) *edits_used = O.e_used;
   if (stats) {

@@ -34,6 +34,10 @@ struct MapParamsDev {
   double overlap_thr, overlap_frac;      // window_overlap
   int Gflag, Tflag;
   int anchor_width;
+  // pair modes that reverse a mate before mapping (read_reverse gmapper.c:174-187, pair_reverse
+  // gmapper-defaults.h:184-191): [0] even reads (first mates), [1] odd reads.  A reversed read is mapped with its
+  // strands swapped (row 2r = the reverse complement, row 2r + 1 = the read as given) and its input strand is 1.
+  int rev_mate[2];
 };
 
 // abs_or_pct (util.h:48-53) with the division already done on the host: x<0 ? -x : base*(x/100.0)
