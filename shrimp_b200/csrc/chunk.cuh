@@ -87,6 +87,7 @@ __device__ __forceinline__ void make_full_task(const FullBuildParams &P, int r, 
 struct Pipeline {
   DevBuf d_in, d_reads, d_read_len, d_initbp, d_hits, d_rs_range, d_counters, d_overflow, d_overflow2, d_scan_slab, d_tie_ent, d_tie_order, d_tie_rec, d_prof, d_mp_tab, d_mp_epoch, d_xover, d_quals, d_fqual, d_pstab, d_gmtab, d_scratch;
   DevBuf d_task[2], d_vtrue[2], d_slot, d_writer, d_sel, d_nsel;
+  DevBuf d_pk, d_pk_info, d_pk_res, d_pk_pool;
   DevBuf d_ftasks, d_finfo, d_fresults, d_frow, d_fbp[RING_CLASSES + 2], d_fops, d_taskoff, d_scan_tmp, d_perm;
   HostBuf h_info, h_results, h_ops, h_nsel, h_hits, h_range, h_xover, h_fqual;
   bool gm_tab_ready = false;
@@ -136,6 +137,9 @@ struct Chunk {
   int mp_mode = 0, pair_mode = 0, min_insert = 0, max_insert = 0;
   size_t ops_stride = 0;
   bool post_sw = false;                // colour space with mapping qualities: post_sw runs after the full SW
+  bool packed = false;                 // the host buffers hold the packed records of chunk_fetch_full_packed
+  int packed_slots = 0;
+  int64_t packed_kept = 0;
 };
 
 // stages (pipeline.cu)
@@ -148,6 +152,7 @@ void host_score_hit(const Chunk &C, int idx, HostHit &h);
 int chunk_full_tasks_unpaired(Chunk &C, double full_thr, int *n_slots);
 int chunk_run_full(Chunk &C, int n_slots);
 int chunk_fetch_full(Chunk &C, int n_slots, bool with_nsel);
+int chunk_fetch_full_packed(Chunk &C, int n_slots);
 void chunk_stats(const Chunk &C, const uint32_t *h_cnt, shrimp_map_stats *stats);
 // read_pass2 after the DP (mapping.c:1644-1722) for one read: tasks [task_base, task_base + n1) -> out
 struct HostOut {

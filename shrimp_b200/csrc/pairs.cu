@@ -558,7 +558,7 @@ static int map_pairs_impl(shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, cons
     int n_slots_b = 0;
     SH_TRY(chunk_full_tasks_unpaired(C, mp->sw_full_threshold, &n_slots_b));
     SH_TRY(chunk_run_full(C, n_slots_b));
-    SH_TRY(chunk_fetch_full(C, n_slots_b, true));
+    SH_TRY(chunk_fetch_full_packed(C, n_slots_b));
     const int32_t *NSEL = pl->h_nsel.as<int32_t>();
     SH_TRY(host_pass2_all(C, NSEL, mp->sw_full_threshold, O, n_unpaired_per_read));
   }

@@ -146,6 +146,52 @@ __global__ void group_full_tasks_kernel(const uint32_t *key, int n, uint32_t *ke
   perm[base + (uint32_t)__popc(peers & ((1u << lane) - 1u))] = t;
 }
 
+// ---- packed fetch: only the alignments that exist travel to the host ---------------------------------------------
+// A full-SW task that stayed below its threshold has score 0 and no edit script (sw-full-cs.c:1216-1226;
+// mapping.c:390-398 in letter space): read_pass2 drops it whatever else happens.  The tasks that have an alignment
+// are compacted on the device, in task order -- SelInfo, FullResult, and one byte record each (edit script, then the
+// base qualities of post_sw) at 4-byte granularity -- so that the D2H copy carries what the host stage looks at.
+__global__ void pack_flag_kernel(const FullResult *res, const SelInfo *info, const int32_t *read_len, int n, int post_sw,
+                                 int cs, uint32_t *keep, uint32_t *units, unsigned long long *vcells) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long cells = 0;
+  if (i < n) {
+    const FullResult r = res[i];
+    const bool k = r.score > 0 || r.ops_len > 0;
+    keep[i] = k ? 1u : 0u;
+    units[i] = k ? (uint32_t)(r.ops_len + (post_sw ? r.rmapped : 0) + 3) >> 2 : 0u;
+    if (!cs) cells = (unsigned long long)info[i].w_len * (unsigned long long)read_len[info[i].read_idx];
+  }
+  if (!cs) {   // the sw_vector re-run of hit_run_full_sw (mapping.c:386) is counted for every task
+    for (int o = 16; o > 0; o >>= 1) cells += __shfl_xor_sync(0xffffffffu, cells, o);
+    if ((threadIdx.x & 31) == 0 && cells) atomicAdd(vcells, cells);
+  }
+}
+
+__global__ void pack_scatter_kernel(const FullResult *res, const SelInfo *info, const uint8_t *ops, size_t ops_stride,
+                                    const uint8_t *fqual, int max_rl, const uint32_t *keep_pos, const uint32_t *unit_off,
+                                    int n, int post_sw, SelInfo *info2, FullResult *res2, uint8_t *pool) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || keep_pos[i + 1] == keep_pos[i]) return;
+  const uint32_t p = keep_pos[i];
+  FullResult r = res[i];
+  const uint8_t *src = ops + ops_stride * (size_t)i + r.ops_start;
+  uint8_t *dst = pool + 4 * (size_t)unit_off[i];
+  for (int b = 0; b < r.ops_len; b++) dst[b] = src[b];
+  if (post_sw) {
+    const uint8_t *q = fqual + (size_t)max_rl * (size_t)i;
+    for (int b = 0; b < r.rmapped; b++) dst[r.ops_len + b] = q[b];
+  }
+  r.ops_start = (int32_t)unit_off[i];   // packed: the record's offset in the pool, in units of 4 bytes
+  info2[p] = info[i];
+  res2[p] = r;
+}
+
+__global__ void pack_counts_kernel(const int32_t *task_off, const uint32_t *keep_pos, int n_reads, int32_t *n_kept) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n_reads) n_kept[r] = (int32_t)(keep_pos[task_off[r + 1]] - keep_pos[task_off[r]]);
+}
+
 void free_pipeline(shrimp_gpu_ctx *ctx) {
   Pipeline *p = (Pipeline *)ctx->pipeline;
   if (!p) return;
@@ -154,7 +200,7 @@ void free_pipeline(shrimp_gpu_ctx *ctx) {
                     &p->d_slot, &p->d_writer, &p->d_sel, &p->d_nsel, &p->d_ftasks, &p->d_finfo, &p->d_fresults,
                     &p->d_frow, &p->d_fbp[0], &p->d_fbp[1], &p->d_fbp[2], &p->d_fbp[3], &p->d_fbp[4], &p->d_fbp[5], &p->d_fops,
                     &p->d_taskoff, &p->d_scan_tmp, &p->d_perm, &p->d_pair_min, &p->d_pair_max, &p->d_saved, &p->d_pairsel,
-                    &p->d_npairsel, &p->d_taskof, &p->d_pairoff};
+                    &p->d_npairsel, &p->d_taskof, &p->d_pairoff, &p->d_pk, &p->d_pk_info, &p->d_pk_res, &p->d_pk_pool};
   for (DevBuf *b : bufs) b->release();
   HostBuf *hb[] = {&p->h_info, &p->h_results, &p->h_ops, &p->h_nsel, &p->h_hits, &p->h_range, &p->h_xover, &p->h_fqual,
                    &p->h_pairsel, &p->h_npairsel, &p->h_saved};
@@ -559,6 +605,10 @@ int chunk_scan(Chunk &C) {
   const int big_k_cap = std::max(32, std::max(K_max, K_slots));
   int cta_bm_log2 = 5, cta_n_part = 1, cta_cap = 512, cta_win = 1024;
   bool cta_hashed = false;
+  // cursor walk over the index lists (scan.cu) unless the mate-pair region tables are in play; SHRIMP_SCAN_WALK=0
+  // brings the staged-window passes back (test hook)
+  bool cta_walk = !C.mp_mode;
+  if (const char *e = getenv("SHRIMP_SCAN_WALK")) cta_walk = cta_walk && atoi(e) != 0;
   {
     const double n_regions = L_total / (double)(1u << C.M.region_bits) + 2.0;
     if (filt && C.mp_mode) {
@@ -601,6 +651,7 @@ int chunk_scan(Chunk &C) {
     while (cta_win < 4096 && cta_win < 0.4 * est / cta_n_part) cta_win <<= 1;
     if (est / cta_n_part > 6000.0) cta_win = 8192;   // hg18 scale: a partition in one window, staged once for both passes
     if (const char *e = getenv("SHRIMP_SCAN_WIN")) cta_win = std::max(64, atoi(e));  // test hook: several windows
+    if (cta_walk) cta_win = 16;   // the cursor walk stages nothing
     if (const char *e = getenv("SHRIMP_SCAN_CTA_CAP")) cta_cap = std::max(32, atoi(e));  // test hook: global slabs
     while (cta_cap > 256 && scan_cta_smem_bytes(cta_cap, max_rl, big_k_cap, cta_bm_log2, cta_n_part, cta_win, false) > 200 * 1024)
       cta_cap >>= 1;
@@ -695,6 +746,11 @@ int chunk_scan(Chunk &C) {
       // lanes per index list: a warp streams 4 positions per lane and step
       double avg_list = est / std::max(1, K_max);
       P.lanes_per_list_log2 = avg_list > 64 ? 5 : avg_list > 32 ? 4 : avg_list > 12 ? 3 : 2;
+      P.walk = cta_walk ? 1 : 0;
+      if (cta_walk) {   // lanes per list by the entries a list has per tile; 8 lanes read one 32-byte sector
+        const double per_tile = avg_list / std::max(1, (filt && !cta_hashed) ? cta_n_part : 1);
+        P.lanes_per_list_log2 = per_tile > 96 ? 5 : per_tile > 40 ? 4 : per_tile > 5 ? 3 : 2;
+      }
       if (const char *e = getenv("SHRIMP_SCAN_LANES_LOG2")) P.lanes_per_list_log2 = std::max(0, std::min(5, atoi(e)));
       if (pl->tie_cap == 0) pl->tie_cap = (uint32_t)std::max<long long>(1 << 20, (long long)n_reads * 2 * 32);
       SH_TRY(pl->d_tie_ent.ensure((size_t)pl->tie_cap * 8));
@@ -859,7 +915,14 @@ int chunk_scan(Chunk &C) {
         set_error("seed scan: hit buffer overflow");
         return SHRIMP_E_NOMEM;
       }
-      pl->hits_cap *= 4;
+      // hits_used kept counting past the capacity: it is the exact demand of this chunk (unless it wrapped)
+      const unsigned long long need = h3[0] > pl->hits_cap ? (unsigned long long)h3[0] + h3[0] / 16 + 1024
+                                                           : (unsigned long long)pl->hits_cap * 4;
+      if (need > 0xfffffff0ull) {
+        set_error("seed scan: more than 2^32 candidate windows in one chunk; map fewer reads per call");
+        return SHRIMP_E_RANGE;
+      }
+      pl->hits_cap = (uint32_t)need;
       continue;
     }
     C.hits_used = h3[0];
@@ -1158,6 +1221,77 @@ int chunk_fetch_full(Chunk &C, int n_slots, bool with_nsel) {
   return SHRIMP_OK;
 }
 
+// Results of the tasks [0, n_slots) of the unpaired flow (tasks of read r at d_taskoff[r] ..): compacted on the device
+// (see pack_flag_kernel), then to the host.  h_nsel receives the number of alignments per read, h_info / h_results /
+// h_ops the packed records; C.packed tells the host stage how to find an edit script.
+int chunk_fetch_full_packed(Chunk &C, int n_slots) {
+  Pipeline *pl = C.pl;
+  shrimp_gpu_ctx *ctx = C.ctx;
+  cudaStream_t st = ctx->stream;
+  const int n_reads = C.n_reads;
+  const size_t n1 = (size_t)n_slots + 1;
+  SH_TRY(pl->d_pk.ensure(n1 * 4 * 4 + (size_t)n_reads * 4));
+  uint32_t *keep = pl->d_pk.as<uint32_t>(), *units = keep + n1, *keep_pos = units + n1, *unit_off = keep_pos + n1;
+  int32_t *d_nkept = (int32_t *)(unit_off + n1);
+  SH_TRY(pl->h_nsel.ensure((size_t)n_reads * 4 + 64 * 4));
+  uint32_t *h_cnt = (uint32_t *)((char *)pl->h_nsel.p + (size_t)n_reads * 4);
+  uint32_t tot[2] = {0, 0};
+  {
+    ScopedStage ss(ctx, ST_OTHER);
+    SH_CUDA(cudaMemsetAsync(C.cnt + 52, 0, 8, st));
+    SH_CUDA(cudaMemsetAsync(keep + n_slots, 0, 4, st));
+    SH_CUDA(cudaMemsetAsync(units + n_slots, 0, 4, st));
+    if (n_slots > 0) {
+      pack_flag_kernel<<<(n_slots + 255) / 256, 256, 0, st>>>(pl->d_fresults.as<FullResult>(), pl->d_finfo.as<SelInfo>(),
+                                                              pl->d_read_len.as<int32_t>(), n_slots, C.post_sw ? 1 : 0,
+                                                              C.cs ? 1 : 0, keep, units, (unsigned long long *)(C.cnt + 52));
+      SH_CUDA(cudaGetLastError());
+      SH_LAUNCHED(ctx, ST_OTHER);
+    }
+    size_t tmp_bytes = 0;
+    SH_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, keep, keep_pos, (int)n1, st));
+    SH_TRY(pl->d_scan_tmp.ensure(tmp_bytes));
+    SH_CUDA(cub::DeviceScan::ExclusiveSum(pl->d_scan_tmp.p, tmp_bytes, keep, keep_pos, (int)n1, st));
+    SH_CUDA(cub::DeviceScan::ExclusiveSum(pl->d_scan_tmp.p, tmp_bytes, units, unit_off, (int)n1, st));
+    ctx->launches += 2;
+    SH_CUDA(cudaMemcpyAsync(&tot[0], keep_pos + n_slots, 4, cudaMemcpyDeviceToHost, st));
+    SH_CUDA(cudaMemcpyAsync(&tot[1], unit_off + n_slots, 4, cudaMemcpyDeviceToHost, st));
+    SH_CUDA(cudaStreamSynchronize(st));
+  }
+  const size_t n_kept = tot[0], pool_bytes = 4 * (size_t)tot[1];
+  SH_TRY(pl->d_pk_info.ensure(std::max<size_t>(n_kept, 1) * sizeof(SelInfo)));
+  SH_TRY(pl->d_pk_res.ensure(std::max<size_t>(n_kept, 1) * sizeof(FullResult)));
+  SH_TRY(pl->d_pk_pool.ensure(std::max<size_t>(pool_bytes, 4)));
+  SH_TRY(pl->h_info.ensure(std::max<size_t>(n_kept, 1) * sizeof(SelInfo)));
+  SH_TRY(pl->h_results.ensure(std::max<size_t>(n_kept, 1) * sizeof(FullResult)));
+  SH_TRY(pl->h_ops.ensure(std::max<size_t>(pool_bytes, 4)));
+  {
+    ScopedStage ss(ctx, ST_OTHER);
+    if (n_slots > 0) {
+      pack_scatter_kernel<<<(n_slots + 127) / 128, 128, 0, st>>>(
+          pl->d_fresults.as<FullResult>(), pl->d_finfo.as<SelInfo>(), pl->d_fops.as<uint8_t>(), C.ops_stride,
+          C.post_sw ? pl->d_fqual.as<uint8_t>() : nullptr, C.max_rl, keep_pos, unit_off, n_slots, C.post_sw ? 1 : 0,
+          pl->d_pk_info.as<SelInfo>(), pl->d_pk_res.as<FullResult>(), pl->d_pk_pool.as<uint8_t>());
+      SH_CUDA(cudaGetLastError());
+      SH_LAUNCHED(ctx, ST_OTHER);
+    }
+    pack_counts_kernel<<<(n_reads + 255) / 256, 256, 0, st>>>(pl->d_taskoff.as<int32_t>(), keep_pos, n_reads, d_nkept);
+    SH_CUDA(cudaGetLastError());
+    SH_LAUNCHED(ctx, ST_OTHER);
+  }
+  SH_CUDA(cudaMemcpyAsync(pl->h_info.p, pl->d_pk_info.p, n_kept * sizeof(SelInfo), cudaMemcpyDeviceToHost, st));
+  SH_CUDA(cudaMemcpyAsync(pl->h_results.p, pl->d_pk_res.p, n_kept * sizeof(FullResult), cudaMemcpyDeviceToHost, st));
+  SH_CUDA(cudaMemcpyAsync(pl->h_ops.p, pl->d_pk_pool.p, pool_bytes, cudaMemcpyDeviceToHost, st));
+  SH_CUDA(cudaMemcpyAsync(pl->h_nsel.p, d_nkept, (size_t)n_reads * 4, cudaMemcpyDeviceToHost, st));
+  SH_CUDA(cudaMemcpyAsync(h_cnt, C.cnt, 64 * 4, cudaMemcpyDeviceToHost, st));
+  SH_CUDA(cudaStreamSynchronize(st));
+  pl->d2h_bytes += n_kept * (sizeof(SelInfo) + sizeof(FullResult)) + pool_bytes + (size_t)n_reads * 4 + 64 * 4 + 8;
+  C.packed = true;
+  C.packed_slots = n_slots;
+  C.packed_kept = (int64_t)n_kept;
+  return SHRIMP_OK;
+}
+
 void chunk_stats(const Chunk &C, const uint32_t *hc, shrimp_map_stats *stats) {
   if (!stats) return;
   stats->heap_replays = hc[8 + 0];
@@ -1235,7 +1369,7 @@ void host_fill_hit(const Chunk &C, const HostHit &h, int r, HostOut &O) {
   o.reserved = 0;
   const uint8_t *OPS = C.pl->h_ops.as<uint8_t>();
   if (O.edits && O.e_used + h.res.ops_len <= O.edits_cap)
-    memcpy(O.edits + O.e_used, OPS + C.ops_stride * (size_t)h.task_idx + h.res.ops_start, (size_t)h.res.ops_len);
+    memcpy(O.edits + O.e_used, OPS + C.ops_stride * (size_t)h.task_idx + h.res.ops_start, (size_t)h.res.ops_len);   // never packed: pairs
   else if (h.res.ops_len > 0)
     O.edits_short = true;
   O.e_used += h.res.ops_len;
@@ -1261,11 +1395,11 @@ static int host_pass2_select(const Chunk &C, int r, int n1, int task_base, doubl
   for (int k = 0; k < n1; k++) {
     HostHit &h = hh[k];
     host_score_hit(C, task_base + k, h);
-    if (!C.cs) {
+    if (!C.cs && !C.packed) {
       vcalls++;
       vcells += (uint64_t)h.info.w_len * (uint64_t)C.read_len[r];
     }
-    if (h.res.score > 0 || h.res.ops_len > 0) full_calls++;
+    if (!C.packed && (h.res.score > 0 || h.res.ops_len > 0)) full_calls++;
     h.pass2_key = full_thr < 0 ? h.score_full : (int)h.pct_score_full;
     const double thr = full_thr < 0 ? -full_thr : h.info.score_max * (full_thr / 100.0);
     if (h.score_full >= thr) h2[n2++] = &h;
@@ -1356,6 +1490,14 @@ int host_pass2_all(const Chunk &C, const int32_t *n_sel, double full_thr, HostOu
     O.pass2_vector_calls += vc[t];
     O.pass2_vector_cells += vl[t];
   }
+  if (C.packed) {   // counted on the device over every task, kept or not (pack_flag_kernel)
+    const uint32_t *hc = (const uint32_t *)((const char *)C.pl->h_nsel.p + (size_t)n_reads * 4);
+    O.full_calls += (uint64_t)C.packed_kept;
+    if (!C.cs) {
+      O.pass2_vector_calls += (uint64_t)C.packed_slots;
+      O.pass2_vector_cells += *(const unsigned long long *)(hc + 52);
+    }
+  }
   const int64_t hit_base = O.n_out, edit_base = O.e_used;
   if (hit_base + nh[T] > O.hits_cap) O.hits_short = true;
   if (O.edits && edit_base + ne[T] > O.edits_cap) O.edits_short = true;
@@ -1404,10 +1546,14 @@ int host_pass2_all(const Chunk &C, const int32_t *n_sel, double full_thr, HostOu
         o.st = info.st;
         o.score_window_gen = info.wg;
         o.reserved = 0;
-        if (fill_edits) memcpy(O.edits + eo, OPS + C.ops_stride * (size_t)kr.task_idx + res.ops_start, (size_t)res.ops_len);
+        const uint8_t *rec = C.packed ? OPS + 4 * (size_t)(uint32_t)res.ops_start
+                                      : OPS + C.ops_stride * (size_t)kr.task_idx + res.ops_start;
+        if (fill_edits) memcpy(O.edits + eo, rec, (size_t)res.ops_len);
         eo += res.ops_len;
         if (C.post_sw) {   // sfrp->qual right after the edit script
-          if (fill_edits) memcpy(O.edits + eo, FQ + (size_t)C.max_rl * (size_t)kr.task_idx, (size_t)res.rmapped);
+          if (fill_edits)
+            memcpy(O.edits + eo, C.packed ? rec + res.ops_len : FQ + (size_t)C.max_rl * (size_t)kr.task_idx,
+                   (size_t)res.rmapped);
           eo += res.rmapped;
         }
       }
@@ -1530,7 +1676,7 @@ static int map_impl(shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, int n_read
   }
   // ---- results back to the host + host stage: read_pass2 after the DP ----------------------------
   const double t_f0 = omp_get_wtime();
-  SH_TRY(chunk_fetch_full(C, n_slots, true));
+  SH_TRY(chunk_fetch_full_packed(C, n_slots));
   const double t_f1 = omp_get_wtime();
   const uint32_t *h_cnt = (const uint32_t *)((char *)pl->h_nsel.p + (size_t)n_reads * 4);
   const int32_t *NSEL = pl->h_nsel.as<int32_t>();

@@ -1061,6 +1061,103 @@ __global__ void __launch_bounds__(SCAN_CTA_MAX_THREADS, 2) scan_cta_kernel(const
     const uint32_t total = s_total;
     if (total == 0) continue;
     PROF_MARK(1);
+    if (P.walk && !mp) {
+      // ---- 2./3. cursor walk: g lanes per index list step through it in ascending order, tile by tile (a tile = the
+      // 2^bm_log2 regions one pair of exact bitmaps covers; one tile with hashed bitmaps or without a region filter).
+      // Pass A marks the regions of the tile's entries, pass B walks the same entries again (L1 / L2) and keeps those of
+      // regions marked twice; the cursor of every list then moves past the tile.  No staging buffer, no cut search:
+      // the lists ascend, so the entries of a tile are the next ones below the tile's end.
+      for (int kk = tid; kk < K; kk += nthr) kA[kk] = 0u;
+      const int n_tiles = (filt && !hashed) ? n_part : 1;
+      for (int part = 0; part < n_tiles; part++) {
+        const uint32_t R0 = (uint32_t)part << P.bm_log2;
+        const uint32_t Rlast = R0 + ((1u << P.bm_log2) - 1u);
+        const unsigned long long pend64 = (unsigned long long)(part + 1) << (P.bm_log2 + M.region_bits);
+        const bool last_tile = part == n_tiles - 1 || pend64 > 0xffffffffull;
+        const uint32_t pend = last_tile ? 0xffffffffu : (uint32_t)pend64;
+        if (filt)
+          for (int w = tid; w < bm_words; w += nthr) {
+            bm1[w] = 0u;
+            bm2[w] = 0u;
+          }
+        __syncthreads();
+        for (int pass = filt ? 0 : 1; pass < 2; pass++) {
+          for (int k0 = wid * lpw; k0 < K; k0 += nwarps * lpw) {   // warp-uniform: lpw lists per warp and step
+            const int kk = k0 + (lane >> glog);
+            const bool have = kk < K;
+            uint32_t c = 0, len = 0, slot = 0;
+            const uint32_t *p = nullptr;
+            if (have) {
+              int sn = 0;
+              while (kk >= kbase[sn + 1]) sn++;
+              c = kA[kk] + (uint32_t)gl;
+              len = klen[kk];
+              p = P.I.pos[sn] + kst[kk];
+              slot = (uint32_t)(sn * max_n_kmers + (kk - kbase[sn]));
+            }
+            uint32_t done = 0;
+            // two entries per lane in flight
+            uint32_t x0 = c < len ? __ldg(p + c) : 0u;
+            for (;;) {
+              const uint32_t cn = c + (uint32_t)g;
+              const uint32_t x1 = cn < len ? __ldg(p + cn) : 0u;
+              const bool act = c < len && (last_tile || x0 < pend);
+              if (!__any_sync(0xffffffffu, act)) break;
+              const uint32_t x = x0;
+              if (pass == 0) {
+                if (act) {
+                  const uint32_t region = x >> M.region_bits;
+                  const uint32_t idx = hashed ? region_hash(region, P.bm_log2) : region - R0;
+                  const uint32_t bit = 1u << (idx & 31);
+                  const uint32_t old = atomicOr(&bm1[idx >> 5], bit);
+                  if (old & bit) atomicOr(&bm2[idx >> 5], bit);
+                  if ((x & rmask) < (uint32_t)M.region_overlap && (hashed ? region > 0 : idx > 0)) {
+                    const uint32_t idx2 = hashed ? region_hash(region - 1, P.bm_log2) : idx - 1;
+                    const uint32_t bit2 = 1u << (idx2 & 31);
+                    const uint32_t old2 = atomicOr(&bm1[idx2 >> 5], bit2);
+                    if (old2 & bit2) atomicOr(&bm2[idx2 >> 5], bit2);
+                  }
+                }
+              } else {
+                bool kp = act;
+                if (kp && filt) {
+                  const uint32_t region = x >> M.region_bits;
+                  const uint32_t idx = hashed ? region_hash(region, P.bm_log2) : region - R0;
+                  kp = ((bm2[idx >> 5] >> (idx & 31)) & 1u) != 0;
+                  if (!kp && (x & rmask) < (uint32_t)M.region_overlap && (hashed ? region > 0 : idx > 0)) {
+                    const uint32_t idx2 = hashed ? region_hash(region - 1, P.bm_log2) : idx - 1;
+                    kp = ((bm2[idx2 >> 5] >> (idx2 & 31)) & 1u) != 0;
+                  }
+                  // marks across a tile cut are not seen here: keep, the neighbour test decides
+                  if (!kp && n_tiles > 1 && ((part > 0 && region == R0) || (part < n_tiles - 1 && region == Rlast))) kp = true;
+                }
+                const uint32_t bal = __ballot_sync(0xffffffffu, kp);
+                if (bal) {
+                  uint32_t at = 0;
+                  if (lane == 0) at = atomicAdd(&s_ns, (uint32_t)__popc(bal));
+                  at = __shfl_sync(0xffffffffu, at, 0) + (uint32_t)__popc(bal & lt);
+                  if (kp && at < (uint32_t)cap) ent[at] = ((unsigned long long)x << 32) | slot;
+                }
+              }
+              if (act) {
+                c = cn;
+                x0 = x1;
+                done++;
+              } else {
+                len = 0;   // this lane is past the tile (or its list): it stays out
+              }
+            }
+            if (pass == 1 && n_tiles > 1) {   // the list's cursor moves past the tile
+              uint32_t tot = done;
+              for (int o = 1; o < g; o <<= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+              if (have && gl == 0) kA[kk] += tot;
+            }
+          }
+          __syncthreads();   // all marks are in before pass B tests them
+          PROF_MARK(3 + pass);
+        }
+      }
+    } else {
     // cut every list at the partition boundaries
     if (n_part > 1) {
       const int nc = n_part - 1;
@@ -1236,6 +1333,7 @@ __global__ void __launch_bounds__(SCAN_CTA_MAX_THREADS, 2) scan_cta_kernel(const
         __syncthreads();   // all marks are in before pass B tests them
         PROF_MARK(3 + pass);
       }
+    }
     }
     if (mp_mark) continue;
     const int ns = (int)s_ns;

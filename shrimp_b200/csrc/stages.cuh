@@ -73,6 +73,7 @@ struct ScanParams {
   int bm_hashed;                 // CTA kernel: hashed region bitmaps (one partition) instead of exact partitions
   int win;                       // entries of the shared-memory staging window
   int lanes_per_list_log2; // lanes that share one index list (2..5): short lists are streamed several per warp
+  int walk;                // CTA kernel: cursor walk over the lists (no staging window, no partition cuts)
 };
 
 struct TaskBuildParams {
