@@ -46,6 +46,14 @@ extern "C" int shrimp_gpu_create(int device, shrimp_gpu_ctx **out) {
     return SHRIMP_E_ARG;
   }
   SH_CUDA(cudaSetDevice(device));
+  // The seed scan gathers short index lists (a handful of 4-byte positions each): ask for 32-byte L2 fetches so that a
+  // list costs the sectors it touches, not whole 64/128-byte lines (a hint; SHRIMP_L2_FETCH=64|128 overrides)
+  {
+    size_t gran = 32;
+    if (const char *e = getenv("SHRIMP_L2_FETCH")) gran = (size_t)atoi(e);
+    if (gran == 32 || gran == 64 || gran == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
+    cudaGetLastError();
+  }
   shrimp_gpu_ctx *c = new shrimp_gpu_ctx();
   c->device = device;
   cudaDeviceProp prop;

@@ -747,6 +747,12 @@ int chunk_scan(Chunk &C) {
       double avg_list = est / std::max(1, K_max);
       P.lanes_per_list_log2 = avg_list > 64 ? 5 : avg_list > 32 ? 4 : avg_list > 12 ? 3 : 2;
       P.walk = cta_walk ? 1 : 0;
+      {   // 64 sort bins over the genome's positions
+        int sh = 0;
+        while (sh < 31 && ((unsigned long long)(L_total > 1 ? L_total - 1 : 0) >> sh) >= 64ull) sh++;
+        P.sort_shift = sh;
+        if (getenv("SHRIMP_SCAN_NO_BINS")) P.sort_shift = 32;   // test hook: everything in one bin -> the CTA-wide network
+      }
       if (cta_walk) {   // lanes per list by the entries a list has per tile; 8 lanes read one 32-byte sector
         const double per_tile = avg_list / std::max(1, (filt && !cta_hashed) ? cta_n_part : 1);
         P.lanes_per_list_log2 = per_tile > 96 ? 5 : per_tile > 40 ? 4 : per_tile > 5 ? 3 : 2;

@@ -883,6 +883,7 @@ template <bool GLOB>
 __global__ void __launch_bounds__(SCAN_CTA_MAX_THREADS, 2) scan_cta_kernel(const ScanParams P) {
   extern __shared__ unsigned char smem_raw[];
   __shared__ uint32_t s_item_next, s_total, s_ns, s_next, s_cnt, s_out0, s_wsum[SCAN_CTA_MAX_THREADS / 32];
+  __shared__ uint32_t s_bcnt[64], s_boff[65];
   __shared__ int s_nanch, kbase[SHRIMP_MAX_SEEDS + 1];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nthr = blockDim.x, nwarps = nthr >> 5;
   constexpr bool glob = GLOB;
@@ -1081,76 +1082,70 @@ __global__ void __launch_bounds__(SCAN_CTA_MAX_THREADS, 2) scan_cta_kernel(const
             bm2[w] = 0u;
           }
         __syncthreads();
+        const int rb = M.region_bits, bml = P.bm_log2;
+        const uint32_t ovl = (uint32_t)M.region_overlap;
+        const bool edge_lo = n_tiles > 1 && part > 0, edge_hi = n_tiles > 1 && part < n_tiles - 1;
         for (int pass = filt ? 0 : 1; pass < 2; pass++) {
-          for (int k0 = wid * lpw; k0 < K; k0 += nwarps * lpw) {   // warp-uniform: lpw lists per warp and step
+          for (int k0 = wid * lpw; k0 < K; k0 += nwarps * lpw) {   // lpw lists per warp and step, g lanes each
             const int kk = k0 + (lane >> glog);
-            const bool have = kk < K;
-            uint32_t c = 0, len = 0, slot = 0;
+            uint32_t c0 = 0, c = 0, len = 0, slot = 0;
             const uint32_t *p = nullptr;
-            if (have) {
+            if (kk < K) {
               int sn = 0;
               while (kk >= kbase[sn + 1]) sn++;
-              c = kA[kk] + (uint32_t)gl;
+              c0 = kA[kk] + (uint32_t)gl;
               len = klen[kk];
               p = P.I.pos[sn] + kst[kk];
               slot = (uint32_t)(sn * max_n_kmers + (kk - kbase[sn]));
             }
-            uint32_t done = 0;
-            // two entries per lane in flight
-            uint32_t x0 = c < len ? __ldg(p + c) : 0u;
-            for (;;) {
-              const uint32_t cn = c + (uint32_t)g;
-              const uint32_t x1 = cn < len ? __ldg(p + cn) : 0u;
-              const bool act = c < len && (last_tile || x0 < pend);
-              if (!__any_sync(0xffffffffu, act)) break;
-              const uint32_t x = x0;
-              if (pass == 0) {
-                if (act) {
-                  const uint32_t region = x >> M.region_bits;
-                  const uint32_t idx = hashed ? region_hash(region, P.bm_log2) : region - R0;
-                  const uint32_t bit = 1u << (idx & 31);
-                  const uint32_t old = atomicOr(&bm1[idx >> 5], bit);
-                  if (old & bit) atomicOr(&bm2[idx >> 5], bit);
-                  if ((x & rmask) < (uint32_t)M.region_overlap && (hashed ? region > 0 : idx > 0)) {
-                    const uint32_t idx2 = hashed ? region_hash(region - 1, P.bm_log2) : idx - 1;
-                    const uint32_t bit2 = 1u << (idx2 & 31);
-                    const uint32_t old2 = atomicOr(&bm1[idx2 >> 5], bit2);
-                    if (old2 & bit2) atomicOr(&bm2[idx2 >> 5], bit2);
-                  }
+            c = c0;
+            // every lane walks its own stride of the list; the next entry is already in flight
+            uint32_t x = c < len ? __ldg(p + c) : 0u;
+            if (pass == 0) {
+              while (c < len && (last_tile || x < pend)) {
+                const uint32_t cn = c + (uint32_t)g;
+                const uint32_t xn = cn < len ? __ldg(p + cn) : 0u;
+                const uint32_t region = x >> rb;
+                const uint32_t idx = hashed ? region_hash(region, bml) : region - R0;
+                const uint32_t bit = 1u << (idx & 31);
+                if (atomicOr(&bm1[idx >> 5], bit) & bit) atomicOr(&bm2[idx >> 5], bit);
+                if ((x & rmask) < ovl && (hashed ? region > 0 : idx > 0)) {
+                  const uint32_t idx2 = hashed ? region_hash(region - 1, bml) : idx - 1;
+                  const uint32_t bit2 = 1u << (idx2 & 31);
+                  if (atomicOr(&bm1[idx2 >> 5], bit2) & bit2) atomicOr(&bm2[idx2 >> 5], bit2);
                 }
-              } else {
-                bool kp = act;
-                if (kp && filt) {
-                  const uint32_t region = x >> M.region_bits;
-                  const uint32_t idx = hashed ? region_hash(region, P.bm_log2) : region - R0;
+                c = cn;
+                x = xn;
+              }
+            } else {
+              while (c < len && (last_tile || x < pend)) {
+                const uint32_t cn = c + (uint32_t)g;
+                const uint32_t xn = cn < len ? __ldg(p + cn) : 0u;
+                bool kp = true;
+                if (filt) {
+                  const uint32_t region = x >> rb;
+                  const uint32_t idx = hashed ? region_hash(region, bml) : region - R0;
                   kp = ((bm2[idx >> 5] >> (idx & 31)) & 1u) != 0;
-                  if (!kp && (x & rmask) < (uint32_t)M.region_overlap && (hashed ? region > 0 : idx > 0)) {
-                    const uint32_t idx2 = hashed ? region_hash(region - 1, P.bm_log2) : idx - 1;
+                  if (!kp && (x & rmask) < ovl && (hashed ? region > 0 : idx > 0)) {
+                    const uint32_t idx2 = hashed ? region_hash(region - 1, bml) : idx - 1;
                     kp = ((bm2[idx2 >> 5] >> (idx2 & 31)) & 1u) != 0;
                   }
                   // marks across a tile cut are not seen here: keep, the neighbour test decides
-                  if (!kp && n_tiles > 1 && ((part > 0 && region == R0) || (part < n_tiles - 1 && region == Rlast))) kp = true;
+                  if (!kp && ((edge_lo && region == R0) || (edge_hi && region == Rlast))) kp = true;
                 }
-                const uint32_t bal = __ballot_sync(0xffffffffu, kp);
-                if (bal) {
-                  uint32_t at = 0;
-                  if (lane == 0) at = atomicAdd(&s_ns, (uint32_t)__popc(bal));
-                  at = __shfl_sync(0xffffffffu, at, 0) + (uint32_t)__popc(bal & lt);
-                  if (kp && at < (uint32_t)cap) ent[at] = ((unsigned long long)x << 32) | slot;
+                if (kp) {   // survivors are few: one shared-memory atomic each
+                  const uint32_t at = atomicAdd(&s_ns, 1u);
+                  if (at < (uint32_t)cap) ent[at] = ((unsigned long long)x << 32) | slot;
                 }
-              }
-              if (act) {
                 c = cn;
-                x0 = x1;
-                done++;
-              } else {
-                len = 0;   // this lane is past the tile (or its list): it stays out
+                x = xn;
               }
-            }
-            if (pass == 1 && n_tiles > 1) {   // the list's cursor moves past the tile
-              uint32_t tot = done;
-              for (int o = 1; o < g; o <<= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-              if (have && gl == 0) kA[kk] += tot;
+              if (n_tiles > 1) {   // the list's cursor moves past the tile: the entries its g lanes consumed
+                __syncwarp();
+                uint32_t tot = (c - c0) >> glog;
+                for (int o = 1; o < g; o <<= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+                if (kk < K && gl == 0) kA[kk] += tot;
+              }
             }
           }
           __syncthreads();   // all marks are in before pass B tests them
@@ -1348,9 +1343,83 @@ __global__ void __launch_bounds__(SCAN_CTA_MAX_THREADS, 2) scan_cta_kernel(const
       if (tid == 0) atomicAdd(&P.stats64[0], (unsigned long long)total);
       continue;
     }
-    // ---- 4a. CTA bitonic sort by position -------------------------------------------------------------------
+    // ---- 4a. sort by position: the candidates are dealt into 64 bins by the high bits of their position (count,
+    // prefix, scatter into the anchor array, which is still unused), every bin is sorted by one warp (a bitonic
+    // network with the padding left virtual), and the bins are copied back in order.  A bin that is too large for
+    // one warp (a tiny genome, a read of one repeat) sends the strand through the CTA-wide network below.
+    bool binned = false;
+    if (ns > 64) {
+      unsigned long long *const scratch = (unsigned long long *)rec;
+      const int bshift = P.sort_shift;
+      if (tid < 64) s_bcnt[tid] = 0u;
+      __syncthreads();
+      for (int t = tid; t < ns; t += nthr) atomicAdd(&s_bcnt[(uint32_t)min(63ull, (ent[t] >> 32) >> bshift)], 1u);
+      __syncthreads();
+      if (wid == 0) {
+        const uint32_t c0 = s_bcnt[2 * lane], c1 = s_bcnt[2 * lane + 1];
+        const uint32_t inc = (uint32_t)warp_incl_scan((int)(c0 + c1), lane);
+        s_boff[2 * lane] = inc - c0 - c1;
+        s_boff[2 * lane + 1] = inc - c1;
+        if (lane == 31) s_boff[64] = inc;
+        const uint32_t mx = max(c0, c1);
+        const uint32_t big = __ballot_sync(0xffffffffu, mx > 1024u);
+        if (lane == 0) s_next = big ? 1u : 0u;
+        s_bcnt[2 * lane] = 0u;
+        s_bcnt[2 * lane + 1] = 0u;
+      }
+      __syncthreads();
+      if (s_next == 0u) {
+        binned = true;
+        for (int t = tid; t < ns; t += nthr) {
+          const unsigned long long e = ent[t];
+          const uint32_t bin = (uint32_t)min(63ull, (e >> 32) >> bshift);
+          scratch[s_boff[bin] + atomicAdd(&s_bcnt[bin], 1u)] = e;
+        }
+        __syncthreads();
+        for (int bin = wid; bin < 64; bin += nwarps) {
+          const int n = (int)(s_boff[bin + 1] - s_boff[bin]);
+          if (n < 2) continue;
+          unsigned long long *a = scratch + s_boff[bin];
+          int P2 = 2;
+          while (P2 < n) P2 <<= 1;
+          for (int k = 2; k <= P2; k <<= 1) {
+            const int h = k >> 1;
+            for (int t = lane; t < (P2 >> 1); t += 32) {   // flip: i in the lower half of its block against its mirror
+              const int blk = t / h, off = t - blk * h;
+              const int i = blk * k + off, l = blk * k + (k - 1 - off);
+              if (l < n) {
+                const unsigned long long u = a[i], v = a[l];
+                if (u > v) {
+                  a[i] = v;
+                  a[l] = u;
+                }
+              }
+            }
+            __syncwarp();
+            for (int j = h >> 1; j > 0; j >>= 1) {
+              for (int t = lane; t < (P2 >> 1); t += 32) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int l = i | j;
+                if (l < n) {
+                  const unsigned long long u = a[i], v = a[l];
+                  if (u > v) {
+                    a[i] = v;
+                    a[l] = u;
+                  }
+                }
+              }
+              __syncwarp();
+            }
+          }
+        }
+        __syncthreads();
+        for (int t = tid; t < ns; t += nthr) ent[t] = scratch[t];
+        __syncthreads();
+      }
+    }
     int Pn = 32;
     while (Pn < ns) Pn <<= 1;
+    if (binned) Pn = 1;   // sorted already
     for (int t = ns + tid; t < Pn; t += nthr) ent[t] = ~0ull;
     __syncthreads();
     for (int k = 2; k <= Pn; k <<= 1) {

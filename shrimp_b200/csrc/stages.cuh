@@ -74,6 +74,7 @@ struct ScanParams {
   int win;                       // entries of the shared-memory staging window
   int lanes_per_list_log2; // lanes that share one index list (2..5): short lists are streamed several per warp
   int walk;                // CTA kernel: cursor walk over the lists (no staging window, no partition cuts)
+  int sort_shift;          // CTA kernel: candidates are binned by position >> sort_shift (64 bins) before the sort
 };
 
 struct TaskBuildParams {
