@@ -655,6 +655,19 @@ int chunk_scan(Chunk &C) {
     if (const char *e = getenv("SHRIMP_SCAN_CTA_CAP")) cta_cap = std::max(32, atoi(e));  // test hook: global slabs
     while (cta_cap > 256 && scan_cta_smem_bytes(cta_cap, max_rl, big_k_cap, cta_bm_log2, cta_n_part, cta_win, false) > 200 * 1024)
       cta_cap >>= 1;
+    // a slab a little smaller than the power of two when that lets one more CTA live on an SM (the serial phases of a
+    // strand -- the collapse runs on one warp -- then overlap another strand's parallel ones)
+    if (!getenv("SHRIMP_SCAN_CTA_CAP")) {
+      auto per_sm_of = [&](int c) {
+        return (int)((size_t)(227 * 1024) / (scan_cta_smem_bytes(c, max_rl, big_k_cap, cta_bm_log2, cta_n_part, cta_win, false) + 1024));
+      };
+      const int per0 = per_sm_of(cta_cap);
+      for (int c2 = cta_cap - cta_cap / 16; c2 >= cta_cap - cta_cap / 8 && per0 < 8; c2 -= cta_cap / 16)
+        if (per_sm_of(c2) > per0) {
+          cta_cap = c2;
+          break;
+        }
+    }
   }
   const int g_cap = 65535;   // global-slab pass: 16-bit candidate indices
   if (scan_cta_smem_bytes(cta_cap, max_rl, big_k_cap, cta_bm_log2, cta_n_part, cta_win, false) > 226 * 1024) {

@@ -854,7 +854,7 @@ __host__ __device__ inline CtaSmem cta_layout(int cap, int max_rl, int k_cap, in
   L.kpre = take(((size_t)k_cap + 1) * 4);
   L.buf = take((size_t)win * 4);
   L.bslot = take((size_t)win * 2);
-  L.cuts = take((size_t)k_cap * (size_t)(n_part > 1 ? n_part - 1 : 0) * 4);
+  L.cuts = take((size_t)k_cap * (size_t)((n_part > 1 && win > 16) ? n_part - 1 : 0) * 4);   // win 16 = cursor walk: no cuts
   L.cache = take((size_t)max_rl * 4);
   L.heap = take((size_t)k_cap * 8);
   L.keep = take((c / 32 + 2) * 4);
@@ -1348,7 +1348,7 @@ __global__ void __launch_bounds__(SCAN_CTA_MAX_THREADS, 2) scan_cta_kernel(const
     // network with the padding left virtual), and the bins are copied back in order.  A bin that is too large for
     // one warp (a tiny genome, a read of one repeat) sends the strand through the CTA-wide network below.
     bool binned = false;
-    if (ns > 64) {
+    if (ns > 1024) {   // below that the CTA-wide network is as fast
       unsigned long long *const scratch = (unsigned long long *)rec;
       const int bshift = P.sort_shift;
       if (tid < 64) s_bcnt[tid] = 0u;
@@ -1376,9 +1376,10 @@ __global__ void __launch_bounds__(SCAN_CTA_MAX_THREADS, 2) scan_cta_kernel(const
           scratch[s_boff[bin] + atomicAdd(&s_bcnt[bin], 1u)] = e;
         }
         __syncthreads();
+        // bins of up to 128 candidates: one warp each
         for (int bin = wid; bin < 64; bin += nwarps) {
           const int n = (int)(s_boff[bin + 1] - s_boff[bin]);
-          if (n < 2) continue;
+          if (n < 2 || n > 128) continue;
           unsigned long long *a = scratch + s_boff[bin];
           int P2 = 2;
           while (P2 < n) P2 <<= 1;
@@ -1409,6 +1410,43 @@ __global__ void __launch_bounds__(SCAN_CTA_MAX_THREADS, 2) scan_cta_kernel(const
                 }
               }
               __syncwarp();
+            }
+          }
+        }
+        // larger bins (the read's own locus: one entry per k-mer): the whole CTA, one bin after the other
+        for (int bin = 0; bin < 64; bin++) {
+          const int n = (int)(s_boff[bin + 1] - s_boff[bin]);
+          if (n <= 128) continue;
+          unsigned long long *a = scratch + s_boff[bin];
+          int P2 = 256;
+          while (P2 < n) P2 <<= 1;
+          for (int k = 2; k <= P2; k <<= 1) {
+            const int h = k >> 1;
+            for (int t = tid; t < (P2 >> 1); t += nthr) {
+              const int blk = t / h, off = t - blk * h;
+              const int i = blk * k + off, l = blk * k + (k - 1 - off);
+              if (l < n) {
+                const unsigned long long u = a[i], v = a[l];
+                if (u > v) {
+                  a[i] = v;
+                  a[l] = u;
+                }
+              }
+            }
+            __syncthreads();
+            for (int j = h >> 1; j > 0; j >>= 1) {
+              for (int t = tid; t < (P2 >> 1); t += nthr) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int l = i | j;
+                if (l < n) {
+                  const unsigned long long u = a[i], v = a[l];
+                  if (u > v) {
+                    a[i] = v;
+                    a[l] = u;
+                  }
+                }
+              }
+              __syncthreads();
             }
           }
         }
