@@ -179,6 +179,14 @@ int shrimp_gpu_index_export(shrimp_gpu_ctx *ctx, int sn, uint32_t *lens_out, uin
  * (the reference's loader reads through gzread, which passes plain files through), so that
  * `gmapper -L <prefix>` runs on exactly the projection held in HBM.  contig_names[num_contigs]. */
 int shrimp_gpu_projection_save(shrimp_gpu_ctx *ctx, const char *prefix, const char *const *contig_names);
+/* Projection load.  Replaces load_genome_map / load_genome_map_seed (gmapper/genome.c:670-832, :69-182) for the
+ * device: <prefix>.genome and <prefix>.seed.N as `gmapper -S` (gzip) or shrimp_gpu_projection_save (plain) wrote them
+ * go straight into HBM -- the letter contigs (reverse complement and colours are derived there) and per seed the CSR
+ * (genomemap_len as offsets, the position lists in file order).  Replaces genome_load + index_build for a saved
+ * projection; contig names as stored in the file. */
+int shrimp_gpu_projection_load(shrimp_gpu_ctx *ctx, const char *prefix);
+int shrimp_gpu_num_contigs(shrimp_gpu_ctx *ctx);
+const char *shrimp_gpu_contig_name(shrimp_gpu_ctx *ctx, int cn);
 
 /* ------------------------------------------------------------------------------------------
  * Chunk-level mapping.  Replaces handle_read (gmapper/mapping.c:1773-1868) for a whole chunk of

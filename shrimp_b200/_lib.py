@@ -138,6 +138,12 @@ def lib() -> C.CDLL:
     L.shrimp_gpu_index_export.restype = i32
     L.shrimp_gpu_projection_save.argtypes = [vp, C.c_char_p, vp]
     L.shrimp_gpu_projection_save.restype = i32
+    L.shrimp_gpu_projection_load.argtypes = [vp, C.c_char_p]
+    L.shrimp_gpu_projection_load.restype = i32
+    L.shrimp_gpu_num_contigs.argtypes = [vp]
+    L.shrimp_gpu_num_contigs.restype = i32
+    L.shrimp_gpu_contig_name.argtypes = [vp, i32]
+    L.shrimp_gpu_contig_name.restype = C.c_char_p
     L.shrimp_gpu_map_reads.argtypes = [vp, C.POINTER(MapParamsC), i32, vp, i32, vp, vp, vp, C.c_int64, vp, vp,
                                        C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64), vp, C.c_int64,
                                        C.POINTER(C.c_int64), C.POINTER(MapStatsC)]

@@ -334,6 +334,14 @@ class GpuContext:
         check(self._L.shrimp_gpu_projection_save(self._h, prefix.encode(), C.cast(names, C.c_void_p)),
               "shrimp_gpu_projection_save")
 
+    def load_projection(self, prefix: str):
+        """load_genome_map + load_genome_map_seed (genome.c:670-832, :69-182): the files of `gmapper -S` or of
+        save_projection straight into HBM; returns the contig names stored in the file."""
+        check(self._L.shrimp_gpu_projection_load(self._h, prefix.encode()), "shrimp_gpu_projection_load")
+        n = int(self._L.shrimp_gpu_num_contigs(self._h))
+        names = [self._L.shrimp_gpu_contig_name(self._h, c).decode() for c in range(n)]
+        return names
+
     # ---- chunk mapping ------------------------------------------------------------------------
     def _buf(self, key, n, dtype, reuse):
         """output buffer; with reuse the same pages serve every call (results are views valid until the next call)"""

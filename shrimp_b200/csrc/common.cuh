@@ -115,6 +115,11 @@ struct SwScores {
 
 }  // namespace shrimp
 
+// Kernels with dynamic shared memory are always opted in to the device maximum (227 KB per CTA on sm_100): the
+// attribute is per function and process-wide, so setting it to the size of ONE launch would race with the launches of
+// the other host threads' contexts (a smaller value set in between makes a launch fail with "invalid argument").
+#define SHRIMP_MAX_DYN_SMEM (227 * 1024)
+
 #define SHRIMP_AUX_STREAMS 4
 
 struct shrimp_gpu_ctx {
@@ -130,6 +135,9 @@ struct shrimp_gpu_ctx {
   shrimp::StageTimer timers[shrimp::ST_COUNT];
   // sw_vector batch scratch
   shrimp::DevBuf d_genome, d_genome_ls, d_reads, d_task, d_scores, d_boundary;
+  // the caller's timing bracket and the L2 flush buffer (bench entries): per context, freed with it
+  cudaEvent_t user_ev[2] = {nullptr, nullptr};
+  shrimp::DevBuf d_flush;
   // opaque owners of the resident genome/index and the chunk pipeline (index.cu / pipeline.cu)
   void *genome = nullptr;
   bool genome_borrowed = false;   // shared from another context (shrimp_gpu_share_genome): not freed here

@@ -85,6 +85,9 @@ extern "C" void shrimp_gpu_destroy(shrimp_gpu_ctx *c) {
   c->d_task.release();
   c->d_scores.release();
   c->d_boundary.release();
+  c->d_flush.release();
+  for (int i = 0; i < 2; i++)
+    if (c->user_ev[i]) cudaEventDestroy(c->user_ev[i]);
   for (int i = 0; i < ST_COUNT; i++) {
     if (c->timers[i].ev0) cudaEventDestroy(c->timers[i].ev0);
     if (c->timers[i].ev1) cudaEventDestroy(c->timers[i].ev1);
@@ -171,34 +174,32 @@ extern "C" int shrimp_gpu_sw_setup(shrimp_gpu_ctx *c, const shrimp_sw_params *p)
 
 // Two user events on the library's stream so a caller can bracket a timed region on the device
 // (bench.py: CUDA-event timing of exactly K steps on the launching stream).
-static cudaEvent_t g_user_ev[2] = {nullptr, nullptr};
 extern "C" int shrimp_gpu_event_record(shrimp_gpu_ctx *c, int which) {
   if (!c || which < 0 || which > 1) {
     set_error("shrimp_gpu_event_record: invalid argument");
     return SHRIMP_E_ARG;
   }
   SH_CUDA(cudaSetDevice(c->device));
-  if (!g_user_ev[which]) SH_CUDA(cudaEventCreate(&g_user_ev[which]));
-  SH_CUDA(cudaEventRecord(g_user_ev[which], c->stream));
+  if (!c->user_ev[which]) SH_CUDA(cudaEventCreate(&c->user_ev[which]));
+  SH_CUDA(cudaEventRecord(c->user_ev[which], c->stream));
   return SHRIMP_OK;
 }
 extern "C" int shrimp_gpu_event_elapsed_ms(shrimp_gpu_ctx *c, float *ms) {
-  if (!c || !ms || !g_user_ev[0] || !g_user_ev[1]) {
+  if (!c || !ms || !c->user_ev[0] || !c->user_ev[1]) {
     set_error("shrimp_gpu_event_elapsed_ms: events not recorded");
     return SHRIMP_E_STATE;
   }
-  SH_CUDA(cudaEventSynchronize(g_user_ev[1]));
-  SH_CUDA(cudaEventElapsedTime(ms, g_user_ev[0], g_user_ev[1]));
+  SH_CUDA(cudaEventSynchronize(c->user_ev[1]));
+  SH_CUDA(cudaEventElapsedTime(ms, c->user_ev[0], c->user_ev[1]));
   return SHRIMP_OK;
 }
 // Writes a buffer larger than L2 (126 MB) on the library's stream: L2 flush between timed steps.
 extern "C" int shrimp_gpu_flush_l2(shrimp_gpu_ctx *c) {
   if (!c) return SHRIMP_E_ARG;
   SH_CUDA(cudaSetDevice(c->device));
-  static shrimp::DevBuf flush;
   const size_t bytes = (size_t)256 << 20;
-  SH_TRY(flush.ensure(bytes));
-  SH_CUDA(cudaMemsetAsync(flush.p, 1, bytes, c->stream));
+  SH_TRY(c->d_flush.ensure(bytes));
+  SH_CUDA(cudaMemsetAsync(c->d_flush.p, 1, bytes, c->stream));
   SH_CUDA(cudaStreamSynchronize(c->stream));
   return SHRIMP_OK;
 }

@@ -45,6 +45,7 @@ struct DeviceGenome {
   uint64_t total[SHRIMP_MAX_SEEDS] = {0};
   DevBuf d_offs[SHRIMP_MAX_SEEDS];  // uint32 [nbuckets+1]
   DevBuf d_pos[SHRIMP_MAX_SEEDS];   // uint32 [total]
+  std::vector<std::string> contig_names;   // set by shrimp_gpu_projection_load
 };
 
 struct IndexView {
@@ -60,6 +61,8 @@ struct GenomeView {
 };
 
 inline DeviceGenome *genome_of(shrimp_gpu_ctx *ctx) { return (DeviceGenome *)ctx->genome; }
+int seed_table_init(SeedTable &S, int n_seeds, const uint64_t *masks, const int32_t *spans, const int32_t *weights,
+                    int hflag, const char *who);
 
 // KMER_TO_MAPIDX (gmapper.h:370) for the k-mer of seed sn that starts at base `start` of the
 // packed sequence `seq`: kmer_to_mapidx_orig (gmapper.h:349-368) concatenates the low two bits

@@ -206,26 +206,22 @@ extern "C" int shrimp_gpu_genome_load(shrimp_gpu_ctx *ctx, int num_contigs, cons
 
 // Replaces the projection loop of load_genome (genome.c:1138-1166) for the seeds of
 // add_spaced_seed (seeds.c:9-42): masks[sn] bit 0 = rightmost seed character.
-extern "C" int shrimp_gpu_index_build(shrimp_gpu_ctx *ctx, int n_seeds, const uint64_t *masks, const int32_t *spans,
-                                      const int32_t *weights, int hflag) {
-  DeviceGenome *g = ctx ? genome_of(ctx) : nullptr;
-  if (!g) {
-    set_error("shrimp_gpu_index_build: load the genome first");
-    return SHRIMP_E_STATE;
-  }
+namespace shrimp {
+// The seed table the kernels take by value, from the reference's seed_type fields (gmapper-definitions.h:59-63).
+int seed_table_init(SeedTable &S, int n_seeds, const uint64_t *masks, const int32_t *spans, const int32_t *weights,
+                    int hflag, const char *who) {
   if (n_seeds <= 0 || n_seeds > SHRIMP_MAX_SEEDS || !masks || !spans || !weights) {
-    set_error("shrimp_gpu_index_build: invalid seed table");
+    set_error("%s: invalid seed table", who);
     return SHRIMP_E_ARG;
   }
-  SeedTable S{};
+  S = SeedTable{};
   S.n_seeds = n_seeds;
   S.hflag = hflag ? 1 : 0;
   S.min_span = 64;
   for (int sn = 0; sn < n_seeds; sn++) {
     if (spans[sn] < 1 || spans[sn] > 64 || weights[sn] < 1 || (!hflag && weights[sn] > 14)) {
       // MAX_SEED_SPAN / MAX_SEED_WEIGHT, gmapper-definitions.h:52-56
-      set_error("shrimp_gpu_index_build: seed %d has span %d weight %d (max 64 / 14 without -H)", sn, spans[sn],
-                weights[sn]);
+      set_error("%s: seed %d has span %d weight %d (max 64 / 14 without -H)", who, sn, spans[sn], weights[sn]);
       return SHRIMP_E_ARG;
     }
     S.mask[sn] = masks[sn];
@@ -260,6 +256,19 @@ extern "C" int shrimp_gpu_index_build(shrimp_gpu_ctx *ctx, int n_seeds, const ui
       if (ok) S.n_runs[sn] = (unsigned char)nr;
     }
   }
+  return SHRIMP_OK;
+}
+}  // namespace shrimp
+
+extern "C" int shrimp_gpu_index_build(shrimp_gpu_ctx *ctx, int n_seeds, const uint64_t *masks, const int32_t *spans,
+                                      const int32_t *weights, int hflag) {
+  DeviceGenome *g = ctx ? genome_of(ctx) : nullptr;
+  if (!g) {
+    set_error("shrimp_gpu_index_build: load the genome first");
+    return SHRIMP_E_STATE;
+  }
+  SeedTable S{};
+  SH_TRY(seed_table_init(S, n_seeds, masks, spans, weights, hflag, "shrimp_gpu_index_build"));
   SH_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   const uint64_t L = g->total_len;

@@ -405,7 +405,7 @@ int launch_post_sw(shrimp_gpu_ctx *ctx, const PostParams &P, DevBuf &scratch) {
   }
   const size_t smem = per_half * halves;
   auto kern = post_sw_kernel;
-  SH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  SH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SHRIMP_MAX_DYN_SMEM));
   int per_sm = 0;
   SH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, halves * 16, smem));
   if (per_sm < 1) per_sm = 1;

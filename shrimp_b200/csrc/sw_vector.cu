@@ -224,48 +224,68 @@ int launch_sw_vector(shrimp_gpu_ctx *ctx, const uint32_t *d_genome, const uint32
     set_error("sw_vector: colour space needs the letter genome for row 0");
     return SHRIMP_E_ARG;
   }
-  SwvParams P;
-  P.genome = d_genome;
-  P.genome_ls = d_genome_ls;
-  P.reads = d_reads;
-  P.read_stride = read_stride_words;
-  P.n_tasks = n_tasks;
-  P.t = t;
-  P.scores = d_scores;
   const int T = choose_T(max_rlen);
-  P.n_strips = (max_rlen + T - 1) / T;
-  P.max_glen = max_glen;
-  const int n_pairs = (n_tasks + 1) / 2;
-  const int n_blocks = (n_pairs + SWV_BLOCK - 1) / SWV_BLOCK;
-  P.n_threads = (uint32_t)n_blocks * SWV_BLOCK;
-  P.boundary = nullptr;
-  if (P.n_strips > 1) {
-    SH_TRY(ctx->d_boundary.ensure((size_t)2 * max_glen * P.n_threads * sizeof(uint32_t)));
-    P.boundary = ctx->d_boundary.as<uint32_t>();
+  const int n_strips = (max_rlen + T - 1) / T;
+  // reads longer than one register strip park a boundary row pair per thread and window column in global memory:
+  // such launches are cut into batches whose boundary rows stay under 1 GB (the sensitive configuration scores
+  // hundreds of millions of windows per chunk)
+  int batch = n_tasks;
+  if (n_strips > 1) {
+    const size_t per_thread = (size_t)2 * (size_t)std::max(1, max_glen) * sizeof(uint32_t);
+    const size_t max_threads = std::max<size_t>((size_t)SWV_BLOCK, ((size_t)1 << 30) / per_thread);
+    batch = (int)std::min<size_t>((size_t)n_tasks, 2 * (max_threads / SWV_BLOCK) * SWV_BLOCK);
   }
-  auto pk = [](int v) { return ((uint32_t)v & 0xffffu) * 0x10001u; };
-  P.ma1 = pk(s.match + 1);
-  P.mm = pk(s.vec_mismatch);
-  P.naoe = pk(-(s.a_open + s.a_ext));
-  P.nae = pk(-s.a_ext);
-  P.nboe = pk(-(s.b_open + s.b_ext));
-  P.nbe = pk(-s.b_ext);
-  P.sh = s.shift;
-  const bool cs = s.use_colours != 0;
-  int rc;
-  switch (T) {
-    case 8: rc = launch_T<8>(ctx, P, cs, n_blocks); break;
-    case 16: rc = launch_T<16>(ctx, P, cs, n_blocks); break;
-    case 24: rc = launch_T<24>(ctx, P, cs, n_blocks); break;
-    case 32: rc = launch_T<32>(ctx, P, cs, n_blocks); break;
-    case 40: rc = launch_T<40>(ctx, P, cs, n_blocks); break;
-    case 48: rc = launch_T<48>(ctx, P, cs, n_blocks); break;
-    case 56: rc = launch_T<56>(ctx, P, cs, n_blocks); break;
-    default: rc = launch_T<64>(ctx, P, cs, n_blocks); break;
+  int rc = SHRIMP_OK;
+  for (int t0 = 0; t0 < n_tasks && rc == SHRIMP_OK; t0 += batch) {
+    const int nb = std::min(batch, n_tasks - t0);
+    SwvParams P;
+    P.genome = d_genome;
+    P.genome_ls = d_genome_ls;
+    P.reads = d_reads;
+    P.read_stride = read_stride_words;
+    P.n_tasks = nb;
+    P.t = t;
+    P.t.goff += t0;
+    P.t.glen += t0;
+    P.t.ridx += t0;
+    P.t.rlen += t0;
+    if (P.t.initbp) P.t.initbp += t0;
+    if (P.t.out) P.t.out += t0;
+    P.scores = t.out ? d_scores : d_scores + t0;
+    P.n_strips = n_strips;
+    P.max_glen = max_glen;
+    const int n_pairs = (nb + 1) / 2;
+    const int n_blocks = (n_pairs + SWV_BLOCK - 1) / SWV_BLOCK;
+    P.n_threads = (uint32_t)n_blocks * SWV_BLOCK;
+    P.boundary = nullptr;
+    if (P.n_strips > 1) {
+      SH_TRY(ctx->d_boundary.ensure((size_t)2 * max_glen * P.n_threads * sizeof(uint32_t)));
+      P.boundary = ctx->d_boundary.as<uint32_t>();
+    }
+    auto pk = [](int v) { return ((uint32_t)v & 0xffffu) * 0x10001u; };
+    P.ma1 = pk(s.match + 1);
+    P.mm = pk(s.vec_mismatch);
+    P.naoe = pk(-(s.a_open + s.a_ext));
+    P.nae = pk(-s.a_ext);
+    P.nboe = pk(-(s.b_open + s.b_ext));
+    P.nbe = pk(-s.b_ext);
+    P.sh = s.shift;
+    const bool cs = s.use_colours != 0;
+    switch (T) {
+      case 8: rc = launch_T<8>(ctx, P, cs, n_blocks); break;
+      case 16: rc = launch_T<16>(ctx, P, cs, n_blocks); break;
+      case 24: rc = launch_T<24>(ctx, P, cs, n_blocks); break;
+      case 32: rc = launch_T<32>(ctx, P, cs, n_blocks); break;
+      case 40: rc = launch_T<40>(ctx, P, cs, n_blocks); break;
+      case 48: rc = launch_T<48>(ctx, P, cs, n_blocks); break;
+      case 56: rc = launch_T<56>(ctx, P, cs, n_blocks); break;
+      default: rc = launch_T<64>(ctx, P, cs, n_blocks); break;
+    }
+    if (rc == SHRIMP_OK) SH_LAUNCHED(ctx, stage);
   }
-  if (rc == SHRIMP_OK) SH_LAUNCHED(ctx, stage);
   return rc;
 }
+
 
 }  // namespace shrimp
 

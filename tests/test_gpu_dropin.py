@@ -117,3 +117,115 @@ def test_dropin_exports_the_reference_symbols():
         rhave = {ln.split()[-1] for ln in rout.splitlines() if " T " in ln}
         assert set(want) <= rhave, sorted(set(want) - rhave)
         assert rhave <= have, sorted(rhave - have)
+
+
+# ---- bench-size genomes (BASELINE.json configs) through the drop-in -------------------------------------------------
+def _bench_case(key, n_reads, tmp_path, extra=()):
+    """reads.fa of a bench.py workload + the projection held in HBM saved in the -S format (byte-identical to
+    `gmapper -S`, tests/test_gpu_index.py), loaded by both binaries with -L so that the reference's serial index build
+    stays out of the test"""
+    sys.path.insert(0, ROOT)
+    import copy
+
+    import bench
+    w = copy.copy(bench.WORKLOADS[key])
+    w._genome = None
+    if key == "c3":
+        w.resize(300)
+    codes, _ = w.reads(n_reads, 31)
+    ctx = bench.build_context(w, 0)[0]
+    try:
+        bench.reference_setup(w, str(tmp_path), codes, ctx)
+    finally:
+        ctx.close()
+    rd = ["-1", "reads.fa.1", "-2", "reads.fa.2"] if w.paired else ["reads.fa"]
+    args = [*w.load_args(), *extra, "-L", "proj", *rd]
+    ref, _ = run_sam(REF, w.binary, args, str(tmp_path), os.cpu_count() or 4)
+    new, _ = run_sam(NEW, w.binary, args, str(tmp_path), 3, ["-K", str(max(1000, (n_reads // 5) & ~1))])
+    assert_same_sam(ref, new)
+    return sum(1 for ln in new if ln and not ln.startswith(b"@"))
+
+
+@needs_bins
+@pytest.mark.gpu
+def test_c1_full_size(tmp_path):
+    """BASELINE.json configs[0] at its full size: 100 k reads of 50 bp against the 10 Mb genome"""
+    assert _bench_case("c1", 100_000, tmp_path) > 90_000
+
+
+@needs_bins
+@pytest.mark.gpu
+def test_c4_full_size_default_and_mirna(tmp_path):
+    """configs[3]: 22 bp reads against 2,000 contigs of 22 bp, default options and -M mirna"""
+    d1, d2 = tmp_path / "a", tmp_path / "b"
+    d1.mkdir()
+    d2.mkdir()
+    assert _bench_case("c4", 60_000, d1) > 50_000
+    assert _bench_case("c4mirna", 60_000, d2) > 40_000
+
+
+@needs_bins
+@pytest.mark.gpu
+def test_c5_sensitive_full_genome(tmp_path):
+    """configs[4]: the overly sensitive option set against the 10 Mb genome (about a thousand windows per read)"""
+    assert _bench_case("c5", 3_000, tmp_path) > 2_000
+
+
+@needs_bins
+@pytest.mark.gpu
+def test_c3_pairs_300mb_sample(tmp_path):
+    assert _bench_case("c3", 8_000, tmp_path) > 6_000
+
+
+def _mixed_reads(case, rng, n, lo, hi, n_frac, colour):
+    """reads of mixed lengths cut from the case's contigs, 2 % substitutions, some N; -> (names, strings, quals)"""
+    import numpy as np
+    out = []
+    for i in range(n):
+        cn = int(rng.integers(0, len(case.contigs)))
+        g = case.contigs[cn][1]
+        rl = int(rng.integers(lo, hi + 1))
+        pos = int(rng.integers(0, g.size - rl - 1))
+        frag = g[pos:pos + rl].copy()
+        sub = rng.random(rl) < 0.02
+        frag[sub] = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=int(sub.sum()))]
+        if rng.random() < 0.5:
+            comp = np.zeros(256, dtype=np.uint8)
+            for a, b in zip(b"ACGTN", b"TGCAN"):
+                comp[a] = b
+            frag = comp[frag][::-1].copy()
+        frag[rng.random(rl) < n_frac] = ord("N")
+        if colour:
+            import gen_synth
+            s = gen_synth.letters_to_colour_read(frag, rng, 0.02)
+            q = bytes((33 + rng.integers(2, 41, size=rl)).astype(np.uint8))
+        else:
+            s = bytes(frag)
+            # some reads of low average quality: the loop of gmapper.c drops them (min_avg_qv 10)
+            top = 8 if rng.random() < 0.1 else 41
+            q = bytes((33 + rng.integers(2, top, size=rl)).astype(np.uint8))
+        out.append((f"m{i}", s, q))
+    return out
+
+
+@needs_bins
+@pytest.mark.gpu
+@pytest.mark.parametrize("colour", [False, True])
+def test_mixed_lengths_fastq_and_n(colour, tmp_path):
+    """one chunk holding reads of 22 to 400 bases (letter space; 25 to 120 colours in colour space), reads with N,
+    FASTQ qualities (letter-space QUAL column, the average-quality filter of gmapper.c:496-527, per-position crossover
+    scores in colour space) -- and a read that is too long for --longest-read"""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    case = LsCase("c2_small" if colour else "c1_small")
+    case.write_fasta(str(tmp_path))
+    rng = np.random.default_rng(77)
+    reads = _mixed_reads(case, rng, 900, 25 if colour else 22, 120 if colour else 400, 0.01, colour)
+    with open(os.path.join(str(tmp_path), "mixed.fq"), "wb") as f:
+        for name, s, q in reads:
+            f.write(b"@" + name.encode() + b"\n" + s + b"\n+\n" + q + b"\n")
+    args = ["-Q", "--longest-read", "380", "mixed.fq", "genome.fa"]
+    ref, _ = run_sam(REF, case.binary, args, str(tmp_path), 4)
+    new, _ = run_sam(NEW, case.binary, args, str(tmp_path), 2, ["-K", "250"])
+    assert_same_sam(ref, new)
+    assert sum(1 for ln in new if ln and not ln.startswith(b"@")) > 500

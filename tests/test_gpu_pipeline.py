@@ -87,11 +87,16 @@ def test_cta_scan_kernel_alone_matches_reference_golden(gpu_ctx, name, monkeypat
     ("c1_repeat", {"SHRIMP_SCAN_CTA_CAP": "32"}),                                  # slab of 32: global-slab pass
     ("c1_repeat", {"SHRIMP_SCAN_CTA_CAP": "32", "SHRIMP_SCAN_BM_LOG2": "5"}),
     ("c5_small", {"SHRIMP_SCAN_CTA_CAP": "64"}),                                   # no region filter
-    ("c1_repeat", {"SHRIMP_SCAN_WIN": "64", "SHRIMP_SCAN_BM_LOG2": "6"}),          # several staging windows
-    ("c5_small", {"SHRIMP_SCAN_WIN": "128", "SHRIMP_SCAN_LANES_LOG2": "5"}),
-    ("c2_small", {"SHRIMP_SCAN_WIN": "96", "SHRIMP_SCAN_LANES_LOG2": "0"}),
+    # the staged-window passes (the mate-pair modes still run them): several staging windows
+    ("c1_repeat", {"SHRIMP_SCAN_WALK": "0", "SHRIMP_SCAN_WIN": "64", "SHRIMP_SCAN_BM_LOG2": "6"}),
+    ("c5_small", {"SHRIMP_SCAN_WALK": "0", "SHRIMP_SCAN_WIN": "128", "SHRIMP_SCAN_LANES_LOG2": "5"}),
+    ("c2_small", {"SHRIMP_SCAN_WALK": "0", "SHRIMP_SCAN_WIN": "96", "SHRIMP_SCAN_LANES_LOG2": "0"}),
     ("c1_repeat", {"SHRIMP_SCAN_HASHED": "1", "SHRIMP_SCAN_BM_LOG2": "7"}),       # hashed bitmaps of 128 bits
-    ("c2_small", {"SHRIMP_SCAN_HASHED": "1", "SHRIMP_SCAN_WIN": "64"}),
+    ("c2_small", {"SHRIMP_SCAN_WALK": "0", "SHRIMP_SCAN_HASHED": "1", "SHRIMP_SCAN_WIN": "64"}),
+    # the cursor walk with one lane and with a whole warp per list, tiles of 32 regions
+    ("c1_repeat", {"SHRIMP_SCAN_LANES_LOG2": "0", "SHRIMP_SCAN_BM_LOG2": "5"}),
+    ("c5_small", {"SHRIMP_SCAN_LANES_LOG2": "5"}),
+    ("c2_small", {"SHRIMP_SCAN_LANES_LOG2": "4", "SHRIMP_SCAN_BM_LOG2": "6"}),
 ])
 def test_cta_scan_partitions_and_global_slabs(gpu_ctx, name, env, monkeypatch):
     """the CTA scan kernel with the genome cut into several bitmap partitions (how a 3 Gb genome runs), and with

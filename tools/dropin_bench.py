@@ -23,7 +23,7 @@ NEW_DIR = os.path.join(ROOT, "integration", "_build")
 
 def run_binary(bindir, w, workdir, threads, reads_fa, extra, sam_path=None, env=None):
     rd = ["-1", reads_fa + ".1", "-2", reads_fa + ".2"] if w.paired else [reads_fa]
-    cmd = [os.path.join(bindir, w.binary), "-N", str(threads), *extra, *w.args, "-L", "proj", *rd]
+    cmd = [os.path.join(bindir, w.binary), "-N", str(threads), *extra, *w.load_args(), "-L", "proj", *rd]
     t0 = time.time()
     out = open(sam_path, "wb") if sam_path else subprocess.DEVNULL
     r = subprocess.run(cmd, cwd=workdir, stdout=out, stderr=subprocess.PIPE, text=True, env=env)
