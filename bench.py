@@ -460,6 +460,7 @@ def measure(a, w, n_reads, rank, world, local_rank, ncores, compact=False):
 
     # ---- device-resident timed region: exactly K steps -------------------------------------------
     dpx_peak = ctx.dpx_peak()
+    fp64_peak_live = ctx.fp64_peak()
     ctx.stage_times_reset()
     with ClockSampler(local_rank) as clk:
         barrier()
@@ -581,13 +582,12 @@ def measure(a, w, n_reads, rank, world, local_rank, ncores, compact=False):
         # instructions each in the libm transcription (glibc_math.cuh); against the nominal FP64 issue rate (64 lanes
         # per clock and SM at the measured SM clock -- MEASURED_PEAKS.json has no FP64 figure)
         fp64_instr = st["post_sw_columns"] * 16.0 * (3 * 11 + 2 * 20)
-        sm_mhz = clocks.get("sm_mhz") or 1965.0
-        fp64_peak = 148 * 64 * sm_mhz * 1e6 / 1e9
+        fp64_peak = fp64_peak_live
         roofs["post_sw"] = {"kernel": "post_sw_kernel", "bound": "fp64", "achieved": fp64_instr / (post_ms * 1e-3) / 1e9,
                             "peak": fp64_peak, "unit": "G FP64 instr/s",
                             "frac": fp64_instr / (post_ms * 1e-3) / 1e9 / fp64_peak, "traffic": None,
                             "columns_per_s": st["post_sw_columns"] / (post_ms * 1e-3), "ms_per_step": post_ms,
-                            "peak_source": "nominal: 148 SMs x 64 FP64 lanes x the SM clock sampled during the run"}
+                            "peak_source": "measured live: register-resident DFMA chains (shrimp_gpu_fp64_peak)"}
     # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture per launch; only for the
     # configuration the capture was taken on (profiles/r01h_ncu_full_scan_kernel_raw.csv, r01f_ncu_full_post_sw_raw.csv: C2, 1 M reads per launch)
     if w.key in ("c2", "c2nomq") and n_reads == 1_000_000:

@@ -349,6 +349,9 @@ int shrimp_gpu_flush_l2(shrimp_gpu_ctx *ctx);
  * bench.py uses it as the denominator of the sw_vector roofline.
  * ---------------------------------------------------------------------------------------- */
 int shrimp_gpu_dpx_peak(shrimp_gpu_ctx *ctx, double *ginstr_per_s);
+/* ... and the FP64 issue peak (giga thread-level DFMA per second, register-resident chains), the denominator of the
+ * post_sw roofline. */
+int shrimp_gpu_fp64_peak(shrimp_gpu_ctx *ctx, double *ginstr_per_s);
 
 /* Host threads of the stages that stay on the CPU as in the reference (read_pass2's duplicate removal and ranking,
  * the -N threads of gmapper.c:2907): n > 0 fixes the count, 0 = the OpenMP default. Process-wide. */

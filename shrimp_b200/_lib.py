@@ -118,6 +118,8 @@ def lib() -> C.CDLL:
     L.shrimp_gpu_sw_full_batch_xover.restype = i32
     L.shrimp_gpu_dpx_peak.argtypes = [vp, C.POINTER(C.c_double)]
     L.shrimp_gpu_dpx_peak.restype = i32
+    L.shrimp_gpu_fp64_peak.argtypes = [vp, C.POINTER(C.c_double)]
+    L.shrimp_gpu_fp64_peak.restype = i32
     L.shrimp_gpu_set_host_threads.argtypes = [C.c_int]
     L.shrimp_gpu_set_host_threads.restype = i32
     L.shrimp_gpu_glibc_explog.argtypes = [vp, vp, C.c_int, vp, vp]

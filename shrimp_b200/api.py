@@ -471,6 +471,12 @@ class GpuContext:
         check(self._L.shrimp_gpu_dpx_peak(self._h, C.byref(v)), "shrimp_gpu_dpx_peak")
         return float(v.value)
 
+    def fp64_peak(self) -> float:
+        """Measured FP64 issue peak in G thread-instructions/s (DFMA)."""
+        v = C.c_double()
+        check(self._L.shrimp_gpu_fp64_peak(self._h, C.byref(v)), "shrimp_gpu_fp64_peak")
+        return float(v.value)
+
     # ---- accounting ---------------------------------------------------------------------------
     def launch_count(self) -> int:
         return int(self._L.shrimp_gpu_launch_count(self._h))

@@ -1,6 +1,7 @@
 // Internal header of libshrimp_b200.so: context, error plumbing, device buffers, bit helpers.
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -119,6 +120,19 @@ struct SwScores {
 // attribute is per function and process-wide, so setting it to the size of ONE launch would race with the launches of
 // the other host threads' contexts (a smaller value set in between makes a launch fail with "invalid argument").
 #define SHRIMP_MAX_DYN_SMEM (227 * 1024)
+// ... minus the kernel's static shared memory; once per kernel and device
+#define SH_OPT_IN_SMEM(K, DEVICE)                                                                              \
+  do {                                                                                                         \
+    static std::atomic<unsigned long long> _done{0ull};                                                        \
+    const unsigned long long _bit = 1ull << ((DEVICE) & 63);                                                   \
+    if (!(_done.load() & _bit)) {                                                                              \
+      cudaFuncAttributes _fa;                                                                                  \
+      SH_CUDA(cudaFuncGetAttributes(&_fa, K));                                                                 \
+      SH_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize,                             \
+                                   SHRIMP_MAX_DYN_SMEM - (int)_fa.sharedSizeBytes));                           \
+      _done.fetch_or(_bit);                                                                                    \
+    }                                                                                                          \
+  } while (0)
 
 #define SHRIMP_AUX_STREAMS 4
 

@@ -440,6 +440,25 @@ int chunk_begin(Chunk &C, shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, int 
     set_error("%s: read length %d exceeds the qrlen given at setup (%d)", who, C.max_rl, ctx->sw.max_read_len);
     return SHRIMP_E_ARG;
   }
+  if (mp->num_outputs < 1 || mp->num_tmp_outputs < mp->num_outputs || mp->num_tmp_outputs > 4096) {
+    set_error("%s: num_outputs %d / num_tmp_outputs %d (need 1 <= num_outputs <= num_tmp_outputs)", who, mp->num_outputs,
+              mp->num_tmp_outputs);
+    return SHRIMP_E_ARG;
+  }
+  if (mp->region_bits < 4 || mp->region_bits > 24 || mp->region_overlap < 0 ||
+      mp->region_overlap >= (1 << mp->region_bits)) {
+    set_error("%s: region_bits %d / region_overlap %d out of range", who, mp->region_bits, mp->region_overlap);
+    return SHRIMP_E_ARG;
+  }
+  if (!resident && cs && mp->crossover_scores && mp->crossover_stride > 0 && mp->crossover_stride < C.max_rl) {
+    set_error("%s: crossover_stride %d is shorter than the longest read (%d)", who, mp->crossover_stride, C.max_rl);
+    return SHRIMP_E_ARG;
+  }
+  if (!resident && cs && mp->read_quals && mp->qual_stride > 0 &&
+      mp->qual_stride < C.max_rl + (mp->qual_vector_offset > 0 ? mp->qual_vector_offset : 0)) {
+    set_error("%s: qual_stride %d is shorter than the longest read (%d)", who, mp->qual_stride, C.max_rl);
+    return SHRIMP_E_ARG;
+  }
   SH_CUDA(cudaSetDevice(ctx->device));
   if (!ctx->pipeline) ctx->pipeline = new Pipeline();
   Pipeline *pl = C.pl = (Pipeline *)ctx->pipeline;

@@ -165,9 +165,11 @@ __global__ void __launch_bounds__(128, PS_CTAS_PER_SM) post_sw_kernel(const Post
         const int j = R.read_start + col;
         const int c = (int)extract4(read, (uint64_t)j);
         PsCol pc;
+        int gl = 15;   // genome letter of a match column
         if (type == 3) {
           const int g = (int)extract4(genome, g0 + (uint64_t)(genbase + ig - isgen));
           pc.let = (int8_t)(g <= 3 ? g : -1);
+          gl = g <= 3 ? g : 15;
         } else {
           pc.let = -2;
         }
@@ -185,7 +187,9 @@ __global__ void __launch_bounds__(128, PS_CTAS_PER_SM) post_sw_kernel(const Post
             pc.q = 0;
           }
         }
-        pc.call = (int8_t)(c == 15 ? 15 : (((kk + init_bp) & 3) ^ (int)pxs[j]));
+        // base_call = the letter qralign shows (sw-post.c:519): the layer's letter -- or, for an unknown colour, the
+        // genome's letter that pretty_print puts in its place on a match column (sw-full-cs.c:1049-1056)
+        pc.call = (int8_t)(c == 15 ? gl : (((kk + init_bp) & 3) ^ (int)pxs[j]));
         pc.maxp = 0;
         pc.qual = 33;
         pc.pad = 0;
@@ -405,7 +409,7 @@ int launch_post_sw(shrimp_gpu_ctx *ctx, const PostParams &P, DevBuf &scratch) {
   }
   const size_t smem = per_half * halves;
   auto kern = post_sw_kernel;
-  SH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SHRIMP_MAX_DYN_SMEM));
+  SH_OPT_IN_SMEM(kern, ctx->device);
   int per_sm = 0;
   SH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, halves * 16, smem));
   if (per_sm < 1) per_sm = 1;

@@ -1762,7 +1762,7 @@ __global__ void __launch_bounds__(REPLAY_WARPS * 32) scan_replay_kernel(const Sc
 
 int launch_scan_replay(shrimp_gpu_ctx *ctx, ScanParams &P, uint32_t n_rec, int ks_cap) {
   const size_t smem = (size_t)REPLAY_WARPS * (((size_t)ks_cap * 18 + 47) & ~(size_t)15);
-  SH_CUDA(cudaFuncSetAttribute(scan_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SHRIMP_MAX_DYN_SMEM));
+  SH_OPT_IN_SMEM(scan_replay_kernel, ctx->device);
   scan_replay_kernel<<<(n_rec + REPLAY_WARPS - 1) / REPLAY_WARPS, REPLAY_WARPS * 32, smem, ctx->stream>>>(P, n_rec, ks_cap);
   SH_CUDA(cudaGetLastError());
   SH_LAUNCHED(ctx, ST_SCAN);
@@ -1775,7 +1775,7 @@ size_t scan_cta_smem_bytes(int cap, int max_rl, int k_cap, int bm_log2, int n_pa
 
 int launch_scan(shrimp_gpu_ctx *ctx, ScanParams &P, int warps_per_cta, int n_ctas) {
   const size_t smem = scan_smem_bytes(P.cap, P.max_rl, P.k_cap, P.bm_log2, warps_per_cta, P.stash);
-  SH_CUDA(cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SHRIMP_MAX_DYN_SMEM));
+  SH_OPT_IN_SMEM(scan_kernel, ctx->device);
   scan_kernel<<<n_ctas, warps_per_cta * 32, smem, ctx->stream>>>(P, warps_per_cta);
   SH_CUDA(cudaGetLastError());
   SH_LAUNCHED(ctx, ST_SCAN);
@@ -1785,10 +1785,10 @@ int launch_scan(shrimp_gpu_ctx *ctx, ScanParams &P, int warps_per_cta, int n_cta
 int launch_scan_cta(shrimp_gpu_ctx *ctx, ScanParams &P, int n_ctas, int threads) {
   const size_t smem = scan_cta_smem_bytes(P.cap, P.max_rl, P.k_cap, P.bm_log2, P.n_part, P.win, P.g_ent != nullptr);
   if (P.g_ent) {
-    SH_CUDA(cudaFuncSetAttribute(scan_cta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SHRIMP_MAX_DYN_SMEM));
+    SH_OPT_IN_SMEM(scan_cta_kernel<true>, ctx->device);
     scan_cta_kernel<true><<<n_ctas, threads, smem, ctx->stream>>>(P);
   } else {
-    SH_CUDA(cudaFuncSetAttribute(scan_cta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SHRIMP_MAX_DYN_SMEM));
+    SH_OPT_IN_SMEM(scan_cta_kernel<false>, ctx->device);
     scan_cta_kernel<false><<<n_ctas, threads, smem, ctx->stream>>>(P);
   }
   SH_CUDA(cudaGetLastError());

@@ -224,7 +224,7 @@ def test_mixed_lengths_fastq_and_n(colour, tmp_path):
     with open(os.path.join(str(tmp_path), "mixed.fq"), "wb") as f:
         for name, s, q in reads:
             f.write(b"@" + name.encode() + b"\n" + s + b"\n+\n" + q + b"\n")
-    args = ["-Q", "--longest-read", "380", "mixed.fq", "genome.fa"]
+    args = ["-Q", "--qv-offset", "33", "--longest-read", "380", "mixed.fq", "genome.fa"]
     ref, _ = run_sam(REF, case.binary, args, str(tmp_path), 4)
     new, _ = run_sam(NEW, case.binary, args, str(tmp_path), 2, ["-K", "250"])
     assert_same_sam(ref, new)

@@ -61,7 +61,10 @@ def test_projection_load_equals_build(name, source, tmp_path):
         params = MapParams(list_cutoff=case.list_cutoff, **opts)
         ra = a.map_reads(params, case.scores, case.packed, case.read_len, initbp=case.initbp)
         rb = b.map_reads(params, case.scores, case.packed, case.read_len, initbp=case.initbp)
-        assert len(ra.hits) > 100 and ra.hits.tobytes() == rb.hits.tobytes() and ra.edits.tobytes() == rb.edits.tobytes()
+        assert len(ra.hits) > 100 and len(ra.hits) == len(rb.hits) and ra.edits.tobytes() == rb.edits.tobytes()
+        for f in ra.hits.dtype.names:
+            if f != "hit_slot":   # the slot a hit got in the chunk's hit buffer depends on the order of the reservations
+                assert np.array_equal(ra.hits[f], rb.hits[f]), f
     finally:
         b.close()
         a.close()
