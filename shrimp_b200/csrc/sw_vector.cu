@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(SWV_BLOCK) sw_vector_kernel(const SwvParams P)
         uint32_t d0B = j < glenB ? (b0 << sh) : DPAD;
         dn0 = ~(d0A | (d0B << 16));
       }
-      uint32_t hd = diag, f = 0;
+      uint32_t hd = diag, f = 0, hd_pair = 0;
       if (strip > 0) {
         size_t o = (size_t)j * P.n_threads;
         diag = bH[o];  // H(row0-1, j): diagonal input of the next column
@@ -165,7 +165,8 @@ __global__ void __launch_bounds__(SWV_BLOCK) sw_vector_kernel(const SwvParams P)
         h[r] = H;
         e[r] = __viaddmax_s16x2(e[r], NAE, H);
         f = __viaddmax_s16x2(f, NBE, H);
-        best = vmax2(best, H);
+        if (r & 1) best = __vimax3_s16x2(best, hd_pair, H);   // one three-way maximum per two rows (T is even)
+        else hd_pair = H;
       }
       if (P.n_strips > 1) {
         size_t o = (size_t)j * P.n_threads;
