@@ -833,6 +833,10 @@ int chunk_scan(Chunk &C) {
         P.prof = pl->d_prof.as<unsigned long long>();
       }
       uint32_t level_work[3] = {0, 0, 0};
+      // global-slab launches: the candidate arrays are in global memory, shared memory holds the bitmaps and the k-mer
+      // tables only -- as many 512-thread CTAs per SM as that leaves room for (three at most: 1536 threads)
+      const int glob_per_sm = (int)std::max<size_t>(1, std::min<size_t>(3, (size_t)(227 * 1024) /
+          (scan_cta_smem_bytes(1, max_rl, big_k_cap, cta_bm_log2, cta_n_part, cta_win, true) + 1024)));
       int big_slab = 8192;
       while (big_slab > cta_cap && scan_cta_smem_bytes(big_slab, max_rl, big_k_cap, cta_bm_log2, cta_n_part, cta_win, false) > 224 * 1024)
         big_slab >>= 1;
@@ -855,7 +859,7 @@ int chunk_scan(Chunk &C) {
           if (const char *e = getenv("SHRIMP_SCAN_CTA_THREADS")) threads = std::max(32, std::min(768, atoi(e) & ~31));
           ctas = (int)std::min<uint32_t>((uint32_t)(ctx->sm_count * per_sm), n_work);
         } else {
-          ctas = (int)std::min<uint32_t>((uint32_t)ctx->sm_count, n_work);
+          ctas = (int)std::min<uint32_t>((uint32_t)(ctx->sm_count * glob_per_sm), n_work);
           threads = 512;
           const size_t per_cta = (size_t)(g_cap + 1) * 8 + (size_t)(g_cap + 1) * sizeof(AnchorRec) +
                                  (size_t)((g_cap + 15) & ~7) * 2 + (size_t)(g_cap / 32 + 2) * 4;
@@ -926,7 +930,7 @@ int chunk_scan(Chunk &C) {
           } else {
             // the global slabs of the level-2 launch above
             P.resume_min = level_work[1] ? big_slab : cta_cap;
-            ctas = (int)std::min<uint32_t>((uint32_t)ctx->sm_count, level_work[2]);
+            ctas = (int)std::min<uint32_t>((uint32_t)(ctx->sm_count * glob_per_sm), level_work[2]);
             threads = 512;
             unsigned char *base = pl->d_scan_slab.as<unsigned char>();
             P.g_ent = (unsigned long long *)base;

@@ -1417,7 +1417,14 @@ __global__ void __launch_bounds__(SCAN_CTA_MAX_THREADS, 2) scan_cta_kernel(const
         for (int bin = 0; bin < 64; bin++) {
           const int n = (int)(s_boff[bin + 1] - s_boff[bin]);
           if (n <= 128) continue;
-          unsigned long long *a = scratch + s_boff[bin];
+          unsigned long long *const a_glob = scratch + s_boff[bin];
+          // global slabs: the bin is sorted in shared memory (the bitmaps are dead by now) and written back
+          const bool staged = glob && (size_t)n * 8 <= ((size_t)2 << P.bm_log2) / 8;
+          unsigned long long *a = staged ? (unsigned long long *)bm1 : a_glob;
+          if (staged) {
+            for (int t = tid; t < n; t += nthr) a[t] = a_glob[t];
+            __syncthreads();
+          }
           int P2 = 256;
           while (P2 < n) P2 <<= 1;
           for (int k = 2; k <= P2; k <<= 1) {
@@ -1448,6 +1455,10 @@ __global__ void __launch_bounds__(SCAN_CTA_MAX_THREADS, 2) scan_cta_kernel(const
               }
               __syncthreads();
             }
+          }
+          if (staged) {
+            for (int t = tid; t < n; t += nthr) a_glob[t] = a[t];
+            __syncthreads();
           }
         }
         __syncthreads();
@@ -1707,7 +1718,15 @@ __global__ void __launch_bounds__(REPLAY_WARPS * 32) scan_replay_kernel(const Sc
   // heads of the lists, in ascending slot order (the load order of mapping.c:913-935)
   for (int k = lane; k < Ks; k += 32) {
     const uint32_t t = first_of[k];
-    stage[k] = t == 0xffffu ? ~0ull : ((ent[t] & 0xffffffffffff0000ull) | t);
+    unsigned long long el = ~0ull;
+    if (t != 0xffffu) {
+      const unsigned long long e = ent[t];
+      el = (e & 0xffffffffffff0000ull) | t;
+      const uint32_t nx = ((uint32_t)e >> 16) & 0xffffu;
+      // the successor of an element that sits in the heap is needed when that element pops: fetch it now
+      if (nx != 0xffffu) asm volatile("prefetch.global.L1 [%0];" ::"l"(ent + nx));
+    }
+    stage[k] = el;
   }
   __syncwarp();
   if (lane != 0) return;
@@ -1731,7 +1750,10 @@ __global__ void __launch_bounds__(REPLAY_WARPS * 32) scan_replay_kernel(const Sc
     order[outn++] = (uint16_t)((uint32_t)root & 0xffffu);
     const uint32_t nx = ((uint32_t)root >> 16) & 0xffffu;
     if (nx != 0xffffu) {
-      heap[0] = (ent[nx] & 0xffffffffffff0000ull) | nx;  // heap_uu_replace_min
+      const unsigned long long e = ent[nx];
+      const uint32_t nx2 = ((uint32_t)e >> 16) & 0xffffu;
+      if (nx2 != 0xffffu) asm volatile("prefetch.global.L1 [%0];" ::"l"(ent + nx2));
+      heap[0] = (e & 0xffffffffffff0000ull) | nx;  // heap_uu_replace_min
     } else {
       load--;  // heap_uu_extract_min
       if (load > 0) heap[0] = heap[load];
