@@ -120,7 +120,7 @@ def test_dropin_exports_the_reference_symbols():
 
 
 # ---- bench-size genomes (BASELINE.json configs) through the drop-in -------------------------------------------------
-def _bench_case(key, n_reads, tmp_path, extra=()):
+def _bench_case(key, n_reads, tmp_path, extra=(), genome_mb=300):
     """reads.fa of a bench.py workload + the projection held in HBM saved in the -S format (byte-identical to
     `gmapper -S`, tests/test_gpu_index.py), loaded by both binaries with -L so that the reference's serial index build
     stays out of the test"""
@@ -131,7 +131,7 @@ def _bench_case(key, n_reads, tmp_path, extra=()):
     w = copy.copy(bench.WORKLOADS[key])
     w._genome = None
     if key == "c3":
-        w.resize(300)
+        w.resize(genome_mb)
     codes, _ = w.reads(n_reads, 31)
     ctx = bench.build_context(w, 0)[0]
     try:
@@ -175,6 +175,25 @@ def test_c5_sensitive_full_genome(tmp_path):
 @pytest.mark.gpu
 def test_c3_pairs_300mb_sample(tmp_path):
     assert _bench_case("c3", 8_000, tmp_path) > 6_000
+
+
+@needs_bins
+@pytest.mark.gpu
+def test_c3_pairs_hg18_size_prefix(tmp_path):
+    """configs[2] at its full genome size: 5,000 pairs of 2 x 100 bp against the 3 Gb genome in 24 contigs (a 36 GB
+    projection, saved from HBM and loaded by both binaries with -L): the drop-in's SAM equals the reference's.  Needs
+    host memory for the reference's copy of the projection and disk for the files."""
+    import shutil
+
+    import psutil
+    if psutil.virtual_memory().available < 120e9 or shutil.disk_usage(str(tmp_path)).free < 60e9:
+        pytest.skip("needs 120 GB of host memory and 60 GB of disk")
+    try:
+        assert _bench_case("c3", 10_000, tmp_path, genome_mb=3000) > 9_000
+    finally:
+        for f in os.listdir(str(tmp_path)):
+            if f.startswith("proj."):
+                os.remove(os.path.join(str(tmp_path), f))
 
 
 def _mixed_reads(case, rng, n, lo, hi, n_frac, colour):

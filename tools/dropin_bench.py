@@ -36,6 +36,34 @@ def run_binary(bindir, w, workdir, threads, reads_fa, extra, sam_path=None, env=
     return float(m.group(1)), wall, r.stderr
 
 
+def run_split(bindir, w, d, codes, procs, threads, chunk, env):
+    """the read set cut into `procs` files, one gmapper process each, all started together: aggregate reads/s =
+    all reads / the longest "Read Mapping Time" (the processes load the same projection and start mapping together)"""
+    n = codes.shape[0]
+    per = ((n // procs) + 1) & ~1
+    jobs = []
+    for p in range(procs):
+        part = codes[p * per:(p + 1) * per]
+        if part.shape[0] == 0:
+            continue
+        w.write_reads_fasta(os.path.join(d, f"part{p}.fa"), part)
+        rd = ["-1", f"part{p}.fa.1", "-2", f"part{p}.fa.2"] if w.paired else [f"part{p}.fa"]
+        cmd = [os.path.join(bindir, w.binary), "-N", str(threads), "-K", str(chunk), *w.load_args(), "-L", "proj", *rd]
+        jobs.append((part.shape[0], cmd))
+    t0 = time.time()
+    running = [(nr, subprocess.Popen(cmd, cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, env=env))
+               for nr, cmd in jobs]
+    secs = []
+    for nr, pr in running:
+        err = pr.communicate()[1]
+        if pr.returncode != 0:
+            raise RuntimeError("split run failed: " + err[-800:])
+        secs.append(float(re.search(r"Read Mapping Time:\s+([0-9.]+) seconds", err).group(1)))
+    wall = time.time() - t0
+    return {"procs": procs, "threads_each": threads, "chunk": chunk, "map_s_max": max(secs), "wall_s": wall,
+            "reads_per_s": n / max(secs)}
+
+
 def sam_body(path):
     with open(path, "rb") as f:
         return [ln for ln in f.read().split(b"\n") if not ln.startswith(b"@PG")]
@@ -51,6 +79,8 @@ def main():
     ap.add_argument("--diff", type=int, default=0, help="also diff the SAM of the first N reads against the reference")
     ap.add_argument("--genome-mb", type=int, default=0)
     ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--procs", default="", help="also run the read file split over P concurrent processes (comma list), "
+                    "the reference's own way of scaling past its serial parser (SPLITTING_AND_MERGING)")
     a = ap.parse_args()
     w = bench.WORKLOADS[a.workload]
     if a.genome_mb or w.key == "c3":
@@ -70,6 +100,9 @@ def main():
                 print(json.dumps(out["runs"][-1]), flush=True)
                 for ln in [x for x in err.splitlines() if x.startswith("[gmapper-b200]")][:3]:
                     print("   ", ln, flush=True)
+        for P in [int(x) for x in a.procs.split(",") if x]:
+            out["runs"].append(run_split(NEW_DIR, w, d, codes, P, max(1, ncores // P), int(a.chunk.split(",")[0]), env))
+            print(json.dumps(out["runs"][-1]), flush=True)
         if a.diff:
             n = a.diff & ~1
             w.write_reads_fasta(os.path.join(d, "sub.fa"), codes[:n])
