@@ -1,0 +1,772 @@
+/*
+ * fast_io.cpp -- SURVEY section 8 row f2: the two host-side string paths that bound the drop-in once the mapping
+ * itself runs on the GPU (the serial FASTA/FASTQ reader inside gmapper.c's
+ * `omp critical (fill_reads_buffer)`, gmapper.c:338, and the SAM record formatter).
+ *
+ *     bool fasta_get_next_read_with_range(fasta_t, read_entry *)                        common/fasta.c:316
+ *     void hit_output(read_entry *, read_hit *, read_hit *, bool, int *, int, bool)     gmapper/output.c:227
+ *
+ * Both carry the reference's C++ linkage and signatures.  integration/Makefile links them over the reference's own
+ * definitions, which `objcopy --weaken-symbol` turns weak in a COPY of the reference's unchanged fasta.o / output.o
+ * (all references in output.o itself go through the symbol, R_X86_64_PLT32, so read_output / readpair_output --
+ * output.c:955, :1070, compiled unchanged -- call this formatter).  The reference's hit_output stays reachable as
+ * `shrimp_ref_hit_output` (objcopy --add-symbol at its address): the output forms this file does not restate (the
+ * old SHRiMP format of -E-less runs, --bfast, --extra-sam-fields) and anything unusual go there.
+ *
+ * Reader: the reference copies every byte three times (gzread block -> line buffer -> parse buffer -> malloc'd
+ * string, util.c:949-1040, fasta.c:344-500), one byte at a time; here lines are found with memchr in one large block
+ * read straight from the same gzFile (plain or gzip input alike) and copied once.  Same strings, same trailing
+ * 17 zero bytes, same `free()`-able allocations, same return values and messages on malformed input.
+ *
+ * Formatter: the reference builds a record with ~12 snprintf calls and ~10 malloc/free pairs (cigar_t, cigar
+ * string, VLAs, reverse-complement scratch); here one pass writes the bytes into the thread's output buffer.
+ * Everything that decides a byte of the record (flag bits, POS of a reverse-strand hit, CIGAR runs, the IUPAC
+ * rule of the SEQ column, Z0..Z6 through the same libm `log`) follows output.c line by line, cited below.
+ */
+#include <ctype.h>
+#include <math.h>
+#include <omp.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <zlib.h>
+
+#include "gmapper/gmapper.h"
+#include "gmapper/output.h"
+#include "common/fasta.h"
+#include "common/util.h"
+#include "common/my-alloc.h"
+#include "common/sw-full-common.h"
+
+// the reference's own hit_output (integration/Makefile: objcopy --add-symbol on the copy of output.o)
+extern "C" void shrimp_ref_hit_output(struct read_entry *, struct read_hit *, struct read_hit *, bool, int *, int, bool);
+
+namespace {
+
+// ================================================================================================================
+// Reader
+// ================================================================================================================
+struct Reader {
+  fasta_t owner = NULL;
+  char *buf = NULL;
+  size_t cap = 0, pos = 0, end = 0;
+  bool eof = false;
+  bool header = true;     // util.c:985: '#' lines before the first record are dropped by the line reader itself
+  // one entry's text, assembled when a line spans block boundaries or an entry has several sequence lines
+  char *acc = NULL;
+  size_t acc_cap = 0;
+};
+
+enum { MAX_READERS = 16 };
+Reader g_readers[MAX_READERS];
+
+Reader *reader_of(fasta_t f) {
+  for (int i = 0; i < MAX_READERS; i++)
+    if (g_readers[i].owner == f) return &g_readers[i];
+  for (int i = 0; i < MAX_READERS; i++)
+    if (g_readers[i].owner == NULL) {
+      Reader *r = &g_readers[i];
+      r->owner = f;
+      r->cap = (size_t)16 << 20;
+      r->buf = (char *)xmalloc(r->cap);
+      r->pos = r->end = 0;
+      r->eof = false;
+      r->header = f->header;
+      return r;
+    }
+  fprintf(stderr, "error: more than %d read files open\n", (int)MAX_READERS);
+  exit(1);
+}
+
+// more bytes behind the unread tail; false at the end of the file
+bool refill(Reader *r) {
+  if (r->eof) return false;
+  if (r->pos > 0) {
+    memmove(r->buf, r->buf + r->pos, r->end - r->pos);
+    r->end -= r->pos;
+    r->pos = 0;
+  }
+  if (r->end == r->cap) return false;   // a line longer than the block: the caller takes it in pieces
+  const int want = (int)((r->cap - r->end) > ((size_t)1 << 30) ? ((size_t)1 << 30) : (r->cap - r->end));
+  const int got = gzread(r->owner->fp, r->buf + r->end, (unsigned)want);
+  if (got <= 0) {
+    r->eof = true;
+    return false;
+  }
+  r->end += (size_t)got;
+  return true;
+}
+
+// The next piece of input as fast_gzgets_safe (util.c:949) would hand it out: up to and including a newline, or what
+// is left of an over-long line / of the file.  *nl tells whether the piece ends a line.  NULL at the end of the file.
+const char *next_piece(Reader *r, size_t *len, bool *nl) {
+  for (;;) {
+    const char *s = r->buf + r->pos;
+    const char *e = (const char *)memchr(s, '\n', r->end - r->pos);
+    if (e) {
+      *len = (size_t)(e - s);
+      *nl = true;
+      r->pos += *len + 1;
+      if (r->header) {
+        if (*len > 0 && s[0] == '#') continue;   // util.c:985-990
+        r->header = false;
+      }
+      return s;
+    }
+    if (refill(r)) continue;
+    if (r->end > r->pos) {   // block full without a newline, or the last line of a file that does not end in one
+      *len = r->end - r->pos;
+      *nl = false;
+      r->pos = r->end;
+      return s;
+    }
+    return NULL;
+  }
+}
+
+// first byte of the next piece without taking it; -1 at the end of the file.  (Only used behind a name line, where
+// the header comments of util.c:985 are over.)
+int peek_first(Reader *r) {
+  for (;;) {
+    if (r->pos < r->end) return (unsigned char)r->buf[r->pos];
+    if (!refill(r)) return -1;
+  }
+}
+
+void acc_reserve(Reader *r, size_t n) {
+  if (n <= r->acc_cap) return;
+  size_t c = r->acc_cap ? r->acc_cap : 4096;
+  while (c < n) c *= 2;
+  r->acc = (char *)xrealloc(r->acc, c);
+  r->acc_cap = c;
+}
+
+// fasta.c's loops stop copying a piece at a NUL byte (`fasta->buffer[i] != '\0'`)
+inline size_t text_len(const char *s, size_t len) {
+  const void *z = memchr(s, 0, len);
+  return z ? (size_t)((const char *)z - s) : len;
+}
+
+char *dup17(const char *s, size_t len) {   // "allocate extra space to appease valgrind", fasta.c:381-383
+  char *p = (char *)xmalloc(len + 17);
+  memcpy(p, s, len);
+  memset(p + len, 0, 17);
+  return p;
+}
+
+// extract_name, fasta.c:243-281: the text after '>' / '@' up to the first tab, trimmed, cut at its first blank; a
+// second tab-separated field is the range string
+char *extract_name_fast(char *line, char **ranges) {
+  char *save = NULL;
+  char *tok = strtok_r(line + 1, "\t", &save);
+  tok = strtrim(tok);
+  const int full = (int)strlen(tok);
+  int len = 0;
+  while (len < full && tok[len] != ' ' && tok[len] != '\t') len++;
+  char *ret = dup17(tok, (size_t)len);
+  if (ranges != NULL && (tok = strtok_r(NULL, "\t", &save)) != NULL) *ranges = dup17(tok, strlen(tok));
+  return ret;
+}
+
+}  // namespace
+
+bool fasta_get_next_read_with_range(fasta_t fasta, read_entry *re) {   // fasta.c:316
+  Reader *r = reader_of(fasta);
+  const char c = fasta->fastq ? '@' : '>';
+  re->name = re->seq = NULL;
+  re->paired = false;
+  re->first_in_pair = false;
+  re->mate_pair = NULL;
+
+  // ---- the name line (fasta.c:340-384); comment lines ('#') in front of it are skipped
+  size_t name_len = 0;
+  bool end_of_line = false;
+  size_t len;
+  bool nl;
+  const char *s;
+  while ((s = next_piece(r, &len, &nl)) != NULL) {
+    const size_t tl = text_len(s, len);
+    acc_reserve(r, name_len + tl + 1);
+    memcpy(r->acc + name_len, s, tl);
+    name_len += tl;
+    const char first = name_len ? r->acc[0] : '\0';
+    if (first != '#' && first != c) {
+      if (c == '>' && first == '@')
+        fprintf(stderr, "Expecting \">\" but got \"%c\" are you sure it's not FASTQ format?\n", first);
+      else if (c == '@' && first == '>')
+        fprintf(stderr, "Expecting \"@\" but got \"%c\" are you sure it's not FASTA format?\n", first);
+      else
+        fprintf(stderr, "Expecting \"%c\" but got \"%c\" are you sure it's right format?\n", c, first);
+      return false;
+    }
+    if (nl) {
+      if (s[0] == '#' && len > 0) {   // fasta.c:366-370 tests the piece, not the assembled line
+        name_len = 0;
+        continue;
+      }
+      end_of_line = true;
+      r->acc[name_len] = '\0';
+      re->name = extract_name_fast(r->acc, &re->range_string);
+      break;
+    }
+  }
+  if (name_len == 0) return false;
+  if (name_len <= 1 || !end_of_line) {
+    r->acc[name_len] = '\0';
+    fprintf(stderr, "error: Invalid read name! Are you sure this is a FASTA or FASTQ file?\n%s\n", r->acc);
+    return false;
+  }
+
+  // ---- the sequence (fasta.c:389-417): every line up to the next '>' (FASTA) or the '+' line (FASTQ)
+  size_t seq_len = 0;
+  bool at_line_start = true;
+  bool plus_seen = false;
+  for (;;) {
+    if (at_line_start) {
+      const int f = peek_first(r);
+      if (f < 0) break;
+      if (fasta->fastq && f == '+') {
+        plus_seen = true;
+        break;
+      }
+      if (!fasta->fastq && f == '>') break;   // stays unread: the reference's `leftover`
+    }
+    s = next_piece(r, &len, &nl);
+    if (s == NULL) break;
+    const bool comment = at_line_start && len > 0 && s[0] == '#';
+    // (a continuation piece of an over-long line is appended whatever it starts with)
+    at_line_start = nl;
+    if (comment) continue;
+    const size_t tl = text_len(s, len);
+    acc_reserve(r, seq_len + tl + 1);
+    memcpy(r->acc + seq_len, s, tl);
+    seq_len += tl;
+  }
+  if (seq_len == 0) {
+    fprintf(stderr, "Read in sequence of length zero!\n");
+    return false;
+  }
+  re->seq = dup17(r->acc, seq_len);
+  re->orig_seq = re->seq;
+
+  if (fasta->fastq) {
+    // ---- the '+' line (fasta.c:418-447)
+    size_t plus_len = 0;
+    bool plus_nl = false;
+    if (plus_seen) {
+      while ((s = next_piece(r, &len, &nl)) != NULL) {
+        const size_t tl = text_len(s, len);
+        acc_reserve(r, plus_len + tl + 1);
+        memcpy(r->acc + plus_len, s, tl);
+        plus_len += tl;
+        if (nl) {
+          plus_nl = true;
+          break;
+        }
+      }
+    }
+    if (plus_len < 1 || !plus_nl) {
+      fprintf(stderr, "error: Error while readingin FASTQ entry!\n");
+      return false;
+    }
+    re->plus_line = dup17(r->acc, plus_len);
+
+    // ---- the qualities (fasta.c:452-506): lines until there are as many as bases (colour space: one less)
+    const size_t want = fasta->space == LETTER_SPACE ? seq_len : seq_len - 1;
+    size_t qual_len = 0;
+    while ((s = next_piece(r, &len, &nl)) != NULL) {
+      const size_t tl = text_len(s, len);
+      acc_reserve(r, qual_len + tl + 1);
+      memcpy(r->acc + qual_len, s, tl);
+      qual_len += tl;
+      if (qual_len == want) break;
+      if (qual_len > seq_len) {
+        fprintf(stderr, "There has been a problem reading in the read \"%s\", the quality length exceeds the sequence length!\n",
+                re->name);
+        fprintf(stderr, "Are you using the right executable? gmapper-cs for color space? and gmapper-ls for letter space?\n");
+        exit(1);
+      }
+    }
+    if (qual_len != want) {
+      fprintf(stderr, "Read in quality string of wrong length!, %d vs %d\n", (int)qual_len, (int)seq_len);
+      free(re->seq);
+      free(re->plus_line);
+      return false;
+    }
+    re->qual = (char *)xmalloc(qual_len + 17);
+    for (size_t i = 0; i < qual_len; i++) re->qual[i] = MAX((char)r->acc[i], '!');
+    memset(re->qual + qual_len, 0, 17);
+    re->orig_qual = re->qual;
+  }
+
+  // ---- RNA? (fasta.c:524-538)
+  bool got_uracil = false, got_thymine = false;
+  for (size_t j = 0; j < seq_len; j++) {
+    const unsigned char chr = (unsigned char)re->seq[j];
+    got_thymine |= (chr == 'T' || chr == 't');
+    got_uracil |= (chr == 'U' || chr == 'u');
+  }
+  if (got_uracil && got_thymine) fprintf(stderr, "WARNING: sequence has both uracil and thymine!?!\n");
+  re->is_rna = (got_uracil && !got_thymine);
+  return true;
+}
+
+void fasta_close(fasta_t fasta) {   // fasta.c:208-220, plus this file's block
+  for (int i = 0; i < MAX_READERS; i++)
+    if (g_readers[i].owner == fasta) {
+      free(g_readers[i].buf);
+      free(g_readers[i].acc);
+      g_readers[i] = Reader();
+    }
+  gzclose(fasta->fp);
+  free(fasta->file);
+  free(fasta->parse_buffer);
+  if (fasta->save_buf != NULL) free(fasta->save_buf);
+  free(fasta);
+}
+
+// ================================================================================================================
+// Formatter
+// ================================================================================================================
+namespace {
+
+inline char *put_str(char *p, const char *s) {
+  const size_t n = strlen(s);
+  memcpy(p, s, n);
+  return p + n;
+}
+inline char *put_mem(char *p, const char *s, size_t n) {
+  memcpy(p, s, n);
+  return p + n;
+}
+inline char *put_u64(char *p, unsigned long long v) {
+  char tmp[24];
+  int n = 0;
+  do {
+    tmp[n++] = (char)('0' + v % 10);
+    v /= 10;
+  } while (v);
+  while (n) *p++ = tmp[--n];
+  return p;
+}
+inline char *put_int(char *p, int v) {   // %i / %d
+  if (v < 0) {
+    *p++ = '-';
+    return put_u64(p, (unsigned long long)(-(long long)v));
+  }
+  return put_u64(p, (unsigned long long)v);
+}
+inline char *put_uint(char *p, int v) { return put_u64(p, (unsigned long long)(unsigned int)v); }   // %u of an int
+
+// reverse(), output.c:167-220: reverse complement that keeps the case; 0 = a character it stops the run on
+unsigned char g_rc[256];
+// SEQ of an unmapped / clipped letter-space base, output.c:314-336: the ten two- and three-fold IUPAC codes become N
+unsigned char g_ls_seq[256];
+bool g_tables_ready = false;
+void init_tables() {
+  memset(g_rc, 0, sizeof(g_rc));
+  const char *a = "ATCGRYKMBVDH", *b = "TAGCYRMKVBHD";
+  for (int i = 0; a[i]; i++) {
+    g_rc[(int)a[i]] = (unsigned char)b[i];
+    g_rc[(int)a[i] + 32] = (unsigned char)(b[i] + 32);
+  }
+  for (const char *c = "-.NnSsWw"; *c; c++) g_rc[(int)*c] = (unsigned char)*c;
+  for (int i = 0; i < 256; i++) {
+    char c = (char)i;
+    if (strchr("RYSWKMBDHV", c) && c) {
+      g_ls_seq[i] = 'N';
+    } else {
+      if (c >= 'a') c -= 32;
+      g_ls_seq[i] = (unsigned char)c;
+    }
+  }
+  __atomic_store_n(&g_tables_ready, true, __ATOMIC_RELEASE);
+}
+
+}  // namespace
+
+void hit_output(struct read_entry *re, struct read_hit *rh, struct read_hit *rh_mp, bool first_in_pair, int *hits,
+                int satisfying_alignments, bool improper_mapping) {   // output.c:227
+  // what this file does not restate goes to the reference's own code
+  if (!Eflag || extra_sam_fields || (shrimp_mode == MODE_COLOUR_SPACE && Qflag && Bflag)) {
+    shrimp_ref_hit_output(re, rh, rh_mp, first_in_pair, hits, satisfying_alignments, improper_mapping);
+    return;
+  }
+  if (!__atomic_load_n(&g_tables_ready, __ATOMIC_ACQUIRE)) {
+#pragma omp critical(shrimp_fast_io_tables)
+    {
+      if (!g_tables_ready) init_tables();
+    }
+  }
+  const bool cs = shrimp_mode == MODE_COLOUR_SPACE;
+  const size_t name_len = strlen(re->name);
+  const size_t seq_str_len = strlen(re->seq);
+  const size_t qual_str_len = (Qflag && re->qual) ? strlen(re->qual) : 0;
+  struct read_entry *re_mp = re->mate_pair;
+  const bool paired_read = re->paired;
+  const size_t mp_seq_len = (sam_r2 && re_mp && re_mp->seq) ? strlen(re_mp->seq) : 0;
+  const size_t rg_len = sam_read_group_name ? strlen(sam_read_group_name) : 0;
+  const struct sw_full_results *sfr = rh ? rh->sfrp : NULL;
+  const size_t al_len = sfr && sfr->qralign ? strlen(sfr->qralign) : 0;
+
+  // an upper bound of the record; the reference's snprintf calls would cut it at the end of the buffer
+  // (thread_output_buffer_safety = 500 KB is guaranteed below), so anything near that goes to the reference's code
+  const size_t bound = name_len + 3 * seq_str_len + 3 * qual_str_len + mp_seq_len + rg_len + 16 * al_len + 1024;
+  if (bound >= thread_output_buffer_safety || (sfr && (!sfr->qralign || !sfr->dbalign)) ||
+      (paired_read && re_mp == NULL) || (sam_r2 && (re_mp == NULL || re_mp->seq == NULL))) {
+    shrimp_ref_hit_output(re, rh, rh_mp, first_in_pair, hits, satisfying_alignments, improper_mapping);
+    return;
+  }
+
+  // output.c:246-268: room for one record
+  const int thread_id = omp_get_thread_num();
+  while ((size_t)(thread_output_buffer[thread_id] + thread_output_buffer_sizes[thread_id] -
+                  thread_output_buffer_filled[thread_id]) < thread_output_buffer_safety) {
+    const size_t new_size = thread_output_buffer_sizes[thread_id] + thread_output_buffer_increment;
+    const size_t filled = thread_output_buffer_filled[thread_id] - thread_output_buffer[thread_id];
+    thread_output_buffer[thread_id] =
+        (char *)my_realloc(thread_output_buffer[thread_id], new_size, thread_output_buffer_sizes[thread_id],
+                           &mem_thread_buffer, "realloc thread_output_buffer");
+    thread_output_buffer_sizes[thread_id] = new_size;
+    thread_output_buffer_filled[thread_id] = thread_output_buffer[thread_id] + filled;
+  }
+  char *const rec = thread_output_buffer_filled[thread_id];
+  char *p = rec;
+
+  // ---- QNAME (output.c:363-378): for a paired read the common prefix of the two names without a trailing ':' / '/'
+  size_t qname_len = name_len;
+  bool mate_unmapped = false, reverse_strand_mp = false;
+  int genome_start_mp = 0, genome_end_mp = 0, mpos = 0;
+  const char *mrnm = "*";
+  if (paired_read) {
+    const size_t mp_name_len = strlen(re_mp->name);
+    const size_t m = MIN(name_len, mp_name_len);
+    size_t i = 0;
+    while (i < m && re->name[i] == re_mp->name[i]) i++;
+    // (the reference copies the whole name first and then cuts it at the first difference, or at the shorter length)
+    if (i > 0 && (re->name[i - 1] == ':' || re->name[i - 1] == '/')) i--;
+    qname_len = i;
+    mate_unmapped = (rh_mp == NULL);
+    if (!mate_unmapped) {   // output.c:381-398
+      const struct sw_full_results *m_sfr = rh_mp->sfrp;
+      const int read_start_mp = m_sfr->read_start + 1;
+      const int read_end_mp = read_start_mp + m_sfr->rmapped - 1;
+      const int genome_length_mp = genome_len[rh_mp->cn];
+      reverse_strand_mp = (rh_mp->gen_st == 1);
+      if (!reverse_strand_mp)
+        genome_start_mp = m_sfr->genome_start + 1;
+      else
+        genome_start_mp = (genome_length_mp - m_sfr->genome_start) -
+                          (read_end_mp - read_start_mp - m_sfr->deletions + m_sfr->insertions);
+      genome_end_mp = genome_start_mp + m_sfr->gmapped - 1;
+      mpos = genome_start_mp;
+      mrnm = contig_names[rh_mp->cn];
+    }
+  }
+  const bool second_in_pair = paired_read && !first_in_pair;
+  const bool paired_alignment = paired_read && (rh != NULL && rh_mp != NULL && !improper_mapping);
+  const bool query_unmapped = (rh == NULL);
+
+  if (query_unmapped || (!half_paired && paired_read && mate_unmapped)) {   // output.c:409-468
+    const int flag = (paired_read ? 0x0001 : 0) | (paired_alignment ? 0x0002 : 0) | (query_unmapped ? 0x0004 : 0) |
+                     (mate_unmapped ? 0x0008 : 0) | (reverse_strand_mp ? 0x0020 : 0) | (first_in_pair ? 0x0040 : 0) |
+                     (second_in_pair ? 0x0080 : 0);
+    p = put_mem(p, re->name, qname_len);
+    *p++ = '\t';
+    p = put_int(p, flag);
+    p = put_str(p, "\t*\t0\t0\t*\t");
+    p = put_str(p, mrnm);
+    *p++ = '\t';
+    p = put_uint(p, mpos);
+    p = put_str(p, "\t0\t");
+    if (!cs) {
+      for (int i = 0; i < re->read_len; i++) *p++ = (char)g_ls_seq[(unsigned char)re->seq[i]];
+    } else {
+      *p++ = '*';
+    }
+    *p++ = '\t';
+    if (Qflag && !cs)
+      p = put_mem(p, re->qual, qual_str_len);
+    else
+      *p++ = '*';
+    if (cs) {
+      p = put_str(p, "\tCQ:Z:");
+      if (Qflag)
+        p = put_mem(p, re->qual, qual_str_len);
+      else
+        *p++ = '*';
+      p = put_str(p, "\tCS:Z:");
+      p = put_mem(p, re->seq, seq_str_len);
+    }
+    if (sam_r2) {
+      p = put_str(p, cs ? "\tX2:Z:" : "\tR2:Z:");
+      p = put_mem(p, re_mp->seq, mp_seq_len);
+    }
+    if (sam_read_group_name != NULL) {
+      p = put_str(p, "\tRG:Z:");
+      p = put_mem(p, sam_read_group_name, rg_len);
+    }
+    *p++ = '\n';
+    *p = '\0';
+    thread_output_buffer_filled[thread_id] = p;
+    return;
+  }
+
+  // ---- a mapped read (output.c:470-774)
+  const char *rname = contig_names[rh->cn];
+  const bool reverse_strand = (rh->gen_st == 1);
+  const int read_length = re->read_len;
+  const int read_start = sfr->read_start + 1;
+  const int read_end = read_start + sfr->rmapped - 1;
+  const int genome_length = genome_len[rh->cn];
+  const char *qr = sfr->qralign, *db = sfr->dbalign;
+  const int qralign_length = (int)al_len;
+
+  // CIGAR runs (make_cigar, output.c:15-62): S, then D / I / M runs of the alignment strings, then S
+  // (colour space: H, output.c:575-579); written later, reversed for a reverse-strand hit (output.c:629)
+  const int max_ops = qralign_length + 2;
+  char ops_small[256];
+  uint32_t lens_small[256];
+  char *ops = ops_small;
+  uint32_t *lens = lens_small;
+  if (max_ops > 256) {
+    ops = (char *)xmalloc((size_t)max_ops);
+    lens = (uint32_t *)xmalloc((size_t)max_ops * sizeof(uint32_t));
+  }
+  int n_ops = 0;
+  const char clip = cs ? 'H' : 'S';
+  if (read_start > 1) {
+    ops[n_ops] = clip;
+    lens[n_ops++] = (uint32_t)(read_start - 1);
+  }
+  for (int i = 0; i < qralign_length;) {
+    int length;
+    char op;
+    if (qr[i] == '-') {
+      for (length = 0; i + length < qralign_length && qr[i + length] == '-'; length++) {}
+      op = 'D';
+    } else if (db[i] == '-') {
+      for (length = 0; i + length < qralign_length && db[i + length] == '-'; length++) {}
+      op = 'I';
+    } else {
+      for (length = 0; i + length < qralign_length && db[i + length] != '-' && qr[i + length] != '-'; length++) {}
+      op = 'M';
+    }
+    ops[n_ops] = op;
+    lens[n_ops++] = (uint32_t)length;
+    i += length;
+  }
+  if (read_end != read_length) {
+    ops[n_ops] = clip;
+    lens[n_ops++] = (uint32_t)(read_length - read_end);
+  }
+
+  // ---- SEQ (output.c:308-341, :484-536): letter space starts from the read's own letters and overlays the aligned
+  // part; colour space prints the aligned part (the corrected base calls) only
+  char seq_small[1280];
+  const size_t seq_cap = (size_t)read_length + (size_t)qralign_length + 2;
+  char *seq = seq_cap <= sizeof(seq_small) ? seq_small : (char *)xmalloc(seq_cap);
+  int j = 0;
+  if (!cs) {
+    for (int i = 0; i < read_length; i++) seq[i] = (char)g_ls_seq[(unsigned char)re->seq[i]];
+    seq[read_length] = '\0';
+    j = read_start - 1;
+  }
+  for (int i = 0; i < qralign_length; i++) {
+    char c = qr[i];
+    if (c == '-') continue;
+    if (c >= 'a') c -= 32;
+    if (c != 'A' && c != 'G' && c != 'C' && c != 'T' && c != 'N') {
+      // output.c:503-531: any other code is printed as N (the table that would resolve it against the genome
+      // letter tests `c` after it was set to 'N'); a genome letter outside ACGT is reported on stderr
+      c = 'N';
+      if (db[i] != '-') {
+        char g = db[i];
+        if (g >= 'a') g -= 32;
+        if (g != 'A' && g != 'C' && g != 'G' && g != 'T')
+          fprintf(stderr, "There has been an error in printing an alignment, %c\n", g);
+      }
+    }
+    seq[j++] = c;
+  }
+  int seq_len;
+  bool bail = false;
+  if (cs && j != read_end - read_start + 1) bail = true;   // output.c:541-543 would print what the stack held
+  if (!cs) {
+    seq_len = j + (read_length - read_end);
+    seq[seq_len] = '\0';   // output.c:539 cuts the string here
+    seq_len = (int)strlen(seq);
+  } else {
+    seq_len = j;
+    seq[seq_len] = '\0';
+  }
+
+  // ---- QUAL (output.c:546-613)
+  char qual_small[1280];
+  const size_t qual_cap = MAX(qual_str_len, (size_t)read_length) + 16 + (sfr->qual ? strlen(sfr->qual) : 0);
+  char *qual = qual_cap <= sizeof(qual_small) ? qual_small : (char *)xmalloc(qual_cap);
+  size_t qual_len = 1;
+  qual[0] = '*';
+  qual[1] = '\0';
+  if (!cs) {
+    if (Qflag) {
+      const int ql = (int)qual_str_len;
+      if (!reverse_strand)
+        memcpy(qual, re->qual, (size_t)ql + 1);
+      else {
+        for (int i = 0; i < ql; i++) qual[(ql - 1) - i] = re->qual[i];
+        qual[ql] = '\0';
+      }
+      if (qual_delta != 33)
+        for (int i = 0; i < ql; i++) qual[i] = (char)(qual[i] - qual_delta + 33);
+      qual_len = strlen(qual);   // a shifted quality can become NUL; snprintf("%s") stops there
+    }
+  } else if (Qflag && compute_mapping_qualities) {
+    if (sfr->qual == NULL) {
+      bail = true;
+    } else {
+      strcpy(qual, sfr->qual);
+      if (reverse_strand)
+        for (int i = 0; i < sfr->rmapped / 2; i++) {
+          const char t = qual[i];
+          qual[i] = qual[sfr->rmapped - i - 1];
+          qual[sfr->rmapped - i - 1] = t;
+        }
+      qual_len = strlen(qual);
+    }
+  }
+
+  // ---- POS and strand (output.c:615-630)
+  int genome_start;
+  if (!reverse_strand) {
+    genome_start = sfr->genome_start + 1;
+  } else {
+    genome_start = (genome_length - sfr->genome_start) - (read_end - read_start - sfr->deletions + sfr->insertions);
+    for (int i = 0; i < seq_len && !bail; i++)
+      if (g_rc[(unsigned char)seq[i]] == 0) bail = true;   // reverse() stops the run on such a letter: let it
+    if (!bail) {
+      for (int a = 0, b = seq_len - 1; a < b; a++, b--) {
+        const char t = (char)g_rc[(unsigned char)seq[a]];
+        seq[a] = (char)g_rc[(unsigned char)seq[b]];
+        seq[b] = t;
+      }
+      if (seq_len & 1) seq[seq_len / 2] = (char)g_rc[(unsigned char)seq[seq_len / 2]];
+    }
+  }
+  if (bail) {
+    if (ops != ops_small) {
+      free(ops);
+      free(lens);
+    }
+    if (seq != seq_small) free(seq);
+    if (qual != qual_small) free(qual);
+    shrimp_ref_hit_output(re, rh, rh_mp, first_in_pair, hits, satisfying_alignments, improper_mapping);
+    return;
+  }
+  const int genome_end = genome_start + sfr->gmapped - 1;
+
+  // ---- mate columns (output.c:637-659)
+  int isize = 0;
+  if (paired_read && !mate_unmapped) {
+    if (strcmp(rname, mrnm) == 0) {
+      mrnm = "=";
+      const int fivep = reverse_strand ? genome_end : genome_start - 1;
+      const int fivep_mp = reverse_strand_mp ? genome_end_mp : genome_start_mp - 1;
+      isize = fivep_mp - fivep;
+    }
+  }
+  const int flag = (paired_read ? 0x0001 : 0) | (paired_alignment ? 0x0002 : 0) | (mate_unmapped ? 0x0008 : 0) |
+                   (reverse_strand ? 0x0010 : 0) | (reverse_strand_mp ? 0x0020 : 0) | (first_in_pair ? 0x0040 : 0) |
+                   (second_in_pair ? 0x0080 : 0);
+
+  // ---- the record (output.c:676-760)
+  p = put_mem(p, re->name, qname_len);
+  *p++ = '\t';
+  p = put_int(p, flag);
+  *p++ = '\t';
+  p = put_str(p, rname);
+  *p++ = '\t';
+  p = put_uint(p, genome_start);
+  *p++ = '\t';
+  p = put_int(p, sfr->mqv);
+  *p++ = '\t';
+  if (!reverse_strand)
+    for (int i = 0; i < n_ops; i++) {
+      p = put_int(p, (int)lens[i]);
+      *p++ = ops[i];
+    }
+  else
+    for (int i = n_ops - 1; i >= 0; i--) {
+      p = put_int(p, (int)lens[i]);
+      *p++ = ops[i];
+    }
+  *p++ = '\t';
+  p = put_str(p, mrnm);
+  *p++ = '\t';
+  p = put_uint(p, mpos);
+  *p++ = '\t';
+  p = put_int(p, isize);
+  *p++ = '\t';
+  p = put_mem(p, seq, (size_t)seq_len);
+  *p++ = '\t';
+  p = put_mem(p, qual, qual_len);
+  p = put_str(p, "\tAS:i:");
+  p = put_int(p, rh->score_full);
+  if (compute_mapping_qualities && !all_contigs) {
+    if (pair_mode == PAIR_NONE) {
+      p = put_str(p, "\tZ0:i:");
+      p = put_int(p, double_to_neglog(sfr->z0));
+      p = put_str(p, "\tZ1:i:");
+      p = put_int(p, double_to_neglog(sfr->z1));
+    } else if (rh != NULL && rh_mp != NULL && !improper_mapping) {
+      p = put_str(p, "\tZ2:i:");
+      p = put_int(p, double_to_neglog(sfr->z2));
+      p = put_str(p, "\tZ3:i:");
+      p = put_int(p, double_to_neglog(sfr->z3));
+      p = put_str(p, "\tZ4:i:");
+      p = put_int(p, double_to_neglog(sfr->pr_top_random_at_location));
+      p = put_str(p, "\tZ6:i:");
+      p = put_int(p, double_to_neglog(sfr->insert_size_denom));
+    } else {
+      p = put_str(p, "\tZ0:i:");
+      p = put_int(p, double_to_neglog(sfr->z0));
+      p = put_str(p, "\tZ1:i:");
+      p = put_int(p, double_to_neglog(sfr->z1));
+      p = put_str(p, "\tZ4:i:");
+      p = put_int(p, double_to_neglog(sfr->pr_top_random_at_location));
+      p = put_str(p, "\tZ5:i:");
+      p = put_int(p, double_to_neglog(sfr->pr_missed_mp));
+    }
+  }
+  p = put_str(p, "\tNM:i:");
+  p = put_int(p, sfr->mismatches + sfr->deletions + sfr->insertions);
+  if (cs) {
+    if (Qflag) {
+      p = put_str(p, "\tCQ:Z:");
+      p = put_mem(p, re->qual, qual_str_len);
+    }
+    p = put_str(p, "\tCS:Z:");
+    p = put_mem(p, re->seq, seq_str_len);
+    p = put_str(p, "\tCM:i:");
+    p = put_int(p, sfr->crossovers);
+    p = put_str(p, "\tXX:Z:");
+    p = put_mem(p, qr, (size_t)qralign_length);
+  }
+  if (sam_r2) {
+    p = put_str(p, cs ? "\tX2:Z:" : "\tR2:Z:");
+    p = put_mem(p, re_mp->seq, mp_seq_len);
+  }
+  if (sam_read_group_name != NULL) {
+    p = put_str(p, "\tRG:Z:");
+    p = put_mem(p, sam_read_group_name, rg_len);
+  }
+  *p++ = '\n';
+  *p = '\0';
+  thread_output_buffer_filled[thread_id] = p;
+  if (ops != ops_small) {
+    free(ops);
+    free(lens);
+  }
+  if (seq != seq_small) free(seq);
+  if (qual != qual_small) free(qual);
+}

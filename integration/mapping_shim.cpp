@@ -430,7 +430,9 @@ static void run_batch(Batch &B, const std::vector<Prep> &preps) {
     for (int r = 0; r < n; r++) B.first_unp[r + 1] = B.first_unp[r] + B.n_unp[r];
   }
   tstats.add(st);
-  tstats.t_device += omp_get_wtime() - t1;
+  const double dt = omp_get_wtime() - t1;
+  tstats.t_device += dt;
+  if (tstats.t_first_device == 0) tstats.t_first_device = dt;   // allocations of the context's buffers
 }
 
 // entries [re, re + ahead) of the chunk that are loaded; `step` entries per unit (2 in paired mode)

@@ -15,7 +15,7 @@ struct ThreadStats {
   uint64_t full_calls = 0, full_cells = 0;                            /* sw-full-ls.c:237, :662 */
   uint64_t post_columns = 0;
   uint64_t batches = 0, mispredicted = 0, reads = 0, records = 0;
-  double t_prep = 0, t_device = 0, t_build = 0, t_output = 0;   /* host seconds of this thread, SHRIMP_B200_VERBOSE */
+  double t_prep = 0, t_device = 0, t_first_device = 0, t_build = 0, t_output = 0;   /* host seconds of this thread, SHRIMP_B200_VERBOSE */
   void add(const shrimp_map_stats &s) {
     vector_calls += s.vector_calls;
     vector_cells += s.vector_cells;

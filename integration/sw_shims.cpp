@@ -126,9 +126,9 @@ int sw_vector_cleanup(void) {   // sw-vector.c:379
   if (getenv("SHRIMP_B200_VERBOSE") && tstats.batches)
     fprintf(stderr,
             "[gmapper-b200] thread: %llu reads in %llu device batches (%llu re-mapped alone), %llu records; host seconds: "
-            "look-ahead %.3f, device calls %.3f, record rebuild %.3f, output.c %.3f\n",
+            "look-ahead %.3f, device calls %.3f (the first %.3f), record rebuild %.3f, output %.3f\n",
             (unsigned long long)tstats.reads, (unsigned long long)tstats.batches, (unsigned long long)tstats.mispredicted,
-            (unsigned long long)tstats.records, tstats.t_prep, tstats.t_device, tstats.t_build, tstats.t_output);
+            (unsigned long long)tstats.records, tstats.t_prep, tstats.t_device, tstats.t_first_device, tstats.t_build, tstats.t_output);
   return 0;
 }
 

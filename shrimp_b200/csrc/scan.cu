@@ -1680,15 +1680,22 @@ size_t scan_smem_bytes(int cap, int max_rl, int k_cap, int bm_log2, int warps, i
 // chains in parallel (match_any), lane 0 replays the heap in shared memory.  A heap element is the candidate word with
 // its slot field replaced by the candidate's index: position << 32 | next-in-list << 16 | index.
 #define REPLAY_WARPS 8
+#define REPLAY_PRE 512
+#define REPLAY_SMEM_PER_WARP(ks_cap) ((((size_t)(ks_cap) * 18 + (size_t)REPLAY_PRE * 12 + 47)) & ~(size_t)15)
 __global__ void __launch_bounds__(REPLAY_WARPS * 32) scan_replay_kernel(const ScanParams P, uint32_t n_rec, int ks_cap) {
   extern __shared__ unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const uint32_t w = blockIdx.x * REPLAY_WARPS + wib;
   if (w >= n_rec) return;
-  unsigned char *base = smem_raw + (size_t)wib * (((size_t)ks_cap * 18 + 47) & ~(size_t)15);
+  unsigned char *base = smem_raw + (size_t)wib * REPLAY_SMEM_PER_WARP(ks_cap);
   unsigned long long *heap = (unsigned long long *)base;
   unsigned long long *stage = heap + ks_cap;
-  uint16_t *first_of = (uint16_t *)(stage + ks_cap);
+  // successor cache: the element that follows a heap member in its list is copied to shared memory (cp.async, 8 bytes)
+  // when the member enters the heap, so that the pop loop -- one lane, a chain of dependent steps -- never waits for
+  // global memory.  Direct-mapped on the successor's index; a miss falls back to the global load.
+  unsigned long long *pre_val = stage + ks_cap;
+  uint32_t *pre_tag = (uint32_t *)(pre_val + REPLAY_PRE);
+  uint16_t *first_of = (uint16_t *)(pre_tag + REPLAY_PRE);
   const uint4 tr = P.tie_rec[w];
   const uint32_t rs = tr.x;
   const int m = (int)tr.z;
@@ -1699,6 +1706,7 @@ __global__ void __launch_bounds__(REPLAY_WARPS * 32) scan_replay_kernel(const Sc
   const int Ks = P.S.n_seeds * max_n_kmers;
   const uint32_t lt = (1u << lane) - 1u;
   for (int k = lane; k < Ks; k += 32) first_of[k] = 0xffffu;
+  for (int k = lane; k < REPLAY_PRE; k += 32) pre_tag[k] = 0xffffffffu;
   __syncwarp();
   // chains: next candidate of the same list, built from the back
   for (int t0 = ((m - 1) >> 5) << 5; t0 >= 0; t0 -= 32) {
@@ -1722,11 +1730,29 @@ __global__ void __launch_bounds__(REPLAY_WARPS * 32) scan_replay_kernel(const Sc
     if (t != 0xffffu) {
       const unsigned long long e = ent[t];
       el = (e & 0xffffffffffff0000ull) | t;
-      const uint32_t nx = ((uint32_t)e >> 16) & 0xffffu;
-      // the successor of an element that sits in the heap is needed when that element pops: fetch it now
-      if (nx != 0xffffu) asm volatile("prefetch.global.L1 [%0];" ::"l"(ent + nx));
+      stage[k] = el;
+    } else {
+      stage[k] = el;
     }
-    stage[k] = el;
+  }
+  __syncwarp();
+  uint32_t seq = 0;   // copy groups issued so far (lane 0)
+  if (lane == 0) {   // successors of the heads; a slot that is taken is left alone (that successor is loaded when needed)
+    for (int k = 0; k < Ks; k++) {
+      const unsigned long long el = stage[k];
+      if (el == ~0ull) continue;
+      const uint32_t nx = ((uint32_t)el >> 16) & 0xffffu;
+      if (nx != 0xffffu) {
+        const uint32_t h = nx & (REPLAY_PRE - 1);
+        if (pre_tag[h] == 0xffffffffu) {
+          pre_tag[h] = (nx << 16) | (seq & 0xffffu);
+          const uint32_t dst = (uint32_t)__cvta_generic_to_shared(pre_val + h);
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst), "l"(ent + nx) : "memory");
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    seq++;
   }
   __syncwarp();
   if (lane != 0) return;
@@ -1750,9 +1776,29 @@ __global__ void __launch_bounds__(REPLAY_WARPS * 32) scan_replay_kernel(const Sc
     order[outn++] = (uint16_t)((uint32_t)root & 0xffffu);
     const uint32_t nx = ((uint32_t)root >> 16) & 0xffffu;
     if (nx != 0xffffu) {
-      const unsigned long long e = ent[nx];
+      const uint32_t h = nx & (REPLAY_PRE - 1);
+      const uint32_t tg = pre_tag[h];
+      unsigned long long e;
+      if ((tg >> 16) == nx) {
+        // copy groups complete in issue order: the newest eight may stay in flight unless this one is among them
+        if (((seq - tg) & 0xffffu) <= 8u) asm volatile("cp.async.wait_all;\n" ::: "memory");
+        else asm volatile("cp.async.wait_group 8;\n" ::: "memory");
+        e = pre_val[h];
+        pre_tag[h] = 0xffffffffu;
+      } else {
+        e = ent[nx];
+      }
       const uint32_t nx2 = ((uint32_t)e >> 16) & 0xffffu;
-      if (nx2 != 0xffffu) asm volatile("prefetch.global.L1 [%0];" ::"l"(ent + nx2));
+      if (nx2 != 0xffffu) {
+        const uint32_t h2 = nx2 & (REPLAY_PRE - 1);
+        if (pre_tag[h2] == 0xffffffffu) {
+          pre_tag[h2] = (nx2 << 16) | (seq & 0xffffu);
+          const uint32_t dst = (uint32_t)__cvta_generic_to_shared(pre_val + h2);
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst), "l"(ent + nx2) : "memory");
+        }
+      }
+      asm volatile("cp.async.commit_group;\n" ::: "memory");
+      seq++;
       heap[0] = (e & 0xffffffffffff0000ull) | nx;  // heap_uu_replace_min
     } else {
       load--;  // heap_uu_extract_min
@@ -1783,7 +1829,7 @@ __global__ void __launch_bounds__(REPLAY_WARPS * 32) scan_replay_kernel(const Sc
 }
 
 int launch_scan_replay(shrimp_gpu_ctx *ctx, ScanParams &P, uint32_t n_rec, int ks_cap) {
-  const size_t smem = (size_t)REPLAY_WARPS * (((size_t)ks_cap * 18 + 47) & ~(size_t)15);
+  const size_t smem = (size_t)REPLAY_WARPS * REPLAY_SMEM_PER_WARP(ks_cap);
   SH_OPT_IN_SMEM(scan_replay_kernel, ctx->device);
   scan_replay_kernel<<<(n_rec + REPLAY_WARPS - 1) / REPLAY_WARPS, REPLAY_WARPS * 32, smem, ctx->stream>>>(P, n_rec, ks_cap);
   SH_CUDA(cudaGetLastError());

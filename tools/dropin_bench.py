@@ -79,6 +79,8 @@ def main():
     ap.add_argument("--diff", type=int, default=0, help="also diff the SAM of the first N reads against the reference")
     ap.add_argument("--genome-mb", type=int, default=0)
     ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--variants", default="fast", help="comma list: fast = the drop-in with fast_io.cpp (f2), refio = the "
+                    "same link line with the reference's own FASTA reader and SAM formatter")
     ap.add_argument("--procs", default="", help="also run the read file split over P concurrent processes (comma list), "
                     "the reference's own way of scaling past its serial parser (SPLITTING_AND_MERGING)")
     a = ap.parse_args()
@@ -93,10 +95,13 @@ def main():
     with tempfile.TemporaryDirectory() as d:
         bench.reference_setup(w, d, codes, ctx)
         ctx.close()
-        for th in [int(x) for x in a.threads.split(",")]:
-            for ck in [int(x) for x in a.chunk.split(",")]:
-                s, wall, err = run_binary(NEW_DIR, w, d, th, "reads.fa", ["-K", str(ck)], env=env)
-                out["runs"].append({"threads": th, "chunk": ck, "map_s": s, "wall_s": wall, "reads_per_s": a.reads / s})
+        for var, th, ck in [(v, int(t), int(c)) for v in a.variants.split(",") for t in a.threads.split(",")
+                            for c in a.chunk.split(",")]:
+            if True:
+                bindir = NEW_DIR if var == "fast" else os.path.join(NEW_DIR, var)
+                s, wall, err = run_binary(bindir, w, d, th, "reads.fa", ["-K", str(ck)], env=env)
+                out["runs"].append({"variant": var, "threads": th, "chunk": ck, "map_s": s, "wall_s": wall,
+                                    "reads_per_s": a.reads / s})
                 print(json.dumps(out["runs"][-1]), flush=True)
                 for ln in [x for x in err.splitlines() if x.startswith("[gmapper-b200]")][:3]:
                     print("   ", ln, flush=True)
