@@ -44,14 +44,25 @@ struct DeviceGenome {
   uint32_t nbuckets[SHRIMP_MAX_SEEDS] = {0};
   uint64_t total[SHRIMP_MAX_SEEDS] = {0};
   DevBuf d_offs[SHRIMP_MAX_SEEDS];  // uint32 [nbuckets+1]
-  DevBuf d_pos[SHRIMP_MAX_SEEDS];   // uint32 [total]
+  DevBuf d_pos[SHRIMP_MAX_SEEDS];   // uint32 [total], then (sparse projections) the bucket heads, see build_bucket_heads
+  uint32_t head_off[SHRIMP_MAX_SEEDS] = {0};   // first word of the bucket heads in d_pos[sn], 0 = none
   std::vector<std::string> contig_names;   // set by shrimp_gpu_projection_load
 };
 
 struct IndexView {
   const uint32_t *offs[SHRIMP_MAX_SEEDS];
   const uint32_t *pos[SHRIMP_MAX_SEEDS];
+  uint32_t head_off[SHRIMP_MAX_SEEDS];   // bucket heads behind the position lists (0 = none)
 };
+
+// Bucket heads of a SPARSE projection (a few entries per bucket: C1, C2, C4, C5).  A k-mer lookup through the CSR costs
+// two dependent DRAM accesses of 64 bytes each for 8 bytes of bucket bounds and ~24 bytes of list (profiles/
+// r02_summary.md section 2: 7 x the algorithmic bytes).  The head of bucket m is one 64-byte record behind the
+// position lists, in the same allocation so that a list is addressed by one 32-bit word offset wherever it lies:
+//   word 0 = list length; length <= 15: words 1..length = the list itself; longer: word 1 = its CSR start.
+// One DRAM access per k-mer; the list entries are then read from the line that is already on chip.
+#define SHRIMP_HEAD_WORDS 16
+int build_bucket_heads(shrimp_gpu_ctx *ctx, DeviceGenome *g);
 
 struct GenomeView {
   const uint32_t *ls, *ls_rc, *cs, *cs_rc;

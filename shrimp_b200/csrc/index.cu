@@ -98,6 +98,48 @@ __global__ void csr_offsets_kernel(const uint32_t *key, uint64_t n, uint32_t nbu
   for (long long m = prev + 1; m <= cur; m++) offs[m] = (uint32_t)i;
 }
 
+__global__ void bucket_heads_kernel(const uint32_t *__restrict__ offs, const uint32_t *__restrict__ pos, uint32_t nbuckets,
+                                    uint32_t *__restrict__ heads) {
+  // a 16-lane group per bucket: one coalesced 64-byte store
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t m = t >> 4;
+  const uint32_t j = (uint32_t)t & 15u;
+  if (m >= nbuckets) return;
+  const uint32_t b = offs[m], len = offs[m + 1] - b;
+  uint32_t w = 0;
+  if (j == 0) w = len;
+  else if (len <= SHRIMP_HEAD_WORDS - 1) w = j <= len ? pos[b + j - 1] : 0u;
+  else if (j == 1) w = b;
+  heads[m * SHRIMP_HEAD_WORDS + j] = w;
+}
+
+int build_bucket_heads(shrimp_gpu_ctx *ctx, DeviceGenome *g) {
+  const char *env = getenv("SHRIMP_BUCKET_HEADS");   // 0 = never, 1 = always (tests), default: sparse projections only
+  for (int sn = 0; sn < g->seeds.n_seeds; sn++) {
+    g->head_off[sn] = 0;
+    const uint64_t nb = g->nbuckets[sn], total = g->total[sn];
+    const uint64_t off = (total + 1 + 63) & ~(uint64_t)63;
+    bool want = total <= 8 * nb;   // a mean of at most eight entries per bucket: most lists fit a head
+    if (env) want = atoi(env) != 0;
+    if (!want || off + nb * SHRIMP_HEAD_WORDS >= 0xffffffffull) continue;
+    DevBuf both;
+    SH_TRY(both.ensure((off + nb * SHRIMP_HEAD_WORDS) * 4));
+    SH_CUDA(cudaMemcpyAsync(both.p, g->d_pos[sn].p, (size_t)total * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    const uint64_t threads = nb * SHRIMP_HEAD_WORDS;
+    bucket_heads_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(
+        g->d_offs[sn].as<uint32_t>(), both.as<uint32_t>(), (uint32_t)nb, both.as<uint32_t>() + off);
+    SH_CUDA(cudaGetLastError());
+    SH_LAUNCHED(ctx, ST_INDEX);
+    SH_CUDA(cudaStreamSynchronize(ctx->stream));
+    g->d_pos[sn].release();
+    g->d_pos[sn] = both;
+    both.p = nullptr;
+    both.cap = 0;
+    g->head_off[sn] = (uint32_t)off;
+  }
+  return SHRIMP_OK;
+}
+
 void free_genome(shrimp_gpu_ctx *ctx) {
   DeviceGenome *g = genome_of(ctx);
   if (!g) return;
@@ -316,6 +358,7 @@ extern "C" int shrimp_gpu_index_build(shrimp_gpu_ctx *ctx, int n_seeds, const ui
   tmp.release();
   g->seeds = S;
   g->have_index = true;
+  if (rc == SHRIMP_OK) rc = build_bucket_heads(ctx, g);
   return rc;
 }
 

@@ -513,6 +513,7 @@ int chunk_begin(Chunk &C, shrimp_gpu_ctx *ctx, const shrimp_map_params *mp, int 
   for (int sn = 0; sn < g->seeds.n_seeds; sn++) {
     C.IV.offs[sn] = g->d_offs[sn].as<uint32_t>();
     C.IV.pos[sn] = g->d_pos[sn].as<uint32_t>();
+    C.IV.head_off[sn] = g->head_off[sn];
   }
   if (n_reads == 0) return SHRIMP_OK;
 

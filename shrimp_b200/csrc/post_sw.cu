@@ -398,8 +398,366 @@ __global__ void __launch_bounds__(128, PS_CTAS_PER_SM) post_sw_kernel(const Post
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Four lanes per alignment, four nodes per lane (round 2).  The 16-node chain factorises: the forward sum of a node
+// depends on its LEFT letter only -- F_q = sum over m of exp(-f[(m, q)]), f'[(l, r)] = prior(l, r) - log F_l -- and
+// the backward sum on its RIGHT letter only -- B_q = sum over m of exp(-(prior'(q, m) + b[(q, m)])),
+// b'[(l, r)] = -log B_r (so backwards[][] has four distinct values per column).  Lane q of a quad owns the four
+// nodes (m, q) of the forward chain and the four nodes (q, m) of the backward chain: both sums are LOCAL, in the
+// reference's order of m, and only the four logarithms travel (an all-gather over four lanes).  Per column a quad
+// evaluates 32 exponentials and 8 logarithms -- what the recurrences need, none twice -- against 32 + 16 on a
+// half-warp, with 20 shuffles instead of 80, and a warp advances eight alignments per iteration instead of two.
+// Every double is computed by the same operations in the same order as in the half-warp kernel above (and in
+// sw-post.c); tests/test_gpu_post_sw.py runs both.
+#define PQ_W 4
+__device__ __forceinline__ double ps_prior(const PostParams &P, const PsCol &pc, int l, int r) {   // nodePrior, sw-post.c:112-140
+  double val = 0;
+  if (pc.let != -2) val = val - (r == pc.let ? P.la1 : P.la2);
+  const bool same = (l ^ r) == pc.col;
+  const double l1 = pc.kind == 0 ? P.lc1 : pc.kind == 2 ? P.ln1 : P.lc1_tab[pc.q];
+  const double l2 = pc.kind == 0 ? P.lc2 : pc.kind == 2 ? P.ln2 : P.lc2_tab[pc.q];
+  val = val - (same ? l1 : l2);
+  return val;
+}
+
+__global__ void __launch_bounds__(128) post_sw_quad_kernel(const PostParams P, int quads_per_cta, int max_cols, int n_groups,
+                                                           double *fw_scratch) {
+  extern __shared__ double ps_smem[];
+  const int lane = threadIdx.x & 31, ql = lane & 3;
+  const int qidx = threadIdx.x >> 2;   // quad of the CTA
+  double *fscale = ps_smem + (size_t)qidx * ps_smem_doubles_per_half(max_cols);
+  double *bsc = fscale + max_cols;
+  PsCol *cols = (PsCol *)(bsc + max_cols);
+  uint8_t *pxs = (uint8_t *)(cols + max_cols);
+  // forwards[max_cols][16] and the four distinct backwards[max_cols][.] of this quad
+  double *fw = fw_scratch + ((size_t)blockIdx.x * quads_per_cta + qidx) * (size_t)max_cols * 20;
+  double *bwr = fw + (size_t)max_cols * 16;
+  const glibc_math::Tables GT = {P.gm_tab, P.gm_tab + 8, P.gm_tab + 8 + 256, P.gm_tab + 8 + 256 + 18};
+  const int hshift = lane & ~3;
+  for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+  int slot = grp * quads_per_cta + qidx;
+  const bool live = slot < P.n_tasks;
+  if (!live) slot = P.n_tasks - 1;
+  const FullTask T = P.tasks[slot];
+  FullResult R = P.results[slot];
+  const bool run = live && T.run && R.score > 0;
+  const uint32_t *genome = T.gen_st ? P.genome_rc : P.genome_fwd;
+  const uint32_t *read = P.reads + (size_t)T.ridx * P.stride;
+  const uint8_t *ops = P.ops + (size_t)slot * (size_t)P.ops_stride;
+  const uint8_t *rq = P.read_quals ? P.read_quals + (size_t)(T.ridx >> 1) * (size_t)P.qual_stride + P.qual_vector_offset
+                                   : nullptr;
+  const int init_bp = T.initbp;
+  // ---- load_local_vectors (sw-post.c:472-545), as in the half-warp kernel with scans over four lanes --------------
+  const int rlen_t = run ? T.rlen : 0, n_ops = run ? R.ops_len : 0;
+  const int w_rlen = warp_max_int(rlen_t), w_ops = warp_max_int(n_ops);
+  int start_run = 0, min_qv = 10000;
+  {
+    int carry = 0, any_n = 0;
+    for (int p0 = 0; p0 < w_rlen; p0 += PQ_W) {
+      const int p = p0 + ql;
+      const bool in = p < rlen_t;
+      const int c = in ? (int)extract4(read, (uint64_t)p) : 15;
+      int v = c != 15 ? c : 0, f = c == 15 ? 1 : 0;
+#pragma unroll
+      for (int d = 1; d < PQ_W; d <<= 1) {
+        const int v2 = __shfl_up_sync(0xffffffffu, v, d, PQ_W), f2 = __shfl_up_sync(0xffffffffu, f, d, PQ_W);
+        if (ql >= d) {
+          if (!f) v ^= v2;
+          f |= f2;
+        }
+      }
+      if (!f) v ^= carry;
+      if (in) pxs[p] = (uint8_t)v;
+      carry = __shfl_sync(0xffffffffu, v, PQ_W - 1, PQ_W);
+      const bool pre = in && p < R.read_start;
+      any_n |= (int)((__ballot_sync(0xffffffffu, pre && c == 15) >> hshift) & 0xfu);
+      int x = (pre && c != 15) ? c : 0, mq = (pre && rq) ? (int)rq[p] : 10000;
+#pragma unroll
+      for (int o = PQ_W / 2; o > 0; o >>= 1) {
+        x ^= __shfl_xor_sync(0xffffffffu, x, o, PQ_W);
+        mq = min(mq, __shfl_xor_sync(0xffffffffu, mq, o, PQ_W));
+      }
+      start_run ^= x;
+      min_qv = min(min_qv, mq);
+    }
+    if (any_n) {
+      start_run = 15;
+      min_qv = 0;
+    }
+  }
+  __syncwarp();
+  int len = 0;
+  {
+    int colbase = 0, genbase = 0;
+    const uint64_t g0 = (uint64_t)T.goff_global + (uint64_t)(R.genome_start - (int)T.goff_contig);
+    for (int q0 = 0; q0 < w_ops; q0 += PQ_W) {
+      const int q = q0 + ql;
+      const bool in = q < n_ops;
+      const int op = in ? (int)ops[R.ops_start + q] : 0, type = op & 3, kk = (op >> 4) & 3;
+      const int isread = (in && type != 1) ? 1 : 0, isgen = (in && type != 2) ? 1 : 0;
+      int ir = isread, ig = isgen;
+#pragma unroll
+      for (int d = 1; d < PQ_W; d <<= 1) {
+        const int r2 = __shfl_up_sync(0xffffffffu, ir, d, PQ_W), g2 = __shfl_up_sync(0xffffffffu, ig, d, PQ_W);
+        if (ql >= d) {
+          ir += r2;
+          ig += g2;
+        }
+      }
+      const int col = colbase + ir - isread;
+      if (isread && col < max_cols) {
+        const int j = R.read_start + col;
+        const int c = (int)extract4(read, (uint64_t)j);
+        PsCol pc;
+        int gl = 15;
+        if (type == 3) {
+          const int g = (int)extract4(genome, g0 + (uint64_t)(genbase + ig - isgen));
+          pc.let = (int8_t)(g <= 3 ? g : -1);
+          gl = g <= 3 ? g : 15;
+        } else {
+          pc.let = -2;
+        }
+        if ((col == 0 && start_run == 15) || c == 15) {
+          pc.col = 0;
+          pc.kind = 2;
+          pc.q = 0;
+        } else {
+          pc.col = (int8_t)(c ^ (col == 0 ? start_run : 0));
+          if (rq) {
+            pc.kind = 1;
+            pc.q = (uint8_t)(col == 0 ? min(min_qv, (int)rq[j]) : (int)rq[j]);
+          } else {
+            pc.kind = 0;
+            pc.q = 0;
+          }
+        }
+        pc.call = (int8_t)(c == 15 ? gl : (((kk + init_bp) & 3) ^ (int)pxs[j]));
+        pc.maxp = 0;
+        pc.qual = 33;
+        pc.pad = 0;
+        cols[col] = pc;
+      }
+      colbase += __shfl_sync(0xffffffffu, ir, PQ_W - 1, PQ_W);
+      genbase += __shfl_sync(0xffffffffu, ig, PQ_W - 1, PQ_W);
+    }
+    len = colbase;
+  }
+  if (len > max_cols) len = 0;
+  if (ql == 0 && len > 0 && P.columns) atomicAdd(P.columns, (unsigned long long)len);
+  const int wlen = warp_max_int(len);
+  __syncwarp();
+  // ---- do_forwards (sw-post.c:318-361) and do_backwards (:270-316) in one loop -----------------------------------
+  // f[l] = forwards[t][(l, ql)]; b[r] = backwards[c][(ql, r)] (the same four values on every lane of the quad)
+  double f[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0}, run_scale = 0, bscale = 0;
+  PsCol blank;
+  blank.let = -2; blank.col = 0; blank.kind = 0; blank.q = 0; blank.call = 15; blank.maxp = 0; blank.qual = 33; blank.pad = 0;
+  for (int t = 0; t < wlen; t++) {
+    const bool on = t < len;
+    const int c = len - 1 - t;   // backward column
+    const PsCol pc = on ? cols[t] : blank;
+    double nf[4], nb[4];
+    if (t == 0) {
+#pragma unroll
+      for (int l = 0; l < 4; l++) {
+        nf[l] = l == init_bp ? ps_prior(P, pc, l, ql) : HUGE_VAL;
+        nb[l] = 0.0;
+      }
+    } else {
+      const PsCol nxt = on ? cols[c + 1] : blank;
+      double sf = 0, sb = 0;
+#pragma unroll
+      for (int m = 0; m < 4; m++) {
+        sf += PS_EXP(-1 * (f[m]));
+        sb += PS_EXP(-1 * (ps_prior(P, nxt, ql, m) + b[m]));
+      }
+      const double lgf = PS_LOG(sf), lgb = PS_LOG(sb);
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const double lf = __shfl_sync(0xffffffffu, lgf, k, PQ_W), lb = __shfl_sync(0xffffffffu, lgb, k, PQ_W);
+        nf[k] = ps_prior(P, pc, k, ql) - lf;
+        nb[k] = on ? -lb : 0.0;
+      }
+    }
+    // forwscale: minimum over the 16 nodes; backscale: over the four distinct values
+    double scf = nf[0], scb = nb[0];
+#pragma unroll
+    for (int k = 1; k < 4; k++) {
+      scf = nf[k] < scf ? nf[k] : scf;
+      scb = nb[k] < scb ? nb[k] : scb;
+    }
+#pragma unroll
+    for (int o = PQ_W / 2; o > 0; o >>= 1) {
+      const double w = __shfl_xor_sync(0xffffffffu, scf, o, PQ_W);
+      scf = w < scf ? w : scf;
+    }
+    if (on) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        f[k] = nf[k] - scf;
+        b[k] = nb[k] - scb;
+        fw[(size_t)t * 16 + k * 4 + ql] = f[k];
+      }
+      run_scale = t == 0 ? scf : scf + run_scale;
+      bscale = t == 0 ? scb : scb + bscale;
+      bwr[(size_t)c * 4 + ql] = ql == 0 ? b[0] : ql == 1 ? b[1] : ql == 2 ? b[2] : b[3];
+      if (ql == 0) {
+        fscale[t] = run_scale;
+        bsc[c] = bscale;
+      }
+    }
+  }
+  double total_score = 0;
+  {
+    double e[4];
+#pragma unroll
+    for (int l = 0; l < 4; l++) e[l] = PS_EXP(-1 * (f[l]));
+    double val = 0;
+#pragma unroll
+    for (int l = 0; l < 4; l++)
+#pragma unroll
+      for (int r = 0; r < 4; r++) val += __shfl_sync(0xffffffffu, e[l], r, PQ_W);   // node order j = 4 l + r
+    total_score = -PS_LOG(val) + run_scale;
+  }
+  __syncwarp();
+  // ---- posteriors of the four letters per column, post_traceback (:182-207), get_base_qualities (:584-601) -------
+  for (int i = 0; i < wlen; i++) {
+    const bool on = i < len;
+    const double bwv = on ? bwr[(size_t)i * 4 + ql] : 0.0;
+    const double fs = on ? fscale[i] : 0.0, bs = on ? bsc[i] : 0.0;
+    const int bc = on ? (int)cols[i].call : 15;
+    double p = 0;   // posterior of letter ql: the nodes (m, ql) in the order of m
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+      const double fwv = on ? fw[(size_t)i * 16 + m * 4 + ql] : 0.0;
+      p += PS_EXP(-1 * (fwv + bwv + fs + bs - total_score));
+    }
+    const double p0 = __shfl_sync(0xffffffffu, p, 0, PQ_W), p1 = __shfl_sync(0xffffffffu, p, 1, PQ_W);
+    const double p2 = __shfl_sync(0xffffffffu, p, 2, PQ_W), p3 = __shfl_sync(0xffffffffu, p, 3, PQ_W);
+    if (on && ql == 0) {
+      int maxval = 0;
+      double pm = p0;
+      if (p1 > pm) { maxval = 1; pm = p1; }
+      if (p2 > pm) { maxval = 2; pm = p2; }
+      if (p3 > pm) { maxval = 3; pm = p3; }
+      fscale[i] = bc != 15 ? 1 - (bc == 0 ? p0 : bc == 1 ? p1 : bc == 2 ? p2 : p3) : 2.0;
+      cols[i].maxp = (int8_t)maxval;
+    }
+  }
+  __syncwarp();
+  {   // get_base_qualities (sw-post.c:584-601)
+    const double log10v = PS_LOG(10.0);
+    for (int c = ql; c < len; c += PQ_W) {
+      const double pe = fscale[c];
+      int tmp = pe == 2.0 ? 0 : ps_qv_from_pr_err(pe, log10v, GT);
+      if (tmp > 40) tmp = 40;
+      cols[c].qual = (uint8_t)(33 + tmp);
+    }
+  }
+  __syncwarp();
+  // ---- fix_base_calls (:548-581) on all lanes, get_posterior (:604-626) by one lane over the gap columns only ----
+  {
+    uint8_t *wops = P.ops + (size_t)slot * (size_t)P.ops_stride;
+    uint8_t *qout = P.quals_out + (size_t)slot * (size_t)P.max_rlen;
+    const uint64_t g0 = (uint64_t)T.goff_global + (uint64_t)(R.genome_start - (int)T.goff_contig);
+    const bool doit = run && len > 0;
+    const int n_ops3 = doit ? n_ops : 0;
+    int matches = 0, mismatches = 0, crossovers = 0;
+    int colbase = 0, genbase = 0, last_type = 0;
+    double res = (doit && ql == 0) ? PS_EXP(-total_score) : 0.0;
+    for (int q0 = 0; q0 < w_ops; q0 += PQ_W) {
+      const int q = q0 + ql;
+      const bool in = q < n_ops3;
+      const int op = in ? (int)wops[R.ops_start + q] : 0, type = in ? (op & 3) : 0;
+      const int isread = (in && type != 1) ? 1 : 0, isgen = (in && type != 2) ? 1 : 0;
+      int ir = isread, ig = isgen;
+#pragma unroll
+      for (int d = 1; d < PQ_W; d <<= 1) {
+        const int r2 = __shfl_up_sync(0xffffffffu, ir, d, PQ_W), g2 = __shfl_up_sync(0xffffffffu, ig, d, PQ_W);
+        if (ql >= d) {
+          ir += r2;
+          ig += g2;
+        }
+      }
+      int ptype = __shfl_up_sync(0xffffffffu, type, 1, PQ_W);
+      if (ql == 0) ptype = last_type;
+      const int col = colbase + ir - isread;
+      if (isread) {
+        const PsCol pc = cols[col];
+        const int crt = pc.maxp;
+        const int prev_base = col == 0 ? init_bp : (int)cols[col - 1].maxp;
+        const bool lower = (prev_base ^ crt) != pc.col;
+        if (lower) crossovers++;
+        if (type == 3) {
+          const int g = (int)extract4(genome, g0 + (uint64_t)(genbase + ig - isgen));
+          if (g == crt) matches++;
+          else mismatches++;
+        }
+        wops[R.ops_start + q] = (uint8_t)(type | (lower ? 4 : 0) | 8 | (crt << 4));
+        qout[col] = pc.qual;
+      }
+      const bool gap = in && type != 3;
+      const bool opens = gap && (q == 0 || ptype != type);
+      uint32_t gm = (__ballot_sync(0xffffffffu, gap) >> hshift) & 0xfu;
+      const uint32_t dm = (__ballot_sync(0xffffffffu, gap && type == 1) >> hshift) & 0xfu;
+      const uint32_t om = (__ballot_sync(0xffffffffu, opens) >> hshift) & 0xfu;
+      if (ql == 0)
+        while (gm) {
+          const int bpos = __ffs(gm) - 1;
+          gm &= gm - 1;
+          const bool del = (dm >> bpos) & 1u;
+          res *= del ? P.pr_del_extend : P.pr_ins_extend;
+          if ((om >> bpos) & 1u) res *= del ? P.pr_del_open : P.pr_ins_open;
+        }
+      colbase += __shfl_sync(0xffffffffu, ir, PQ_W - 1, PQ_W);
+      genbase += __shfl_sync(0xffffffffu, ig, PQ_W - 1, PQ_W);
+      last_type = __shfl_sync(0xffffffffu, type, PQ_W - 1, PQ_W);
+    }
+#pragma unroll
+    for (int o = PQ_W / 2; o > 0; o >>= 1) {
+      matches += __shfl_xor_sync(0xffffffffu, matches, o, PQ_W);
+      mismatches += __shfl_xor_sync(0xffffffffu, mismatches, o, PQ_W);
+      crossovers += __shfl_xor_sync(0xffffffffu, crossovers, o, PQ_W);
+    }
+    if (doit && ql == 0) {
+      R.matches = matches;
+      R.mismatches = mismatches;
+      R.crossovers = crossovers;
+      R.posterior = res;
+      P.results[slot] = R;
+    }
+  }
+  __syncwarp();   // the next group reuses the columns
+  }
+}
+
+static int launch_post_sw_quad(shrimp_gpu_ctx *ctx, const PostParams &P, DevBuf &scratch) {
+  const int max_cols = std::max(1, P.max_rlen);
+  const size_t per_quad = ps_smem_doubles_per_half(max_cols) * sizeof(double);
+  int warps = 4;   // eight alignments per warp
+  while (warps > 1 && per_quad * 8 * warps > 64 * 1024) warps >>= 1;
+  if (per_quad * 8 * warps > 200 * 1024) {
+    set_error("post_sw: reads of %d bases need more shared memory than a CTA has", P.max_rlen);
+    return SHRIMP_E_RANGE;
+  }
+  const int quads = 8 * warps;
+  const size_t smem = per_quad * quads;
+  auto kern = post_sw_quad_kernel;
+  SH_OPT_IN_SMEM(kern, ctx->device);
+  int per_sm = 0;
+  SH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, quads * 4, smem));
+  if (per_sm < 1) per_sm = 1;
+  const int n_groups = (P.n_tasks + quads - 1) / quads;
+  const int grid = std::min(n_groups, ctx->sm_count * per_sm);
+  SH_TRY(scratch.ensure((size_t)grid * quads * (size_t)max_cols * 20 * sizeof(double)));
+  kern<<<grid, quads * 4, smem, ctx->stream>>>(P, quads, max_cols, n_groups, scratch.as<double>());
+  SH_CUDA(cudaGetLastError());
+  SH_LAUNCHED(ctx, ST_POST);
+  return SHRIMP_OK;
+}
+
 int launch_post_sw(shrimp_gpu_ctx *ctx, const PostParams &P, DevBuf &scratch) {
   if (P.n_tasks <= 0) return SHRIMP_OK;
+  if (!getenv("SHRIMP_POST_SW_HALF")) return launch_post_sw_quad(ctx, P, scratch);   // the half-warp kernel: A/B and tests
   const int max_cols = std::max(1, P.max_rlen);
   const size_t per_half = ps_smem_doubles_per_half(max_cols) * sizeof(double);
   const int halves = 8;

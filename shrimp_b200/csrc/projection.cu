@@ -259,7 +259,7 @@ extern "C" int shrimp_gpu_projection_load(shrimp_gpu_ctx *ctx, const char *prefi
   SH_TRY(seed_table_init(S, n_seeds, masks, spans, weights, (int)hflag, "shrimp_gpu_projection_load"));
   g->seeds = S;
   g->have_index = true;
-  return SHRIMP_OK;
+  return build_bucket_heads(ctx, g);
 }
 
 extern "C" int shrimp_gpu_num_contigs(shrimp_gpu_ctx *ctx) {

@@ -643,9 +643,16 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) scan_kernel(const ScanParams 
         uint32_t start = 0, len = 0;
         if (i < nk) {
           const uint32_t m = S.n_runs[sn] ? mapidx_fast(S, sn, r2, mkp + i) : kmer_to_mapidx(S, sn, seq, (uint64_t)(mkp + i));
-          const uint2 be = make_uint2(__ldg(P.I.offs[sn] + m), __ldg(P.I.offs[sn] + m + 1));
-          start = be.x;
-          len = be.y - be.x;
+          if (P.I.head_off[sn]) {   // bucket head: length and list in one 64-byte record (genome.cuh)
+            const uint32_t hw = P.I.head_off[sn] + m * SHRIMP_HEAD_WORDS;
+            const uint2 hv = __ldg((const uint2 *)(P.I.pos[sn] + hw));
+            len = hv.x;
+            start = len <= SHRIMP_HEAD_WORDS - 1 ? hw + 1 : hv.y;
+          } else {
+            const uint2 be = make_uint2(__ldg(P.I.offs[sn] + m), __ldg(P.I.offs[sn] + m + 1));
+            start = be.x;
+            len = be.y - be.x;
+          }
           if (len > M.list_cutoff) len = 0;  // mapping.c:497,:889
         }
         const uint32_t incl = (uint32_t)warp_incl_scan((int)len, lane);

@@ -57,6 +57,18 @@ def test_pipeline_matches_reference_golden(gpu_ctx, name):
         assert [b for _, b in sq] == gold["qual"].tolist()
 
 
+@pytest.mark.parametrize("name,env", [("c1_small", {"SHRIMP_BUCKET_HEADS": "0"}), ("c2_small", {"SHRIMP_BUCKET_HEADS": "0"}),
+                                      ("c1_repeat", {"SHRIMP_BUCKET_HEADS": "0"}),
+                                      ("c2_small_mq", {"SHRIMP_POST_SW_HALF": "1"}),
+                                      ("c2_small_fastq_mq", {"SHRIMP_POST_SW_HALF": "1"})])
+def test_alternative_paths_match_reference_golden(gpu_ctx, name, env, monkeypatch):
+    """the paths the defaults no longer take on these small cases: k-mer lookups through the CSR bounds instead of
+    the bucket heads of a sparse projection (genome.cuh), and the half-warp post_sw kernel instead of the quad one"""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    test_pipeline_matches_reference_golden(gpu_ctx, name)
+
+
 def test_repeats_reach_the_cta_scan_kernel(gpu_ctx):
     """read strands with more candidates than a warp's slab go through scan_big_kernel (and still match, see the
     golden test of c1_repeat)"""
