@@ -59,6 +59,9 @@ struct Reader {
 
 enum { MAX_READERS = 16 };
 Reader g_readers[MAX_READERS];
+// SHRIMP_B200_VERBOSE: seconds spent in the reader (it runs inside gmapper.c's critical section: the serial part of a run)
+unsigned long long g_reader_ticks, g_reader_calls, g_tick0;
+double g_wall0;
 
 Reader *reader_of(fasta_t f) {
   for (int i = 0; i < MAX_READERS; i++)
@@ -170,13 +173,90 @@ char *extract_name_fast(char *line, char **ranges) {
 
 }  // namespace
 
+static bool next_read(fasta_t fasta, read_entry *re);
 bool fasta_get_next_read_with_range(fasta_t fasta, read_entry *re) {   // fasta.c:316
+  const unsigned long long t0 = __builtin_ia32_rdtsc();
+  if (g_tick0 == 0) {
+    g_tick0 = t0;
+    g_wall0 = omp_get_wtime();
+  }
+  const bool ok = next_read(fasta, re);
+  g_reader_ticks += __builtin_ia32_rdtsc() - t0;
+  g_reader_calls++;
+  return ok;
+}
+
+// The common shape of an entry -- a name line without tabs, ONE sequence line, (FASTQ: a '+' line and ONE quality line
+// of the right length), the next entry's marker behind it, all inside the current block, no NUL bytes -- is taken
+// apart in place with memchr; anything else returns false without having consumed a byte and next_read's general
+// path (the restatement of fasta.c:316-545 piece by piece) takes the entry.
+static bool next_read_fast(Reader *r, fasta_t fasta, read_entry *re, char c) {
+  if (r->header) return false;
+  char *s = r->buf + r->pos, *const end = r->buf + r->end;
+  if (s >= end || *s != c) return false;
+  char *e = (char *)memchr(s, '\n', (size_t)(end - s));
+  if (!e) return false;
+  char *q = e + 1;                                  // the sequence line
+  if (q >= end || *q == '#' || *q == '>' || *q == '+') return false;
+  char *qe = (char *)memchr(q, '\n', (size_t)(end - q));
+  if (!qe || qe == q) return false;
+  char *nx = qe + 1;                                // what follows the sequence line
+  char *plus = NULL, *pe = NULL, *ql = NULL, *qle = NULL;
+  if (!fasta->fastq) {
+    if (nx >= end || *nx != '>') return false;      // more sequence lines, a comment, or the end of the block / file
+  } else {
+    if (nx >= end || *nx != '+') return false;
+    plus = nx;
+    pe = (char *)memchr(plus, '\n', (size_t)(end - plus));
+    if (!pe) return false;
+    ql = pe + 1;
+    if (ql >= end) return false;
+    qle = (char *)memchr(ql, '\n', (size_t)(end - ql));
+    if (!qle) return false;
+    const size_t want = fasta->space == LETTER_SPACE ? (size_t)(qe - q) : (size_t)(qe - q) - 1;
+    if ((size_t)(qle - ql) != want || want == 0) return false;
+    nx = qle + 1;
+  }
+  if (memchr(s, 0, (size_t)(nx - s)) || memchr(s, '\t', (size_t)(e - s))) return false;
+  // the name: trimmed, cut at its first blank (extract_name, fasta.c:243-281, without a range field)
+  char *b = s + 1, *t = e;
+  while (b < t && isspace((unsigned char)*b)) b++;
+  while (t > b && isspace((unsigned char)t[-1])) t--;
+  if (b == t) return false;
+  char *sp = (char *)memchr(b, ' ', (size_t)(t - b));
+  re->name = dup17(b, (size_t)((sp ? sp : t) - b));
+  const size_t seq_len = (size_t)(qe - q);
+  re->seq = dup17(q, seq_len);
+  re->orig_seq = re->seq;
+  if (fasta->fastq) {
+    re->plus_line = dup17(plus, (size_t)(pe - plus));
+    const size_t qual_len = (size_t)(qle - ql);
+    re->qual = (char *)xmalloc(qual_len + 17);
+    for (size_t i = 0; i < qual_len; i++) re->qual[i] = MAX((char)ql[i], '!');
+    memset(re->qual + qual_len, 0, 17);
+    re->orig_qual = re->qual;
+  }
+  // RNA? (fasta.c:524-538)
+  const bool got_uracil = memchr(q, 'U', seq_len) || memchr(q, 'u', seq_len);
+  if (got_uracil) {
+    const bool got_thymine = memchr(q, 'T', seq_len) || memchr(q, 't', seq_len);
+    if (got_thymine) fprintf(stderr, "WARNING: sequence has both uracil and thymine!?!\n");
+    re->is_rna = !got_thymine;
+  } else {
+    re->is_rna = false;
+  }
+  r->pos = (size_t)(nx - r->buf);
+  return true;
+}
+
+static bool next_read(fasta_t fasta, read_entry *re) {
   Reader *r = reader_of(fasta);
   const char c = fasta->fastq ? '@' : '>';
   re->name = re->seq = NULL;
   re->paired = false;
   re->first_in_pair = false;
   re->mate_pair = NULL;
+  if (next_read_fast(r, fasta, re, c)) return true;
 
   // ---- the name line (fasta.c:340-384); comment lines ('#') in front of it are skipped
   size_t name_len = 0;
@@ -312,6 +392,12 @@ bool fasta_get_next_read_with_range(fasta_t fasta, read_entry *re) {   // fasta.
 }
 
 void fasta_close(fasta_t fasta) {   // fasta.c:208-220, plus this file's block
+  if (getenv("SHRIMP_B200_VERBOSE") && g_reader_calls > 1000) {
+    const double tps = (double)(__builtin_ia32_rdtsc() - g_tick0) / (omp_get_wtime() - g_wall0);
+    fprintf(stderr, "[gmapper-b200] reader: %llu entries in %.3f s (%.0f ns each), inside the critical section of gmapper.c:338\n",
+            g_reader_calls, (double)g_reader_ticks / tps, 1e9 * (double)g_reader_ticks / tps / (double)g_reader_calls);
+    g_reader_calls = 0;
+  }
   for (int i = 0; i < MAX_READERS; i++)
     if (g_readers[i].owner == fasta) {
       free(g_readers[i].buf);
@@ -325,6 +411,7 @@ void fasta_close(fasta_t fasta) {   // fasta.c:208-220, plus this file's block
   free(fasta);
 }
 
+#ifndef FAST_IO_READER_ONLY   // (tools: a reader-only build for the parser micro-benchmark)
 // ================================================================================================================
 // Formatter
 // ================================================================================================================
@@ -770,3 +857,4 @@ void hit_output(struct read_entry *re, struct read_hit *rh, struct read_hit *rh_
   if (seq != seq_small) free(seq);
   if (qual != qual_small) free(qual);
 }
+#endif   // FAST_IO_READER_ONLY

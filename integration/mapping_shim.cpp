@@ -28,6 +28,7 @@
 #include <string>
 #include <vector>
 
+#include <malloc.h>
 #include <math.h>
 #include <omp.h>
 #include <stdio.h>
@@ -69,7 +70,18 @@ static void init_thread_ctx() {
   // only once the genome is in memory and this is a mapping run (gmapper -S exits before the set-up calls)
   if (genome_contigs != NULL && num_contigs > 0 && n_seeds > 0) thread_ctx();
 }
-static const bool g_hooked = ((chunk_ctx_hook = ctx_if_any), (chunk_init_hook = init_thread_ctx), true);
+// gmapper.c allocates a 10 MB output buffer per chunk and grows it in 10 MB steps (gmapper.c:403, output.c:246-268):
+// at GPU rates that is an mmap / page-fault / munmap cycle of tens of megabytes per thread every few milliseconds, all
+// of them serialised on the process's address-space lock.  Keep such blocks on the heap and never trim it.
+static bool tune_malloc() {
+  if (!getenv("SHRIMP_B200_NO_MALLOPT")) {
+    mallopt(M_MMAP_THRESHOLD, 32 << 20);   // the largest value glibc accepts
+    mallopt(M_TRIM_THRESHOLD, -1);
+    mallopt(M_TOP_PAD, 64 << 20);
+  }
+  return true;
+}
+static const bool g_hooked = ((chunk_ctx_hook = ctx_if_any), (chunk_init_hook = init_thread_ctx), tune_malloc());
 
 static shrimp_sw_params sw_params_from_globals() {
   shrimp_sw_params sp;

@@ -410,18 +410,38 @@ __global__ void __launch_bounds__(128, PS_CTAS_PER_SM) post_sw_kernel(const Post
 // Every double is computed by the same operations in the same order as in the half-warp kernel above (and in
 // sw-post.c); tests/test_gpu_post_sw.py runs both.
 #define PQ_W 4
-__device__ __forceinline__ double ps_prior(const PostParams &P, const PsCol &pc, int l, int r) {   // nodePrior, sw-post.c:112-140
-  double val = 0;
-  if (pc.let != -2) val = val - (r == pc.let ? P.la1 : P.la2);
-  const bool same = (l ^ r) == pc.col;
+// nodePrior (sw-post.c:112-140) of the nodes of one column: val = 0; val -= (right == letter ? la1 : la2) when the
+// column emits a letter; val -= ((left ^ right) == colour ? l1 : l2).  Four distinct values per column: the
+// selections are made once per column, a node picks its value by two compares.
+struct PsEmit {
+  double v[2][2];   // [right == letter ? 0 : 1][colour matches ? 0 : 1]
+  int let, col;
+};
+__device__ __forceinline__ PsEmit ps_emit(const PostParams &P, const PsCol &pc) {
+  PsEmit E;
   const double l1 = pc.kind == 0 ? P.lc1 : pc.kind == 2 ? P.ln1 : P.lc1_tab[pc.q];
   const double l2 = pc.kind == 0 ? P.lc2 : pc.kind == 2 ? P.ln2 : P.lc2_tab[pc.q];
-  val = val - (same ? l1 : l2);
-  return val;
+  const bool has = pc.let != -2;
+  const double a1 = has ? 0.0 - P.la1 : 0.0, a2 = has ? 0.0 - P.la2 : 0.0;
+  E.v[0][0] = a1 - l1;
+  E.v[0][1] = a1 - l2;
+  E.v[1][0] = a2 - l1;
+  E.v[1][1] = a2 - l2;
+  E.let = has ? pc.let : 4;   // 4: no letter of the node equals it; a1 == a2 == 0 then
+  E.col = pc.col;
+  return E;
+}
+__device__ __forceinline__ double ps_prior(const PsEmit &E, int l, int r) {
+  const bool lm = r == E.let, cm = (l ^ r) == E.col;
+  const double m0 = cm ? E.v[0][0] : E.v[0][1], m1 = cm ? E.v[1][0] : E.v[1][1];
+  return lm ? m0 : m1;
 }
 
-__global__ void __launch_bounds__(128) post_sw_quad_kernel(const PostParams P, int quads_per_cta, int max_cols, int n_groups,
-                                                           double *fw_scratch) {
+// MINB (resident CTAs per SM the register allocation aims at): 6 = 80 registers measured fastest (12.0 ms per C2 step;
+// 4 = 128 registers: 12.5, 8 = 64 registers with spills: 13.3)
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) post_sw_quad_kernel(const PostParams P, int quads_per_cta, int max_cols,
+                                                                 int n_groups, double *fw_scratch) {
   extern __shared__ double ps_smem[];
   const int lane = threadIdx.x & 31, ql = lane & 3;
   const int qidx = threadIdx.x >> 2;   // quad of the CTA
@@ -554,27 +574,27 @@ __global__ void __launch_bounds__(128) post_sw_quad_kernel(const PostParams P, i
   for (int t = 0; t < wlen; t++) {
     const bool on = t < len;
     const int c = len - 1 - t;   // backward column
-    const PsCol pc = on ? cols[t] : blank;
+    const PsEmit E = ps_emit(P, on ? cols[t] : blank);
     double nf[4], nb[4];
     if (t == 0) {
 #pragma unroll
       for (int l = 0; l < 4; l++) {
-        nf[l] = l == init_bp ? ps_prior(P, pc, l, ql) : HUGE_VAL;
+        nf[l] = l == init_bp ? ps_prior(E, l, ql) : HUGE_VAL;
         nb[l] = 0.0;
       }
     } else {
-      const PsCol nxt = on ? cols[c + 1] : blank;
+      const PsEmit En = ps_emit(P, on ? cols[c + 1] : blank);
       double sf = 0, sb = 0;
 #pragma unroll
       for (int m = 0; m < 4; m++) {
         sf += PS_EXP(-1 * (f[m]));
-        sb += PS_EXP(-1 * (ps_prior(P, nxt, ql, m) + b[m]));
+        sb += PS_EXP(-1 * (ps_prior(En, ql, m) + b[m]));
       }
       const double lgf = PS_LOG(sf), lgb = PS_LOG(sb);
 #pragma unroll
       for (int k = 0; k < 4; k++) {
         const double lf = __shfl_sync(0xffffffffu, lgf, k, PQ_W), lb = __shfl_sync(0xffffffffu, lgb, k, PQ_W);
-        nf[k] = ps_prior(P, pc, k, ql) - lf;
+        nf[k] = ps_prior(E, k, ql) - lf;
         nb[k] = on ? -lb : 0.0;
       }
     }
@@ -741,7 +761,7 @@ static int launch_post_sw_quad(shrimp_gpu_ctx *ctx, const PostParams &P, DevBuf 
   }
   const int quads = 8 * warps;
   const size_t smem = per_quad * quads;
-  auto kern = post_sw_quad_kernel;
+  auto kern = post_sw_quad_kernel<6>;
   SH_OPT_IN_SMEM(kern, ctx->device);
   int per_sm = 0;
   SH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, quads * 4, smem));

@@ -103,8 +103,11 @@ def main():
                 out["runs"].append({"variant": var, "threads": th, "chunk": ck, "map_s": s, "wall_s": wall,
                                     "reads_per_s": a.reads / s})
                 print(json.dumps(out["runs"][-1]), flush=True)
-                for ln in [x for x in err.splitlines() if x.startswith("[gmapper-b200]")][:3]:
+                for ln in [x for x in err.splitlines() if x.startswith("[gmapper-b200] thread")][:3]:
                     print("   ", ln, flush=True)
+                for ln in [x for x in err.splitlines() if x.startswith("[gmapper-b200] reader") or "Wait Time" in x or
+                           "Read Load Time" in x or "Fasta Lib Time" in x]:
+                    print("   ", ln.strip(), flush=True)
         for P in [int(x) for x in a.procs.split(",") if x]:
             out["runs"].append(run_split(NEW_DIR, w, d, codes, P, max(1, ncores // P), int(a.chunk.split(",")[0]), env))
             print(json.dumps(out["runs"][-1]), flush=True)
