@@ -5,6 +5,10 @@
  *
  *     bool fasta_get_next_read_with_range(fasta_t, read_entry *)                        common/fasta.c:316
  *     void hit_output(read_entry *, read_hit *, read_hit *, bool, int *, int, bool)     gmapper/output.c:227
+ *     uint32_t *fasta_sequence_to_bitfield(fasta_t, char *)                             common/fasta.c:610
+ *     uint32_t *reverse_complement_read_cs(uint32_t *, int8_t, int8_t, uint32_t, bool)  common/util.c:601
+ * (the last two are the per-read packing of gmapper.c:475-488: one out-of-line call per base in the reference, 0.5 us
+ * per read -- as much as the device spends on the whole read)
  *
  * Both carry the reference's C++ linkage and signatures.  integration/Makefile links them over the reference's own
  * definitions, which `objcopy --weaken-symbol` turns weak in a COPY of the reference's unchanged fasta.o / output.o
@@ -23,8 +27,14 @@
  * Everything that decides a byte of the record (flag bits, POS of a reverse-strand hit, CIGAR runs, the IUPAC
  * rule of the SEQ column, Z0..Z6 through the same libm `log`) follows output.c line by line, cited below.
  */
+#include <atomic>
+#include <thread>
+#include <vector>
+
 #include <ctype.h>
 #include <math.h>
+#include <sched.h>
+#include <unistd.h>
 #include <omp.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -174,15 +184,127 @@ char *extract_name_fast(char *line, char **ranges) {
 }  // namespace
 
 static bool next_read(fasta_t fasta, read_entry *re);
-bool fasta_get_next_read_with_range(fasta_t fasta, read_entry *re) {   // fasta.c:316
-  const unsigned long long t0 = __builtin_ia32_rdtsc();
-  if (g_tick0 == 0) {
-    g_tick0 = t0;
-    g_wall0 = omp_get_wtime();
+
+// ---- read-ahead ------------------------------------------------------------------------------------------------------
+// gmapper.c calls the reader inside `omp critical (fill_reads_buffer)` (gmapper.c:338): whatever an entry costs there
+// is serial time of the whole run -- at 150 ns per entry a ceiling of 6 M reads/s however many threads map.  Once a
+// file has delivered READ_AHEAD_AFTER entries (a read file, not a genome of a few contigs) a thread of this file's own
+// parses ahead, entry by entry with the very same next_read(), into a ring; the call inside the critical section then
+// only takes the next entry off the ring.  Order, strings, allocations (free()-able, one per string) and the
+// end-of-file / error outcome are those of calling next_read() in place.
+struct Ahead {
+  struct Entry {
+    char *name, *seq, *orig_seq, *qual, *orig_qual, *plus_line, *range_string;
+    bool is_rna, ok;
+    size_t bytes;
+  };
+  fasta_t owner = NULL;
+  std::vector<Entry> ring;
+  std::atomic<size_t> head{0}, tail{0};     // consumer takes ring[head % cap], producer fills ring[tail % cap]
+  std::atomic<size_t> bytes_in{0}, bytes_out{0};
+  std::atomic<bool> stop{false}, done{false};
+  std::thread th;
+};
+enum { AHEAD_CAP = 1 << 18 };
+static const size_t READ_AHEAD_AFTER =
+    getenv("SHRIMP_B200_READ_AHEAD_AFTER") ? (size_t)atol(getenv("SHRIMP_B200_READ_AHEAD_AFTER")) : 4096;   // (tests: 50)
+static const size_t AHEAD_BYTES = (size_t)256 << 20;
+static Ahead *g_ahead[MAX_READERS];
+static size_t g_delivered[MAX_READERS];
+
+static void ahead_main(Ahead *A) {
+  for (;;) {
+    size_t t = A->tail.load(std::memory_order_relaxed);
+    while (!A->stop.load(std::memory_order_relaxed) &&
+           (t - A->head.load(std::memory_order_acquire) >= AHEAD_CAP ||
+            (A->bytes_in.load(std::memory_order_relaxed) - A->bytes_out.load(std::memory_order_acquire) > AHEAD_BYTES &&
+             t != A->head.load(std::memory_order_acquire))))
+      usleep(200);   // the ring holds far more than is taken in 200 us
+    if (A->stop.load(std::memory_order_relaxed)) break;
+    read_entry tmp;
+    memset(&tmp, 0, sizeof(tmp));
+    Ahead::Entry &E = A->ring[t % AHEAD_CAP];
+    E.ok = next_read(A->owner, &tmp);
+    E.name = tmp.name; E.seq = tmp.seq; E.orig_seq = tmp.orig_seq; E.qual = tmp.qual; E.orig_qual = tmp.orig_qual;
+    E.plus_line = tmp.plus_line; E.range_string = tmp.range_string; E.is_rna = tmp.is_rna;
+    E.bytes = E.ok ? strlen(tmp.seq) * (tmp.qual ? 2 : 1) + 64 : 0;
+    A->bytes_in.fetch_add(E.bytes, std::memory_order_relaxed);
+    A->tail.store(t + 1, std::memory_order_release);
+    if (!E.ok) break;
   }
-  const bool ok = next_read(fasta, re);
-  g_reader_ticks += __builtin_ia32_rdtsc() - t0;
-  g_reader_calls++;
+  A->done.store(true, std::memory_order_release);
+}
+
+static bool ahead_take(Ahead *A, read_entry *re) {
+  const size_t h = A->head.load(std::memory_order_relaxed);
+  int spins = 0;
+  while (A->tail.load(std::memory_order_acquire) == h) {
+    if (A->done.load(std::memory_order_acquire) && A->tail.load(std::memory_order_acquire) == h) {
+      re->name = re->seq = NULL;   // past the end of the file: fasta.c:340-372 finds no line
+      re->paired = false;
+      re->first_in_pair = false;
+      re->mate_pair = NULL;
+      return false;
+    }
+    if (++spins < 64) sched_yield();
+    else usleep(50);
+  }
+  const Ahead::Entry &E = A->ring[h % AHEAD_CAP];
+  re->name = E.name;
+  re->seq = E.seq;
+  re->paired = false;
+  re->first_in_pair = false;
+  re->mate_pair = NULL;
+  if (E.range_string) re->range_string = E.range_string;
+  if (E.seq) re->orig_seq = E.orig_seq;
+  if (E.plus_line) re->plus_line = E.plus_line;
+  if (E.qual) {
+    re->qual = E.qual;
+    re->orig_qual = E.orig_qual;
+  }
+  if (E.ok) re->is_rna = E.is_rna;
+  const bool ok = E.ok;
+  A->bytes_out.fetch_add(E.bytes, std::memory_order_release);
+  if (ok) A->head.store(h + 1, std::memory_order_release);   // the entry that ended the file stays: every later call sees it
+  return ok;
+}
+
+static int reader_slot(fasta_t f) {
+  for (int i = 0; i < MAX_READERS; i++)
+    if (g_readers[i].owner == f) return i;
+  return -1;
+}
+
+bool fasta_get_next_read_with_range(fasta_t fasta, read_entry *re) {   // fasta.c:316
+  static const bool verbose = getenv("SHRIMP_B200_VERBOSE") != NULL;
+  static const bool no_ahead = getenv("SHRIMP_B200_NO_READ_AHEAD") != NULL;
+  unsigned long long t0 = 0;
+  if (verbose) {
+    t0 = __builtin_ia32_rdtsc();
+    if (g_tick0 == 0) {
+      g_tick0 = t0;
+      g_wall0 = omp_get_wtime();
+    }
+  }
+  bool ok;
+  int slot = reader_slot(fasta);
+  if (slot >= 0 && g_ahead[slot]) {
+    ok = ahead_take(g_ahead[slot], re);
+  } else {
+    ok = next_read(fasta, re);
+    if (slot < 0) slot = reader_slot(fasta);
+    if (ok && slot >= 0 && !no_ahead && ++g_delivered[slot] == READ_AHEAD_AFTER) {
+      Ahead *A = new Ahead;
+      A->owner = fasta;
+      A->ring.resize(AHEAD_CAP);
+      g_ahead[slot] = A;
+      A->th = std::thread(ahead_main, A);
+    }
+  }
+  if (verbose) {
+    g_reader_ticks += __builtin_ia32_rdtsc() - t0;
+    g_reader_calls++;
+  }
   return ok;
 }
 
@@ -217,15 +339,29 @@ static bool next_read_fast(Reader *r, fasta_t fasta, read_entry *re, char c) {
     if ((size_t)(qle - ql) != want || want == 0) return false;
     nx = qle + 1;
   }
-  if (memchr(s, 0, (size_t)(nx - s)) || memchr(s, '\t', (size_t)(e - s))) return false;
   // the name: trimmed, cut at its first blank (extract_name, fasta.c:243-281, without a range field)
   char *b = s + 1, *t = e;
   while (b < t && isspace((unsigned char)*b)) b++;
   while (t > b && isspace((unsigned char)t[-1])) t--;
   if (b == t) return false;
-  char *sp = (char *)memchr(b, ' ', (size_t)(t - b));
-  re->name = dup17(b, (size_t)((sp ? sp : t) - b));
+  char *cut = NULL;
+  for (char *p = s + 1; p < e; p++) {
+    const char ch = *p;
+    if (ch == '\t' || ch == '\0') return false;
+    if (ch == ' ' && !cut && p >= b) cut = p;
+  }
+  // the sequence: a NUL ends the reference's copy (general path); uracil marks RNA (fasta.c:524-538)
   const size_t seq_len = (size_t)(qe - q);
+  unsigned nul = 0, ur = 0, th = 0;
+  for (size_t i = 0; i < seq_len; i++) {
+    const char ch = q[i];
+    nul |= ch == '\0';
+    ur |= (ch == 'U') | (ch == 'u');
+    th |= (ch == 'T') | (ch == 't');
+  }
+  if (nul) return false;
+  if (fasta->fastq && (memchr(plus, 0, (size_t)(pe - plus)) || memchr(ql, 0, (size_t)(qle - ql)))) return false;
+  re->name = dup17(b, (size_t)((cut && cut < t ? cut : t) - b));
   re->seq = dup17(q, seq_len);
   re->orig_seq = re->seq;
   if (fasta->fastq) {
@@ -236,15 +372,8 @@ static bool next_read_fast(Reader *r, fasta_t fasta, read_entry *re, char c) {
     memset(re->qual + qual_len, 0, 17);
     re->orig_qual = re->qual;
   }
-  // RNA? (fasta.c:524-538)
-  const bool got_uracil = memchr(q, 'U', seq_len) || memchr(q, 'u', seq_len);
-  if (got_uracil) {
-    const bool got_thymine = memchr(q, 'T', seq_len) || memchr(q, 't', seq_len);
-    if (got_thymine) fprintf(stderr, "WARNING: sequence has both uracil and thymine!?!\n");
-    re->is_rna = !got_thymine;
-  } else {
-    re->is_rna = false;
-  }
+  if (ur && th) fprintf(stderr, "WARNING: sequence has both uracil and thymine!?!\n");
+  re->is_rna = ur && !th;
   r->pos = (size_t)(nx - r->buf);
   return true;
 }
@@ -400,6 +529,21 @@ void fasta_close(fasta_t fasta) {   // fasta.c:208-220, plus this file's block
   }
   for (int i = 0; i < MAX_READERS; i++)
     if (g_readers[i].owner == fasta) {
+      if (Ahead *A = g_ahead[i]) {   // stop the read-ahead; entries nobody took are released
+        A->stop.store(true);
+        A->th.join();
+        for (size_t h = A->head.load(); h != A->tail.load(); h++) {
+          const Ahead::Entry &E = A->ring[h % AHEAD_CAP];
+          free(E.name);
+          free(E.seq);
+          free(E.qual);
+          free(E.plus_line);
+          free(E.range_string);
+        }
+        delete A;
+        g_ahead[i] = NULL;
+      }
+      g_delivered[i] = 0;
       free(g_readers[i].buf);
       free(g_readers[i].acc);
       g_readers[i] = Reader();
@@ -409,6 +553,53 @@ void fasta_close(fasta_t fasta) {   // fasta.c:208-220, plus this file's block
   free(fasta->parse_buffer);
   if (fasta->save_buf != NULL) free(fasta->save_buf);
   free(fasta);
+}
+
+// ================================================================================================================
+// Packing a read (gmapper.c:475-488)
+// ================================================================================================================
+uint32_t *fasta_sequence_to_bitfield(fasta_t fasta, char *sequence) {   // fasta.c:610
+  const uint32_t length = (uint32_t)strlen(sequence);
+  if (length == 0) return NULL;
+  const size_t words = BPTO32BW(length);
+  uint32_t *bitfield = (uint32_t *)xmalloc(words * sizeof(uint32_t));
+  memset(bitfield, 0, words * sizeof(uint32_t));
+  uint32_t i = 0;
+  if (fasta->space == COLOUR_SPACE) {   // the initial base is not part of the bitfield
+    const char c = sequence[0];
+    if (c != 'A' && c != 'a' && c != 'C' && c != 'c' && c != 'G' && c != 'g' && c != 'T' && c != 't') {
+      free(bitfield);
+      return NULL;
+    }
+    i = 1;
+  }
+  for (uint32_t idx = 0; i < length; i++, idx++) {
+    const unsigned char ch = (unsigned char)sequence[i];
+    const int a = ch < 128 ? fasta->translate[ch] : -1;
+    if (a == -1) {   // the reference's message (it tests the translated value, so no character is printed)
+      fprintf(stderr, "error: invalid character ");
+      fprintf(stderr, "in input file [%s]\n", fasta->file);
+      fprintf(stderr, "       (Did you mix up letter space and colour space programs?)\n");
+      exit(1);
+    }
+    bitfield[idx >> 3] |= ((uint32_t)a & 0xfu) << (4 * (idx & 7));
+  }
+  return bitfield;
+}
+
+uint32_t *reverse_complement_read_cs(uint32_t *read, int8_t initbp, int8_t initbp_rc, uint32_t len, bool is_rna) {   // util.c:601
+  const size_t words = BPTO32BW(len);
+  uint32_t *read_rc = (uint32_t *)xmalloc(sizeof(uint32_t) * words);
+  memset(read_rc, 0, sizeof(uint32_t) * words);   // (the reference leaves the unused nibbles of the last word unset)
+  int8_t base = (int8_t)cstols(initbp, EXTRACT(read, 0), is_rna);
+  for (uint32_t i = 1; i < len; i++) {
+    const uint32_t c = EXTRACT(read, i);
+    base = (int8_t)cstols(base, (int)c, is_rna);
+    const uint32_t at = len - i;
+    read_rc[at >> 3] |= c << (4 * (at & 7));
+  }
+  read_rc[0] |= (uint32_t)lstocs(base, complement_base(initbp_rc, is_rna), is_rna) & 0xfu;
+  return read_rc;
 }
 
 #ifndef FAST_IO_READER_ONLY   // (tools: a reader-only build for the parser micro-benchmark)

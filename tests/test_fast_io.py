@@ -27,7 +27,9 @@ pytestmark = pytest.mark.skipif(
 
 def run(bindir, binary, args, cwd, threads=4, stdin=None, ok=(0,)):
     cmd = [os.path.join(bindir, binary), "-N", str(threads), *args]
-    r = subprocess.run(cmd, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=1200, stdin=stdin)
+    # the read-ahead thread of fast_io.cpp starts after 50 entries instead of 4,096, so that these small files use it
+    env = dict(os.environ, SHRIMP_B200_READ_AHEAD_AFTER=os.environ.get("SHRIMP_B200_READ_AHEAD_AFTER", "50"))
+    r = subprocess.run(cmd, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=1200, stdin=stdin, env=env)
     assert r.returncode in ok, (cmd, r.returncode, r.stderr.decode(errors="replace")[-2000:])
     body = [ln for ln in r.stdout.split(b"\n") if not ln.startswith(b"@PG")]
     return body, r.stderr.decode(errors="replace"), r.returncode
@@ -245,13 +247,25 @@ def test_malformed_input_same_outcome(kind, tmp_path):
     same(ref, new)
 
 
-def test_fast_io_replaces_exactly_two_reference_symbols():
+def test_without_read_ahead(tmp_path, monkeypatch):
+    """the reader called in place (no read-ahead thread), chunks of 100 reads"""
+    monkeypatch.setenv("SHRIMP_B200_READ_AHEAD_AFTER", "1000000000")
+    case = subset(LsCase("c2_small_fastq_mq"), 900)
+    case.write_fasta(str(tmp_path))
+    args = ["-Q", "-K", "100", "reads.fa", "genome.fa"]
+    ref, _, _ = run(REF, case.binary, args, str(tmp_path))
+    new, _, _ = run(NEW, case.binary, args, str(tmp_path), 3)
+    same(ref, new)
+
+
+def test_fast_io_replaces_exactly_the_named_reference_symbols():
     b = os.path.join(ROOT, "integration", "_build")
     out = subprocess.run(["nm", "--defined-only", os.path.join(b, "fast_io.o")], stdout=subprocess.PIPE,
                          check=True).stdout.decode()
     have = {ln.split()[-1] for ln in out.splitlines() if " T " in ln}
     assert have == {"_Z10hit_outputP10read_entryP8read_hitS2_bPiib", "_Z11fasta_closeP8_fasta_t",
-                    "_Z30fasta_get_next_read_with_rangeP8_fasta_tP10read_entry"}, have
+                    "_Z30fasta_get_next_read_with_rangeP8_fasta_tP10read_entry",
+                    "_Z26fasta_sequence_to_bitfieldP8_fasta_tPc", "_Z26reverse_complement_read_csPjaajb"}, have
     weak = subprocess.run(["nm", os.path.join(b, "weak", "gmapper_output.o")], stdout=subprocess.PIPE,
                           check=True).stdout.decode()
     assert " W _Z10hit_outputP10read_entryP8read_hitS2_bPiib" in weak and " T shrimp_ref_hit_output" in weak
