@@ -184,89 +184,202 @@ char *extract_name_fast(char *line, char **ranges) {
 }  // namespace
 
 static bool next_read(fasta_t fasta, read_entry *re);
+struct Views {   // the strings of one entry, in the reader's block (fast path) or in strings next_read() made
+  const char *name, *seq, *plus, *qual, *range;
+  size_t name_len, seq_len, plus_len, qual_len, range_len;
+  bool is_rna;
+};
+static bool next_read_fast(Reader *r, fasta_t fasta, Views *V, char c);
 
 // ---- read-ahead ------------------------------------------------------------------------------------------------------
 // gmapper.c calls the reader inside `omp critical (fill_reads_buffer)` (gmapper.c:338): whatever an entry costs there
-// is serial time of the whole run -- at 150 ns per entry a ceiling of 6 M reads/s however many threads map.  Once a
-// file has delivered READ_AHEAD_AFTER entries (a read file, not a genome of a few contigs) a thread of this file's own
-// parses ahead, entry by entry with the very same next_read(), into a ring; the call inside the critical section then
-// only takes the next entry off the ring.  Order, strings, allocations (free()-able, one per string) and the
-// end-of-file / error outcome are those of calling next_read() in place.
+// is serial time of the whole run -- at 150-200 ns per entry a ceiling of 5-6 M reads/s however many threads map.  Once
+// a file has delivered READ_AHEAD_AFTER entries (a read file, not a genome of a few contigs) a thread of this file's
+// own parses ahead -- the same next_read_fast() / next_read() -- and lays the TEXT of every entry into a byte ring; the
+// call inside the critical section allocates the entry's strings from that text and nothing else.  (The strings are
+// allocated by the thread that will free them: handing malloc'd blocks from one producer thread to sixteen consumers
+// was measured three times slower than parsing in place -- every block and its allocator metadata change cores.)
+// Order, strings, allocations (free()-able, one per string) and the end-of-file / error outcome are those of calling
+// next_read() in place.
 struct Ahead {
-  struct Entry {
-    char *name, *seq, *orig_seq, *qual, *orig_qual, *plus_line, *range_string;
-    bool is_rna, ok;
-    size_t bytes;
+  struct Rec {   // followed by the text: name, sequence, '+' line, qualities, range field
+    uint32_t total;   // bytes to the next record
+    uint32_t name_len, seq_len, plus_len, qual_len, range_len;
+    uint8_t ok, is_rna, has_name, has_seq, has_plus, has_qual, has_range, pad;
   };
   fasta_t owner = NULL;
-  std::vector<Entry> ring;
-  std::atomic<size_t> head{0}, tail{0};     // consumer takes ring[head % cap], producer fills ring[tail % cap]
-  std::atomic<size_t> bytes_in{0}, bytes_out{0};
-  std::atomic<bool> stop{false}, done{false};
+  char *slab = NULL;
+  size_t size = 0;
+  // bytes written / taken since the start.  Each side works on its own copy and publishes it every PUBLISH bytes (and
+  // whenever it has to wait): a counter the other side polls changes cores with every store otherwise
+  alignas(64) std::atomic<unsigned long long> w{0};
+  alignas(64) std::atomic<unsigned long long> r{0};
+  alignas(64) unsigned long long w_local = 0, w_published = 0;   // producer
+  alignas(64) unsigned long long r_local = 0, r_published = 0, w_seen = 0;   // consumer
+  bool ended = false;   // consumer: the record that ended the file has been seen
+  alignas(64) std::atomic<bool> stop{false};
+  std::atomic<bool> done{false};
   std::thread th;
 };
-enum { AHEAD_CAP = 1 << 18 };
+enum { PUBLISH = 32 << 10 };
 static const size_t READ_AHEAD_AFTER =
     getenv("SHRIMP_B200_READ_AHEAD_AFTER") ? (size_t)atol(getenv("SHRIMP_B200_READ_AHEAD_AFTER")) : 4096;   // (tests: 50)
-static const size_t AHEAD_BYTES = (size_t)256 << 20;
 static Ahead *g_ahead[MAX_READERS];
 static size_t g_delivered[MAX_READERS];
 
-static void ahead_main(Ahead *A) {
+// room for a record of `need` bytes that does not wrap; NULL when asked to stop
+static char *ahead_reserve(Ahead *A, size_t need, double *waited) {
   for (;;) {
-    size_t t = A->tail.load(std::memory_order_relaxed);
-    while (!A->stop.load(std::memory_order_relaxed) &&
-           (t - A->head.load(std::memory_order_acquire) >= AHEAD_CAP ||
-            (A->bytes_in.load(std::memory_order_relaxed) - A->bytes_out.load(std::memory_order_acquire) > AHEAD_BYTES &&
-             t != A->head.load(std::memory_order_acquire))))
-      usleep(200);   // the ring holds far more than is taken in 200 us
-    if (A->stop.load(std::memory_order_relaxed)) break;
+    const unsigned long long w = A->w_local;
+    const size_t at = (size_t)(w % A->size), to_end = A->size - at;
+    const size_t want = need <= to_end ? need : to_end + need;   // a pad record to the end of the slab first
+    while (w + want - A->r.load(std::memory_order_acquire) > A->size) {
+      if (A->stop.load(std::memory_order_relaxed)) return NULL;
+      if (A->w_published != w) {
+        A->w.store(w, std::memory_order_release);
+        A->w_published = w;
+      }
+      const double t0 = omp_get_wtime();
+      usleep(200);   // the slab holds far more than is taken in 200 us
+      *waited += omp_get_wtime() - t0;
+    }
+    if (need <= to_end) return A->slab + at;
+    Ahead::Rec pad;
+    memset(&pad, 0, sizeof(pad));
+    pad.total = (uint32_t)to_end;
+    pad.pad = 1;
+    memcpy(A->slab + at, &pad, sizeof(pad));   // to_end >= sizeof(Rec): records are multiples of 32 bytes
+    A->w_local = w + to_end;
+  }
+}
+
+static void ahead_main(Ahead *A) {
+  Reader *r = reader_of(A->owner);
+  const bool fastq = A->owner->fastq;
+  const char c = fastq ? '@' : '>';
+  unsigned long long n_entries = 0, n_general = 0;
+  const double t_start = omp_get_wtime();
+  double t_waited = 0;
+  for (;;) {
+    Views V;
     read_entry tmp;
     memset(&tmp, 0, sizeof(tmp));
-    Ahead::Entry &E = A->ring[t % AHEAD_CAP];
-    E.ok = next_read(A->owner, &tmp);
-    E.name = tmp.name; E.seq = tmp.seq; E.orig_seq = tmp.orig_seq; E.qual = tmp.qual; E.orig_qual = tmp.orig_qual;
-    E.plus_line = tmp.plus_line; E.range_string = tmp.range_string; E.is_rna = tmp.is_rna;
-    E.bytes = E.ok ? strlen(tmp.seq) * (tmp.qual ? 2 : 1) + 64 : 0;
-    A->bytes_in.fetch_add(E.bytes, std::memory_order_relaxed);
-    A->tail.store(t + 1, std::memory_order_release);
-    if (!E.ok) break;
+    bool ok = true, general = false;
+    if (!next_read_fast(r, A->owner, &V, c)) {   // the general path makes strings: their text goes into the slab too
+      general = true;
+      ok = next_read(A->owner, &tmp);
+      memset(&V, 0, sizeof(V));
+      V.name = tmp.name; V.name_len = tmp.name ? strlen(tmp.name) : 0;
+      V.seq = tmp.seq; V.seq_len = tmp.seq ? strlen(tmp.seq) : 0;
+      V.plus = tmp.plus_line; V.plus_len = tmp.plus_line ? strlen(tmp.plus_line) : 0;
+      V.qual = tmp.qual; V.qual_len = tmp.qual ? strlen(tmp.qual) : 0;
+      V.range = tmp.range_string; V.range_len = tmp.range_string ? strlen(tmp.range_string) : 0;
+      V.is_rna = tmp.is_rna;
+    }
+    const size_t text = V.name_len + V.seq_len + V.plus_len + V.qual_len + V.range_len;
+    const size_t need = (sizeof(Ahead::Rec) + text + 31) & ~(size_t)31;
+    n_entries++;
+    n_general += general;
+    char *at = ahead_reserve(A, need, &t_waited);
+    if (at) {
+      Ahead::Rec R;
+      memset(&R, 0, sizeof(R));
+      R.total = (uint32_t)need;
+      R.name_len = (uint32_t)V.name_len; R.seq_len = (uint32_t)V.seq_len; R.plus_len = (uint32_t)V.plus_len;
+      R.qual_len = (uint32_t)V.qual_len; R.range_len = (uint32_t)V.range_len;
+      R.ok = ok; R.is_rna = V.is_rna;
+      R.has_name = V.name != NULL; R.has_seq = V.seq != NULL; R.has_plus = V.plus != NULL; R.has_qual = V.qual != NULL;
+      R.has_range = V.range != NULL;
+      memcpy(at, &R, sizeof(R));
+      char *p = at + sizeof(R);
+      if (V.name_len) memcpy(p, V.name, V.name_len);
+      p += V.name_len;
+      if (V.seq_len) memcpy(p, V.seq, V.seq_len);
+      p += V.seq_len;
+      if (V.plus_len) memcpy(p, V.plus, V.plus_len);
+      p += V.plus_len;
+      if (V.qual_len) memcpy(p, V.qual, V.qual_len);
+      p += V.qual_len;
+      if (V.range_len) memcpy(p, V.range, V.range_len);
+      A->w_local += need;
+      if (general || !ok || A->w_local - A->w_published >= PUBLISH) {
+        A->w.store(A->w_local, std::memory_order_release);
+        A->w_published = A->w_local;
+      }
+    }
+    if (general) {
+      free(tmp.name);
+      free(tmp.seq);
+      free(tmp.plus_line);
+      free(tmp.qual);
+      free(tmp.range_string);
+    }
+    if (!at || !ok) break;
   }
+  A->w.store(A->w_local, std::memory_order_release);
   A->done.store(true, std::memory_order_release);
+  if (getenv("SHRIMP_B200_VERBOSE"))
+    fprintf(stderr, "[gmapper-b200] read-ahead thread: %llu entries (%llu through the general path), %.3f s of its own\n",
+            n_entries, n_general, omp_get_wtime() - t_start - t_waited);
 }
 
 static bool ahead_take(Ahead *A, read_entry *re) {
-  const size_t h = A->head.load(std::memory_order_relaxed);
-  int spins = 0;
-  while (A->tail.load(std::memory_order_acquire) == h) {
-    if (A->done.load(std::memory_order_acquire) && A->tail.load(std::memory_order_acquire) == h) {
-      re->name = re->seq = NULL;   // past the end of the file: fasta.c:340-372 finds no line
-      re->paired = false;
-      re->first_in_pair = false;
-      re->mate_pair = NULL;
-      return false;
-    }
-    if (++spins < 64) sched_yield();
-    else usleep(50);
-  }
-  const Ahead::Entry &E = A->ring[h % AHEAD_CAP];
-  re->name = E.name;
-  re->seq = E.seq;
+  re->name = re->seq = NULL;
   re->paired = false;
   re->first_in_pair = false;
   re->mate_pair = NULL;
-  if (E.range_string) re->range_string = E.range_string;
-  if (E.seq) re->orig_seq = E.orig_seq;
-  if (E.plus_line) re->plus_line = E.plus_line;
-  if (E.qual) {
-    re->qual = E.qual;
-    re->orig_qual = E.orig_qual;
+  if (A->ended) return false;   // past the end of the file: fasta.c:340-372 finds no line
+  for (;;) {
+    const unsigned long long rd = A->r_local;
+    int spins = 0;
+    while (A->w_seen == rd) {
+      A->w_seen = A->w.load(std::memory_order_acquire);
+      if (A->w_seen != rd) break;
+      if (A->r_published != rd) {   // about to wait: the producer may be waiting for this room
+        A->r.store(rd, std::memory_order_release);
+        A->r_published = rd;
+      }
+      if (A->done.load(std::memory_order_acquire) && A->w.load(std::memory_order_acquire) == rd) {
+        A->ended = true;
+        return false;
+      }
+      if (++spins < 64) sched_yield();
+      else usleep(50);
+    }
+    const char *at = A->slab + (size_t)(rd % A->size);
+    Ahead::Rec R;
+    memcpy(&R, at, sizeof(R));
+    if (R.pad) {
+      A->r_local = rd + R.total;
+      continue;
+    }
+    const char *p = at + sizeof(R);
+    if (R.has_name) re->name = dup17(p, R.name_len);
+    p += R.name_len;
+    if (R.has_seq) {
+      re->seq = dup17(p, R.seq_len);
+      re->orig_seq = re->seq;
+    }
+    p += R.seq_len;
+    if (R.has_plus) re->plus_line = dup17(p, R.plus_len);
+    p += R.plus_len;
+    if (R.has_qual) {   // (already raised to '!' when it came through the general path; idempotent)
+      re->qual = (char *)xmalloc((size_t)R.qual_len + 17);
+      for (uint32_t i = 0; i < R.qual_len; i++) re->qual[i] = MAX((char)p[i], '!');
+      memset(re->qual + R.qual_len, 0, 17);
+      re->orig_qual = re->qual;
+    }
+    p += R.qual_len;
+    if (R.has_range) re->range_string = dup17(p, R.range_len);
+    if (R.ok) re->is_rna = R.is_rna;
+    A->r_local = rd + R.total;
+    if (A->r_local - A->r_published >= PUBLISH) {
+      A->r.store(A->r_local, std::memory_order_release);
+      A->r_published = A->r_local;
+    }
+    if (!R.ok) A->ended = true;
+    return R.ok;
   }
-  if (E.ok) re->is_rna = E.is_rna;
-  const bool ok = E.ok;
-  A->bytes_out.fetch_add(E.bytes, std::memory_order_release);
-  if (ok) A->head.store(h + 1, std::memory_order_release);   // the entry that ended the file stays: every later call sees it
-  return ok;
 }
 
 static int reader_slot(fasta_t f) {
@@ -296,7 +409,8 @@ bool fasta_get_next_read_with_range(fasta_t fasta, read_entry *re) {   // fasta.
     if (ok && slot >= 0 && !no_ahead && ++g_delivered[slot] == READ_AHEAD_AFTER) {
       Ahead *A = new Ahead;
       A->owner = fasta;
-      A->ring.resize(AHEAD_CAP);
+      A->size = (size_t)8 << 20;   // small enough to stay in the last-level cache between the two threads
+      A->slab = (char *)xmalloc(A->size);
       g_ahead[slot] = A;
       A->th = std::thread(ahead_main, A);
     }
@@ -312,7 +426,7 @@ bool fasta_get_next_read_with_range(fasta_t fasta, read_entry *re) {   // fasta.
 // of the right length), the next entry's marker behind it, all inside the current block, no NUL bytes -- is taken
 // apart in place with memchr; anything else returns false without having consumed a byte and next_read's general
 // path (the restatement of fasta.c:316-545 piece by piece) takes the entry.
-static bool next_read_fast(Reader *r, fasta_t fasta, read_entry *re, char c) {
+static bool next_read_fast(Reader *r, fasta_t fasta, Views *V, char c) {
   if (r->header) return false;
   char *s = r->buf + r->pos, *const end = r->buf + r->end;
   if (s >= end || *s != c) return false;
@@ -344,39 +458,61 @@ static bool next_read_fast(Reader *r, fasta_t fasta, read_entry *re, char c) {
   while (b < t && isspace((unsigned char)*b)) b++;
   while (t > b && isspace((unsigned char)t[-1])) t--;
   if (b == t) return false;
-  char *cut = NULL;
-  for (char *p = s + 1; p < e; p++) {
-    const char ch = *p;
-    if (ch == '\t' || ch == '\0') return false;
-    if (ch == ' ' && !cut && p >= b) cut = p;
-  }
-  // the sequence: a NUL ends the reference's copy (general path); uracil marks RNA (fasta.c:524-538)
+  // one table look-up per byte: tabs and NULs send the entry to the general path, the first blank cuts the name,
+  // uracil marks RNA (fasta.c:524-538)
+  static const struct Classes {
+    unsigned char t[256];
+    Classes() {
+      memset(t, 0, sizeof(t));
+      t[0] = 1; t[(int)'\t'] = 2; t[(int)' '] = 4;
+      t[(int)'U'] = t[(int)'u'] = 8; t[(int)'T'] = t[(int)'t'] = 16;
+    }
+  } K;
+  unsigned ncls = 0;
+  for (const char *p = b; p < t; p++) ncls |= K.t[(unsigned char)*p];
+  for (const char *p = s + 1; p < b; p++) ncls |= K.t[(unsigned char)*p] & 3;
+  for (const char *p = t; p < e; p++) ncls |= K.t[(unsigned char)*p] & 3;
+  if (ncls & 3) return false;
+  char *cut = (ncls & 4) ? (char *)memchr(b, ' ', (size_t)(t - b)) : NULL;
   const size_t seq_len = (size_t)(qe - q);
-  unsigned nul = 0, ur = 0, th = 0;
-  for (size_t i = 0; i < seq_len; i++) {
-    const char ch = q[i];
-    nul |= ch == '\0';
-    ur |= (ch == 'U') | (ch == 'u');
-    th |= (ch == 'T') | (ch == 't');
-  }
+  unsigned scls = 0;
+  for (size_t i = 0; i < seq_len; i++) scls |= K.t[(unsigned char)q[i]];
+  const unsigned nul = scls & 1, ur = scls & 8, th = scls & 16;
   if (nul) return false;
   if (fasta->fastq && (memchr(plus, 0, (size_t)(pe - plus)) || memchr(ql, 0, (size_t)(qle - ql)))) return false;
-  re->name = dup17(b, (size_t)((cut && cut < t ? cut : t) - b));
-  re->seq = dup17(q, seq_len);
-  re->orig_seq = re->seq;
-  if (fasta->fastq) {
-    re->plus_line = dup17(plus, (size_t)(pe - plus));
-    const size_t qual_len = (size_t)(qle - ql);
-    re->qual = (char *)xmalloc(qual_len + 17);
-    for (size_t i = 0; i < qual_len; i++) re->qual[i] = MAX((char)ql[i], '!');
-    memset(re->qual + qual_len, 0, 17);
-    re->orig_qual = re->qual;
-  }
+  V->name = b;
+  V->name_len = (size_t)((cut && cut < t ? cut : t) - b);
+  V->seq = q;
+  V->seq_len = seq_len;
+  V->plus = plus;
+  V->plus_len = plus ? (size_t)(pe - plus) : 0;
+  V->qual = ql;
+  V->qual_len = ql ? (size_t)(qle - ql) : 0;
+  V->range = NULL;
+  V->range_len = 0;
   if (ur && th) fprintf(stderr, "WARNING: sequence has both uracil and thymine!?!\n");
-  re->is_rna = ur && !th;
+  V->is_rna = ur && !th;
   r->pos = (size_t)(nx - r->buf);
   return true;
 }
+
+// the strings of an entry as fasta.c leaves them in a read_entry: one allocation each, 17 zero bytes behind the text,
+// qualities raised to '!' (fasta.c:381-383, :508-513)
+static void materialise(const Views &V, bool fastq, read_entry *re) {
+  re->name = dup17(V.name, V.name_len);
+  re->seq = dup17(V.seq, V.seq_len);
+  re->orig_seq = re->seq;
+  if (V.range) re->range_string = dup17(V.range, V.range_len);
+  if (fastq) {
+    re->plus_line = dup17(V.plus, V.plus_len);
+    re->qual = (char *)xmalloc(V.qual_len + 17);
+    for (size_t i = 0; i < V.qual_len; i++) re->qual[i] = MAX((char)V.qual[i], '!');
+    memset(re->qual + V.qual_len, 0, 17);
+    re->orig_qual = re->qual;
+  }
+  re->is_rna = V.is_rna;
+}
+
 
 static bool next_read(fasta_t fasta, read_entry *re) {
   Reader *r = reader_of(fasta);
@@ -385,7 +521,11 @@ static bool next_read(fasta_t fasta, read_entry *re) {
   re->paired = false;
   re->first_in_pair = false;
   re->mate_pair = NULL;
-  if (next_read_fast(r, fasta, re, c)) return true;
+  Views V;
+  if (next_read_fast(r, fasta, &V, c)) {
+    materialise(V, fasta->fastq, re);
+    return true;
+  }
 
   // ---- the name line (fasta.c:340-384); comment lines ('#') in front of it are skipped
   size_t name_len = 0;
@@ -532,14 +672,7 @@ void fasta_close(fasta_t fasta) {   // fasta.c:208-220, plus this file's block
       if (Ahead *A = g_ahead[i]) {   // stop the read-ahead; entries nobody took are released
         A->stop.store(true);
         A->th.join();
-        for (size_t h = A->head.load(); h != A->tail.load(); h++) {
-          const Ahead::Entry &E = A->ring[h % AHEAD_CAP];
-          free(E.name);
-          free(E.seq);
-          free(E.qual);
-          free(E.plus_line);
-          free(E.range_string);
-        }
+        free(A->slab);
         delete A;
         g_ahead[i] = NULL;
       }
