@@ -668,7 +668,7 @@ def measure(a, w, n_reads, rank, world, local_rank, ncores, compact=False):
     if dropin_job is not None:
         # the drop-in binary runs with the GPU to itself, as it would in production: this process's contexts are closed
         dropin, d, n_sam = dropin_job
-        th, ck = min(ncores, 16), max(2000, min(125_000, n_sam // 16)) & ~1
+        th, ck = min(ncores, 16), max(2000, min(50_000, n_sam // 32)) & ~1
         rd = ["-1", "big.fa.1", "-2", "big.fa.2"] if w.paired else ["big.fa"]
         r = subprocess.run([dropin, "-N", str(th), "-K", str(ck), *w.load_args(), "-L", "proj", *rd], cwd=d,
                            stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
@@ -678,8 +678,9 @@ def measure(a, w, n_reads, rank, world, local_rank, ncores, compact=False):
                        "reference_value": cpu["value"] if cpu else None,
                        "how": f"integration/_build/{w.binary} -N {th} -K {ck} {' '.join(w.load_args())} -L <projection> "
                               "<reads.fa>: FASTA in, SAM out, the binary's own Read Mapping Time (the reference's clock, "
-                              "gmapper.c:3015-3021); the reference's unchanged serial FASTA parser (fasta.c:316, inside an "
-                              "omp critical section, gmapper.c:339) and output.c bound it, not the device"}
+                              "gmapper.c:3015-3021): the reference's unchanged gmapper.c / genome.c / output.c with the "
+                              "mapping shims and integration/fast_io.cpp (reader + SAM formatter, SURVEY 8 f2); the reader "
+                              "runs inside gmapper.c's omp critical section (gmapper.c:338) and bounds it, not the device"}
         else:
             e2e_sam = {"value": None, "unit": "reads/s", "how": "failed: " + r.stderr[-300:]}
         line["e2e_sam"] = e2e_sam

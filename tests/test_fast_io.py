@@ -27,8 +27,10 @@ pytestmark = pytest.mark.skipif(
 
 def run(bindir, binary, args, cwd, threads=4, stdin=None, ok=(0,)):
     cmd = [os.path.join(bindir, binary), "-N", str(threads), *args]
-    # the read-ahead thread of fast_io.cpp starts after 50 entries instead of 4,096, so that these small files use it
-    env = dict(os.environ, SHRIMP_B200_READ_AHEAD_AFTER=os.environ.get("SHRIMP_B200_READ_AHEAD_AFTER", "50"))
+    # the optional read-ahead thread of fast_io.cpp is switched on, and starts after 50 entries instead of 4,096 so
+    # that these small files use it (test_without_read_ahead covers the default)
+    env = dict(os.environ, SHRIMP_B200_READ_AHEAD="1",
+               SHRIMP_B200_READ_AHEAD_AFTER=os.environ.get("SHRIMP_B200_READ_AHEAD_AFTER", "50"))
     r = subprocess.run(cmd, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=1200, stdin=stdin, env=env)
     assert r.returncode in ok, (cmd, r.returncode, r.stderr.decode(errors="replace")[-2000:])
     body = [ln for ln in r.stdout.split(b"\n") if not ln.startswith(b"@PG")]
