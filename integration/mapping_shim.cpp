@@ -296,18 +296,58 @@ static shrimp_map_params map_params_from_globals() {
   return mp;
 }
 
-static void check_unpaired_options(const read_mapping_options_t *o, int n_options) {
-  if (n_options != 1) unsupported("a multi-stage --unpaired-options list");
+// One option set of an --unpaired-options list (gmapper.c:1632-1717) as parameters of a device call.  Served: the
+// sets that compute every structure afresh (regions when they are used, anchor list, hit list, pass 1) -- what the
+// reference's own default is, with any thresholds, match mode, window overlap and output counts -- because a device
+// call keeps no per-read state from one option set to the next.  A set that reuses the previous set's anchor or hit
+// list (`recompute` 0) stops the run.
+static shrimp_map_params map_params_from_globals();
+static shrimp_map_params stage_params(const read_mapping_options_t &o, int k) {
+  if (!o.anchor_list.recompute || !o.hit_list.recompute || !o.pass1.recompute)
+    unsupported("an --unpaired-options set that reuses the previous set's anchor list, hit list or pass 1 (recompute 0)");
+  if (o.anchor_list.use_region_counts && !o.regions.recompute && k == 0)
+    unsupported("an --unpaired-options set that uses region counts it does not compute");
+  if (!o.anchor_list.collapse) unsupported("an --unpaired-options set without anchor collapsing");
+  if (o.anchor_list.use_mp_region_counts != 0 || o.pass1.only_paired)
+    unsupported("mate-pair options in an --unpaired-options set");
+  if (o.hit_list.match_mode != 1 && o.hit_list.match_mode != 2) unsupported("an unpaired hit-list match mode other than 1 or 2");
+  if (o.pass1.min_matches != o.hit_list.match_mode)
+    unsupported("an --unpaired-options set whose pass-1 min_matches differs from its hit-list match mode");
+  if (o.pass1.gapless != o.hit_list.gapless) unsupported("an --unpaired-options set that is gapless in one of hit list / pass 1 only");
+  if (o.anchor_list.use_region_counts && o.hit_list.match_mode != 2)
+    unsupported("region counts with a hit-list match mode other than 2");
+  shrimp_map_params mp = map_params_from_globals();
+  mp.match_mode = o.hit_list.match_mode;
+  mp.use_regions = o.anchor_list.use_region_counts ? 1 : 0;
+  mp.gapless = o.hit_list.gapless ? 1 : 0;
+  mp.window_gen_threshold = o.hit_list.threshold;
+  mp.sw_vect_threshold = o.pass1.threshold;
+  mp.window_overlap = o.pass1.window_overlap;
+  mp.num_tmp_outputs = o.pass1.num_outputs;
+  mp.sw_full_threshold = o.pass2.threshold;
+  mp.strata = o.pass2.strata ? 1 : 0;
+  mp.num_outputs = o.pass2.num_outputs;
+  return mp;
+}
+
+// true: the list is not the single default set gmapper.c builds from the globals (gmapper.c:2601-2632) but one the
+// user gave with --unpaired-options; every set of it must be one stage_params() accepts
+static bool custom_unpaired_options(const read_mapping_options_t *o, int n_options) {
   const bool rc = (match_mode == 2 && use_regions);
-  if (o->regions.recompute != rc || !o->anchor_list.recompute || !o->anchor_list.collapse ||
-      o->anchor_list.use_region_counts != rc || o->anchor_list.use_mp_region_counts != 0 || !o->hit_list.recompute ||
-      o->hit_list.gapless != gapless_sw || o->hit_list.match_mode != match_mode ||
-      o->hit_list.threshold != window_gen_threshold || !o->pass1.recompute || o->pass1.only_paired ||
-      o->pass1.gapless != gapless_sw || o->pass1.min_matches != match_mode || o->pass1.num_outputs != num_tmp_outputs ||
-      o->pass1.threshold != sw_vect_threshold || o->pass1.window_overlap != window_overlap ||
-      o->pass2.strata != strata_flag || o->pass2.num_outputs != num_outputs || o->pass2.threshold != sw_full_threshold ||
-      o->pass2.stop_count != 0)
-    unsupported("a custom --unpaired-options set");
+  if (n_options == 1 && o->regions.recompute == rc && o->anchor_list.recompute && o->anchor_list.collapse &&
+      o->anchor_list.use_region_counts == rc && o->anchor_list.use_mp_region_counts == 0 && o->hit_list.recompute &&
+      o->hit_list.gapless == gapless_sw && o->hit_list.match_mode == match_mode &&
+      o->hit_list.threshold == window_gen_threshold && o->pass1.recompute && !o->pass1.only_paired &&
+      o->pass1.gapless == gapless_sw && o->pass1.min_matches == match_mode && o->pass1.num_outputs == num_tmp_outputs &&
+      o->pass1.threshold == sw_vect_threshold && o->pass1.window_overlap == window_overlap &&
+      o->pass2.strata == strata_flag && o->pass2.num_outputs == num_outputs && o->pass2.threshold == sw_full_threshold &&
+      o->pass2.stop_count == 0)
+    return false;
+  for (int k = 0; k < n_options; k++) {
+    (void)stage_params(o[k], k);
+    if (n_options > 1 && o[k].pass2.save_outputs) unsupported("save_outputs in a multi-stage --unpaired-options list");
+  }
+  return true;
 }
 
 static void check_paired_options(const readpair_mapping_options_t *o, int n_options) {
@@ -436,6 +476,16 @@ struct Batch {
   std::vector<shrimp_pair> pairs;
   std::vector<int32_t> n_pairs;      // per pair
   std::vector<int64_t> first_pair;
+  // the later option sets of a multi-stage --unpaired-options list (mapping.c:1790-1841): the rows whose earlier
+  // sets did not meet their stop condition, mapped again with the next set's parameters
+  struct Stage {
+    std::vector<int32_t> sub_of_row;   // row of the batch -> row of this stage's call, -1 = not mapped in this stage
+    std::vector<shrimp_hit> hits;
+    std::vector<uint8_t> edits;
+    std::vector<int32_t> n_unp;
+    std::vector<int64_t> first_unp;
+  };
+  std::vector<Stage> later;
 };
 static thread_local Batch t_batch;
 static thread_local long long t_drop_snapshot, t_own_drops;
@@ -465,7 +515,82 @@ static void fill_row(Batch &B, int row, const Prep &p) {
   if (B.qstride) memcpy(&B.quals[(size_t)row * B.qstride], p.qual, (size_t)std::min(p.qual_len, B.qstride - 1));
 }
 
-static void run_batch(Batch &B, const std::vector<Prep> &preps) {
+// the option list of the handle_read call that triggered this batch (every call of a run passes the same list)
+static thread_local const read_mapping_options_t *t_stages;   // NULL: the default set, parameters from the globals
+static thread_local int t_n_stages;
+
+// read_pass2's stop condition (mapping.c:1737-1749): `stop_count` alignments at or above the stop threshold
+static bool stage_done(const read_mapping_options_t &o, const shrimp_hit *h, int n) {
+  if (o.pass2.stop_count == 0) return true;
+  int cnt = 0;
+  for (int i = 0; i < n; i++)
+    if (h[i].score_full >= (int)abs_or_pct(o.pass2.stop_threshold, h[i].score_max)) cnt++;
+  return cnt >= o.pass2.stop_count;
+}
+
+static void run_later_stages(Batch &B, int max_len) {
+  const bool cs = shrimp_mode == MODE_COLOUR_SPACE;
+  shrimp_gpu_ctx *ctx = thread_ctx();
+  const int n = B.n_rows;
+  std::vector<char> go((size_t)n, 0);   // rows that move on to the next set
+  for (int r = 0; r < n; r++) go[r] = !stage_done(t_stages[0], &B.hits[(size_t)B.first_unp[r]], B.n_unp[r]);
+  for (int k = 1; k < t_n_stages; k++) {
+    B.later.emplace_back();
+    Batch::Stage &S = B.later.back();
+    S.sub_of_row.assign((size_t)n, -1);
+    int m = 0;
+    for (int r = 0; r < n; r++)
+      if (go[r]) S.sub_of_row[r] = m++;
+    if (m == 0) break;
+    std::vector<uint32_t> reads((size_t)m * B.stride);
+    std::vector<int32_t> rlen((size_t)m), xover((size_t)m * B.xstride);
+    std::vector<int8_t> initbp((size_t)m);
+    std::vector<uint8_t> quals((size_t)m * B.qstride);
+    for (int r = 0; r < n; r++) {
+      const int sub = S.sub_of_row[r];
+      if (sub < 0) continue;
+      memcpy(&reads[(size_t)sub * B.stride], &B.reads[(size_t)r * B.stride], (size_t)B.stride * 4);
+      rlen[sub] = B.rlen[r];
+      initbp[sub] = B.initbp[r];
+      if (B.xstride) memcpy(&xover[(size_t)sub * B.xstride], &B.xover[(size_t)r * B.xstride], (size_t)B.xstride * 4);
+      if (B.qstride) memcpy(&quals[(size_t)sub * B.qstride], &B.quals[(size_t)r * B.qstride], (size_t)B.qstride);
+    }
+    shrimp_map_params mp = stage_params(t_stages[k], k);
+    if (B.xstride) {
+      mp.crossover_scores = xover.data();
+      mp.crossover_stride = B.xstride;
+      mp.read_quals = quals.data();
+      mp.qual_stride = B.qstride;
+    }
+    shrimp_map_stats st;
+    memset(&st, 0, sizeof(st));
+    int64_t n_hits = 0, e_used = 0;
+    S.n_unp.assign((size_t)m, 0);
+    S.hits.resize((size_t)m * std::max(1, mp.num_outputs));
+    size_t e_cap = std::max<size_t>(4096, (size_t)m * 2 * (size_t)max_len);
+    for (;;) {
+      S.edits.resize(e_cap);
+      const int rc = shrimp_gpu_map_reads(ctx, &mp, m, reads.data(), B.stride, rlen.data(), cs ? initbp.data() : nullptr,
+                                          S.hits.data(), (int64_t)S.hits.size(), S.n_unp.data(), S.edits.data(),
+                                          (int64_t)e_cap, &n_hits, &e_used, nullptr, 0, nullptr, &st);
+      if (rc == SHRIMP_E_NOMEM && (size_t)e_used > e_cap) {
+        e_cap = (size_t)e_used + 4096;
+        continue;
+      }
+      if (rc != SHRIMP_OK) die("shrimp_gpu_map_reads (a later option set)");
+      break;
+    }
+    tstats.add(st);
+    S.first_unp.assign((size_t)m + 1, 0);
+    for (int i = 0; i < m; i++) S.first_unp[i + 1] = S.first_unp[i] + S.n_unp[i];
+    for (int r = 0; r < n; r++) {
+      const int sub = S.sub_of_row[r];
+      go[r] = sub >= 0 && !stage_done(t_stages[k], &S.hits[(size_t)S.first_unp[sub]], S.n_unp[sub]);
+    }
+  }
+}
+
+static void run_batch(Batch &B, const std::vector<Prep> &preps, const shrimp_map_params *stage0 = nullptr) {
   const bool cs = shrimp_mode == MODE_COLOUR_SPACE;
   shrimp_gpu_ctx *ctx = thread_ctx();
   const double t0 = omp_get_wtime();
@@ -494,7 +619,8 @@ static void run_batch(Batch &B, const std::vector<Prep> &preps) {
       }
       fill_row(B, B.row_of[i], preps[i]);
     }
-  shrimp_map_params mp = map_params_from_globals();
+  shrimp_map_params mp = stage0 ? *stage0 : (!B.paired && t_stages) ? stage_params(t_stages[0], 0) : map_params_from_globals();
+  B.later.clear();
   if (use_q) {
     mp.crossover_scores = B.xover.data();
     mp.crossover_stride = B.xstride;
@@ -512,7 +638,7 @@ static void run_batch(Batch &B, const std::vector<Prep> &preps) {
   B.n_unp.assign((size_t)std::max(n, 1), 0);
   size_t e_cap = std::max<size_t>(B.edits.size(), std::max<size_t>(4096, (size_t)n * 2 * (size_t)max_len));
   if (!B.paired) {
-    B.hits.resize((size_t)std::max(n, 1) * num_outputs);
+    B.hits.resize((size_t)std::max(n, 1) * std::max(1, mp.num_outputs));
     for (;;) {
       B.edits.resize(e_cap);
       const int rc = shrimp_gpu_map_reads(ctx, &mp, n, B.reads.data(), B.stride, B.rlen.data(),
@@ -528,6 +654,7 @@ static void run_batch(Batch &B, const std::vector<Prep> &preps) {
     }
     B.pairs.clear();
     for (int r = 0; r < n; r++) B.first_unp[r + 1] = B.first_unp[r] + B.n_unp[r];
+    if (t_stages && t_n_stages > 1) run_later_stages(B, max_len);
   } else {
     const int np = n / 2;
     shrimp_pair_params pp = {pair_mode, min_insert_size, max_insert_size, half_paired ? 1 : 0};
@@ -639,7 +766,7 @@ static int ensure_batch(read_entry *re, bool paired) {
 // shrimp_hit -> struct read_hit + struct sw_full_results (what hit_run_full_sw / hit_run_post_sw leave behind,
 // mapping.c:331-402, :1609-1625)
 // ------------------------------------------------------------------------------------------------
-static void build_hit(const Batch &B, const shrimp_hit &h, read_entry *re, read_hit *rh) {
+static void build_hit(const std::vector<uint8_t> &edits, const shrimp_hit &h, read_entry *re, read_hit *rh) {
   const bool cs = shrimp_mode == MODE_COLOUR_SPACE;
   memset(rh, 0, sizeof(*rh));
   struct sw_full_results *s = (struct sw_full_results *)my_calloc(sizeof(*s), &mem_mapping, "sfrp [%s]", re->name);
@@ -676,7 +803,7 @@ static void build_hit(const Batch &B, const shrimp_hit &h, read_entry *re, read_
     s->pct_posterior_score = (1000 * 100 * h.score_full) / h.score_max;
   }
   // dbalign / qralign (shim_align.h), on the genome strand and the read strand the alignment ran on
-  const uint8_t *ed = &B.edits[(size_t)h.edit_off];
+  const uint8_t *ed = &edits[(size_t)h.edit_off];
   const int n = h.edit_len;
   char *db = (char *)xmalloc((size_t)n + 1), *qr = (char *)xmalloc((size_t)n + 1);
   const uint32_t *gen = h.gen_st == 0 ? genome_contigs[h.cn] : genome_contigs_rc[h.cn];
@@ -698,13 +825,11 @@ static void free_hits(read_entry *re, read_hit *rh, int n) {
 
 // the unpaired records of row `row` -> read_output now (save_outputs false) or re->final_unpaired_hits
 // (read_save_final_hits, mapping.c:1754-1770)
-static void emit_unpaired(const Batch &B, int row, read_entry *re, bool save_outputs) {
-  const int n = B.n_unp[row];
+static void emit_records(const shrimp_hit *h, int n, const std::vector<uint8_t> &edits, read_entry *re, bool save_outputs) {
   if (n <= 0) return;
-  const shrimp_hit *h = &B.hits[(size_t)B.first_unp[row]];
   read_hit *rh = (read_hit *)my_malloc((size_t)n * sizeof(read_hit), &mem_mapping, "final_unpaired_hits [%s]", re->name);
   const double t0 = omp_get_wtime();
-  for (int i = 0; i < n; i++) build_hit(B, h[i], re, &rh[i]);
+  for (int i = 0; i < n; i++) build_hit(edits, h[i], re, &rh[i]);
   tstats.t_build += omp_get_wtime() - t0;
   tstats.records += (uint64_t)n;
   re->final_matches += n;
@@ -727,6 +852,18 @@ static void emit_unpaired(const Batch &B, int row, read_entry *re, bool save_out
   re->mapped = true;
 }
 
+static void emit_unpaired(const Batch &B, int row, read_entry *re, bool save_outputs) {
+  const int n = B.n_unp[row];
+  if (n > 0) emit_records(&B.hits[(size_t)B.first_unp[row]], n, B.edits, re, save_outputs);
+  // the later option sets this read went through, in their order (every set that finds alignments prints them,
+  // mapping.c:1824-1833)
+  for (const Batch::Stage &S : B.later) {
+    const int sub = S.sub_of_row[row];
+    if (sub < 0) break;
+    if (S.n_unp[sub] > 0) emit_records(&S.hits[(size_t)S.first_unp[sub]], S.n_unp[sub], S.edits, re, save_outputs);
+  }
+}
+
 }  // namespace shrimp_shim
 
 using namespace shrimp_shim;
@@ -738,7 +875,14 @@ using namespace shrimp_shim;
 void handle_read(struct read_entry *re, struct read_mapping_options_t *options, int n_options) {   // mapping.c:1773
   const llint before = gettimeinusecs();
   if (pair_mode != PAIR_NONE) unsupported("handle_read outside handle_readpair in paired mode");
-  check_unpaired_options(options, n_options);
+  static thread_local const read_mapping_options_t *checked;
+  static thread_local bool checked_custom;
+  if (checked != options) {   // once per thread: the list is the same for every read of a run
+    checked_custom = custom_unpaired_options(options, n_options);
+    checked = options;
+  }
+  t_stages = checked_custom ? options : nullptr;
+  t_n_stages = n_options;
   const int i = ensure_batch(re, false);
   Batch &B = t_batch;
   emit_unpaired(B, B.row_of[i], re, options[0].pass2.save_outputs);
@@ -794,7 +938,7 @@ void handle_readpair(pair_entry *pe, struct readpair_mapping_options_t *options,
           q = (int)slot_of[nip].size();
           slot_of[nip].push_back(h.hit_slot);
           pool[nip].emplace_back();
-          build_hit(B, h, pe->re[nip], &pool[nip].back());
+          build_hit(B.edits, h, pe->re[nip], &pool[nip].back());
           idx[nip].emplace_back();
         }
         idx[nip][q].push_back(p);

@@ -78,6 +78,34 @@ def test_output_options_c1(extra, tmp_path):
     assert_same_sam(ref, new)
 
 
+STAGE_LISTS = {
+    # a strict first set that stops at one alignment of 95 % of the maximum score, then a one-seed-match set with
+    # lower thresholds for the reads that are left (every set that finds alignments prints them, mapping.c:1824-1833)
+    "two_sets": ["--unpaired-options", "0;1/1,1,1/1,0,2,55%/1,60%,90%,2,0,30/68%,0,0,10/1,95%",
+                 "--unpaired-options", "0;0/1,1,0/1,0,1,55%/1,50%,90%,1,0,30/55%,0,0,10/0"],
+    "three_sets": ["--unpaired-options", "0;1/1,1,1/1,0,2,60%/1,70%,90%,2,0,20/75%,1,0,5/2,90%",
+                   "--unpaired-options", "0;1/1,1,1/1,0,2,55%/1,60%,80%,2,0,30/65%,0,0,10/1,80%",
+                   "--unpaired-options", "0;0/1,1,0/1,0,1,50%/1,45%,90%,1,0,30/50%,0,0,10/0"],
+    # one user-given set that is not the default one
+    "one_custom_set": ["--unpaired-options", "0;0/1,1,0/1,0,1,50%/1,55%,80%,1,0,25/60%,1,0,4/0"],
+}
+
+
+@needs_bins
+@pytest.mark.gpu
+@pytest.mark.parametrize("which", sorted(STAGE_LISTS))
+@pytest.mark.parametrize("name", ["c1_small", "c2_small_mq"])
+def test_unpaired_option_lists(name, which, tmp_path):
+    """--unpaired-options (gmapper.c:2199-2218, handle_read's loop over the option sets mapping.c:1790-1841)"""
+    case = LsCase(name)
+    case.write_fasta(str(tmp_path))
+    args = [*STAGE_LISTS[which], "reads.fa", "genome.fa"]
+    ref, _ = run_sam(REF, case.binary, args, str(tmp_path), 4)
+    new, _ = run_sam(NEW, case.binary, args, str(tmp_path), 2, ["-K", "700"])
+    assert_same_sam(ref, new)
+    assert sum(1 for ln in new if ln and not ln.startswith(b"@")) > 100
+
+
 @needs_bins
 @pytest.mark.gpu
 @pytest.mark.parametrize("mode", ["opp-out", "col-fw", "col-bw"])
