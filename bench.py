@@ -579,23 +579,24 @@ def measure(a, w, n_reads, rank, world, local_rank, ncores, compact=False):
     post_ms = stage.get("post_sw", (0.0, 0))[0] / a.steps
     if post_ms > 0:
         # post_sw: per aligned column 16 nodes x (3 exp + 2 log: forward, backward, posterior), 11 / 20 FP64
-        # instructions each in the libm transcription (glibc_math.cuh); against the nominal FP64 issue rate (64 lanes
-        # per clock and SM at the measured SM clock -- MEASURED_PEAKS.json has no FP64 figure)
+        # instructions each in the libm transcription (glibc_math.cuh) -- round 1's count, kept so that the fractions
+        # of the rounds compare (the quad kernel of round 2 evaluates 48 exp + 8 log per column, the half-warp kernel
+        # evaluated 48 + 32); against the FP64 issue rate measured live (shrimp_gpu_fp64_peak)
         fp64_instr = st["post_sw_columns"] * 16.0 * (3 * 11 + 2 * 20)
         fp64_peak = fp64_peak_live
-        roofs["post_sw"] = {"kernel": "post_sw_kernel", "bound": "fp64", "achieved": fp64_instr / (post_ms * 1e-3) / 1e9,
+        roofs["post_sw"] = {"kernel": "post_sw_quad_kernel", "bound": "fp64", "achieved": fp64_instr / (post_ms * 1e-3) / 1e9,
                             "peak": fp64_peak, "unit": "G FP64 instr/s",
                             "frac": fp64_instr / (post_ms * 1e-3) / 1e9 / fp64_peak, "traffic": None,
                             "columns_per_s": st["post_sw_columns"] / (post_ms * 1e-3), "ms_per_step": post_ms,
                             "peak_source": "measured live: register-resident DFMA chains (shrimp_gpu_fp64_peak)"}
     # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture per launch; only for the
-    # configuration the capture was taken on (profiles/r01h_ncu_full_scan_kernel_raw.csv, r01f_ncu_full_post_sw_raw.csv: C2, 1 M reads per launch)
+    # configuration the capture was taken on (profiles/r02b_ncu_full_scan_kernel_raw.csv, r02b_ncu_full_post_sw_quad_raw.csv: C2, 1 M reads per launch)
     if w.key in ("c2", "c2nomq") and n_reads == 1_000_000:
-        roofs["seed_scan"]["traffic"] = 28.42e9
-        roofs["seed_scan"]["traffic_source"] = "profiles/r01h_ncu_full_scan_kernel_raw.csv"
+        roofs["seed_scan"]["traffic"] = 14.26e9
+        roofs["seed_scan"]["traffic_source"] = "profiles/r02b_ncu_full_scan_kernel_raw.csv"
         if "post_sw" in roofs:
-            roofs["post_sw"]["traffic"] = 4.08e9
-            roofs["post_sw"]["traffic_source"] = "profiles/r01f_ncu_full_post_sw_raw.csv"
+            roofs["post_sw"]["traffic"] = 9.15e9
+            roofs["post_sw"]["traffic_source"] = "profiles/r02b_ncu_full_post_sw_quad_raw.csv"
     roofline = dict(roofs.get(dominant, roofs["seed_scan"]))
     roofline["dominant_stage"] = dominant
     roofline["other"] = {k: v for k, v in roofs.items() if k != dominant}

@@ -308,8 +308,8 @@ static shrimp_map_params stage_params(const read_mapping_options_t &o, int k) {
   if (o.anchor_list.use_region_counts && !o.regions.recompute && k == 0)
     unsupported("an --unpaired-options set that uses region counts it does not compute");
   if (!o.anchor_list.collapse) unsupported("an --unpaired-options set without anchor collapsing");
-  if (o.anchor_list.use_mp_region_counts != 0 || o.pass1.only_paired)
-    unsupported("mate-pair options in an --unpaired-options set");
+  // (anchor_list.use_mp_region_counts and pass1.only_paired are not parsed for an unpaired set, gmapper.c:1651-1654,
+  // :1686-1689: the reference leaves them as the allocator gave them, and they mean nothing for a read without a mate)
   if (o.hit_list.match_mode != 1 && o.hit_list.match_mode != 2) unsupported("an unpaired hit-list match mode other than 1 or 2");
   if (o.pass1.min_matches != o.hit_list.match_mode)
     unsupported("an --unpaired-options set whose pass-1 min_matches differs from its hit-list match mode");
