@@ -22,7 +22,11 @@ import tempfile
 import threading
 import time
 
-import numpy as np
+# the host stages of a step (OpenMP inside the library) share a rank's few cores with the other contexts of the rank:
+# idle OpenMP workers must sleep, not spin (libgomp reads this when it is loaded, i.e. before torch is imported)
+os.environ.setdefault("OMP_WAIT_POLICY", "passive")
+
+import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -430,7 +434,7 @@ def measure(a, w, n_reads, rank, world, local_rank, ncores, compact=False):
     ctx, scores, seeds, index_s = build_context(w, local_rank)
     # torchrun exports OMP_NUM_THREADS=1: give every rank its share of the host cores for the host stages
     from shrimp_b200.api import set_host_threads
-    set_host_threads(max(1, ncores // max(1, world)))
+    set_host_threads(a.host_threads or max(1, ncores // max(1, world)))
     params = w.map_params()
 
     def map_host():
@@ -729,6 +733,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-workloads-block", action="store_true",
                     help="skip the compact C1 / C3 / C4 / C5 legs the default C2 run appends")
+    ap.add_argument("--host-threads", type=int, default=0, help="OpenMP threads of the library's host stages per call "
+                    "(0 = the rank's share of the host cores)")
     ap.add_argument("--e2e-threads", type=int, default=0,
                     help="host threads (one context each) of the end-to-end leg; 0 = 4 on one GPU, 3 per GPU on several")
     a = ap.parse_args()
