@@ -13,6 +13,13 @@ namespace shrimp {
 
 void set_error(const char *fmt, ...);
 
+// Every wait of a host thread for its stream goes through here: SHRIMP_BLOCKING_SYNC=1 makes it block on an event
+// instead of spinning (for hosts that need the core; see ctx.cu for what was measured).
+cudaError_t sync_stream(cudaStream_t s);
+#ifndef SHRIMP_NO_SYNC_WRAP
+#define cudaStreamSynchronize(s) shrimp::sync_stream(s)
+#endif
+
 #define SH_CUDA(call)                                                                   \
   do {                                                                                  \
     cudaError_t _e = (call);                                                            \

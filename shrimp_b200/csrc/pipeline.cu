@@ -1189,6 +1189,9 @@ int chunk_run_full(Chunk &C, int n_slots) {
     PS.max_rlen = C.max_rl;
     PS.n_tasks = n_slots;
     PS.columns = (unsigned long long *)(C.cnt + 46);
+    PS.score_alpha = alpha;
+    PS.score_2ab = 2.0 * alpha + beta;
+    PS.log2v = log(2.0);
     PS.la1 = log(1 - pr_snp);
     PS.la2 = log(pr_snp / 3.0);
     PS.lc1 = log(1 - pr_xover);
@@ -1363,14 +1366,17 @@ void host_score_hit(const Chunk &C, int idx, HostHit &h) {
   h.score_full = h.res.score;
   h.pct_score_full = (1000 * 100 * h.score_full) / h.info.score_max;
   if (mp->compute_mapping_qualities && h.score_full > 0) {
-    if (C.cs)   // post_sw ran on the device
+    int ps;
+    if (C.cs) {   // post_sw ran on the device; it also took the logarithm of the score below (FullResult::post_score)
       h.posterior = h.res.posterior;
-    else
+      ps = h.res.post_score;
+    } else {
       h.posterior = pow(2.0, ((double)h.res.score - (double)h.res.rmapped * (2.0 * mp->score_alpha + mp->score_beta)) /
                                  mp->score_alpha);
-    int ps = (int)rint(mp->score_alpha * log(h.posterior) / log(2.0) +
-                       (double)h.res.rmapped * (2.0 * mp->score_alpha + mp->score_beta));
-    if (ps < 0) ps = 0;
+      ps = (int)rint(mp->score_alpha * log(h.posterior) / log(2.0) +
+                     (double)h.res.rmapped * (2.0 * mp->score_alpha + mp->score_beta));
+      if (ps < 0) ps = 0;
+    }
     const int pct = (1000 * 100 * ps) / h.info.score_max;
     h.score_full = ps;
     h.pct_score_full = pct;

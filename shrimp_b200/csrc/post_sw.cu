@@ -391,6 +391,12 @@ __global__ void __launch_bounds__(128, PS_CTAS_PER_SM) post_sw_kernel(const Post
       R.mismatches = mismatches;
       R.crossovers = crossovers;
       R.posterior = res;
+      {   // mapping.c:1619-1621 (-fmad=false: the host's operations in the host's order)
+        const double ps = P.score_alpha * PS_LOG(res) / P.log2v + (double)R.rmapped * P.score_2ab;
+        int v = (int)rint(ps);
+        R.post_score = v < 0 ? 0 : v;
+        R.pad_ = 0;
+      }
       P.results[slot] = R;
     }
   }
@@ -743,6 +749,12 @@ __global__ void __launch_bounds__(128, MINB) post_sw_quad_kernel(const PostParam
       R.mismatches = mismatches;
       R.crossovers = crossovers;
       R.posterior = res;
+      {   // mapping.c:1619-1621 (-fmad=false: the host's operations in the host's order)
+        const double ps = P.score_alpha * PS_LOG(res) / P.log2v + (double)R.rmapped * P.score_2ab;
+        int v = (int)rint(ps);
+        R.post_score = v < 0 ? 0 : v;
+        R.pad_ = 0;
+      }
       P.results[slot] = R;
     }
   }

@@ -145,6 +145,9 @@ struct FullResult {
   int32_t matches, mismatches, insertions, deletions, crossovers;
   int32_t ops_start, ops_len;   // into this task's ops column
   double posterior;             // colour space with mapping qualities: sfrp->posterior of post_sw (post_sw.cu)
+  // ... and the score hit_run_post_sw derives from it, (int)rint(alpha log2(posterior) + rmapped (2 alpha + beta))
+  // (mapping.c:1619-1621), taken on the device with the same libm logarithm: one log() per alignment less on the host
+  int32_t post_score, pad_;
 };
 
 struct FullParams {
@@ -197,6 +200,7 @@ struct PostParams {
   double lc1, lc2;         // reads without qualities: log(1 - pr_xover), log(pr_xover / 3)
   double ln1, ln2;         // colour N: rate .75
   double pr_del_open, pr_del_extend, pr_ins_open, pr_ins_extend;
+  double score_alpha, score_2ab, log2v;   // alpha, 2 alpha + beta, the host's log(2.0)
 };
 
 }  // namespace shrimp
