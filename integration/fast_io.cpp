@@ -40,6 +40,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <zlib.h>
+#include <emmintrin.h>
 
 #include "gmapper/gmapper.h"
 #include "gmapper/output.h"
@@ -81,7 +82,7 @@ Reader *reader_of(fasta_t f) {
       Reader *r = &g_readers[i];
       r->owner = f;
       r->cap = (size_t)16 << 20;
-      r->buf = (char *)xmalloc(r->cap);
+      r->buf = (char *)xmalloc(r->cap + 64);   // 16-byte loads of scan_line may start at the last byte
       r->pos = r->end = 0;
       r->eof = false;
       r->header = f->header;
@@ -429,16 +430,47 @@ bool fasta_get_next_read_with_range(fasta_t fasta, read_entry *re) {   // fasta.
 // of the right length), the next entry's marker behind it, all inside the current block, no NUL bytes -- is taken
 // apart in place with memchr; anything else returns false without having consumed a byte and next_read's general
 // path (the restatement of fasta.c:316-545 piece by piece) takes the entry.
+// One SSE2 pass over a line: where it ends, and whether a NUL, a tab or a uracil lies before its end; the first blank.
+// (16-byte loads may run past `end` into the slack behind the block; a newline found there does not count.)
+enum { LN_NUL = 1, LN_TAB = 2, LN_U = 4 };
+static inline char *scan_line(char *p, char *end, unsigned *flags, char **first_blank) {
+  const __m128i vnl = _mm_set1_epi8('\n'), vz = _mm_setzero_si128(), vtab = _mm_set1_epi8('\t'), vsp = _mm_set1_epi8(' '),
+                vu = _mm_set1_epi8('u'), v20 = _mm_set1_epi8(0x20);
+  unsigned fl = 0;
+  char *fb = NULL;
+  for (; p < end; p += 16) {
+    const __m128i v = _mm_loadu_si128((const __m128i *)p);
+    const unsigned mnl = (unsigned)_mm_movemask_epi8(_mm_cmpeq_epi8(v, vnl));
+    const unsigned before = mnl ? ((mnl & (0u - mnl)) - 1u) : 0xffffu;   // the bytes in front of the first newline
+    const unsigned mz = (unsigned)_mm_movemask_epi8(_mm_cmpeq_epi8(v, vz)) & before;
+    const unsigned mt = (unsigned)_mm_movemask_epi8(_mm_cmpeq_epi8(v, vtab)) & before;
+    const unsigned ms = (unsigned)_mm_movemask_epi8(_mm_cmpeq_epi8(v, vsp)) & before;
+    const unsigned mu = (unsigned)_mm_movemask_epi8(_mm_cmpeq_epi8(_mm_or_si128(v, v20), vu)) & before;
+    fl |= (mz ? LN_NUL : 0) | (mt ? LN_TAB : 0) | (mu ? LN_U : 0);
+    if (ms && !fb) fb = p + __builtin_ctz(ms);
+    if (mnl) {
+      char *at = p + __builtin_ctz(mnl);
+      if (at >= end) return NULL;
+      *flags = fl;
+      *first_blank = fb;
+      return at;
+    }
+  }
+  return NULL;
+}
+
 static bool next_read_fast(Reader *r, fasta_t fasta, Views *V, char c) {
   if (r->header) return false;
   char *s = r->buf + r->pos, *const end = r->buf + r->end;
   if (s >= end || *s != c) return false;
-  char *e = (char *)memchr(s, '\n', (size_t)(end - s));
-  if (!e) return false;
+  unsigned nfl = 0, sfl = 0, xfl = 0;
+  char *nblank = NULL, *xblank = NULL;
+  char *e = scan_line(s, end, &nfl, &nblank);
+  if (!e || (nfl & (LN_NUL | LN_TAB))) return false;
   char *q = e + 1;                                  // the sequence line
   if (q >= end || *q == '#' || *q == '>' || *q == '+') return false;
-  char *qe = (char *)memchr(q, '\n', (size_t)(end - q));
-  if (!qe || qe == q) return false;
+  char *qe = scan_line(q, end, &sfl, &xblank);
+  if (!qe || qe == q || (sfl & LN_NUL)) return false;   // (a NUL ends the reference's copy: general path)
   char *nx = qe + 1;                                // what follows the sequence line
   char *plus = NULL, *pe = NULL, *ql = NULL, *qle = NULL;
   if (!fasta->fastq) {
@@ -446,12 +478,12 @@ static bool next_read_fast(Reader *r, fasta_t fasta, Views *V, char c) {
   } else {
     if (nx >= end || *nx != '+') return false;
     plus = nx;
-    pe = (char *)memchr(plus, '\n', (size_t)(end - plus));
-    if (!pe) return false;
+    pe = scan_line(plus, end, &xfl, &xblank);
+    if (!pe || (xfl & LN_NUL)) return false;
     ql = pe + 1;
     if (ql >= end) return false;
-    qle = (char *)memchr(ql, '\n', (size_t)(end - ql));
-    if (!qle) return false;
+    qle = scan_line(ql, end, &xfl, &xblank);
+    if (!qle || (xfl & LN_NUL)) return false;
     const size_t want = fasta->space == LETTER_SPACE ? (size_t)(qe - q) : (size_t)(qe - q) - 1;
     if ((size_t)(qle - ql) != want || want == 0) return false;
     nx = qle + 1;
@@ -461,28 +493,12 @@ static bool next_read_fast(Reader *r, fasta_t fasta, Views *V, char c) {
   while (b < t && isspace((unsigned char)*b)) b++;
   while (t > b && isspace((unsigned char)t[-1])) t--;
   if (b == t) return false;
-  // one table look-up per byte: tabs and NULs send the entry to the general path, the first blank cuts the name,
-  // uracil marks RNA (fasta.c:524-538)
-  static const struct Classes {
-    unsigned char t[256];
-    Classes() {
-      memset(t, 0, sizeof(t));
-      t[0] = 1; t[(int)'\t'] = 2; t[(int)' '] = 4;
-      t[(int)'U'] = t[(int)'u'] = 8; t[(int)'T'] = t[(int)'t'] = 16;
-    }
-  } K;
-  unsigned ncls = 0;
-  for (const char *p = b; p < t; p++) ncls |= K.t[(unsigned char)*p];
-  for (const char *p = s + 1; p < b; p++) ncls |= K.t[(unsigned char)*p] & 3;
-  for (const char *p = t; p < e; p++) ncls |= K.t[(unsigned char)*p] & 3;
-  if (ncls & 3) return false;
-  char *cut = (ncls & 4) ? (char *)memchr(b, ' ', (size_t)(t - b)) : NULL;
+  char *cut = nblank;
+  if (cut && cut < b) cut = (char *)memchr(b, ' ', (size_t)(t - b));   // (blanks in front of the name)
   const size_t seq_len = (size_t)(qe - q);
-  unsigned scls = 0;
-  for (size_t i = 0; i < seq_len; i++) scls |= K.t[(unsigned char)q[i]];
-  const unsigned nul = scls & 1, ur = scls & 8, th = scls & 16;
-  if (nul) return false;
-  if (fasta->fastq && (memchr(plus, 0, (size_t)(pe - plus)) || memchr(ql, 0, (size_t)(qle - ql)))) return false;
+  // uracil without thymine marks RNA (fasta.c:524-538)
+  const bool ur = (sfl & LN_U) != 0;
+  const bool th = ur && (memchr(q, 'T', seq_len) || memchr(q, 't', seq_len));
   V->name = b;
   V->name_len = (size_t)((cut && cut < t ? cut : t) - b);
   V->seq = q;
