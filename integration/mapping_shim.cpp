@@ -28,8 +28,11 @@
 #include <string>
 #include <vector>
 
+#include <execinfo.h>
 #include <malloc.h>
 #include <math.h>
+#include <signal.h>
+#include <unistd.h>
 #include <omp.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -79,7 +82,15 @@ static void init_thread_ctx() {
 // gmapper.c allocates a 10 MB output buffer per chunk and grows it in 10 MB steps (gmapper.c:403, output.c:246-268):
 // at GPU rates that is an mmap / page-fault / munmap cycle of tens of megabytes per thread every few milliseconds, all
 // of them serialised on the process's address-space lock.  Keep such blocks on the heap and never trim it.
+static void segv_backtrace(int sig) {   // SHRIMP_B200_BACKTRACE=1: where a crash happened (no debugger on the GPU boxes)
+  void *frames[64];
+  const int n = backtrace(frames, 64);
+  backtrace_symbols_fd(frames, n, 2);
+  signal(sig, SIG_DFL);
+  raise(sig);
+}
 static bool tune_malloc() {
+  if (getenv("SHRIMP_B200_BACKTRACE")) signal(SIGSEGV, segv_backtrace);
   if (!getenv("SHRIMP_B200_NO_MALLOPT")) {
     mallopt(M_MMAP_THRESHOLD, 32 << 20);   // the largest value glibc accepts
     mallopt(M_TRIM_THRESHOLD, -1);
@@ -687,14 +698,27 @@ static void run_batch(Batch &B, const std::vector<Prep> &preps, const shrimp_map
 }
 
 // entries [re, re + ahead) of the chunk that are loaded; `step` entries per unit (2 in paired mode)
+//
+// The look-ahead must not run past re_buffer[], whose bounds the shim is not told.  What it knows: a thread's
+// re_buffer is ONE allocation of chunk_size entries for the whole run, zeroed before every fill (gmapper.c:325-332),
+// and handle_read is called for its entries in ascending order, skipping the ones the loop dropped -- each of which is
+// counted in total_reads_dropped / total_pairs_dropped (gmapper.c:510-527).  So, with D the drops counted since this
+// thread's previous call, `re - D * step` is at or below the first entry of the buffer whenever `re` is the first
+// surviving entry of a chunk (drops by other threads only lower it), and the buffer's end is at least
+// `re - D * step + chunk_size` there: the MINIMUM of that expression over all calls is a safe end (a call in the
+// middle of a chunk gives a larger value and is ignored by the minimum).  One past the highest entry ever seen is
+// a lower bound of the end as well, and it becomes exact once a full chunk has gone by.  (Until round 2 the bound
+// was taken from the current call alone: a batch that had been cut short by another thread's drops was followed by
+// a look-ahead from the middle of the chunk that ran past the buffer.)
+static thread_local const read_entry *t_end_min, *t_end_low;
 static int lookahead_limit(const read_entry *re, int step) {
-  // re_buffer[] has chunk_size entries and was zeroed before it was filled (gmapper.c:329-332); `re` is not entry 0
-  // only if the loop dropped what came before it, and every drop is counted in total_reads_dropped /
-  // total_pairs_dropped (gmapper.c:510-527) -- so chunk_size minus the drops since this thread's last call can never
-  // run past the end of the buffer (drops by other threads only make the bound smaller)
   long long drops = (total_reads_dropped + total_pairs_dropped) - t_own_drops - t_drop_snapshot;
   if (drops < 0) drops = 0;
-  long long limit = (long long)chunk_size - drops * step;
+  const read_entry *cand = re + (long long)chunk_size - drops * step;
+  if (!t_end_min || cand < t_end_min) t_end_min = cand;
+  if (!t_end_low || re + step > t_end_low) t_end_low = re + step;
+  const read_entry *end = t_end_min > t_end_low ? t_end_min : t_end_low;
+  long long limit = end - re;
   if (const char *e = getenv("SHRIMP_B200_BATCH")) limit = std::min<long long>(limit, std::max(step, atoi(e)));
   if (limit < step) limit = step;
   int n = step;
