@@ -27,6 +27,7 @@
  * Everything that decides a byte of the record (flag bits, POS of a reverse-strand hit, CIGAR runs, the IUPAC
  * rule of the SEQ column, Z0..Z6 through the same libm `log`) follows output.c line by line, cited below.
  */
+#include <algorithm>
 #include <atomic>
 #include <thread>
 #include <vector>
@@ -82,6 +83,7 @@ Reader *reader_of(fasta_t f) {
       Reader *r = &g_readers[i];
       r->owner = f;
       r->cap = (size_t)16 << 20;
+      if (const char *e = getenv("SHRIMP_B200_READER_BLOCK")) r->cap = (size_t)std::max(256L, atol(e));   // (tests: entries across block ends)
       r->buf = (char *)xmalloc(r->cap + 64);   // 16-byte loads of scan_line may start at the last byte
       r->pos = r->end = 0;
       r->eof = false;

@@ -249,6 +249,30 @@ def test_malformed_input_same_outcome(kind, tmp_path):
     same(ref, new)
 
 
+@pytest.mark.parametrize("block", ["300", "4096", "70000"])
+@pytest.mark.parametrize("ahead", ["0", "1"])
+def test_entries_across_block_ends(block, ahead, tmp_path, monkeypatch):
+    """the reader's block made so small that most entries (300 bytes: every one) straddle a block end: the in-place
+    path hands those to the piece-wise path, which carries the tail over; FASTQ and folded FASTA"""
+    monkeypatch.setenv("SHRIMP_B200_READER_BLOCK", block)
+    monkeypatch.setenv("SHRIMP_B200_READ_AHEAD_AFTER", "50" if ahead == "1" else "1000000000")
+    case = LsCase("c1_small")
+    case.write_fasta(str(tmp_path))
+    rng = np.random.default_rng(21)
+    recs = _letter_fastq(case, rng, 500)
+    with open(os.path.join(str(tmp_path), "b.fq"), "wb") as f:
+        for name, s, q in recs:
+            f.write(b"@" + name + b"\n" + s + b"\n+\n" + q + b"\n")
+    with open(os.path.join(str(tmp_path), "b.fa"), "wb") as f:
+        for k, (name, s, _) in enumerate(recs):
+            f.write(b">" + name + b"\n" + (b"\n".join(s[i:i + 40] for i in range(0, len(s), 40)) if k % 3 == 0 else s) + b"\n")
+    for args in (["-Q", "--qv-offset", "33", "b.fq", "genome.fa"], ["b.fa", "genome.fa"]):
+        ref, _, _ = run(REF, "gmapper-ls", args, str(tmp_path))
+        new, _, _ = run(NEW, "gmapper-ls", args, str(tmp_path), 3)
+        same(ref, new)
+        assert sum(1 for ln in new if ln and not ln.startswith(b"@")) > 300
+
+
 def test_without_read_ahead(tmp_path, monkeypatch):
     """the reader called in place (no read-ahead thread), chunks of 100 reads"""
     monkeypatch.setenv("SHRIMP_B200_READ_AHEAD_AFTER", "1000000000")

@@ -78,6 +78,28 @@ def test_output_options_c1(extra, tmp_path):
     assert_same_sam(ref, new)
 
 
+@needs_bins
+@pytest.mark.gpu
+def test_lookahead_with_dropped_reads_and_many_threads(tmp_path):
+    """one read in seven is dropped by the loop of gmapper.c (too long / low average quality) while four threads take
+    chunks of 100: another thread's drops cut a look-ahead batch short, and the next batch starts in the middle of the
+    chunk -- its look-ahead must stop at the end of re_buffer[] (it ran past it until round 2: a crash in one run of
+    five).  Five runs, all equal to the reference."""
+    import numpy as np
+    case = LsCase("c1_small")
+    case.write_fasta(str(tmp_path))
+    rng = np.random.default_rng(77)
+    reads = _mixed_reads(case, rng, 900, 22, 400, 0.01, False)
+    with open(os.path.join(str(tmp_path), "mixed.fq"), "wb") as f:
+        for name, s, q in reads:
+            f.write(b"@" + name.encode() + b"\n" + s + b"\n+\n" + q + b"\n")
+    args = ["-Q", "--qv-offset", "33", "--longest-read", "380", "mixed.fq", "genome.fa"]
+    ref, _ = run_sam(REF, case.binary, args, str(tmp_path), 4)
+    for threads, chunk in ((4, "100"), (2, "250"), (4, "100"), (3, "64"), (2, "250")):
+        new, _ = run_sam(NEW, case.binary, args, str(tmp_path), threads, ["-K", chunk])
+        assert_same_sam(ref, new)
+
+
 STAGE_LISTS = {
     # a strict first set that stops at one alignment of 95 % of the maximum score, then a one-seed-match set with
     # lower thresholds for the reads that are left (every set that finds alignments prints them, mapping.c:1824-1833)
