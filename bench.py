@@ -24,7 +24,18 @@ import time
 
 # the host stages of a step (OpenMP inside the library) share a rank's few cores with the other contexts of the rank:
 # idle OpenMP workers must sleep, not spin (libgomp reads this when it is loaded, i.e. before torch is imported)
+_USER_WAIT_POLICY = os.environ.get("OMP_WAIT_POLICY")
 os.environ.setdefault("OMP_WAIT_POLICY", "passive")
+
+
+def child_env():
+    """environment of the gmapper binaries this script starts (the reference and the drop-in): the caller's own, without
+    the wait policy set above for this process"""
+    env = dict(os.environ)
+    if _USER_WAIT_POLICY is None:
+        env.pop("OMP_WAIT_POLICY", None)
+    return env
+
 
 import numpy as np  # noqa: E402
 
@@ -337,7 +348,7 @@ def run_reference(w: Workload, workdir: str, n_threads: int, reads_fa: str, pref
     rd = ["-1", reads_fa + ".1", "-2", reads_fa + ".2"] if w.paired else [reads_fa]
     cmd = [os.path.join(REF_DIR, w.binary), "-N", str(n_threads), *w.load_args(), "-L", prefix, *rd]
     t0 = time.time()
-    r = subprocess.run(cmd, cwd=workdir, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
+    r = subprocess.run(cmd, cwd=workdir, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, env=child_env())
     wall = time.time() - t0
     if r.returncode != 0:
         raise RuntimeError("reference gmapper failed: " + r.stderr[-500:])
@@ -362,7 +373,7 @@ def reference_setup(w: Workload, workdir: str, reads_codes, ctx=None):
         return "projection saved from HBM in the -S format"
     w.write_genome_fasta(os.path.join(workdir, "genome.fa"))
     r = subprocess.run([os.path.join(REF_DIR, w.binary), *(w.args if w.paired else []), "-S", "proj", "genome.fa"], cwd=workdir,
-                       stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
+                       stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, env=child_env())
     if r.returncode != 0:
         raise RuntimeError("reference gmapper -S failed: " + r.stderr[-500:])
     return "projection built by gmapper -S"
@@ -680,7 +691,7 @@ def measure(a, w, n_reads, rank, world, local_rank, ncores, compact=False):
         runs = []
         for _ in range(2):
             r = subprocess.run([dropin, "-N", str(th), "-K", str(ck), *w.load_args(), "-L", "proj", *rd], cwd=d,
-                               stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
+                               stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, env=child_env())
             m = re.search(r"Read Mapping Time:\s+([0-9.]+) seconds", r.stderr)
             if r.returncode != 0 or not m or float(m.group(1)) <= 0:
                 break
@@ -781,7 +792,7 @@ def main():
         if not os.path.exists(os.path.join(cache, "proj.genome")):
             w.write_genome_fasta(os.path.join(cache, "genome.fa"))
             r = subprocess.run([ref_bin, *[x for x in w.args if x in ("-s", "w11", "-M", "mirna")], "-S", "proj.tmp",
-                                "genome.fa"], cwd=cache, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
+                                "genome.fa"], cwd=cache, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, env=child_env())
             if r.returncode != 0:
                 raise RuntimeError("reference gmapper -S failed: " + r.stderr[-500:])
             for f in sorted(os.listdir(cache)):
