@@ -688,16 +688,27 @@ def measure(a, w, n_reads, rank, world, local_rank, ncores, compact=False):
         rd = ["-1", "big.fa.1", "-2", "big.fa.2"] if w.paired else ["big.fa"]
         # two runs, the faster one counts, both are reported: the binary's time is host-bound (sixteen threads on
         # sixteen cores, a serial reader) and moves by +-25 % from run to run on the same box
-        runs = []
+        runs, detail = [], []
         for _ in range(2):
             r = subprocess.run([dropin, "-N", str(th), "-K", str(ck), *w.load_args(), "-L", "proj", *rd], cwd=d,
-                               stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, env=child_env())
+                               stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True,
+                               env=dict(child_env(), SHRIMP_B200_VERBOSE="1"))
             m = re.search(r"Read Mapping Time:\s+([0-9.]+) seconds", r.stderr)
             if r.returncode != 0 or not m or float(m.group(1)) <= 0:
                 break
             runs.append(n_sam / float(m.group(1)))
+            # where the run's time went: the serial reader (inside gmapper.c's critical section), the threads' summed
+            # wait for that lock, and one thread's own split
+            rd_ns = re.search(r"reader: \d+ entries in ([0-9.]+) s \((\d+) ns each\)", r.stderr)
+            wait = re.search(r"Wait Time:\s+([0-9.]+) seconds", r.stderr)
+            thr = re.search(r"device calls ([0-9.]+) \(the first ([0-9.]+)\), record rebuild ([0-9.]+), output ([0-9.]+)", r.stderr)
+            detail.append({"map_s": float(m.group(1)), "reader_s": float(rd_ns.group(1)) if rd_ns else None,
+                           "reader_ns_per_entry": int(rd_ns.group(2)) if rd_ns else None,
+                           "threads_wait_s_sum": float(wait.group(1)) if wait else None,
+                           "one_thread": {"device_calls_s": float(thr.group(1)), "first_call_s": float(thr.group(2)),
+                                          "rebuild_s": float(thr.group(3)), "output_s": float(thr.group(4))} if thr else None})
         if r.returncode == 0 and m and float(m.group(1)) > 0:
-            e2e_sam = {"value": max(runs), "unit": "reads/s", "reads": n_sam, "runs": runs,
+            e2e_sam = {"value": max(runs), "unit": "reads/s", "reads": n_sam, "runs": runs, "runs_detail": detail,
                        "reference_value": cpu["value"] if cpu else None,
                        "how": f"integration/_build/{w.binary} -N {th} -K {ck} {' '.join(w.load_args())} -L <projection> "
                               "<reads.fa>: FASTA in, SAM out, the binary's own Read Mapping Time (the reference's clock, "
