@@ -392,6 +392,10 @@ static int reader_slot(fasta_t f) {
 }
 
 bool fasta_get_next_read_with_range(fasta_t fasta, read_entry *re) {   // fasta.c:316
+  // gmapper.c fills re_buffer[] entry after entry (gmapper.c:344-378): the entries behind this one are the next to be
+  // written, and the chunk buffer (tens of megabytes, zeroed just before) is no longer in the near caches
+  __builtin_prefetch((const char *)(re + 2), 1);
+  __builtin_prefetch((const char *)(re + 2) + 192, 1);
   static const bool verbose = getenv("SHRIMP_B200_VERBOSE") != NULL;
   // measured on a 16-core B200 box (8 M C2 reads, -N 16): 4.4 M reads/s with the read-ahead thread, 4.5-4.8 M
   // without -- the parser thread delivers an entry every ~150 ns, which is what parsing in place costs, so the ring
