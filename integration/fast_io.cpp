@@ -131,10 +131,11 @@ const char *next_piece(Reader *r, size_t *len, bool *nl) {
     }
     if (refill(r)) continue;
     if (r->end > r->pos) {   // block full without a newline, or the last line of a file that does not end in one
+      const char *piece = r->buf + r->pos;   // (refill may have moved the tail to the front of the block)
       *len = r->end - r->pos;
       *nl = false;
       r->pos = r->end;
-      return s;
+      return piece;
     }
     return NULL;
   }
