@@ -282,6 +282,11 @@ static void ahead_main(Ahead *A) {
     }
     const size_t text = V.name_len + V.seq_len + V.plus_len + V.qual_len + V.range_len;
     const size_t need = (sizeof(Ahead::Rec) + text + 31) & ~(size_t)31;
+    if (need > A->size / 2) {
+      fprintf(stderr, "error: an entry of %zu bytes in a read file is more than the read-ahead ring takes; "
+                      "run without SHRIMP_B200_READ_AHEAD\n", text);
+      exit(1);
+    }
     n_entries++;
     n_general += general;
     char *at = ahead_reserve(A, need, &t_waited);
@@ -666,6 +671,7 @@ static bool next_read(fasta_t fasta, read_entry *re) {
       fprintf(stderr, "Read in quality string of wrong length!, %d vs %d\n", (int)qual_len, (int)seq_len);
       free(re->seq);
       free(re->plus_line);
+      re->seq = re->orig_seq = re->plus_line = NULL;   // (the reference leaves them dangling; its caller drops the entry)
       return false;
     }
     re->qual = (char *)xmalloc(qual_len + 17);
