@@ -707,8 +707,21 @@ def measure(a, w, n_reads, rank, world, local_rank, ncores, compact=False):
                            "threads_wait_s_sum": float(wait.group(1)) if wait else None,
                            "one_thread": {"device_calls_s": float(thr.group(1)), "first_call_s": float(thr.group(2)),
                                           "rebuild_s": float(thr.group(3)), "output_s": float(thr.group(4))} if thr else None})
+        # the same link line with the reference's OWN reader and SAM formatter (gmapper-b200-refio: nothing of
+        # fast_io.cpp; the strict reading of "input/output and SAM emission unchanged"), one run
+        ref_io = None
+        refio_bin = os.path.join(os.path.dirname(dropin), "refio", w.binary)
+        if runs and os.path.exists(refio_bin):
+            r2 = subprocess.run([refio_bin, "-N", str(th), "-K", str(ck), *w.load_args(), "-L", "proj", *rd], cwd=d,
+                                stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, env=child_env())
+            m2 = re.search(r"Read Mapping Time:\s+([0-9.]+) seconds", r2.stderr)
+            if r2.returncode == 0 and m2 and float(m2.group(1)) > 0:
+                ref_io = {"value": n_sam / float(m2.group(1)), "unit": "reads/s",
+                          "how": "integration/_build/refio: the reference's unchanged fasta.o / util.o / output.o in "
+                                 "place of integration/fast_io.cpp, same options"}
         if r.returncode == 0 and m and float(m.group(1)) > 0:
             e2e_sam = {"value": max(runs), "unit": "reads/s", "reads": n_sam, "runs": runs, "runs_detail": detail,
+                       "reference_io": ref_io,
                        "reference_value": cpu["value"] if cpu else None,
                        "how": f"integration/_build/{w.binary} -N {th} -K {ck} {' '.join(w.load_args())} -L <projection> "
                               "<reads.fa>: FASTA in, SAM out, the binary's own Read Mapping Time (the reference's clock, "

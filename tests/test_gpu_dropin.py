@@ -100,6 +100,24 @@ def test_lookahead_with_dropped_reads_and_many_threads(tmp_path):
         assert_same_sam(ref, new)
 
 
+@needs_bins
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["c1_small", "c2_small_fastq_mq"])
+def test_dropin_with_the_references_own_reader_and_formatter(name, tmp_path):
+    """gmapper-b200-refio: the same link line without integration/fast_io.cpp -- the reference's fasta.o, util.o and
+    output.o as they are (the strict reading of "input/output and SAM emission unchanged"); bench.py reports it next to
+    the default binary"""
+    refio = os.path.join(NEW, "refio")
+    if not os.path.exists(os.path.join(refio, "gmapper-ls")):
+        pytest.skip("integration/_build/refio not built")
+    case = LsCase(name)
+    case.write_fasta(str(tmp_path))
+    args = [*MAP_CASES[name]["args"], "reads.fa", "genome.fa"]
+    ref, _ = run_sam(REF, case.binary, args, str(tmp_path), 4)
+    new, _ = run_sam(refio, case.binary, args, str(tmp_path), 2, ["-K", "700"])
+    assert_same_sam(ref, new)
+
+
 STAGE_LISTS = {
     # a strict first set that stops at one alignment of 95 % of the maximum score, then a one-seed-match set with
     # lower thresholds for the reads that are left (every set that finds alignments prints them, mapping.c:1824-1833)
