@@ -544,7 +544,7 @@ static void run_later_stages(Batch &B, int max_len) {
   shrimp_gpu_ctx *ctx = thread_ctx();
   const int n = B.n_rows;
   std::vector<char> go((size_t)n, 0);   // rows that move on to the next set
-  for (int r = 0; r < n; r++) go[r] = !stage_done(t_stages[0], &B.hits[(size_t)B.first_unp[r]], B.n_unp[r]);
+  for (int r = 0; r < n; r++) go[r] = !stage_done(t_stages[0], B.hits.data() + B.first_unp[r], B.n_unp[r]);
   for (int k = 1; k < t_n_stages; k++) {
     B.later.emplace_back();
     Batch::Stage &S = B.later.back();
@@ -596,7 +596,7 @@ static void run_later_stages(Batch &B, int max_len) {
     for (int i = 0; i < m; i++) S.first_unp[i + 1] = S.first_unp[i] + S.n_unp[i];
     for (int r = 0; r < n; r++) {
       const int sub = S.sub_of_row[r];
-      go[r] = sub >= 0 && !stage_done(t_stages[k], &S.hits[(size_t)S.first_unp[sub]], S.n_unp[sub]);
+      go[r] = sub >= 0 && !stage_done(t_stages[k], S.hits.data() + S.first_unp[sub], S.n_unp[sub]);
     }
   }
 }
@@ -878,13 +878,13 @@ static void emit_records(const shrimp_hit *h, int n, const std::vector<uint8_t> 
 
 static void emit_unpaired(const Batch &B, int row, read_entry *re, bool save_outputs) {
   const int n = B.n_unp[row];
-  if (n > 0) emit_records(&B.hits[(size_t)B.first_unp[row]], n, B.edits, re, save_outputs);
+  if (n > 0) emit_records(B.hits.data() + B.first_unp[row], n, B.edits, re, save_outputs);
   // the later option sets this read went through, in their order (every set that finds alignments prints them,
   // mapping.c:1824-1833)
   for (const Batch::Stage &S : B.later) {
     const int sub = S.sub_of_row[row];
     if (sub < 0) break;
-    if (S.n_unp[sub] > 0) emit_records(&S.hits[(size_t)S.first_unp[sub]], S.n_unp[sub], S.edits, re, save_outputs);
+    if (S.n_unp[sub] > 0) emit_records(S.hits.data() + S.first_unp[sub], S.n_unp[sub], S.edits, re, save_outputs);
   }
 }
 
