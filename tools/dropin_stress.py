@@ -1,4 +1,9 @@
-"""bisect helper: the mixed-length letter-space FASTQ case of tests/test_gpu_dropin.py under a few toggles"""
+"""Stress run of the linked drop-in: the mixed-length letter-space FASTQ case of tests/test_gpu_dropin.py (one read in
+seven dropped by the loop of gmapper.c) N times with two threads and small chunks, crash back-traces switched on
+(SHRIMP_B200_BACKTRACE=1).  This is the run that showed the look-ahead bound bug of round 2 (13 crashes in 60 runs).
+
+    python tools/dropin_stress.py 60
+"""
 import os, subprocess, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
