@@ -118,6 +118,54 @@ def test_dropin_with_the_references_own_reader_and_formatter(name, tmp_path):
     assert_same_sam(ref, new)
 
 
+@needs_bins
+@pytest.mark.gpu
+def test_long_reads_and_contig_ends(tmp_path):
+    """reads of 500 to 1,000 bases (--longest-read is 1,000 by default, gmapper-defaults.h:72; the full SW leaves the
+    256-column ring classes for the global-scratch kernel) and reads cut from the first and last 60 bases of every
+    contig, both strands, some of them hanging over the end by a few random bases"""
+    import numpy as np
+    case = LsCase("c1_small")
+    case.write_fasta(str(tmp_path))
+    rng = np.random.default_rng(99)
+    comp = np.zeros(256, dtype=np.uint8)
+    for a, b in zip(b"ACGTN", b"TGCAN"):
+        comp[a] = b
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    recs = []
+    for i in range(120):   # long reads, 1 % substitutions, a few short indels
+        cn = int(rng.integers(0, len(case.contigs)))
+        g = case.contigs[cn][1]
+        rl = int(rng.integers(500, 1001))
+        pos = int(rng.integers(0, g.size - rl - 1))
+        frag = g[pos:pos + rl].copy()
+        sub = rng.random(rl) < 0.01
+        frag[sub] = acgt[rng.integers(0, 4, size=int(sub.sum()))]
+        if i % 3 == 0:
+            cut = int(rng.integers(50, rl - 50))
+            frag = np.concatenate([frag[:cut], frag[cut + int(rng.integers(1, 4)):]])
+        if rng.random() < 0.5:
+            frag = comp[frag][::-1].copy()
+        recs.append((b"long%d" % i, bytes(frag)))
+    for cn, (_, g) in enumerate(case.contigs):   # contig ends
+        for k in range(12):
+            rl = int(rng.integers(40, 61))
+            over = int(rng.integers(0, 6))
+            junk = acgt[rng.integers(0, 4, size=over)]
+            frag = np.concatenate([junk, g[:rl - over]]) if k % 2 == 0 else np.concatenate([g[g.size - (rl - over):], junk])
+            if k % 4 >= 2:
+                frag = comp[frag][::-1].copy()
+            recs.append((b"end%d_%d" % (cn, k), bytes(frag)))
+    with open(os.path.join(str(tmp_path), "long.fa"), "wb") as f:
+        for name, s_ in recs:
+            f.write(b">" + name + b"\n" + s_ + b"\n")
+    args = ["long.fa", "genome.fa"]
+    ref, _ = run_sam(REF, case.binary, args, str(tmp_path), 4)
+    new, _ = run_sam(NEW, case.binary, args, str(tmp_path), 2, ["-K", "60"])
+    assert_same_sam(ref, new)
+    assert sum(1 for ln in new if ln and not ln.startswith(b"@")) > 100
+
+
 STAGE_LISTS = {
     # a strict first set that stops at one alignment of 95 % of the maximum score, then a one-seed-match set with
     # lower thresholds for the reads that are left (every set that finds alignments prints them, mapping.c:1824-1833)
