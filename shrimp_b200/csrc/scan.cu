@@ -1692,7 +1692,7 @@ size_t scan_smem_bytes(int cap, int max_rl, int k_cap, int bm_log2, int warps, i
 __global__ void __launch_bounds__(REPLAY_WARPS * 32) scan_replay_kernel(const ScanParams P, uint32_t n_rec, int ks_cap) {
   extern __shared__ unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const uint32_t w = blockIdx.x * REPLAY_WARPS + wib;
+  const uint32_t w = blockIdx.x * (blockDim.x >> 5) + wib;   // (fewer than REPLAY_WARPS warps per CTA for long reads)
   if (w >= n_rec) return;
   unsigned char *base = smem_raw + (size_t)wib * REPLAY_SMEM_PER_WARP(ks_cap);
   unsigned long long *heap = (unsigned long long *)base;
@@ -1836,9 +1836,19 @@ __global__ void __launch_bounds__(REPLAY_WARPS * 32) scan_replay_kernel(const Sc
 }
 
 int launch_scan_replay(shrimp_gpu_ctx *ctx, ScanParams &P, uint32_t n_rec, int ks_cap) {
-  const size_t smem = (size_t)REPLAY_WARPS * REPLAY_SMEM_PER_WARP(ks_cap);
+  // a warp's heap, stage and first-of table grow with the k-mers of the longest read (18 bytes per k-mer slot: 53 KB at
+  // 1,000 bases): as many warps per CTA as the shared memory of an SM holds (eight until round 2, which made the launch
+  // of a chunk with reads of more than about 450 bases and equal-position ties fail with "invalid argument")
+  const size_t per_warp = REPLAY_SMEM_PER_WARP(ks_cap);
+  int warps = REPLAY_WARPS;
+  while (warps > 1 && per_warp * warps > (size_t)SHRIMP_MAX_DYN_SMEM - 1024) warps >>= 1;
+  if (per_warp * warps > (size_t)SHRIMP_MAX_DYN_SMEM - 1024) {
+    set_error("seed scan: reads of this length need %zu bytes of shared memory per warp in the heap replay", per_warp);
+    return SHRIMP_E_RANGE;
+  }
+  const size_t smem = per_warp * warps;
   SH_OPT_IN_SMEM(scan_replay_kernel, ctx->device);
-  scan_replay_kernel<<<(n_rec + REPLAY_WARPS - 1) / REPLAY_WARPS, REPLAY_WARPS * 32, smem, ctx->stream>>>(P, n_rec, ks_cap);
+  scan_replay_kernel<<<(n_rec + warps - 1) / warps, warps * 32, smem, ctx->stream>>>(P, n_rec, ks_cap);
   SH_CUDA(cudaGetLastError());
   SH_LAUNCHED(ctx, ST_SCAN);
   return SHRIMP_OK;
