@@ -166,6 +166,38 @@ def test_long_reads_and_contig_ends(tmp_path):
     assert sum(1 for ln in new if ln and not ln.startswith(b"@")) > 100
 
 
+@needs_bins
+@pytest.mark.gpu
+def test_long_colour_space_reads(tmp_path):
+    """colour-space reads of 300 to 900 colours with qualities (per-position crossover scores, post_sw over hundreds of
+    columns: one warp of eight alignments per CTA, the global-scratch full SW for the wide bands)"""
+    import numpy as np
+    import gen_synth
+    case = LsCase("c2_small")
+    case.write_fasta(str(tmp_path))
+    rng = np.random.default_rng(123)
+    comp = np.zeros(256, dtype=np.uint8)
+    for a, b in zip(b"ACGTN", b"TGCAN"):
+        comp[a] = b
+    with open(os.path.join(str(tmp_path), "long.fq"), "wb") as f:
+        for i in range(90):
+            cn = int(rng.integers(0, len(case.contigs)))
+            g = case.contigs[cn][1]
+            rl = int(rng.integers(300, 901))
+            pos = int(rng.integers(0, g.size - rl - 1))
+            frag = g[pos:pos + rl].copy()
+            if rng.random() < 0.5:
+                frag = comp[frag][::-1].copy()
+            s_ = gen_synth.letters_to_colour_read(frag, rng, 0.01)
+            q = bytes((33 + rng.integers(5, 41, size=rl)).astype(np.uint8))
+            f.write(b"@lc%d\n" % i + s_ + b"\n+\n" + q + b"\n")
+    args = ["-Q", "--qv-offset", "33", "long.fq", "genome.fa"]
+    ref, _ = run_sam(REF, case.binary, args, str(tmp_path), 4)
+    new, _ = run_sam(NEW, case.binary, args, str(tmp_path), 2, ["-K", "40"])
+    assert_same_sam(ref, new)
+    assert sum(1 for ln in new if ln and not ln.startswith(b"@")) > 50
+
+
 STAGE_LISTS = {
     # a strict first set that stops at one alignment of 95 % of the maximum score, then a one-seed-match set with
     # lower thresholds for the reads that are left (every set that finds alignments prints them, mapping.c:1824-1833)
