@@ -198,6 +198,47 @@ def test_long_colour_space_reads(tmp_path):
     assert sum(1 for ln in new if ln and not ln.startswith(b"@")) > 50
 
 
+@needs_bins
+@pytest.mark.gpu
+def test_long_mates(tmp_path):
+    """pairs whose mates are 250 to 450 bases long (inserts of 700 to 1,100, -I 0,1200), some mates with a short
+    indel, some pairs with one mate that maps nowhere (half-paired output)"""
+    import numpy as np
+    case = PairCase("c3_small")
+    case.write_fasta(str(tmp_path))
+    rng = np.random.default_rng(321)
+    comp = np.zeros(256, dtype=np.uint8)
+    for a, b in zip(b"ACGTN", b"TGCAN"):
+        comp[a] = b
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    with open(os.path.join(str(tmp_path), "l1.fa"), "wb") as f1, open(os.path.join(str(tmp_path), "l2.fa"), "wb") as f2:
+        for i in range(150):
+            cn = int(rng.integers(0, len(case.contigs)))
+            g = case.contigs[cn][1]
+            ins = int(rng.integers(700, 1101))
+            l1, l2 = int(rng.integers(250, 451)), int(rng.integers(250, 451))
+            pos = int(rng.integers(0, g.size - ins - 1))
+            a = g[pos:pos + l1].copy()
+            b = comp[g[pos + ins - l2:pos + ins]][::-1].copy()
+            for m in (a, b):
+                sub = rng.random(m.size) < 0.01
+                m[sub] = acgt[rng.integers(0, 4, size=int(sub.sum()))]
+            if i % 4 == 0:
+                cut = int(rng.integers(40, l1 - 40))
+                a = np.concatenate([a[:cut], a[cut + 2:]])
+            if i % 9 == 0:
+                b = acgt[rng.integers(0, 4, size=l2)]
+            if rng.random() < 0.5:   # the pair read from the other strand
+                a, b = b, a
+            f1.write(b">lp%d/1\n" % i + bytes(a) + b"\n")
+            f2.write(b">lp%d/2\n" % i + bytes(b) + b"\n")
+    args = ["-p", "opp-in", "-I", "0,1200", "-1", "l1.fa", "-2", "l2.fa", "genome.fa"]
+    ref, _ = run_sam(REF, case.binary, args, str(tmp_path), 4)
+    new, _ = run_sam(NEW, case.binary, args, str(tmp_path), 2, ["-K", "60"])
+    assert_same_sam(ref, new)
+    assert sum(1 for ln in new if ln and not ln.startswith(b"@")) > 150
+
+
 STAGE_LISTS = {
     # a strict first set that stops at one alignment of 95 % of the maximum score, then a one-seed-match set with
     # lower thresholds for the reads that are left (every set that finds alignments prints them, mapping.c:1824-1833)
