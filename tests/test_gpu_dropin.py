@@ -67,7 +67,8 @@ def test_paired_sam_identical(name, tmp_path):
 @needs_bins
 @pytest.mark.gpu
 @pytest.mark.parametrize("extra", [["--sam-unaligned"], ["--single-best-mapping"], ["--strata"], ["-o", "3"],
-                                   ["--extra-sam-fields"], ["--all-contigs"], ["--trim-front", "3", "--trim-end", "2"]])
+                                   ["--extra-sam-fields"], ["--all-contigs"], ["--trim-front", "3", "--trim-end", "2"],
+                                   ["-U", "--local"], ["--local"], ["-n", "1"], ["-h", "40%", "-o", "20", "--strata"]])
 def test_output_options_c1(extra, tmp_path):
     """options that only touch the unchanged output code or the loop of gmapper.c the look-ahead has to predict"""
     case = LsCase("c1_small")
