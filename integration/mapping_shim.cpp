@@ -45,6 +45,7 @@
 
 #include "shrimp_b200.h"
 #include "shim_align.h"
+#include "shim_lookahead.h"
 #include "shim_state.h"
 
 namespace shrimp_shim {
@@ -697,28 +698,12 @@ static void run_batch(Batch &B, const std::vector<Prep> &preps, const shrimp_map
   if (tstats.t_first_device == 0) tstats.t_first_device = dt;   // allocations of the context's buffers
 }
 
-// entries [re, re + ahead) of the chunk that are loaded; `step` entries per unit (2 in paired mode)
-//
-// The look-ahead must not run past re_buffer[], whose bounds the shim is not told.  What it knows: a thread's
-// re_buffer is ONE allocation of chunk_size entries for the whole run, zeroed before every fill (gmapper.c:325-332),
-// and handle_read is called for its entries in ascending order, skipping the ones the loop dropped -- each of which is
-// counted in total_reads_dropped / total_pairs_dropped (gmapper.c:510-527).  So, with D the drops counted since this
-// thread's previous call, `re - D * step` is at or below the first entry of the buffer whenever `re` is the first
-// surviving entry of a chunk (drops by other threads only lower it), and the buffer's end is at least
-// `re - D * step + chunk_size` there: the MINIMUM of that expression over all calls is a safe end (a call in the
-// middle of a chunk gives a larger value and is ignored by the minimum).  One past the highest entry ever seen is
-// a lower bound of the end as well, and it becomes exact once a full chunk has gone by.  (Until round 2 the bound
-// was taken from the current call alone: a batch that had been cut short by another thread's drops was followed by
-// a look-ahead from the middle of the chunk that ran past the buffer.)
-static thread_local const read_entry *t_end_min, *t_end_low;
+// entries [re, re + ahead) of the chunk that are loaded; `step` entries per unit (2 in paired mode).  The bound on
+// re_buffer[], whose ends the shim is not told, is shim_lookahead.h's.
+static thread_local LookaheadBound<read_entry> t_bound;
 static int lookahead_limit(const read_entry *re, int step) {
-  long long drops = (total_reads_dropped + total_pairs_dropped) - t_own_drops - t_drop_snapshot;
-  if (drops < 0) drops = 0;
-  const read_entry *cand = re + (long long)chunk_size - drops * step;
-  if (!t_end_min || cand < t_end_min) t_end_min = cand;
-  if (!t_end_low || re + step > t_end_low) t_end_low = re + step;
-  const read_entry *end = t_end_min > t_end_low ? t_end_min : t_end_low;
-  long long limit = end - re;
+  const long long drops = (total_reads_dropped + total_pairs_dropped) - t_own_drops - t_drop_snapshot;
+  long long limit = t_bound.limit(re, drops, step, (long long)chunk_size);
   if (const char *e = getenv("SHRIMP_B200_BATCH")) limit = std::min<long long>(limit, std::max(step, atoi(e)));
   if (limit < step) limit = step;
   int n = step;
