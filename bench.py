@@ -690,9 +690,14 @@ def measure(a, w, n_reads, rank, world, local_rank, ncores, compact=False):
         # sixteen cores, a serial reader) and moves by +-25 % from run to run on the same box
         runs, detail = [], []
         for verbose in (False, True):   # the second run also times its reader (two rdtsc per entry) and its threads
-            r = subprocess.run([dropin, "-N", str(th), "-K", str(ck), *w.load_args(), "-L", "proj", *rd], cwd=d,
-                               stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True,
-                               env=dict(child_env(), **({"SHRIMP_B200_VERBOSE": "1"} if verbose else {})))
+            try:
+                r = subprocess.run([dropin, "-N", str(th), "-K", str(ck), *w.load_args(), "-L", "proj", *rd], cwd=d,
+                                   stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, timeout=900,
+                                   env=dict(child_env(), **({"SHRIMP_B200_VERBOSE": "1"} if verbose else {})))
+            except subprocess.TimeoutExpired:
+                r = subprocess.CompletedProcess([dropin], 124, "", "timed out after 900 s")
+                m = None
+                break
             m = re.search(r"Read Mapping Time:\s+([0-9.]+) seconds", r.stderr)
             if r.returncode != 0 or not m or float(m.group(1)) <= 0:
                 break
@@ -712,14 +717,17 @@ def measure(a, w, n_reads, rank, world, local_rank, ncores, compact=False):
         ref_io = None
         refio_bin = os.path.join(os.path.dirname(dropin), "refio", w.binary)
         if runs and os.path.exists(refio_bin):
-            r2 = subprocess.run([refio_bin, "-N", str(th), "-K", str(ck), *w.load_args(), "-L", "proj", *rd], cwd=d,
-                                stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, env=child_env())
-            m2 = re.search(r"Read Mapping Time:\s+([0-9.]+) seconds", r2.stderr)
-            if r2.returncode == 0 and m2 and float(m2.group(1)) > 0:
+            try:
+                r2 = subprocess.run([refio_bin, "-N", str(th), "-K", str(ck), *w.load_args(), "-L", "proj", *rd], cwd=d,
+                                    stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, timeout=900, env=child_env())
+                m2 = re.search(r"Read Mapping Time:\s+([0-9.]+) seconds", r2.stderr)
+            except subprocess.TimeoutExpired:
+                r2, m2 = None, None
+            if r2 is not None and r2.returncode == 0 and m2 and float(m2.group(1)) > 0:
                 ref_io = {"value": n_sam / float(m2.group(1)), "unit": "reads/s",
                           "how": "integration/_build/refio: the reference's unchanged fasta.o / util.o / output.o in "
                                  "place of integration/fast_io.cpp, same options"}
-        if r.returncode == 0 and m and float(m.group(1)) > 0:
+        if runs:
             e2e_sam = {"value": max(runs), "unit": "reads/s", "reads": n_sam, "runs": runs, "runs_detail": detail,
                        "reference_io": ref_io,
                        "reference_value": cpu["value"] if cpu else None,
